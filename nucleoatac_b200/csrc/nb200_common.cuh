@@ -1,6 +1,7 @@
 // nb200_common.cuh -- shared declarations of libnucleo_b200 (sm_100a).
 #pragma once
 #include <cuda_runtime.h>
+#include <math_constants.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -12,6 +13,8 @@
 
 #define NB200_MAX_PWM_WIDTH 64
 #define NB200_MAX_NUC 8
+#define NB200_MAX_UPPER 2048
+#define NB200_MAX_ALPHA 128
 
 // ---------------------------------------------------------------------------------------------
 // device buffer that only ever grows (no per-batch cudaMalloc on the steady-state path)
@@ -25,7 +28,7 @@ struct DevBuf {
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
-        size_t want = bytes + bytes / 4 + 256;
+        size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;
@@ -55,21 +58,24 @@ struct RunConst {
     // VMat
     bool have_vmat = false;
     int v_rows = 0, v_cols = 0, v_lower = 0, v_upper = 0, v_w = 0;
+    int v_wpad = 0;   // v_cols rounded up to a multiple of 16 (zero padded rows of vmat_fp)
     bool v_has_zero = false;
     DevBuf vmat;      // f64 [R][W]
-    DevBuf vmat_f;    // f64 [R][W]  f_i * V      (needs fragment sizes)
-    DevBuf vmat_f2;   // f64 [R][W]  f_i * V^2
+    DevBuf vmat_fp;   // f64 [R][Wpad]  f_i * V, zero padded (operand of the dense background xcor)
     std::vector<double> h_vmat;
     // fragment sizes
     bool have_sizes = false;
     int sizes_upper = 0;
+    bool f_has_zero = false;  // a zero frequency inside [v_lower, v_upper)
+    double f_sum_v = 0.0;     // sum of f over [v_lower, v_upper)
     DevBuf sizes;     // f64 [upper]
     std::vector<double> h_sizes;
     // occupancy model
     bool have_occ_model = false;
     int occ_upper = 0, n_alpha = 0;
     double cutoff = 0.0;
-    int pn_has_zero = 0, pf_has_zero = 0;
+    int pn_has_zero = 0, pf_has_zero = 0, both_zero = 0;
+    double pn_sum = 0.0, pf_sum = 0.0;
     DevBuf nuc_probs, nfr_probs, alphas;
     // jitter
     int64_t n_jitter = 0;
@@ -109,10 +115,10 @@ struct nb200_ctx {
 int nb200_fail(nb200_ctx *ctx, int code, const char *fmt, ...);
 int nb200_cuda_fail(nb200_ctx *ctx, cudaError_t e, const char *what, const char *file, int line);
 
-#define NB_CUDA(ctx, call)                                                             \
-    do {                                                                               \
-        cudaError_t _e = (call);                                                       \
-        if (_e != cudaSuccess) return nb200_cuda_fail((ctx), _e, #call, __FILE__, __LINE__); \
+#define NB_CUDA(ctx, call)                                                                    \
+    do {                                                                                      \
+        cudaError_t _e = (call);                                                              \
+        if (_e != cudaSuccess) return nb200_cuda_fail((ctx), _e, #call, __FILE__, __LINE__);  \
     } while (0)
 
 #define NB_CHECK(call)                 \
@@ -120,6 +126,8 @@ int nb200_cuda_fail(nb200_ctx *ctx, cudaError_t e, const char *what, const char 
         int _s = (call);               \
         if (_s != NB200_OK) return _s; \
     } while (0)
+
+#define NB_LAUNCH_CHECK(ctx) NB_CUDA(ctx, cudaGetLastError())
 
 // profiling bracket around a kernel launch
 struct ProfScope {
@@ -134,7 +142,8 @@ struct ProfScope {
 void nb200_prof_collect(nb200_ctx *ctx);  // drain pending events (sync)
 
 // ---------------------------------------------------------------------------------------------
-// batch on the device
+// batch on the device.  Every packed per-position track of a batch has total_len values; chunk c
+// occupies [out_off[c], out_off[c+1]).
 // ---------------------------------------------------------------------------------------------
 struct nb200_dbatch {
     cudaStream_t stream = nullptr;
@@ -145,55 +154,54 @@ struct nb200_dbatch {
     int64_t n_seq = 0;
     int64_t h2d_bytes = 0;
     bool have_seq = false;
-    int max_len = 0;
-    // geometry (host copies for launch configuration)
-    std::vector<int32_t> h_start, h_end;
+    int max_len = 0, min_len = 0;
+    // geometry (host copies for launch configuration / validation)
+    std::vector<int32_t> h_start, h_end, h_seq_start;
     std::vector<int64_t> h_out_off, h_frag_off, h_seq_off;
-    std::vector<int32_t> h_seq_start;
     // device inputs
     DevBuf d_start, d_end, d_frag_off, d_pos, d_tlen, d_seq_off, d_seq_start, d_seq, d_out_off;
-    // derived: bias track (log-bias b and E = exp(b)), offsets per chunk
+    // bias track: E = exp(log-bias) packed per chunk; chunk c covers genomic [bias0[c], bias0[c]+bias_len[c])
+    bool bias_done = false;
     DevBuf d_bias_off;  // int64 [n+1]
-    DevBuf d_bias0;     // int32 [n] genomic coordinate of b[bias_off[c]]
-    DevBuf d_b, d_E;    // f64 packed
-    std::vector<int64_t> h_bias_off;
-    std::vector<int32_t> h_bias0;
-    bool prep_done = false;
-    // fragment matrix in CSC form (columns = genomic positions over [start-pad, end+pad))
-    int csc_pad = 0, csc_upper = 0, csc_atac = -1;
-    DevBuf d_col_off;   // int64 [n+1] offsets into col arrays (each chunk ncol+1 entries)
-    std::vector<int64_t> h_col_off;
-    DevBuf d_col_ptr;   // int32 packed [ncol+1] per chunk: all entries
-    DevBuf d_cursor;    // int32 scratch same shape
-    DevBuf d_ent;       // int2 {col,row} packed at frag_off
+    DevBuf d_E;         // f64 packed
+    int64_t n_bias = 0;
+    // fragment matrix in compressed-column form over genomic columns [start-pad, end+pad)
+    int csc_pad = -1, csc_upper = -1, csc_atac = -1, csc_lower_split = -1;
+    DevBuf d_col_off;   // int64 [n+1] offsets into col_ptr / col_low (chunk c has ncol_c+1 entries)
+    DevBuf d_col_ptr;   // int32 packed: exclusive prefix of per-column counts (all rows < upper)
+    DevBuf d_col_low;   // int32 packed: same for rows < lower_split (only when lower_split > 0)
+    DevBuf d_cursor;    // int32 scratch, same shape
+    DevBuf d_ent;       // int2 {col (relative to start-pad), row} packed at frag_off
+    int64_t n_colptr = 0;
     // occ outputs (device)
     DevBuf o_vals, o_lower, o_upper, o_svals, o_slower, o_supper, o_cov, o_nuc_dist;
     DevBuf o_peak_count, o_peak_pos, o_peak_occ, o_peak_lower, o_peak_upper, o_peak_reads;
-    DevBuf o_cn, o_cf;          // per-column sums of pn*Bp, pf*Bp
+    DevBuf o_cn, o_cf;          // per-column sums of pn*Bp, pf*Bp over [start-flank, end+flank)
+    DevBuf o_colsum_off;        // int64 [n+1]
     DevBuf o_peak_off;          // int64 [n+1]
     std::vector<int64_t> h_opeak_off;
     bool occ_done = false;
+    int occ_upper = 0;
     // nuc outputs (device)
-    DevBuf n_signal, n_bg, n_norm, n_smooth, n_nuc_cov, n_nfr_cov, n_bx, n_colsum;
+    DevBuf n_signal, n_bg, n_norm, n_smooth, n_nuc_cov, n_nfr_cov, n_bx, n_bcov, n_cB;
+    DevBuf n_cB_off;            // int64 [n+1]
     DevBuf n_cand_count, n_cand_pos, n_cand_flag, n_cand_z, n_cand_lr, n_cand_norm, n_cand_sig, n_cand_cov,
         n_cand_nfr, n_cand_smooth;
     DevBuf n_cand_off;          // int64 [n+1]
     std::vector<int64_t> h_ncand_off;
-    DevBuf n_work;              // candidate work list
-    DevBuf n_work_count;
-    // tensor-core path operands
-    DevBuf t_a_hi, t_a_lo;      // fp16 materialised prenorm bias rows (when not generated in-kernel)
+    DevBuf n_work;              // candidate work list {chunk, slot}
+    DevBuf n_work_count;        // int32[2]: appended, consumed
     bool nuc_done = false;
-    DevBuf misc;
+    // scratch shared by the peak callers
+    DevBuf sc_i32, sc_f64, sc_u8;
 };
 
-// kernels / stage drivers implemented across the .cu files
-int nb200_prep_batch(nb200_ctx *ctx, nb200_dbatch *b, int pad, int upper, int atac, bool need_bias);
-int nb200_background_fp64(nb200_ctx *ctx, nb200_dbatch *b);
-int nb200_background_tc(nb200_ctx *ctx, nb200_dbatch *b);
-int nb200_tc_setup(nb200_ctx *ctx);  // (re)build the band operand after vmat / sizes change
+// stage drivers implemented across the .cu files
+int nb200_prep_bias(nb200_ctx *ctx, nb200_dbatch *b);
+int nb200_prep_csc(nb200_ctx *ctx, nb200_dbatch *b, int pad, int upper, int atac, int lower_split);
+int nb200_nuc_bx_fp64(nb200_ctx *ctx, nb200_dbatch *b);   // dense background xcor, fp64 CUDA cores
+int nb200_nuc_bx_tc(nb200_ctx *ctx, nb200_dbatch *b);     // dense background xcor, tcgen05
+int nb200_tc_setup(nb200_ctx *ctx);                       // (re)build tensor-core operands after vmat / sizes change
+int nb200_tc_available(nb200_ctx *ctx);
 
 static inline int64_t div_up64(int64_t a, int64_t b) { return (a + b - 1) / b; }
-
-// floor division helpers matching Python semantics for the (i-1)//2 taps
-__host__ __device__ static inline int floordiv2(int a) { return a >> 1; }  // arithmetic shift == floor for /2

@@ -122,7 +122,7 @@ int nb200_ctx_destroy(nb200_ctx *c)
     nb200_prof_collect(c);
     for (auto ev : c->ev_pool) cudaEventDestroy(ev);
     RunConst &r = c->rc;
-    DevBuf *bufs[] = {&r.log_pwm, &r.nuc_code, &r.vmat,   &r.vmat_f, &r.vmat_f2, &r.sizes,  &r.nuc_probs, &r.nfr_probs,
+    DevBuf *bufs[] = {&r.log_pwm, &r.nuc_code, &r.vmat,   &r.vmat_fp, &r.sizes,  &r.nuc_probs, &r.nfr_probs,
                       &r.alphas,  &r.jitter,   &r.occ_win, &r.nuc_win, &c->s0,     &c->s1,    &c->s2,       &c->s3,
                       &c->s4,     &c->flush};
     for (auto b : bufs) b->release();
@@ -174,18 +174,18 @@ static int rebuild_scaled_vmat(nb200_ctx *ctx)
     if (r.sizes_upper < r.v_upper)
         return nb200_fail(ctx, NB200_ERR_ARG, "fragment sizes cover [0,%d) but the VMat needs sizes up to %d",
                           r.sizes_upper, r.v_upper);
-    size_t n = (size_t)r.v_rows * r.v_cols;
-    std::vector<double> vf(n), vf2(n);
+    // T = f_i * V, rows zero padded to a multiple of 16 columns (operand of the dense background xcor)
+    r.v_wpad = (r.v_cols + 15) / 16 * 16;
+    std::vector<double> vf((size_t)r.v_rows * r.v_wpad, 0.0);
+    r.f_has_zero = false;
+    r.f_sum_v = 0.0;
     for (int i = 0; i < r.v_rows; i++) {
         double f = r.h_sizes[r.v_lower + i];
-        for (int k = 0; k < r.v_cols; k++) {
-            double v = r.h_vmat[(size_t)i * r.v_cols + k];
-            vf[(size_t)i * r.v_cols + k] = f * v;
-            vf2[(size_t)i * r.v_cols + k] = f * (v * v);
-        }
+        if (!(f != 0.0)) r.f_has_zero = true;
+        r.f_sum_v += f;
+        for (int k = 0; k < r.v_cols; k++) vf[(size_t)i * r.v_wpad + k] = f * r.h_vmat[(size_t)i * r.v_cols + k];
     }
-    NB_CHECK(upload(ctx, r.vmat_f, vf.data(), n * sizeof(double)));
-    NB_CHECK(upload(ctx, r.vmat_f2, vf2.data(), n * sizeof(double)));
+    NB_CHECK(upload(ctx, r.vmat_fp, vf.data(), vf.size() * sizeof(double)));
     return nb200_tc_setup(ctx);
 }
 
@@ -257,10 +257,14 @@ int nb200_set_occ_model(nb200_ctx *ctx, const double *nuc_probs, const double *n
     NB_CHECK(upload(ctx, r.nuc_probs, nuc_probs, sizeof(double) * upper));
     NB_CHECK(upload(ctx, r.nfr_probs, nfr_probs, sizeof(double) * upper));
     NB_CHECK(upload(ctx, r.alphas, alphas, sizeof(double) * n_alpha));
-    r.pn_has_zero = r.pf_has_zero = 0;
+    r.pn_has_zero = r.pf_has_zero = r.both_zero = 0;
+    r.pn_sum = r.pf_sum = 0.0;
     for (int i = 0; i < upper; i++) {
         if (!(nuc_probs[i] != 0.0)) r.pn_has_zero = 1;
         if (!(nfr_probs[i] != 0.0)) r.pf_has_zero = 1;
+        if (!(nuc_probs[i] != 0.0) && !(nfr_probs[i] != 0.0)) r.both_zero = 1;
+        r.pn_sum += nuc_probs[i];
+        r.pf_sum += nfr_probs[i];
     }
     r.occ_upper = upper;
     r.n_alpha = n_alpha;

@@ -1,0 +1,242 @@
+// nb200_dev.cuh -- device-side helpers shared by the kernels of libnucleo_b200 (sm_100a).
+#pragma once
+#include "nb200_common.cuh"
+
+#define NB_FULL 0xffffffffu
+
+__device__ __forceinline__ double nb_nan() { return __longlong_as_double(0x7ff8000000000000LL); }
+__device__ __forceinline__ double nb_ninf() { return __longlong_as_double(0xfff0000000000000LL); }
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(NB_FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(NB_FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_min_i(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(NB_FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_max_i(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(NB_FULL, v, o));
+    return v;
+}
+
+// block-wide sum of doubles; `red` is shared scratch of >= 32 doubles.  All threads get the result.
+__device__ __forceinline__ double block_sum(double v, double *red)
+{
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    double r = (lane < nw) ? red[lane] : 0.0;
+    r = warp_sum(r);
+    return r;
+}
+
+// Cell of the (pre-normalisation) Tn5 bias matrix, pyatac/chunkmat2d.py:140-153 in the derived two-tap
+// form: Bp[i, c] = exp(b[c-(i-1)//2] + b[c+i//2]) = E[l] * E[r]; i == 1 has a single tap.
+// `Ec` points at E[c] (the caller guarantees the taps are inside the uploaded track).
+__device__ __forceinline__ double bias_cell(const double *Ec, int i)
+{
+    if (i == 1) return Ec[0];
+    int a = (i - 1) >> 1;  // arithmetic shift == Python floor division, (0-1)//2 = -1
+    int b = i >> 1;
+    return Ec[-a] * Ec[b];
+}
+
+// ATAC shift + centre of a fragment, pyatac/fragments.pyx:26-36.  Returns false when the row is outside
+// [0, upper - lower).
+__device__ __forceinline__ void frag_geometry(int pos, int tlen, int atac, int &l_pos, int &ilen)
+{
+    int t = tlen < 0 ? -tlen : tlen;
+    if (atac) {
+        l_pos = pos + 4;
+        ilen = t - 8;
+    } else {
+        l_pos = pos;
+        ilen = t;
+    }
+}
+__device__ __forceinline__ int floordiv2(int a) { return a >> 1; }
+
+// ---------------------------------------------------------------------------------------------
+// Greedy non-maximum suppression of pyatac/utils.py:56-78 (reduce_peaks), run by one thread block
+// on m candidates sorted by position.  Equivalent to walking the candidates by descending score:
+// a candidate that outranks every undecided neighbour within `sep` is kept, then its neighbours are
+// excluded; repeat.  Ties: the later candidate outranks (np.argsort stable order walked backwards).
+// state: 0 undecided, 1 kept, 2 excluded.  NaN scores rank lowest (np.argsort puts NaN last -> the
+// reference would walk them FIRST; callers never pass NaN scores).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool nms_outranks(double va, int ia, double vb, int ib)
+{
+    return (va > vb) || (va == vb && ia > ib);
+}
+
+static __device__ void block_nms(const int *pos, const double *val, unsigned char *state, int m, int sep, int *flag_sh)
+{
+    for (int j = threadIdx.x; j < m; j += blockDim.x) state[j] = 0;
+    __syncthreads();
+    for (int it = 0; it < m + 1; it++) {
+        if (threadIdx.x == 0) *flag_sh = 0;
+        __syncthreads();
+        // phase 1: winners
+        for (int j = threadIdx.x; j < m; j += blockDim.x) {
+            if (state[j] != 0) continue;
+            bool win = true;
+            for (int k = j - 1; k >= 0 && pos[j] - pos[k] < sep && win; k--)
+                if ((state[k] == 0 || state[k] == 3) && nms_outranks(val[k], k, val[j], j)) win = false;
+            for (int k = j + 1; k < m && pos[k] - pos[j] < sep && win; k++)
+                if ((state[k] == 0 || state[k] == 3) && nms_outranks(val[k], k, val[j], j)) win = false;
+            if (win) state[j] = 3;  // provisional keep; 3 still counts as undecided for the others in this phase
+        }
+        __syncthreads();
+        // phase 2: exclusion around winners
+        for (int j = threadIdx.x; j < m; j += blockDim.x) {
+            if (state[j] != 0) continue;
+            bool ex = false;
+            for (int k = j - 1; k >= 0 && pos[j] - pos[k] < sep && !ex; k--)
+                if (state[k] == 3) ex = true;
+            for (int k = j + 1; k < m && pos[k] - pos[j] < sep && !ex; k++)
+                if (state[k] == 3) ex = true;
+            if (ex) state[j] = 4;  // provisional exclude
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < m; j += blockDim.x) {
+            if (state[j] == 3) state[j] = 1;
+            else if (state[j] == 4) state[j] = 2;
+            if (state[j] == 0) *flag_sh = 1;
+        }
+        __syncthreads();
+        int more = *flag_sh;
+        __syncthreads();
+        if (!more) break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ordered block compaction: every thread passes flag (0/1) for the element it holds in this round
+// (elements are visited in rounds of blockDim.x consecutive indices); returns the output slot of a
+// flagged element and advances *base_sh (shared) by the round's total.  red: shared int[32].
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int block_compact_slot(int flag, int *base_sh, int *red)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    unsigned m = __ballot_sync(NB_FULL, flag);
+    int within = __popc(m & ((1u << lane) - 1));
+    if (lane == 0) red[wid] = __popc(m);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < nw; w++) {
+        int v = red[w];
+        if (w < wid) before += v;
+        total += v;
+    }
+    int base = *base_sh;
+    __syncthreads();
+    if (threadIdx.x == 0) *base_sh = base + total;
+    __syncthreads();
+    return base + before + within;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pyatac/utils.py:23-52 smooth(mode='same', norm=True) on packed tracks: out[n] = sum_m w[m]*x[n+h-m]
+// over non-NaN x (zero padded), divided by the same sum over the non-NaN indicator; 0 -> NaN.
+// clip_neg: values < 0 are taken as 0 first (NucChunk.smoothSignal, NucleosomeCalling.py:278-280).
+// grid (tiles, chunks, tracks); block SM_TILE threads; dynamic smem (SM_TILE + 2*wlen) doubles.
+// ---------------------------------------------------------------------------------------------
+#define SM_TILE 256
+struct SmoothTracks {
+    const double *in[3];
+    double *out[3];
+};
+static __global__ void __launch_bounds__(SM_TILE) k_smooth_same(SmoothTracks tr, const int64_t *__restrict__ out_off,
+                                                         const double *__restrict__ win, int wlen, int clip_neg)
+{
+    extern __shared__ double sm_s[];
+    double *s_w = sm_s;                 // [wlen]
+    double *s_x = sm_s + wlen;          // [SM_TILE + wlen - 1]
+    const int c = blockIdx.y;
+    const int64_t o = out_off[c];
+    const int L = (int)(out_off[c + 1] - o);
+    const int x0 = blockIdx.x * SM_TILE;
+    if (x0 >= L) return;
+    const double *in = tr.in[blockIdx.z] + o;
+    double *out = tr.out[blockIdx.z] + o;
+    const int h = (wlen - 1) / 2;
+    for (int i = threadIdx.x; i < wlen; i += blockDim.x) s_w[i] = win[i];
+    // s_x[j] = x[x0 - (wlen-1-h) + j]  (index range needed: n+h-m for m in [0,wlen))
+    const int lo = x0 + h - (wlen - 1);
+    for (int j = threadIdx.x; j < SM_TILE + wlen - 1; j += blockDim.x) {
+        int idx = lo + j;
+        double v = (idx >= 0 && idx < L) ? in[idx] : 0.0;   // zero padding; NaN kept as NaN marker
+        if (clip_neg && v < 0) v = 0.0;
+        s_x[j] = v;
+    }
+    __syncthreads();
+    const int n = x0 + threadIdx.x;
+    if (n >= L) return;
+    double num = 0.0, den = 0.0;
+    for (int m = 0; m < wlen; m++) {
+        int idx = n + h - m;            // global index
+        double v = s_x[idx - lo];
+        double w = s_w[m];
+        if (idx >= 0 && idx < L && v == v) {
+            num += w * v;
+            den += w;
+        }
+    }
+    out[n] = (den == 0.0) ? nb_nan() : num / den;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: InsertionBiasTrack.computeBias, pyatac/bias.py:85-92 + seq.py:37-45.
+//   b[p] = sum_j logPWM[nuc(seq[p - up + j]), j]   (non-ACGT contributes 0: all-zero one-hot column)
+// written as E[p] = exp(b[p]) and / or b[p].  grid (tiles, chunks); block 256; the sequence tile is
+// staged in shared memory as PWM row codes.
+// ---------------------------------------------------------------------------------------------
+#define BT_TILE 1024
+static __global__ void __launch_bounds__(256) k_bias_track(const uint8_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
+                                                           const int64_t *__restrict__ bias_off,
+                                                           const double *__restrict__ log_pwm,
+                                                           const int8_t *__restrict__ nuc_code, int n_nuc, int width,
+                                                           double *__restrict__ E, double *__restrict__ b_out)
+{
+    __shared__ double s_pwm[NB200_MAX_NUC * NB200_MAX_PWM_WIDTH];
+    __shared__ int8_t s_code[256];
+    __shared__ int8_t s_seq[BT_TILE + NB200_MAX_PWM_WIDTH];
+    const int c = blockIdx.y;
+    const int64_t so = seq_off[c];
+    const int64_t slen = seq_off[c + 1] - so;
+    const int64_t blen = slen - (width - 1);
+    const int64_t x0 = (int64_t)blockIdx.x * BT_TILE;
+    if (x0 >= blen) return;
+    for (int i = threadIdx.x; i < n_nuc * width; i += blockDim.x) s_pwm[i] = log_pwm[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_code[i] = nuc_code[i];
+    __syncthreads();
+    const int nload = (int)min((int64_t)(BT_TILE + width - 1), slen - x0);
+    for (int i = threadIdx.x; i < nload; i += blockDim.x) s_seq[i] = s_code[seq[so + x0 + i]];
+    __syncthreads();
+    const int n = (int)min((int64_t)BT_TILE, blen - x0);
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        double acc = 0.0;
+        for (int j = 0; j < width; j++) {
+            int code = s_seq[t + j];
+            if (code >= 0) acc += s_pwm[code * width + j];
+        }
+        int64_t o = bias_off[c] + x0 + t;
+        if (E) E[o] = exp(acc);
+        if (b_out) b_out[o] = acc;
+    }
+}

@@ -1,0 +1,733 @@
+// nb200_nuc.cu -- NucChunk.process on the device (nucleoatac/NucleosomeCalling.py:230-345, run_nuc.py:22-39),
+// without fit/getFuzz (host scipy optimiser).
+//
+// Stages (per batch, every chunk in parallel):
+//   k_nuc_colsums   cB[c] = sum_{i in [lv,uv)} f_i * Bp[i,c]                      (bias coverage operand, :56-58)
+//   k_nuc_bx_fp64   bx[x] = sum_i sum_k f_i V[i,k] Bp[i, x-w+k]   dense background xcor, fp64 CUDA cores  (:60-63)
+//                   (nb200_xcor_tc.cu holds the tcgen05 version of the same contraction)
+//   k_nuc_tracks    nuc_cov / nfr_cov from the CSC prefix, bias coverage, sparse signal xcor (:29-36),
+//                   background = bx*nuc_cov/bcov (:64), norm = signal - background (:42-43)
+//   k_smooth_same   gaussian smoothing of max(norm,0) (:274-283)
+//   k_nuc_peaks     candidates = call_peaks(norm+smoothed, order 12, sep 25, boundary 60)   (:294-301)
+//   k_cand_stats    per candidate: likelihood ratio (:110-122), closed-form multinomial variance
+//                   (multinomial_cov.pyx:20-31) and z-score (:123-127), fp64, one block per candidate
+//   k_nuc_reduce    nonredundant set = reduce_peaks by z, sep 120 (:312-315)
+#include "nb200_dev.cuh"
+
+// ---------------------------------------------------------------------------------------------
+#define NC_TILE 128
+__global__ void __launch_bounds__(NC_TILE) k_nuc_colsums(const int32_t *__restrict__ start, const int64_t *__restrict__ out_off,
+                                                         const int64_t *__restrict__ bias_off,
+                                                         const int32_t *__restrict__ seq_start, int pwm_up,
+                                                         const double *__restrict__ E, const double *__restrict__ f, int lv,
+                                                         int uv, int w, double *__restrict__ cB)
+{
+    extern __shared__ double sm_nc[];
+    double *s_f = sm_nc, *s_E = sm_nc + uv;  // s_E[NC_TILE + uv + 2]
+    const int c = blockIdx.y;
+    const int L = (int)(out_off[c + 1] - out_off[c]);
+    const int ncol = L + 2 * w;
+    const int j0 = blockIdx.x * NC_TILE;
+    if (j0 >= ncol) return;
+    for (int i = threadIdx.x; i < uv; i += blockDim.x) s_f[i] = f[i];
+    const int half = uv / 2;
+    const int g0 = start[c] - w + j0;
+    const int64_t eb = bias_off[c] - (int64_t)(seq_start[c] + pwm_up);
+    const int nE = NC_TILE + 2 * half + 2;
+    for (int i = threadIdx.x; i < nE; i += blockDim.x) s_E[i] = E[eb + g0 - half + i];
+    __syncthreads();
+    const int j = j0 + threadIdx.x;
+    if (j >= ncol) return;
+    const double *Ec = s_E + half + threadIdx.x;
+    double acc = 0.0;
+    for (int i = lv; i < uv; i++) acc += s_f[i] * bias_cell(Ec, i);
+    cB[out_off[c] + 2 * (int64_t)w * c + j] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dense background cross-correlation, fp64.  One block = BX_NT threads x BX_XT consecutive outputs
+// each; for every insert-size row the pre-normalisation bias row Bp_i is generated on the fly from
+// the 1-D track E (never materialised in HBM) into shared memory in an XT-way interleaved layout so
+// that the sliding-window register tile reads it conflict-free; T = f_i*V rows are zero padded to a
+// multiple of XT.  2*R*Wpad flops per output.
+// ---------------------------------------------------------------------------------------------
+#define BX_NT 64
+#define BX_XT 16
+#define BX_TX (BX_NT * BX_XT)
+__global__ void __launch_bounds__(BX_NT) k_nuc_bx_fp64(const int32_t *__restrict__ start, const int64_t *__restrict__ out_off,
+                                                       const int64_t *__restrict__ bias_off,
+                                                       const int32_t *__restrict__ seq_start, int pwm_up,
+                                                       const double *__restrict__ E, const double *__restrict__ Tfp, int lv,
+                                                       int R, int w, int wpad, double *__restrict__ bx)
+{
+    extern __shared__ double sm_bx[];
+    const int c = blockIdx.y;
+    const int64_t oo = out_off[c];
+    const int L = (int)(out_off[c + 1] - oo);
+    const int x0 = blockIdx.x * BX_TX;
+    if (x0 >= L) return;
+    const int uv = lv + R;
+    const int half = uv / 2;
+    const int nB = BX_TX + wpad;            // Bp values per row tile (those past Tx+W-1 are multiplied by T == 0)
+    const int Q = nB / BX_XT;               // interleave stride
+    const int nE = nB + 2 * half + 2;
+    double *s_E = sm_bx;                    // [nE]   E over genomic [g0 - w - half, ...)
+    double *s_B = s_E + nE;                 // [2][nB]
+    double *s_T = s_B + 2 * nB;             // [2][wpad]
+    const int g0 = start[c] + x0;
+    const int64_t eb = bias_off[c] - (int64_t)(seq_start[c] + pwm_up);
+    const int64_t e_lo = bias_off[c], e_hi = bias_off[c + 1];
+    for (int i = threadIdx.x; i < nE; i += BX_NT) {
+        int64_t idx = eb + g0 - w - half + i;
+        s_E[i] = (idx >= e_lo && idx < e_hi) ? E[idx] : 0.0;  // beyond the track only under zero T padding
+    }
+    __syncthreads();
+    auto fill = [&](int r, int buf) {
+        const int i = lv + r;
+        double *B = s_B + buf * nB;
+        for (int n = threadIdx.x; n < nB; n += BX_NT)
+            B[(n % BX_XT) * Q + n / BX_XT] = bias_cell(s_E + half + n, i);
+        double *T = s_T + buf * wpad;
+        for (int k = threadIdx.x; k < wpad; k += BX_NT) T[k] = Tfp[(size_t)r * wpad + k];
+    };
+    double acc[BX_XT];
+#pragma unroll
+    for (int u = 0; u < BX_XT; u++) acc[u] = 0.0;
+    fill(0, 0);
+    __syncthreads();
+    for (int r = 0; r < R; r++) {
+        if (r + 1 < R) fill(r + 1, (r + 1) & 1);
+        const double *B = s_B + (r & 1) * nB + threadIdx.x;   // element n = t*XT + e  ->  B[(e%XT)*Q + e/XT]
+        const double *T = s_T + (r & 1) * wpad;
+        double win[BX_XT];
+#pragma unroll
+        for (int u = 0; u < BX_XT; u++) win[u] = B[u * Q];
+        for (int k = 0; k < wpad; k += BX_XT) {
+            const int q = k / BX_XT + 1;
+#pragma unroll
+            for (int kk = 0; kk < BX_XT; kk++) {
+                const double t = T[k + kk];
+#pragma unroll
+                for (int u = 0; u < BX_XT; u++) acc[u] = fma(win[(u + kk) % BX_XT], t, acc[u]);
+                win[kk] = B[kk * Q + q];   // element k + kk + XT
+            }
+        }
+        __syncthreads();
+    }
+    const int xb = x0 + threadIdx.x * BX_XT;
+#pragma unroll
+    for (int u = 0; u < BX_XT; u++)
+        if (xb + u < L) bx[oo + xb + u] = acc[u];
+}
+
+int nb200_nuc_bx_fp64(nb200_ctx *ctx, nb200_dbatch *b)
+{
+    RunConst &r = ctx->rc;
+    const int nB = BX_TX + r.v_wpad;
+    const int half = r.v_upper / 2;
+    size_t smem = sizeof(double) * ((size_t)nB + 2 * half + 2 + 2 * (size_t)nB + 2 * (size_t)r.v_wpad);
+    if (smem > 200 * 1024) return nb200_fail(ctx, NB200_ERR_ARG, "VMat too large for the fp64 background kernel");
+    if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_nuc_bx_fp64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps(ctx, b->stream, "k_nuc_bx_fp64");
+    dim3 grid((unsigned)div_up64(b->max_len, BX_TX), b->n_chunks);
+    k_nuc_bx_fp64<<<grid, BX_NT, smem, b->stream>>>(b->d_start.as<int32_t>(), b->d_out_off.as<int64_t>(),
+                                                    b->d_bias_off.as<int64_t>(), b->d_seq_start.as<int32_t>(), r.pwm_up,
+                                                    b->d_E.as<double>(), r.vmat_fp.as<double>(), r.v_lower, r.v_rows, r.v_w,
+                                                    r.v_wpad, b->n_bx.as<double>());
+    NB_LAUNCH_CHECK(ctx);
+    return NB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct NucTrackArgs {
+    const int64_t *out_off, *col_off, *frag_off;
+    const int32_t *col_ptr, *col_low;
+    const int2 *ent;
+    const double *V, *cB, *bx;
+    double *nuc_cov, *nfr_cov, *bcov, *signal, *bg, *norm;
+    int lv, uv, W, w, csc_pad, use_bias;
+    double bcov_nobias, bx_nobias;
+};
+
+#define NT_TILE 256
+__global__ void __launch_bounds__(NT_TILE) k_nuc_tracks(NucTrackArgs a)
+{
+    extern __shared__ double sm_nt[];  // cB tile [NT_TILE + 2w]
+    const int c = blockIdx.y;
+    const int64_t oo = a.out_off[c];
+    const int L = (int)(a.out_off[c + 1] - oo);
+    const int x0 = blockIdx.x * NT_TILE;
+    if (x0 >= L) return;
+    if (a.use_bias) {
+        const int64_t co = oo + 2 * (int64_t)a.w * c + x0;
+        const int nc = min(NT_TILE, L - x0) + 2 * a.w;
+        for (int i = threadIdx.x; i < nc; i += blockDim.x) sm_nt[i] = a.cB[co + i];
+        __syncthreads();
+    }
+    const int x = x0 + threadIdx.x;
+    if (x >= L) return;
+    const int32_t *cp = a.col_ptr + a.col_off[c];
+    const int lo = x - a.w + a.csc_pad, hi = x + a.w + 1 + a.csc_pad;
+    const int e0 = cp[lo], e1 = cp[hi];
+    int nlow = 0;
+    if (a.col_low) {
+        const int32_t *cl = a.col_low + a.col_off[c];
+        nlow = cl[hi] - cl[lo];
+    }
+    const double nuc_cov = (double)(e1 - e0 - nlow), nfr_cov = (double)nlow;
+    double bcov, bxv;
+    if (a.use_bias) {
+        double s = 0.0;
+        for (int k = 0; k < a.W; k++) s += sm_nt[threadIdx.x + k];
+        bcov = s;
+        bxv = a.bx[oo + x];
+    } else {
+        bcov = a.bcov_nobias;
+        bxv = a.bx_nobias;
+    }
+    // sparse signal xcor: every fragment centred within +-w contributes one VMat entry
+    const int2 *en = a.ent + a.frag_off[c];
+    double sig = 0.0;
+    const int kb = a.w - (x + a.csc_pad);
+    for (int e = e0; e < e1; e++) {
+        const int2 v = en[e];
+        if (v.y >= a.lv && v.y < a.uv) sig += a.V[(size_t)(v.y - a.lv) * a.W + (v.x + kb)];
+    }
+    const double bg = bxv * nuc_cov / bcov;  // NucleosomeCalling.py:64
+    a.nuc_cov[oo + x] = nuc_cov;
+    a.nfr_cov[oo + x] = nfr_cov;
+    a.bcov[oo + x] = bcov;
+    a.signal[oo + x] = sig;
+    a.bg[oo + x] = bg;
+    a.norm[oo + x] = sig - bg;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct NucPeakArgs {
+    const int32_t *start;
+    const int64_t *out_off, *cand_off;
+    const double *jitter, *norm, *smooth, *signal, *nuc_cov, *nfr_cov;
+    double *comb;                    // scratch track
+    int32_t *sc_pos;
+    double *sc_val;
+    unsigned char *sc_state;
+    int32_t *cand_count, *cand_pos, *cand_flag;
+    double *cand_z, *cand_lr, *cand_norm, *cand_sig, *cand_cov, *cand_nfr, *cand_smooth;
+    int2 *work;
+    int32_t *work_count;
+    int sep, boundary, order;
+    double min_signal, min_reads;
+};
+
+#define PK_THREADS_N 512
+__global__ void __launch_bounds__(PK_THREADS_N) k_nuc_peaks(NucPeakArgs a)
+{
+    __shared__ double red_d[32];
+    __shared__ int red_i[32];
+    __shared__ int s_base, s_flag;
+    const int c = blockIdx.x;
+    const int64_t oo = a.out_off[c];
+    const int L = (int)(a.out_off[c + 1] - oo);
+    double *cb = a.comb + oo;
+    int32_t *cpos = a.sc_pos + oo;
+    double *cval = a.sc_val + oo;
+    unsigned char *cst = a.sc_state + oo;
+    const int tid = threadIdx.x;
+    double mn = CUDART_INF;
+    int nnan = 0;
+    for (int x = tid; x < L; x += blockDim.x) {
+        double v = a.norm[oo + x] + a.smooth[oo + x];  // NucleosomeCalling.py:297
+        cb[x] = v;
+        if (v != v) nnan++;
+        else mn = fmin(mn, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(NB_FULL, mn, o));
+        nnan += __shfl_xor_sync(NB_FULL, nnan, o);
+    }
+    if ((tid & 31) == 0) {
+        red_d[tid >> 5] = mn;
+        red_i[tid >> 5] = nnan;
+    }
+    __syncthreads();
+    mn = CUDART_INF;
+    nnan = 0;
+    for (int wv = 0; wv < (int)(blockDim.x >> 5); wv++) {
+        mn = fmin(mn, red_d[wv]);
+        nnan += red_i[wv];
+    }
+    __syncthreads();
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    int m = 0;
+    if (nnan < L) {
+        if (nnan > 0)
+            for (int x = tid; x < L; x += blockDim.x)
+                if (cb[x] != cb[x]) cb[x] = mn;
+        __syncthreads();
+        const int lo = max(0, a.boundary), hi = L - a.boundary;
+        for (int x0 = 0; x0 < L; x0 += blockDim.x) {
+            const int x = x0 + tid;
+            int flag = 0;
+            double v = 0.0;
+            if (x >= lo && x < hi) {
+                v = cb[x];
+                const double j0 = v * (1.0 + a.jitter[x]);
+                flag = (v >= a.min_signal);
+                for (int d = 1; d <= a.order && flag; d++) {  // argrelmax(order), mode='clip'
+                    const int xl = max(x - d, 0), xr = min(x + d, L - 1);
+                    flag = (j0 > cb[xl] * (1.0 + a.jitter[xl])) && (j0 > cb[xr] * (1.0 + a.jitter[xr]));
+                }
+            }
+            int slot = block_compact_slot(flag, &s_base, red_i);
+            if (flag) {
+                cpos[slot] = x;
+                cval[slot] = v;
+            }
+        }
+        __syncthreads();
+        m = s_base;
+        block_nms(cpos, cval, cst, m, a.sep, &s_flag);
+    }
+    __syncthreads();
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    const int64_t po = a.cand_off[c];
+    const int cap = (int)(a.cand_off[c + 1] - po);
+    for (int j0 = 0; j0 < m; j0 += blockDim.x) {
+        const int j = j0 + tid;
+        const int flag = (j < m && cst[j] == 1);
+        int slot = block_compact_slot(flag, &s_base, red_i);
+        if (flag && slot < cap) {
+            const int x = cpos[j];
+            const double cov = a.nuc_cov[oo + x];
+            a.cand_pos[po + slot] = a.start[c] + x;
+            a.cand_norm[po + slot] = a.norm[oo + x];
+            a.cand_sig[po + slot] = a.signal[oo + x];
+            a.cand_cov[po + slot] = cov;
+            a.cand_nfr[po + slot] = a.nfr_cov[oo + x];
+            a.cand_smooth[po + slot] = a.smooth[oo + x];
+            a.cand_z[po + slot] = nb_nan();
+            a.cand_lr[po + slot] = nb_nan();
+            int fl = 0;
+            if (cov > a.min_reads) {  // NucleosomeCalling.py:304
+                fl = 1;
+                int wslot = atomicAdd(&a.work_count[0], 1);
+                a.work[wslot] = make_int2(c, slot);
+            }
+            a.cand_flag[po + slot] = fl;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) a.cand_count[c] = (s_base <= cap) ? s_base : -s_base;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct CandArgs {
+    const int32_t *start;
+    const int64_t *out_off, *col_off, *frag_off, *bias_off, *cand_off;
+    const int32_t *seq_start;
+    const int32_t *col_ptr;
+    const int2 *ent;
+    const double *E, *V, *f;
+    const int2 *work;
+    const int32_t *work_count;
+    const int32_t *cand_pos;
+    int32_t *cand_flag;
+    const double *cand_norm, *cand_cov;
+    double *cand_z, *cand_lr;
+    int pwm_up, lv, R, W, w, csc_pad, use_bias, lr_is_nan;
+    double min_lr, min_z;
+};
+
+#define CS_THREADS 256
+__global__ void __launch_bounds__(CS_THREADS) k_cand_stats(CandArgs a)
+{
+    __shared__ double red[32];
+    const int nwork = a.work_count[0];
+    const int tid = threadIdx.x;
+    for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+        const int2 it = a.work[wi];
+        const int c = it.x;
+        const int64_t ci = a.cand_off[c] + it.y;
+        const int P = a.cand_pos[ci];
+        const int x = P - a.start[c];
+        const double *Eg = a.use_bias ? a.E + (a.bias_off[c] - (int64_t)(a.seq_start[c] + a.pwm_up)) + (P - a.w) : nullptr;
+        // dense window sums: S_VB = sum V*Bp, S_B = sum f*Bp, S_BV = sum f*V*Bp, S_BV2 = sum f*V^2*Bp
+        double sVB = 0.0, sB = 0.0, sBV = 0.0, sBV2 = 0.0;
+        const int n = a.R * a.W;
+        for (int idx = tid; idx < n; idx += CS_THREADS) {
+            const int r = idx / a.W, k = idx - r * a.W;
+            const int i = a.lv + r;
+            const double bp = a.use_bias ? bias_cell(Eg + k, i) : 1.0;
+            const double v = a.V[idx];
+            const double b = __dmul_rn(bp, a.f[i]);  // normByInsertDist, chunkmat2d.py:154-156
+            sVB += v * bp;
+            sB += b;
+            sBV += b * v;
+            sBV2 += b * v * v;
+        }
+        sVB = block_sum(sVB, red);
+        sB = block_sum(sB, red);
+        sBV = block_sum(sBV, red);
+        sBV2 = block_sum(sBV2, red);
+        // sparse likelihoods over the fragments of the window, NucleosomeCalling.py:110-122
+        const int32_t *cp = a.col_ptr + a.col_off[c];
+        const int2 *en = a.ent + a.frag_off[c];
+        const int e0 = cp[x - a.w + a.csc_pad], e1 = cp[x + a.w + 1 + a.csc_pad];
+        const int kb = a.w - (x + a.csc_pad);
+        double nl = 0.0, ul = 0.0;
+        for (int e = e0 + tid; e < e1; e += CS_THREADS) {
+            const int2 v = en[e];
+            const int r = v.y - a.lv;
+            if (r >= 0 && r < a.R) {
+                const int k = v.x + kb;
+                const double bp = a.use_bias ? bias_cell(Eg + k, v.y) : 1.0;
+                nl += log(__dmul_rn(a.V[(size_t)r * a.W + k], bp) / sVB);
+                ul += log(__dmul_rn(bp, a.f[v.y]) / sB);
+            }
+        }
+        nl = block_sum(nl, red);
+        ul = block_sum(ul, red);
+        if (tid == 0) {
+            double lr = a.lr_is_nan ? nb_nan() : nl - ul;  // 0*log(0) cells make both likelihoods NaN in the reference
+            int fl = a.cand_flag[ci];
+            double z = nb_nan();
+            if (lr > a.min_lr) {
+                fl |= 2;
+                const double mean = sBV / sB;
+                // calculateCov closed form r*(sum p v^2 - (sum p v)^2), r truncated to C int (multinomial_cov.pyx:20)
+                const double var = (double)(int)a.cand_cov[ci] * (sBV2 / sB - mean * mean);
+                z = a.cand_norm[ci] / sqrt(var);
+                if (z >= a.min_z) fl |= 4;
+            }
+            a.cand_lr[ci] = lr;
+            a.cand_z[ci] = z;
+            a.cand_flag[ci] = fl;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct NucReduceArgs {
+    const int64_t *cand_off;
+    const int32_t *cand_count, *cand_pos;
+    int32_t *cand_flag;
+    const double *cand_z;
+    int32_t *sc_pos;   // scratch sized like the candidate arrays
+    double *sc_val;
+    unsigned char *sc_state;
+    int32_t *sc_idx;
+    int sep;
+};
+
+__global__ void __launch_bounds__(256) k_nuc_reduce(NucReduceArgs a)
+{
+    __shared__ int red_i[32];
+    __shared__ int s_base, s_flag;
+    const int c = blockIdx.x;
+    const int64_t po = a.cand_off[c];
+    int n = a.cand_count[c];
+    if (n < 0) n = (int)(a.cand_off[c + 1] - po);
+    const int tid = threadIdx.x;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int j0 = 0; j0 < n; j0 += blockDim.x) {
+        const int j = j0 + tid;
+        const int flag = (j < n) && (a.cand_flag[po + j] & 4);
+        int slot = block_compact_slot(flag, &s_base, red_i);
+        if (flag) {
+            a.sc_pos[po + slot] = a.cand_pos[po + j];
+            a.sc_val[po + slot] = a.cand_z[po + j];
+            a.sc_idx[po + slot] = j;
+        }
+    }
+    __syncthreads();
+    const int m = s_base;
+    block_nms(a.sc_pos + po, a.sc_val + po, a.sc_state + po, m, a.sep, &s_flag);
+    __syncthreads();
+    for (int j = tid; j < m; j += blockDim.x)
+        if (a.sc_state[po + j] == 1) a.cand_flag[po + a.sc_idx[po + j]] |= 8;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
+{
+    if (!ctx || !b) return nb200_fail(ctx, NB200_ERR_ARG, "nb200_nuc_run: NULL argument");
+    if (!ctx->nuc_configured) return nb200_fail(ctx, NB200_ERR_STATE, "nb200_nuc_configure has not been called");
+    RunConst &r = ctx->rc;
+    const nb200_nuc_params &p = ctx->nuc;
+    if (!r.have_vmat) return nb200_fail(ctx, NB200_ERR_STATE, "nb200_set_vmat has not been called");
+    if (!r.have_sizes || r.sizes_upper < r.v_upper)
+        return nb200_fail(ctx, NB200_ERR_STATE, "nb200_set_fragment_sizes missing or shorter than the VMat's upper size");
+    if (r.v_upper > NB200_MAX_UPPER) return nb200_fail(ctx, NB200_ERR_ARG, "VMat upper > %d unsupported", NB200_MAX_UPPER);
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int n = b->n_chunks;
+    const int W = r.v_cols, w = r.v_w, lv = r.v_lower, uv = r.v_upper;
+    if (b->min_len < p.smooth_len)
+        return nb200_fail(ctx, NB200_ERR_ARG, "a chunk is shorter (%d) than the smoothing window (%d)", b->min_len, p.smooth_len);
+    if (r.n_jitter < b->max_len)
+        return nb200_fail(ctx, NB200_ERR_STATE, "nb200_set_jitter: need >= %d values (longest chunk), have %lld", b->max_len,
+                          (long long)r.n_jitter);
+    const int pad = W > uv / 2 + 1 ? W : uv / 2 + 1;  // NucleosomeCalling.py:240
+    NB_CHECK(nb200_prep_csc(ctx, b, pad, uv, p.atac, lv));
+    if (p.use_bias) {
+        NB_CHECK(nb200_prep_bias(ctx, b));
+        for (int c = 0; c < n; c++) {
+            int64_t b0 = (int64_t)b->h_seq_start[c] + r.pwm_up;
+            int64_t b1 = b0 + (b->h_seq_off[c + 1] - b->h_seq_off[c]) - (r.pwm_width - 1);
+            if (b0 > (int64_t)b->h_start[c] - w - uv / 2 || b1 < (int64_t)b->h_end[c] + w + uv / 2 + 1)
+                return nb200_fail(ctx, NB200_ERR_FLANK,
+                                  "Insufficient flanking region: chunk %d needs sequence over [%lld, %lld)", c,
+                                  (long long)b->h_start[c] - w - uv / 2 - r.pwm_up,
+                                  (long long)b->h_end[c] + w + uv / 2 + 1 + r.pwm_down);
+        }
+    }
+    const size_t tl = (size_t)b->total_len;
+    DevBuf *tracks[] = {&b->n_signal, &b->n_bg, &b->n_norm, &b->n_smooth, &b->n_nuc_cov, &b->n_nfr_cov, &b->n_bcov, &b->sc_f64};
+    for (auto t : tracks) NB_CUDA(ctx, t->reserve(sizeof(double) * tl));
+    NB_CUDA(ctx, b->sc_i32.reserve(sizeof(int32_t) * tl));
+    NB_CUDA(ctx, b->sc_u8.reserve(tl));
+    // candidate capacities: kept candidates are >= redundant_sep apart
+    b->h_ncand_off.assign(n + 1, 0);
+    for (int c = 0; c < n; c++) b->h_ncand_off[c + 1] = b->h_ncand_off[c] + (b->h_end[c] - b->h_start[c]) / p.redundant_sep + 2;
+    const size_t nc = (size_t)b->h_ncand_off[n];
+    NB_CUDA(ctx, b->n_cand_off.reserve(sizeof(int64_t) * (n + 1)));
+    NB_CUDA(ctx, cudaMemcpyAsync(b->n_cand_off.p, b->h_ncand_off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, b->stream));
+    NB_CUDA(ctx, b->n_cand_count.reserve(sizeof(int32_t) * n));
+    NB_CUDA(ctx, b->n_cand_pos.reserve(sizeof(int32_t) * nc));
+    NB_CUDA(ctx, b->n_cand_flag.reserve(sizeof(int32_t) * nc));
+    DevBuf *cd[] = {&b->n_cand_z, &b->n_cand_lr, &b->n_cand_norm, &b->n_cand_sig, &b->n_cand_cov, &b->n_cand_nfr, &b->n_cand_smooth};
+    for (auto t : cd) NB_CUDA(ctx, t->reserve(sizeof(double) * nc));
+    NB_CUDA(ctx, b->n_work.reserve(sizeof(int2) * nc));
+    NB_CUDA(ctx, b->n_work_count.reserve(sizeof(int32_t) * 4));
+    NB_CUDA(ctx, cudaMemsetAsync(b->n_work_count.p, 0, sizeof(int32_t) * 4, b->stream));
+
+    if (p.use_bias) {
+        NB_CUDA(ctx, b->n_bx.reserve(sizeof(double) * tl));
+        NB_CUDA(ctx, b->n_cB.reserve(sizeof(double) * (tl + 2 * (size_t)w * n)));
+        {
+            size_t smem = sizeof(double) * ((size_t)uv + NC_TILE + 2 * (uv / 2) + 8);
+            if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_nuc_colsums, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ProfScope ps(ctx, b->stream, "k_nuc_colsums");
+            dim3 grid((unsigned)div_up64(b->max_len + 2 * w, NC_TILE), n);
+            k_nuc_colsums<<<grid, NC_TILE, smem, b->stream>>>(b->d_start.as<int32_t>(), b->d_out_off.as<int64_t>(),
+                                                              b->d_bias_off.as<int64_t>(), b->d_seq_start.as<int32_t>(), r.pwm_up,
+                                                              b->d_E.as<double>(), r.sizes.as<double>(), lv, uv, w, b->n_cB.as<double>());
+            NB_LAUNCH_CHECK(ctx);
+        }
+        int mode = p.xcor_mode;
+        if (mode == 0) mode = 1;  // auto: fp64 CUDA cores unless the tensor-core path is requested
+        if (mode == 2) {
+            if (!nb200_tc_available(ctx)) return nb200_fail(ctx, NB200_ERR_STATE, "xcor_mode 2 (tcgen05) is not available in this build");
+            NB_CHECK(nb200_nuc_bx_tc(ctx, b));
+        } else
+            NB_CHECK(nb200_nuc_bx_fp64(ctx, b));
+    }
+    {
+        NucTrackArgs a;
+        a.out_off = b->d_out_off.as<int64_t>();
+        a.col_off = b->d_col_off.as<int64_t>();
+        a.frag_off = b->d_frag_off.as<int64_t>();
+        a.col_ptr = b->d_col_ptr.as<int32_t>();
+        a.col_low = (lv > 0) ? b->d_col_low.as<int32_t>() : nullptr;
+        a.ent = b->d_ent.as<int2>();
+        a.V = r.vmat.as<double>();
+        a.cB = b->n_cB.as<double>();
+        a.bx = b->n_bx.as<double>();
+        a.nuc_cov = b->n_nuc_cov.as<double>();
+        a.nfr_cov = b->n_nfr_cov.as<double>();
+        a.bcov = b->n_bcov.as<double>();
+        a.signal = b->n_signal.as<double>();
+        a.bg = b->n_bg.as<double>();
+        a.norm = b->n_norm.as<double>();
+        a.lv = lv;
+        a.uv = uv;
+        a.W = W;
+        a.w = w;
+        a.csc_pad = b->csc_pad;
+        a.use_bias = p.use_bias;
+        // no --fasta: bias matrix = ones * f_i (NucleosomeCalling.py:248-254) -> both xcors are constants
+        a.bcov_nobias = r.f_sum_v * W;
+        double s = 0.0;
+        for (int i = 0; i < r.v_rows; i++) {
+            double rs = 0.0;
+            for (int k = 0; k < W; k++) rs += r.h_vmat[(size_t)i * W + k];
+            s += rs * r.h_sizes[lv + i];
+        }
+        a.bx_nobias = s;
+        size_t smem = sizeof(double) * (NT_TILE + 2 * (size_t)w + 2);
+        if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_nuc_tracks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ProfScope ps(ctx, b->stream, "k_nuc_tracks");
+        dim3 grid((unsigned)div_up64(b->max_len, NT_TILE), n);
+        k_nuc_tracks<<<grid, NT_TILE, smem, b->stream>>>(a);
+        NB_LAUNCH_CHECK(ctx);
+    }
+    {
+        SmoothTracks tr;
+        tr.in[0] = tr.in[1] = tr.in[2] = b->n_norm.as<double>();
+        tr.out[0] = tr.out[1] = tr.out[2] = b->n_smooth.as<double>();
+        size_t smem = sizeof(double) * (SM_TILE + 2 * (size_t)p.smooth_len);
+        if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_smooth_same, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ProfScope ps(ctx, b->stream, "k_smooth_same");
+        dim3 grid((unsigned)div_up64(b->max_len, SM_TILE), n, 1);
+        k_smooth_same<<<grid, SM_TILE, smem, b->stream>>>(tr, b->d_out_off.as<int64_t>(), r.nuc_win.as<double>(), p.smooth_len, 1);
+        NB_LAUNCH_CHECK(ctx);
+    }
+    {
+        NB_CUDA(ctx, b->n_bx.reserve(sizeof(double) * tl));  // reused as the combined-signal scratch when bias is off
+        NucPeakArgs a;
+        a.start = b->d_start.as<int32_t>();
+        a.out_off = b->d_out_off.as<int64_t>();
+        a.cand_off = b->n_cand_off.as<int64_t>();
+        a.jitter = r.jitter.as<double>();
+        a.norm = b->n_norm.as<double>();
+        a.smooth = b->n_smooth.as<double>();
+        a.signal = b->n_signal.as<double>();
+        a.nuc_cov = b->n_nuc_cov.as<double>();
+        a.nfr_cov = b->n_nfr_cov.as<double>();
+        a.comb = b->n_bcov.as<double>();  // bcov is consumed by k_nuc_tracks; reuse as norm+smoothed scratch
+        a.sc_pos = b->sc_i32.as<int32_t>();
+        a.sc_val = b->sc_f64.as<double>();
+        a.sc_state = b->sc_u8.as<unsigned char>();
+        a.cand_count = b->n_cand_count.as<int32_t>();
+        a.cand_pos = b->n_cand_pos.as<int32_t>();
+        a.cand_flag = b->n_cand_flag.as<int32_t>();
+        a.cand_z = b->n_cand_z.as<double>();
+        a.cand_lr = b->n_cand_lr.as<double>();
+        a.cand_norm = b->n_cand_norm.as<double>();
+        a.cand_sig = b->n_cand_sig.as<double>();
+        a.cand_cov = b->n_cand_cov.as<double>();
+        a.cand_nfr = b->n_cand_nfr.as<double>();
+        a.cand_smooth = b->n_cand_smooth.as<double>();
+        a.work = b->n_work.as<int2>();
+        a.work_count = b->n_work_count.as<int32_t>();
+        a.sep = p.redundant_sep;
+        a.boundary = p.nonredundant_sep / 2;
+        a.order = p.redundant_sep / 2;
+        a.min_signal = 0.0;
+        a.min_reads = p.min_reads;
+        ProfScope ps(ctx, b->stream, "k_nuc_peaks");
+        k_nuc_peaks<<<n, PK_THREADS_N, 0, b->stream>>>(a);
+        NB_LAUNCH_CHECK(ctx);
+    }
+    {
+        CandArgs a;
+        a.start = b->d_start.as<int32_t>();
+        a.out_off = b->d_out_off.as<int64_t>();
+        a.col_off = b->d_col_off.as<int64_t>();
+        a.frag_off = b->d_frag_off.as<int64_t>();
+        a.bias_off = b->d_bias_off.as<int64_t>();
+        a.cand_off = b->n_cand_off.as<int64_t>();
+        a.seq_start = b->d_seq_start.as<int32_t>();
+        a.col_ptr = b->d_col_ptr.as<int32_t>();
+        a.ent = b->d_ent.as<int2>();
+        a.E = b->d_E.as<double>();
+        a.V = r.vmat.as<double>();
+        a.f = r.sizes.as<double>();
+        a.work = b->n_work.as<int2>();
+        a.work_count = b->n_work_count.as<int32_t>();
+        a.cand_pos = b->n_cand_pos.as<int32_t>();
+        a.cand_flag = b->n_cand_flag.as<int32_t>();
+        a.cand_norm = b->n_cand_norm.as<double>();
+        a.cand_cov = b->n_cand_cov.as<double>();
+        a.cand_z = b->n_cand_z.as<double>();
+        a.cand_lr = b->n_cand_lr.as<double>();
+        a.pwm_up = r.pwm_up;
+        a.lv = lv;
+        a.R = r.v_rows;
+        a.W = W;
+        a.w = w;
+        a.csc_pad = b->csc_pad;
+        a.use_bias = p.use_bias;
+        a.lr_is_nan = (r.v_has_zero || r.f_has_zero) ? 1 : 0;
+        a.min_lr = p.min_lr;
+        a.min_z = p.min_z;
+        ProfScope ps(ctx, b->stream, "k_cand_stats");
+        k_cand_stats<<<ctx->sm_count * 8, CS_THREADS, 0, b->stream>>>(a);
+        NB_LAUNCH_CHECK(ctx);
+    }
+    {
+        NucReduceArgs a;
+        a.cand_off = b->n_cand_off.as<int64_t>();
+        a.cand_count = b->n_cand_count.as<int32_t>();
+        a.cand_pos = b->n_cand_pos.as<int32_t>();
+        a.cand_flag = b->n_cand_flag.as<int32_t>();
+        a.cand_z = b->n_cand_z.as<double>();
+        // the per-position scratch arrays are larger than the candidate arrays (cand capacity <= len/sep+2 <= len)
+        a.sc_pos = b->sc_i32.as<int32_t>();
+        a.sc_val = b->sc_f64.as<double>();
+        a.sc_state = b->sc_u8.as<unsigned char>();
+        a.sc_idx = reinterpret_cast<int32_t *>(b->n_bcov.p);
+        a.sep = p.nonredundant_sep;
+        ProfScope ps(ctx, b->stream, "k_nuc_reduce");
+        k_nuc_reduce<<<n, 256, 0, b->stream>>>(a);
+        NB_LAUNCH_CHECK(ctx);
+    }
+    b->nuc_done = true;
+    return NB200_OK;
+}
+
+static int d2h(nb200_ctx *ctx, nb200_dbatch *b, void *dst, const DevBuf &src, size_t bytes)
+{
+    if (!dst || !bytes) return NB200_OK;
+    NB_CUDA(ctx, cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, b->stream));
+    return NB200_OK;
+}
+
+int nb200_nuc_download(nb200_ctx *ctx, nb200_dbatch *b, const nb200_nuc_out *o)
+{
+    if (!ctx || !b || !o) return nb200_fail(ctx, NB200_ERR_ARG, "nb200_nuc_download: NULL argument");
+    if (!b->nuc_done) return nb200_fail(ctx, NB200_ERR_STATE, "nb200_nuc_download: nb200_nuc_run has not been called on this batch");
+    const size_t tb = sizeof(double) * (size_t)b->total_len;
+    const int n = b->n_chunks;
+    NB_CHECK(d2h(ctx, b, o->nuc_signal, b->n_signal, tb));
+    NB_CHECK(d2h(ctx, b, o->background, b->n_bg, tb));
+    NB_CHECK(d2h(ctx, b, o->norm_signal, b->n_norm, tb));
+    NB_CHECK(d2h(ctx, b, o->smoothed, b->n_smooth, tb));
+    NB_CHECK(d2h(ctx, b, o->nuc_cov, b->n_nuc_cov, tb));
+    NB_CHECK(d2h(ctx, b, o->nfr_cov, b->n_nfr_cov, tb));
+    NB_CHECK(d2h(ctx, b, o->cand_count, b->n_cand_count, sizeof(int32_t) * n));
+    if (o->cand_pos) {
+        if (!o->cand_off) return nb200_fail(ctx, NB200_ERR_ARG, "nb200_nuc_download: cand_off is required with cand_pos");
+        for (int c = 0; c <= n; c++)
+            if (o->cand_off[c] != b->h_ncand_off[c])
+                return nb200_fail(ctx, NB200_ERR_CAPACITY, "nb200_nuc_download: cand_off must equal len/redundant_sep+2 capacities (chunk %d)", c);
+        const size_t nc = (size_t)b->h_ncand_off[n];
+        NB_CHECK(d2h(ctx, b, o->cand_pos, b->n_cand_pos, sizeof(int32_t) * nc));
+        NB_CHECK(d2h(ctx, b, o->cand_flag, b->n_cand_flag, sizeof(int32_t) * nc));
+        NB_CHECK(d2h(ctx, b, o->cand_z, b->n_cand_z, sizeof(double) * nc));
+        NB_CHECK(d2h(ctx, b, o->cand_lr, b->n_cand_lr, sizeof(double) * nc));
+        NB_CHECK(d2h(ctx, b, o->cand_norm_signal, b->n_cand_norm, sizeof(double) * nc));
+        NB_CHECK(d2h(ctx, b, o->cand_nuc_signal, b->n_cand_sig, sizeof(double) * nc));
+        NB_CHECK(d2h(ctx, b, o->cand_nuc_cov, b->n_cand_cov, sizeof(double) * nc));
+        NB_CHECK(d2h(ctx, b, o->cand_nfr_cov, b->n_cand_nfr, sizeof(double) * nc));
+        NB_CHECK(d2h(ctx, b, o->cand_smoothed, b->n_cand_smooth, sizeof(double) * nc));
+    }
+    return NB200_OK;
+}
+
+int64_t nb200_nuc_d2h_bytes(nb200_dbatch *b, const nb200_nuc_out *o)
+{
+    if (!b || !o) return 0;
+    const int64_t tb = 8 * b->total_len;
+    int64_t s = 0;
+    const void *tr[] = {o->nuc_signal, o->background, o->norm_signal, o->smoothed, o->nuc_cov, o->nfr_cov};
+    for (auto p : tr)
+        if (p) s += tb;
+    if (o->cand_count) s += 4LL * b->n_chunks;
+    if (o->cand_pos && !b->h_ncand_off.empty()) {
+        int64_t nc = b->h_ncand_off[b->n_chunks];
+        s += 4 * nc;
+        if (o->cand_flag) s += 4 * nc;
+        const void *cd[] = {o->cand_z, o->cand_lr, o->cand_norm_signal, o->cand_nuc_signal, o->cand_nuc_cov, o->cand_nfr_cov, o->cand_smoothed};
+        for (auto p : cd)
+            if (p) s += 8 * nc;
+    }
+    return s;
+}
+
+}  // extern "C"

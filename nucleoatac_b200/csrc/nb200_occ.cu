@@ -1,0 +1,583 @@
+// nb200_occ.cu -- OccChunk.process on the device (nucleoatac/Occupancy.py:195-253, run_occ.py:23-39).
+//
+// Stages (per batch, every chunk in parallel):
+//   k_occ_colsums  per-column sums  cn[c] = sum_i pn[i]*Bp[i,c],  cf[c] = sum_i pf[i]*Bp[i,c]   (bias only)
+//   k_occ_mle      one warp per window: sparse insert-size histogram of the window from the CSC fragment
+//                  matrix, window bias for the sizes that occur, 101-point alpha log-likelihood grid in
+//                  fp64, first-max argmax and the likelihood-ratio confidence bounds   (Occupancy.py:104-146)
+//   k_smooth_same  NaN-aware gaussian smoothing of the three tracks                     (Occupancy.py:147-153)
+//   k_occ_peaks    coverage, call_peaks + OccPeak filter + getNucDist, one block per chunk (Occupancy.py:221-240)
+#include "nb200_dev.cuh"
+
+// ---------------------------------------------------------------------------------------------
+#define OC_TILE 128
+__global__ void __launch_bounds__(OC_TILE) k_occ_colsums(const int32_t *__restrict__ start, const int64_t *__restrict__ out_off,
+                                                         const int64_t *__restrict__ bias_off,
+                                                         const int32_t *__restrict__ seq_start, int pwm_up,
+                                                         const double *__restrict__ E, const double *__restrict__ pn,
+                                                         const double *__restrict__ pf, int upper, int flank,
+                                                         double *__restrict__ cn, double *__restrict__ cf)
+{
+    extern __shared__ double sm_oc[];
+    double *s_pn = sm_oc, *s_pf = sm_oc + upper, *s_E = sm_oc + 2 * upper;  // s_E[OC_TILE + upper + 2]
+    const int c = blockIdx.y;
+    const int L = (int)(out_off[c + 1] - out_off[c]);
+    const int ncol = L + 2 * flank;
+    const int j0 = blockIdx.x * OC_TILE;
+    if (j0 >= ncol) return;
+    for (int i = threadIdx.x; i < upper; i += blockDim.x) {
+        s_pn[i] = pn[i];
+        s_pf[i] = pf[i];
+    }
+    const int half = upper / 2;
+    const int g0 = start[c] - flank + j0;                 // genomic coordinate of the tile's first column
+    const int64_t eb = bias_off[c] - (int64_t)(seq_start[c] + pwm_up);  // E index = eb + genomic
+    const int nE = OC_TILE + 2 * half + 2;
+    for (int i = threadIdx.x; i < nE; i += blockDim.x) s_E[i] = E[eb + g0 - half + i];
+    __syncthreads();
+    const int j = j0 + threadIdx.x;
+    if (j >= ncol) return;
+    const double *Ec = s_E + half + threadIdx.x;
+    double an = 0.0, af = 0.0;
+    for (int i = 0; i < upper; i++) {
+        double bp = bias_cell(Ec, i);
+        an += s_pn[i] * bp;
+        af += s_pf[i] * bp;
+    }
+    const int64_t o = out_off[c] + 2 * (int64_t)flank * c + j;
+    cn[o] = an;
+    cf[o] = af;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct OccMleArgs {
+    const int32_t *start;
+    const int64_t *out_off, *col_off, *frag_off, *bias_off;
+    const int32_t *seq_start;
+    const int32_t *col_ptr;
+    const int2 *ent;
+    const double *E, *cn, *cf, *pn, *pf, *alphas;
+    double *vals, *lower, *upper_b;
+    int pwm_up, upper, flank, step, halfstep, csc_pad, n_alpha, use_bias;
+    int pn_has_zero, pf_has_zero, both_zero;
+    double cutoff, sn_nobias, sf_nobias;
+};
+
+#define MLE_WARPS 4
+__global__ void __launch_bounds__(MLE_WARPS * 32) k_occ_mle(OccMleArgs a)
+{
+    extern __shared__ unsigned char sm_mle[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int upper = a.upper;
+    // per-warp carve-up: nucp f64[upper], nfrp f64[upper], hist i32[upper], sz i32[upper], cnt i32[upper]
+    unsigned char *base = sm_mle + (size_t)warp * upper * 28;
+    double *s_nucp = reinterpret_cast<double *>(base);
+    double *s_nfrp = s_nucp + upper;
+    int *s_hist = reinterpret_cast<int *>(s_nfrp + upper);
+    int *s_sz = s_hist + upper;
+    int *s_cnt = s_sz + upper;
+
+    const int c = blockIdx.y;
+    const int64_t oo = a.out_off[c];
+    const int L = (int)(a.out_off[c + 1] - oo);
+    const int nwin = (L - a.halfstep + a.step - 1) / a.step;  // windows at t = halfstep + k*step < L
+    const int wi = blockIdx.x * MLE_WARPS + warp;
+    if (wi >= nwin) return;
+    const int t = a.halfstep + wi * a.step;
+    const int left = t - a.halfstep, right = min(t + a.halfstep + 1, L);
+    const bool last = (wi == nwin - 1);
+    const int32_t *cp = a.col_ptr + a.col_off[c];
+    const int window = 2 * a.flank + 1;
+    const int e0 = cp[t - a.flank + a.csc_pad], e1 = cp[t + a.flank + 1 + a.csc_pad];
+    const int n = e1 - e0;
+    double occ = nb_nan(), lo = nb_nan(), hi = nb_nan();
+    if (n > 0) {  // Occupancy.py:141 `if sum(new_inserts)>0`
+        const int2 *en = a.ent + a.frag_off[c];
+        for (int i = lane; i < upper; i += 32) s_hist[i] = 0;
+        __syncwarp();
+        for (int e = e0 + lane; e < e1; e += 32) atomicAdd(&s_hist[en[e].y], 1);
+        __syncwarp();
+        int J = 0;
+        for (int b0 = 0; b0 < upper; b0 += 32) {
+            int i = b0 + lane;
+            int v = (i < upper) ? s_hist[i] : 0;
+            unsigned m = __ballot_sync(NB_FULL, v > 0);
+            if (v > 0) {
+                int p = J + __popc(m & ((1u << lane) - 1));
+                s_sz[p] = i;
+                s_cnt[p] = v;
+            }
+            J += __popc(m);
+        }
+        __syncwarp();
+        double SN, SF;
+        const int g0 = a.start[c] + t - a.flank;  // genomic coordinate of the first window column
+        const double *Eg = nullptr;
+        if (a.use_bias) {
+            const int64_t co = oo + 2 * (int64_t)a.flank * c + t;  // colsum index of column g0
+            double sn = 0.0, sf = 0.0;
+            for (int k = lane; k < window; k += 32) {
+                sn += a.cn[co + k];
+                sf += a.cf[co + k];
+            }
+            SN = warp_sum(sn);
+            SF = warp_sum(sf);
+            Eg = a.E + (a.bias_off[c] - (int64_t)(a.seq_start[c] + a.pwm_up)) + g0;
+        } else {
+            SN = a.sn_nobias;
+            SF = a.sf_nobias;
+        }
+        for (int j = 0; j < J; j++) {
+            const int sz = s_sz[j];
+            double bias;
+            if (a.use_bias) {
+                double acc = 0.0;
+                for (int k = lane; k < window; k += 32) acc += bias_cell(Eg + k, sz);
+                bias = warp_sum(acc);
+            } else
+                bias = (double)window;
+            if (lane == 0) {
+                s_nucp[j] = __dmul_rn(a.pn[sz], bias) / SN;  // nuc_probs * bias / sum, Occupancy.py:106-109
+                s_nfrp[j] = __dmul_rn(a.pf[sz], bias) / SF;
+            }
+        }
+        __syncwarp();
+        // log-likelihood grid; lane owns alphas lane, lane+32, ...
+        double ll[NB200_MAX_ALPHA / 32];
+#pragma unroll
+        for (int q = 0; q < NB200_MAX_ALPHA / 32; q++) {
+            const int ai = lane + 32 * q;
+            double acc = nb_ninf();
+            if (ai < a.n_alpha) {
+                const double al = a.alphas[ai];
+                const double om = 1.0 - al;
+                // 0 * log(0) = NaN -> -inf (Occupancy.py:112-114) for sizes with no reads but zero probability
+                bool dead = a.both_zero || (al == 0.0 && a.pf_has_zero) || (om == 0.0 && a.pn_has_zero);
+                if (!dead) {
+                    acc = 0.0;
+                    for (int j = 0; j < J; j++) {
+                        double v = __dadd_rn(__dmul_rn(al, s_nucp[j]), __dmul_rn(om, s_nfrp[j]));
+                        acc = __dadd_rn(acc, __dmul_rn(log(v), (double)s_cnt[j]));
+                    }
+                    if (acc != acc) acc = nb_ninf();
+                }
+            }
+            ll[q] = acc;
+        }
+        // first maximum (np.argmax)
+        double best = nb_ninf();
+        int besti = 1 << 30;
+#pragma unroll
+        for (int q = 0; q < NB200_MAX_ALPHA / 32; q++) {
+            const int ai = lane + 32 * q;
+            if (ai < a.n_alpha && (ll[q] > best || (ll[q] == best && ai < besti))) {
+                best = ll[q];
+                besti = ai;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ob = __shfl_xor_sync(NB_FULL, best, o);
+            int oi = __shfl_xor_sync(NB_FULL, besti, o);
+            if (ob > best || (ob == best && oi < besti)) {
+                best = ob;
+                besti = oi;
+            }
+        }
+        int okmin = 1 << 30, okmax = -1;
+#pragma unroll
+        for (int q = 0; q < NB200_MAX_ALPHA / 32; q++) {
+            const int ai = lane + 32 * q;
+            if (ai < a.n_alpha) {
+                double ratio = 2.0 * (best - ll[q]);  // Occupancy.py:116
+                if (ratio < a.cutoff) {
+                    okmin = min(okmin, ai);
+                    okmax = max(okmax, ai);
+                }
+            }
+        }
+        okmin = warp_min_i(okmin);
+        okmax = warp_max_i(okmax);
+        if (okmax >= 0 && besti < a.n_alpha) {
+            occ = a.alphas[besti];
+            lo = a.alphas[okmin];
+            hi = a.alphas[okmax];
+        }
+    }
+    for (int x = left + lane; x < right; x += 32) {
+        a.vals[oo + x] = occ;
+        a.lower[oo + x] = lo;
+        a.upper_b[oo + x] = hi;
+    }
+    if (last)  // positions past the last window stay NaN (np.ones(n)*nan, Occupancy.py:133-135)
+        for (int x = right + lane; x < L; x += 32) {
+            a.vals[oo + x] = nb_nan();
+            a.lower[oo + x] = nb_nan();
+            a.upper_b[oo + x] = nb_nan();
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct OccPeakArgs {
+    const int32_t *start;
+    const int64_t *out_off, *col_off, *frag_off, *peak_off;
+    const int32_t *col_ptr;
+    const int2 *ent;
+    const double *jitter;
+    double *svals;                   // NaN -> min in place, like utils.py:86-91
+    const double *slower, *supper;
+    double *cov;
+    int32_t *sc_pos;                 // scratch, packed like a track
+    double *sc_val;
+    unsigned char *sc_state;
+    int32_t *peak_count, *peak_pos;
+    double *peak_occ, *peak_lower, *peak_upper, *peak_reads, *nuc_dist;
+    int upper, flank, sep, csc_pad;
+    double min_occ;
+};
+
+#define PK_THREADS 512
+__global__ void __launch_bounds__(PK_THREADS) k_occ_peaks(OccPeakArgs a)
+{
+    extern __shared__ unsigned char sm_pk[];
+    double *s_nd = reinterpret_cast<double *>(sm_pk);          // [upper]
+    int *s_hist = reinterpret_cast<int *>(s_nd + a.upper);      // [upper]
+    __shared__ double red_d[32];
+    __shared__ int red_i[32];
+    __shared__ int s_base, s_flag;
+    const int c = blockIdx.x;
+    const int64_t oo = a.out_off[c];
+    const int L = (int)(a.out_off[c + 1] - oo);
+    const int32_t *cp = a.col_ptr + a.col_off[c];
+    double *sv = a.svals + oo;
+    double *cov = a.cov + oo;
+    int32_t *cpos = a.sc_pos + oo;
+    double *cval = a.sc_val + oo;
+    unsigned char *cst = a.sc_state + oo;
+    const int tid = threadIdx.x;
+    // coverage: flat window over fragment centres = difference of the CSC prefix (tracks.py:209-222)
+    for (int x = tid; x < L; x += blockDim.x)
+        cov[x] = (double)(cp[x + a.flank + 1 + a.csc_pad] - cp[x - a.flank + a.csc_pad]);
+    // NaN -> min (utils.py:86-91)
+    double mn = CUDART_INF;
+    int nnan = 0;
+    for (int x = tid; x < L; x += blockDim.x) {
+        double v = sv[x];
+        if (v != v) nnan++;
+        else mn = fmin(mn, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(NB_FULL, mn, o));
+        nnan += __shfl_xor_sync(NB_FULL, nnan, o);
+    }
+    if ((tid & 31) == 0) {
+        red_d[tid >> 5] = mn;
+        red_i[tid >> 5] = nnan;
+    }
+    __syncthreads();
+    mn = CUDART_INF;
+    nnan = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
+        mn = fmin(mn, red_d[w]);
+        nnan += red_i[w];
+    }
+    __syncthreads();
+    for (int i = tid; i < a.upper; i += blockDim.x) s_nd[i] = 0.0;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    int m = 0;
+    if (nnan < L) {
+        if (nnan > 0)
+            for (int x = tid; x < L; x += blockDim.x)
+                if (sv[x] != sv[x]) sv[x] = mn;
+        __syncthreads();
+        // strict local maxima of sig*(1+jitter), order 1 (argrelmax, clip mode), utils.py:94-100
+        const int boundary = a.sep / 2;
+        const int lo = max(1, boundary), hi = min(L - 1, L - boundary);
+        for (int x0 = 0; x0 < L; x0 += blockDim.x) {
+            const int x = x0 + tid;
+            int flag = 0;
+            double v = 0.0;
+            if (x >= lo && x < hi) {
+                v = sv[x];
+                double j0 = v * (1.0 + a.jitter[x]);
+                double jl = sv[x - 1] * (1.0 + a.jitter[x - 1]);
+                double jr = sv[x + 1] * (1.0 + a.jitter[x + 1]);
+                flag = (j0 > jl) && (j0 > jr) && (v >= a.min_occ);
+            }
+            int slot = block_compact_slot(flag, &s_base, red_i);
+            if (flag) {
+                cpos[slot] = x;
+                cval[slot] = v;
+            }
+        }
+        __syncthreads();
+        m = s_base;
+        block_nms(cpos, cval, cst, m, a.sep, &s_flag);
+    }
+    __syncthreads();
+    // OccPeak filter (Occupancy.py:228-231) and ordered output
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    const int64_t po = a.peak_off[c];
+    const int cap = (int)(a.peak_off[c + 1] - po);
+    for (int j0 = 0; j0 < m; j0 += blockDim.x) {
+        const int j = j0 + tid;
+        int flag = 0, p = 0;
+        if (j < m && cst[j] == 1) {
+            p = cpos[j];
+            flag = (a.slower[oo + p] > a.min_occ) && (cov[p] > 0);
+        }
+        int slot = block_compact_slot(flag, &s_base, red_i);
+        if (flag && slot < cap) {
+            a.peak_pos[po + slot] = a.start[c] + p;
+            a.peak_occ[po + slot] = sv[p];
+            a.peak_lower[po + slot] = a.slower[oo + p];
+            a.peak_upper[po + slot] = a.supper[oo + p];
+            a.peak_reads[po + slot] = cov[p];
+        }
+    }
+    __syncthreads();
+    const int npk = min(s_base, cap);
+    if (tid == 0) a.peak_count[c] = (s_base <= cap) ? s_base : -s_base;  // negative: capacity exceeded
+    // getNucDist, Occupancy.py:232-240: sum over peaks of the window's insert-size histogram / its total
+    const int2 *en = a.ent + a.frag_off[c];
+    for (int k = 0; k < npk; k++) {
+        const int p = a.peak_pos[po + k] - a.start[c];
+        const int e0 = cp[p - a.flank + a.csc_pad], e1 = cp[p + a.flank + 1 + a.csc_pad];
+        for (int i = tid; i < a.upper; i += blockDim.x) s_hist[i] = 0;
+        __syncthreads();
+        for (int e = e0 + tid; e < e1; e += blockDim.x) atomicAdd(&s_hist[en[e].y], 1);
+        __syncthreads();
+        const double tot = (double)(e1 - e0);
+        for (int i = tid; i < a.upper; i += blockDim.x) s_nd[i] += (double)s_hist[i] / tot;
+        __syncthreads();
+    }
+    for (int i = tid; i < a.upper; i += blockDim.x) a.nuc_dist[(int64_t)c * a.upper + i] = s_nd[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int nb200_occ_run(nb200_ctx *ctx, nb200_dbatch *b)
+{
+    if (!ctx || !b) return nb200_fail(ctx, NB200_ERR_ARG, "nb200_occ_run: NULL argument");
+    if (!ctx->occ_configured) return nb200_fail(ctx, NB200_ERR_STATE, "nb200_occ_configure has not been called");
+    RunConst &r = ctx->rc;
+    const nb200_occ_params &p = ctx->occ;
+    if (!r.have_occ_model || r.occ_upper != p.upper)
+        return nb200_fail(ctx, NB200_ERR_STATE, "nb200_set_occ_model missing or its size range differs from --upper");
+    if (p.upper > NB200_MAX_UPPER) return nb200_fail(ctx, NB200_ERR_ARG, "upper > %d unsupported", NB200_MAX_UPPER);
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int n = b->n_chunks;
+    const int window = 2 * p.flank + 1;
+    const int halfstep = (p.step - 1) / 2;
+    if (b->min_len < p.smooth_len)
+        return nb200_fail(ctx, NB200_ERR_ARG, "a chunk is shorter (%d) than the smoothing window (%d)", b->min_len, p.smooth_len);
+    if (r.n_jitter < b->max_len)
+        return nb200_fail(ctx, NB200_ERR_STATE, "nb200_set_jitter: need >= %d values (longest chunk), have %lld", b->max_len,
+                          (long long)r.n_jitter);
+    int pad = p.flank;
+    if (ctx->nuc_configured && r.have_vmat && r.v_upper == p.upper) {  // share one CSC with the nuc path
+        int npad = r.v_cols > r.v_upper / 2 + 1 ? r.v_cols : r.v_upper / 2 + 1;
+        if (npad > pad) pad = npad;
+    }
+    int lower_split = (ctx->nuc_configured && r.have_vmat && r.v_upper == p.upper && r.v_lower > 0) ? r.v_lower : 0;
+    NB_CHECK(nb200_prep_csc(ctx, b, pad, p.upper, p.atac, lower_split));
+    if (p.use_bias) {
+        NB_CHECK(nb200_prep_bias(ctx, b));
+        for (int c = 0; c < n; c++) {  // Occupancy.py:131-132 / bias.py:93-107 flank checks
+            int64_t b0 = (int64_t)b->h_seq_start[c] + r.pwm_up;
+            int64_t b1 = b0 + (b->h_seq_off[c + 1] - b->h_seq_off[c]) - (r.pwm_width - 1);
+            if (b0 > (int64_t)b->h_start[c] - p.flank - p.upper / 2 || b1 < (int64_t)b->h_end[c] + p.flank + p.upper / 2 + 1)
+                return nb200_fail(ctx, NB200_ERR_FLANK,
+                                  "Insufficient flanking region: chunk %d needs sequence over [%lld, %lld)", c,
+                                  (long long)b->h_start[c] - p.flank - p.upper / 2 - r.pwm_up,
+                                  (long long)b->h_end[c] + p.flank + p.upper / 2 + 1 + r.pwm_down);
+        }
+    }
+    const size_t tl = (size_t)b->total_len;
+    DevBuf *tracks[] = {&b->o_vals, &b->o_lower, &b->o_upper, &b->o_svals, &b->o_slower, &b->o_supper, &b->o_cov, &b->sc_f64};
+    for (auto t : tracks) NB_CUDA(ctx, t->reserve(sizeof(double) * tl));
+    NB_CUDA(ctx, b->sc_i32.reserve(sizeof(int32_t) * tl));
+    NB_CUDA(ctx, b->sc_u8.reserve(tl));
+    NB_CUDA(ctx, b->o_nuc_dist.reserve(sizeof(double) * (size_t)n * p.upper));
+    // peak capacities: kept peaks are >= sep apart
+    b->h_opeak_off.assign(n + 1, 0);
+    for (int c = 0; c < n; c++) b->h_opeak_off[c + 1] = b->h_opeak_off[c] + (b->h_end[c] - b->h_start[c]) / p.sep + 2;
+    const size_t np = (size_t)b->h_opeak_off[n];
+    NB_CUDA(ctx, b->o_peak_off.reserve(sizeof(int64_t) * (n + 1)));
+    NB_CUDA(ctx, cudaMemcpyAsync(b->o_peak_off.p, b->h_opeak_off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, b->stream));
+    NB_CUDA(ctx, b->o_peak_count.reserve(sizeof(int32_t) * n));
+    NB_CUDA(ctx, b->o_peak_pos.reserve(sizeof(int32_t) * np));
+    DevBuf *pk[] = {&b->o_peak_occ, &b->o_peak_lower, &b->o_peak_upper, &b->o_peak_reads};
+    for (auto t : pk) NB_CUDA(ctx, t->reserve(sizeof(double) * np));
+
+    if (p.use_bias) {
+        const size_t ncs = tl + 2 * (size_t)p.flank * n;
+        NB_CUDA(ctx, b->o_cn.reserve(sizeof(double) * ncs));
+        NB_CUDA(ctx, b->o_cf.reserve(sizeof(double) * ncs));
+        size_t smem = sizeof(double) * (3 * (size_t)p.upper + OC_TILE + 8);
+        if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_occ_colsums, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ProfScope ps(ctx, b->stream, "k_occ_colsums");
+        dim3 grid((unsigned)div_up64(b->max_len + 2 * p.flank, OC_TILE), n);
+        k_occ_colsums<<<grid, OC_TILE, smem, b->stream>>>(b->d_start.as<int32_t>(), b->d_out_off.as<int64_t>(),
+                                                          b->d_bias_off.as<int64_t>(), b->d_seq_start.as<int32_t>(), r.pwm_up,
+                                                          b->d_E.as<double>(), r.nuc_probs.as<double>(), r.nfr_probs.as<double>(),
+                                                          p.upper, p.flank, b->o_cn.as<double>(), b->o_cf.as<double>());
+        NB_LAUNCH_CHECK(ctx);
+    }
+    {
+        OccMleArgs a;
+        a.start = b->d_start.as<int32_t>();
+        a.out_off = b->d_out_off.as<int64_t>();
+        a.col_off = b->d_col_off.as<int64_t>();
+        a.frag_off = b->d_frag_off.as<int64_t>();
+        a.bias_off = b->d_bias_off.as<int64_t>();
+        a.seq_start = b->d_seq_start.as<int32_t>();
+        a.col_ptr = b->d_col_ptr.as<int32_t>();
+        a.ent = b->d_ent.as<int2>();
+        a.E = b->d_E.as<double>();
+        a.cn = b->o_cn.as<double>();
+        a.cf = b->o_cf.as<double>();
+        a.pn = r.nuc_probs.as<double>();
+        a.pf = r.nfr_probs.as<double>();
+        a.alphas = r.alphas.as<double>();
+        a.vals = b->o_vals.as<double>();
+        a.lower = b->o_lower.as<double>();
+        a.upper_b = b->o_upper.as<double>();
+        a.pwm_up = r.pwm_up;
+        a.upper = p.upper;
+        a.flank = p.flank;
+        a.step = p.step;
+        a.halfstep = halfstep;
+        a.csc_pad = b->csc_pad;
+        a.n_alpha = r.n_alpha;
+        a.use_bias = p.use_bias;
+        a.pn_has_zero = r.pn_has_zero;
+        a.pf_has_zero = r.pf_has_zero;
+        a.both_zero = r.both_zero;
+        a.cutoff = r.cutoff;
+        a.sn_nobias = r.pn_sum * window;
+        a.sf_nobias = r.pf_sum * window;
+        size_t smem = (size_t)MLE_WARPS * p.upper * 28;
+        if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_occ_mle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int max_win = (b->max_len - halfstep + p.step - 1) / p.step;
+        if (max_win < 1) max_win = 1;
+        ProfScope ps(ctx, b->stream, "k_occ_mle");
+        dim3 grid((unsigned)div_up64(max_win, MLE_WARPS), n);
+        k_occ_mle<<<grid, MLE_WARPS * 32, smem, b->stream>>>(a);
+        NB_LAUNCH_CHECK(ctx);
+    }
+    {
+        SmoothTracks tr;
+        tr.in[0] = b->o_vals.as<double>();
+        tr.in[1] = b->o_lower.as<double>();
+        tr.in[2] = b->o_upper.as<double>();
+        tr.out[0] = b->o_svals.as<double>();
+        tr.out[1] = b->o_slower.as<double>();
+        tr.out[2] = b->o_supper.as<double>();
+        size_t smem = sizeof(double) * (SM_TILE + 2 * (size_t)p.smooth_len);
+        if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_smooth_same, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ProfScope ps(ctx, b->stream, "k_smooth_same");
+        dim3 grid((unsigned)div_up64(b->max_len, SM_TILE), n, 3);
+        k_smooth_same<<<grid, SM_TILE, smem, b->stream>>>(tr, b->d_out_off.as<int64_t>(), r.occ_win.as<double>(), p.smooth_len, 0);
+        NB_LAUNCH_CHECK(ctx);
+    }
+    {
+        OccPeakArgs a;
+        a.start = b->d_start.as<int32_t>();
+        a.out_off = b->d_out_off.as<int64_t>();
+        a.col_off = b->d_col_off.as<int64_t>();
+        a.frag_off = b->d_frag_off.as<int64_t>();
+        a.peak_off = b->o_peak_off.as<int64_t>();
+        a.col_ptr = b->d_col_ptr.as<int32_t>();
+        a.ent = b->d_ent.as<int2>();
+        a.jitter = r.jitter.as<double>();
+        a.svals = b->o_svals.as<double>();
+        a.slower = b->o_slower.as<double>();
+        a.supper = b->o_supper.as<double>();
+        a.cov = b->o_cov.as<double>();
+        a.sc_pos = b->sc_i32.as<int32_t>();
+        a.sc_val = b->sc_f64.as<double>();
+        a.sc_state = b->sc_u8.as<unsigned char>();
+        a.peak_count = b->o_peak_count.as<int32_t>();
+        a.peak_pos = b->o_peak_pos.as<int32_t>();
+        a.peak_occ = b->o_peak_occ.as<double>();
+        a.peak_lower = b->o_peak_lower.as<double>();
+        a.peak_upper = b->o_peak_upper.as<double>();
+        a.peak_reads = b->o_peak_reads.as<double>();
+        a.nuc_dist = b->o_nuc_dist.as<double>();
+        a.upper = p.upper;
+        a.flank = p.flank;
+        a.sep = p.sep;
+        a.csc_pad = b->csc_pad;
+        a.min_occ = p.min_occ;
+        size_t smem = (size_t)p.upper * 12;
+        ProfScope ps(ctx, b->stream, "k_occ_peaks");
+        k_occ_peaks<<<n, PK_THREADS, smem, b->stream>>>(a);
+        NB_LAUNCH_CHECK(ctx);
+    }
+    b->occ_upper = p.upper;
+    b->occ_done = true;
+    return NB200_OK;
+}
+
+static int d2h(nb200_ctx *ctx, nb200_dbatch *b, void *dst, const DevBuf &src, size_t bytes)
+{
+    if (!dst || !bytes) return NB200_OK;
+    NB_CUDA(ctx, cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, b->stream));
+    return NB200_OK;
+}
+
+int nb200_occ_download(nb200_ctx *ctx, nb200_dbatch *b, const nb200_occ_out *o)
+{
+    if (!ctx || !b || !o) return nb200_fail(ctx, NB200_ERR_ARG, "nb200_occ_download: NULL argument");
+    if (!b->occ_done) return nb200_fail(ctx, NB200_ERR_STATE, "nb200_occ_download: nb200_occ_run has not been called on this batch");
+    const size_t tb = sizeof(double) * (size_t)b->total_len;
+    const int n = b->n_chunks;
+    NB_CHECK(d2h(ctx, b, o->smoothed_vals, b->o_svals, tb));
+    NB_CHECK(d2h(ctx, b, o->smoothed_lower, b->o_slower, tb));
+    NB_CHECK(d2h(ctx, b, o->smoothed_upper, b->o_supper, tb));
+    NB_CHECK(d2h(ctx, b, o->vals, b->o_vals, tb));
+    NB_CHECK(d2h(ctx, b, o->lower_bound, b->o_lower, tb));
+    NB_CHECK(d2h(ctx, b, o->upper_bound, b->o_upper, tb));
+    NB_CHECK(d2h(ctx, b, o->cov, b->o_cov, tb));
+    NB_CHECK(d2h(ctx, b, o->nuc_dist, b->o_nuc_dist, sizeof(double) * (size_t)n * ctx->occ.upper));
+    NB_CHECK(d2h(ctx, b, o->peak_count, b->o_peak_count, sizeof(int32_t) * n));
+    if (o->peak_pos) {
+        if (!o->peak_off) return nb200_fail(ctx, NB200_ERR_ARG, "nb200_occ_download: peak_off is required with peak_pos");
+        for (int c = 0; c <= n; c++)
+            if (o->peak_off[c] != b->h_opeak_off[c])
+                return nb200_fail(ctx, NB200_ERR_CAPACITY, "nb200_occ_download: peak_off must equal len/sep+2 capacities (chunk %d)", c);
+        const size_t np = (size_t)b->h_opeak_off[n];
+        NB_CHECK(d2h(ctx, b, o->peak_pos, b->o_peak_pos, sizeof(int32_t) * np));
+        NB_CHECK(d2h(ctx, b, o->peak_occ, b->o_peak_occ, sizeof(double) * np));
+        NB_CHECK(d2h(ctx, b, o->peak_lower, b->o_peak_lower, sizeof(double) * np));
+        NB_CHECK(d2h(ctx, b, o->peak_upper, b->o_peak_upper, sizeof(double) * np));
+        NB_CHECK(d2h(ctx, b, o->peak_reads, b->o_peak_reads, sizeof(double) * np));
+    }
+    return NB200_OK;
+}
+
+int64_t nb200_occ_d2h_bytes(nb200_dbatch *b, const nb200_occ_out *o)
+{
+    if (!b || !o) return 0;
+    const int64_t tb = 8 * b->total_len;
+    int64_t s = 0;
+    const void *tr[] = {o->smoothed_vals, o->smoothed_lower, o->smoothed_upper, o->vals, o->lower_bound, o->upper_bound, o->cov};
+    for (auto p : tr)
+        if (p) s += tb;
+    if (o->nuc_dist) s += 8LL * b->n_chunks * b->occ_upper;
+    if (o->peak_count) s += 4LL * b->n_chunks;
+    if (o->peak_pos && !b->h_opeak_off.empty()) {
+        int64_t np = b->h_opeak_off[b->n_chunks];
+        s += 4 * np;
+        const void *pk[] = {o->peak_occ, o->peak_lower, o->peak_upper, o->peak_reads};
+        for (auto p : pk)
+            if (p) s += 8 * np;
+    }
+    return s;
+}
+
+}  // extern "C"
