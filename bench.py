@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- bp scored/sec (occ+nuc) on synthetic 10 kb chunks with a 251x251 VMat (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+A step = one pass of the whole per-chunk hot path (OccChunk.process + NucChunk.process on the
+device) over one batch of B synthetic chunks per GPU.  With the defaults (B=2000, K=25) one run
+covers BASELINE.json configs[1] (50 000 x 10 kb chunks) on one B200; with N GPUs every rank takes the
+chunks k = r mod N of the round-robin shard (weak scaling, no data-path collective; NCCL only for
+the end-of-run nuc_dist / fragment-size reductions).
+
+Printed JSON line (rank 0):
+  value   whole-job bp/s with the step's inputs already resident in HBM (CUDA-event time of the
+          compute of each step, max over ranks)
+  e2e     the same metric through the public API with HOST buffers: pinned H2D of reads+sequence,
+          compute, D2H of every track and call table, double-buffered on two streams, wall clock
+          bracketed by device synchronisation
+  roofline / cpu_baseline / clocks / gpu_launches as the task contract asks.
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/, multiprocessing
+like run_occ.py:101-119) on the same workload; it is the only mode that executes oracle/ for timing.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "bp scored/sec (occ+nuc), synthetic 10 kb chunks, 251x251 VMat"
+R_V, W_V = 251, 251
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"], source="measured")
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ----------------------------------------------------------------------------- batch generation
+def _gen(args):
+    from nucleoatac_b200 import synth
+    step, rank, world, B = args
+    ks = [(step * B + j) * world + rank for j in range(B)]
+    pb = synth.PackedBatch.from_chunks([synth.make_chunk(k) for k in ks])
+    return pb
+
+
+def generate_batches(n_steps, rank, world, B):
+    import multiprocessing as mp
+    tasks = [(s, rank, world, B) for s in range(n_steps)]
+    nproc = max(1, min(len(tasks), (os.cpu_count() or 2) // max(1, min(world, 8))))
+    if nproc == 1:
+        return [_gen(t) for t in tasks]
+    with mp.get_context("fork").Pool(nproc) as pool:
+        return pool.map(_gen, tasks)
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def _cpu_chunk(k):
+    """One chunk through the CPU restatement of the reference (occ + nuc), reference algorithms:
+    scipy correlate (auto -> fft), O(n^2) calculateCov loop, per-window occupancy grid."""
+    from nucleoatac_b200 import synth
+    from oracle import refalgo as ra, refnuc, refocc
+    wl = _cpu_chunk.wl
+    s, e, pos, tlen, seq, s0 = synth.make_chunk(k)
+    sq = bytes(seq).decode()
+    op = refocc.OccParams(wl.nuc_probs, wl.nfr_probs, upper=wl.upper)
+    npar = refnuc.NucParams((wl.vmat, wl.v_lower, wl.v_upper), wl.fragmentsizes, sd=10)
+    span = refocc.occ_bias_track_span(s, e, op)
+    bt = ra.log_bias_track(sq[span[0] - 10 - s0:span[1] + 10 - s0], wl.pwm, wl.nucleotides)
+    refocc.process_occ_chunk(pos, tlen, s, e, op, bias_track=bt, bias_track_start=span[0])
+    _, _, span = refnuc.nuc_geometry(s, e, npar)
+    bt = ra.log_bias_track(sq[span[0] - 10 - s0:span[1] + 10 - s0], wl.pwm, wl.nucleotides)
+    r = refnuc.process_nuc_chunk(pos, tlen, s, e, npar, bias_track=bt, bias_track_start=span[0], fit=False, closed_cov=False)
+    return e - s, len(r["nuc_collection"])
+
+
+def _cpu_init():
+    from nucleoatac_b200 import synth
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    _cpu_chunk.wl = synth.Workload(R_V, W_V)
+
+
+def cpu_pool(cores):
+    import multiprocessing as mp
+    nworkers = max(1, cores - 1)  # run_occ.py:102 Pool(processes=max(1, cores-1))
+    return mp.get_context("fork").Pool(nworkers, initializer=_cpu_init), nworkers
+
+
+def cpu_baseline_sample(chunk_ids):
+    cores = os.cpu_count() or 1
+    pool, nworkers = cpu_pool(cores)
+    with pool:
+        pool.map(_cpu_chunk, range(10 ** 6, 10 ** 6 + nworkers))  # warm the workers (imports, fft plans)
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_chunk, chunk_ids)
+        dt = time.perf_counter() - t0
+    bp = sum(r[0] for r in res)
+    return dict(value=bp / dt, unit="bp/s", cores=nworkers, kind="port",
+                sample="chunks %d-%d of the same synthetic workload (occ+nuc, fft correlate, O(n^2) calculateCov), "
+                       "Pool(%d) on %d visible cores, %.1f s" % (chunk_ids[0], chunk_ids[-1], nworkers, cores, dt))
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    pool, nworkers = cpu_pool(cores)
+    per_step = nworkers
+    with pool:
+        k = 0
+        for _ in range(args.warmup):
+            pool.map(_cpu_chunk, range(k, k + per_step))
+            k += per_step
+        t0 = time.perf_counter()
+        bp = 0
+        for _ in range(args.steps):
+            res = pool.map(_cpu_chunk, range(k, k + per_step))
+            bp += sum(r[0] for r in res)
+            k += per_step
+        dt = time.perf_counter() - t0
+    val = bp / dt
+    line = dict(impl="reference", metric=METRIC, value=val, unit="bp/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=dt / args.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                data="synthetic",
+                config=dict(workload="synthetic 10 kb chunks, 251x251 VMat, occ+nuc; CPU arm: %d chunks per step" % per_step,
+                            chunk_len=10000, vmat="251x251", chunks_per_step=per_step),
+                cpu_baseline=dict(value=val, unit="bp/s", cores=nworkers, kind="port",
+                                  sample="%d steps x %d chunks through oracle/ (CPU restatement of the reference: fft correlate, "
+                                         "O(n^2) calculateCov), Pool(%d) of %d visible cores" % (args.steps, per_step, nworkers, cores)),
+                e2e=dict(value=val, unit="bp/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args, rank, world, local_rank):
+    from nucleoatac_b200 import synth
+    from nucleoatac_b200.engine import Engine
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    B, K, Wm = args.batch, args.steps, args.warmup
+    eng = Engine(local_rank)
+    wl = synth.Workload(R_V, W_V)
+    wl.configure(eng, use_bias=not args.no_bias, xcor_mode=args.xcor_mode)
+    t_gen = time.perf_counter()
+    batches = generate_batches(K + Wm, rank, world, B)
+    t_gen = time.perf_counter() - t_gen
+    # pinned staging of every step's inputs (H2D source) and two pinned result sets (D2H target)
+    pinned = []
+    for pb in batches:
+        q = synth.PackedBatch.__new__(synth.PackedBatch)
+        q.__dict__.update(pb.__dict__)
+        for name in ("starts", "ends", "frag_off", "frag_pos", "frag_tlen", "seq_off", "seq_start", "seq"):
+            a = getattr(pb, name)
+            if a is not None:
+                p = eng.pinned(a.shape, a.dtype)
+                p[...] = a
+                setattr(q, name, p)
+        pinned.append(q)
+    batches = pinned
+    outs = [(eng.occ_alloc(batches[0], raw=False, alloc=eng.pinned), eng.nuc_alloc(batches[0], cov=False, alloc=eng.pinned))
+            for _ in range(2)]
+    bp_step = batches[0].total_len
+    hs = [None, None]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    # ---- pass A: device-resident compute, CUDA-event timed per step
+    def compute_step(i, timed):
+        pb = batches[i]
+        hs[0] = eng.upload(pb, hs[0])
+        eng.sync(hs[0])
+        eng.flush_l2(hs[0])
+        eng.sync(hs[0])
+        eng.timer_start(hs[0])
+        eng.nuc_run(hs[0])
+        eng.occ_run(hs[0])
+        eng.timer_stop(hs[0])
+        return eng.timer_ms(hs[0])
+
+    for i in range(Wm):
+        compute_step(i, False)
+    eng.profile_reset()
+    eng.profile(True)
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    t_wall = time.perf_counter()
+    dev_ms = [compute_step(Wm + i, True) for i in range(K)]
+    eng.sync(hs[0])
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    prof = eng.profile_report()
+    eng.profile(False)
+    total_ms = float(np.sum(dev_ms))
+
+    # ---- pass B: end to end with host buffers, double buffered on two streams
+    def e2e_loop(idx):
+        h2d = d2h = 0
+        for n, i in enumerate(idx):
+            s = n & 1
+            if hs[s] is not None and n >= 2:
+                eng.sync(hs[s])  # results of step n-2 are on the host; its buffers can be recycled
+            hs[s] = eng.upload(batches[i], hs[s])
+            eng.nuc_run(hs[s])
+            eng.occ_run(hs[s])
+            d2h = eng.occ_download(hs[s], outs[s][0]) + eng.nuc_download(hs[s], outs[s][1])
+            h2d = eng.h2d_bytes(hs[s])
+        for s in (0, 1):
+            if hs[s] is not None:
+                eng.sync(hs[s])
+        return h2d, d2h
+
+    e2e_loop(range(Wm))
+    barrier()
+    t0 = time.perf_counter()
+    h2d_b, d2h_b = e2e_loop(range(Wm, Wm + K))
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clk = clocks.stop()
+
+    # ---- end-of-run reductions (the only collectives on the path): nuc_dist and fragment sizes
+    nd = outs[(K - 1) & 1][0]["nuc_dist"].sum(axis=0)
+    fs = eng.fragment_sizes(batches[-1].starts, batches[-1].ends, batches[-1].frag_off, batches[-1].frag_pos,
+                            batches[-1].frag_tlen, 0, wl.upper)
+    if dist is not None:
+        import torch
+        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s = float(t[0]), float(t[1])
+        ndt = torch.from_numpy(nd).cuda()
+        fst = torch.from_numpy(fs).cuda()
+        dist.all_reduce(ndt)
+        dist.all_reduce(fst)
+        nd, fs = ndt.cpu().numpy(), fst.cpu().numpy()
+
+    if rank == 0:
+        peaks = load_peaks()
+        launches = int(sum(v[0] for v in prof.values()))
+        top = max(prof.items(), key=lambda kv: kv[1][1]) if prof else ("none", (0, 0.0))
+        kname, (kcount, kms) = top
+        # algorithmic work of the dominant kernel: the dense background cross-correlation, 2*R*W flop per bp
+        flop_per_launch = 2.0 * R_V * W_V * bp_step
+        k_avg_s = (kms / max(kcount, 1)) * 1e-3
+        achieved = flop_per_launch / k_avg_s / 1e12 if k_avg_s > 0 else 0.0
+        roofline = dict(bound="tensor", kernel=kname, achieved=achieved, peak=peaks["tf_sustained"], unit="TFLOP/s",
+                        frac=achieved / peaks["tf_sustained"], traffic=None, peak_source=peaks["source"] + " bf16 sustained",
+                        kernel_ms_per_launch=kms / max(kcount, 1), kernel_share_of_step=kms / total_ms if total_ms else None,
+                        algorithmic_flop_per_bp=2.0 * R_V * W_V,
+                        per_kernel_ms={k: round(v[1] / K, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])})
+        cpu = None if args.no_cpu_baseline else cpu_baseline_sample(list(range(0, max(4, (os.cpu_count() or 2) - 1))))
+        value = bp_step * K * world / (total_ms * 1e-3)
+        line = dict(metric=METRIC, value=value, unit="bp/s", n_gpus=world, steps=K, warmup=Wm, ms_per_step=total_ms / K,
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                    config=dict(workload="synthetic 10 kb chunks (BASELINE configs[1]: 50k x 10 kb at B=2000,K=25), 251x251 VMat, "
+                                         "occ+nuc with Tn5 bias" + (" OFF" if args.no_bias else ""),
+                                chunks_per_step_per_gpu=B, chunk_len=10000, vmat="251x251", fragments_per_bp=0.25,
+                                l2="flushed before every timed step (256 MiB write) and working set >> L2",
+                                xcor_mode=args.xcor_mode, shard="round-robin chunk k -> rank k mod N"),
+                    roofline=roofline, cpu_baseline=cpu,
+                    e2e=dict(value=bp_step * K * world / e2e_s, unit="bp/s", h2d_bytes_per_step=int(h2d_b), d2h_bytes_per_step=int(d2h_b),
+                             ms_per_step=e2e_s / K * 1e3),
+                    gpu_launches=launches, clocks=clk, wall_s_device_pass=t_wall, gen_s=t_gen,
+                    checks=dict(nuc_dist_sum=float(nd.sum()), fragment_size_count=int(fs.sum())))
+        print(json.dumps(line), flush=True)
+    for h in hs:
+        if h is not None:
+            eng.free_batch(h)
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=25)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=2000, help="chunks per step per GPU")
+    ap.add_argument("--no-bias", action="store_true")
+    ap.add_argument("--xcor-mode", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -70,12 +70,13 @@ __global__ void __launch_bounds__(MLE_WARPS * 32) k_occ_mle(OccMleArgs a)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int upper = a.upper;
     // per-warp carve-up: nucp f64[upper], nfrp f64[upper], hist i32[upper], sz i32[upper], cnt i32[upper]
-    unsigned char *base = sm_mle + (size_t)warp * upper * 28;
+    const int up2 = (upper + 1) & ~1;  // keep every per-warp slice 8-byte aligned
+    unsigned char *base = sm_mle + (size_t)warp * up2 * 28;
     double *s_nucp = reinterpret_cast<double *>(base);
-    double *s_nfrp = s_nucp + upper;
-    int *s_hist = reinterpret_cast<int *>(s_nfrp + upper);
-    int *s_sz = s_hist + upper;
-    int *s_cnt = s_sz + upper;
+    double *s_nfrp = s_nucp + up2;
+    int *s_hist = reinterpret_cast<int *>(s_nfrp + up2);
+    int *s_sz = s_hist + up2;
+    int *s_cnt = s_sz + up2;
 
     const int c = blockIdx.y;
     const int64_t oo = a.out_off[c];
@@ -460,7 +461,7 @@ int nb200_occ_run(nb200_ctx *ctx, nb200_dbatch *b)
         a.cutoff = r.cutoff;
         a.sn_nobias = r.pn_sum * window;
         a.sf_nobias = r.pf_sum * window;
-        size_t smem = (size_t)MLE_WARPS * p.upper * 28;
+        size_t smem = (size_t)MLE_WARPS * ((p.upper + 1) & ~1) * 28;
         if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_occ_mle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int max_win = (b->max_len - halfstep + p.step - 1) / p.step;
         if (max_win < 1) max_win = 1;

@@ -189,7 +189,7 @@ def test_synthetic_251(eng):
     from nucleoatac_b200 import synth
     wl = synth.Workload(251, 251)
     wl.configure(eng, use_bias=True, xcor_mode=1)
-    ks = [0, 3, 5]  # chunk 5... includes a planted array for this seed? asserted below via calls
+    ks = [2, 0, 5]  # chunk 2 carries a planted nucleosome array (calls asserted below)
     chunks = [synth.make_chunk(k) for k in ks]
     from nucleoatac_b200.engine import PackedBatch
     pb = PackedBatch.from_chunks(chunks)
@@ -280,7 +280,7 @@ def test_kats_through_cabi(eng, example, golden):
         eng.multinomial_cov(prob.flatten(), V.flatten()[:-1], 35)
     # bias track (bias.py:85-92) and smooth (utils.py:23-52)
     eng.set_pwm(example.pwm, example.pwm_up, example.pwm_down, example.nucleotides)
-    seq = example.seq_slice(0, *[example.sequence(0)[1], example.sequence(0)[1] + 3000])
+    seq = example.seq_slice(0, *[example.sequence(0)[1], example.sequence(0)[1] + 1500])
     close(ra.log_bias_track(seq, example.pwm, example.nucleotides), eng.bias_track(seq), 1e-12, atol=1e-13)
     x = rng.uniform(0, 1, 500)
     x[100:130] = np.nan
