@@ -40,9 +40,10 @@ def test_every_declared_symbol_is_exported(lib):
 def test_struct_layouts_match_header():
     from nucleoatac_b200 import _lib
     h = open(os.path.join(ROOT, "include", "nucleo_b200.h")).read()
+    h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
     for cname, cls in (("nb200_occ_params", _lib.OccParams), ("nb200_nuc_params", _lib.NucParams), ("nb200_batch", _lib.Batch),
                        ("nb200_occ_out", _lib.OccOut), ("nb200_nuc_out", _lib.NucOut)):
-        body = re.search(r"typedef struct \{([^{}]*)\} %s;" % cname, h).group(1)
+        body = re.search(r"typedef struct \{([^{}]*)\} " + cname + ";", h).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         names = []
         for decl in body.split(";"):
