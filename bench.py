@@ -296,8 +296,9 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         peaks = load_peaks()
         launches = int(sum(v[0] for v in prof.values()))
-        top = max(prof.items(), key=lambda kv: kv[1][1]) if prof else ("none", (0, 0.0))
-        kname, (kcount, kms) = top
+        # the kernel the roofline is quoted for: the dense background cross-correlation (the path's only contraction)
+        kname = "k_nuc_bx_tc" if "k_nuc_bx_tc" in prof else "k_nuc_bx_fp64"
+        kcount, kms = prof.get(kname, (0, 0.0))
         # algorithmic work of the dominant kernel: the dense background cross-correlation, 2*R*W flop per bp
         flop_per_launch = 2.0 * R_V * W_V * bp_step
         k_avg_s = (kms / max(kcount, 1)) * 1e-3

@@ -110,6 +110,7 @@ struct nb200_ctx {
     void *nccl_lib = nullptr;
     void *nccl_comm = nullptr;
     int nccl_rank = 0, nccl_world = 1;
+    void *tc_plan = nullptr;  // tensor-core xcor plan (nb200_xcor_tc.cu)
 };
 
 int nb200_fail(nb200_ctx *ctx, int code, const char *fmt, ...);
@@ -203,5 +204,6 @@ int nb200_nuc_bx_fp64(nb200_ctx *ctx, nb200_dbatch *b);   // dense background xc
 int nb200_nuc_bx_tc(nb200_ctx *ctx, nb200_dbatch *b);     // dense background xcor, tcgen05
 int nb200_tc_setup(nb200_ctx *ctx);                       // (re)build tensor-core operands after vmat / sizes change
 int nb200_tc_available(nb200_ctx *ctx);
+void nb200_tc_release(nb200_ctx *ctx);
 
 static inline int64_t div_up64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -120,6 +120,7 @@ int nb200_ctx_destroy(nb200_ctx *c)
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     nb200_prof_collect(c);
+    nb200_tc_release(c);
     for (auto ev : c->ev_pool) cudaEventDestroy(ev);
     RunConst &r = c->rc;
     DevBuf *bufs[] = {&r.log_pwm, &r.nuc_code, &r.vmat,   &r.vmat_fp, &r.sizes,  &r.nuc_probs, &r.nfr_probs,

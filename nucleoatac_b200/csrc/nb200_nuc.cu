@@ -343,29 +343,48 @@ struct CandArgs {
 #define CS_THREADS 256
 __global__ void __launch_bounds__(CS_THREADS) k_cand_stats(CandArgs a)
 {
+    extern __shared__ double sm_cs[];
     __shared__ double red[32];
+    const int uv = a.lv + a.R;
+    const int half = uv / 2;
+    const int nEw = a.W + 2 * half + 2;
+    double *s_E = sm_cs;         // [nEw]  E over genomic [P - w - half, ...)
+    double *s_f = sm_cs + nEw;   // [R]    f_i over the VMat's sizes
     const int nwork = a.work_count[0];
     const int tid = threadIdx.x;
+    // thread layout over the R x W window: column kk, rows rr, rr + rows_par, ...
+    const int wcols = min(a.W, CS_THREADS);
+    const int rows_par = CS_THREADS / wcols;
+    const int kk = tid % wcols, rr = tid / wcols;
+    for (int i = tid; i < a.R; i += CS_THREADS) s_f[i] = a.f[a.lv + i];
     for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
         const int2 it = a.work[wi];
         const int c = it.x;
         const int64_t ci = a.cand_off[c] + it.y;
         const int P = a.cand_pos[ci];
         const int x = P - a.start[c];
-        const double *Eg = a.use_bias ? a.E + (a.bias_off[c] - (int64_t)(a.seq_start[c] + a.pwm_up)) + (P - a.w) : nullptr;
+        __syncthreads();
+        if (a.use_bias) {
+            const double *Eg = a.E + (a.bias_off[c] - (int64_t)(a.seq_start[c] + a.pwm_up)) + (P - a.w - half);
+            for (int i = tid; i < nEw; i += CS_THREADS) s_E[i] = Eg[i];
+        }
+        __syncthreads();
         // dense window sums: S_VB = sum V*Bp, S_B = sum f*Bp, S_BV = sum f*V*Bp, S_BV2 = sum f*V^2*Bp
         double sVB = 0.0, sB = 0.0, sBV = 0.0, sBV2 = 0.0;
-        const int n = a.R * a.W;
-        for (int idx = tid; idx < n; idx += CS_THREADS) {
-            const int r = idx / a.W, k = idx - r * a.W;
-            const int i = a.lv + r;
-            const double bp = a.use_bias ? bias_cell(Eg + k, i) : 1.0;
-            const double v = a.V[idx];
-            const double b = __dmul_rn(bp, a.f[i]);  // normByInsertDist, chunkmat2d.py:154-156
-            sVB += v * bp;
-            sB += b;
-            sBV += b * v;
-            sBV2 += b * v * v;
+        if (rr < rows_par) {
+            for (int k = kk; k < a.W; k += wcols) {
+                const double *Ec = s_E + half + k;
+                for (int r = rr; r < a.R; r += rows_par) {
+                    const double bp = a.use_bias ? bias_cell(Ec, a.lv + r) : 1.0;
+                    const double v = a.V[(size_t)r * a.W + k];
+                    const double b = __dmul_rn(bp, s_f[r]);  // normByInsertDist, chunkmat2d.py:154-156
+                    sVB = fma(v, bp, sVB);
+                    sB += b;
+                    const double bv = b * v;
+                    sBV += bv;
+                    sBV2 = fma(bv, v, sBV2);
+                }
+            }
         }
         sVB = block_sum(sVB, red);
         sB = block_sum(sB, red);
@@ -382,9 +401,9 @@ __global__ void __launch_bounds__(CS_THREADS) k_cand_stats(CandArgs a)
             const int r = v.y - a.lv;
             if (r >= 0 && r < a.R) {
                 const int k = v.x + kb;
-                const double bp = a.use_bias ? bias_cell(Eg + k, v.y) : 1.0;
+                const double bp = a.use_bias ? bias_cell(s_E + half + k, v.y) : 1.0;
                 nl += log(__dmul_rn(a.V[(size_t)r * a.W + k], bp) / sVB);
-                ul += log(__dmul_rn(bp, a.f[v.y]) / sB);
+                ul += log(__dmul_rn(bp, s_f[r]) / sB);
             }
         }
         nl = block_sum(nl, red);
@@ -405,7 +424,6 @@ __global__ void __launch_bounds__(CS_THREADS) k_cand_stats(CandArgs a)
             a.cand_z[ci] = z;
             a.cand_flag[ci] = fl;
         }
-        __syncthreads();
     }
 }
 
@@ -520,7 +538,7 @@ int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
             NB_LAUNCH_CHECK(ctx);
         }
         int mode = p.xcor_mode;
-        if (mode == 0) mode = 1;  // auto: fp64 CUDA cores unless the tensor-core path is requested
+        if (mode == 0) mode = nb200_tc_available(ctx) ? 2 : 1;  // auto: tcgen05 contraction when its plan exists
         if (mode == 2) {
             if (!nb200_tc_available(ctx)) return nb200_fail(ctx, NB200_ERR_STATE, "xcor_mode 2 (tcgen05) is not available in this build");
             NB_CHECK(nb200_nuc_bx_tc(ctx, b));
@@ -647,7 +665,9 @@ int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
         a.min_lr = p.min_lr;
         a.min_z = p.min_z;
         ProfScope ps(ctx, b->stream, "k_cand_stats");
-        k_cand_stats<<<ctx->sm_count * 8, CS_THREADS, 0, b->stream>>>(a);
+        size_t smem = sizeof(double) * ((size_t)W + 2 * (uv / 2) + 2 + r.v_rows);
+        if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_cand_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_cand_stats<<<ctx->sm_count * 8, CS_THREADS, smem, b->stream>>>(a);
         NB_LAUNCH_CHECK(ctx);
     }
     {

@@ -129,41 +129,70 @@ __global__ void __launch_bounds__(MLE_WARPS * 32) k_occ_mle(OccMleArgs a)
             SF = a.sf_nobias;
         }
         for (int j = 0; j < J; j++) {
-            const int sz = s_sz[j];
             double bias;
             if (a.use_bias) {
+                const int sz = s_sz[j];
                 double acc = 0.0;
                 for (int k = lane; k < window; k += 32) acc += bias_cell(Eg + k, sz);
                 bias = warp_sum(acc);
             } else
                 bias = (double)window;
-            if (lane == 0) {
-                s_nucp[j] = __dmul_rn(a.pn[sz], bias) / SN;  // nuc_probs * bias / sum, Occupancy.py:106-109
-                s_nfrp[j] = __dmul_rn(a.pf[sz], bias) / SF;
-            }
+            if (lane == 0) s_nucp[j] = bias;
         }
         __syncwarp();
-        // log-likelihood grid; lane owns alphas lane, lane+32, ...
-        double ll[NB200_MAX_ALPHA / 32];
+        for (int j = lane; j < J; j += 32) {  // nuc_probs * bias / sum, Occupancy.py:106-109 (one size per lane)
+            const int sz = s_sz[j];
+            const double bias = s_nucp[j];
+            s_nucp[j] = __dmul_rn(a.pn[sz], bias) / SN;
+            s_nfrp[j] = __dmul_rn(a.pf[sz], bias) / SF;
+        }
+        __syncwarp();
+        // log-likelihood grid; lane owns alphas lane, lane+32, ...  ll[a] = sum_s ins[s]*log(v_s(a)) is evaluated as
+        // log(prod_s v_s^ins[s]) with the product kept as (mantissa, binary exponent): one log per alpha instead of
+        // one per (alpha, size).  Rounding: ~n ulp on the product, i.e. the same order as the sum of n rounded logs.
+        constexpr int NQ = NB200_MAX_ALPHA / 32;
+        double al[NQ], om[NQ], mant[NQ];
+        int ex[NQ];
+        bool dead[NQ];
 #pragma unroll
-        for (int q = 0; q < NB200_MAX_ALPHA / 32; q++) {
+        for (int q = 0; q < NQ; q++) {
             const int ai = lane + 32 * q;
-            double acc = nb_ninf();
-            if (ai < a.n_alpha) {
-                const double al = a.alphas[ai];
-                const double om = 1.0 - al;
-                // 0 * log(0) = NaN -> -inf (Occupancy.py:112-114) for sizes with no reads but zero probability
-                bool dead = a.both_zero || (al == 0.0 && a.pf_has_zero) || (om == 0.0 && a.pn_has_zero);
-                if (!dead) {
-                    acc = 0.0;
-                    for (int j = 0; j < J; j++) {
-                        double v = __dadd_rn(__dmul_rn(al, s_nucp[j]), __dmul_rn(om, s_nfrp[j]));
-                        acc = __dadd_rn(acc, __dmul_rn(log(v), (double)s_cnt[j]));
+            al[q] = (ai < a.n_alpha) ? a.alphas[ai] : 0.5;
+            om[q] = 1.0 - al[q];
+            mant[q] = 1.0;
+            ex[q] = 0;
+            // 0 * log(0) = NaN -> -inf (Occupancy.py:112-114) for sizes with no reads but zero probability
+            dead[q] = (ai >= a.n_alpha) || a.both_zero || (al[q] == 0.0 && a.pf_has_zero) || (om[q] == 0.0 && a.pn_has_zero);
+        }
+        int nf = 0;
+        for (int j = 0; j < J; j++) {
+            const double pj = s_nucp[j], qj = s_nfrp[j];
+            const int cj = s_cnt[j];
+            double v[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; q++) v[q] = __dadd_rn(__dmul_rn(al[q], pj), __dmul_rn(om[q], qj));
+            for (int r = 0; r < cj; r++) {
+#pragma unroll
+                for (int q = 0; q < NQ; q++) mant[q] *= v[q];
+                if ((++nf & 3) == 0) {  // renormalise every 4 factors (factors >= 1e-75 cannot underflow in between)
+#pragma unroll
+                    for (int q = 0; q < NQ; q++) {
+                        const long long bits = __double_as_longlong(mant[q]);
+                        const int e = (int)((bits >> 52) & 0x7ff);
+                        if (e != 0 && e != 0x7ff) {  // positive normal: move the exponent into ex
+                            ex[q] += e - 1023;
+                            mant[q] = __longlong_as_double(bits - ((long long)(e - 1023) << 52));
+                        }
                     }
-                    if (acc != acc) acc = nb_ninf();
                 }
             }
-            ll[q] = acc;
+        }
+        double ll[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            double acc = nb_ninf();
+            if (!dead[q] && mant[q] > 0.0) acc = log(mant[q]) + (double)ex[q] * 0.6931471805599453094;
+            ll[q] = acc;  // NaN / zero products (log 0) -> -inf like `logliks[np.isnan(logliks)] = -inf`
         }
         // first maximum (np.argmax)
         double best = nb_ninf();

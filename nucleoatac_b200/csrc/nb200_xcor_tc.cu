@@ -1,8 +1,508 @@
-// nb200_xcor_tc.cu -- tcgen05 (5th-generation tensor core) version of the dense background
-// cross-correlation.  Placeholder until the kernel lands: reports "not available" so that
-// xcor_mode 2 fails loudly instead of silently running the fp64 kernel.
+// nb200_xcor_tc.cu -- the dense background cross-correlation (BiasTrack.calculateBackgroundSignal,
+// nucleoatac/NucleosomeCalling.py:60-63) as a tcgen05 tensor-core contraction.
+//
+//   bx[x] = sum_i sum_k f_i V[i,k] Bp[i, x-w+k],   Bp[i,c] = E[c-(i-1)//2] * E[c+i//2]   (chunkmat2d.py:140-156)
+//
+// Every cell of the bias matrix is a product of two taps of the SAME 1-D track, so with a = left-tap offset and
+// b = right-tap offset relative to x the sum is a windowed bilinear form
+//
+//   bx[x] = sum_a E[x+a] * H[x,a],      H[x,a] = sum_b G[a,b] * E[x+b],      G[a,b] = f_i V[i,k]  ((a,b) <-> (i,k), 1:1)
+//
+// H = Hankel(E) x G^T is a GEMM whose A operand (M = 128 output positions, K = b) is a Hankel matrix of the track:
+// A[m,kb] = Es[m + kb].  It is never expanded: shared memory holds the track once per 8 element shifts
+// (Z[t][s][0..7] = Es[8t+s .. 8t+s+7], 16 B rows) and the UMMA shared-memory descriptor walks it with
+// SBO = LBO = 128 B, i.e. the 8x16B core matrices of neighbouring row groups / K chunks overlap in memory.
+// B = G (constant per run: VMat x fragment-size distribution) is pre-split, pre-tiled and block-sparsified on the
+// host (the non-zero region of G is a parallelogram) and streamed L2 -> SMEM with cp.async.bulk through a 6-stage
+// mbarrier ring.  fp64-grade accuracy of the operands comes from a 2-term fp16 split (hi + lo, 22 bits) of both
+// operands, scaled by powers of two into the fp16 range: three MMAs hi*hi + hi*lo + lo*hi accumulate in fp32 TMEM.
+// The epilogue (4 warps, one TMEM lane = one output position per thread) reads H with tcgen05.ld and contracts it
+// with the unscaled fp64 track, double-buffered against the MMAs of the next 64-column slab of H.
+//
+// Per CTA: 4 x-tiles of 128 outputs share every G stage (TMEM: 2 buffers x 4 tiles x 64 columns = 512 columns).
+// Warp roles: 0-3 epilogue (+ operand generation), 4 bulk-copy producer, 5 MMA issuer (+ TMEM alloc).
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+
 #include "nb200_dev.cuh"
 
-int nb200_tc_setup(nb200_ctx *) { return NB200_OK; }
-int nb200_tc_available(nb200_ctx *) { return 0; }
-int nb200_nuc_bx_tc(nb200_ctx *ctx, nb200_dbatch *) { return nb200_fail(ctx, NB200_ERR_STATE, "tcgen05 xcor not built"); }
+#define TC_XT 4
+#define TC_M 128
+#define TC_TX (TC_XT * TC_M)
+#define TC_N 64
+#define TC_KS 64
+#define TC_STAGES 6
+#define TC_PART_BYTES (TC_N * TC_KS * 2)
+#define TC_STAGE_BYTES (2 * TC_PART_BYTES)
+#define TC_THREADS 192
+
+struct TcPlan {
+    bool ok = false;
+    int A0 = 0, B0 = 0, NA = 0, NB = 0, NAp = 0, NBp = 0, gmin = 0, span = 0;
+    int n_stages = 0, n_achunks = 0;
+    int sG = 0;           // G scaled by 2^sG
+    int has_row1 = 0;     // insert size 1 has a single tap (linear term), kept out of G
+    double density = 0.0; // active K16 x 64 blocks / all blocks
+    DevBuf g_img, stage_tab, t_row1, emax;
+    std::vector<int4> h_tab;
+};
+
+static TcPlan *plan_of(nb200_ctx *ctx, bool create)
+{
+    if (!ctx->tc_plan && create) ctx->tc_plan = new TcPlan();
+    return static_cast<TcPlan *>(ctx->tc_plan);
+}
+
+void nb200_tc_release(nb200_ctx *ctx)
+{
+    TcPlan *pl = static_cast<TcPlan *>(ctx->tc_plan);
+    if (!pl) return;
+    pl->g_img.release();
+    pl->stage_tab.release();
+    pl->t_row1.release();
+    pl->emax.release();
+    delete pl;
+    ctx->tc_plan = nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    int spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!done && ++spins > (1 << 20)) __trap();  // never hang the GPU on a protocol bug
+    }
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 8x16B core matrices,
+// SBO = byte stride between 8-row groups, LBO = byte stride between the 16-byte K chunks, version 1 (sm_100).
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo)
+{
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+           (1ull << 46);
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t *r)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+struct TcArgs {
+    const int32_t *start;
+    const int64_t *out_off, *bias_off;
+    const int32_t *seq_start;
+    const double *E;
+    const double *emax;       // device scalar: max of E over the batch (bit pattern max, E > 0)
+    const int4 *tab;          // per stage {a-chunk q, first K16 block, #K16 blocks, flags: bit0 first of chunk, bit1 last}
+    const unsigned char *g_img;
+    const double *t_row1;     // f_1 * V[1 - lv, :] (size-1 fragments: single tap)
+    double *bx;
+    int pwm_up, A0, B0, NAp, NBp, gmin, span, n_stages, n_achunks, sG, has_row1, W, w;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
+{
+    extern __shared__ __align__(128) unsigned char sm_tc[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.y;
+    const int64_t oo = a.out_off[c];
+    const int L = (int)(a.out_off[c + 1] - oo);
+    const int x0 = blockIdx.x * TC_TX;
+    if (x0 >= L) return;
+
+    // ---- shared memory carve-up
+    const int nZ = (TC_TX + a.NBp) / 8;                     // 128-byte chunks per Z part
+    unsigned char *p = sm_tc;
+    unsigned char *s_stage = p;            p += TC_STAGES * TC_STAGE_BYTES;
+    unsigned char *s_zhi = p;              p += (size_t)nZ * 128;
+    unsigned char *s_zlo = p;              p += (size_t)nZ * 128;
+    double *s_E = reinterpret_cast<double *>(p);            // [span] E over genomic [g0 + gmin, ...)
+    p += sizeof(double) * a.span;
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(p);      // full[S], empty[S], tmem_full[2], tmem_empty[2]
+    p += sizeof(uint64_t) * (2 * TC_STAGES + 4);
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(p);
+    const uint32_t bar_full = smem_u32(s_bar), bar_empty = bar_full + 8 * TC_STAGES, bar_tfull = bar_empty + 8 * TC_STAGES,
+                   bar_tempty = bar_tfull + 16;
+
+    // ---- one-time setup
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < TC_STAGES; i++) {
+            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(bar_tfull + 8 * i, 1);
+            mbar_init(bar_tempty + 8 * i, 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {  // TMEM: all 512 columns (one CTA per SM by __launch_bounds__ + shared memory footprint)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(s_tmem)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // E window (fp64) -> shared; out of track -> 0 (only reached under zero columns of G / unused outputs)
+    {
+        const int64_t eb = a.bias_off[c] - (int64_t)(a.seq_start[c] + a.pwm_up);
+        const int64_t e_lo = a.bias_off[c], e_hi = a.bias_off[c + 1];
+        const int64_t g0 = (int64_t)a.start[c] + x0 + a.gmin;
+        for (int i = threadIdx.x; i < a.span; i += TC_THREADS) {
+            const int64_t idx = eb + g0 + i;
+            s_E[i] = (idx >= e_lo && idx < e_hi) ? a.E[idx] : 0.0;
+        }
+    }
+    __syncthreads();
+    // A operand: Z[t][s][0..7] = fp16 hi/lo of scale * E[b-window start + 8t + s + j]
+    int eexp = 1;
+    const double emax = a.emax[0];
+    if (emax > 0.0) frexp(32768.0 / emax, &eexp);
+    const int sE = eexp - 1;
+    {
+        const double scale = ldexp(1.0, sE);
+        const int boff = a.B0 - a.gmin;  // s_E index of the first b tap of output 0
+        for (int e = threadIdx.x; e < nZ * 8; e += TC_THREADS) {
+            const int t = e >> 3, s = e & 7;
+            __align__(16) __half hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int idx = boff + 8 * t + s + j;
+                const float v = (idx < a.span) ? (float)(s_E[idx] * scale) : 0.f;
+                hi[j] = __float2half_rn(v);
+                lo[j] = __float2half_rn(v - __half2float(hi[j]));
+            }
+            *reinterpret_cast<uint4 *>(s_zhi + (size_t)e * 16) = *reinterpret_cast<uint4 *>(hi);
+            *reinterpret_cast<uint4 *>(s_zlo + (size_t)e * 16) = *reinterpret_cast<uint4 *>(lo);
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+
+    if (warp == 4) {
+        // ===== producer: stream the G stages (hi + lo, 16 KB) through the ring =====
+        if (lane == 0) {
+            for (int s = 0; s < a.n_stages; s++) {
+                const int slot = s % TC_STAGES;
+                const uint32_t ph = (s / TC_STAGES) & 1;
+                mbar_wait(bar_empty + 8 * slot, ph ^ 1);
+                mbar_expect_tx(bar_full + 8 * slot, TC_STAGE_BYTES);
+                bulk_g2s(smem_u32(s_stage + (size_t)slot * TC_STAGE_BYTES), a.g_img + (size_t)s * TC_STAGE_BYTES, TC_STAGE_BYTES,
+                         bar_full + 8 * slot);
+            }
+        }
+    } else if (warp == 5) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);  // f16 x f16 -> f32
+            const uint32_t zhi = smem_u32(s_zhi), zlo = smem_u32(s_zlo);
+            for (int s = 0; s < a.n_stages; s++) {
+                const int4 st = a.tab[s];
+                const int q = st.x, kblk0 = st.y, nblk = st.z;
+                const bool first = st.w & 1, last = st.w & 2;
+                const int buf = q & 1;
+                const int slot = s % TC_STAGES;
+                const uint32_t ph = (s / TC_STAGES) & 1;
+                if (first) {
+                    mbar_wait(bar_tempty + 8 * buf, ((q >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                }
+                mbar_wait(bar_full + 8 * slot, ph);
+                tc_fence_after();
+                const uint32_t sb = smem_u32(s_stage + (size_t)slot * TC_STAGE_BYTES);
+                for (int t = 0; t < nblk; t++) {
+                    const uint64_t b_hi = tc_smem_desc(sb + t * 2048, 1024, 128);
+                    const uint64_t b_lo = tc_smem_desc(sb + TC_PART_BYTES + t * 2048, 1024, 128);
+#pragma unroll
+                    for (int j = 0; j < TC_XT; j++) {
+                        const uint32_t zoff = (uint32_t)(16 * j + 2 * (kblk0 + t)) * 128;
+                        const uint64_t a_hi = tc_smem_desc(zhi + zoff, 128, 128);
+                        const uint64_t a_lo = tc_smem_desc(zlo + zoff, 128, 128);
+                        const uint32_t d = tmem + (uint32_t)(buf * (TC_XT * TC_N) + j * TC_N);
+                        tc_mma_f16(d, a_hi, b_hi, idesc, (first && t == 0) ? 0u : 1u);
+                        tc_mma_f16(d, a_hi, b_lo, idesc, 1u);
+                        tc_mma_f16(d, a_lo, b_hi, idesc, 1u);
+                    }
+                }
+                tc_commit(bar_empty + 8 * slot);               // smem slot reusable once these MMAs retire
+                if (last) tc_commit(bar_tfull + 8 * buf);      // slab q of H complete in TMEM
+            }
+        }
+    } else {
+        // ===== epilogue: bx[x] += sum_n E[x + A0 + 64 q + n] * H[x, 64 q + n] =====
+        const int m = warp * 32 + lane;                        // TMEM lane = output position within the x-tile
+        const int aoff = a.A0 - a.gmin;
+        double acc[TC_XT];
+#pragma unroll
+        for (int j = 0; j < TC_XT; j++) acc[j] = 0.0;
+        for (int q = 0; q < a.n_achunks; q++) {
+            const int buf = q & 1;
+            mbar_wait(bar_tfull + 8 * buf, (q >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < TC_XT; j++) {
+                const double *Ew = s_E + aoff + TC_M * j + m + TC_N * q;
+#pragma unroll
+                for (int h = 0; h < TC_N / 32; h++) {
+                    uint32_t r[32];
+                    tc_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * (TC_XT * TC_N) + j * TC_N + 32 * h), r);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int n = 0; n < 32; n++) acc[j] = fma((double)__uint_as_float(r[n]), Ew[32 * h + n], acc[j]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        }
+        const double unscale = ldexp(1.0, -(sE + a.sG));
+#pragma unroll
+        for (int j = 0; j < TC_XT; j++) {
+            const int x = x0 + TC_M * j + m;
+            if (x < L) {
+                double v = acc[j] * unscale;
+                if (a.has_row1) {  // insert size 1: Bp[1,c] = E[c] (one tap) -> plain 1-D correlation
+                    const double *Ew = s_E + (TC_M * j + m - a.w - a.gmin);
+                    double lin = 0.0;
+                    for (int k = 0; k < a.W; k++) lin = fma(a.t_row1[k], Ew[k], lin);
+                    v += lin;
+                }
+                a.bx[oo + x] = v;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: G images + stage table (once per VMat / fragment-size change)
+// ---------------------------------------------------------------------------------------------
+int nb200_tc_setup(nb200_ctx *ctx)
+{
+    RunConst &r = ctx->rc;
+    TcPlan *pl = plan_of(ctx, true);
+    if (!pl) return NB200_OK;
+    pl->ok = false;
+    if (!r.have_vmat || !r.have_sizes) return NB200_OK;
+    const int lv = r.v_lower, uv = r.v_upper, W = r.v_cols, w = r.v_w, R = r.v_rows;
+    auto fd2 = [](int v) { return v >> 1; };  // floor division by 2
+    // tap offsets relative to the output position: a = (k-w) - (i-1)//2, b = (k-w) + i//2   (i != 1)
+    int amin = INT32_MAX, amax = INT32_MIN, bmin = INT32_MAX, bmax = INT32_MIN;
+    for (int i = lv; i < uv; i++) {
+        if (i == 1) continue;
+        amin = std::min(amin, -w - fd2(i - 1));
+        amax = std::max(amax, w - fd2(i - 1));
+        bmin = std::min(bmin, -w + fd2(i));
+        bmax = std::max(bmax, w + fd2(i));
+    }
+    if (amin > amax) return NB200_OK;  // VMat with only size 1: nothing for the tensor core
+    pl->A0 = amin;
+    pl->B0 = bmin;
+    pl->NA = amax - amin + 1;
+    pl->NB = bmax - bmin + 1;
+    pl->NAp = (pl->NA + TC_N - 1) / TC_N * TC_N;
+    pl->NBp = (pl->NB + 15) / 16 * 16;
+    pl->n_achunks = pl->NAp / TC_N;
+    pl->has_row1 = (lv <= 1 && 1 < uv) ? 1 : 0;
+    // shared E window: genomic offsets [gmin, gmax] relative to the CTA's first output
+    int gmin = std::min(std::min(amin, bmin), -w);
+    int gmax = std::max(std::max(TC_TX - 1 + pl->A0 + pl->NAp - 1, TC_TX + pl->B0 + pl->NBp + 8), TC_TX - 1 + w);
+    pl->gmin = gmin;
+    pl->span = gmax - gmin + 1;
+    std::vector<double> G((size_t)pl->NAp * pl->NBp, 0.0);
+    double gmaxv = 0.0;
+    for (int i = lv; i < uv; i++) {
+        if (i == 1) continue;
+        const double f = r.h_sizes[i];
+        for (int k = 0; k < W; k++) {
+            const int ia = (k - w) - fd2(i - 1) - pl->A0, ib = (k - w) + fd2(i) - pl->B0;
+            const double g = f * r.h_vmat[(size_t)(i - lv) * W + k];
+            G[(size_t)ia * pl->NBp + ib] += g;
+            gmaxv = std::max(gmaxv, fabs(g));
+        }
+    }
+    if (!(gmaxv > 0.0) || !std::isfinite(gmaxv)) return NB200_OK;
+    int ex;
+    frexp(32768.0 / gmaxv, &ex);
+    pl->sG = ex - 1;
+    const double sc = ldexp(1.0, pl->sG);
+    // active K16 blocks per a-chunk -> stages of up to 4 consecutive K16 blocks
+    pl->h_tab.clear();
+    std::vector<unsigned char> img;
+    const int nkb = pl->NBp / 16;
+    int active = 0;
+    for (int q = 0; q < pl->n_achunks; q++) {
+        int k_lo = nkb, k_hi = -1;
+        for (int kb = 0; kb < nkb; kb++) {
+            bool nz = false;
+            for (int n = 0; n < TC_N && !nz; n++)
+                for (int k = 0; k < 16 && !nz; k++) nz = G[(size_t)(q * TC_N + n) * pl->NBp + kb * 16 + k] != 0.0;
+            if (nz) {
+                k_lo = std::min(k_lo, kb);
+                k_hi = std::max(k_hi, kb);
+            }
+        }
+        if (k_hi < 0) k_lo = k_hi = 0;  // keep every a-chunk present (one zero block)
+        active += k_hi - k_lo + 1;
+        for (int kb0 = k_lo; kb0 <= k_hi; kb0 += TC_KS / 16) {
+            const int nblk = std::min(TC_KS / 16, k_hi - kb0 + 1);
+            int flags = (kb0 == k_lo ? 1 : 0) | (kb0 + nblk > k_hi ? 2 : 0);
+            pl->h_tab.push_back(make_int4(q, kb0, nblk, flags));
+            const size_t base = img.size();
+            img.resize(base + TC_STAGE_BYTES, 0);
+            __half *hi = reinterpret_cast<__half *>(img.data() + base);
+            __half *lo = reinterpret_cast<__half *>(img.data() + base + TC_PART_BYTES);
+            for (int n = 0; n < TC_N; n++)
+                for (int k = 0; k < nblk * 16; k++) {
+                    const double g = G[(size_t)(q * TC_N + n) * pl->NBp + kb0 * 16 + k] * sc;
+                    const float gf = (float)g;
+                    const __half h = __float2half_rn(gf);
+                    const __half l = __float2half_rn(gf - __half2float(h));
+                    // canonical K-major no-swizzle image: core matrix (n/8, k/8) at ((k/8)*8 + n/8)*128 B, row n%8, elt k%8
+                    const size_t off = ((size_t)(k / 8) * (TC_N / 8) + n / 8) * 64 + (n % 8) * 8 + (k % 8);
+                    hi[off] = h;
+                    lo[off] = l;
+                }
+        }
+    }
+    pl->n_stages = (int)pl->h_tab.size();
+    pl->density = (double)active / ((double)pl->n_achunks * nkb);
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    NB_CUDA(ctx, pl->g_img.reserve(img.size()));
+    NB_CUDA(ctx, cudaMemcpy(pl->g_img.p, img.data(), img.size(), cudaMemcpyHostToDevice));
+    NB_CUDA(ctx, pl->stage_tab.reserve(sizeof(int4) * pl->h_tab.size()));
+    NB_CUDA(ctx, cudaMemcpy(pl->stage_tab.p, pl->h_tab.data(), sizeof(int4) * pl->h_tab.size(), cudaMemcpyHostToDevice));
+    std::vector<double> t1(W, 0.0);
+    if (pl->has_row1)
+        for (int k = 0; k < W; k++) t1[k] = r.h_sizes[1] * r.h_vmat[(size_t)(1 - lv) * W + k];
+    NB_CUDA(ctx, pl->t_row1.reserve(sizeof(double) * W));
+    NB_CUDA(ctx, cudaMemcpy(pl->t_row1.p, t1.data(), sizeof(double) * W, cudaMemcpyHostToDevice));
+    NB_CUDA(ctx, pl->emax.reserve(sizeof(double)));
+    pl->ok = true;
+    return NB200_OK;
+}
+
+int nb200_tc_available(nb200_ctx *ctx)
+{
+    TcPlan *pl = plan_of(ctx, false);
+    return pl && pl->ok;
+}
+
+// max over the batch's E track (E > 0: IEEE bit patterns order like unsigned integers)
+__global__ void k_emax(const double *__restrict__ E, int64_t n, unsigned long long *out)
+{
+    unsigned long long m = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = E[i];
+        if (v == v && v < CUDART_INF) m = max(m, (unsigned long long)__double_as_longlong(v));
+    }
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(NB_FULL, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+int nb200_nuc_bx_tc(nb200_ctx *ctx, nb200_dbatch *b)
+{
+    TcPlan *pl = plan_of(ctx, false);
+    if (!pl || !pl->ok) return nb200_fail(ctx, NB200_ERR_STATE, "tcgen05 xcor plan is not available");
+    RunConst &r = ctx->rc;
+    NB_CUDA(ctx, cudaMemsetAsync(pl->emax.p, 0, sizeof(double), b->stream));
+    {
+        ProfScope ps(ctx, b->stream, "k_emax");
+        k_emax<<<ctx->sm_count * 4, 256, 0, b->stream>>>(b->d_E.as<double>(), b->n_bias, pl->emax.as<unsigned long long>());
+        NB_LAUNCH_CHECK(ctx);
+    }
+    TcArgs a;
+    a.start = b->d_start.as<int32_t>();
+    a.out_off = b->d_out_off.as<int64_t>();
+    a.bias_off = b->d_bias_off.as<int64_t>();
+    a.seq_start = b->d_seq_start.as<int32_t>();
+    a.E = b->d_E.as<double>();
+    a.emax = pl->emax.as<double>();
+    a.tab = pl->stage_tab.as<int4>();
+    a.g_img = pl->g_img.as<unsigned char>();
+    a.t_row1 = pl->t_row1.as<double>();
+    a.bx = b->n_bx.as<double>();
+    a.pwm_up = r.pwm_up;
+    a.A0 = pl->A0;
+    a.B0 = pl->B0;
+    a.NAp = pl->NAp;
+    a.NBp = pl->NBp;
+    a.gmin = pl->gmin;
+    a.span = pl->span;
+    a.n_stages = pl->n_stages;
+    a.n_achunks = pl->n_achunks;
+    a.sG = pl->sG;
+    a.has_row1 = pl->has_row1;
+    a.W = r.v_cols;
+    a.w = r.v_w;
+    const int nZ = (TC_TX + pl->NBp) / 8;
+    size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 2 * (size_t)nZ * 128 + sizeof(double) * pl->span + 8 * (2 * TC_STAGES + 4) + 16;
+    smem = (smem + 127) / 128 * 128;
+    if (smem > 227 * 1024) return nb200_fail(ctx, NB200_ERR_ARG, "VMat too large for the tcgen05 background kernel");
+    NB_CUDA(ctx, cudaFuncSetAttribute(k_nuc_bx_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps(ctx, b->stream, "k_nuc_bx_tc");
+    dim3 grid((unsigned)div_up64(b->max_len, TC_TX), b->n_chunks);
+    k_nuc_bx_tc<<<grid, TC_THREADS, smem, b->stream>>>(a);
+    NB_LAUNCH_CHECK(ctx);
+    return NB200_OK;
+}

@@ -41,7 +41,7 @@ def _sizes(rng, n):
     return np.rint(size).astype(np.int64)
 
 
-def make_chunk(k, length=CHUNK_LEN, density=0.25, seed=SEED, with_seq=True):
+def make_chunk(k, length=CHUNK_LEN, density=0.25, seed=SEED, with_seq=True, seq_margin=SEQ_MARGIN):
     """-> (start, end, pos int32[], tlen int32[], seq uint8[] | None, seq_start)."""
     rng = np.random.default_rng([seed, k])
     s, e = chunk_span(k, length)
@@ -68,14 +68,14 @@ def make_chunk(k, length=CHUNK_LEN, density=0.25, seed=SEED, with_seq=True):
     tlen = (size[order] + 8).astype(np.int32)
     seq = None
     if with_seq:
-        codes = rng.choice(5, size=length + 2 * SEQ_MARGIN, p=[0.2997, 0.1998, 0.1998, 0.2997, 0.001])
+        codes = rng.choice(5, size=length + 2 * seq_margin, p=[0.2997, 0.1998, 0.1998, 0.2997, 0.001])
         seq = np.frombuffer(b"ACGTN", dtype=np.uint8)[codes]
-    return s, e, pos, tlen, seq, s - SEQ_MARGIN
+    return s, e, pos, tlen, seq, s - seq_margin
 
 
-def make_batch(k0, n, length=CHUNK_LEN, density=0.25, seed=SEED, with_seq=True):
+def make_batch(k0, n, length=CHUNK_LEN, density=0.25, seed=SEED, with_seq=True, seq_margin=SEQ_MARGIN):
     """PackedBatch of chunks k0 .. k0+n-1."""
-    return PackedBatch.from_chunks([make_chunk(k, length, density, seed, with_seq) for k in range(k0, k0 + n)])
+    return PackedBatch.from_chunks([make_chunk(k, length, density, seed, with_seq, seq_margin) for k in range(k0, k0 + n)])
 
 
 def size_mixture(upper):

@@ -318,3 +318,75 @@ def test_error_paths(eng, example):
         eng.nuc_run(h)
     assert ei.value.code == _lib.ERR_FLANK
     eng.free_batch(h)
+
+
+# ---------------------------------------------------------------------------------- tcgen05 background xcor
+TC_RTOL = 1e-5  # BASELINE.json: floats within 1e-5 relative (fp16x2 split operands, fp32 TMEM accumulation)
+
+
+@pytest.mark.parametrize("which", ["example_146x121", "synthetic_251x251"])
+def test_nuc_tensor_core_path(eng, example, which):
+    """xcor_mode 2 (tcgen05 Hankel-GEMM) against the oracle: tracks within 1e-5 of the signal scale, coverage exact,
+    the same candidates / calls, statistics within 1e-5."""
+    from nucleoatac_b200 import synth
+    from nucleoatac_b200.engine import PackedBatch
+    if which == "example_146x121":
+        params = refnuc.NucParams(example.vmat, example.fragmentsizes, sd=10)
+        eng.set_pwm(example.pwm, example.pwm_up, example.pwm_down, example.nucleotides)
+        eng.set_vmat(*example.vmat)
+        eng.set_fragment_sizes(example.fragmentsizes)
+        eng.configure_nuc(sd=10, use_bias=True, xcor_mode=2)
+        idx = list(range(example.n_chunks))
+        pb = example_batch(example, idx)
+        inputs = []
+        for i in idx:
+            _, s, e = example.chunk(i)
+            _, _, span = refnuc.nuc_geometry(s, e, params)
+            inputs.append((s, e) + tuple(example.reads(i)) + (oracle_bias(example, i, span), span[0]))
+    else:
+        wl = synth.Workload(251, 251)
+        wl.configure(eng, use_bias=True, xcor_mode=2)
+        params = refnuc.NucParams((wl.vmat, wl.v_lower, wl.v_upper), wl.fragmentsizes, sd=10)
+        chunks = [synth.make_chunk(k) for k in (2, 4)]
+        pb = PackedBatch.from_chunks(chunks)
+        inputs = []
+        for (s, e, pos, tlen, seq, s0) in chunks:
+            _, _, span = refnuc.nuc_geometry(s, e, params)
+            bt = ra.log_bias_track(bytes(seq).decode()[span[0] - 10 - s0:span[1] + 10 - s0], wl.pwm, wl.nucleotides)
+            inputs.append((s, e, pos, tlen, bt, span[0]))
+    out = eng.process_nuc(pb)
+    assert "k_nuc_bx_tc" in eng.profile_report()
+    worst, flips, ncand = 0.0, [], 0
+    for j, (s, e, pos, tlen, bt, b0) in enumerate(inputs):
+        r = refnuc.process_nuc_chunk(pos, tlen, s, e, params, bias_track=bt, bias_track_start=b0, fit=False)
+        a, b = int(pb.out_off[j]), int(pb.out_off[j + 1])
+        scale = max(float(np.abs(r["nuc_signal"]).max()), float(np.abs(r["bias"]).max()), 1e-300)
+        for key, okey in (("background", "bias"), ("norm_signal", "norm_signal"), ("smoothed", "smoothed")):
+            err = float(np.abs(out[key][a:b] - r[okey]).max()) / scale
+            worst = max(worst, err)
+            assert err <= TC_RTOL, (j, key, err)
+        close(r["nuc_signal"], out["nuc_signal"][a:b], 1e-12, atol=1e-12 * scale)  # sparse gather: fp64
+        assert np.array_equal(out["nuc_cov"][a:b], r["nuc_cov"])
+        n, co = int(out["cand_count"][j]), int(out["cand_off"][j])
+        mine = [int(x) for x in out["cand_pos"][co:co + n] - s]
+        ref = [int(x) for x in r["cands"]]
+        # peak calling is discontinuous: a candidate may differ from the float64 oracle only where the oracle's own
+        # decision margin (threshold at 0, local-maximum test, or NMS ranking) is below the track tolerance
+        comb = r["norm_signal"] + r["smoothed"]
+        for p in set(mine) ^ set(ref):
+            lo_, hi_ = max(p - 25, 0), min(p + 26, len(comb))
+            others = np.delete(comb[lo_:hi_], p - lo_)
+            margin = min(abs(comb[p]), float(np.min(np.abs(others - comb[p]))))
+            assert margin <= 4 * TC_RTOL * scale, (j, p, margin)
+            flips.append((j, p, margin))
+        kept = [int(p - s) for p, f in zip(out["cand_pos"][co:co + n], out["cand_flag"][co:co + n]) if f & 4]
+        assert kept == sorted(r["nuc_collection"].keys())
+        by_pos = {rec["pos"] - s: rec for rec in r["cand_stats"]}
+        for q, p in enumerate(mine):
+            rec = by_pos.get(p)
+            if rec is not None and rec["nuc_cov"] > 1:
+                close(rec["lr"], out["cand_lr"][co + q], 1e-8, atol=1e-9)  # candidate statistics stay fp64
+                if rec["lr"] > 0:
+                    close(rec["z"], out["cand_z"][co + q], TC_RTOL, atol=TC_RTOL)
+    print("tensor-core path worst error / signal scale: %.2e; candidate flips at near-ties: %s" % (worst, flips))
+    assert len(flips) <= 2
