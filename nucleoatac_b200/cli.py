@@ -1,0 +1,74 @@
+"""Command line: `python -m nucleoatac_b200 occ|nuc ...` with the reference's flags (nucleoatac/cli.py:96-125,
+203-240) plus `--gpus`, `--batch` and `--xcor_mode`.  `--cores` is accepted and ignored (the device replaces the pool)."""
+import argparse
+import time
+
+
+def build_parser():
+    p = argparse.ArgumentParser(prog="nucleoatac", description="B200-native occ / nuc scoring path of NucleoATAC")
+    sub = p.add_subparsers(dest="command")
+    occ = sub.add_parser("occ", help="nucleoatac function:  Call nucleosome occupancy")
+    g = occ.add_argument_group("Required", "Necessary arguments")
+    g.add_argument("--bed", metavar="bed_file", required=True, help="Peaks in bed format")
+    g.add_argument("--bam", metavar="bam_file", required=True, help="Sorted (and indexed) BAM file")
+    g.add_argument("--out", metavar="basename", required=True, help="give output basename")
+    g = occ.add_argument_group("Bias calculation information", "Highly recommended. If fasta is not provided, will not calculate bias")
+    g.add_argument("--fasta", metavar="genome_seq", help="Indexed fasta file")
+    g.add_argument("--pwm", metavar="Tn5_PWM", default="Human", help="PWM descriptor file. Default is Human.PWM.txt included in package")
+    g = occ.add_argument_group("General Options", "")
+    g.add_argument("--sizes", metavar="fragmentsizes_file", help="File with fragment size distribution.  Use if don't want calculation of fragment size")
+    g.add_argument("--cores", metavar="int", default=1, type=int, help="Number of cores to use (ignored: chunks are scored on the GPU)")
+    g = occ.add_argument_group("Occupancy parameter", "Change with caution")
+    g.add_argument("--upper", metavar="int", default=251, type=int, help="upper limit in insert size. default is 251")
+    g.add_argument("--flank", metavar="int", default=60, type=int, help="Distance on each side of dyad to include for local occ calculation. Default is 60.")
+    g.add_argument("--min_occ", metavar="float", default=0.1, type=float, help="Occupancy cutoff for determining nucleosome distribution. Default is 0.1")
+    g.add_argument("--nuc_sep", metavar="int", default=120, type=int, help="minimum separation between occupany peaks. Default is 120.")
+    g.add_argument("--confidence_interval", metavar="float", default=0.9, type=float, help="confidence interval level for lower and upper bounds.  default is 0.9, should be between 0 and 1")
+    g.add_argument("--step", metavar="int", default=5, type=int, help="step size along genome for comuting occ. Default is 5.  Should be odd, or will be subtracted by 1")
+    nuc = sub.add_parser("nuc", help="nucleoatac function:  Call nucleosome positions and make signal tracks")
+    g = nuc.add_argument_group("Required", "Necessary arguments")
+    g.add_argument("--bed", metavar="bed_file", required=True, help="Regions for which to do stuff.")
+    g.add_argument("--vmat", metavar="vdensity_file", required=True, help="VMat object")
+    g.add_argument("--bam", metavar="bam_file", required=True, help="Accepts sorted BAM file")
+    g.add_argument("--out", metavar="basename", required=True, help="give output basename")
+    g = nuc.add_argument_group("Bias options", "If --fasta not provided, bias not calculated")
+    g.add_argument("--fasta", metavar="genome_seq", help="Indexed fasta file")
+    g.add_argument("--pwm", metavar="Tn5_PWM", default="Human", help="PWM descriptor file. Default is Human.PWM.txt included in package")
+    g = nuc.add_argument_group("General options", "")
+    g.add_argument("--sizes", metavar="fragmentsizes_file", help="File with fragment size distribution.  Use if don't want calculation of fragment size")
+    g.add_argument("--occ_track", metavar="occ_file", help="bgzip compressed bedgraph file with occcupancy track. Otherwise occ not determined for nuc positions.")
+    g.add_argument("--cores", metavar="num_cores", default=1, type=int, help="Number of cores to use (ignored: chunks are scored on the GPU)")
+    g.add_argument("--write_all", action="store_true", default=False, help="write all tracks")
+    g.add_argument("--not_atac", dest="atac", action="store_false", default=True, help="data is not atac-seq")
+    g = nuc.add_argument_group("Nucleosome calling parameters", "Change with caution")
+    g.add_argument("--min_z", metavar="float", default=3, type=float, help="Z-score threshold for nucleosome calls. Default is 3")
+    g.add_argument("--min_lr", metavar="float", default=0, type=float, help="Log likelihood ratio threshold for nucleosome calls. Default is 0")
+    g.add_argument("--nuc_sep", metavar="int", default=120, type=int, help="Minimum separation between non-redundant nucleosomes. Default is 120")
+    g.add_argument("--redundant_sep", metavar="int", default=25, type=int, help="Minimum separation between redundant nucleosomes. Not recommended to be below 15. Default is 25")
+    g.add_argument("--sd", metavar="int", default=10, type=int, help="Standard deviation for smoothing. Default is 10")
+    g.add_argument("--xcor_mode", default=0, type=int, help="0 auto (tcgen05), 1 fp64 CUDA cores, 2 tcgen05 tensor cores")
+    for sp in (occ, nuc):
+        g = sp.add_argument_group("Device options", "")
+        g.add_argument("--device", default=0, type=int, help="CUDA device of this process")
+        g.add_argument("--rank", default=0, type=int, help="shard index: this process scores chunks k with k %% world == rank")
+        g.add_argument("--world", default=1, type=int, help="number of shards (one process per GPU)")
+        g.add_argument("--batch", default=256, type=int, help="chunks per device batch")
+    return p
+
+
+def nucleoatac_main(argv=None):
+    args = build_parser().parse_args(argv)
+    t0 = time.time()
+    if args.command == "occ":
+        print("---------Computing Occupancy and Nucleosomal Insert Distribution----")
+        from .run_occ import run_occ
+        run_occ(args)
+    elif args.command == "nuc":
+        print("---------Obtaining nucleosome signal and calling positions----------")
+        from .run_nuc import run_nuc
+        run_nuc(args)
+    else:
+        build_parser().print_help()
+        return 2
+    print("nucleoatac %s done in %.1f s" % (args.command, time.time() - t0))
+    return 0

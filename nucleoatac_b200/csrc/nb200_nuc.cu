@@ -341,15 +341,18 @@ struct CandArgs {
 };
 
 #define CS_THREADS 256
+#define CS_GROUP 8   // candidates scored together: every VMat element is loaded once per group
 __global__ void __launch_bounds__(CS_THREADS) k_cand_stats(CandArgs a)
 {
     extern __shared__ double sm_cs[];
     __shared__ double red[32];
+    __shared__ double s_sum[4][CS_GROUP];
+    __shared__ int s_need2;
     const int uv = a.lv + a.R;
     const int half = uv / 2;
     const int nEw = a.W + 2 * half + 2;
-    double *s_E = sm_cs;         // [nEw]  E over genomic [P - w - half, ...)
-    double *s_f = sm_cs + nEw;   // [R]    f_i over the VMat's sizes
+    double *s_E = sm_cs;                      // [CS_GROUP][nEw]  E over genomic [P - w - half, ...) per candidate
+    double *s_f = sm_cs + CS_GROUP * nEw;     // [R]              f_i over the VMat's sizes
     const int nwork = a.work_count[0];
     const int tid = threadIdx.x;
     // thread layout over the R x W window: column kk, rows rr, rr + rows_par, ...
@@ -357,72 +360,125 @@ __global__ void __launch_bounds__(CS_THREADS) k_cand_stats(CandArgs a)
     const int rows_par = CS_THREADS / wcols;
     const int kk = tid % wcols, rr = tid / wcols;
     for (int i = tid; i < a.R; i += CS_THREADS) s_f[i] = a.f[a.lv + i];
-    for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
-        const int2 it = a.work[wi];
-        const int c = it.x;
-        const int64_t ci = a.cand_off[c] + it.y;
-        const int P = a.cand_pos[ci];
-        const int x = P - a.start[c];
+    for (int g0 = blockIdx.x * CS_GROUP; g0 < nwork; g0 += gridDim.x * CS_GROUP) {
+        const int ng = min(CS_GROUP, nwork - g0);
         __syncthreads();
-        if (a.use_bias) {
-            const double *Eg = a.E + (a.bias_off[c] - (int64_t)(a.seq_start[c] + a.pwm_up)) + (P - a.w - half);
-            for (int i = tid; i < nEw; i += CS_THREADS) s_E[i] = Eg[i];
+        if (tid == 0) s_need2 = 0;
+        for (int cg = 0; cg < CS_GROUP; cg++) {
+            if (cg < ng && a.use_bias) {
+                const int2 it = a.work[g0 + cg];
+                const int c = it.x;
+                const int P = a.cand_pos[a.cand_off[c] + it.y];
+                const double *Eg = a.E + (a.bias_off[c] - (int64_t)(a.seq_start[c] + a.pwm_up)) + (P - a.w - half);
+                for (int i = tid; i < nEw; i += CS_THREADS) s_E[cg * nEw + i] = Eg[i];
+            } else
+                for (int i = tid; i < nEw; i += CS_THREADS) s_E[cg * nEw + i] = a.use_bias ? 0.0 : 1.0;
         }
         __syncthreads();
-        // dense window sums: S_VB = sum V*Bp, S_B = sum f*Bp, S_BV = sum f*V*Bp, S_BV2 = sum f*V^2*Bp
-        double sVB = 0.0, sB = 0.0, sBV = 0.0, sBV2 = 0.0;
+        // ---- phase 1: S_VB = sum V*Bp and S_B = sum f*Bp  (likelihood-ratio normalisers)
+        double sVB[CS_GROUP], sB[CS_GROUP];
+#pragma unroll
+        for (int cg = 0; cg < CS_GROUP; cg++) sVB[cg] = sB[cg] = 0.0;
         if (rr < rows_par) {
             for (int k = kk; k < a.W; k += wcols) {
                 const double *Ec = s_E + half + k;
                 for (int r = rr; r < a.R; r += rows_par) {
-                    const double bp = a.use_bias ? bias_cell(Ec, a.lv + r) : 1.0;
+                    const int i = a.lv + r;
                     const double v = a.V[(size_t)r * a.W + k];
-                    const double b = __dmul_rn(bp, s_f[r]);  // normByInsertDist, chunkmat2d.py:154-156
-                    sVB = fma(v, bp, sVB);
-                    sB += b;
-                    const double bv = b * v;
-                    sBV += bv;
-                    sBV2 = fma(bv, v, sBV2);
+                    const double fr = s_f[r];
+#pragma unroll
+                    for (int cg = 0; cg < CS_GROUP; cg++) {
+                        const double bp = a.use_bias ? bias_cell(Ec + cg * nEw, i) : 1.0;
+                        sVB[cg] = fma(v, bp, sVB[cg]);
+                        sB[cg] = fma(bp, fr, sB[cg]);  // normByInsertDist, chunkmat2d.py:154-156
+                    }
                 }
             }
         }
-        sVB = block_sum(sVB, red);
-        sB = block_sum(sB, red);
-        sBV = block_sum(sBV, red);
-        sBV2 = block_sum(sBV2, red);
-        // sparse likelihoods over the fragments of the window, NucleosomeCalling.py:110-122
-        const int32_t *cp = a.col_ptr + a.col_off[c];
-        const int2 *en = a.ent + a.frag_off[c];
-        const int e0 = cp[x - a.w + a.csc_pad], e1 = cp[x + a.w + 1 + a.csc_pad];
-        const int kb = a.w - (x + a.csc_pad);
-        double nl = 0.0, ul = 0.0;
-        for (int e = e0 + tid; e < e1; e += CS_THREADS) {
-            const int2 v = en[e];
-            const int r = v.y - a.lv;
-            if (r >= 0 && r < a.R) {
-                const int k = v.x + kb;
-                const double bp = a.use_bias ? bias_cell(s_E + half + k, v.y) : 1.0;
-                nl += log(__dmul_rn(a.V[(size_t)r * a.W + k], bp) / sVB);
-                ul += log(__dmul_rn(bp, s_f[r]) / sB);
+#pragma unroll
+        for (int cg = 0; cg < CS_GROUP; cg++) {
+            const double x1 = block_sum(sVB[cg], red), x2 = block_sum(sB[cg], red);
+            if (tid == 0) {
+                s_sum[0][cg] = x1;
+                s_sum[1][cg] = x2;
             }
         }
-        nl = block_sum(nl, red);
-        ul = block_sum(ul, red);
-        if (tid == 0) {
-            double lr = a.lr_is_nan ? nb_nan() : nl - ul;  // 0*log(0) cells make both likelihoods NaN in the reference
-            int fl = a.cand_flag[ci];
-            double z = nb_nan();
-            if (lr > a.min_lr) {
-                fl |= 2;
-                const double mean = sBV / sB;
-                // calculateCov closed form r*(sum p v^2 - (sum p v)^2), r truncated to C int (multinomial_cov.pyx:20)
-                const double var = (double)(int)a.cand_cov[ci] * (sBV2 / sB - mean * mean);
-                z = a.cand_norm[ci] / sqrt(var);
-                if (z >= a.min_z) fl |= 4;
+        __syncthreads();
+        // ---- sparse likelihoods over the fragments of each window, NucleosomeCalling.py:110-122
+        for (int cg = 0; cg < ng; cg++) {
+            const int2 it = a.work[g0 + cg];
+            const int c = it.x;
+            const int64_t ci = a.cand_off[c] + it.y;
+            const int x = a.cand_pos[ci] - a.start[c];
+            const int32_t *cp = a.col_ptr + a.col_off[c];
+            const int2 *en = a.ent + a.frag_off[c];
+            const int e0 = cp[x - a.w + a.csc_pad], e1 = cp[x + a.w + 1 + a.csc_pad];
+            const int kb = a.w - (x + a.csc_pad);
+            const double cVB = s_sum[0][cg], cB = s_sum[1][cg];
+            double nl = 0.0, ul = 0.0;
+            for (int e = e0 + tid; e < e1; e += CS_THREADS) {
+                const int2 v = en[e];
+                const int r = v.y - a.lv;
+                if (r >= 0 && r < a.R) {
+                    const int k = v.x + kb;
+                    const double bp = a.use_bias ? bias_cell(s_E + cg * nEw + half + k, v.y) : 1.0;
+                    nl += log(__dmul_rn(a.V[(size_t)r * a.W + k], bp) / cVB);
+                    ul += log(__dmul_rn(bp, s_f[r]) / cB);
+                }
             }
-            a.cand_lr[ci] = lr;
-            a.cand_z[ci] = z;
-            a.cand_flag[ci] = fl;
+            nl = block_sum(nl, red);
+            ul = block_sum(ul, red);
+            if (tid == 0) {
+                const double lr = a.lr_is_nan ? nb_nan() : nl - ul;  // 0*log(0) cells make both likelihoods NaN in the reference
+                a.cand_lr[ci] = lr;
+                if (lr > a.min_lr) {
+                    a.cand_flag[ci] |= 2;
+                    s_need2 |= 1 << cg;
+                }
+            }
+        }
+        __syncthreads();
+        const int need2 = s_need2;
+        if (!need2) continue;
+        // ---- phase 2 (only where lr > min_lr): S_BV = sum f*V*Bp, S_BV2 = sum f*V^2*Bp  -> variance, z
+        double sBV[CS_GROUP], sBV2[CS_GROUP];
+#pragma unroll
+        for (int cg = 0; cg < CS_GROUP; cg++) sBV[cg] = sBV2[cg] = 0.0;
+        if (rr < rows_par) {
+            for (int k = kk; k < a.W; k += wcols) {
+                const double *Ec = s_E + half + k;
+                for (int r = rr; r < a.R; r += rows_par) {
+                    const int i = a.lv + r;
+                    const double v = a.V[(size_t)r * a.W + k];
+                    const double fr = s_f[r];
+#pragma unroll
+                    for (int cg = 0; cg < CS_GROUP; cg++) {
+                        if (need2 & (1 << cg)) {
+                            const double bp = a.use_bias ? bias_cell(Ec + cg * nEw, i) : 1.0;
+                            const double bv = __dmul_rn(bp, fr) * v;
+                            sBV[cg] += bv;
+                            sBV2[cg] = fma(bv, v, sBV2[cg]);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int cg = 0; cg < CS_GROUP; cg++) {
+            if (need2 & (1 << cg)) {
+                const double x1 = block_sum(sBV[cg], red), x2 = block_sum(sBV2[cg], red);
+                if (tid == 0) {
+                    const int2 it = a.work[g0 + cg];
+                    const int64_t ci = a.cand_off[it.x] + it.y;
+                    const double cB = s_sum[1][cg];
+                    const double mean = x1 / cB;
+                    // calculateCov closed form r*(sum p v^2 - (sum p v)^2), r truncated to C int (multinomial_cov.pyx:20)
+                    const double var = (double)(int)a.cand_cov[ci] * (x2 / cB - mean * mean);
+                    const double z = a.cand_norm[ci] / sqrt(var);
+                    a.cand_z[ci] = z;
+                    if (z >= a.min_z) a.cand_flag[ci] |= 4;
+                }
+            }
         }
     }
 }
@@ -665,7 +721,7 @@ int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
         a.min_lr = p.min_lr;
         a.min_z = p.min_z;
         ProfScope ps(ctx, b->stream, "k_cand_stats");
-        size_t smem = sizeof(double) * ((size_t)W + 2 * (uv / 2) + 2 + r.v_rows);
+        size_t smem = sizeof(double) * (CS_GROUP * ((size_t)W + 2 * (uv / 2) + 2) + r.v_rows);
         if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_cand_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_cand_stats<<<ctx->sm_count * 8, CS_THREADS, smem, b->stream>>>(a);
         NB_LAUNCH_CHECK(ctx);

@@ -1,0 +1,314 @@
+"""Host I/O without pysam/htslib: BGZF + BAM (+ .bai region fetch), .fai-indexed FASTA, BGZF
+writer, bgzip'd bedgraph reader.  Replaces what the reference gets from pysam on this path:
+``AlignmentFile.fetch`` (pyatac/fragments.pyx:21-24), ``FastaFile.fetch`` (pyatac/seq.py:17-18),
+``tabix_compress`` (nucleoatac/run_occ.py:130-136) and ``Tabixfile.fetch`` (pyatac/bedgraph.py:9-14).
+
+Only what the occ / nuc paths need is decoded: for every alignment its reference id, position,
+flag and template length; reads are filtered to ``is_proper_pair and not is_reverse`` exactly as
+fragments.pyx:25 does, and handed to the device as int32 (pos, tlen) arrays.
+"""
+import gzip
+import os
+import struct
+import zlib
+
+import numpy as np
+
+_BGZF_EOF = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+
+
+# ----------------------------------------------------------------------------------------- BGZF
+def _read_block(fh, coffset):
+    """Inflate the BGZF block at compressed offset `coffset` -> (data, size of the block on disk)."""
+    fh.seek(coffset)
+    head = fh.read(18)
+    if len(head) < 18:
+        return b"", 0
+    if head[:4] != b"\x1f\x8b\x08\x04":
+        raise ValueError("not a BGZF block at offset %d" % coffset)
+    xlen = struct.unpack_from("<H", head, 10)[0]
+    extra = head[12:18] + fh.read(xlen - 6)
+    bsize, off = None, 0
+    while off + 4 <= len(extra):
+        si1, si2, slen = extra[off], extra[off + 1], struct.unpack_from("<H", extra, off + 2)[0]
+        if si1 == 66 and si2 == 67:
+            bsize = struct.unpack_from("<H", extra, off + 4)[0] + 1
+        off += 4 + slen
+    if bsize is None:
+        raise ValueError("BGZF block without BC field")
+    cdata = fh.read(bsize - 12 - xlen - 8)
+    fh.read(8)
+    return zlib.decompress(cdata, -15), bsize
+
+
+class BgzfWriter:
+    """Write BGZF (what pysam.tabix_compress produces): <= 64 KiB deflate blocks + EOF marker."""
+
+    def __init__(self, path):
+        self.fh = open(path, "wb")
+        self.buf = bytearray()
+
+    def write(self, data):
+        if isinstance(data, str):
+            data = data.encode()
+        self.buf += data
+        while len(self.buf) >= 0xff00:
+            self._flush(self.buf[:0xff00])
+            del self.buf[:0xff00]
+
+    def _flush(self, chunk):
+        c = zlib.compressobj(6, zlib.DEFLATED, -15)
+        comp = c.compress(bytes(chunk)) + c.flush()
+        bsize = len(comp) + 25
+        self.fh.write(struct.pack("<BBBBIBBHBBHH", 31, 139, 8, 4, 0, 0, 255, 6, 66, 67, 2, bsize))
+        self.fh.write(comp)
+        self.fh.write(struct.pack("<II", zlib.crc32(bytes(chunk)) & 0xffffffff, len(chunk)))
+
+    def close(self):
+        if self.buf:
+            self._flush(self.buf)
+            self.buf = bytearray()
+        self.fh.write(_BGZF_EOF)
+        self.fh.close()
+
+
+def bgzip_file(src, dst):
+    w = BgzfWriter(dst)
+    with open(src, "rb") as fh:
+        while True:
+            block = fh.read(1 << 20)
+            if not block:
+                break
+            w.write(block)
+    w.close()
+
+
+# ----------------------------------------------------------------------------------------- BAM
+class BamFile:
+    """Coordinate-sorted BAM reader.  `fetch_fragments(chrom, start, end)` returns the int32 arrays
+    (pos, tlen) of the reads overlapping [start, end) that are proper-pair and forward."""
+
+    def __init__(self, path):
+        self.path = path
+        self.fh = open(path, "rb")
+        data, size = _read_block(self.fh, 0)
+        buf, coff = data, size
+        while len(buf) < 12 or len(buf) < 12 + struct.unpack_from("<i", buf, 4)[0] + 4:
+            d, s = _read_block(self.fh, coff)
+            buf += d
+            coff += s
+        if buf[:4] != b"BAM\x01":
+            raise ValueError("not a BAM file: %s" % path)
+        l_text = struct.unpack_from("<i", buf, 4)[0]
+        off = 8 + l_text
+        n_ref = struct.unpack_from("<i", buf, off)[0]
+        off += 4
+        self.references, self.lengths = [], []
+        for _ in range(n_ref):
+            while len(buf) < off + 4:
+                d, s = _read_block(self.fh, coff)
+                buf += d
+                coff += s
+            l_name = struct.unpack_from("<i", buf, off)[0]
+            while len(buf) < off + 8 + l_name:
+                d, s = _read_block(self.fh, coff)
+                buf += d
+                coff += s
+            self.references.append(buf[off + 4:off + 4 + l_name - 1].decode())
+            self.lengths.append(struct.unpack_from("<i", buf, off + 4 + l_name)[0])
+            off += 8 + l_name
+        self._tid = {n: i for i, n in enumerate(self.references)}
+        self._index = None
+        self._all = None
+        bai = path + ".bai" if os.path.exists(path + ".bai") else path[:-4] + ".bai"
+        if os.path.exists(bai):
+            self._index = self._read_bai(bai)
+
+    def close(self):
+        self.fh.close()
+
+    @staticmethod
+    def _read_bai(path):
+        with open(path, "rb") as fh:
+            raw = fh.read()
+        if raw[:4] != b"BAI\x01":
+            raise ValueError("not a BAI index: %s" % path)
+        n_ref = struct.unpack_from("<i", raw, 4)[0]
+        off = 8
+        linear = []
+        for _ in range(n_ref):
+            n_bin = struct.unpack_from("<i", raw, off)[0]
+            off += 4
+            for _b in range(n_bin):
+                _bin, n_chunk = struct.unpack_from("<Ii", raw, off)
+                off += 8 + 16 * n_chunk
+            n_intv = struct.unpack_from("<i", raw, off)[0]
+            off += 4
+            linear.append(np.frombuffer(raw, dtype="<u8", count=n_intv, offset=off).copy())
+            off += 8 * n_intv
+        return linear
+
+    def _records(self, voffset):
+        """Yield (tid, pos, flag, tlen, end) from virtual offset `voffset` onwards."""
+        coff, uoff = voffset >> 16, voffset & 0xffff
+        data, size = _read_block(self.fh, coff)
+        buf = data[uoff:]
+        coff += size
+        p = 0
+        while True:
+            while len(buf) - p < 4:
+                d, s = _read_block(self.fh, coff)
+                if s == 0:
+                    return
+                buf = buf[p:] + d
+                p = 0
+                coff += s
+            bs = struct.unpack_from("<i", buf, p)[0]
+            while len(buf) - p < 4 + bs:
+                d, s = _read_block(self.fh, coff)
+                if s == 0:
+                    return
+                buf = buf[p:] + d
+                p = 0
+                coff += s
+            tid, pos, _l_rn, _mq, _bin, _n_cig, flag, l_seq, _nt, _np, tlen = struct.unpack_from("<iiBBHHHiiii", buf, p + 4)
+            # end of the alignment approximated by the read length (a superset of pysam's overlap test is
+            # enough: the device re-checks every cell bound like fragments.pyx:37)
+            yield tid, pos, flag, tlen, pos + max(l_seq, 1) + 64
+            p += 4 + bs
+
+    def _fetch_indexed(self, tid, start, end):
+        lin = self._index[tid]
+        if len(lin) == 0:
+            return np.zeros(0, np.int32), np.zeros(0, np.int32)
+        w = min(max(start, 0) >> 14, len(lin) - 1)
+        voff = int(lin[w])
+        if voff == 0:  # window without reads: walk back to the previous non-empty one
+            nz = np.nonzero(lin[:w + 1])[0]
+            if len(nz) == 0:
+                nz2 = np.nonzero(lin)[0]
+                if len(nz2) == 0:
+                    return np.zeros(0, np.int32), np.zeros(0, np.int32)
+                voff = int(lin[nz2[0]])
+            else:
+                voff = int(lin[nz[-1]])
+        ps, ts = [], []
+        for rtid, pos, flag, tlen, rend in self._records(voff):
+            if rtid != tid or pos >= end:
+                break
+            if rend > start and (flag & 0x2) and not (flag & 0x10):  # fragments.pyx:25
+                ps.append(pos)
+                ts.append(tlen)
+        return np.asarray(ps, dtype=np.int32), np.asarray(ts, dtype=np.int32)
+
+    def _load_all(self):
+        per = {i: ([], []) for i in range(len(self.references))}
+        # first alignment follows the header: re-scan from the start and skip the header bytes
+        with gzip.open(self.path, "rb") as fh:
+            raw = fh.read()
+        l_text = struct.unpack_from("<i", raw, 4)[0]
+        off = 8 + l_text
+        n_ref = struct.unpack_from("<i", raw, off)[0]
+        off += 4
+        for _ in range(n_ref):
+            l_name = struct.unpack_from("<i", raw, off)[0]
+            off += 8 + l_name
+        n = len(raw)
+        while off < n:
+            bs = struct.unpack_from("<i", raw, off)[0]
+            tid, pos, _l, _m, _b, _c, flag, _ls, _nt, _np, tlen = struct.unpack_from("<iiBBHHHiiii", raw, off + 4)
+            off += 4 + bs
+            if tid >= 0 and (flag & 0x2) and not (flag & 0x10):
+                per[tid][0].append(pos)
+                per[tid][1].append(tlen)
+        self._all = {i: (np.asarray(p, dtype=np.int32), np.asarray(t, dtype=np.int32)) for i, (p, t) in per.items()}
+
+    def fetch_fragments(self, chrom, start, end):
+        if chrom not in self._tid:
+            return np.zeros(0, np.int32), np.zeros(0, np.int32)
+        tid = self._tid[chrom]
+        if self._index is not None:
+            return self._fetch_indexed(tid, max(0, start), end)
+        if self._all is None:
+            self._load_all()
+        pos, tlen = self._all[tid]
+        # without an index: a superset by position (the device re-checks every cell bound, fragments.pyx:37)
+        sel = (pos >= start - 5000) & (pos < end)
+        return pos[sel], tlen[sel]
+
+
+# ----------------------------------------------------------------------------------------- FASTA
+class FastaFile:
+    """.fai-indexed FASTA fetch (pysam.FastaFile stand-in): `.references`, `.lengths`, `.fetch`."""
+
+    def __init__(self, path):
+        self.path = path
+        self.index = {}
+        if not os.path.exists(path + ".fai"):
+            self._build_index()
+        with open(path + ".fai") as fh:
+            for line in fh:
+                name, length, offset, linebases, linewidth = line.rstrip("\n").split("\t")[:5]
+                self.index[name] = (int(length), int(offset), int(linebases), int(linewidth))
+        self.references = list(self.index.keys())
+        self.lengths = [self.index[k][0] for k in self.references]
+        self.fh = open(path, "rb")
+
+    def _build_index(self):
+        entries, name, length, offset, lb, lw, pos = [], None, 0, 0, 0, 0, 0
+        with open(self.path, "rb") as fh:
+            for line in fh:
+                if line.startswith(b">"):
+                    if name is not None:
+                        entries.append((name, length, offset, lb, lw))
+                    name, length, lb, lw = line[1:].split()[0].decode(), 0, 0, 0
+                    offset = pos + len(line)
+                else:
+                    if lb == 0:
+                        lb, lw = len(line.rstrip(b"\r\n")), len(line)
+                    length += len(line.rstrip(b"\r\n"))
+                pos += len(line)
+        if name is not None:
+            entries.append((name, length, offset, lb, lw))
+        with open(self.path + ".fai", "w") as out:
+            for e in entries:
+                out.write("\t".join(str(x) for x in e) + "\n")
+
+    def fetch(self, chrom, start, end):
+        length, offset, linebases, linewidth = self.index[chrom]
+        start, end = max(0, start), min(length, end)
+        if end <= start:
+            return ""
+        b0 = offset + (start // linebases) * linewidth + start % linebases
+        b1 = offset + ((end - 1) // linebases) * linewidth + (end - 1) % linebases + 1
+        self.fh.seek(b0)
+        return self.fh.read(b1 - b0).replace(b"\n", b"").replace(b"\r", b"").decode()
+
+    def close(self):
+        self.fh.close()
+
+
+# ----------------------------------------------------------------------------------------- bedgraph
+class BedGraphReader:
+    """bgzip'd (or plain) bedgraph; region queries by scanning per-chromosome row tables read once."""
+
+    def __init__(self, path):
+        opener = gzip.open if path.endswith(".gz") else open
+        self.rows = {}
+        with opener(path, "rt") as fh:
+            for line in fh:
+                f = line.rstrip("\n").split("\t")
+                if len(f) >= 4:
+                    self.rows.setdefault(f[0], []).append((int(f[1]), int(f[2]), float(f[3])))
+        self.tables = {c: (np.array([r[0] for r in v]), np.array([r[1] for r in v]), np.array([r[2] for r in v]))
+                       for c, v in self.rows.items()}
+
+    def read(self, chrom, start, end, empty=np.nan):
+        out = np.ones(end - start) * empty  # pyatac/bedgraph.py:10
+        if chrom not in self.tables:
+            return out
+        s, e, v = self.tables[chrom]
+        lo, hi = np.searchsorted(e, start, side="right"), np.searchsorted(s, end, side="left")
+        for i in range(lo, hi):
+            out[max(s[i] - start, 0):min(e[i] - start, end - start)] = v[i]
+        return out

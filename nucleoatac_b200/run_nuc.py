@@ -1,0 +1,70 @@
+"""`nucleoatac nuc` driver (nucleoatac/run_nuc.py:141-201): VMat + fragment sizes -> batches of chunks through the
+device -> nucpos / signal writers, in chunk order; chunk k -> GPU k mod N."""
+import os
+
+from . import hostio
+from .bias import PWM
+from .chunk import ChunkList
+from .fragmentsizes import FragmentSizes
+from .NucleosomeCalling import NucChunk, NucParameters, process_chunks
+from .utils import read_chrom_sizes_from_bam, read_chrom_sizes_from_fasta
+from .VMat import VMat
+
+
+def nuc_chunks(args, vmat):
+    chrs = read_chrom_sizes_from_fasta(args.fasta) if args.fasta else read_chrom_sizes_from_bam(args.bam)
+    pwm = PWM.open(args.pwm)
+    chunks = ChunkList.read(args.bed, chromDict=chrs,
+                            min_offset=vmat.mat.shape[1] + vmat.upper // 2 + max(pwm.up, pwm.down) + args.nuc_sep // 2,
+                            min_length=args.nuc_sep * 2)
+    chunks.slop(chrs, up=args.nuc_sep // 2, down=args.nuc_sep // 2)
+    chunks.merge()
+    return chunks
+
+
+def run_nuc(args):
+    rank, world = getattr(args, "rank", 0), getattr(args, "world", 1)
+    vmat = VMat.open(args.vmat)
+    chunks = nuc_chunks(args, vmat)
+    if args.sizes is not None:
+        fragment_dist = FragmentSizes.open(args.sizes)
+    else:
+        fragment_dist = FragmentSizes(0, upper=vmat.upper)
+        fragment_dist.calculateSizes(args.bam, chunks)
+    params = NucParameters(vmat=vmat, fragmentsizes=fragment_dist, bam=args.bam, fasta=args.fasta, pwm=args.pwm,
+                           occ_track=args.occ_track, sd=args.sd, nonredundant_sep=args.nuc_sep,
+                           redundant_sep=args.redundant_sep, min_z=args.min_z, min_lr=args.min_lr, atac=args.atac,
+                           device=getattr(args, "device", 0), xcor_mode=getattr(args, "xcor_mode", 0))
+    outputs = ["nucpos", "nucpos.redundant", "nucleoatac_signal", "nucleoatac_signal.smooth"]
+    if args.write_all:
+        outputs += ["nucleoatac_background", "nucleoatac_raw"]
+    suffix = "" if world == 1 else ".rank%d" % rank
+    ext = lambda n: ".bed" if n.startswith("nucpos") else ".bedgraph"
+    handles = {n: open(args.out + "." + n + ext(n) + suffix, "w") for n in outputs}
+    mine = ChunkList(*[c for k, c in enumerate(chunks) if k % world == rank])
+    batch = max(1, getattr(args, "batch", 256))
+    for group in mine.split(items=batch):
+        nucs = [NucChunk(c) for c in group]
+        try:
+            process_chunks(nucs, params)
+        except Exception:
+            print("Caught exception when processing:\n" + ChunkList(*group).asBed() + "\n")
+            raise
+        for nc in nucs:  # run_nuc.py:30-32: what _nucHelper returns per chunk
+            for k in sorted(int(x) for x in nc.nonredundant):
+                nc.nuc_collection[k].write(handles["nucpos"])
+            for k in sorted(int(x) for x in nc.redundant):
+                nc.nuc_collection[k].write(handles["nucpos.redundant"])
+            nc.norm_signal.write_track(handles["nucleoatac_signal"])
+            nc.smoothed.write_track(handles["nucleoatac_signal.smooth"])
+            if args.write_all:
+                nc.bias.write_track(handles["nucleoatac_background"])
+                nc.nuc_signal.write_track(handles["nucleoatac_raw"])
+            nc.removeData()
+    for h in handles.values():
+        h.close()
+    if world == 1:
+        for n in outputs:
+            plain = args.out + "." + n + ext(n)
+            hostio.bgzip_file(plain, plain + ".gz")
+            os.remove(plain)

@@ -1,0 +1,76 @@
+"""`nucleoatac occ` driver (nucleoatac/run_occ.py:77-148): BED -> chunks -> fragment-size model -> batches of chunks
+through the device -> bedgraph / bed writers.  The reference's multiprocessing pool + writer processes become: one
+process per GPU, chunk k of the list -> GPU k mod N (round-robin), results written in chunk order."""
+import os
+
+import numpy as np
+
+from . import hostio
+from .bias import PWM
+from .chunk import ChunkList
+from .fragmentsizes import FragmentSizes
+from .Occupancy import FragmentMixDistribution, OccChunk, OccupancyParameters, process_chunks
+from .utils import read_chrom_sizes_from_bam, read_chrom_sizes_from_fasta
+
+
+def _finish(path_plain, path_gz):
+    hostio.bgzip_file(path_plain, path_gz)  # pysam.tabix_compress; the .tbi index is a "next" row
+    os.remove(path_plain)
+
+
+def occ_chunks(args):
+    chrs = read_chrom_sizes_from_fasta(args.fasta) if args.fasta else read_chrom_sizes_from_bam(args.bam)
+    pwm = PWM.open(args.pwm)
+    chunks = ChunkList.read(args.bed, chromDict=chrs,
+                            min_offset=args.flank + args.upper // 2 + max(pwm.up, pwm.down) + args.nuc_sep // 2)
+    chunks.slop(chrs, up=args.nuc_sep // 2, down=args.nuc_sep // 2)
+    chunks.merge()
+    return chunks
+
+
+def run_occ(args):
+    rank, world = getattr(args, "rank", 0), getattr(args, "world", 1)
+    chunks = occ_chunks(args)
+    fragment_dist = FragmentMixDistribution(0, upper=args.upper)
+    if args.sizes is not None:
+        tmp = FragmentSizes.open(args.sizes)
+        fragment_dist.fragmentsizes = FragmentSizes(0, args.upper, vals=tmp.get(0, args.upper))
+    else:
+        fragment_dist.getFragmentSizes(args.bam, chunks)
+    fragment_dist.modelNFR()
+    if rank == 0:
+        fragment_dist.plotFits(args.out + ".occ_fit.eps")
+        fragment_dist.fragmentsizes.save(args.out + ".fragmentsizes.txt")
+    params = OccupancyParameters(fragment_dist, args.upper, args.fasta, args.pwm, sep=args.nuc_sep, min_occ=args.min_occ,
+                                 flank=args.flank, bam=args.bam, ci=args.confidence_interval, step=args.step,
+                                 device=getattr(args, "device", 0))
+    mine = ChunkList(*[c for k, c in enumerate(chunks) if k % world == rank])
+    suffix = "" if world == 1 else ".rank%d" % rank
+    names = ("occ", "occ.lower_bound", "occ.upper_bound")
+    handles = [open(args.out + "." + n + ".bedgraph" + suffix, "w") for n in names]
+    peaks_handle = open(args.out + ".occpeaks.bed" + suffix, "w")
+    nuc_dist = np.zeros(args.upper)
+    batch = max(1, getattr(args, "batch", 256))
+    for group in mine.split(items=batch):
+        occs = [OccChunk(c) for c in group]
+        try:
+            process_chunks(occs, params)
+        except Exception:
+            print("Caught exception when processing:\n" + ChunkList(*group).asBed() + "\n")
+            raise
+        for oc in occs:
+            nuc_dist += oc.getNucDist()
+            oc.occ.write_track(handles[0], vals=oc.occ.smoothed_vals)
+            oc.occ.write_track(handles[1], vals=oc.occ.smoothed_lower)
+            oc.occ.write_track(handles[2], vals=oc.occ.smoothed_upper)
+            for i in sorted(oc.peaks.keys()):
+                oc.peaks[i].write(peaks_handle)
+            oc.removeData()
+    for h in handles + [peaks_handle]:
+        h.close()
+    if world == 1:
+        _finish(args.out + ".occpeaks.bed", args.out + ".occpeaks.bed.gz")
+        for n in names:
+            _finish(args.out + "." + n + ".bedgraph", args.out + "." + n + ".bedgraph.gz")
+        FragmentSizes(0, args.upper, vals=nuc_dist).save(args.out + ".nuc_dist.txt")
+    return nuc_dist

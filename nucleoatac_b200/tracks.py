@@ -1,0 +1,119 @@
+"""Track / InsertionTrack / CoverageTrack (pyatac/tracks.py:16-242): 1-D values on [start, end)."""
+import numpy as np
+
+from .bedgraph import BedGraphFile
+from .chunk import Chunk
+from .engine import default_engine
+from .fragments import getInsertions
+from .utils import fmt12, smooth
+
+
+class Track(Chunk):
+    def __init__(self, chrom, start, end, name="track", vals=None, log=False):
+        Chunk.__init__(self, chrom, start, end, name=name)
+        self.log = log
+        if vals is not None and len(vals) != self.length():
+            raise Exception("Input vals must be of length as set by start and end!")
+        self.vals = vals
+
+    def assign_track(self, vals, start=None, end=None):
+        if start:
+            self.start = start
+        if end:
+            self.end = end
+        if len(vals) != self.end - self.start:
+            raise Exception("The values being assigned to track do not span the start to end of the track")
+        self.vals = vals
+
+    def write_track(self, handle, start=None, end=None, vals=None, write_zero=True):
+        """Run-length bedgraph text, NaN runs skipped, numbers as the reference prints them (tracks.py:37-74)."""
+        start = self.start if start is None else start
+        end = self.end if end is None else end
+        vals = self.vals if vals is None else vals
+        if len(vals) != self.end - self.start:
+            raise Exception("Error! Inconsistency between length of values and start/end values")
+        vals = np.asarray(vals, dtype=np.float64)
+        n = len(vals)
+        if n == 0:
+            return
+        isn = np.isnan(vals)
+        # a run starts where the value changes (NaN == NaN counts as "same": the reference keeps prev_value = nan)
+        change = np.ones(n, dtype=bool)
+        change[1:] = (vals[1:] != vals[:-1]) & ~(isn[1:] & isn[:-1])
+        idx = np.nonzero(change)[0]
+        ends = np.append(idx[1:], n)
+        out = []
+        for i, j in zip(idx, ends):
+            v = vals[i]
+            if v != v:
+                continue
+            if j < n and isn[j]:
+                continue  # reference quirk (tracks.py:59-60): a run that is followed by NaN is never flushed
+            if v == 0 and not write_zero:
+                continue
+            out.append("%s\t%d\t%d\t%s\n" % (self.chrom, start + i, end if j == n else start + j, fmt12(v)))
+        handle.write("".join(out))
+
+    def read_track(self, bedgraph, start=None, end=None, empty=np.nan, flank=None):
+        if start:
+            self.start = start
+        if end:
+            self.end = end
+        if flank:
+            self.start -= flank
+            self.end += flank
+        self.vals = BedGraphFile(bedgraph).read(self.chrom, self.start, self.end, empty=empty)
+
+    def exp(self):
+        self.vals = np.exp(self.vals)
+        self.log = False
+
+    def smooth_track(self, window_len, window="flat", sd=None, mode="valid", norm=True):
+        self.smoothed = True
+        self.vals = smooth(self.vals, window_len, window=window, sd=sd, mode=mode, norm=norm)
+        if mode == "valid":
+            self.start += window_len // 2
+            self.end -= window_len // 2
+
+    def get(self, start=None, end=None, pos=None):
+        if pos:  # pos == 0 falls through to the slice branch, as in the reference (tracks.py:112)
+            try:
+                return self.vals[pos - self.start]
+            except Exception:
+                raise Exception("Looks like position given doesn't match track")
+        start = self.start if start is None else start
+        end = self.end if end is None else end
+        try:
+            return self.vals[start - self.start:end - self.start]
+        except Exception:
+            raise Exception("Looks like dimensions from get probaby don't match track, or there are no vals in track")
+
+    def slop(self, chromDict, up=0, down=0, new=False):
+        lo, hi = (down, up) if self.strand == "-" else (up, down)
+        s, e = max(0, self.start - lo), min(chromDict[self.chrom], self.end + hi)
+        if new:
+            return Track(self.chrom, s, e, name=self.name)
+        self.start, self.end = s, e
+
+
+class InsertionTrack(Track):
+    def __init__(self, chrom, start, end):
+        Track.__init__(self, chrom, start, end, "insertions")
+
+    def calculateInsertions(self, bamfile, flank=0, lower=0, upper=2000, atac=True):
+        self.start -= flank
+        self.end += flank
+        self.vals = getInsertions(bamfile, self.chrom, self.start, self.end, lower, upper, atac)
+
+
+class CoverageTrack(Track):
+    def __init__(self, chrom, start, end):
+        Track.__init__(self, chrom, start, end, "coverage")
+
+    def calculateCoverage(self, mat, lower, upper, window_len):
+        """Flat-window coverage of fragment centres (tracks.py:209-222), column sums + window on the device."""
+        offset = self.start - mat.start - (window_len // 2)
+        if offset < 0:
+            raise Exception("Insufficient flanking region on mat to calculate coverage with desired window")
+        sub = mat.mat[:, offset:mat.mat.shape[1] - offset] if offset != 0 else mat.mat
+        self.vals = default_engine().coverage_dense(sub, lower - mat.lower, upper - mat.lower, window_len)

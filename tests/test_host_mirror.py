@@ -1,0 +1,119 @@
+"""CPU tests of the host-side mirror of the reference API (no device calls): BED/VMat/sizes IO, the bedgraph
+writer against the oracle's literal restatement, BGZF/BAM/FASTA readers and writers, CLI flags."""
+import gzip
+import io
+import os
+
+import numpy as np
+import pytest
+
+from nucleoatac_b200 import hostio
+from nucleoatac_b200.chunk import Chunk, ChunkList
+from oracle import refalgo as ra
+
+
+def test_chunklist_read_slop_merge_split(tmp_path):
+    bed = tmp_path / "a.bed"
+    bed.write_text("chr1\t100\t300\nchr1\t350\t500\nchr1\t5000\t5100\nchr2\t10\t90\nchrX\t1\t2\n")
+    chrs = {"chr1": 6000, "chr2": 1000}
+    with pytest.warns(UserWarning):
+        cl = ChunkList.read(str(bed), chromDict=chrs, min_offset=50)
+    assert [(c.chrom, c.start, c.end) for c in cl] == [("chr1", 100, 300), ("chr1", 350, 500), ("chr1", 5000, 5100), ("chr2", 50, 90)]
+    ref = ra.merge_chunks(ra.slop_chunks(ra.read_bed_chunks(str(bed), chrs, min_offset=50), chrs, 60, 60))
+    cl.slop(chrs, up=60, down=60)
+    cl.merge()
+    assert [[c.chrom, c.start, c.end] for c in cl] == ref
+    assert [len(x) for x in cl.split(items=2)] == [2, 1]
+    assert Chunk("c", 1, 5).asBed() == "c\t1\t5\t1\tregion\t*"
+    c = Chunk("chr1", 10, 31)
+    c.center()
+    assert (c.start, c.end) == (20, 21)
+
+
+def test_write_track_matches_reference_semantics():
+    from nucleoatac_b200.tracks import Track
+    rng = np.random.RandomState(0)
+    for trial in range(30):
+        n = 60
+        vals = np.round(rng.rand(n), 1)
+        vals[rng.rand(n) < 0.25] = np.nan
+        vals[rng.rand(n) < 0.2] = 0.0
+        if trial % 3 == 0:
+            vals[-3:] = np.nan
+        for wz in (True, False):
+            h = io.StringIO()
+            Track("chrT", 1000, 1000 + n).write_track(h, vals=vals, write_zero=wz)
+            assert h.getvalue() == ra.write_track("chrT", 1000, 1000 + n, vals, write_zero=wz), (trial, wz)
+
+
+def test_vmat_and_sizes_io(tmp_path, example):
+    from nucleoatac_b200.fragmentsizes import FragmentSizes
+    from nucleoatac_b200.VMat import VMat, VMat_Error
+    mat, lo, hi = example.vmat
+    p = str(tmp_path / "x.VMat")
+    VMat(mat, lo, hi).save(p)
+    v = VMat.open(p)
+    assert (v.lower, v.upper, v.w) == (lo, hi, mat.shape[1] // 2)
+    np.testing.assert_allclose(v.mat, mat, rtol=1e-11)
+    m2, l2, u2 = ra.read_vmat(p)
+    assert np.array_equal(m2, v.mat)
+    with pytest.raises(VMat_Error):
+        VMat(mat, lo, hi + 1)
+    # vprocess steps against the oracle restatement of pyatac/VMat.py
+    from oracle import refvmat
+    raw = example.z["std_vplot"].astype(np.float64)
+    v = VMat(np.array(raw), int(example.z["std_vplot_lower"]), int(example.z["std_vplot_upper"]))
+    v.trim(105, 251, 60)
+    v.symmetrize()
+    v.smooth(0.75)
+    v.norm()
+    np.testing.assert_allclose(v.mat, refvmat.vprocess(raw, 0, 105, 251, 60), rtol=1e-12)
+    s = str(tmp_path / "s.txt")
+    FragmentSizes(0, 251, vals=example.fragmentsizes).save(s)
+    f = FragmentSizes.open(s)
+    np.testing.assert_allclose(f.get(0, 251), example.fragmentsizes, rtol=1e-11)
+    assert f.get(size=100) == f.vals[100]
+
+
+def test_bgzf_bam_fasta_roundtrip(tmp_path):
+    from tests.synthfiles import write_bam
+    rng = np.random.RandomState(1)
+    pos = np.sort(rng.randint(100, 200000, 5000))
+    tlen = rng.randint(40, 400, 5000)
+    path = str(tmp_path / "t.bam")
+    write_bam(path, {"chrA": 250000, "chrB": 1000}, [(0, int(p), int(t)) for p, t in zip(pos, tlen)])
+    assert gzip.open(path).read(4) == b"BAM\x01"
+    bam = hostio.BamFile(path)
+    assert bam.references == ["chrA", "chrB"] and bam.lengths == [250000, 1000]
+    p, t = bam.fetch_fragments("chrA", 50000, 60000)
+    sel = (pos >= 50000) & (pos < 60000)
+    keep = p >= 50000
+    assert np.array_equal(p[keep], pos[sel]) and np.array_equal(t[keep], tlen[sel])  # forward proper-pair mates only
+    assert len(bam.fetch_fragments("chrB", 0, 1000)[0]) == 0
+    fa = tmp_path / "g.fa"
+    seq = "".join(rng.choice(list("ACGTN"), 1000))
+    fa.write_text(">c1 desc\n" + "\n".join(seq[i:i + 70] for i in range(0, 1000, 70)) + "\n>c2\nACGT\n")
+    f = hostio.FastaFile(str(fa))
+    assert f.references == ["c1", "c2"] and f.lengths == [1000, 4]
+    assert f.fetch("c1", 65, 215) == seq[65:215] and f.fetch("c2", 0, 10) == "ACGT"
+    bg = tmp_path / "t.bedgraph"
+    bg.write_text("c1\t0\t5\t1.5\nc1\t5\t9\t2.0\nc1\t20\t30\t3.0\n")
+    hostio.bgzip_file(str(bg), str(bg) + ".gz")
+    r = hostio.BedGraphReader(str(bg) + ".gz")
+    out = r.read("c1", 3, 25)
+    assert out[0] == 1.5 and out[2] == 2.0 and np.isnan(out[10]) and out[-1] == 3.0
+
+
+def test_cli_flags_match_reference():
+    from nucleoatac_b200.cli import build_parser
+    a = build_parser().parse_args("occ --bed b --bam m --out o".split())
+    assert (a.upper, a.flank, a.min_occ, a.nuc_sep, a.confidence_interval, a.step, a.pwm, a.cores) == (251, 60, 0.1, 120, 0.9, 5, "Human", 1)
+    a = build_parser().parse_args("nuc --bed b --bam m --out o --vmat v --not_atac --write_all".split())
+    assert (a.min_z, a.min_lr, a.nuc_sep, a.redundant_sep, a.sd, a.atac, a.write_all) == (3, 0, 120, 25, 10, False, True)
+
+
+def test_pwm_bundled(example):
+    from nucleoatac_b200.bias import PWM
+    p = PWM.open("Human")
+    assert (p.up, p.down, p.nucleotides) == (10, 10, ["A", "C", "G", "T"])
+    np.testing.assert_allclose(p.mat, example.pwm, rtol=1e-12)
