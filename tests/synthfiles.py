@@ -54,7 +54,7 @@ def make_files(tmpdir, ks=(2, 0, 5), R=251, W=251):
     write_bam(bam, {"chrS": length}, reads)
     bed = os.path.join(tmpdir, "regions.bed")
     with open(bed, "w") as fh:  # the drivers slop by nuc_sep/2 = 60 on both sides
-        for (s, e, *_r) in chunks:
+        for (s, e, *_r) in sorted(chunks, key=lambda c: c[0]):  # the reference requires a sorted BED (docs/nucleoatac.md:10)
             fh.write("chrS\t%d\t%d\n" % (s + 60, e - 60))
     from nucleoatac_b200.fragmentsizes import FragmentSizes
     from nucleoatac_b200.VMat import VMat
