@@ -1,6 +1,7 @@
 """Command line: `python -m nucleoatac_b200 occ|nuc ...` with the reference's flags (nucleoatac/cli.py:96-125,
 203-240) plus `--gpus`, `--batch` and `--xcor_mode`.  `--cores` is accepted and ignored (the device replaces the pool)."""
 import argparse
+import os
 import time
 
 
@@ -59,6 +60,13 @@ def build_parser():
 def nucleoatac_main(argv=None):
     args = build_parser().parse_args(argv)
     t0 = time.time()
+    if getattr(args, "world", 1) == 1 and int(os.environ.get("WORLD_SIZE", "1")) > 1:  # launched by torchrun
+        from . import dist
+        args.rank, args.world, args.device = dist.env_rank_world()
+        import torch.distributed as td
+        if not td.is_initialized():
+            import torch
+            td.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
     if args.command == "occ":
         print("---------Computing Occupancy and Nucleosomal Insert Distribution----")
         from .run_occ import run_occ

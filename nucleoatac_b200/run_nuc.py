@@ -2,7 +2,7 @@
 device -> nucpos / signal writers, in chunk order; chunk k -> GPU k mod N."""
 import os
 
-from . import hostio
+from . import dist, hostio
 from .bias import PWM
 from .chunk import ChunkList
 from .fragmentsizes import FragmentSizes
@@ -22,7 +22,7 @@ def nuc_chunks(args, vmat):
     return chunks
 
 
-def run_nuc(args):
+def run_nuc(args, score=process_chunks):
     rank, world = getattr(args, "rank", 0), getattr(args, "world", 1)
     vmat = VMat.open(args.vmat)
     chunks = nuc_chunks(args, vmat)
@@ -38,15 +38,14 @@ def run_nuc(args):
     outputs = ["nucpos", "nucpos.redundant", "nucleoatac_signal", "nucleoatac_signal.smooth"]
     if args.write_all:
         outputs += ["nucleoatac_background", "nucleoatac_raw"]
-    suffix = "" if world == 1 else ".rank%d" % rank
     ext = lambda n: ".bed" if n.startswith("nucpos") else ".bedgraph"
-    handles = {n: open(args.out + "." + n + ext(n) + suffix, "w") for n in outputs}
-    mine = ChunkList(*[c for k, c in enumerate(chunks) if k % world == rank])
+    handles = {n: dist.ShardWriter(args.out + "." + n + ext(n), rank, world) for n in outputs}
+    mine = ChunkList(*dist.shard(chunks, rank, world))
     batch = max(1, getattr(args, "batch", 256))
     for group in mine.split(items=batch):
         nucs = [NucChunk(c) for c in group]
         try:
-            process_chunks(nucs, params)
+            score(nucs, params)
         except Exception:
             print("Caught exception when processing:\n" + ChunkList(*group).asBed() + "\n")
             raise
@@ -60,11 +59,16 @@ def run_nuc(args):
             if args.write_all:
                 nc.bias.write_track(handles["nucleoatac_background"])
                 nc.nuc_signal.write_track(handles["nucleoatac_raw"])
+            for h in handles.values():
+                h.end_chunk()
             nc.removeData()
     for h in handles.values():
         h.close()
-    if world == 1:
+    dist.barrier()
+    if rank == 0:
         for n in outputs:
             plain = args.out + "." + n + ext(n)
+            dist.ShardWriter.merge(plain, world, len(chunks))
             hostio.bgzip_file(plain, plain + ".gz")
             os.remove(plain)
+    dist.barrier()

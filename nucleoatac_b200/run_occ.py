@@ -5,9 +5,10 @@ import os
 
 import numpy as np
 
-from . import hostio
+from . import dist, hostio
 from .bias import PWM
 from .chunk import ChunkList
+from .fragments import getFragmentSizesFromChunkList
 from .fragmentsizes import FragmentSizes
 from .Occupancy import FragmentMixDistribution, OccChunk, OccupancyParameters, process_chunks
 from .utils import read_chrom_sizes_from_bam, read_chrom_sizes_from_fasta
@@ -28,15 +29,19 @@ def occ_chunks(args):
     return chunks
 
 
-def run_occ(args):
+def run_occ(args, score=process_chunks, count_sizes=getFragmentSizesFromChunkList):
+    """`score(list of OccChunk, params)` fills the chunks (default: the device path); `count_sizes(chunks, bam, lower,
+    upper)` is the fragment-size histogram of a chunk list (default: host BAM decode + device binning)."""
     rank, world = getattr(args, "rank", 0), getattr(args, "world", 1)
     chunks = occ_chunks(args)
     fragment_dist = FragmentMixDistribution(0, upper=args.upper)
     if args.sizes is not None:
         tmp = FragmentSizes.open(args.sizes)
         fragment_dist.fragmentsizes = FragmentSizes(0, args.upper, vals=tmp.get(0, args.upper))
-    else:
-        fragment_dist.getFragmentSizes(args.bam, chunks)
+    else:  # fragments.pyx:122-145, one shard per rank, summed exactly (integer-valued counts)
+        counts = dist.allreduce_sum(np.asarray(count_sizes(dist.shard(chunks, rank, world), args.bam, 0, args.upper), dtype=np.float64))
+        total = np.sum(counts)
+        fragment_dist.fragmentsizes = FragmentSizes(0, args.upper, vals=counts / (total + (total == 0)))
     fragment_dist.modelNFR()
     if rank == 0:
         fragment_dist.plotFits(args.out + ".occ_fit.eps")
@@ -44,33 +49,39 @@ def run_occ(args):
     params = OccupancyParameters(fragment_dist, args.upper, args.fasta, args.pwm, sep=args.nuc_sep, min_occ=args.min_occ,
                                  flank=args.flank, bam=args.bam, ci=args.confidence_interval, step=args.step,
                                  device=getattr(args, "device", 0))
-    mine = ChunkList(*[c for k, c in enumerate(chunks) if k % world == rank])
-    suffix = "" if world == 1 else ".rank%d" % rank
+    mine = ChunkList(*dist.shard(chunks, rank, world))
     names = ("occ", "occ.lower_bound", "occ.upper_bound")
-    handles = [open(args.out + "." + n + ".bedgraph" + suffix, "w") for n in names]
-    peaks_handle = open(args.out + ".occpeaks.bed" + suffix, "w")
+    writers = [dist.ShardWriter(args.out + "." + n + ".bedgraph", rank, world) for n in names]
+    peaks_writer = dist.ShardWriter(args.out + ".occpeaks.bed", rank, world)
     nuc_dist = np.zeros(args.upper)
     batch = max(1, getattr(args, "batch", 256))
     for group in mine.split(items=batch):
         occs = [OccChunk(c) for c in group]
         try:
-            process_chunks(occs, params)
+            score(occs, params)
         except Exception:
             print("Caught exception when processing:\n" + ChunkList(*group).asBed() + "\n")
             raise
         for oc in occs:
             nuc_dist += oc.getNucDist()
-            oc.occ.write_track(handles[0], vals=oc.occ.smoothed_vals)
-            oc.occ.write_track(handles[1], vals=oc.occ.smoothed_lower)
-            oc.occ.write_track(handles[2], vals=oc.occ.smoothed_upper)
+            oc.occ.write_track(writers[0], vals=oc.occ.smoothed_vals)
+            oc.occ.write_track(writers[1], vals=oc.occ.smoothed_lower)
+            oc.occ.write_track(writers[2], vals=oc.occ.smoothed_upper)
             for i in sorted(oc.peaks.keys()):
-                oc.peaks[i].write(peaks_handle)
+                oc.peaks[i].write(peaks_writer)
+            for w in writers + [peaks_writer]:
+                w.end_chunk()
             oc.removeData()
-    for h in handles + [peaks_handle]:
-        h.close()
-    if world == 1:
+    for w in writers + [peaks_writer]:
+        w.close()
+    nuc_dist = dist.allreduce_sum(nuc_dist)  # run_occ.py:117-121 summed over the shards
+    dist.barrier()
+    if rank == 0:
+        dist.ShardWriter.merge(args.out + ".occpeaks.bed", world, len(chunks))
         _finish(args.out + ".occpeaks.bed", args.out + ".occpeaks.bed.gz")
         for n in names:
+            dist.ShardWriter.merge(args.out + "." + n + ".bedgraph", world, len(chunks))
             _finish(args.out + "." + n + ".bedgraph", args.out + "." + n + ".bedgraph.gz")
         FragmentSizes(0, args.upper, vals=nuc_dist).save(args.out + ".nuc_dist.txt")
+    dist.barrier()
     return nuc_dist
