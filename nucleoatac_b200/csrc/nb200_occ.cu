@@ -7,6 +7,8 @@
 //                  fp64, first-max argmax and the likelihood-ratio confidence bounds   (Occupancy.py:104-146)
 //   k_smooth_same  NaN-aware gaussian smoothing of the three tracks                     (Occupancy.py:147-153)
 //   k_occ_peaks    coverage, call_peaks + OccPeak filter + getNucDist, one block per chunk (Occupancy.py:221-240)
+#include <algorithm>
+
 #include "nb200_dev.cuh"
 
 // ---------------------------------------------------------------------------------------------
@@ -57,27 +59,72 @@ struct OccMleArgs {
     const int32_t *col_ptr;
     const int2 *ent;
     const double *E, *cn, *cf, *pn, *pf, *alphas;
+    double *fragbias;          // [n_frag][maxw]: window bias of every fragment for each window that contains it
     double *vals, *lower, *upper_b;
-    int pwm_up, upper, flank, step, halfstep, csc_pad, n_alpha, use_bias;
+    int pwm_up, upper, flank, step, halfstep, csc_pad, n_alpha, use_bias, maxw;
     int pn_has_zero, pf_has_zero, both_zero;
     double cutoff, sn_nobias, sf_nobias;
 };
 
+__device__ __forceinline__ int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+__device__ __forceinline__ int ceil_div(int a, int b) { return -floor_div(-a, b); }
+
+// Window bias per fragment: a fragment of size i centred at column u lies in the <= 2*flank/step + 1 windows
+// t_j = halfstep + step*j with |t_j - u| <= flank; for each of them bias = sum_{c = t_j-flank}^{t_j+flank} Bp[i,c]
+// (the `new_bias` row of Occupancy.py:139-140 for the sizes that actually occur).  One warp per fragment: products
+// over the union of its windows' columns, warp prefix sum, window sums as prefix differences.
+#define FB_WARPS 4
+#define FB_MAXCOLS 512
+__global__ void __launch_bounds__(FB_WARPS * 32) k_occ_fragbias(OccMleArgs a)
+{
+    __shared__ double s_S[FB_WARPS][FB_MAXCOLS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.y;
+    const int L = (int)(a.out_off[c + 1] - a.out_off[c]);
+    const int nwin = (L - a.halfstep + a.step - 1) / a.step;
+    const int64_t f0 = a.frag_off[c];
+    const int32_t *cp = a.col_ptr + a.col_off[c];
+    const int nent = cp[L + 2 * a.csc_pad];
+    const int2 *en = a.ent + f0;
+    const int window = 2 * a.flank + 1;
+    const double *Eg = a.E + (a.bias_off[c] - (int64_t)(a.seq_start[c] + a.pwm_up)) + a.start[c];  // E at chunk column 0
+    double *S = s_S[warp];
+    for (int e = blockIdx.x * FB_WARPS + warp; e < nent; e += gridDim.x * FB_WARPS) {
+        const int2 v = en[e];
+        const int u = v.x - a.csc_pad;  // column relative to the chunk start
+        const int jf = max(0, ceil_div(u - a.flank - a.halfstep, a.step));
+        const int jl = min(nwin - 1, floor_div(u + a.flank - a.halfstep, a.step));
+        const int nw = jl - jf + 1;
+        if (nw <= 0) continue;
+        const int c_lo = a.halfstep + a.step * jf - a.flank;  // first column of the first window
+        const int ncols = window + a.step * (nw - 1);
+        double run = 0.0;
+        for (int base = 0; base < ncols; base += 32) {
+            const int idx = base + lane;
+            double x = (idx < ncols) ? bias_cell(Eg + c_lo + idx, v.y) : 0.0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double y = __shfl_up_sync(NB_FULL, x, o);
+                if (lane >= o) x += y;
+            }
+            x += run;
+            if (idx < ncols) S[idx] = x;
+            run = __shfl_sync(NB_FULL, x, 31);
+        }
+        __syncwarp();
+        for (int w = lane; w < nw; w += 32) {
+            const int lo = a.step * w;
+            a.fragbias[(f0 + e) * a.maxw + w] = S[lo + window - 1] - (lo > 0 ? S[lo - 1] : 0.0);
+        }
+        __syncwarp();
+    }
+}
+
 #define MLE_WARPS 4
 __global__ void __launch_bounds__(MLE_WARPS * 32) k_occ_mle(OccMleArgs a)
 {
-    extern __shared__ unsigned char sm_mle[];
+    __shared__ double s_p[MLE_WARPS][32], s_q[MLE_WARPS][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int upper = a.upper;
-    // per-warp carve-up: nucp f64[upper], nfrp f64[upper], hist i32[upper], sz i32[upper], cnt i32[upper]
-    const int up2 = (upper + 1) & ~1;  // keep every per-warp slice 8-byte aligned
-    unsigned char *base = sm_mle + (size_t)warp * up2 * 28;
-    double *s_nucp = reinterpret_cast<double *>(base);
-    double *s_nfrp = s_nucp + up2;
-    int *s_hist = reinterpret_cast<int *>(s_nfrp + up2);
-    int *s_sz = s_hist + up2;
-    int *s_cnt = s_sz + up2;
-
     const int c = blockIdx.y;
     const int64_t oo = a.out_off[c];
     const int L = (int)(a.out_off[c + 1] - oo);
@@ -93,29 +140,11 @@ __global__ void __launch_bounds__(MLE_WARPS * 32) k_occ_mle(OccMleArgs a)
     const int n = e1 - e0;
     double occ = nb_nan(), lo = nb_nan(), hi = nb_nan();
     if (n > 0) {  // Occupancy.py:141 `if sum(new_inserts)>0`
-        const int2 *en = a.ent + a.frag_off[c];
-        for (int i = lane; i < upper; i += 32) s_hist[i] = 0;
-        __syncwarp();
-        for (int e = e0 + lane; e < e1; e += 32) atomicAdd(&s_hist[en[e].y], 1);
-        __syncwarp();
-        int J = 0;
-        for (int b0 = 0; b0 < upper; b0 += 32) {
-            int i = b0 + lane;
-            int v = (i < upper) ? s_hist[i] : 0;
-            unsigned m = __ballot_sync(NB_FULL, v > 0);
-            if (v > 0) {
-                int p = J + __popc(m & ((1u << lane) - 1));
-                s_sz[p] = i;
-                s_cnt[p] = v;
-            }
-            J += __popc(m);
-        }
-        __syncwarp();
+        const int64_t f0 = a.frag_off[c];
+        const int2 *en = a.ent + f0;
         double SN, SF;
-        const int g0 = a.start[c] + t - a.flank;  // genomic coordinate of the first window column
-        const double *Eg = nullptr;
         if (a.use_bias) {
-            const int64_t co = oo + 2 * (int64_t)a.flank * c + t;  // colsum index of column g0
+            const int64_t co = oo + 2 * (int64_t)a.flank * c + t;  // colsum index of the first window column
             double sn = 0.0, sf = 0.0;
             for (int k = lane; k < window; k += 32) {
                 sn += a.cn[co + k];
@@ -123,33 +152,13 @@ __global__ void __launch_bounds__(MLE_WARPS * 32) k_occ_mle(OccMleArgs a)
             }
             SN = warp_sum(sn);
             SF = warp_sum(sf);
-            Eg = a.E + (a.bias_off[c] - (int64_t)(a.seq_start[c] + a.pwm_up)) + g0;
         } else {
             SN = a.sn_nobias;
             SF = a.sf_nobias;
         }
-        for (int j = 0; j < J; j++) {
-            double bias;
-            if (a.use_bias) {
-                const int sz = s_sz[j];
-                double acc = 0.0;
-                for (int k = lane; k < window; k += 32) acc += bias_cell(Eg + k, sz);
-                bias = warp_sum(acc);
-            } else
-                bias = (double)window;
-            if (lane == 0) s_nucp[j] = bias;
-        }
-        __syncwarp();
-        for (int j = lane; j < J; j += 32) {  // nuc_probs * bias / sum, Occupancy.py:106-109 (one size per lane)
-            const int sz = s_sz[j];
-            const double bias = s_nucp[j];
-            s_nucp[j] = __dmul_rn(a.pn[sz], bias) / SN;
-            s_nfrp[j] = __dmul_rn(a.pf[sz], bias) / SF;
-        }
-        __syncwarp();
-        // log-likelihood grid; lane owns alphas lane, lane+32, ...  ll[a] = sum_s ins[s]*log(v_s(a)) is evaluated as
-        // log(prod_s v_s^ins[s]) with the product kept as (mantissa, binary exponent): one log per alpha instead of
-        // one per (alpha, size).  Rounding: ~n ulp on the product, i.e. the same order as the sum of n rounded logs.
+        // log-likelihood grid; lane owns alphas lane, lane+32, ...  ll[a] = sum_f log(v_f(a)) over the fragments of the
+        // window is evaluated as log(prod_f v_f) with the product kept as (mantissa, binary exponent): one log per
+        // alpha instead of one per (alpha, fragment).  Rounding: ~n ulp, the same order as a sum of n rounded logs.
         constexpr int NQ = NB200_MAX_ALPHA / 32;
         double al[NQ], om[NQ], mant[NQ];
         int ex[NQ];
@@ -165,27 +174,38 @@ __global__ void __launch_bounds__(MLE_WARPS * 32) k_occ_mle(OccMleArgs a)
             dead[q] = (ai >= a.n_alpha) || a.both_zero || (al[q] == 0.0 && a.pf_has_zero) || (om[q] == 0.0 && a.pn_has_zero);
         }
         int nf = 0;
-        for (int j = 0; j < J; j++) {
-            const double pj = s_nucp[j], qj = s_nfrp[j];
-            const int cj = s_cnt[j];
-            double v[NQ];
+        for (int base = e0; base < e1; base += 32) {
+            const int e = base + lane;
+            const int cnt = min(32, e1 - base);
+            if (e < e1) {  // nuc_probs * bias / sum, Occupancy.py:106-109, one fragment per lane
+                const int2 v = en[e];
+                double bias = (double)window;
+                if (a.use_bias) {
+                    const int u = v.x - a.csc_pad;
+                    const int jf = max(0, ceil_div(u - a.flank - a.halfstep, a.step));
+                    bias = a.fragbias[(f0 + e) * a.maxw + (wi - jf)];
+                }
+                s_p[warp][lane] = __dmul_rn(a.pn[v.y], bias) / SN;
+                s_q[warp][lane] = __dmul_rn(a.pf[v.y], bias) / SF;
+            }
+            __syncwarp();
+            for (int j = 0; j < cnt; j++) {
+                const double pj = s_p[warp][j], qj = s_q[warp][j];
 #pragma unroll
-            for (int q = 0; q < NQ; q++) v[q] = __dadd_rn(__dmul_rn(al[q], pj), __dmul_rn(om[q], qj));
-            for (int r = 0; r < cj; r++) {
-#pragma unroll
-                for (int q = 0; q < NQ; q++) mant[q] *= v[q];
+                for (int q = 0; q < NQ; q++) mant[q] *= __dadd_rn(__dmul_rn(al[q], pj), __dmul_rn(om[q], qj));
                 if ((++nf & 3) == 0) {  // renormalise every 4 factors (factors >= 1e-75 cannot underflow in between)
 #pragma unroll
                     for (int q = 0; q < NQ; q++) {
                         const long long bits = __double_as_longlong(mant[q]);
-                        const int e = (int)((bits >> 52) & 0x7ff);
-                        if (e != 0 && e != 0x7ff) {  // positive normal: move the exponent into ex
-                            ex[q] += e - 1023;
-                            mant[q] = __longlong_as_double(bits - ((long long)(e - 1023) << 52));
+                        const int e2 = (int)((bits >> 52) & 0x7ff);
+                        if (e2 != 0 && e2 != 0x7ff) {  // positive normal: move the exponent into ex
+                            ex[q] += e2 - 1023;
+                            mant[q] = __longlong_as_double(bits - ((long long)(e2 - 1023) << 52));
                         }
                     }
                 }
             }
+            __syncwarp();
         }
         double ll[NQ];
 #pragma unroll
@@ -490,13 +510,22 @@ int nb200_occ_run(nb200_ctx *ctx, nb200_dbatch *b)
         a.cutoff = r.cutoff;
         a.sn_nobias = r.pn_sum * window;
         a.sf_nobias = r.pf_sum * window;
-        size_t smem = (size_t)MLE_WARPS * ((p.upper + 1) & ~1) * 28;
-        if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_occ_mle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        a.maxw = (2 * p.flank) / p.step + 1;
+        a.fragbias = nullptr;
+        if (p.use_bias) {
+            if (window + 2 * p.flank > FB_MAXCOLS) return nb200_fail(ctx, NB200_ERR_ARG, "flank > %d unsupported", (FB_MAXCOLS - 1) / 4);
+            NB_CUDA(ctx, b->o_fragbias.reserve(sizeof(double) * (size_t)(b->n_frag > 0 ? b->n_frag : 1) * a.maxw));
+            a.fragbias = b->o_fragbias.as<double>();
+            ProfScope ps(ctx, b->stream, "k_occ_fragbias");
+            dim3 gridf((unsigned)std::max<int64_t>(1, std::min<int64_t>(64, div_up64(b->n_frag / n + 1, FB_WARPS))), n);
+            k_occ_fragbias<<<gridf, FB_WARPS * 32, 0, b->stream>>>(a);
+            NB_LAUNCH_CHECK(ctx);
+        }
         int max_win = (b->max_len - halfstep + p.step - 1) / p.step;
         if (max_win < 1) max_win = 1;
         ProfScope ps(ctx, b->stream, "k_occ_mle");
         dim3 grid((unsigned)div_up64(max_win, MLE_WARPS), n);
-        k_occ_mle<<<grid, MLE_WARPS * 32, smem, b->stream>>>(a);
+        k_occ_mle<<<grid, MLE_WARPS * 32, 0, b->stream>>>(a);
         NB_LAUNCH_CHECK(ctx);
     }
     {
