@@ -28,15 +28,19 @@
 
 #include "nb200_dev.cuh"
 
-#define TC_XT 4
+#define TC_XT 2
 #define TC_M 128
 #define TC_TX (TC_XT * TC_M)
-#define TC_N 64
+#define TC_N 128
 #define TC_KS 64
-#define TC_STAGES 6
+#define TC_STAGES 4
 #define TC_PART_BYTES (TC_N * TC_KS * 2)
 #define TC_STAGE_BYTES (2 * TC_PART_BYTES)
-#define TC_THREADS 192
+#define TC_EPI_WARPS (4 * TC_XT)       // 4 warps (one TMEM lane quarter each) per x-tile
+#define TC_WARP_PROD TC_EPI_WARPS
+#define TC_WARP_MMA (TC_EPI_WARPS + 1)
+#define TC_THREADS (32 * (TC_EPI_WARPS + 2))
+#define TC_LBO_B (TC_N * 16)          // bytes between the two 16-byte K chunks of a K16 block in a G stage image
 
 struct TcPlan {
     bool ok = false;
@@ -120,6 +124,19 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same, descriptors given as (low word, high word): the issuing thread only does 32-bit adds on the low word
+__device__ __forceinline__ void tc_mma_f16_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                             uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 8x16B core matrices,
 // SBO = byte stride between 8-row groups, LBO = byte stride between the 16-byte K chunks, version 1 (sm_100).
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo)
@@ -173,6 +190,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
     unsigned char *s_zlo = p;              p += (size_t)nZ * 128;
     double *s_E = reinterpret_cast<double *>(p);            // [span] E over genomic [g0 + gmin, ...)
     p += sizeof(double) * a.span;
+    double *s_t1 = reinterpret_cast<double *>(p);           // [W] f_1 * V[1,:] (size-1 fragments)
+    p += sizeof(double) * a.W;
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(p);      // full[S], empty[S], tmem_full[2], tmem_empty[2]
     p += sizeof(uint64_t) * (2 * TC_STAGES + 4);
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(p);
@@ -187,11 +206,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(bar_tfull + 8 * i, 1);
-            mbar_init(bar_tempty + 8 * i, 4);
+            mbar_init(bar_tempty + 8 * i, TC_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) {  // TMEM: all 512 columns (one CTA per SM by __launch_bounds__ + shared memory footprint)
+    if (warp == TC_WARP_MMA) {  // TMEM: all 512 columns (one CTA per SM by __launch_bounds__ + shared memory footprint)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(s_tmem)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -204,6 +223,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
             const int64_t idx = eb + g0 + i;
             s_E[i] = (idx >= e_lo && idx < e_hi) ? a.E[idx] : 0.0;
         }
+        if (a.has_row1)
+            for (int i = threadIdx.x; i < a.W; i += TC_THREADS) s_t1[i] = a.t_row1[i];
     }
     __syncthreads();
     // A operand: Z[t][s][0..7] = fp16 hi/lo of scale * E[b-window start + 8t + s + j]
@@ -234,7 +255,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
 
-    if (warp == 4) {
+    if (warp == TC_WARP_PROD) {
         // ===== producer: stream the G stages (hi + lo, 16 KB) through the ring =====
         if (lane == 0) {
             for (int s = 0; s < a.n_stages; s++) {
@@ -246,11 +267,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
                          bar_full + 8 * slot);
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == TC_WARP_MMA) {
         // ===== MMA issuer =====
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);  // f16 x f16 -> f32
-            const uint32_t zhi = smem_u32(s_zhi), zlo = smem_u32(s_zlo);
+            // descriptor words: low = start address >> 4 | (LBO >> 4) << 16, high = SBO >> 4 | version 1 << 14
+            const uint32_t desc_hi = (128u >> 4) | (1u << 14);                                // SBO = 128 B for both operands
+            const uint32_t a_hi0 = ((smem_u32(s_zhi) >> 4) & 0x3FFF) | ((128u >> 4) << 16);   // Hankel view: LBO = SBO = 128 B
+            const uint32_t a_lo0 = ((smem_u32(s_zlo) >> 4) & 0x3FFF) | ((128u >> 4) << 16);
             for (int s = 0; s < a.n_stages; s++) {
                 const int4 st = a.tab[s];
                 const int q = st.x, kblk0 = st.y, nblk = st.z;
@@ -265,70 +289,69 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
                 mbar_wait(bar_full + 8 * slot, ph);
                 tc_fence_after();
                 const uint32_t sb = smem_u32(s_stage + (size_t)slot * TC_STAGE_BYTES);
+                uint32_t bh = ((sb >> 4) & 0x3FFF) | ((uint32_t)(TC_LBO_B >> 4) << 16);
+                uint32_t ah = a_hi0 + (uint32_t)(2 * kblk0) * 8, al = a_lo0 + (uint32_t)(2 * kblk0) * 8;
+                const uint32_t d0 = tmem + (uint32_t)(buf * (TC_XT * TC_N));
+                uint32_t acc0 = first ? 0u : 1u;
                 for (int t = 0; t < nblk; t++) {
-                    const uint64_t b_hi = tc_smem_desc(sb + t * 2048, 1024, 128);
-                    const uint64_t b_lo = tc_smem_desc(sb + TC_PART_BYTES + t * 2048, 1024, 128);
+                    const uint32_t bl = bh + (TC_PART_BYTES >> 4);
 #pragma unroll
                     for (int j = 0; j < TC_XT; j++) {
-                        const uint32_t zoff = (uint32_t)(16 * j + 2 * (kblk0 + t)) * 128;
-                        const uint64_t a_hi = tc_smem_desc(zhi + zoff, 128, 128);
-                        const uint64_t a_lo = tc_smem_desc(zlo + zoff, 128, 128);
-                        const uint32_t d = tmem + (uint32_t)(buf * (TC_XT * TC_N) + j * TC_N);
-                        tc_mma_f16(d, a_hi, b_hi, idesc, (first && t == 0) ? 0u : 1u);
-                        tc_mma_f16(d, a_hi, b_lo, idesc, 1u);
-                        tc_mma_f16(d, a_lo, b_hi, idesc, 1u);
+                        const uint32_t d = d0 + (uint32_t)(j * TC_N);
+                        tc_mma_f16_w(d, ah + 128u * j, desc_hi, bh, desc_hi, idesc, acc0);   // hi * hi
+                        tc_mma_f16_w(d, ah + 128u * j, desc_hi, bl, desc_hi, idesc, 1u);     // hi * lo
+                        tc_mma_f16_w(d, al + 128u * j, desc_hi, bh, desc_hi, idesc, 1u);     // lo * hi
                     }
+                    acc0 = 1u;
+                    bh += (2 * TC_LBO_B) >> 4;   // next K16 block of the stage
+                    ah += 16;                    // Hankel view advances by 16 elements = 2 chunks of 128 B
+                    al += 16;
                 }
                 tc_commit(bar_empty + 8 * slot);               // smem slot reusable once these MMAs retire
                 if (last) tc_commit(bar_tfull + 8 * buf);      // slab q of H complete in TMEM
             }
         }
     } else {
-        // ===== epilogue: bx[x] += sum_n E[x + A0 + 64 q + n] * H[x, 64 q + n] =====
-        const int m = warp * 32 + lane;                        // TMEM lane = output position within the x-tile
+        // ===== epilogue: bx[x] = sum_n E[x + A0 + n] * H[x, n]; warps 4j..4j+3 own x-tile j (one TMEM lane quarter each)
+        const int j = warp >> 2, wq = warp & 3;
+        const int m = wq * 32 + lane;                          // TMEM lane = output position within the x-tile
         const int aoff = a.A0 - a.gmin;
-        double acc[TC_XT];
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};                  // independent chains: the fp64 pipe is latency bound otherwise
+        if (a.has_row1) {  // insert size 1: Bp[1,c] = E[c] (one tap) -> plain 1-D correlation, done while the MMAs start
+            const double *Ew = s_E + (TC_M * j + m - a.w - a.gmin);
+            int k = 0;
+            for (; k + 4 <= a.W; k += 4) {
 #pragma unroll
-        for (int j = 0; j < TC_XT; j++) acc[j] = 0.0;
+                for (int u = 0; u < 4; u++) acc[u] = fma(s_t1[k + u], Ew[k + u], acc[u]);
+            }
+            for (; k < a.W; k++) acc[0] = fma(s_t1[k], Ew[k], acc[0]);
+        }
+        const double lin = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+        acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
         for (int q = 0; q < a.n_achunks; q++) {
             const int buf = q & 1;
             mbar_wait(bar_tfull + 8 * buf, (q >> 1) & 1);
             tc_fence_after();
+            const double *Ew = s_E + aoff + TC_M * j + m + TC_N * q;
 #pragma unroll
-            for (int j = 0; j < TC_XT; j++) {
-                const double *Ew = s_E + aoff + TC_M * j + m + TC_N * q;
+            for (int h = 0; h < TC_N / 32; h++) {
+                uint32_t r[32];
+                tc_ld32(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * (TC_XT * TC_N) + j * TC_N + 32 * h), r);
+                tc_wait_ld();
 #pragma unroll
-                for (int h = 0; h < TC_N / 32; h++) {
-                    uint32_t r[32];
-                    tc_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * (TC_XT * TC_N) + j * TC_N + 32 * h), r);
-                    tc_wait_ld();
-#pragma unroll
-                    for (int n = 0; n < 32; n++) acc[j] = fma((double)__uint_as_float(r[n]), Ew[32 * h + n], acc[j]);
-                }
+                for (int n = 0; n < 32; n++) acc[n & 3] = fma((double)__uint_as_float(r[n]), Ew[32 * h + n], acc[n & 3]);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
         }
         const double unscale = ldexp(1.0, -(sE + a.sG));
-#pragma unroll
-        for (int j = 0; j < TC_XT; j++) {
-            const int x = x0 + TC_M * j + m;
-            if (x < L) {
-                double v = acc[j] * unscale;
-                if (a.has_row1) {  // insert size 1: Bp[1,c] = E[c] (one tap) -> plain 1-D correlation
-                    const double *Ew = s_E + (TC_M * j + m - a.w - a.gmin);
-                    double lin = 0.0;
-                    for (int k = 0; k < a.W; k++) lin = fma(a.t_row1[k], Ew[k], lin);
-                    v += lin;
-                }
-                a.bx[oo + x] = v;
-            }
-        }
+        const int x = x0 + TC_M * j + m;
+        if (x < L) a.bx[oo + x] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) * unscale + lin;
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == TC_WARP_MMA) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
     }
@@ -496,7 +519,7 @@ int nb200_nuc_bx_tc(nb200_ctx *ctx, nb200_dbatch *b)
     a.W = r.v_cols;
     a.w = r.v_w;
     const int nZ = (TC_TX + pl->NBp) / 8;
-    size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 2 * (size_t)nZ * 128 + sizeof(double) * pl->span + 8 * (2 * TC_STAGES + 4) + 16;
+    size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 2 * (size_t)nZ * 128 + sizeof(double) * (pl->span + r.v_cols) + 8 * (2 * TC_STAGES + 4) + 16;
     smem = (smem + 127) / 128 * 128;
     if (smem > 227 * 1024) return nb200_fail(ctx, NB200_ERR_ARG, "VMat too large for the tcgen05 background kernel");
     NB_CUDA(ctx, cudaFuncSetAttribute(k_nuc_bx_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
