@@ -33,7 +33,9 @@
 #define TC_TX (TC_XT * TC_M)
 #define TC_N 128
 #define TC_KS 64
-#define TC_STAGES 4
+#define TC_STAGES 2
+#define TC_BUFS 1                         // TMEM accumulator buffers per CTA (two CTAs per SM overlap each other instead)
+#define TC_TMEM_COLS (TC_BUFS * TC_XT * TC_N)
 #define TC_PART_BYTES (TC_N * TC_KS * 2)
 #define TC_STAGE_BYTES (2 * TC_PART_BYTES)
 #define TC_EPI_WARPS (4 * TC_XT)       // 4 warps (one TMEM lane quarter each) per x-tile
@@ -172,7 +174,7 @@ struct TcArgs {
     int pwm_up, A0, B0, NAp, NBp, gmin, span, n_stages, n_achunks, sG, has_row1, W, w;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
+__global__ void __launch_bounds__(TC_THREADS, 512 / TC_TMEM_COLS) k_nuc_bx_tc(TcArgs a)
 {
     extern __shared__ __align__(128) unsigned char sm_tc[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -192,11 +194,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
     p += sizeof(double) * a.span;
     double *s_t1 = reinterpret_cast<double *>(p);           // [W] f_1 * V[1,:] (size-1 fragments)
     p += sizeof(double) * a.W;
-    uint64_t *s_bar = reinterpret_cast<uint64_t *>(p);      // full[S], empty[S], tmem_full[2], tmem_empty[2]
-    p += sizeof(uint64_t) * (2 * TC_STAGES + 4);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(p);      // full[S], empty[S], tmem_full[BUFS], tmem_empty[BUFS]
+    p += sizeof(uint64_t) * (2 * TC_STAGES + 2 * TC_BUFS);
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(p);
     const uint32_t bar_full = smem_u32(s_bar), bar_empty = bar_full + 8 * TC_STAGES, bar_tfull = bar_empty + 8 * TC_STAGES,
-                   bar_tempty = bar_tfull + 16;
+                   bar_tempty = bar_tfull + 8 * TC_BUFS;
 
     // ---- one-time setup
     if (threadIdx.x == 0) {
@@ -204,14 +206,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
             mbar_init(bar_full + 8 * i, 1);
             mbar_init(bar_empty + 8 * i, 1);
         }
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < TC_BUFS; i++) {
             mbar_init(bar_tfull + 8 * i, 1);
             mbar_init(bar_tempty + 8 * i, TC_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == TC_WARP_MMA) {  // TMEM: all 512 columns (one CTA per SM by __launch_bounds__ + shared memory footprint)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(s_tmem)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(TC_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // E window (fp64) -> shared; out of track -> 0 (only reached under zero columns of G / unused outputs)
@@ -279,11 +281,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
                 const int4 st = a.tab[s];
                 const int q = st.x, kblk0 = st.y, nblk = st.z;
                 const bool first = st.w & 1, last = st.w & 2;
-                const int buf = q & 1;
+                const int buf = q % TC_BUFS;
                 const int slot = s % TC_STAGES;
                 const uint32_t ph = (s / TC_STAGES) & 1;
                 if (first) {
-                    mbar_wait(bar_tempty + 8 * buf, ((q >> 1) & 1) ^ 1);
+                    mbar_wait(bar_tempty + 8 * buf, ((q / TC_BUFS) & 1) ^ 1);
                     tc_fence_after();
                 }
                 mbar_wait(bar_full + 8 * slot, ph);
@@ -329,8 +331,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
         const double lin = (acc[0] + acc[1]) + (acc[2] + acc[3]);
         acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
         for (int q = 0; q < a.n_achunks; q++) {
-            const int buf = q & 1;
-            mbar_wait(bar_tfull + 8 * buf, (q >> 1) & 1);
+            const int buf = q % TC_BUFS;
+            mbar_wait(bar_tfull + 8 * buf, (q / TC_BUFS) & 1);
             tc_fence_after();
             const double *Ew = s_E + aoff + TC_M * j + m + TC_N * q;
 #pragma unroll
@@ -353,7 +355,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
     __syncthreads();
     if (warp == TC_WARP_MMA) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS) : "memory");
     }
 }
 
@@ -519,7 +521,7 @@ int nb200_nuc_bx_tc(nb200_ctx *ctx, nb200_dbatch *b)
     a.W = r.v_cols;
     a.w = r.v_w;
     const int nZ = (TC_TX + pl->NBp) / 8;
-    size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 2 * (size_t)nZ * 128 + sizeof(double) * (pl->span + r.v_cols) + 8 * (2 * TC_STAGES + 4) + 16;
+    size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 2 * (size_t)nZ * 128 + sizeof(double) * (pl->span + r.v_cols) + 8 * (2 * TC_STAGES + 2 * TC_BUFS) + 16;
     smem = (smem + 127) / 128 * 128;
     if (smem > 227 * 1024) return nb200_fail(ctx, NB200_ERR_ARG, "VMat too large for the tcgen05 background kernel");
     NB_CUDA(ctx, cudaFuncSetAttribute(k_nuc_bx_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
