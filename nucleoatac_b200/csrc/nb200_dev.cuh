@@ -157,16 +157,26 @@ __device__ __forceinline__ int block_compact_slot(int flag, int *base_sh, int *r
 // grid (tiles, chunks, tracks); block SM_TILE threads; dynamic smem (SM_TILE + 2*wlen) doubles.
 // ---------------------------------------------------------------------------------------------
 #define SM_TILE 256
+#define SM_XT 4
+#define SM_THREADS (SM_TILE / SM_XT)
 struct SmoothTracks {
     const double *in[3];
     double *out[3];
 };
-static __global__ void __launch_bounds__(SM_TILE) k_smooth_same(SmoothTracks tr, const int64_t *__restrict__ out_off,
-                                                         const double *__restrict__ win, int wlen, int clip_neg)
+// Each thread owns SM_XT consecutive outputs and slides a register window over the taps; the tile is stored
+// SM_XT-way interleaved in shared memory (element e at (e % XT) * Q + e / XT) so those reads are conflict free.
+// Tiles without NaN / zero padding take the fast path (denominator = sum of the window, as np.convolve of the
+// window with an all-ones indicator gives); the others evaluate the NaN-aware form tap by tap.
+static __global__ void __launch_bounds__(SM_THREADS) k_smooth_same(SmoothTracks tr, const int64_t *__restrict__ out_off,
+                                                                 const double *__restrict__ win, int wlen, int clip_neg)
 {
     extern __shared__ double sm_s[];
-    double *s_w = sm_s;                 // [wlen]
-    double *s_x = sm_s + wlen;          // [SM_TILE + wlen - 1]
+    __shared__ int s_slow;
+    const int wpad = (wlen + SM_XT - 1) / SM_XT * SM_XT;
+    const int nX = SM_TILE + wpad;                       // elements staged per tile (multiple of XT)
+    const int Q = nX / SM_XT;
+    double *s_w = sm_s;                 // [wpad] window, zero padded
+    double *s_x = sm_s + wpad;          // [nX] interleaved
     const int c = blockIdx.y;
     const int64_t o = out_off[c];
     const int L = (int)(out_off[c + 1] - o);
@@ -175,29 +185,79 @@ static __global__ void __launch_bounds__(SM_TILE) k_smooth_same(SmoothTracks tr,
     const double *in = tr.in[blockIdx.z] + o;
     double *out = tr.out[blockIdx.z] + o;
     const int h = (wlen - 1) / 2;
-    for (int i = threadIdx.x; i < wlen; i += blockDim.x) s_w[i] = win[i];
-    // s_x[j] = x[x0 - (wlen-1-h) + j]  (index range needed: n+h-m for m in [0,wlen))
-    const int lo = x0 + h - (wlen - 1);
-    for (int j = threadIdx.x; j < SM_TILE + wlen - 1; j += blockDim.x) {
-        int idx = lo + j;
-        double v = (idx >= 0 && idx < L) ? in[idx] : 0.0;   // zero padding; NaN kept as NaN marker
-        if (clip_neg && v < 0) v = 0.0;
-        s_x[j] = v;
-    }
+    if (threadIdx.x == 0) s_slow = 0;
+    for (int i = threadIdx.x; i < wpad; i += blockDim.x) s_w[i] = (i < wlen) ? win[i] : 0.0;
     __syncthreads();
-    const int n = x0 + threadIdx.x;
-    if (n >= L) return;
-    double num = 0.0, den = 0.0;
-    for (int m = 0; m < wlen; m++) {
-        int idx = n + h - m;            // global index
-        double v = s_x[idx - lo];
-        double w = s_w[m];
-        if (idx >= 0 && idx < L && v == v) {
-            num += w * v;
-            den += w;
+    // s_x element j <-> global index lo + j; the taps of output n are indices n + h - m, m in [0, wlen)
+    const int lo = x0 + h - (wpad - 1);
+    int slow = 0;
+    for (int j = threadIdx.x; j < nX; j += blockDim.x) {
+        const int idx = lo + j;
+        double v = nb_nan();
+        if (idx >= 0 && idx < L) {
+            v = in[idx];
+            if (clip_neg && v < 0) v = 0.0;
+        }
+        if (v != v) {
+            if (idx > x0 + h - wlen && idx < min(x0 + SM_TILE, L) + h) slow = 1;  // a real tap of this tile is missing
+            else v = 0.0;                                                          // only ever multiplied by padded (zero) taps
+        }
+        s_x[(j % SM_XT) * Q + j / SM_XT] = v;
+    }
+    if (slow) s_slow = 1;
+    __syncthreads();
+    const int n0 = x0 + threadIdx.x * SM_XT;
+    if (n0 >= L) return;
+    if (!s_slow) {
+        double den = 0.0;
+        for (int m = 0; m < wlen; m++) den += s_w[m];
+        double acc[SM_XT], wv[SM_XT];
+#pragma unroll
+        for (int u = 0; u < SM_XT; u++) acc[u] = 0.0;
+        // window registers hold elements e0 + u, e0 = (n0 + h - m) - lo for the current tap group
+        const int t = threadIdx.x;
+        int e0 = n0 + h - lo;            // multiple of XT offset: (x0 + t*XT + h) - (x0 + h - wpad + 1) = t*XT + wpad - 1
+#pragma unroll
+        for (int u = 0; u < SM_XT; u++) {
+            const int e = e0 + u;
+            wv[u] = s_x[(e % SM_XT) * Q + e / SM_XT];
+        }
+        for (int m0 = 0; m0 < wpad; m0 += SM_XT) {
+            double nw[SM_XT];
+#pragma unroll
+            for (int mm = 0; mm < SM_XT; mm++) {
+                const double w = s_w[m0 + mm];
+#pragma unroll
+                for (int u = 0; u < SM_XT; u++) {
+                    const int wi = u - mm;
+                    acc[u] = fma(w, wi >= 0 ? wv[wi] : nw[-wi - 1], acc[u]);
+                }
+                const int e = e0 - m0 - mm - 1;   // next lower element
+                nw[mm] = (e >= 0) ? s_x[(e % SM_XT) * Q + e / SM_XT] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < SM_XT; u++) wv[u] = nw[SM_XT - 1 - u];
+        }
+#pragma unroll
+        for (int u = 0; u < SM_XT; u++)
+            if (n0 + u < L) out[n0 + u] = acc[u] / den;
+        (void)t;
+    } else {
+        for (int u = 0; u < SM_XT; u++) {
+            const int n = n0 + u;
+            if (n >= L) break;
+            double num = 0.0, den = 0.0;
+            for (int m = 0; m < wlen; m++) {
+                const int e = n + h - m - lo;
+                const double v = s_x[(e % SM_XT) * Q + e / SM_XT];
+                if (v == v) {
+                    num += s_w[m] * v;
+                    den += s_w[m];
+                }
+            }
+            out[n] = (den == 0.0) ? nb_nan() : num / den;
         }
     }
-    out[n] = (den == 0.0) ? nb_nan() : num / den;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -40,7 +40,13 @@ __global__ void __launch_bounds__(NC_TILE) k_nuc_colsums(const int32_t *__restri
     if (j >= ncol) return;
     const double *Ec = s_E + half + threadIdx.x;
     double acc = 0.0;
-    for (int i = lv; i < uv; i++) acc += s_f[i] * bias_cell(Ec, i);
+    double ea = Ec[-((lv - 1) >> 1)], eb = Ec[lv >> 1];  // consecutive sizes share one tap
+    for (int i = lv; i < uv; i++) {
+        acc += s_f[i] * ((i == 1) ? ea : ea * eb);
+        const int in = i + 1;
+        if (in & 1) ea = Ec[-((in - 1) >> 1)];
+        else eb = Ec[in >> 1];
+    }
     cB[out_off[c] + 2 * (int64_t)w * c + j] = acc;
 }
 
@@ -382,15 +388,45 @@ __global__ void __launch_bounds__(CS_THREADS) k_cand_stats(CandArgs a)
         if (rr < rows_par) {
             for (int k = kk; k < a.W; k += wcols) {
                 const double *Ec = s_E + half + k;
-                for (int r = rr; r < a.R; r += rows_par) {
-                    const int i = a.lv + r;
-                    const double v = a.V[(size_t)r * a.W + k];
-                    const double fr = s_f[r];
+                if (rows_par == 1 && a.use_bias) {
+                    // one thread walks all insert sizes of its column: consecutive sizes share a tap
+                    // (i -> i+1 moves the left tap when i+1 is odd, the right tap when it is even)
+                    double ea[CS_GROUP], eb[CS_GROUP];
+                    int i = a.lv;
 #pragma unroll
                     for (int cg = 0; cg < CS_GROUP; cg++) {
-                        const double bp = a.use_bias ? bias_cell(Ec + cg * nEw, i) : 1.0;
-                        sVB[cg] = fma(v, bp, sVB[cg]);
-                        sB[cg] = fma(bp, fr, sB[cg]);  // normByInsertDist, chunkmat2d.py:154-156
+                        ea[cg] = Ec[cg * nEw - ((i - 1) >> 1)];
+                        eb[cg] = Ec[cg * nEw + (i >> 1)];
+                    }
+                    for (int r = 0; r < a.R; r++, i++) {
+                        const double v = a.V[(size_t)r * a.W + k];
+                        const double fr = s_f[r];
+#pragma unroll
+                        for (int cg = 0; cg < CS_GROUP; cg++) {
+                            const double bp = (i == 1) ? ea[cg] : ea[cg] * eb[cg];
+                            sVB[cg] = fma(v, bp, sVB[cg]);
+                            sB[cg] = fma(bp, fr, sB[cg]);  // normByInsertDist, chunkmat2d.py:154-156
+                        }
+                        const int in = i + 1;
+                        if (in & 1) {
+#pragma unroll
+                            for (int cg = 0; cg < CS_GROUP; cg++) ea[cg] = Ec[cg * nEw - ((in - 1) >> 1)];
+                        } else {
+#pragma unroll
+                            for (int cg = 0; cg < CS_GROUP; cg++) eb[cg] = Ec[cg * nEw + (in >> 1)];
+                        }
+                    }
+                } else {
+                    for (int r = rr; r < a.R; r += rows_par) {
+                        const int i = a.lv + r;
+                        const double v = a.V[(size_t)r * a.W + k];
+                        const double fr = s_f[r];
+#pragma unroll
+                        for (int cg = 0; cg < CS_GROUP; cg++) {
+                            const double bp = a.use_bias ? bias_cell(Ec + cg * nEw, i) : 1.0;
+                            sVB[cg] = fma(v, bp, sVB[cg]);
+                            sB[cg] = fma(bp, fr, sB[cg]);
+                        }
                     }
                 }
             }
@@ -644,11 +680,11 @@ int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
         SmoothTracks tr;
         tr.in[0] = tr.in[1] = tr.in[2] = b->n_norm.as<double>();
         tr.out[0] = tr.out[1] = tr.out[2] = b->n_smooth.as<double>();
-        size_t smem = sizeof(double) * (SM_TILE + 2 * (size_t)p.smooth_len);
+        size_t smem = sizeof(double) * (SM_TILE + 2 * (size_t)p.smooth_len + 16);
         if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_smooth_same, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ProfScope ps(ctx, b->stream, "k_smooth_same");
         dim3 grid((unsigned)div_up64(b->max_len, SM_TILE), n, 1);
-        k_smooth_same<<<grid, SM_TILE, smem, b->stream>>>(tr, b->d_out_off.as<int64_t>(), r.nuc_win.as<double>(), p.smooth_len, 1);
+        k_smooth_same<<<grid, SM_THREADS, smem, b->stream>>>(tr, b->d_out_off.as<int64_t>(), r.nuc_win.as<double>(), p.smooth_len, 1);
         NB_LAUNCH_CHECK(ctx);
     }
     {

@@ -41,10 +41,14 @@ __global__ void __launch_bounds__(OC_TILE) k_occ_colsums(const int32_t *__restri
     if (j >= ncol) return;
     const double *Ec = s_E + half + threadIdx.x;
     double an = 0.0, af = 0.0;
+    double ea = Ec[1], eb = Ec[0];  // i = 0: taps c+1 and c; consecutive sizes share one tap
     for (int i = 0; i < upper; i++) {
-        double bp = bias_cell(Ec, i);
+        const double bp = (i == 1) ? ea : ea * eb;
         an += s_pn[i] * bp;
         af += s_pf[i] * bp;
+        const int in = i + 1;
+        if (in & 1) ea = Ec[-((in - 1) >> 1)];
+        else eb = Ec[in >> 1];
     }
     const int64_t o = out_off[c] + 2 * (int64_t)flank * c + j;
     cn[o] = an;
@@ -536,11 +540,11 @@ int nb200_occ_run(nb200_ctx *ctx, nb200_dbatch *b)
         tr.out[0] = b->o_svals.as<double>();
         tr.out[1] = b->o_slower.as<double>();
         tr.out[2] = b->o_supper.as<double>();
-        size_t smem = sizeof(double) * (SM_TILE + 2 * (size_t)p.smooth_len);
+        size_t smem = sizeof(double) * (SM_TILE + 2 * (size_t)p.smooth_len + 16);
         if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_smooth_same, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ProfScope ps(ctx, b->stream, "k_smooth_same");
         dim3 grid((unsigned)div_up64(b->max_len, SM_TILE), n, 3);
-        k_smooth_same<<<grid, SM_TILE, smem, b->stream>>>(tr, b->d_out_off.as<int64_t>(), r.occ_win.as<double>(), p.smooth_len, 0);
+        k_smooth_same<<<grid, SM_THREADS, smem, b->stream>>>(tr, b->d_out_off.as<int64_t>(), r.occ_win.as<double>(), p.smooth_len, 0);
         NB_LAUNCH_CHECK(ctx);
     }
     {
