@@ -185,7 +185,7 @@ struct nb200_dbatch {
     bool occ_done = false;
     int occ_upper = 0;
     // nuc outputs (device)
-    DevBuf n_signal, n_bg, n_norm, n_smooth, n_nuc_cov, n_nfr_cov, n_bx, n_bcov, n_cB;
+    DevBuf n_signal, n_bg, n_norm, n_smooth, n_nuc_cov, n_nfr_cov, n_bx, n_bcov, n_cB, n_comb, n_cand_bcov;
     DevBuf n_cB_off;            // int64 [n+1]
     DevBuf n_cand_count, n_cand_pos, n_cand_flag, n_cand_z, n_cand_lr, n_cand_norm, n_cand_sig, n_cand_cov,
         n_cand_nfr, n_cand_smooth;

@@ -40,12 +40,12 @@ __global__ void __launch_bounds__(NC_TILE) k_nuc_colsums(const int32_t *__restri
     if (j >= ncol) return;
     const double *Ec = s_E + half + threadIdx.x;
     double acc = 0.0;
-    double ea = Ec[-((lv - 1) >> 1)], eb = Ec[lv >> 1];  // consecutive sizes share one tap
+    double ta = Ec[-((lv - 1) >> 1)], tb = Ec[lv >> 1];  // consecutive sizes share one tap
     for (int i = lv; i < uv; i++) {
-        acc += s_f[i] * ((i == 1) ? ea : ea * eb);
+        acc += s_f[i] * ((i == 1) ? ta : ta * tb);
         const int in = i + 1;
-        if (in & 1) ea = Ec[-((in - 1) >> 1)];
-        else eb = Ec[in >> 1];
+        if (in & 1) ta = Ec[-((in - 1) >> 1)];
+        else tb = Ec[in >> 1];
     }
     cB[out_off[c] + 2 * (int64_t)w * c + j] = acc;
 }
@@ -218,7 +218,8 @@ struct NucPeakArgs {
     double *sc_val;
     unsigned char *sc_state;
     int32_t *cand_count, *cand_pos, *cand_flag;
-    double *cand_z, *cand_lr, *cand_norm, *cand_sig, *cand_cov, *cand_nfr, *cand_smooth;
+    double *cand_z, *cand_lr, *cand_norm, *cand_sig, *cand_cov, *cand_nfr, *cand_smooth, *cand_bcov;
+    const double *bcov;
     int2 *work;
     int32_t *work_count;
     int sep, boundary, order;
@@ -313,6 +314,7 @@ __global__ void __launch_bounds__(PK_THREADS_N) k_nuc_peaks(NucPeakArgs a)
             a.cand_cov[po + slot] = cov;
             a.cand_nfr[po + slot] = a.nfr_cov[oo + x];
             a.cand_smooth[po + slot] = a.smooth[oo + x];
+            a.cand_bcov[po + slot] = a.bcov[oo + x];
             a.cand_z[po + slot] = nb_nan();
             a.cand_lr[po + slot] = nb_nan();
             int fl = 0;
@@ -340,15 +342,15 @@ struct CandArgs {
     const int32_t *work_count;
     const int32_t *cand_pos;
     int32_t *cand_flag;
-    const double *cand_norm, *cand_cov;
+    const double *cand_norm, *cand_cov, *cand_bcov;  // cand_bcov = S_B = sum f*Bp over the window (bias coverage track)
     double *cand_z, *cand_lr;
     int pwm_up, lv, R, W, w, csc_pad, use_bias, lr_is_nan;
     double min_lr, min_z;
 };
 
 #define CS_THREADS 256
-#define CS_GROUP 8   // candidates scored together: every VMat element is loaded once per group
-__global__ void __launch_bounds__(CS_THREADS) k_cand_stats(CandArgs a)
+#define CS_GROUP 4   // candidates scored together: every VMat element is loaded once per group
+__global__ void __launch_bounds__(CS_THREADS, 4) k_cand_stats(CandArgs a)
 {
     extern __shared__ double sm_cs[];
     __shared__ double red[32];
@@ -381,10 +383,10 @@ __global__ void __launch_bounds__(CS_THREADS) k_cand_stats(CandArgs a)
                 for (int i = tid; i < nEw; i += CS_THREADS) s_E[cg * nEw + i] = a.use_bias ? 0.0 : 1.0;
         }
         __syncthreads();
-        // ---- phase 1: S_VB = sum V*Bp and S_B = sum f*Bp  (likelihood-ratio normalisers)
-        double sVB[CS_GROUP], sB[CS_GROUP];
+        // ---- phase 1: S_VB = sum V*Bp (normaliser of the nucleosome model in the likelihood ratio)
+        double sVB[CS_GROUP];
 #pragma unroll
-        for (int cg = 0; cg < CS_GROUP; cg++) sVB[cg] = sB[cg] = 0.0;
+        for (int cg = 0; cg < CS_GROUP; cg++) sVB[cg] = 0.0;
         if (rr < rows_par) {
             for (int k = kk; k < a.W; k += wcols) {
                 const double *Ec = s_E + half + k;
@@ -400,12 +402,10 @@ __global__ void __launch_bounds__(CS_THREADS) k_cand_stats(CandArgs a)
                     }
                     for (int r = 0; r < a.R; r++, i++) {
                         const double v = a.V[(size_t)r * a.W + k];
-                        const double fr = s_f[r];
 #pragma unroll
                         for (int cg = 0; cg < CS_GROUP; cg++) {
                             const double bp = (i == 1) ? ea[cg] : ea[cg] * eb[cg];
                             sVB[cg] = fma(v, bp, sVB[cg]);
-                            sB[cg] = fma(bp, fr, sB[cg]);  // normByInsertDist, chunkmat2d.py:154-156
                         }
                         const int in = i + 1;
                         if (in & 1) {
@@ -420,12 +420,10 @@ __global__ void __launch_bounds__(CS_THREADS) k_cand_stats(CandArgs a)
                     for (int r = rr; r < a.R; r += rows_par) {
                         const int i = a.lv + r;
                         const double v = a.V[(size_t)r * a.W + k];
-                        const double fr = s_f[r];
 #pragma unroll
                         for (int cg = 0; cg < CS_GROUP; cg++) {
                             const double bp = a.use_bias ? bias_cell(Ec + cg * nEw, i) : 1.0;
                             sVB[cg] = fma(v, bp, sVB[cg]);
-                            sB[cg] = fma(bp, fr, sB[cg]);
                         }
                     }
                 }
@@ -433,10 +431,11 @@ __global__ void __launch_bounds__(CS_THREADS) k_cand_stats(CandArgs a)
         }
 #pragma unroll
         for (int cg = 0; cg < CS_GROUP; cg++) {
-            const double x1 = block_sum(sVB[cg], red), x2 = block_sum(sB[cg], red);
+            const double x1 = block_sum(sVB[cg], red);
             if (tid == 0) {
                 s_sum[0][cg] = x1;
-                s_sum[1][cg] = x2;
+                // S_B = sum f*Bp over the window = the bias coverage at the candidate (NucleosomeCalling.py:56-58)
+                s_sum[1][cg] = (cg < ng) ? a.cand_bcov[a.cand_off[a.work[g0 + cg].x] + a.work[g0 + cg].y] : 1.0;
             }
         }
         __syncthreads();
@@ -597,7 +596,7 @@ int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
         }
     }
     const size_t tl = (size_t)b->total_len;
-    DevBuf *tracks[] = {&b->n_signal, &b->n_bg, &b->n_norm, &b->n_smooth, &b->n_nuc_cov, &b->n_nfr_cov, &b->n_bcov, &b->sc_f64};
+    DevBuf *tracks[] = {&b->n_signal, &b->n_bg, &b->n_norm, &b->n_smooth, &b->n_nuc_cov, &b->n_nfr_cov, &b->n_bcov, &b->n_comb, &b->sc_f64};
     for (auto t : tracks) NB_CUDA(ctx, t->reserve(sizeof(double) * tl));
     NB_CUDA(ctx, b->sc_i32.reserve(sizeof(int32_t) * tl));
     NB_CUDA(ctx, b->sc_u8.reserve(tl));
@@ -610,7 +609,7 @@ int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
     NB_CUDA(ctx, b->n_cand_count.reserve(sizeof(int32_t) * n));
     NB_CUDA(ctx, b->n_cand_pos.reserve(sizeof(int32_t) * nc));
     NB_CUDA(ctx, b->n_cand_flag.reserve(sizeof(int32_t) * nc));
-    DevBuf *cd[] = {&b->n_cand_z, &b->n_cand_lr, &b->n_cand_norm, &b->n_cand_sig, &b->n_cand_cov, &b->n_cand_nfr, &b->n_cand_smooth};
+    DevBuf *cd[] = {&b->n_cand_z, &b->n_cand_lr, &b->n_cand_norm, &b->n_cand_sig, &b->n_cand_cov, &b->n_cand_nfr, &b->n_cand_smooth, &b->n_cand_bcov};
     for (auto t : cd) NB_CUDA(ctx, t->reserve(sizeof(double) * nc));
     NB_CUDA(ctx, b->n_work.reserve(sizeof(int2) * nc));
     NB_CUDA(ctx, b->n_work_count.reserve(sizeof(int32_t) * 4));
@@ -699,7 +698,9 @@ int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
         a.signal = b->n_signal.as<double>();
         a.nuc_cov = b->n_nuc_cov.as<double>();
         a.nfr_cov = b->n_nfr_cov.as<double>();
-        a.comb = b->n_bcov.as<double>();  // bcov is consumed by k_nuc_tracks; reuse as norm+smoothed scratch
+        a.comb = b->n_comb.as<double>();
+        a.bcov = b->n_bcov.as<double>();
+        a.cand_bcov = b->n_cand_bcov.as<double>();
         a.sc_pos = b->sc_i32.as<int32_t>();
         a.sc_val = b->sc_f64.as<double>();
         a.sc_state = b->sc_u8.as<unsigned char>();
@@ -744,6 +745,7 @@ int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
         a.cand_flag = b->n_cand_flag.as<int32_t>();
         a.cand_norm = b->n_cand_norm.as<double>();
         a.cand_cov = b->n_cand_cov.as<double>();
+        a.cand_bcov = b->n_cand_bcov.as<double>();
         a.cand_z = b->n_cand_z.as<double>();
         a.cand_lr = b->n_cand_lr.as<double>();
         a.pwm_up = r.pwm_up;
@@ -773,7 +775,7 @@ int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
         a.sc_pos = b->sc_i32.as<int32_t>();
         a.sc_val = b->sc_f64.as<double>();
         a.sc_state = b->sc_u8.as<unsigned char>();
-        a.sc_idx = reinterpret_cast<int32_t *>(b->n_bcov.p);
+        a.sc_idx = reinterpret_cast<int32_t *>(b->n_comb.p);
         a.sep = p.nonredundant_sep;
         ProfScope ps(ctx, b->stream, "k_nuc_reduce");
         k_nuc_reduce<<<n, 256, 0, b->stream>>>(a);

@@ -41,14 +41,14 @@ __global__ void __launch_bounds__(OC_TILE) k_occ_colsums(const int32_t *__restri
     if (j >= ncol) return;
     const double *Ec = s_E + half + threadIdx.x;
     double an = 0.0, af = 0.0;
-    double ea = Ec[1], eb = Ec[0];  // i = 0: taps c+1 and c; consecutive sizes share one tap
+    double ta = Ec[1], tb = Ec[0];  // i = 0: taps c+1 and c; consecutive sizes share one tap
     for (int i = 0; i < upper; i++) {
-        const double bp = (i == 1) ? ea : ea * eb;
+        const double bp = (i == 1) ? ta : ta * tb;
         an += s_pn[i] * bp;
         af += s_pf[i] * bp;
         const int in = i + 1;
-        if (in & 1) ea = Ec[-((in - 1) >> 1)];
-        else eb = Ec[in >> 1];
+        if (in & 1) ta = Ec[-((in - 1) >> 1)];
+        else tb = Ec[in >> 1];
     }
     const int64_t o = out_off[c] + 2 * (int64_t)flank * c + j;
     cn[o] = an;
