@@ -215,8 +215,16 @@ def run_ours(args, rank, world, local_rank):
                 setattr(q, name, p)
         pinned.append(q)
     batches = pinned
-    outs = [(eng.occ_alloc(batches[0], raw=False, alloc=eng.pinned), eng.nuc_alloc(batches[0], cov=False, alloc=eng.pinned))
-            for _ in range(2)]
+    # results a default `nucleoatac occ` + `nucleoatac nuc` run writes: 3 smoothed occupancy tracks + occupancy peaks +
+    # nuc_dist, nucleoatac_signal + its smoothed track + the call table (run_occ.py:45-49, run_nuc.py:30-32)
+    def default_outputs(pb):
+        o = eng.occ_alloc(pb, raw=False, alloc=eng.pinned)
+        o.pop("cov")
+        n = eng.nuc_alloc(pb, cov=False, alloc=eng.pinned)
+        n.pop("nuc_signal")
+        n.pop("background")
+        return o, n
+    outs = [default_outputs(batches[0]) for _ in range(2)]
     bp_step = batches[0].total_len
     hs = [None, None]
 
@@ -319,7 +327,8 @@ def run_ours(args, rank, world, local_rank):
                                 xcor_mode=args.xcor_mode, shard="round-robin chunk k -> rank k mod N"),
                     roofline=roofline, cpu_baseline=cpu,
                     e2e=dict(value=bp_step * K * world / e2e_s, unit="bp/s", h2d_bytes_per_step=int(h2d_b), d2h_bytes_per_step=int(d2h_b),
-                             ms_per_step=e2e_s / K * 1e3),
+                             ms_per_step=e2e_s / K * 1e3,
+                             d2h="3 smoothed occupancy tracks + peaks + nuc_dist, nucleoatac_signal + smooth + call table (f64)"),
                     gpu_launches=launches, clocks=clk, wall_s_device_pass=t_wall, gen_s=t_gen,
                     checks=dict(nuc_dist_sum=float(nd.sum()), fragment_size_count=int(fs.sum())))
         print(json.dumps(line), flush=True)
