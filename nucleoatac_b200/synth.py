@@ -150,8 +150,8 @@ class Workload:
 
     def configure(self, eng, use_bias=True, xcor_mode=0, sd=10):
         eng.set_pwm(self.pwm, self.pwm_up, self.pwm_down, self.nucleotides)
+        eng.set_fragment_sizes(self.fragmentsizes)  # before the VMat: the scaled template needs sizes up to vmat.upper
         eng.set_vmat(self.vmat, self.v_lower, self.v_upper)
-        eng.set_fragment_sizes(self.fragmentsizes)
         eng.set_occ_model(self.nuc_probs, self.nfr_probs)
         eng.configure_nuc(sd=sd, use_bias=use_bias, xcor_mode=xcor_mode)
         eng.configure_occ(upper=self.upper, use_bias=use_bias)
