@@ -34,6 +34,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "bp scored/sec (occ+nuc), synthetic 10 kb chunks, 251x251 VMat"
 R_V, W_V = 251, 251
+TC_DRAM_BYTES_PER_CHUNK = 17.55e6 / 200  # measured, see roofline.traffic_source
 
 
 def load_peaks():
@@ -312,7 +313,9 @@ def run_ours(args, rank, world, local_rank):
         k_avg_s = (kms / max(kcount, 1)) * 1e-3
         achieved = flop_per_launch / k_avg_s / 1e12 if k_avg_s > 0 else 0.0
         roofline = dict(bound="tensor", kernel=kname, achieved=achieved, peak=peaks["tf_sustained"], unit="TFLOP/s",
-                        frac=achieved / peaks["tf_sustained"], traffic=None, peak_source=peaks["source"] + " bf16 sustained",
+                        frac=achieved / peaks["tf_sustained"], traffic=TC_DRAM_BYTES_PER_CHUNK * B if kname == "k_nuc_bx_tc" else None,
+                        traffic_source="ncu --set full, dram__bytes_read+write of k_nuc_bx_tc: 17.55 MB per 200-chunk launch "
+                                       "(profiles/r1_tc_path_ncu_full.txt), scaled to this launch's chunk count", peak_source=peaks["source"] + " bf16 sustained",
                         kernel_ms_per_launch=kms / max(kcount, 1), kernel_share_of_step=kms / total_ms if total_ms else None,
                         algorithmic_flop_per_bp=2.0 * R_V * W_V,
                         per_kernel_ms={k: round(v[1] / K, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])})

@@ -182,6 +182,8 @@ int nb200_batch_upload(nb200_ctx *ctx, const nb200_batch *h, nb200_dbatch **io)
     if (!ctx || !h || !io) return nb200_fail(ctx, NB200_ERR_ARG, "nb200_batch_upload: NULL argument");
     if (h->n_chunks < 1 || !h->chunk_start || !h->chunk_end || !h->frag_off)
         return nb200_fail(ctx, NB200_ERR_ARG, "nb200_batch_upload: need n_chunks >= 1, chunk_start, chunk_end, frag_off");
+    if (h->n_chunks > 65535)  // chunks ride on gridDim.y
+        return nb200_fail(ctx, NB200_ERR_CAPACITY, "nb200_batch_upload: at most 65535 chunks per batch (got %d); split the chunk list", h->n_chunks);
     NB_CUDA(ctx, cudaSetDevice(ctx->device));
     nb200_dbatch *b = *io;
     if (!b) {

@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(MLE_WARPS * 32) k_occ_mle(OccMleArgs a)
             for (int j = 0; j < cnt; j++) {
                 const double pj = s_p[warp][j], qj = s_q[warp][j];
 #pragma unroll
-                for (int q = 0; q < NQ; q++) mant[q] *= __dadd_rn(__dmul_rn(al[q], pj), __dmul_rn(om[q], qj));
+                for (int q = 0; q < NQ; q++) mant[q] *= __dadd_rn(__dmul_rn(al[q], pj), __dmul_rn(om[q], qj));  // as numpy evaluates it
                 if ((++nf & 3) == 0) {  // renormalise every 4 factors (factors >= 1e-75 cannot underflow in between)
 #pragma unroll
                     for (int q = 0; q < NQ; q++) {
