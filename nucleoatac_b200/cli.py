@@ -48,6 +48,20 @@ def build_parser():
     g.add_argument("--redundant_sep", metavar="int", default=25, type=int, help="Minimum separation between redundant nucleosomes. Not recommended to be below 15. Default is 25")
     g.add_argument("--sd", metavar="int", default=10, type=int, help="Standard deviation for smoothing. Default is 10")
     g.add_argument("--xcor_mode", default=0, type=int, help="0 auto (tcgen05), 1 fp64 CUDA cores, 2 tcgen05 tensor cores")
+    vp = sub.add_parser("vprocess", help="nucleoatac function:  Make processed vplot to use for nucleosome calling")
+    g = vp.add_argument_group("Required", "Necessary arguments")
+    g.add_argument("--out", metavar="output_basename", required=True)
+    g = vp.add_argument_group("VPlot and Insert Size Options", "Optional")
+    g.add_argument("--sizes", metavar="file", help="Insert distribution file")
+    from .run_vprocess import DEFAULT_VPLOT
+    g.add_argument("--vplot", metavar="vmat_file", default=DEFAULT_VPLOT, help="Accepts VMat file.  Default is Vplot from S. Cer.")
+    g = vp.add_argument_group("Size parameers", "Use sensible values")
+    g.add_argument("--lower", metavar="int", default=105, type=int, help="lower limit (inclusive) in insert size. default is 105")
+    g.add_argument("--upper", metavar="int", default=251, type=int, help="upper limit (exclusive) in insert size. default 251")
+    g.add_argument("--flank", metavar="int", default=60, type=int, help="distance on each side of dyad to include")
+    g = vp.add_argument_group("Options", "")
+    g.add_argument("--smooth", metavar="float", default=0.75, type=float, help="SD to use for gaussian smoothing.  Use 0 for no smoothing.")
+    g.add_argument("--plot_extra", action="store_true", default=False, help="accepted for compatibility; plotting is not part of this package")
     for sp in (occ, nuc):
         g = sp.add_argument_group("Device options", "")
         g.add_argument("--device", default=0, type=int, help="CUDA device of this process")
@@ -75,6 +89,10 @@ def nucleoatac_main(argv=None):
         print("---------Obtaining nucleosome signal and calling positions----------")
         from .run_nuc import run_nuc
         run_nuc(args)
+    elif args.command == "vprocess":
+        print("---------Processing VPlot-----------------------------------------")
+        from .run_vprocess import run_vprocess
+        run_vprocess(args)
     else:
         build_parser().print_help()
         return 2

@@ -312,3 +312,180 @@ class BedGraphReader:
         for i in range(lo, hi):
             out[max(s[i] - start, 0):min(e[i] - start, end - start)] = v[i]
         return out
+
+
+# ----------------------------------------------------------------------------------------- tabix (.tbi)
+def _reg2bin(beg, end):
+    """UCSC binning scheme of tabix/BAI (min_shift 14, depth 5)."""
+    end -= 1
+    if beg >> 14 == end >> 14:
+        return ((1 << 15) - 1) // 7 + (beg >> 14)
+    if beg >> 17 == end >> 17:
+        return ((1 << 12) - 1) // 7 + (beg >> 17)
+    if beg >> 20 == end >> 20:
+        return ((1 << 9) - 1) // 7 + (beg >> 20)
+    if beg >> 23 == end >> 23:
+        return ((1 << 6) - 1) // 7 + (beg >> 23)
+    if beg >> 26 == end >> 26:
+        return ((1 << 3) - 1) // 7 + (beg >> 26)
+    return 0
+
+
+def _bgzf_lines(path):
+    """Yield (virtual offset of line start, virtual offset after the line, line bytes) of a BGZF text file."""
+    with open(path, "rb") as fh:
+        coff = 0
+        pending, pending_start = b"", None
+        while True:
+            data, size = _read_block(fh, coff)
+            if size == 0:
+                break
+            pos = 0
+            while True:
+                nl = data.find(b"\n", pos)
+                if nl < 0:
+                    if pos < len(data):
+                        if pending_start is None:
+                            pending_start = (coff << 16) | pos
+                        pending += data[pos:]
+                    break
+                start = pending_start if pending_start is not None else (coff << 16) | pos
+                line = pending + data[pos:nl]
+                pending, pending_start = b"", None
+                end_u = nl + 1
+                end_v = ((coff << 16) | end_u) if end_u < len(data) else ((coff + size) << 16)
+                yield start, end_v, line
+                pos = nl + 1
+            coff += size
+
+
+def tabix_index(path_gz, seq_col=1, beg_col=2, end_col=3, zero_based=True):
+    """Write `path_gz + '.tbi'` for a coordinate-sorted, BGZF-compressed BED / bedgraph -- what
+    `pysam.tabix_index(..., preset='bed')` produces for the reference's outputs (run_occ.py:130-136)."""
+    names, bins, linear = [], [], []
+    tid = {}
+    for start_v, end_v, line in _bgzf_lines(path_gz):
+        if not line or line.startswith(b"#"):
+            continue
+        f = line.split(b"\t")
+        chrom = f[seq_col - 1].decode()
+        beg = int(f[beg_col - 1]) - (0 if zero_based else 1)
+        end = int(f[end_col - 1])
+        if end <= beg:
+            end = beg + 1
+        if chrom not in tid:
+            tid[chrom] = len(names)
+            names.append(chrom)
+            bins.append({})
+            linear.append([])
+        t = tid[chrom]
+        b = _reg2bin(beg, end)
+        chunks = bins[t].setdefault(b, [])
+        if chunks and chunks[-1][1] == start_v:
+            chunks[-1][1] = end_v            # records are consecutive in the file: extend the chunk
+        else:
+            chunks.append([start_v, end_v])
+        lin = linear[t]
+        w0, w1 = beg >> 14, (end - 1) >> 14
+        if len(lin) <= w1:
+            lin.extend([-1] * (w1 + 1 - len(lin)))
+        for w in range(w0, w1 + 1):
+            if lin[w] < 0:
+                lin[w] = start_v
+    out = bytearray()
+    nm = b"".join(n.encode() + b"\x00" for n in names)
+    out += b"TBI\x01" + struct.pack("<iiiiiii", len(names), 0x10000 if zero_based else 0, seq_col, beg_col, end_col, ord("#"), 0)
+    out += struct.pack("<i", len(nm)) + nm
+    for t in range(len(names)):
+        out += struct.pack("<i", len(bins[t]))
+        for b in sorted(bins[t]):
+            out += struct.pack("<Ii", b, len(bins[t][b]))
+            for c0, c1 in bins[t][b]:
+                out += struct.pack("<QQ", c0, c1)
+        lin = linear[t]
+        # windows without records: leading ones point at the first record, later ones repeat the previous window
+        # (the layout of the .tbi files the reference shipped, written by pysam/htslib)
+        first = next((v for v in lin if v >= 0), 0)
+        prev = first
+        for w in range(len(lin)):
+            if lin[w] < 0:
+                lin[w] = prev
+            else:
+                prev = lin[w]
+        out += struct.pack("<i", len(lin)) + b"".join(struct.pack("<Q", v) for v in lin)
+    w = BgzfWriter(path_gz + ".tbi")
+    w.write(bytes(out))
+    w.close()
+    return path_gz + ".tbi"
+
+
+class TabixFile:
+    """Region queries on a BGZF file through its .tbi (pysam.Tabixfile stand-in for `--occ_track`)."""
+
+    def __init__(self, path_gz):
+        self.path = path_gz
+        with gzip.open(path_gz + ".tbi", "rb") as fh:
+            raw = fh.read()
+        if raw[:4] != b"TBI\x01":
+            raise ValueError("not a tabix index")
+        n_ref, self.fmt, self.sc, self.bc, self.ec, _meta, _skip, l_nm = struct.unpack_from("<iiiiiiii", raw, 4)
+        off = 36
+        self.names = [x.decode() for x in raw[off:off + l_nm].split(b"\x00")[:-1]]
+        off += l_nm
+        self.linear, self.bins = [], []
+        for _ in range(n_ref):
+            n_bin = struct.unpack_from("<i", raw, off)[0]
+            off += 4
+            bd = {}
+            for _b in range(n_bin):
+                b, n_chunk = struct.unpack_from("<Ii", raw, off)
+                off += 8
+                bd[b] = [struct.unpack_from("<QQ", raw, off + 16 * i) for i in range(n_chunk)]
+                off += 16 * n_chunk
+            n_intv = struct.unpack_from("<i", raw, off)[0]
+            off += 4
+            self.linear.append(list(struct.unpack_from("<%dQ" % n_intv, raw, off)))
+            off += 8 * n_intv
+            self.bins.append(bd)
+        self.fh = open(path_gz, "rb")
+
+    def fetch(self, chrom, start, end):
+        """Lines (split on tabs) overlapping [start, end)."""
+        if chrom not in self.names:
+            return []
+        t = self.names.index(chrom)
+        lin = self.linear[t]
+        if not lin:
+            return []
+        voff = lin[min(start >> 14, len(lin) - 1)]
+        coff, uoff = voff >> 16, voff & 0xffff
+        out, buf = [], b""
+        data, size = _read_block(self.fh, coff)
+        buf = data[uoff:]
+        coff += size
+        while True:
+            nl = buf.find(b"\n")
+            if nl < 0:
+                data, size = _read_block(self.fh, coff)
+                if size == 0:
+                    break
+                buf += data
+                coff += size
+                continue
+            f = buf[:nl].split(b"\t")
+            buf = buf[nl + 1:]
+            if len(f) < 3 or f[0].startswith(b"#"):
+                continue
+            if f[self.sc - 1].decode() != chrom:
+                if out:
+                    break
+                continue
+            b, e = int(f[self.bc - 1]), int(f[self.ec - 1])
+            if b >= end:
+                break
+            if e > start:
+                out.append([x.decode() for x in f])
+        return out
+
+    def close(self):
+        self.fh.close()

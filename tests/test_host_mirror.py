@@ -117,3 +117,59 @@ def test_pwm_bundled(example):
     p = PWM.open("Human")
     assert (p.up, p.down, p.nucleotides) == (10, 10, ["A", "C", "G", "T"])
     np.testing.assert_allclose(p.mat, example.pwm, rtol=1e-12)
+
+
+def test_vprocess_reproduces_shipped_vmat(tmp_path, example, golden):
+    """`nucleoatac vprocess` on the bundled S. cer V-plot with the example's nuc_dist reproduces the VMat the
+    reference shipped in example_results (what `nucleoatac run` wires from occ to nuc, cli.py:38-41)."""
+    from nucleoatac_b200.cli import nucleoatac_main
+    from nucleoatac_b200.fragmentsizes import FragmentSizes
+    from nucleoatac_b200.VMat import VMat
+    sizes = str(tmp_path / "nuc_dist.txt")
+    FragmentSizes(0, 251, vals=golden["nuc_dist"]).save(sizes)
+    out = str(tmp_path / "ex")
+    assert nucleoatac_main(["vprocess", "--sizes", sizes, "--out", out]) == 0
+    v = VMat.open(out + ".VMat")
+    mat, lo, hi = example.vmat
+    assert (v.lower, v.upper, v.mat.shape) == (lo, hi, mat.shape)
+    np.testing.assert_allclose(v.mat, mat, rtol=2e-11, atol=1e-15)
+
+
+def test_tabix_index_roundtrip_and_reference_layout(tmp_path):
+    """.tbi writer: region queries through our own index return exactly the overlapping rows; when the reference tree
+    is present (build container) the index built for its shipped bedgraph has the same bins / chunks / linear
+    offsets as the .tbi htslib wrote for that file."""
+    import gzip as gz
+    import struct
+    rng = np.random.RandomState(5)
+    rows, pos = [], 0
+    for chrom in ("chrA", "chrB"):
+        pos = 100
+        for _ in range(30000):
+            ln = int(rng.randint(1, 40))
+            rows.append((chrom, pos, pos + ln, round(float(rng.rand()), 6)))
+            pos += ln + int(rng.randint(0, 30))
+    plain = tmp_path / "t.bedgraph"
+    plain.write_text("".join("%s\t%d\t%d\t%s\n" % r for r in rows))
+    hostio.bgzip_file(str(plain), str(plain) + ".gz")
+    hostio.tabix_index(str(plain) + ".gz")
+    tb = hostio.TabixFile(str(plain) + ".gz")
+    for chrom, s, e in (("chrA", 5000, 5600), ("chrB", 400000, 401000), ("chrA", 0, 150), ("chrB", 10 ** 7, 10 ** 7 + 5)):
+        got = [(r[0], int(r[1]), int(r[2])) for r in tb.fetch(chrom, s, e)]
+        exp = [(c, a, b) for (c, a, b, _v) in rows if c == chrom and b > s and a < e]
+        assert got == exp, (chrom, s, e)
+    ref = "/root/reference/example/example_results/example.occ.bedgraph.gz"
+    if not os.path.exists(ref):
+        return
+    import shutil
+    mine = str(tmp_path / "ref.bedgraph.gz")
+    shutil.copy(ref, mine)
+    hostio.tabix_index(mine)
+    a, b = hostio.TabixFile(mine), hostio.TabixFile.__new__(hostio.TabixFile)
+    shutil.copy(ref + ".tbi", mine + ".tbi")
+    b.__init__(mine)
+    assert a.names == b.names and (a.fmt, a.sc, a.bc, a.ec) == (b.fmt, b.sc, b.bc, b.ec)
+    for t in range(len(a.names)):
+        ref_bins = {k: v for k, v in b.bins[t].items() if k != 37450}   # htslib's metadata pseudo-bin
+        assert a.bins[t] == ref_bins, a.names[t]
+        assert a.linear[t] == b.linear[t], a.names[t]
