@@ -199,6 +199,10 @@ int nb200_flush_l2(nb200_ctx *ctx, nb200_dbatch *b);
 int64_t nb200_format_track(const char *chrom, int64_t start, const double *vals, int64_t n, int32_t write_zero, char *out,
                            int64_t cap);
 
+/* pysam.tabix_compress + pysam.tabix_index(preset="bed") of nucleoatac/run_occ.py:130-136 / run_nuc.py:194-201 in one
+ * pass: plain sorted BED / bedgraph -> BGZF file + .tbi.  Pure host code (zlib, `threads` deflate workers). */
+int nb200_bgzip_tabix(const char *path_plain, const char *path_gz, int threads, char *err, int errcap);
+
 /* ---- multi-GPU end-of-run reductions (NCCL over NVLink) ----------------------------------- */
 /* fragment-size histogram (fragments.pyx:122-145), nuc_dist (run_occ.py:117-121), V-plot sum
  * (pyatac/make_vplot.py:70-73).  unique_id is the 128-byte ncclUniqueId from rank 0. */

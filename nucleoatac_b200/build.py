@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libnucleo_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["nb200_ctx.cu", "nb200_batch.cu", "nb200_occ.cu", "nb200_nuc.cu", "nb200_prims.cu", "nb200_xcor_tc.cu", "nb200_hostfmt.cu"]
+SOURCES = ["nb200_ctx.cu", "nb200_batch.cu", "nb200_occ.cu", "nb200_nuc.cu", "nb200_prims.cu", "nb200_xcor_tc.cu", "nb200_hostfmt.cu", "nb200_hostio.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--fmad=true", "-Xptxas", "-v"]
 
@@ -46,7 +46,7 @@ def build(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(lambda s: _compile(s, force, hdr_mtime, log), SOURCES))
     if force or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
-        res = subprocess.run([NVCC, "-shared", "-o", LIB] + objs + ["-cudart", "static", "-ldl", "-lpthread"],
+        res = subprocess.run([NVCC, "-shared", "-o", LIB] + objs + ["-cudart", "static", "-ldl", "-lpthread", "-lz"],
                              capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("link failed:\n%s" % res.stderr)

@@ -83,6 +83,17 @@ def bgzip_file(src, dst):
     w.close()
 
 
+def bgzip_tabix(path_plain, path_gz, threads=None):
+    """BGZF-compress a sorted BED / bedgraph and write its .tbi in one native pass (nb200_bgzip_tabix)."""
+    import ctypes as C
+    from . import _lib
+    err = C.create_string_buffer(256)
+    st = _lib.load().nb200_bgzip_tabix(path_plain.encode(), path_gz.encode(), int(threads or min(16, os.cpu_count() or 1)), err, 256)
+    if st != 0:
+        raise IOError("bgzip/tabix of %s failed: %s" % (path_plain, err.value.decode()))
+    return path_gz
+
+
 # ----------------------------------------------------------------------------------------- BAM
 class BamFile:
     """Coordinate-sorted BAM reader.  `fetch_fragments(chrom, start, end)` returns the int32 arrays

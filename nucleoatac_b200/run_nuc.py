@@ -69,7 +69,6 @@ def run_nuc(args, score=process_chunks):
         for n in outputs:
             plain = args.out + "." + n + ext(n)
             dist.ShardWriter.merge(plain, world, len(chunks))
-            hostio.bgzip_file(plain, plain + ".gz")  # tabix_compress + tabix_index, run_nuc.py:194-201
+            hostio.bgzip_tabix(plain, plain + ".gz")  # tabix_compress + tabix_index, run_nuc.py:194-201
             os.remove(plain)
-            hostio.tabix_index(plain + ".gz")
     dist.barrier()

@@ -15,9 +15,8 @@ from .utils import read_chrom_sizes_from_bam, read_chrom_sizes_from_fasta
 
 
 def _finish(path_plain, path_gz):
-    hostio.bgzip_file(path_plain, path_gz)  # pysam.tabix_compress + tabix_index(preset="bed"), run_occ.py:130-136
+    hostio.bgzip_tabix(path_plain, path_gz)  # pysam.tabix_compress + tabix_index(preset="bed"), run_occ.py:130-136
     os.remove(path_plain)
-    hostio.tabix_index(path_gz)
 
 
 def occ_chunks(args):
