@@ -103,7 +103,13 @@ bool bgzf_write(FILE *fh, const std::vector<unsigned char> &data, int threads, i
     return fwrite(BGZF_EOF, 1, 28, fh) == 28;
 }
 
-inline uint64_t voffset(uint64_t u, const std::vector<uint64_t> &coff) { return (coff[u / BLOCK] << 16) | (u % BLOCK); }
+// virtual offset of uncompressed position u; a position at the very end of the data is the start of the block that
+// would follow (what bgzf_tell reports after the last line)
+inline uint64_t voffset(uint64_t u, const std::vector<uint64_t> &coff, uint64_t total)
+{
+    if (u >= total) return coff.back() << 16;
+    return (coff[u / BLOCK] << 16) | (u % BLOCK);
+}
 
 }  // namespace
 
@@ -202,8 +208,8 @@ int nb200_bgzip_tabix(const char *path_plain, const char *path_gz, int threads, 
             put32((int32_t)kv.first);
             put32((int32_t)kv.second.size());
             for (auto &c : kv.second) {
-                put64(voffset(c.beg, coff));
-                put64(voffset(c.end, coff));
+                put64(voffset(c.beg, coff, N));
+                put64(voffset(c.end, coff, N));
             }
         }
         // windows without rows: leading ones point at the first row, later ones repeat the previous window
@@ -216,7 +222,7 @@ int nb200_bgzip_tabix(const char *path_plain, const char *path_gz, int threads, 
         put32((int32_t)r.linear.size());
         for (auto v : r.linear) {
             if (v >= 0) prev = v;
-            put64(voffset((uint64_t)prev, coff));
+            put64(voffset((uint64_t)prev, coff, N));
         }
     }
     std::string tpath = std::string(path_gz) + ".tbi";
