@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_occ_fragbias(OccMleArgs a)
 #define MLE_WARPS 4
 __global__ void __launch_bounds__(MLE_WARPS * 32) k_occ_mle(OccMleArgs a)
 {
-    __shared__ double s_p[MLE_WARPS][32], s_q[MLE_WARPS][32];
+    __shared__ double s_p[MLE_WARPS][32], s_q[MLE_WARPS][32], s_n[MLE_WARPS][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = blockIdx.y;
     const int64_t oo = a.out_off[c];
@@ -189,15 +189,22 @@ __global__ void __launch_bounds__(MLE_WARPS * 32) k_occ_mle(OccMleArgs a)
                     const int jf = max(0, ceil_div(u - a.flank - a.halfstep, a.step));
                     bias = a.fragbias[(f0 + e) * a.maxw + (wi - jf)];
                 }
-                s_p[warp][lane] = __dmul_rn(a.pn[v.y], bias) / SN;
-                s_q[warp][lane] = __dmul_rn(a.pf[v.y], bias) / SF;
+                const double pv = __dmul_rn(a.pn[v.y], bias) / SN, qv = __dmul_rn(a.pf[v.y], bias) / SF;
+                s_p[warp][lane] = pv - qv;  // alpha*p + (1-alpha)*q is evaluated as q + alpha*(p-q): one FMA per (fragment, alpha)
+                s_q[warp][lane] = qv;
+                s_n[warp][lane] = pv;       // alpha == 1 uses p itself (q + (p-q) would lose p when p << q)
             }
             __syncwarp();
             for (int j = 0; j < cnt; j++) {
-                const double pj = s_p[warp][j], qj = s_q[warp][j];
+                const double dj = s_p[warp][j], qj = s_q[warp][j];
 #pragma unroll
-                for (int q = 0; q < NQ; q++) mant[q] *= __dadd_rn(__dmul_rn(al[q], pj), __dmul_rn(om[q], qj));  // as numpy evaluates it
-                if ((++nf & 3) == 0) {  // renormalise every 4 factors (factors >= 1e-75 cannot underflow in between)
+                for (int q = 0; q < NQ - 1; q++) mant[q] *= fma(al[q], dj, qj);
+                {
+                    double v = fma(al[NQ - 1], dj, qj);
+                    if (om[NQ - 1] == 0.0) v = s_n[warp][j];
+                    mant[NQ - 1] *= v;
+                }
+                if ((++nf & 7) == 0) {  // renormalise every 8 factors (factors >= 1e-37 cannot underflow in between)
 #pragma unroll
                     for (int q = 0; q < NQ; q++) {
                         const long long bits = __double_as_longlong(mant[q]);
