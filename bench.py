@@ -296,11 +296,16 @@ def run_ours(args, rank, world, local_rank):
         t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_s = float(t[0]), float(t[1])
-        ndt = torch.from_numpy(nd).cuda()
-        fst = torch.from_numpy(fs).cuda()
-        dist.all_reduce(ndt)
-        dist.all_reduce(fst)
-        nd, fs = ndt.cpu().numpy(), fst.cpu().numpy()
+        # the path's only collectives: nuc_dist (run_occ.py:117-121) and the fragment-size histogram
+        # (fragments.pyx:122-145, int64 => exact), summed by the library's own NCCL all-reduce
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.tensor(list(eng.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(uid, 0)
+        eng.nccl_init(bytes(uid.cpu().tolist()), rank, world)
+        nd = eng.allreduce(np.ascontiguousarray(nd, dtype=np.float64))
+        fs = eng.allreduce(np.ascontiguousarray(fs, dtype=np.int64))
+        eng.nccl_finalize()
 
     if rank == 0:
         peaks = load_peaks()

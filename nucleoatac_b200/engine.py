@@ -306,6 +306,32 @@ class Engine:
             rep[name.value.decode()] = (int(cnt.value), float(ms.value))
         return rep
 
+    # ------------------------------------------------------------------ end-of-run reductions (NCCL inside the library)
+    def nccl_unique_id(self):
+        buf = (C.c_ubyte * 128)()
+        st = self.lib.nb200_nccl_unique_id(buf)
+        if st != 0:
+            raise L.NB200Error(st, self.lib.nb200_last_error(None).decode())
+        return bytes(buf)
+
+    def nccl_init(self, unique_id, rank, world):
+        raw = (C.c_ubyte * 128)(*unique_id)
+        self.check(self.lib.nb200_nccl_init(self.h, raw, int(rank), int(world)))
+
+    def allreduce(self, arr):
+        """In-place sum over the ranks of a float64 or int64 numpy array (fragment sizes, nuc_dist, V-plot sums)."""
+        assert arr.flags["C_CONTIGUOUS"]
+        if arr.dtype == np.float64:
+            self.check(self.lib.nb200_allreduce_f64(self.h, L.ptr(arr, C.c_double), arr.size))
+        elif arr.dtype == np.int64:
+            self.check(self.lib.nb200_allreduce_i64(self.h, L.ptr(arr, C.c_int64), arr.size))
+        else:
+            raise TypeError("allreduce takes float64 or int64 arrays")
+        return arr
+
+    def nccl_finalize(self):
+        self.check(self.lib.nb200_nccl_finalize(self.h))
+
     # ------------------------------------------------------------------ primitives (reference seams)
     def fragmat(self, pos, tlen, start, end, lower, upper, atac=True):
         pos, tlen = L.as_i32(pos), L.as_i32(tlen)
