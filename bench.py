@@ -241,8 +241,10 @@ def run_ours(args, rank, world, local_rank):
         eng.flush_l2(hs[0])
         eng.sync(hs[0])
         eng.timer_start(hs[0])
-        eng.nuc_run(hs[0])
-        eng.occ_run(hs[0])
+        if args.path != "occ":
+            eng.nuc_run(hs[0])
+        if args.path != "nuc":
+            eng.occ_run(hs[0])
         eng.timer_stop(hs[0])
         return eng.timer_ms(hs[0])
 
@@ -270,9 +272,13 @@ def run_ours(args, rank, world, local_rank):
             if hs[s] is not None and n >= 2:
                 eng.sync(hs[s])  # results of step n-2 are on the host; its buffers can be recycled
             hs[s] = eng.upload(batches[i], hs[s])
-            eng.nuc_run(hs[s])
-            eng.occ_run(hs[s])
-            d2h = eng.occ_download(hs[s], outs[s][0]) + eng.nuc_download(hs[s], outs[s][1])
+            d2h = 0
+            if args.path != "occ":
+                eng.nuc_run(hs[s])
+                d2h += eng.nuc_download(hs[s], outs[s][1])
+            if args.path != "nuc":
+                eng.occ_run(hs[s])
+                d2h += eng.occ_download(hs[s], outs[s][0])
             h2d = eng.h2d_bytes(hs[s])
         for s in (0, 1):
             if hs[s] is not None:
@@ -288,7 +294,7 @@ def run_ours(args, rank, world, local_rank):
     clk = clocks.stop()
 
     # ---- end-of-run reductions (the only collectives on the path): nuc_dist and fragment sizes
-    nd = outs[(K - 1) & 1][0]["nuc_dist"].sum(axis=0)
+    nd = outs[(K - 1) & 1][0]["nuc_dist"].sum(axis=0) if args.path != "nuc" else np.zeros(wl.upper)
     fs = eng.fragment_sizes(batches[-1].starts, batches[-1].ends, batches[-1].frag_off, batches[-1].frag_pos,
                             batches[-1].frag_tlen, 0, wl.upper)
     if dist is not None:
@@ -311,7 +317,7 @@ def run_ours(args, rank, world, local_rank):
         peaks = load_peaks()
         launches = int(sum(v[0] for v in prof.values()))
         # the kernel the roofline is quoted for: the dense background cross-correlation (the path's only contraction)
-        kname = "k_nuc_bx_tc" if "k_nuc_bx_tc" in prof else "k_nuc_bx_fp64"
+        kname = "k_nuc_bx_tc" if "k_nuc_bx_tc" in prof else ("k_nuc_bx_fp64" if "k_nuc_bx_fp64" in prof else "k_occ_mle")
         kcount, kms = prof.get(kname, (0, 0.0))
         # algorithmic work of the dominant kernel: the dense background cross-correlation, 2*R*W flop per bp
         flop_per_launch = 2.0 * R_V * W_V * bp_step
@@ -332,7 +338,7 @@ def run_ours(args, rank, world, local_rank):
                                          "occ+nuc with Tn5 bias" + (" OFF" if args.no_bias else ""),
                                 chunks_per_step_per_gpu=B, chunk_len=10000, vmat="251x251", fragments_per_bp=0.25,
                                 l2="flushed before every timed step (256 MiB write) and working set >> L2",
-                                xcor_mode=args.xcor_mode, shard="round-robin chunk k -> rank k mod N"),
+                                xcor_mode=args.xcor_mode, shard="round-robin chunk k -> rank k mod N", path=args.path),
                     roofline=roofline, cpu_baseline=cpu,
                     e2e=dict(value=bp_step * K * world / e2e_s, unit="bp/s", h2d_bytes_per_step=int(h2d_b), d2h_bytes_per_step=int(d2h_b),
                              ms_per_step=e2e_s / K * 1e3,
@@ -355,6 +361,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=2000, help="chunks per step per GPU")
+    ap.add_argument("--path", default="both", choices=["both", "occ", "nuc"], help="which part of the hot path a step runs (default: occ + nuc, the BASELINE metric)")
     ap.add_argument("--no-bias", action="store_true")
     ap.add_argument("--xcor-mode", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

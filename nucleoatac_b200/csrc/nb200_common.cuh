@@ -179,14 +179,12 @@ struct nb200_dbatch {
     DevBuf o_peak_count, o_peak_pos, o_peak_occ, o_peak_lower, o_peak_upper, o_peak_reads;
     DevBuf o_cn, o_cf;          // per-column sums of pn*Bp, pf*Bp over [start-flank, end+flank)
     DevBuf o_fragbias;          // f64 [n_frag][2*flank/step+1] window bias per fragment
-    DevBuf o_colsum_off;        // int64 [n+1]
     DevBuf o_peak_off;          // int64 [n+1]
     std::vector<int64_t> h_opeak_off;
     bool occ_done = false;
     int occ_upper = 0;
     // nuc outputs (device)
     DevBuf n_signal, n_bg, n_norm, n_smooth, n_nuc_cov, n_nfr_cov, n_bx, n_bcov, n_cB, n_comb, n_cand_bcov;
-    DevBuf n_cB_off;            // int64 [n+1]
     DevBuf n_cand_count, n_cand_pos, n_cand_flag, n_cand_z, n_cand_lr, n_cand_norm, n_cand_sig, n_cand_cov,
         n_cand_nfr, n_cand_smooth;
     DevBuf n_cand_off;          // int64 [n+1]
