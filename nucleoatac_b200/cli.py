@@ -62,6 +62,24 @@ def build_parser():
     g = vp.add_argument_group("Options", "")
     g.add_argument("--smooth", metavar="float", default=0.75, type=float, help="SD to use for gaussian smoothing.  Use 0 for no smoothing.")
     g.add_argument("--plot_extra", action="store_true", default=False, help="accepted for compatibility; plotting is not part of this package")
+    mg = sub.add_parser("merge", help="nucleoatac function: Merge occ and nuc calls")
+    g = mg.add_argument_group("Required", "Necessary arguments")
+    g.add_argument("--occpeaks", metavar="occpeaks_file", required=True, help="Output from occ utility")
+    g.add_argument("--nucpos", metavar="nucpos_file", required=True, help="Output from nuc utility")
+    g = mg.add_argument_group("Options", "optional")
+    g.add_argument("--out", metavar="out_basename", help="output file basename")
+    g.add_argument("--sep", metavar="min_separation", default=120, help="minimum separation between call")
+    g.add_argument("--min_occ", metavar="min_occ", default=0.1, help="minimum lower bound occupancy of nucleosomes to be considered for excluding NFR. default is 0.1")
+    rn = sub.add_parser("run", help="Main nucleoatac utility: occ, vprocess, nuc and merge in one go (the NFR step of the reference is not part of this package)")
+    g = rn.add_argument_group("Required", "Necessary arguments")
+    g.add_argument("--bed", metavar="bed_file", required=True, help="Regions for which to do stuff.")
+    g.add_argument("--bam", metavar="bam_file", required=True, help="Accepts sorted BAM file")
+    g.add_argument("--out", metavar="output_basename", required=True, help="give output basename")
+    g.add_argument("--fasta", metavar="genome_seq", required=True, help="Indexed fasta file")
+    g = rn.add_argument_group("Options", "optional")
+    g.add_argument("--pwm", metavar="Tn5_PWM", default="Human", help="PWM descriptor file. Default is Human.PWM.txt included in package")
+    g.add_argument("--cores", metavar="num_cores", default=1, type=int, help="Number of cores to use (ignored)")
+    g.add_argument("--write_all", action="store_true", default=False, help="write all tracks")
     for sp in (occ, nuc):
         g = sp.add_argument_group("Device options", "")
         g.add_argument("--device", default=0, type=int, help="CUDA device of this process")
@@ -89,6 +107,27 @@ def nucleoatac_main(argv=None):
         print("---------Obtaining nucleosome signal and calling positions----------")
         from .run_nuc import run_nuc
         run_nuc(args)
+    elif args.command == "merge":
+        print("---------Merging----------------------------------------------------")
+        from .merge import run_merge
+        run_merge(args)
+    elif args.command == "run":  # nucleoatac/cli.py:34-64 without the final nfr step
+        p = build_parser()
+        base = ["--bed", args.bed, "--bam", args.bam, "--fasta", args.fasta, "--pwm", args.pwm, "--out", args.out]
+        print("---------Step1: Computing Occupancy and Nucleosomal Insert Distribution---------")
+        from .run_occ import run_occ
+        run_occ(p.parse_args(["occ"] + base))
+        print("---------Step2: Processing Vplot------------------------------------------------")
+        from .run_vprocess import run_vprocess
+        run_vprocess(p.parse_args(["vprocess", "--sizes", args.out + ".nuc_dist.txt", "--out", args.out]))
+        print("---------Step3: Obtaining nucleosome signal and calling positions---------------")
+        from .run_nuc import run_nuc
+        run_nuc(p.parse_args(["nuc"] + base + ["--occ_track", args.out + ".occ.bedgraph.gz", "--vmat", args.out + ".VMat",
+                                               "--sizes", args.out + ".fragmentsizes.txt"] + (["--write_all"] if args.write_all else [])))
+        print("---------Step4: Making combined nucleosome position map ------------------------")
+        from .merge import run_merge
+        run_merge(p.parse_args(["merge", "--occpeaks", args.out + ".occpeaks.bed.gz", "--nucpos", args.out + ".nucpos.bed.gz",
+                                "--out", args.out]))
     elif args.command == "vprocess":
         print("---------Processing VPlot-----------------------------------------")
         from .run_vprocess import run_vprocess

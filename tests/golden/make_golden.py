@@ -117,12 +117,17 @@ def main():
     oc, op, ov = bed_table(RES + "example.occpeaks.bed.gz", 4)
     nc_, np_, nv = bed_table(RES + "example.nucpos.bed.gz", 10)
     rc, rp, rv = bed_table(RES + "example.nucpos.redundant.bed.gz", 10)
+    merged = hostio.read_bedgraph_gz(RES + "example.nucmap_combined.bed.gz")
+    occ_text = "".join("\t".join(r) + "\n" for r in hostio.read_bedgraph_gz(RES + "example.occpeaks.bed.gz"))
+    nuc_text = "".join("\t".join(r) + "\n" for r in hostio.read_bedgraph_gz(RES + "example.nucpos.bed.gz"))
+    merged_text = "".join("\t".join(r) + "\n" for r in merged)
     np.savez_compressed(
         os.path.join(HERE, "example_golden.npz"),
         track_off=np.cumsum([0] + [e - s for _, s, e in chunks]).astype(np.int64),
         occpeaks_chrom=oc, occpeaks_pos=op, occpeaks_vals=ov,
         nucpos_chrom=nc_, nucpos_pos=np_, nucpos_vals=nv,
         redundant_chrom=rc, redundant_pos=rp, redundant_vals=rv,
+        occpeaks_text=occ_text, nucpos_text=nuc_text, nucmap_combined_text=merged_text,
         nuc_dist=ndist, fragmentsizes=fsz, scores_706661=hostio.bedgraph_region(scores_rows, "chrII", 706661, 706662)[0],
         **tracks)
     for f in ("example_inputs.npz", "example_golden.npz"):

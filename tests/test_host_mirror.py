@@ -218,3 +218,16 @@ def test_native_bgzip_tabix_equals_python(tmp_path):
         for t in range(len(mine.names)):
             assert mine.bins[t] == {k: v for k, v in theirs.bins[t].items() if k != 37450}
             assert mine.linear[t] == theirs.linear[t]
+
+
+def test_merge_reproduces_shipped_nucmap(tmp_path, golden):
+    """`nucleoatac merge` on the reference's shipped occpeaks + nucpos gives its shipped nucmap_combined, byte for byte."""
+    import gzip as gz
+    from nucleoatac_b200.cli import nucleoatac_main
+    occ, nuc = str(tmp_path / "e.occpeaks.bed"), str(tmp_path / "e.nucpos.bed")
+    open(occ, "w").write(str(golden["occpeaks_text"]))
+    open(nuc, "w").write(str(golden["nucpos_text"]))
+    out = str(tmp_path / "e")
+    assert nucleoatac_main(["merge", "--occpeaks", occ, "--nucpos", nuc, "--out", out]) == 0
+    assert gz.open(out + ".nucmap_combined.bed.gz", "rt").read() == str(golden["nucmap_combined_text"])
+    assert os.path.exists(out + ".nucmap_combined.bed.gz.tbi")
