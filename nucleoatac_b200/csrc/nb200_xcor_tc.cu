@@ -13,35 +13,44 @@
 // (Z[t][s][0..7] = Es[8t+s .. 8t+s+7], 16 B rows) and the UMMA shared-memory descriptor walks it with
 // SBO = LBO = 128 B, i.e. the 8x16B core matrices of neighbouring row groups / K chunks overlap in memory.
 // B = G (constant per run: VMat x fragment-size distribution) is pre-split, pre-tiled and block-sparsified on the
-// host (the non-zero region of G is a parallelogram) and streamed L2 -> SMEM with cp.async.bulk through a 6-stage
-// mbarrier ring.  fp64-grade accuracy of the operands comes from a 2-term fp16 split (hi + lo, 22 bits) of both
-// operands, scaled by powers of two into the fp16 range: three MMAs hi*hi + hi*lo + lo*hi accumulate in fp32 TMEM.
-// The epilogue (4 warps, one TMEM lane = one output position per thread) reads H with tcgen05.ld and contracts it
-// with the unscaled fp64 track, double-buffered against the MMAs of the next 64-column slab of H.
+// host (the non-zero region of G is a parallelogram) and streamed L2 -> SMEM with cp.async.bulk through an mbarrier
+// ring.  fp64-grade accuracy of the operands comes from a 2-term fp16 split (hi + lo, 22 bits) of both operands,
+// scaled by powers of two into the fp16 range: three MMAs hi*hi + hi*lo + lo*hi accumulate in fp32 TMEM.
 //
-// Per CTA: 4 x-tiles of 128 outputs share every G stage (TMEM: 2 buffers x 4 tiles x 64 columns = 512 columns).
-// Warp roles: 0-3 epilogue (+ operand generation), 4 bulk-copy producer, 5 MMA issuer (+ TMEM alloc).
+// Persistent kernel, one CTA per SM, work item = (chunk, 2 x-tiles of 128 outputs).  TMEM (512 columns) holds two
+// buffers of 2 x 128 accumulator columns, so the slab q+1 of H is contracted while slab q is read back.  Warp roles
+// (connected by mbarriers only): 0-7 epilogue (tcgen05.ld of H, contraction with the fp32 track in runs of 8 summed in
+// fp64), 8 bulk-copy producer, 9-10 MMA issuers (one per x-tile; the whole warp runs the loop, one elected lane issues
+// -- two independent accumulation streams), 11-14 operand generation for the NEXT item (E window -> fp32 + fp16 hi/lo
+// Hankel rows, double-buffered).  What bounds it now is the shared-memory data pipe: each 128x128x16 MMA fetches 64
+// wavefronts of operands in its 64 cycles, on top of the epilogue's E reads and the bulk-copy writes.
 #include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 
 #include "nb200_dev.cuh"
 
-#define TC_XT 2
+#define TC_XT 2                           // x-tiles of 128 outputs per work item (they share every G stage)
 #define TC_M 128
 #define TC_TX (TC_XT * TC_M)
 #define TC_N 128
-#define TC_KS 64
-#define TC_STAGES 2
-#define TC_BUFS 1                         // TMEM accumulator buffers per CTA (two CTAs per SM overlap each other instead)
-#define TC_TMEM_COLS (TC_BUFS * TC_XT * TC_N)
+#define TC_KS 64                          // K (b taps) per G stage
+#define TC_MAX_STAGES 5
+#define TC_BUFS 2                         // TMEM accumulator buffers: slab q+1 is contracted while slab q is read back
+#define TC_TMEM_COLS (TC_BUFS * TC_XT * TC_N)   // = 512: one persistent CTA per SM
 #define TC_PART_BYTES (TC_N * TC_KS * 2)
 #define TC_STAGE_BYTES (2 * TC_PART_BYTES)
-#define TC_EPI_WARPS (4 * TC_XT)       // 4 warps (one TMEM lane quarter each) per x-tile
+#define TC_EPI_WARPS (4 * TC_XT)          // 4 warps (one TMEM lane quarter each) per x-tile
 #define TC_WARP_PROD TC_EPI_WARPS
 #define TC_WARP_MMA (TC_EPI_WARPS + 1)
-#define TC_THREADS (32 * (TC_EPI_WARPS + 2))
+#define TC_WARP_PREP (TC_EPI_WARPS + 1 + TC_XT)   // first of the operand-generation warps (one MMA warp per x-tile before them)
+#define TC_PREP_WARPS 4
+#define TC_PREP_THREADS (32 * TC_PREP_WARPS)
+#define TC_THREADS (32 * (TC_EPI_WARPS + 1 + TC_XT + TC_PREP_WARPS))
 #define TC_LBO_B (TC_N * 16)          // bytes between the two 16-byte K chunks of a K16 block in a G stage image
 
 struct TcPlan {
@@ -139,6 +148,29 @@ __device__ __forceinline__ void tc_mma_f16_w(uint32_t d_tmem, uint32_t a_lo, uin
         "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Whole-warp (convergent) forms: every lane executes the call, one elected lane issues.  Keeping the issuing warp convergent
+// lets ptxas emit a bare ELECT + predicated UTCHMMA instead of a per-instruction election loop.
+__device__ __forceinline__ void tc_mma_f16_e(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                             uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_e(uint32_t bar)
+{
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+        : "memory");
+}
 // K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 8x16B core matrices,
 // SBO = byte stride between 8-row groups, LBO = byte stride between the 16-byte K chunks, version 1 (sm_100).
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo)
@@ -171,185 +203,279 @@ struct TcArgs {
     const unsigned char *g_img;
     const double *t_row1;     // f_1 * V[1 - lv, :] (size-1 fragments: single tap)
     double *bx;
+    unsigned long long *dbg;  // NB200_TC_DEBUG: per-CTA clock sums (8 words), else null
     int pwm_up, A0, B0, NAp, NBp, gmin, span, n_stages, n_achunks, sG, has_row1, W, w;
+    int n_chunks, tiles_per_chunk, ring;   // work items = n_chunks * tiles_per_chunk; ring = G stages resident in smem
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 512 / TC_TMEM_COLS) k_nuc_bx_tc(TcArgs a)
+// Persistent kernel: one CTA per SM walks the work items (chunk, pair of x-tiles) it = blockIdx.x + i * gridDim.x.
+// Four warp roles, all connected by mbarriers only (no CTA-wide barrier inside the item loop):
+//   prep  (4 warps)  E window of item n+1 -> fp32 smem copy + fp16 hi/lo Hankel operand Z, double-buffered sets
+//   prod  (1 thread) cp.async.bulk of the G stages through the ring (continues across items)
+//   mma   (1 thread) tcgen05.mma into TMEM buffer gq & 1 (gq = running slab count)
+//   epi   (8 warps)  tcgen05.ld of a finished slab, contraction with E, bx store at the end of the item
+template <bool DBG>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
 {
     extern __shared__ __align__(128) unsigned char sm_tc[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c = blockIdx.y;
-    const int64_t oo = a.out_off[c];
-    const int L = (int)(a.out_off[c + 1] - oo);
-    const int x0 = blockIdx.x * TC_TX;
-    if (x0 >= L) return;
 
     // ---- shared memory carve-up
     const int nZ = (TC_TX + a.NBp) / 8;                     // 128-byte chunks per Z part
+    const int spanp = (a.span + 3) & ~3;
     unsigned char *p = sm_tc;
-    unsigned char *s_stage = p;            p += TC_STAGES * TC_STAGE_BYTES;
-    unsigned char *s_zhi = p;              p += (size_t)nZ * 128;
-    unsigned char *s_zlo = p;              p += (size_t)nZ * 128;
-    double *s_E = reinterpret_cast<double *>(p);            // [span] E over genomic [g0 + gmin, ...)
-    p += sizeof(double) * a.span;
-    double *s_t1 = reinterpret_cast<double *>(p);           // [W] f_1 * V[1,:] (size-1 fragments)
-    p += sizeof(double) * a.W;
-    uint64_t *s_bar = reinterpret_cast<uint64_t *>(p);      // full[S], empty[S], tmem_full[BUFS], tmem_empty[BUFS]
-    p += sizeof(uint64_t) * (2 * TC_STAGES + 2 * TC_BUFS);
+    unsigned char *s_stage = p;            p += (size_t)a.ring * TC_STAGE_BYTES;
+    unsigned char *s_z = p;                p += (size_t)4 * nZ * 128;             // [set][hi|lo][nZ * 128]
+    double *s_t1 = reinterpret_cast<double *>(p);           // [W] f_1 * V[1,:] (size-1 fragments; only if non-zero)
+    p += sizeof(double) * (a.has_row1 ? ((a.W + 1) & ~1) : 0);
+    float *s_Eb = reinterpret_cast<float *>(p);             // [set][span] E over genomic [g0 + gmin, ...), rounded to fp32:
+    p += sizeof(float) * 2 * spanp;                         //   both the fp16 split and the epilogue work at that precision
+    int4 *s_tab = reinterpret_cast<int4 *>(p);              // stage table (kept out of the issue loop's global-load latency)
+    p += sizeof(int4) * a.n_stages;
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(p);      // full[ring], empty[ring], tfull[buf][tile], tempty[buf][tile], zfull[2], zempty[2]
+    p += sizeof(uint64_t) * (2 * TC_MAX_STAGES + 4 * TC_XT + 4);
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(p);
-    const uint32_t bar_full = smem_u32(s_bar), bar_empty = bar_full + 8 * TC_STAGES, bar_tfull = bar_empty + 8 * TC_STAGES,
-                   bar_tempty = bar_tfull + 8 * TC_BUFS;
+    const uint32_t bar_full = smem_u32(s_bar), bar_empty = bar_full + 8 * TC_MAX_STAGES, bar_tfull = bar_empty + 8 * TC_MAX_STAGES,
+                   bar_tempty = bar_tfull + 16 * TC_XT, bar_zfull = bar_tempty + 16 * TC_XT, bar_zempty = bar_zfull + 16;
 
     // ---- one-time setup
     if (threadIdx.x == 0) {
-        for (int i = 0; i < TC_STAGES; i++) {
+        for (int i = 0; i < a.ring; i++) {
             mbar_init(bar_full + 8 * i, 1);
-            mbar_init(bar_empty + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, TC_XT);                // one commit per MMA warp
         }
-        for (int i = 0; i < TC_BUFS; i++) {
+        for (int i = 0; i < 2 * TC_XT; i++) {                   // index buf * TC_XT + tile
             mbar_init(bar_tfull + 8 * i, 1);
-            mbar_init(bar_tempty + 8 * i, TC_EPI_WARPS);
+            mbar_init(bar_tempty + 8 * i, 4);                   // the 4 epilogue warps of the tile
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(bar_zfull + 8 * i, TC_PREP_WARPS);
+            mbar_init(bar_zempty + 8 * i, TC_EPI_WARPS + TC_XT);   // epilogue warps (E window) + the MMA warps' commits (Z)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == TC_WARP_MMA) {  // TMEM: all 512 columns (one CTA per SM by __launch_bounds__ + shared memory footprint)
+    if (warp == TC_WARP_MMA) {  // TMEM: all 512 columns (one CTA per SM by shared-memory footprint)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(TC_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // E window (fp64) -> shared; out of track -> 0 (only reached under zero columns of G / unused outputs)
-    {
-        const int64_t eb = a.bias_off[c] - (int64_t)(a.seq_start[c] + a.pwm_up);
-        const int64_t e_lo = a.bias_off[c], e_hi = a.bias_off[c + 1];
-        const int64_t g0 = (int64_t)a.start[c] + x0 + a.gmin;
-        for (int i = threadIdx.x; i < a.span; i += TC_THREADS) {
-            const int64_t idx = eb + g0 + i;
-            s_E[i] = (idx >= e_lo && idx < e_hi) ? a.E[idx] : 0.0;
-        }
-        if (a.has_row1)
-            for (int i = threadIdx.x; i < a.W; i += TC_THREADS) s_t1[i] = a.t_row1[i];
-    }
-    __syncthreads();
-    // A operand: Z[t][s][0..7] = fp16 hi/lo of scale * E[b-window start + 8t + s + j]
+    if (a.has_row1)
+        for (int i = threadIdx.x; i < a.W; i += TC_THREADS) s_t1[i] = a.t_row1[i];
+    for (int i = threadIdx.x; i < a.n_stages; i += TC_THREADS) s_tab[i] = a.tab[i];
     int eexp = 1;
     const double emax = a.emax[0];
     if (emax > 0.0) frexp(32768.0 / emax, &eexp);
     const int sE = eexp - 1;
-    {
-        const double scale = ldexp(1.0, sE);
-        const int boff = a.B0 - a.gmin;  // s_E index of the first b tap of output 0
-        for (int e = threadIdx.x; e < nZ * 8; e += TC_THREADS) {
-            const int t = e >> 3, s = e & 7;
-            __align__(16) __half hi[8], lo[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int idx = boff + 8 * t + s + j;
-                const float v = (idx < a.span) ? (float)(s_E[idx] * scale) : 0.f;
-                hi[j] = __float2half_rn(v);
-                lo[j] = __float2half_rn(v - __half2float(hi[j]));
-            }
-            *reinterpret_cast<uint4 *>(s_zhi + (size_t)e * 16) = *reinterpret_cast<uint4 *>(hi);
-            *reinterpret_cast<uint4 *>(s_zlo + (size_t)e * 16) = *reinterpret_cast<uint4 *>(lo);
-        }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
+    const long long t_begin = DBG ? clock64() : 0;
+    unsigned long long *dbg = DBG ? a.dbg + 8 * (size_t)blockIdx.x : nullptr;
+    const int n_items = a.n_chunks * a.tiles_per_chunk;
 
-    if (warp == TC_WARP_PROD) {
-        // ===== producer: stream the G stages (hi + lo, 16 KB) through the ring =====
+    if (warp >= TC_WARP_PREP) {
+        // ===== operand generation: E window (fp32) and Z[t][s][0..7] = fp16 hi/lo of 2^sE * E[b-window start + 8t + s + j]
+        const int tid = threadIdx.x - 32 * TC_WARP_PREP;
+        const float scale = (float)ldexp(1.0, sE);
+        const int boff = a.B0 - a.gmin;  // s_E index of the first b tap of output 0
+        long long w_ze = 0;
+        int n = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+            const int c = it / a.tiles_per_chunk, x0 = (it - c * a.tiles_per_chunk) * TC_TX;
+            const int64_t oo = a.out_off[c];
+            if (x0 >= (int)(a.out_off[c + 1] - oo)) continue;
+            const int set = n & 1;
+            const long long t0 = DBG ? clock64() : 0;
+            mbar_wait(bar_zempty + 8 * set, ((n >> 1) & 1) ^ 1);
+            if (DBG) w_ze += clock64() - t0;
+            float *s_E = s_Eb + (size_t)set * spanp;
+            const int64_t e_lo = a.bias_off[c], e_hi = a.bias_off[c + 1];
+            const int64_t ebase = e_lo - (int64_t)(a.seq_start[c] + a.pwm_up) + (int64_t)a.start[c] + x0 + a.gmin;
+#pragma unroll 4
+            for (int i = tid; i < a.span; i += TC_PREP_THREADS) {   // out of track -> 0 (only under zero columns of G / unused outputs)
+                const int64_t idx = ebase + i;
+                s_E[i] = (idx >= e_lo && idx < e_hi) ? (float)a.E[idx] : 0.f;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_PREP_THREADS) : "memory");
+            unsigned char *zh = s_z + (size_t)set * 2 * nZ * 128, *zl = zh + (size_t)nZ * 128;
+            for (int e = tid; e < nZ * 8; e += TC_PREP_THREADS) {
+                __align__(16) __half hi[8], lo[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int idx = boff + e + j;                       // = boff + 8t + s + j with e = 8t + s
+                    const float v = (idx < a.span) ? s_E[idx] * scale : 0.f;   // power-of-two scale: exact
+                    hi[j] = __float2half_rn(v);
+                    lo[j] = __float2half_rn(v - __half2float(hi[j]));
+                }
+                *reinterpret_cast<uint4 *>(zh + (size_t)e * 16) = *reinterpret_cast<uint4 *>(hi);
+                *reinterpret_cast<uint4 *>(zl + (size_t)e * 16) = *reinterpret_cast<uint4 *>(lo);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_zfull + 8 * set);
+            n++;
+        }
+        if (DBG && tid == 0) dbg[6] = (unsigned long long)w_ze;
+    } else if (warp == TC_WARP_PROD) {
+        // ===== producer: stream the G stages (hi + lo) through the ring, once per item =====
         if (lane == 0) {
-            for (int s = 0; s < a.n_stages; s++) {
-                const int slot = s % TC_STAGES;
-                const uint32_t ph = (s / TC_STAGES) & 1;
-                mbar_wait(bar_empty + 8 * slot, ph ^ 1);
-                mbar_expect_tx(bar_full + 8 * slot, TC_STAGE_BYTES);
-                bulk_g2s(smem_u32(s_stage + (size_t)slot * TC_STAGE_BYTES), a.g_img + (size_t)s * TC_STAGE_BYTES, TC_STAGE_BYTES,
-                         bar_full + 8 * slot);
+            const unsigned char *g_img = a.g_img;
+            int slot = 0;
+            uint32_t ph = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+                const int c = it / a.tiles_per_chunk, x0 = (it - c * a.tiles_per_chunk) * TC_TX;
+                if (x0 >= (int)(a.out_off[c + 1] - a.out_off[c])) continue;
+                for (int s = 0; s < a.n_stages; s++) {
+                    mbar_wait(bar_empty + 8 * slot, ph ^ 1);
+                    mbar_expect_tx(bar_full + 8 * slot, TC_STAGE_BYTES);
+                    bulk_g2s(smem_u32(s_stage + (size_t)slot * TC_STAGE_BYTES), g_img + (size_t)s * TC_STAGE_BYTES, TC_STAGE_BYTES,
+                             bar_full + 8 * slot);
+                    if (++slot == a.ring) {
+                        slot = 0;
+                        ph ^= 1;
+                    }
+                }
             }
         }
-    } else if (warp == TC_WARP_MMA) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);  // f16 x f16 -> f32
-            // descriptor words: low = start address >> 4 | (LBO >> 4) << 16, high = SBO >> 4 | version 1 << 14
-            const uint32_t desc_hi = (128u >> 4) | (1u << 14);                                // SBO = 128 B for both operands
-            const uint32_t a_hi0 = ((smem_u32(s_zhi) >> 4) & 0x3FFF) | ((128u >> 4) << 16);   // Hankel view: LBO = SBO = 128 B
-            const uint32_t a_lo0 = ((smem_u32(s_zlo) >> 4) & 0x3FFF) | ((128u >> 4) << 16);
+    } else if (warp >= TC_WARP_MMA) {
+        // ===== MMA issuers: warp TC_WARP_MMA + j contracts x-tile j.  The whole warp runs the loop (convergent); one elected
+        // lane issues.  Two issuing warps keep two independent accumulation streams in the tensor pipe.
+        const int j = warp - TC_WARP_MMA;
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);  // f16 x f16 -> f32
+        // descriptor words: low = start address >> 4 | (LBO >> 4) << 16, high = SBO >> 4 | version 1 << 14
+        const uint32_t desc_hi = (128u >> 4) | (1u << 14);                                // SBO = 128 B for both operands
+        long long w_zf = 0, w_te = 0, w_full = 0;
+        int n = 0, gq = 0, slot = 0;
+        uint32_t ph = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+            const int c = it / a.tiles_per_chunk, x0 = (it - c * a.tiles_per_chunk) * TC_TX;
+            if (x0 >= (int)(a.out_off[c + 1] - a.out_off[c])) continue;
+            const int set = n & 1;
+            {
+                const long long t0 = DBG ? clock64() : 0;
+                mbar_wait(bar_zfull + 8 * set, (n >> 1) & 1);
+                tc_fence_after();
+                if (DBG) w_zf += clock64() - t0;
+            }
+            const uint32_t zb = smem_u32(s_z + (size_t)set * 2 * nZ * 128) + 2048u * j;      // x-tile j: 128 elements = 16 chunks of 128 B on
+            const uint32_t a_hi0 = ((zb >> 4) & 0x3FFF) | ((128u >> 4) << 16);            // Hankel view: LBO = SBO = 128 B
+            const uint32_t a_lo0 = (((zb + (uint32_t)nZ * 128u) >> 4) & 0x3FFF) | ((128u >> 4) << 16);
             for (int s = 0; s < a.n_stages; s++) {
-                const int4 st = a.tab[s];
-                const int q = st.x, kblk0 = st.y, nblk = st.z;
+                const int4 st = s_tab[s];
+                const int kblk0 = st.y, nblk = st.z;
                 const bool first = st.w & 1, last = st.w & 2;
-                const int buf = q % TC_BUFS;
-                const int slot = s % TC_STAGES;
-                const uint32_t ph = (s / TC_STAGES) & 1;
+                const int buf = gq & 1;
                 if (first) {
-                    mbar_wait(bar_tempty + 8 * buf, ((q / TC_BUFS) & 1) ^ 1);
+                    const long long t0 = DBG ? clock64() : 0;
+                    mbar_wait(bar_tempty + 8 * (buf * TC_XT + j), ((gq >> 1) & 1) ^ 1);
                     tc_fence_after();
+                    if (DBG) w_te += clock64() - t0;
                 }
+                const long long t1 = DBG ? clock64() : 0;
                 mbar_wait(bar_full + 8 * slot, ph);
                 tc_fence_after();
+                if (DBG) w_full += clock64() - t1;
                 const uint32_t sb = smem_u32(s_stage + (size_t)slot * TC_STAGE_BYTES);
                 uint32_t bh = ((sb >> 4) & 0x3FFF) | ((uint32_t)(TC_LBO_B >> 4) << 16);
                 uint32_t ah = a_hi0 + (uint32_t)(2 * kblk0) * 8, al = a_lo0 + (uint32_t)(2 * kblk0) * 8;
-                const uint32_t d0 = tmem + (uint32_t)(buf * (TC_XT * TC_N));
+                const uint32_t d = tmem + (uint32_t)(buf * (TC_XT * TC_N) + j * TC_N);
                 uint32_t acc0 = first ? 0u : 1u;
                 for (int t = 0; t < nblk; t++) {
                     const uint32_t bl = bh + (TC_PART_BYTES >> 4);
-#pragma unroll
-                    for (int j = 0; j < TC_XT; j++) {
-                        const uint32_t d = d0 + (uint32_t)(j * TC_N);
-                        tc_mma_f16_w(d, ah + 128u * j, desc_hi, bh, desc_hi, idesc, acc0);   // hi * hi
-                        tc_mma_f16_w(d, ah + 128u * j, desc_hi, bl, desc_hi, idesc, 1u);     // hi * lo
-                        tc_mma_f16_w(d, al + 128u * j, desc_hi, bh, desc_hi, idesc, 1u);     // lo * hi
-                    }
+                    tc_mma_f16_e(d, ah, desc_hi, bh, desc_hi, idesc, acc0);   // hi * hi
+                    tc_mma_f16_e(d, ah, desc_hi, bl, desc_hi, idesc, 1u);     // hi * lo
+                    tc_mma_f16_e(d, al, desc_hi, bh, desc_hi, idesc, 1u);     // lo * hi
                     acc0 = 1u;
                     bh += (2 * TC_LBO_B) >> 4;   // next K16 block of the stage
                     ah += 16;                    // Hankel view advances by 16 elements = 2 chunks of 128 B
                     al += 16;
                 }
-                tc_commit(bar_empty + 8 * slot);               // smem slot reusable once these MMAs retire
-                if (last) tc_commit(bar_tfull + 8 * buf);      // slab q of H complete in TMEM
+                tc_commit_e(bar_empty + 8 * slot);                     // smem slot reusable once these MMAs retire
+                if (last) {
+                    tc_commit_e(bar_tfull + 8 * (buf * TC_XT + j));    // slab of H complete in TMEM
+                    gq++;
+                }
+                if (++slot == a.ring) {
+                    slot = 0;
+                    ph ^= 1;
+                }
             }
+            tc_commit_e(bar_zempty + 8 * set);                         // Z set free once every MMA of the item has retired
+            n++;
+        }
+        if (DBG && j == 0 && lane == 0) {
+            dbg[1] = (unsigned long long)w_zf;
+            dbg[2] = (unsigned long long)w_te;
+            dbg[3] = (unsigned long long)w_full;
+            dbg[7] = (unsigned long long)n;
         }
     } else {
         // ===== epilogue: bx[x] = sum_n E[x + A0 + n] * H[x, n]; warps 4j..4j+3 own x-tile j (one TMEM lane quarter each)
         const int j = warp >> 2, wq = warp & 3;
         const int m = wq * 32 + lane;                          // TMEM lane = output position within the x-tile
         const int aoff = a.A0 - a.gmin;
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};                  // independent chains: the fp64 pipe is latency bound otherwise
-        if (a.has_row1) {  // insert size 1: Bp[1,c] = E[c] (one tap) -> plain 1-D correlation, done while the MMAs start
-            const double *Ew = s_E + (TC_M * j + m - a.w - a.gmin);
-            int k = 0;
-            for (; k + 4 <= a.W; k += 4) {
-#pragma unroll
-                for (int u = 0; u < 4; u++) acc[u] = fma(s_t1[k + u], Ew[k + u], acc[u]);
-            }
-            for (; k < a.W; k++) acc[0] = fma(s_t1[k], Ew[k], acc[0]);
-        }
-        const double lin = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-        acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
-        for (int q = 0; q < a.n_achunks; q++) {
-            const int buf = q % TC_BUFS;
-            mbar_wait(bar_tfull + 8 * buf, (q / TC_BUFS) & 1);
-            tc_fence_after();
-            const double *Ew = s_E + aoff + TC_M * j + m + TC_N * q;
-#pragma unroll
-            for (int h = 0; h < TC_N / 32; h++) {
-                uint32_t r[32];
-                tc_ld32(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * (TC_XT * TC_N) + j * TC_N + 32 * h), r);
-                tc_wait_ld();
-#pragma unroll
-                for (int n = 0; n < 32; n++) acc[n & 3] = fma((double)__uint_as_float(r[n]), Ew[32 * h + n], acc[n & 3]);
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
-        }
         const double unscale = ldexp(1.0, -(sE + a.sG));
-        const int x = x0 + TC_M * j + m;
-        if (x < L) a.bx[oo + x] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) * unscale + lin;
+        long long w_tf = 0, t_epi = 0;
+        int n = 0, gq = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+            const int c = it / a.tiles_per_chunk, x0 = (it - c * a.tiles_per_chunk) * TC_TX;
+            const int64_t oo = a.out_off[c];
+            const int L = (int)(a.out_off[c + 1] - oo);
+            if (x0 >= L) continue;
+            const int set = n & 1;
+            mbar_wait(bar_zfull + 8 * set, (n >> 1) & 1);
+            const float *s_E = s_Eb + (size_t)set * spanp;
+            double lin = 0.0;
+            if (a.has_row1) {  // insert size 1: Bp[1,c] = E[c] (one tap) -> plain 1-D correlation
+                const float *Ew = s_E + (TC_M * j + m - a.w - a.gmin);
+                double l4[4] = {0.0, 0.0, 0.0, 0.0};
+                int k = 0;
+                for (; k + 4 <= a.W; k += 4) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) l4[u] = fma(s_t1[k + u], (double)Ew[k + u], l4[u]);
+                }
+                for (; k < a.W; k++) l4[0] = fma(s_t1[k], (double)Ew[k], l4[0]);
+                lin = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+            }
+            // H (fp32 from TMEM) x E (fp32): runs of 8 products are summed in fp32 (4 independent chains per 32 columns),
+            // the runs in fp64 -- rounding ~1e-7 of a run, below the fp16-split error of H itself
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int q = 0; q < a.n_achunks; q++, gq++) {
+                const int buf = gq & 1;
+                const long long t0 = DBG ? clock64() : 0;
+                mbar_wait(bar_tfull + 8 * (buf * TC_XT + j), (gq >> 1) & 1);
+                tc_fence_after();
+                const long long t1 = DBG ? clock64() : 0;
+                if (DBG) w_tf += t1 - t0;
+                const float *Ew = s_E + aoff + TC_M * j + m + TC_N * q;
+#pragma unroll
+                for (int h = 0; h < TC_N / 32; h++) {
+                    uint32_t r[32];
+                    tc_ld32(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * (TC_XT * TC_N) + j * TC_N + 32 * h), r);
+                    tc_wait_ld();
+                    float f[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+#pragma unroll
+                    for (int nn = 0; nn < 32; nn++) f[nn >> 3] = fmaf(__uint_as_float(r[nn]), Ew[32 * h + nn], f[nn >> 3]);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) acc[u] += (double)f[u];
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * (buf * TC_XT + j));
+                if (DBG) t_epi += clock64() - t1;
+            }
+            const int x = x0 + TC_M * j + m;
+            if (x < L) a.bx[oo + x] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) * unscale + lin;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_zempty + 8 * set);      // this warp no longer reads the E window of the set
+            n++;
+        }
+        if (DBG && threadIdx.x == 0) {
+            dbg[4] = (unsigned long long)w_tf;
+            dbg[5] = (unsigned long long)t_epi;
+            dbg[0] = (unsigned long long)(clock64() - t_begin);
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -388,7 +514,10 @@ int nb200_tc_setup(nb200_ctx *ctx)
     pl->NAp = (pl->NA + TC_N - 1) / TC_N * TC_N;
     pl->NBp = (pl->NB + 15) / 16 * 16;
     pl->n_achunks = pl->NAp / TC_N;
-    pl->has_row1 = (lv <= 1 && 1 < uv) ? 1 : 0;
+    pl->has_row1 = 0;  // size-1 row: a linear term, only paid for when f_1 * V[1,:] is not identically zero
+    if (lv <= 1 && 1 < uv)
+        for (int k = 0; k < W; k++)
+            if (r.h_sizes[1] * r.h_vmat[(size_t)(1 - lv) * W + k] != 0.0) pl->has_row1 = 1;
     // shared E window: genomic offsets [gmin, gmax] relative to the CTA's first output
     int gmin = std::min(std::min(amin, bmin), -w);
     int gmax = std::max(std::max(TC_TX - 1 + pl->A0 + pl->NAp - 1, TC_TX + pl->B0 + pl->NBp + 8), TC_TX - 1 + w);
@@ -507,6 +636,7 @@ int nb200_nuc_bx_tc(nb200_ctx *ctx, nb200_dbatch *b)
     a.g_img = pl->g_img.as<unsigned char>();
     a.t_row1 = pl->t_row1.as<double>();
     a.bx = b->n_bx.as<double>();
+    a.dbg = nullptr;
     a.pwm_up = r.pwm_up;
     a.A0 = pl->A0;
     a.B0 = pl->B0;
@@ -520,14 +650,47 @@ int nb200_nuc_bx_tc(nb200_ctx *ctx, nb200_dbatch *b)
     a.has_row1 = pl->has_row1;
     a.W = r.v_cols;
     a.w = r.v_w;
+    a.n_chunks = b->n_chunks;
+    a.tiles_per_chunk = (int)div_up64(b->max_len, TC_TX);
     const int nZ = (TC_TX + pl->NBp) / 8;
-    size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 2 * (size_t)nZ * 128 + sizeof(double) * (pl->span + r.v_cols) + 8 * (2 * TC_STAGES + 2 * TC_BUFS) + 16;
-    smem = (smem + 127) / 128 * 128;
+    const size_t fixed = 4 * (size_t)nZ * 128 + sizeof(double) * (pl->has_row1 ? ((r.v_cols + 1) & ~1) : 0) + sizeof(float) * 2 * ((pl->span + 3) & ~3) +
+                         sizeof(int4) * pl->n_stages + 8 * (2 * TC_MAX_STAGES + 4 * TC_XT + 4) + 16 + 128;
+    int ring = TC_MAX_STAGES;
+    while (ring > 2 && fixed + (size_t)ring * TC_STAGE_BYTES > 227 * 1024) ring--;
+    const size_t smem = (fixed + (size_t)ring * TC_STAGE_BYTES + 127) / 128 * 128;
     if (smem > 227 * 1024) return nb200_fail(ctx, NB200_ERR_ARG, "VMat too large for the tcgen05 background kernel");
-    NB_CUDA(ctx, cudaFuncSetAttribute(k_nuc_bx_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    a.ring = ring;
+    NB_CUDA(ctx, cudaFuncSetAttribute(k_nuc_bx_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NB_CUDA(ctx, cudaFuncSetAttribute(k_nuc_bx_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps(ctx, b->stream, "k_nuc_bx_tc");
-    dim3 grid((unsigned)div_up64(b->max_len, TC_TX), b->n_chunks);
-    k_nuc_bx_tc<<<grid, TC_THREADS, smem, b->stream>>>(a);
+    const int n_items = a.n_chunks * a.tiles_per_chunk;
+    dim3 grid((unsigned)std::max(1, std::min(ctx->sm_count, n_items)));
+    static const bool tc_debug = getenv("NB200_TC_DEBUG") != nullptr;
+    unsigned long long *d_dbg = nullptr;
+    const size_t n_cta = grid.x;
+    if (tc_debug) {
+        NB_CUDA(ctx, cudaMalloc(&d_dbg, n_cta * 8 * sizeof(unsigned long long)));
+        NB_CUDA(ctx, cudaMemsetAsync(d_dbg, 0, n_cta * 8 * sizeof(unsigned long long), b->stream));
+        a.dbg = d_dbg;
+    }
+    if (tc_debug)
+        k_nuc_bx_tc<true><<<grid, TC_THREADS, smem, b->stream>>>(a);
+    else
+        k_nuc_bx_tc<false><<<grid, TC_THREADS, smem, b->stream>>>(a);
     NB_LAUNCH_CHECK(ctx);
+    if (tc_debug) {  // developer aid: mean clock counts per CTA of the waits of each warp role
+        std::vector<unsigned long long> h(n_cta * 8);
+        NB_CUDA(ctx, cudaStreamSynchronize(b->stream));
+        NB_CUDA(ctx, cudaMemcpy(h.data(), d_dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        cudaFree(d_dbg);
+        double m[8] = {0};
+        for (size_t i = 0; i < n_cta; i++)
+            for (int k = 0; k < 8; k++) m[k] += (double)h[8 * i + k];
+        static const char *nm[8] = {"cta_total", "mma_wait_operands", "mma_wait_tmem_empty", "mma_wait_stage_full", "epi_wait_tmem_full",
+                                    "epi_compute", "prep_wait_set_empty", "items"};
+        fprintf(stderr, "[tc debug] %zu CTAs, ring %d (%d stages, %d slabs per item):", n_cta, ring, pl->n_stages, pl->n_achunks);
+        for (int k = 0; k < 8; k++) fprintf(stderr, " %s=%.0f", nm[k], m[k] / (double)n_cta);
+        fprintf(stderr, "\n");
+    }
     return NB200_OK;
 }
