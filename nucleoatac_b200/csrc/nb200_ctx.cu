@@ -254,6 +254,9 @@ int nb200_set_occ_model(nb200_ctx *ctx, const double *nuc_probs, const double *n
 {
     if (!ctx || !nuc_probs || !nfr_probs || !alphas || upper < 1 || n_alpha < 1 || n_alpha > 128)
         return nb200_fail(ctx, NB200_ERR_ARG, "nb200_set_occ_model: bad argument (n_alpha must be in [1,128])");
+    for (int i = 0; i + 1 < n_alpha; i++)
+        if (alphas[i] == 1.0)
+            return nb200_fail(ctx, NB200_ERR_ARG, "nb200_set_occ_model: alpha == 1 is only supported as the last grid value");
     RunConst &r = ctx->rc;
     NB_CHECK(upload(ctx, r.nuc_probs, nuc_probs, sizeof(double) * upper));
     NB_CHECK(upload(ctx, r.nfr_probs, nfr_probs, sizeof(double) * upper));

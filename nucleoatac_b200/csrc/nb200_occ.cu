@@ -2,9 +2,9 @@
 //
 // Stages (per batch, every chunk in parallel):
 //   k_occ_colsums  per-column sums  cn[c] = sum_i pn[i]*Bp[i,c],  cf[c] = sum_i pf[i]*Bp[i,c]   (bias only)
-//   k_occ_mle      one warp per window: sparse insert-size histogram of the window from the CSC fragment
-//                  matrix, window bias for the sizes that occur, 101-point alpha log-likelihood grid in
-//                  fp64, first-max argmax and the likelihood-ratio confidence bounds   (Occupancy.py:104-146)
+//   k_occ_mle      one window per 8 lanes: the window's fragments from the CSC fragment matrix, 101-point alpha
+//                  log-likelihood grid in fp64 (as the log of a product), first-max argmax and the
+//                  likelihood-ratio confidence bounds                                   (Occupancy.py:104-146)
 //   k_smooth_same  NaN-aware gaussian smoothing of the three tracks                     (Occupancy.py:147-153)
 //   k_occ_peaks    coverage, call_peaks + OccPeak filter + getNucDist, one block per chunk (Occupancy.py:221-240)
 #include <algorithm>
@@ -63,183 +63,144 @@ struct OccMleArgs {
     const int32_t *col_ptr;
     const int2 *ent;
     const double *E, *cn, *cf, *pn, *pf, *alphas;
-    double *fragbias;          // [n_frag][maxw]: window bias of every fragment for each window that contains it
     double *vals, *lower, *upper_b;
-    int pwm_up, upper, flank, step, halfstep, csc_pad, n_alpha, use_bias, maxw;
+    int pwm_up, upper, flank, step, halfstep, csc_pad, n_alpha, use_bias;
     int pn_has_zero, pf_has_zero, both_zero;
     double cutoff, sn_nobias, sf_nobias;
 };
 
-__device__ __forceinline__ int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
-__device__ __forceinline__ int ceil_div(int a, int b) { return -floor_div(-a, b); }
-
-// Window bias per fragment: a fragment of size i centred at column u lies in the <= 2*flank/step + 1 windows
-// t_j = halfstep + step*j with |t_j - u| <= flank; for each of them bias = sum_{c = t_j-flank}^{t_j+flank} Bp[i,c]
-// (the `new_bias` row of Occupancy.py:139-140 for the sizes that actually occur).  One warp per fragment: products
-// over the union of its windows' columns, warp prefix sum, window sums as prefix differences.
-#define FB_WARPS 4
-#define FB_MAXCOLS 512
-__global__ void __launch_bounds__(FB_WARPS * 32) k_occ_fragbias(OccMleArgs a)
-{
-    __shared__ double s_S[FB_WARPS][FB_MAXCOLS];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c = blockIdx.y;
-    const int L = (int)(a.out_off[c + 1] - a.out_off[c]);
-    const int nwin = (L - a.halfstep + a.step - 1) / a.step;
-    const int64_t f0 = a.frag_off[c];
-    const int32_t *cp = a.col_ptr + a.col_off[c];
-    const int nent = cp[L + 2 * a.csc_pad];
-    const int2 *en = a.ent + f0;
-    const int window = 2 * a.flank + 1;
-    const double *Eg = a.E + (a.bias_off[c] - (int64_t)(a.seq_start[c] + a.pwm_up)) + a.start[c];  // E at chunk column 0
-    double *S = s_S[warp];
-    for (int e = blockIdx.x * FB_WARPS + warp; e < nent; e += gridDim.x * FB_WARPS) {
-        const int2 v = en[e];
-        const int u = v.x - a.csc_pad;  // column relative to the chunk start
-        const int jf = max(0, ceil_div(u - a.flank - a.halfstep, a.step));
-        const int jl = min(nwin - 1, floor_div(u + a.flank - a.halfstep, a.step));
-        const int nw = jl - jf + 1;
-        if (nw <= 0) continue;
-        const int c_lo = a.halfstep + a.step * jf - a.flank;  // first column of the first window
-        const int ncols = window + a.step * (nw - 1);
-        double run = 0.0;
-        for (int base = 0; base < ncols; base += 32) {
-            const int idx = base + lane;
-            double x = (idx < ncols) ? bias_cell(Eg + c_lo + idx, v.y) : 0.0;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const double y = __shfl_up_sync(NB_FULL, x, o);
-                if (lane >= o) x += y;
-            }
-            x += run;
-            if (idx < ncols) S[idx] = x;
-            run = __shfl_sync(NB_FULL, x, 31);
-        }
-        __syncwarp();
-        for (int w = lane; w < nw; w += 32) {
-            const int lo = a.step * w;
-            a.fragbias[(f0 + e) * a.maxw + w] = S[lo + window - 1] - (lo > 0 ? S[lo - 1] : 0.0);
-        }
-        __syncwarp();
-    }
-}
-
+// One window per 8-lane group, 4 windows per warp (Occupancy.py:104-146).  The bias of a fragment's insert size over the
+// window multiplies both mixture components (nuc[s] = pn[s]*bias[s]/SN, nfr[s] = pf[s]*bias[s]/SF, Occupancy.py:106-109),
+// so it is a factor of the likelihood that does not depend on alpha: it drops out of the argmax and of the likelihood
+// ratios 2*(max - ll).  What a window needs from the bias model is only SN and SF (sums of the per-column sums cn, cf).
+// ll[a] = sum_f log(v_f(a)) is evaluated as log(prod_f v_f) with every factor pre-scaled by a power of two (again constant
+// in alpha) and the running product renormalised every 32 factors: one log per alpha instead of one per (alpha, fragment).
 #define MLE_WARPS 4
+#define MLE_GROUPS 4
+template <int NQ>  // alphas per lane: lane r of a group owns alphas r, r + 8, ...
 __global__ void __launch_bounds__(MLE_WARPS * 32) k_occ_mle(OccMleArgs a)
 {
-    __shared__ double s_p[MLE_WARPS][32], s_q[MLE_WARPS][32], s_n[MLE_WARPS][32];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    extern __shared__ double sm_mle[];  // pn[upper], pf[upper]
+    __shared__ double s_d[MLE_WARPS][32], s_q[MLE_WARPS][32], s_p[MLE_WARPS][32];
+    double *s_pn = sm_mle, *s_pf = sm_mle + a.upper;
+    for (int i = threadIdx.x; i < a.upper; i += blockDim.x) {
+        s_pn[i] = a.pn[i];
+        s_pf[i] = a.pf[i];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3, r = lane & 7;
     const int c = blockIdx.y;
     const int64_t oo = a.out_off[c];
     const int L = (int)(a.out_off[c + 1] - oo);
     const int nwin = (L - a.halfstep + a.step - 1) / a.step;  // windows at t = halfstep + k*step < L
-    const int wi = blockIdx.x * MLE_WARPS + warp;
-    if (wi >= nwin) return;
+    const int wi = (blockIdx.x * MLE_WARPS + warp) * MLE_GROUPS + g;
+    if ((blockIdx.x * MLE_WARPS + warp) * MLE_GROUPS >= nwin) return;  // whole warp past the last window
+    const bool valid = wi < nwin;
     const int t = a.halfstep + wi * a.step;
-    const int left = t - a.halfstep, right = min(t + a.halfstep + 1, L);
-    const bool last = (wi == nwin - 1);
     const int32_t *cp = a.col_ptr + a.col_off[c];
     const int window = 2 * a.flank + 1;
-    const int e0 = cp[t - a.flank + a.csc_pad], e1 = cp[t + a.flank + 1 + a.csc_pad];
+    const int e0 = valid ? cp[t - a.flank + a.csc_pad] : 0, e1 = valid ? cp[t + a.flank + 1 + a.csc_pad] : 0;
     const int n = e1 - e0;
-    double occ = nb_nan(), lo = nb_nan(), hi = nb_nan();
-    if (n > 0) {  // Occupancy.py:141 `if sum(new_inserts)>0`
-        const int64_t f0 = a.frag_off[c];
-        const int2 *en = a.ent + f0;
-        double SN, SF;
-        if (a.use_bias) {
+    int nmax = n;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(NB_FULL, nmax, o));
+    double SN = a.sn_nobias, SF = a.sf_nobias;
+    if (a.use_bias) {
+        double sn = 0.0, sf = 0.0;
+        if (n > 0) {
             const int64_t co = oo + 2 * (int64_t)a.flank * c + t;  // colsum index of the first window column
-            double sn = 0.0, sf = 0.0;
-            for (int k = lane; k < window; k += 32) {
+            for (int k = r; k < window; k += 8) {
                 sn += a.cn[co + k];
                 sf += a.cf[co + k];
             }
-            SN = warp_sum(sn);
-            SF = warp_sum(sf);
-        } else {
-            SN = a.sn_nobias;
-            SF = a.sf_nobias;
         }
-        // log-likelihood grid; lane owns alphas lane, lane+32, ...  ll[a] = sum_f log(v_f(a)) over the fragments of the
-        // window is evaluated as log(prod_f v_f) with the product kept as (mantissa, binary exponent): one log per
-        // alpha instead of one per (alpha, fragment).  Rounding: ~n ulp, the same order as a sum of n rounded logs.
-        constexpr int NQ = NB200_MAX_ALPHA / 32;
-        double al[NQ], om[NQ], mant[NQ];
-        int ex[NQ];
-        bool dead[NQ];
 #pragma unroll
-        for (int q = 0; q < NQ; q++) {
-            const int ai = lane + 32 * q;
-            al[q] = (ai < a.n_alpha) ? a.alphas[ai] : 0.5;
-            om[q] = 1.0 - al[q];
-            mant[q] = 1.0;
-            ex[q] = 0;
-            // 0 * log(0) = NaN -> -inf (Occupancy.py:112-114) for sizes with no reads but zero probability
-            dead[q] = (ai >= a.n_alpha) || a.both_zero || (al[q] == 0.0 && a.pf_has_zero) || (om[q] == 0.0 && a.pn_has_zero);
+        for (int o = 4; o > 0; o >>= 1) {
+            sn += __shfl_xor_sync(NB_FULL, sn, o);
+            sf += __shfl_xor_sync(NB_FULL, sf, o);
         }
-        int nf = 0;
-        for (int base = e0; base < e1; base += 32) {
-            const int e = base + lane;
-            const int cnt = min(32, e1 - base);
-            if (e < e1) {  // nuc_probs * bias / sum, Occupancy.py:106-109, one fragment per lane
-                const int2 v = en[e];
-                double bias = (double)window;
-                if (a.use_bias) {
-                    const int u = v.x - a.csc_pad;
-                    const int jf = max(0, ceil_div(u - a.flank - a.halfstep, a.step));
-                    bias = a.fragbias[(f0 + e) * a.maxw + (wi - jf)];
-                }
-                const double pv = __dmul_rn(a.pn[v.y], bias) / SN, qv = __dmul_rn(a.pf[v.y], bias) / SF;
-                s_p[warp][lane] = pv - qv;  // alpha*p + (1-alpha)*q is evaluated as q + alpha*(p-q): one FMA per (fragment, alpha)
-                s_q[warp][lane] = qv;
-                s_n[warp][lane] = pv;       // alpha == 1 uses p itself (q + (p-q) would lose p when p << q)
-            }
-            __syncwarp();
-            for (int j = 0; j < cnt; j++) {
-                const double dj = s_p[warp][j], qj = s_q[warp][j];
+        SN = sn;
+        SF = sf;
+    }
+    const double rSN = 1.0 / SN, rSF = 1.0 / SF;
+    double al[NQ], mant[NQ];
+    int ex[NQ];
+    unsigned dead = 0;
 #pragma unroll
-                for (int q = 0; q < NQ - 1; q++) mant[q] *= fma(al[q], dj, qj);
-                {
-                    double v = fma(al[NQ - 1], dj, qj);
-                    if (om[NQ - 1] == 0.0) v = s_n[warp][j];
-                    mant[NQ - 1] *= v;
-                }
-                if ((++nf & 7) == 0) {  // renormalise every 8 factors (factors >= 1e-37 cannot underflow in between)
-#pragma unroll
-                    for (int q = 0; q < NQ; q++) {
-                        const long long bits = __double_as_longlong(mant[q]);
-                        const int e2 = (int)((bits >> 52) & 0x7ff);
-                        if (e2 != 0 && e2 != 0x7ff) {  // positive normal: move the exponent into ex
-                            ex[q] += e2 - 1023;
-                            mant[q] = __longlong_as_double(bits - ((long long)(e2 - 1023) << 52));
-                        }
-                    }
+    for (int q = 0; q < NQ; q++) {
+        const int ai = r + 8 * q;
+        al[q] = (ai < a.n_alpha) ? a.alphas[ai] : 0.5;
+        mant[q] = 1.0;
+        ex[q] = 0;
+        // 0 * log(0) = NaN -> -inf (Occupancy.py:112-114) for sizes with no reads but zero probability
+        if ((ai >= a.n_alpha) || a.both_zero || (al[q] == 0.0 && a.pf_has_zero) || (al[q] == 1.0 && a.pn_has_zero)) dead |= 1u << q;
+    }
+    const bool last_is_one = (al[NQ - 1] == 1.0);  // alpha == 1 (only ever the last grid value, checked on the host)
+    const int2 *en = a.ent + a.frag_off[c];
+    for (int base = 0; base < nmax; base += 8) {
+        {   // lane (g, r) prepares fragment base + r of window g: nuc_probs / sum, nfr_probs / sum, Occupancy.py:106-109
+            const int idx = base + r;
+            double pv = 1.0, qv = 1.0;  // padding fragments contribute the factor 1
+            if (idx < n) {
+                const int sz = en[e0 + idx].y;
+                pv = s_pn[sz] * rSN;
+                qv = s_pf[sz] * rSF;
+                const long long mb = __double_as_longlong(fmax(pv, qv));
+                const int e2 = (int)((mb >> 52) & 0x7ff);
+                if (e2 > 0 && e2 < 0x7fe) {  // scale the pair so that max(p, q) is in [1, 2): exact, constant in alpha
+                    const double sc = __longlong_as_double((long long)(2046 - e2) << 52);
+                    pv *= sc;
+                    qv *= sc;
                 }
             }
-            __syncwarp();
+            s_d[warp][lane] = pv - qv;  // alpha*p + (1-alpha)*q is evaluated as q + alpha*(p-q): one FMA per (fragment, alpha)
+            s_q[warp][lane] = qv;
+            s_p[warp][lane] = pv;       // alpha == 1 uses p itself (q + (p-q) would lose p when p << q)
         }
-        double ll[NQ];
+        __syncwarp();
 #pragma unroll
-        for (int q = 0; q < NQ; q++) {
-            double acc = nb_ninf();
-            if (!dead[q] && mant[q] > 0.0) acc = log(mant[q]) + (double)ex[q] * 0.6931471805599453094;
-            ll[q] = acc;  // NaN / zero products (log 0) -> -inf like `logliks[np.isnan(logliks)] = -inf`
+        for (int j = 0; j < 8; j++) {
+            const double dj = s_d[warp][8 * g + j], qj = s_q[warp][8 * g + j];
+#pragma unroll
+            for (int q = 0; q < NQ - 1; q++) mant[q] *= fma(al[q], dj, qj);
+            double v = fma(al[NQ - 1], dj, qj);
+            if (last_is_one) v = s_p[warp][8 * g + j];
+            mant[NQ - 1] *= v;
         }
-        // first maximum (np.argmax)
+        __syncwarp();
+        if ((base & 24) == 24) {  // every 32 factors (each in (2^-7, 2) away from the grid ends): exponent -> ex
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                const long long bits = __double_as_longlong(mant[q]);
+                const int e2 = (int)((bits >> 52) & 0x7ff);
+                if (e2 != 0 && e2 != 0x7ff) {  // positive normal
+                    ex[q] += e2 - 1023;
+                    mant[q] = __longlong_as_double(bits - ((long long)(e2 - 1023) << 52));
+                }
+            }
+        }
+    }
+    double occ = nb_nan(), lo = nb_nan(), hi = nb_nan();
+    {
+        // NaN / zero products (log 0) -> -inf like `logliks[np.isnan(logliks)] = -inf`; first maximum (np.argmax)
         double best = nb_ninf();
         int besti = 1 << 30;
 #pragma unroll
-        for (int q = 0; q < NB200_MAX_ALPHA / 32; q++) {
-            const int ai = lane + 32 * q;
-            if (ai < a.n_alpha && (ll[q] > best || (ll[q] == best && ai < besti))) {
-                best = ll[q];
+        for (int q = 0; q < NQ; q++) {
+            double acc = nb_ninf();
+            if (!((dead >> q) & 1) && mant[q] > 0.0) acc = log(mant[q]) + (double)ex[q] * 0.6931471805599453094;
+            mant[q] = acc;
+            const int ai = r + 8 * q;
+            if (ai < a.n_alpha && acc > best) {
+                best = acc;
                 besti = ai;
             }
         }
+        if (besti == (1 << 30) && r < a.n_alpha) besti = r;  // all -inf on this lane: its first alpha ties with the others
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            double ob = __shfl_xor_sync(NB_FULL, best, o);
-            int oi = __shfl_xor_sync(NB_FULL, besti, o);
+        for (int o = 4; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(NB_FULL, best, o);
+            const int oi = __shfl_xor_sync(NB_FULL, besti, o);
             if (ob > best || (ob == best && oi < besti)) {
                 best = ob;
                 besti = oi;
@@ -247,31 +208,36 @@ __global__ void __launch_bounds__(MLE_WARPS * 32) k_occ_mle(OccMleArgs a)
         }
         int okmin = 1 << 30, okmax = -1;
 #pragma unroll
-        for (int q = 0; q < NB200_MAX_ALPHA / 32; q++) {
-            const int ai = lane + 32 * q;
+        for (int q = 0; q < NQ; q++) {
+            const int ai = r + 8 * q;
             if (ai < a.n_alpha) {
-                double ratio = 2.0 * (best - ll[q]);  // Occupancy.py:116
+                const double ratio = 2.0 * (best - mant[q]);  // Occupancy.py:116
                 if (ratio < a.cutoff) {
                     okmin = min(okmin, ai);
                     okmax = max(okmax, ai);
                 }
             }
         }
-        okmin = warp_min_i(okmin);
-        okmax = warp_max_i(okmax);
-        if (okmax >= 0 && besti < a.n_alpha) {
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            okmin = min(okmin, __shfl_xor_sync(NB_FULL, okmin, o));
+            okmax = max(okmax, __shfl_xor_sync(NB_FULL, okmax, o));
+        }
+        if (n > 0 && okmax >= 0 && besti < a.n_alpha) {  // Occupancy.py:141 `if sum(new_inserts)>0`
             occ = a.alphas[besti];
             lo = a.alphas[okmin];
             hi = a.alphas[okmax];
         }
     }
-    for (int x = left + lane; x < right; x += 32) {
+    if (!valid) return;
+    const int left = t - a.halfstep, right = min(t + a.halfstep + 1, L);
+    for (int x = left + r; x < right; x += 8) {
         a.vals[oo + x] = occ;
         a.lower[oo + x] = lo;
         a.upper_b[oo + x] = hi;
     }
-    if (last)  // positions past the last window stay NaN (np.ones(n)*nan, Occupancy.py:133-135)
-        for (int x = right + lane; x < L; x += 32) {
+    if (wi == nwin - 1)  // positions past the last window stay NaN (np.ones(n)*nan, Occupancy.py:133-135)
+        for (int x = right + r; x < L; x += 8) {
             a.vals[oo + x] = nb_nan();
             a.lower[oo + x] = nb_nan();
             a.upper_b[oo + x] = nb_nan();
@@ -521,22 +487,15 @@ int nb200_occ_run(nb200_ctx *ctx, nb200_dbatch *b)
         a.cutoff = r.cutoff;
         a.sn_nobias = r.pn_sum * window;
         a.sf_nobias = r.pf_sum * window;
-        a.maxw = (2 * p.flank) / p.step + 1;
-        a.fragbias = nullptr;
-        if (p.use_bias) {
-            if (window + 2 * p.flank > FB_MAXCOLS) return nb200_fail(ctx, NB200_ERR_ARG, "flank > %d unsupported", (FB_MAXCOLS - 1) / 4);
-            NB_CUDA(ctx, b->o_fragbias.reserve(sizeof(double) * (size_t)(b->n_frag > 0 ? b->n_frag : 1) * a.maxw));
-            a.fragbias = b->o_fragbias.as<double>();
-            ProfScope ps(ctx, b->stream, "k_occ_fragbias");
-            dim3 gridf((unsigned)std::max<int64_t>(1, std::min<int64_t>(64, div_up64(b->n_frag / n + 1, FB_WARPS))), n);
-            k_occ_fragbias<<<gridf, FB_WARPS * 32, 0, b->stream>>>(a);
-            NB_LAUNCH_CHECK(ctx);
-        }
         int max_win = (b->max_len - halfstep + p.step - 1) / p.step;
         if (max_win < 1) max_win = 1;
+        const size_t smem = sizeof(double) * 2 * (size_t)p.upper;
         ProfScope ps(ctx, b->stream, "k_occ_mle");
-        dim3 grid((unsigned)div_up64(max_win, MLE_WARPS), n);
-        k_occ_mle<<<grid, MLE_WARPS * 32, 0, b->stream>>>(a);
+        dim3 grid((unsigned)div_up64(max_win, MLE_WARPS * MLE_GROUPS), n);
+        if (r.n_alpha <= 104)
+            k_occ_mle<13><<<grid, MLE_WARPS * 32, smem, b->stream>>>(a);
+        else
+            k_occ_mle<16><<<grid, MLE_WARPS * 32, smem, b->stream>>>(a);
         NB_LAUNCH_CHECK(ctx);
     }
     {
