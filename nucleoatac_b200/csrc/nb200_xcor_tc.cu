@@ -17,13 +17,18 @@
 // ring.  fp64-grade accuracy of the operands comes from a 2-term fp16 split (hi + lo, 22 bits) of both operands,
 // scaled by powers of two into the fp16 range: three MMAs hi*hi + hi*lo + lo*hi accumulate in fp32 TMEM.
 //
-// Persistent kernel, one CTA per SM, work item = (chunk, 2 x-tiles of 128 outputs).  TMEM (512 columns) holds two
-// buffers of 2 x 128 accumulator columns, so the slab q+1 of H is contracted while slab q is read back.  Warp roles
-// (connected by mbarriers only): 0-7 epilogue (tcgen05.ld of H, contraction with the fp32 track in runs of 8 summed in
-// fp64), 8 bulk-copy producer, 9-10 MMA issuers (one per x-tile; the whole warp runs the loop, one elected lane issues
-// -- two independent accumulation streams), 11-14 operand generation for the NEXT item (E window -> fp32 + fp16 hi/lo
-// Hankel rows, double-buffered).  What bounds it now is the shared-memory data pipe: each 128x128x16 MMA fetches 64
-// wavefronts of operands in its 64 cycles, on top of the epilogue's E reads and the bulk-copy writes.
+// Persistent kernel, one CTA per SM, work item = (chunk, 2 x-tiles of 128 outputs).  H is produced in slabs of
+// TC_N = 192 columns (a taps); every K16 block of a slab is contracted by MMAs whose N is TRIMMED to the 16-row
+// granules of G that are non-zero in that block (the non-zero region of G is a hexagon inside the NA x NB box), so
+// the tensor pipe neither multiplies nor fetches the zero corners: 7.8 k MMA cycles per x-tile at 251x251 against
+// 10.8 k for untrimmed 128-wide slabs, and the A operand is fetched once per 192 instead of 128 columns.
+// TMEM holds one 192-column accumulator per x-tile; the two x-tiles are independent accumulation streams (one issuing
+// warp each), so while the finished slab of one tile is read back the tensor pipe contracts the other tile.  Warp
+// roles (connected by mbarriers only): 0-7 epilogue (tcgen05.ld of H, contraction with the fp32 track in runs of 8
+// summed in fp64), 8 bulk-copy producer, 9-10 MMA issuers (the whole warp runs the loop, one elected lane issues),
+// 11-14 operand generation for the NEXT item (E window -> fp32 + fp16 hi/lo Hankel rows, double-buffered).  What
+// bounds it is the shared-memory data pipe (MMA operand fetches + the epilogue's E reads, which are laid out so that
+// a warp's 32 consecutive floats never straddle a 128-byte line).
 #include <cuda_fp16.h>
 
 #include <algorithm>
@@ -37,13 +42,12 @@
 #define TC_XT 2                           // x-tiles of 128 outputs per work item (they share every G stage)
 #define TC_M 128
 #define TC_TX (TC_XT * TC_M)
-#define TC_N 128
-#define TC_KS 64                          // K (b taps) per G stage
+#define TC_N 192                          // slab width (a taps): one accumulator of TC_N TMEM columns per x-tile
 #define TC_MAX_STAGES 5
-#define TC_BUFS 2                         // TMEM accumulator buffers: slab q+1 is contracted while slab q is read back
-#define TC_TMEM_COLS (TC_BUFS * TC_XT * TC_N)   // = 512: one persistent CTA per SM
-#define TC_PART_BYTES (TC_N * TC_KS * 2)
-#define TC_STAGE_BYTES (2 * TC_PART_BYTES)
+#define TC_TMEM_COLS 512                  // allocation (power of two >= TC_XT * TC_N); one persistent CTA per SM
+#define TC_BLOCK_BYTES (TC_N * 16 * 2 * 2)      // one untrimmed K16 block of G: hi + lo images
+#define TC_SLOT_BYTES (3 * TC_BLOCK_BYTES)      // ring slot = one G stage (as many trimmed K16 blocks as fit)
+#define TC_MAX_STAGE_BLOCKS 8
 #define TC_EPI_WARPS (4 * TC_XT)          // 4 warps (one TMEM lane quarter each) per x-tile
 #define TC_WARP_PROD TC_EPI_WARPS
 #define TC_WARP_MMA (TC_EPI_WARPS + 1)
@@ -51,17 +55,16 @@
 #define TC_PREP_WARPS 4
 #define TC_PREP_THREADS (32 * TC_PREP_WARPS)
 #define TC_THREADS (32 * (TC_EPI_WARPS + 1 + TC_XT + TC_PREP_WARPS))
-#define TC_LBO_B (TC_N * 16)          // bytes between the two 16-byte K chunks of a K16 block in a G stage image
 
 struct TcPlan {
     bool ok = false;
     int A0 = 0, B0 = 0, NA = 0, NB = 0, NAp = 0, NBp = 0, gmin = 0, span = 0;
-    int n_stages = 0, n_achunks = 0;
+    int n_stages = 0, n_achunks = 0, n_blocks = 0;
     int sG = 0;           // G scaled by 2^sG
     int has_row1 = 0;     // insert size 1 has a single tap (linear term), kept out of G
-    double density = 0.0; // active K16 x 64 blocks / all blocks
-    DevBuf g_img, stage_tab, t_row1, emax;
-    std::vector<int4> h_tab;
+    double density = 0.0; // MMA columns issued / (NAp * NBp / 16)
+    DevBuf g_img, stage_tab, block_tab, t_row1, emax;
+    std::vector<int4> h_tab, h_blk;
 };
 
 static TcPlan *plan_of(nb200_ctx *ctx, bool create)
@@ -76,6 +79,7 @@ void nb200_tc_release(nb200_ctx *ctx)
     if (!pl) return;
     pl->g_img.release();
     pl->stage_tab.release();
+    pl->block_tab.release();
     pl->t_row1.release();
     pl->emax.release();
     delete pl;
@@ -199,12 +203,13 @@ struct TcArgs {
     const int32_t *seq_start;
     const double *E;
     const double *emax;       // device scalar: max of E over the batch (bit pattern max, E > 0)
-    const int4 *tab;          // per stage {a-chunk q, first K16 block, #K16 blocks, flags: bit0 first of chunk, bit1 last}
+    const int4 *tab;          // per stage {first block, #blocks | flags << 8 (bit0 first of slab, bit1 last), bytes, image offset / 16}
+    const int4 *blk;          // per K16 block {A descriptor advance (16 B units), first row n_lo, rows N_t, byte offset in the stage}
     const unsigned char *g_img;
     const double *t_row1;     // f_1 * V[1 - lv, :] (size-1 fragments: single tap)
     double *bx;
     unsigned long long *dbg;  // NB200_TC_DEBUG: per-CTA clock sums (8 words), else null
-    int pwm_up, A0, B0, NAp, NBp, gmin, span, n_stages, n_achunks, sG, has_row1, W, w;
+    int pwm_up, A0, B0, NAp, NBp, gmin, span, n_stages, n_achunks, n_blocks, sG, has_row1, W, w, epad, stagger;
     int n_chunks, tiles_per_chunk, ring;   // work items = n_chunks * tiles_per_chunk; ring = G stages resident in smem
 };
 
@@ -212,7 +217,7 @@ struct TcArgs {
 // Four warp roles, all connected by mbarriers only (no CTA-wide barrier inside the item loop):
 //   prep  (4 warps)  E window of item n+1 -> fp32 smem copy + fp16 hi/lo Hankel operand Z, double-buffered sets
 //   prod  (1 thread) cp.async.bulk of the G stages through the ring (continues across items)
-//   mma   (1 thread) tcgen05.mma into TMEM buffer gq & 1 (gq = running slab count)
+//   mma   (2 warps)  tcgen05.mma of x-tile j into its TMEM accumulator, N trimmed per K16 block
 //   epi   (8 warps)  tcgen05.ld of a finished slab, contraction with E, bx store at the end of the item
 template <bool DBG>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
@@ -222,21 +227,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
 
     // ---- shared memory carve-up
     const int nZ = (TC_TX + a.NBp) / 8;                     // 128-byte chunks per Z part
-    const int spanp = (a.span + 3) & ~3;
+    const int spanp = (a.epad + a.span + 31) & ~31;
     unsigned char *p = sm_tc;
-    unsigned char *s_stage = p;            p += (size_t)a.ring * TC_STAGE_BYTES;
+    unsigned char *s_stage = p;            p += (size_t)a.ring * TC_SLOT_BYTES;
     unsigned char *s_z = p;                p += (size_t)4 * nZ * 128;             // [set][hi|lo][nZ * 128]
-    double *s_t1 = reinterpret_cast<double *>(p);           // [W] f_1 * V[1,:] (size-1 fragments; only if non-zero)
-    p += sizeof(double) * (a.has_row1 ? ((a.W + 1) & ~1) : 0);
-    float *s_Eb = reinterpret_cast<float *>(p);             // [set][span] E over genomic [g0 + gmin, ...), rounded to fp32:
-    p += sizeof(float) * 2 * spanp;                         //   both the fp16 split and the epilogue work at that precision
-    int4 *s_tab = reinterpret_cast<int4 *>(p);              // stage table (kept out of the issue loop's global-load latency)
+    float *s_Eb = reinterpret_cast<float *>(p);             // [set][epad + span] E over genomic [g0 + gmin, ...), rounded to fp32
+    p += sizeof(float) * 2 * spanp;                         //   (epad: the epilogue's 32-float runs start on 128-byte lines)
+    // size-1 fragments have a single tap (a term linear in E): f_1 * V[1,:] as fp32 (zero padded), a 16-byte aligned
+    // copy of the E window whose element x + k is tap k of output x, and the finished term per output  [only if f_1 V[1,:] != 0]
+    const int Wp = (a.W + 3) & ~3, e1p = TC_TX + Wp + 8;
+    float *s_t1 = reinterpret_cast<float *>(p);             p += sizeof(float) * (a.has_row1 ? Wp : 0);
+    float *s_E1b = reinterpret_cast<float *>(p);            p += sizeof(float) * (a.has_row1 ? 2 * e1p : 0);
+    float *s_linb = reinterpret_cast<float *>(p);           p += sizeof(float) * (a.has_row1 ? 2 * TC_TX : 0);
+    int4 *s_tab = reinterpret_cast<int4 *>(p);              // stage + block tables (kept out of the issue loop's global-load latency)
     p += sizeof(int4) * a.n_stages;
-    uint64_t *s_bar = reinterpret_cast<uint64_t *>(p);      // full[ring], empty[ring], tfull[buf][tile], tempty[buf][tile], zfull[2], zempty[2]
-    p += sizeof(uint64_t) * (2 * TC_MAX_STAGES + 4 * TC_XT + 4);
+    int4 *s_blk = reinterpret_cast<int4 *>(p);
+    p += sizeof(int4) * a.n_blocks;
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(p);      // full[ring], empty[ring], tfull[tile], tempty[tile], zfull[2], zempty[2]
+    p += sizeof(uint64_t) * (2 * TC_MAX_STAGES + 2 * TC_XT + 4 + 1);
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(p);
     const uint32_t bar_full = smem_u32(s_bar), bar_empty = bar_full + 8 * TC_MAX_STAGES, bar_tfull = bar_empty + 8 * TC_MAX_STAGES,
-                   bar_tempty = bar_tfull + 16 * TC_XT, bar_zfull = bar_tempty + 16 * TC_XT, bar_zempty = bar_zfull + 16;
+                   bar_tempty = bar_tfull + 8 * TC_XT, bar_zfull = bar_tempty + 8 * TC_XT, bar_zempty = bar_zfull + 16,
+                   bar_stag = bar_zempty + 16;
 
     // ---- one-time setup
     if (threadIdx.x == 0) {
@@ -244,7 +256,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
             mbar_init(bar_full + 8 * i, 1);
             mbar_init(bar_empty + 8 * i, TC_XT);                // one commit per MMA warp
         }
-        for (int i = 0; i < 2 * TC_XT; i++) {                   // index buf * TC_XT + tile
+        for (int i = 0; i < TC_XT; i++) {
             mbar_init(bar_tfull + 8 * i, 1);
             mbar_init(bar_tempty + 8 * i, 4);                   // the 4 epilogue warps of the tile
         }
@@ -252,6 +264,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
             mbar_init(bar_zfull + 8 * i, TC_PREP_WARPS);
             mbar_init(bar_zempty + 8 * i, TC_EPI_WARPS + TC_XT);   // epilogue warps (E window) + the MMA warps' commits (Z)
         }
+        mbar_init(bar_stag, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == TC_WARP_MMA) {  // TMEM: all 512 columns (one CTA per SM by shared-memory footprint)
@@ -259,8 +272,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (a.has_row1)
-        for (int i = threadIdx.x; i < a.W; i += TC_THREADS) s_t1[i] = a.t_row1[i];
+        for (int i = threadIdx.x; i < Wp; i += TC_THREADS) s_t1[i] = (i < a.W) ? (float)a.t_row1[i] : 0.f;
     for (int i = threadIdx.x; i < a.n_stages; i += TC_THREADS) s_tab[i] = a.tab[i];
+    for (int i = threadIdx.x; i < a.n_blocks; i += TC_THREADS) s_blk[i] = a.blk[i];
     int eexp = 1;
     const double emax = a.emax[0];
     if (emax > 0.0) frexp(32768.0 / emax, &eexp);
@@ -288,7 +302,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
             const long long t0 = DBG ? clock64() : 0;
             mbar_wait(bar_zempty + 8 * set, ((n >> 1) & 1) ^ 1);
             if (DBG) w_ze += clock64() - t0;
-            float *s_E = s_Eb + (size_t)set * spanp;
+            float *s_E = s_Eb + (size_t)set * spanp + a.epad;
             const int64_t e_lo = a.bias_off[c], e_hi = a.bias_off[c + 1];
             const int64_t ebase = e_lo - (int64_t)(a.seq_start[c] + a.pwm_up) + (int64_t)a.start[c] + x0 + a.gmin;
 #pragma unroll 4
@@ -311,13 +325,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
                 *reinterpret_cast<uint4 *>(zl + (size_t)e * 16) = *reinterpret_cast<uint4 *>(lo);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+            if (a.has_row1) {
+                // insert size 1: Bp[1,c] = E[c] (one tap) -> lin[x] = sum_k t1[k] E[x - w + k], a plain 1-D correlation.  Two warps,
+                // 4 consecutive outputs per lane, 4 taps per step from one aligned 16-byte load (64 FMAs per smem wavefront).
+                float *s_E1 = s_E1b + (size_t)set * e1p;
+                const int sh = -a.w - a.gmin;                    // >= 0
+                for (int i = tid; i < e1p; i += TC_PREP_THREADS) {
+                    const int idx = i + sh;
+                    s_E1[i] = (idx < a.span) ? s_E[idx] : 0.f;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(TC_PREP_THREADS) : "memory");
+                if (tid < TC_TX / 4) {
+                    const float4 *e4 = reinterpret_cast<const float4 *>(s_E1 + 4 * tid);
+                    const float4 *t4 = reinterpret_cast<const float4 *>(s_t1);
+                    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+                    float4 e0 = e4[0];
+                    for (int k4 = 0; k4 < Wp / 4; k4++) {
+                        const float4 t = t4[k4], e1 = e4[k4 + 1];
+                        l0 = fmaf(t.x, e0.x, fmaf(t.y, e0.y, fmaf(t.z, e0.z, fmaf(t.w, e0.w, l0))));
+                        l1 = fmaf(t.x, e0.y, fmaf(t.y, e0.z, fmaf(t.z, e0.w, fmaf(t.w, e1.x, l1))));
+                        l2 = fmaf(t.x, e0.z, fmaf(t.y, e0.w, fmaf(t.z, e1.x, fmaf(t.w, e1.y, l2))));
+                        l3 = fmaf(t.x, e0.w, fmaf(t.y, e1.x, fmaf(t.z, e1.y, fmaf(t.w, e1.z, l3))));
+                        e0 = e1;
+                    }
+                    *reinterpret_cast<float4 *>(s_linb + (size_t)set * TC_TX + 4 * tid) = make_float4(l0, l1, l2, l3);
+                }
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_zfull + 8 * set);
             n++;
         }
         if (DBG && tid == 0) dbg[6] = (unsigned long long)w_ze;
     } else if (warp == TC_WARP_PROD) {
-        // ===== producer: stream the G stages (hi + lo) through the ring, once per item =====
+        // ===== producer: stream the G stages (hi + lo images of the trimmed K16 blocks) through the ring, once per item =====
         if (lane == 0) {
             const unsigned char *g_img = a.g_img;
             int slot = 0;
@@ -326,10 +366,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
                 const int c = it / a.tiles_per_chunk, x0 = (it - c * a.tiles_per_chunk) * TC_TX;
                 if (x0 >= (int)(a.out_off[c + 1] - a.out_off[c])) continue;
                 for (int s = 0; s < a.n_stages; s++) {
+                    const int4 st = s_tab[s];
                     mbar_wait(bar_empty + 8 * slot, ph ^ 1);
-                    mbar_expect_tx(bar_full + 8 * slot, TC_STAGE_BYTES);
-                    bulk_g2s(smem_u32(s_stage + (size_t)slot * TC_STAGE_BYTES), g_img + (size_t)s * TC_STAGE_BYTES, TC_STAGE_BYTES,
-                             bar_full + 8 * slot);
+                    mbar_expect_tx(bar_full + 8 * slot, (uint32_t)st.z);
+                    bulk_g2s(smem_u32(s_stage + (size_t)slot * TC_SLOT_BYTES), g_img + (size_t)st.w * 16, (uint32_t)st.z, bar_full + 8 * slot);
                     if (++slot == a.ring) {
                         slot = 0;
                         ph ^= 1;
@@ -341,9 +381,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
         // ===== MMA issuers: warp TC_WARP_MMA + j contracts x-tile j.  The whole warp runs the loop (convergent); one elected
         // lane issues.  Two issuing warps keep two independent accumulation streams in the tensor pipe.
         const int j = warp - TC_WARP_MMA;
-        const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);  // f16 x f16 -> f32
         // descriptor words: low = start address >> 4 | (LBO >> 4) << 16, high = SBO >> 4 | version 1 << 14
         const uint32_t desc_hi = (128u >> 4) | (1u << 14);                                // SBO = 128 B for both operands
+        const uint32_t d0 = tmem + (uint32_t)(j * TC_N);
         long long w_zf = 0, w_te = 0, w_full = 0;
         int n = 0, gq = 0, slot = 0;
         uint32_t ph = 0;
@@ -360,14 +400,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
             const uint32_t zb = smem_u32(s_z + (size_t)set * 2 * nZ * 128) + 2048u * j;      // x-tile j: 128 elements = 16 chunks of 128 B on
             const uint32_t a_hi0 = ((zb >> 4) & 0x3FFF) | ((128u >> 4) << 16);            // Hankel view: LBO = SBO = 128 B
             const uint32_t a_lo0 = (((zb + (uint32_t)nZ * 128u) >> 4) & 0x3FFF) | ((128u >> 4) << 16);
+            // The two tiles share every G stage but each has a single accumulator: if they finished their slabs together the
+            // tensor pipe would idle while both are read back.  Tile 1 therefore starts a few stages behind tile 0 (once; the
+            // offset persists because both streams have the same period), so one tile is contracted while the other drains.
+            if (n == 0 && j == 1 && a.stagger >= 0) mbar_wait(bar_stag, 0);
             for (int s = 0; s < a.n_stages; s++) {
                 const int4 st = s_tab[s];
-                const int kblk0 = st.y, nblk = st.z;
-                const bool first = st.w & 1, last = st.w & 2;
-                const int buf = gq & 1;
-                if (first) {
+                const int b0 = st.x, nblk = st.y & 0xff;
+                const bool first = (st.y >> 8) & 1, last = (st.y >> 9) & 1;
+                if (first) {  // the accumulator of this tile is free once its previous slab has been read back
                     const long long t0 = DBG ? clock64() : 0;
-                    mbar_wait(bar_tempty + 8 * (buf * TC_XT + j), ((gq >> 1) & 1) ^ 1);
+                    mbar_wait(bar_tempty + 8 * j, (gq & 1) ^ 1);
                     tc_fence_after();
                     if (DBG) w_te += clock64() - t0;
                 }
@@ -375,24 +418,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
                 mbar_wait(bar_full + 8 * slot, ph);
                 tc_fence_after();
                 if (DBG) w_full += clock64() - t1;
-                const uint32_t sb = smem_u32(s_stage + (size_t)slot * TC_STAGE_BYTES);
-                uint32_t bh = ((sb >> 4) & 0x3FFF) | ((uint32_t)(TC_LBO_B >> 4) << 16);
-                uint32_t ah = a_hi0 + (uint32_t)(2 * kblk0) * 8, al = a_lo0 + (uint32_t)(2 * kblk0) * 8;
-                const uint32_t d = tmem + (uint32_t)(buf * (TC_XT * TC_N) + j * TC_N);
-                uint32_t acc0 = first ? 0u : 1u;
+                const uint32_t sb = (smem_u32(s_stage + (size_t)slot * TC_SLOT_BYTES) >> 4) & 0x3FFF;
+                uint32_t acc0 = first ? 0u : 1u;   // the first block of a slab is stored untrimmed: it initialises all TC_N columns
                 for (int t = 0; t < nblk; t++) {
-                    const uint32_t bl = bh + (TC_PART_BYTES >> 4);
-                    tc_mma_f16_e(d, ah, desc_hi, bh, desc_hi, idesc, acc0);   // hi * hi
-                    tc_mma_f16_e(d, ah, desc_hi, bl, desc_hi, idesc, 1u);     // hi * lo
-                    tc_mma_f16_e(d, al, desc_hi, bh, desc_hi, idesc, 1u);     // lo * hi
+                    const int4 bk = s_blk[b0 + t];   // {A advance, n_lo, instruction descriptor, B descriptor low word (relative)}
+                    const uint32_t bh = (uint32_t)bk.w + sb;                       // hi image: N_t rows, LBO = N_t * 16 B
+                    const uint32_t bl = bh + 2u * ((uint32_t)bk.w >> 16);           // lo image follows (N_t * 32 B)
+                    const uint32_t ah = a_hi0 + (uint32_t)bk.x, al = a_lo0 + (uint32_t)bk.x;
+                    const uint32_t d = d0 + (uint32_t)bk.y;
+                    tc_mma_f16_e(d, ah, desc_hi, bh, desc_hi, (uint32_t)bk.z, acc0);   // hi * hi
+                    tc_mma_f16_e(d, ah, desc_hi, bl, desc_hi, (uint32_t)bk.z, 1u);     // hi * lo
+                    tc_mma_f16_e(d, al, desc_hi, bh, desc_hi, (uint32_t)bk.z, 1u);     // lo * hi
                     acc0 = 1u;
-                    bh += (2 * TC_LBO_B) >> 4;   // next K16 block of the stage
-                    ah += 16;                    // Hankel view advances by 16 elements = 2 chunks of 128 B
-                    al += 16;
                 }
                 tc_commit_e(bar_empty + 8 * slot);                     // smem slot reusable once these MMAs retire
+                if (n == 0 && j == 0 && s == a.stagger) tc_commit_e(bar_stag);
                 if (last) {
-                    tc_commit_e(bar_tfull + 8 * (buf * TC_XT + j));    // slab of H complete in TMEM
+                    tc_commit_e(bar_tfull + 8 * j);                    // slab of H complete in TMEM
                     gq++;
                 }
                 if (++slot == a.ring) {
@@ -415,6 +457,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
         const int m = wq * 32 + lane;                          // TMEM lane = output position within the x-tile
         const int aoff = a.A0 - a.gmin;
         const double unscale = ldexp(1.0, -(sE + a.sG));
+        const uint32_t t0addr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(j * TC_N);
         long long w_tf = 0, t_epi = 0;
         int n = 0, gq = 0;
         for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
@@ -424,45 +467,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
             if (x0 >= L) continue;
             const int set = n & 1;
             mbar_wait(bar_zfull + 8 * set, (n >> 1) & 1);
-            const float *s_E = s_Eb + (size_t)set * spanp;
-            double lin = 0.0;
-            if (a.has_row1) {  // insert size 1: Bp[1,c] = E[c] (one tap) -> plain 1-D correlation
-                const float *Ew = s_E + (TC_M * j + m - a.w - a.gmin);
-                double l4[4] = {0.0, 0.0, 0.0, 0.0};
-                int k = 0;
-                for (; k + 4 <= a.W; k += 4) {
-#pragma unroll
-                    for (int u = 0; u < 4; u++) l4[u] = fma(s_t1[k + u], (double)Ew[k + u], l4[u]);
-                }
-                for (; k < a.W; k++) l4[0] = fma(s_t1[k], (double)Ew[k], l4[0]);
-                lin = (l4[0] + l4[1]) + (l4[2] + l4[3]);
-            }
+            const float *s_E = s_Eb + (size_t)set * spanp + a.epad;
+            const double lin = a.has_row1 ? (double)s_linb[(size_t)set * TC_TX + TC_M * j + m] : 0.0;  // size-1 term (prep warps)
             // H (fp32 from TMEM) x E (fp32): runs of 8 products are summed in fp32 (4 independent chains per 32 columns),
             // the runs in fp64 -- rounding ~1e-7 of a run, below the fp16-split error of H itself
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
             for (int q = 0; q < a.n_achunks; q++, gq++) {
-                const int buf = gq & 1;
                 const long long t0 = DBG ? clock64() : 0;
-                mbar_wait(bar_tfull + 8 * (buf * TC_XT + j), (gq >> 1) & 1);
+                mbar_wait(bar_tfull + 8 * j, gq & 1);
                 tc_fence_after();
                 const long long t1 = DBG ? clock64() : 0;
                 if (DBG) w_tf += t1 - t0;
-                const float *Ew = s_E + aoff + TC_M * j + m + TC_N * q;
+                const float *Ew = s_E + aoff + TC_M * j + m + TC_N * q;   // lane 0: a multiple of 32 floats from a 128-byte line
+                // two register sets: the tcgen05.ld of columns 32(h+1).. is in flight while columns 32h.. are contracted;
+                // the accumulator is handed back to the MMA warp as soon as its last columns have landed in registers
+                uint32_t r[2][32];
+                tc_ld32(t0addr, r[0]);
 #pragma unroll
                 for (int h = 0; h < TC_N / 32; h++) {
-                    uint32_t r[32];
-                    tc_ld32(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * (TC_XT * TC_N) + j * TC_N + 32 * h), r);
                     tc_wait_ld();
+                    if (h + 1 < TC_N / 32) {
+                        tc_ld32(t0addr + (uint32_t)(32 * (h + 1)), r[(h + 1) & 1]);
+                    } else {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_tempty + 8 * j);
+                    }
                     float f[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-#pragma unroll
-                    for (int nn = 0; nn < 32; nn++) f[nn >> 3] = fmaf(__uint_as_float(r[nn]), Ew[32 * h + nn], f[nn >> 3]);
+                    for (int nn = 0; nn < 32; nn++) f[nn >> 3] = fmaf(__uint_as_float(r[h & 1][nn]), Ew[32 * h + nn], f[nn >> 3]);
 #pragma unroll
                     for (int u = 0; u < 4; u++) acc[u] += (double)f[u];
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_tempty + 8 * (buf * TC_XT + j));
                 if (DBG) t_epi += clock64() - t1;
             }
             const int x = x0 + TC_M * j + m;
@@ -540,52 +576,75 @@ int nb200_tc_setup(nb200_ctx *ctx)
     frexp(32768.0 / gmaxv, &ex);
     pl->sG = ex - 1;
     const double sc = ldexp(1.0, pl->sG);
-    // active K16 blocks per a-chunk -> stages of up to 4 consecutive K16 blocks
+    // Per slab (TC_N rows of G = a taps) the K16 blocks that hold a non-zero, each trimmed to the 16-row granules that are
+    // non-zero in it; the first block of a slab stays untrimmed (its MMA initialises every accumulator column).  Blocks
+    // are packed into stages of at most TC_SLOT_BYTES.  Block image (hi, then lo): canonical K-major no-swizzle core
+    // matrices, (n/8, k/8) at ((k/8) * (N_t/8) + n/8) * 128 B, row n%8, element k%8.
     pl->h_tab.clear();
+    pl->h_blk.clear();
     std::vector<unsigned char> img;
     const int nkb = pl->NBp / 16;
-    int active = 0;
+    long long cols_issued = 0;
     for (int q = 0; q < pl->n_achunks; q++) {
-        int k_lo = nkb, k_hi = -1;
+        struct Blk { int kb, n_lo, n_t; };
+        std::vector<Blk> blks;
         for (int kb = 0; kb < nkb; kb++) {
-            bool nz = false;
-            for (int n = 0; n < TC_N && !nz; n++)
-                for (int k = 0; k < 16 && !nz; k++) nz = G[(size_t)(q * TC_N + n) * pl->NBp + kb * 16 + k] != 0.0;
-            if (nz) {
-                k_lo = std::min(k_lo, kb);
-                k_hi = std::max(k_hi, kb);
-            }
-        }
-        if (k_hi < 0) k_lo = k_hi = 0;  // keep every a-chunk present (one zero block)
-        active += k_hi - k_lo + 1;
-        for (int kb0 = k_lo; kb0 <= k_hi; kb0 += TC_KS / 16) {
-            const int nblk = std::min(TC_KS / 16, k_hi - kb0 + 1);
-            int flags = (kb0 == k_lo ? 1 : 0) | (kb0 + nblk > k_hi ? 2 : 0);
-            pl->h_tab.push_back(make_int4(q, kb0, nblk, flags));
-            const size_t base = img.size();
-            img.resize(base + TC_STAGE_BYTES, 0);
-            __half *hi = reinterpret_cast<__half *>(img.data() + base);
-            __half *lo = reinterpret_cast<__half *>(img.data() + base + TC_PART_BYTES);
+            int r_lo = TC_N, r_hi = -1;
             for (int n = 0; n < TC_N; n++)
-                for (int k = 0; k < nblk * 16; k++) {
-                    const double g = G[(size_t)(q * TC_N + n) * pl->NBp + kb0 * 16 + k] * sc;
-                    const float gf = (float)g;
-                    const __half h = __float2half_rn(gf);
-                    const __half l = __float2half_rn(gf - __half2float(h));
-                    // canonical K-major no-swizzle image: core matrix (n/8, k/8) at ((k/8)*8 + n/8)*128 B, row n%8, elt k%8
-                    const size_t off = ((size_t)(k / 8) * (TC_N / 8) + n / 8) * 64 + (n % 8) * 8 + (k % 8);
-                    hi[off] = h;
-                    lo[off] = l;
-                }
+                for (int k = 0; k < 16; k++)
+                    if (G[(size_t)(q * TC_N + n) * pl->NBp + kb * 16 + k] != 0.0) {
+                        r_lo = std::min(r_lo, n);
+                        r_hi = std::max(r_hi, n);
+                    }
+            if (r_hi < 0) continue;
+            const int n_lo = r_lo / 16 * 16, n_hi = (r_hi + 16) / 16 * 16;
+            blks.push_back({kb, n_lo, n_hi - n_lo});
+        }
+        if (blks.empty()) blks.push_back({0, 0, TC_N});  // keep every slab present (one zero block)
+        blks[0].n_lo = 0;
+        blks[0].n_t = TC_N;
+        size_t bi = 0;
+        while (bi < blks.size()) {
+            const int first_blk = (int)pl->h_blk.size();
+            const size_t base = img.size();
+            int bytes = 0, cnt = 0;
+            const size_t bi_start = bi;
+            while (bi < blks.size() && cnt < TC_MAX_STAGE_BLOCKS && bytes + blks[bi].n_t * 64 <= TC_SLOT_BYTES) {
+                const Blk &bk = blks[bi];
+                const uint32_t idesc = (1u << 4) | ((uint32_t)(bk.n_t >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);  // f16 x f16 -> f32
+                pl->h_blk.push_back(make_int4(16 * bk.kb, bk.n_lo, (int)idesc, (bytes >> 4) | (bk.n_t << 16)));
+                img.resize(base + bytes + (size_t)bk.n_t * 64, 0);
+                __half *hi = reinterpret_cast<__half *>(img.data() + base + bytes);
+                __half *lo = hi + (size_t)bk.n_t * 16;
+                for (int n = 0; n < bk.n_t; n++)
+                    for (int k = 0; k < 16; k++) {
+                        const double g = G[(size_t)(q * TC_N + bk.n_lo + n) * pl->NBp + bk.kb * 16 + k] * sc;
+                        const float gf = (float)g;
+                        const __half h = __float2half_rn(gf);
+                        const __half l = __float2half_rn(gf - __half2float(h));
+                        const size_t off = ((size_t)(k / 8) * (bk.n_t / 8) + n / 8) * 64 + (n % 8) * 8 + (k % 8);
+                        hi[off] = h;
+                        lo[off] = l;
+                    }
+                bytes += bk.n_t * 64;
+                cols_issued += bk.n_t;
+                cnt++;
+                bi++;
+            }
+            const int flags = (bi_start == 0 ? 1 : 0) | (bi == blks.size() ? 2 : 0);
+            pl->h_tab.push_back(make_int4(first_blk, cnt | (flags << 8), bytes, (int)(base >> 4)));
         }
     }
+    pl->n_blocks = (int)pl->h_blk.size();
     pl->n_stages = (int)pl->h_tab.size();
-    pl->density = (double)active / ((double)pl->n_achunks * nkb);
+    pl->density = (double)cols_issued / ((double)pl->NAp * nkb);
     NB_CUDA(ctx, cudaSetDevice(ctx->device));
     NB_CUDA(ctx, pl->g_img.reserve(img.size()));
     NB_CUDA(ctx, cudaMemcpy(pl->g_img.p, img.data(), img.size(), cudaMemcpyHostToDevice));
     NB_CUDA(ctx, pl->stage_tab.reserve(sizeof(int4) * pl->h_tab.size()));
     NB_CUDA(ctx, cudaMemcpy(pl->stage_tab.p, pl->h_tab.data(), sizeof(int4) * pl->h_tab.size(), cudaMemcpyHostToDevice));
+    NB_CUDA(ctx, pl->block_tab.reserve(sizeof(int4) * pl->h_blk.size()));
+    NB_CUDA(ctx, cudaMemcpy(pl->block_tab.p, pl->h_blk.data(), sizeof(int4) * pl->h_blk.size(), cudaMemcpyHostToDevice));
     std::vector<double> t1(W, 0.0);
     if (pl->has_row1)
         for (int k = 0; k < W; k++) t1[k] = r.h_sizes[1] * r.h_vmat[(size_t)(1 - lv) * W + k];
@@ -633,6 +692,7 @@ int nb200_nuc_bx_tc(nb200_ctx *ctx, nb200_dbatch *b)
     a.E = b->d_E.as<double>();
     a.emax = pl->emax.as<double>();
     a.tab = pl->stage_tab.as<int4>();
+    a.blk = pl->block_tab.as<int4>();
     a.g_img = pl->g_img.as<unsigned char>();
     a.t_row1 = pl->t_row1.as<double>();
     a.bx = b->n_bx.as<double>();
@@ -646,6 +706,8 @@ int nb200_nuc_bx_tc(nb200_ctx *ctx, nb200_dbatch *b)
     a.span = pl->span;
     a.n_stages = pl->n_stages;
     a.n_achunks = pl->n_achunks;
+    a.n_blocks = pl->n_blocks;
+    a.epad = (32 - ((pl->A0 - pl->gmin) & 31)) & 31;
     a.sG = pl->sG;
     a.has_row1 = pl->has_row1;
     a.W = r.v_cols;
@@ -653,13 +715,16 @@ int nb200_nuc_bx_tc(nb200_ctx *ctx, nb200_dbatch *b)
     a.n_chunks = b->n_chunks;
     a.tiles_per_chunk = (int)div_up64(b->max_len, TC_TX);
     const int nZ = (TC_TX + pl->NBp) / 8;
-    const size_t fixed = 4 * (size_t)nZ * 128 + sizeof(double) * (pl->has_row1 ? ((r.v_cols + 1) & ~1) : 0) + sizeof(float) * 2 * ((pl->span + 3) & ~3) +
-                         sizeof(int4) * pl->n_stages + 8 * (2 * TC_MAX_STAGES + 4 * TC_XT + 4) + 16 + 128;
+    const size_t fixed = 4 * (size_t)nZ * 128 + sizeof(float) * 2 * ((a.epad + pl->span + 31) & ~31) +
+                         sizeof(float) * (pl->has_row1 ? (((r.v_cols + 3) & ~3) + 2 * (TC_TX + ((r.v_cols + 3) & ~3) + 8) + 2 * TC_TX) : 0) + sizeof(int4) * (pl->n_stages + pl->n_blocks) +
+                         8 * (2 * TC_MAX_STAGES + 2 * TC_XT + 4 + 1) + 16 + 128;
     int ring = TC_MAX_STAGES;
-    while (ring > 2 && fixed + (size_t)ring * TC_STAGE_BYTES > 227 * 1024) ring--;
-    const size_t smem = (fixed + (size_t)ring * TC_STAGE_BYTES + 127) / 128 * 128;
+    while (ring > 2 && fixed + (size_t)ring * TC_SLOT_BYTES > 227 * 1024) ring--;
+    const size_t smem = (fixed + (size_t)ring * TC_SLOT_BYTES + 127) / 128 * 128;
     if (smem > 227 * 1024) return nb200_fail(ctx, NB200_ERR_ARG, "VMat too large for the tcgen05 background kernel");
     a.ring = ring;
+    static const int stag_env = getenv("NB200_TC_STAGGER") ? atoi(getenv("NB200_TC_STAGGER")) : 2;
+    a.stagger = stag_env < 0 ? -1 : std::min(std::min(stag_env, ring - 2), pl->n_stages - 1);
     NB_CUDA(ctx, cudaFuncSetAttribute(k_nuc_bx_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     NB_CUDA(ctx, cudaFuncSetAttribute(k_nuc_bx_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps(ctx, b->stream, "k_nuc_bx_tc");
