@@ -62,6 +62,11 @@ struct RunConst {
     bool v_has_zero = false;
     DevBuf vmat;      // f64 [R][W]
     DevBuf vmat_fp;   // f64 [R][Wpad]  f_i * V, zero padded (operand of the dense background xcor)
+    // "paired" templates of the candidate statistics (k_cand_stats): for T in {V, f*V, f*V^2}
+    //   pair[t][j][k] = (T[2j+1,k], T[2j+2,k]) (j = 0: (0, T[0,k] + T[2,k])), one[t][k] = T[1,k]; zero outside [lower, upper),
+    //   J2 x W2 (both even) double2 per template
+    DevBuf vp_pair, vp_one;
+    int vp_J2 = 0, vp_W2 = 0;
     std::vector<double> h_vmat;
     // fragment sizes
     bool have_sizes = false;

@@ -125,7 +125,7 @@ int nb200_ctx_destroy(nb200_ctx *c)
     RunConst &r = c->rc;
     DevBuf *bufs[] = {&r.log_pwm, &r.nuc_code, &r.vmat,   &r.vmat_fp, &r.sizes,  &r.nuc_probs, &r.nfr_probs,
                       &r.alphas,  &r.jitter,   &r.occ_win, &r.nuc_win, &c->s0,     &c->s1,    &c->s2,       &c->s3,
-                      &c->s4,     &c->flush};
+                      &c->s4,     &c->flush,   &r.vp_pair, &r.vp_one};
     for (auto b : bufs) b->release();
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -187,6 +187,31 @@ static int rebuild_scaled_vmat(nb200_ctx *ctx)
         for (int k = 0; k < r.v_cols; k++) vf[(size_t)i * r.v_wpad + k] = f * r.h_vmat[(size_t)i * r.v_cols + k];
     }
     NB_CHECK(upload(ctx, r.vmat_fp, vf.data(), vf.size() * sizeof(double)));
+    {
+        // Window sums sum_i T[i,k] Bp[i,c] regrouped by the left tap (sizes 2j+1 and 2j+2 share l = c - j):
+        //   sum_j E[c-j] * (T[2j+1,k] E[c+j] + T[2j+2,k] E[c+j+1]);  size 0 has the taps of size 2, size 1 a single tap.
+        const int uv = r.v_upper, lv = r.v_lower, W = r.v_cols;
+        const int J2 = (std::max(1, uv / 2) + 1) & ~1, W2 = (W + 1) & ~1;
+        std::vector<double> pair((size_t)3 * J2 * W2 * 2, 0.0), one((size_t)3 * W2, 0.0);
+        auto T = [&](int t, int i, int k) -> double {
+            if (i < lv || i >= uv) return 0.0;
+            const double v = r.h_vmat[(size_t)(i - lv) * W + k], f = r.h_sizes[i];
+            return t == 0 ? v : (t == 1 ? f * v : f * v * v);
+        };
+        for (int t = 0; t < 3; t++)
+            for (int k = 0; k < W; k++) {
+                one[(size_t)t * W2 + k] = T(t, 1, k);
+                for (int j = 0; j < J2; j++) {
+                    double *c = &pair[(((size_t)t * J2 + j) * W2 + k) * 2];
+                    c[0] = j == 0 ? 0.0 : T(t, 2 * j + 1, k);
+                    c[1] = T(t, 2 * j + 2, k) + (j == 0 ? T(t, 0, k) : 0.0);
+                }
+            }
+        NB_CHECK(upload(ctx, r.vp_pair, pair.data(), pair.size() * sizeof(double)));
+        NB_CHECK(upload(ctx, r.vp_one, one.data(), one.size() * sizeof(double)));
+        r.vp_J2 = J2;
+        r.vp_W2 = W2;
+    }
     return nb200_tc_setup(ctx);
 }
 

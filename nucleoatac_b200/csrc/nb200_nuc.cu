@@ -338,35 +338,101 @@ struct CandArgs {
     const int32_t *col_ptr;
     const int2 *ent;
     const double *E, *V, *f;
+    const double2 *pair;       // [3][J2][W2] paired templates V, f*V, f*V^2 (RunConst::vp_pair)
+    const double *one;         // [3][W2]     their insert-size-1 rows
     const int2 *work;
     const int32_t *work_count;
     const int32_t *cand_pos;
     int32_t *cand_flag;
     const double *cand_norm, *cand_cov, *cand_bcov;  // cand_bcov = S_B = sum f*Bp over the window (bias coverage track)
     double *cand_z, *cand_lr;
-    int pwm_up, lv, R, W, w, csc_pad, use_bias, lr_is_nan;
+    int pwm_up, lv, R, W, w, csc_pad, use_bias, lr_is_nan, J2, W2;
     double min_lr, min_z;
 };
 
 #define CS_THREADS 256
-#define CS_GROUP 4   // candidates scored together: every VMat element is loaded once per group
-__global__ void __launch_bounds__(CS_THREADS, 4) k_cand_stats(CandArgs a)
+#define CS_GROUP_DEFAULT 4   // candidates scored together: every template element is loaded once per group
+
+// Dense window sum  sum_{i,k} T[i,k] * Bp[i, c_k]  (c_k = P - w + k) for NG candidates at once, T given as a paired template.
+// Sizes 2j+1 and 2j+2 share their left tap (Bp[2j+1,c] = E[c-j] E[c+j], Bp[2j+2,c] = E[c-j] E[c+j+1]), so a column costs
+//   sum_j E[c-j] * (T[2j+1,k] * E[c+j] + T[2j+2,k] * E[c+j+1])          -- 1.5 flops-pairs per cell instead of 2.
+// A thread owns two adjacent columns and walks j two steps at a time: the taps of (k, k+1) x (j, j+1) are two sliding
+// aligned pairs per side, i.e. one 16-byte shared-memory load per side per candidate for 8 cells.  Thread groups split
+// the j range when the window has fewer than 2 * CS_THREADS columns.  s_E: per candidate nEw2 doubles, element off0 + k
+// is E[c_k]; both even, so every pair is 16-byte aligned.  Adds the partial sums of this thread to acc[0..NG).
+template <int NG>
+__device__ __forceinline__ void pair_window_sums(const double2 *__restrict__ T, const double *__restrict__ t1, int J2, int W2,
+                                                 const double *s_E, int nEw2, int off0, double *acc)
 {
-    extern __shared__ double sm_cs[];
+    const int ncp = W2 >> 1, tpc = min(ncp, CS_THREADS), rows_par = CS_THREADS / tpc;
+    const int cp0 = threadIdx.x % tpc, rr = threadIdx.x / tpc;
+    const int jseg = ((J2 / 2 + rows_par - 1) / rows_par) * 2;
+    const int j0 = rr * jseg, j1 = min(J2, j0 + jseg);
+    if (rr >= rows_par || j0 >= j1) return;
+    for (int cp = cp0; cp < ncp; cp += tpc) {
+        const int k = 2 * cp;
+        const double *Ec = s_E + off0 + k;
+        double2 L[NG], Rt[NG];   // carries: (E[c-j], E[c-j+1]) and (E[c+j], E[c+j+1])
+#pragma unroll
+        for (int cg = 0; cg < NG; cg++) {
+            L[cg] = *reinterpret_cast<const double2 *>(Ec + cg * nEw2 - j0);
+            Rt[cg] = *reinterpret_cast<const double2 *>(Ec + cg * nEw2 + j0);
+        }
+        if (j0 == 0) {  // insert size 1: a single tap, Bp[1,c] = E[c]
+            const double2 c1 = *reinterpret_cast<const double2 *>(t1 + k);
+#pragma unroll
+            for (int cg = 0; cg < NG; cg++) acc[cg] = fma(c1.x, L[cg].x, fma(c1.y, L[cg].y, acc[cg]));
+        }
+        const double2 *Tp = T + (size_t)j0 * W2 + k;
+        double2 a0 = __ldg(Tp), a1 = __ldg(Tp + 1), b0 = __ldg(Tp + W2), b1 = __ldg(Tp + W2 + 1);
+#pragma unroll 2
+        for (int j = j0; j < j1; j += 2) {
+            Tp += 2 * (size_t)W2;
+            double2 na0 = a0, na1 = a1, nb0 = b0, nb1 = b1;
+            if (j + 2 < j1) {   // next step's template values are in flight while this step is contracted
+                na0 = __ldg(Tp);
+                na1 = __ldg(Tp + 1);
+                nb0 = __ldg(Tp + W2);
+                nb1 = __ldg(Tp + W2 + 1);
+            }
+#pragma unroll
+            for (int cg = 0; cg < NG; cg++) {
+                const double2 Ln = *reinterpret_cast<const double2 *>(Ec + cg * nEw2 - j - 2);   // (E[c-j-2], E[c-j-1])
+                const double2 Rn = *reinterpret_cast<const double2 *>(Ec + cg * nEw2 + j + 2);   // (E[c+j+2], E[c+j+3])
+                const double2 Lc = L[cg], Rc = Rt[cg];
+                double s = acc[cg];
+                s = fma(Lc.x, fma(a0.x, Rc.x, a0.y * Rc.y), s);   // column k,   step j
+                s = fma(Lc.y, fma(a1.x, Rc.y, a1.y * Rn.x), s);   // column k+1, step j
+                s = fma(Ln.y, fma(b0.x, Rc.y, b0.y * Rn.x), s);   // column k,   step j+1
+                s = fma(Lc.x, fma(b1.x, Rn.x, b1.y * Rn.y), s);   // column k+1, step j+1
+                acc[cg] = s;
+                L[cg] = Ln;
+                Rt[cg] = Rn;
+            }
+            a0 = na0;
+            a1 = na1;
+            b0 = nb0;
+            b1 = nb1;
+        }
+    }
+}
+
+template <int CS_GROUP>
+__global__ void __launch_bounds__(CS_THREADS, 2) k_cand_stats(CandArgs a)
+{
+    extern __shared__ __align__(16) double sm_cs[];
     __shared__ double red[32];
-    __shared__ double s_sum[4][CS_GROUP];
+    __shared__ double s_sum[2][CS_GROUP];
+    __shared__ double s_part[CS_GROUP][CS_THREADS / 32], s_ll[2][CS_THREADS / 32];
     __shared__ int s_need2;
-    const int uv = a.lv + a.R;
-    const int half = uv / 2;
-    const int nEw = a.W + 2 * half + 2;
-    double *s_E = sm_cs;                      // [CS_GROUP][nEw]  E over genomic [P - w - half, ...) per candidate
+    static_assert((CS_THREADS / 32) % CS_GROUP == 0, "warps must divide evenly over the candidates of a group");
+    // E window of a candidate: element off0 + k is E[P - w + k]; J2 + 2 doubles of reach on both sides
+    const int off0 = a.J2 + 2, nEw = off0 + a.W2 + a.J2 + 4;
+    double *s_E = sm_cs;                      // [CS_GROUP][nEw]
     double *s_f = sm_cs + CS_GROUP * nEw;     // [R]              f_i over the VMat's sizes
     const int nwork = a.work_count[0];
     const int tid = threadIdx.x;
-    // thread layout over the R x W window: column kk, rows rr, rr + rows_par, ...
-    const int wcols = min(a.W, CS_THREADS);
-    const int rows_par = CS_THREADS / wcols;
-    const int kk = tid % wcols, rr = tid / wcols;
+    const size_t tsz = (size_t)a.J2 * a.W2;
     for (int i = tid; i < a.R; i += CS_THREADS) s_f[i] = a.f[a.lv + i];
     for (int g0 = blockIdx.x * CS_GROUP; g0 < nwork; g0 += gridDim.x * CS_GROUP) {
         const int ng = min(CS_GROUP, nwork - g0);
@@ -377,8 +443,12 @@ __global__ void __launch_bounds__(CS_THREADS, 4) k_cand_stats(CandArgs a)
                 const int2 it = a.work[g0 + cg];
                 const int c = it.x;
                 const int P = a.cand_pos[a.cand_off[c] + it.y];
-                const double *Eg = a.E + (a.bias_off[c] - (int64_t)(a.seq_start[c] + a.pwm_up)) + (P - a.w - half);
-                for (int i = tid; i < nEw; i += CS_THREADS) s_E[cg * nEw + i] = Eg[i];
+                const int64_t e_lo = a.bias_off[c], e_hi = a.bias_off[c + 1];
+                const int64_t eb = e_lo - (int64_t)(a.seq_start[c] + a.pwm_up) + (P - a.w - off0);
+                for (int i = tid; i < nEw; i += CS_THREADS) {   // the few elements of reach past the window may lie off the track
+                    const int64_t idx = eb + i;
+                    s_E[cg * nEw + i] = (idx >= e_lo && idx < e_hi) ? a.E[idx] : 0.0;
+                }
             } else
                 for (int i = tid; i < nEw; i += CS_THREADS) s_E[cg * nEw + i] = a.use_bias ? 0.0 : 1.0;
         }
@@ -387,88 +457,68 @@ __global__ void __launch_bounds__(CS_THREADS, 4) k_cand_stats(CandArgs a)
         double sVB[CS_GROUP];
 #pragma unroll
         for (int cg = 0; cg < CS_GROUP; cg++) sVB[cg] = 0.0;
-        if (rr < rows_par) {
-            for (int k = kk; k < a.W; k += wcols) {
-                const double *Ec = s_E + half + k;
-                if (rows_par == 1 && a.use_bias) {
-                    // one thread walks all insert sizes of its column: consecutive sizes share a tap
-                    // (i -> i+1 moves the left tap when i+1 is odd, the right tap when it is even)
-                    double ea[CS_GROUP], eb[CS_GROUP];
-                    int i = a.lv;
-#pragma unroll
-                    for (int cg = 0; cg < CS_GROUP; cg++) {
-                        ea[cg] = Ec[cg * nEw - ((i - 1) >> 1)];
-                        eb[cg] = Ec[cg * nEw + (i >> 1)];
-                    }
-                    for (int r = 0; r < a.R; r++, i++) {
-                        const double v = a.V[(size_t)r * a.W + k];
-#pragma unroll
-                        for (int cg = 0; cg < CS_GROUP; cg++) {
-                            const double bp = (i == 1) ? ea[cg] : ea[cg] * eb[cg];
-                            sVB[cg] = fma(v, bp, sVB[cg]);
-                        }
-                        const int in = i + 1;
-                        if (in & 1) {
-#pragma unroll
-                            for (int cg = 0; cg < CS_GROUP; cg++) ea[cg] = Ec[cg * nEw - ((in - 1) >> 1)];
-                        } else {
-#pragma unroll
-                            for (int cg = 0; cg < CS_GROUP; cg++) eb[cg] = Ec[cg * nEw + (in >> 1)];
-                        }
-                    }
-                } else {
-                    for (int r = rr; r < a.R; r += rows_par) {
-                        const int i = a.lv + r;
-                        const double v = a.V[(size_t)r * a.W + k];
-#pragma unroll
-                        for (int cg = 0; cg < CS_GROUP; cg++) {
-                            const double bp = a.use_bias ? bias_cell(Ec + cg * nEw, i) : 1.0;
-                            sVB[cg] = fma(v, bp, sVB[cg]);
-                        }
-                    }
-                }
-            }
-        }
+        pair_window_sums<CS_GROUP>(a.pair, a.one, a.J2, a.W2, s_E, nEw, off0, sVB);
+        // block totals of the NG sums: one pass of warp shuffles, one barrier
+        const int lane = tid & 31, wid = tid >> 5;
 #pragma unroll
         for (int cg = 0; cg < CS_GROUP; cg++) {
-            const double x1 = block_sum(sVB[cg], red);
-            if (tid == 0) {
-                s_sum[0][cg] = x1;
-                // S_B = sum f*Bp over the window = the bias coverage at the candidate (NucleosomeCalling.py:56-58)
-                s_sum[1][cg] = (cg < ng) ? a.cand_bcov[a.cand_off[a.work[g0 + cg].x] + a.work[g0 + cg].y] : 1.0;
-            }
+            const double v = warp_sum(sVB[cg]);
+            if (lane == 0) s_part[cg][wid] = v;
         }
         __syncthreads();
-        // ---- sparse likelihoods over the fragments of each window, NucleosomeCalling.py:110-122
-        for (int cg = 0; cg < ng; cg++) {
-            const int2 it = a.work[g0 + cg];
-            const int c = it.x;
-            const int64_t ci = a.cand_off[c] + it.y;
-            const int x = a.cand_pos[ci] - a.start[c];
-            const int32_t *cp = a.col_ptr + a.col_off[c];
-            const int2 *en = a.ent + a.frag_off[c];
-            const int e0 = cp[x - a.w + a.csc_pad], e1 = cp[x + a.w + 1 + a.csc_pad];
-            const int kb = a.w - (x + a.csc_pad);
-            const double cVB = s_sum[0][cg], cB = s_sum[1][cg];
+        // ---- sparse likelihoods over the fragments of each window, NucleosomeCalling.py:110-122: warp `wid` takes candidate
+        // wid % NG (CS_THREADS / 32 / NG warps share a candidate's fragment list)
+        {
+            constexpr int NWARP = CS_THREADS / 32, WPC = NWARP / CS_GROUP;   // warps per candidate
+            const int cg = wid % CS_GROUP, sub = wid / CS_GROUP;
             double nl = 0.0, ul = 0.0;
-            for (int e = e0 + tid; e < e1; e += CS_THREADS) {
-                const int2 v = en[e];
-                const int r = v.y - a.lv;
-                if (r >= 0 && r < a.R) {
-                    const int k = v.x + kb;
-                    const double bp = a.use_bias ? bias_cell(s_E + cg * nEw + half + k, v.y) : 1.0;
-                    nl += log(__dmul_rn(a.V[(size_t)r * a.W + k], bp) / cVB);
-                    ul += log(__dmul_rn(bp, s_f[r]) / cB);
+            if (cg < ng) {
+                double cVB = 0.0;
+#pragma unroll
+                for (int w2 = 0; w2 < NWARP; w2++) cVB += s_part[cg][w2];
+                const int2 it = a.work[g0 + cg];
+                const int c = it.x;
+                const int64_t ci = a.cand_off[c] + it.y;
+                // S_B = sum f*Bp over the window = the bias coverage at the candidate (NucleosomeCalling.py:56-58)
+                const double cB = a.cand_bcov[ci];
+                const int x = a.cand_pos[ci] - a.start[c];
+                const int32_t *cp = a.col_ptr + a.col_off[c];
+                const int2 *en = a.ent + a.frag_off[c];
+                const int e0 = cp[x - a.w + a.csc_pad], e1 = cp[x + a.w + 1 + a.csc_pad];
+                const int kb = a.w - (x + a.csc_pad);
+                for (int e = e0 + sub * 32 + lane; e < e1; e += 32 * WPC) {
+                    const int2 v = en[e];
+                    const int r = v.y - a.lv;
+                    if (r >= 0 && r < a.R) {
+                        const int k = v.x + kb;
+                        const double bp = a.use_bias ? bias_cell(s_E + cg * nEw + off0 + k, v.y) : 1.0;
+                        nl += log(__dmul_rn(a.V[(size_t)r * a.W + k], bp) / cVB);
+                        ul += log(__dmul_rn(bp, s_f[r]) / cB);
+                    }
                 }
+                if (sub == 0 && lane == 0) s_sum[1][cg] = cB;
             }
-            nl = block_sum(nl, red);
-            ul = block_sum(ul, red);
-            if (tid == 0) {
-                const double lr = a.lr_is_nan ? nb_nan() : nl - ul;  // 0*log(0) cells make both likelihoods NaN in the reference
+            nl = warp_sum(nl);
+            ul = warp_sum(ul);
+            if (lane == 0) {
+                s_ll[0][wid] = nl;
+                s_ll[1][wid] = ul;
+            }
+            __syncthreads();
+            if (tid < ng) {
+                double tn = 0.0, tu = 0.0;
+#pragma unroll
+                for (int q = 0; q < WPC; q++) {
+                    tn += s_ll[0][tid + q * CS_GROUP];
+                    tu += s_ll[1][tid + q * CS_GROUP];
+                }
+                const int2 it = a.work[g0 + tid];
+                const int64_t ci = a.cand_off[it.x] + it.y;
+                const double lr = a.lr_is_nan ? nb_nan() : tn - tu;  // 0*log(0) cells make both likelihoods NaN in the reference
                 a.cand_lr[ci] = lr;
                 if (lr > a.min_lr) {
                     a.cand_flag[ci] |= 2;
-                    s_need2 |= 1 << cg;
+                    atomicOr(&s_need2, 1 << tid);
                 }
             }
         }
@@ -476,43 +526,22 @@ __global__ void __launch_bounds__(CS_THREADS, 4) k_cand_stats(CandArgs a)
         const int need2 = s_need2;
         if (!need2) continue;
         // ---- phase 2 (only where lr > min_lr): S_BV = sum f*V*Bp, S_BV2 = sum f*V^2*Bp  -> variance, z
-        double sBV[CS_GROUP], sBV2[CS_GROUP];
-#pragma unroll
-        for (int cg = 0; cg < CS_GROUP; cg++) sBV[cg] = sBV2[cg] = 0.0;
-        if (rr < rows_par) {
-            for (int k = kk; k < a.W; k += wcols) {
-                const double *Ec = s_E + half + k;
-                for (int r = rr; r < a.R; r += rows_par) {
-                    const int i = a.lv + r;
-                    const double v = a.V[(size_t)r * a.W + k];
-                    const double fr = s_f[r];
-#pragma unroll
-                    for (int cg = 0; cg < CS_GROUP; cg++) {
-                        if (need2 & (1 << cg)) {
-                            const double bp = a.use_bias ? bias_cell(Ec + cg * nEw, i) : 1.0;
-                            const double bv = __dmul_rn(bp, fr) * v;
-                            sBV[cg] += bv;
-                            sBV2[cg] = fma(bv, v, sBV2[cg]);
-                        }
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int cg = 0; cg < CS_GROUP; cg++) {
-            if (need2 & (1 << cg)) {
-                const double x1 = block_sum(sBV[cg], red), x2 = block_sum(sBV2[cg], red);
-                if (tid == 0) {
-                    const int2 it = a.work[g0 + cg];
-                    const int64_t ci = a.cand_off[it.x] + it.y;
-                    const double cB = s_sum[1][cg];
-                    const double mean = x1 / cB;
-                    // calculateCov closed form r*(sum p v^2 - (sum p v)^2), r truncated to C int (multinomial_cov.pyx:20)
-                    const double var = (double)(int)a.cand_cov[ci] * (x2 / cB - mean * mean);
-                    const double z = a.cand_norm[ci] / sqrt(var);
-                    a.cand_z[ci] = z;
-                    if (z >= a.min_z) a.cand_flag[ci] |= 4;
-                }
+        for (int cg = 0; cg < ng; cg++) {
+            if (!(need2 & (1 << cg))) continue;
+            double sBV = 0.0, sBV2 = 0.0;
+            pair_window_sums<1>(a.pair + tsz, a.one + a.W2, a.J2, a.W2, s_E + cg * nEw, nEw, off0, &sBV);
+            pair_window_sums<1>(a.pair + 2 * tsz, a.one + 2 * a.W2, a.J2, a.W2, s_E + cg * nEw, nEw, off0, &sBV2);
+            const double x1 = block_sum(sBV, red), x2 = block_sum(sBV2, red);
+            if (tid == 0) {
+                const int2 it = a.work[g0 + cg];
+                const int64_t ci = a.cand_off[it.x] + it.y;
+                const double cB = s_sum[1][cg];
+                const double mean = x1 / cB;
+                // calculateCov closed form r*(sum p v^2 - (sum p v)^2), r truncated to C int (multinomial_cov.pyx:20)
+                const double var = (double)(int)a.cand_cov[ci] * (x2 / cB - mean * mean);
+                const double z = a.cand_norm[ci] / sqrt(var);
+                a.cand_z[ci] = z;
+                if (z >= a.min_z) a.cand_flag[ci] |= 4;
             }
         }
     }
@@ -739,6 +768,10 @@ int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
         a.E = b->d_E.as<double>();
         a.V = r.vmat.as<double>();
         a.f = r.sizes.as<double>();
+        a.pair = r.vp_pair.as<double2>();
+        a.one = r.vp_one.as<double>();
+        a.J2 = r.vp_J2;
+        a.W2 = r.vp_W2;
         a.work = b->n_work.as<int2>();
         a.work_count = b->n_work_count.as<int32_t>();
         a.cand_pos = b->n_cand_pos.as<int32_t>();
@@ -759,9 +792,12 @@ int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
         a.min_lr = p.min_lr;
         a.min_z = p.min_z;
         ProfScope ps(ctx, b->stream, "k_cand_stats");
-        size_t smem = sizeof(double) * (CS_GROUP * ((size_t)W + 2 * (uv / 2) + 2) + r.v_rows);
-        if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_cand_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_cand_stats<<<ctx->sm_count * 8, CS_THREADS, smem, b->stream>>>(a);
+        static const int cs_group = getenv("NB200_CS_GROUP") ? atoi(getenv("NB200_CS_GROUP")) : CS_GROUP_DEFAULT;
+        const int G = cs_group <= 4 ? 4 : 8;
+        size_t smem = sizeof(double) * (G * ((size_t)r.vp_W2 + 2 * r.vp_J2 + 6) + r.v_rows);
+        auto kern = G == 4 ? k_cand_stats<4> : k_cand_stats<8>;
+        if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<ctx->sm_count * 4, CS_THREADS, smem, b->stream>>>(a);
         NB_LAUNCH_CHECK(ctx);
     }
     {
