@@ -1,5 +1,7 @@
 // nb200_dev.cuh -- device-side helpers shared by the kernels of libnucleo_b200 (sm_100a).
 #pragma once
+#include <algorithm>
+
 #include "nb200_common.cuh"
 
 #define NB_FULL 0xffffffffu
@@ -54,6 +56,96 @@ __device__ __forceinline__ double bias_cell(const double *Ec, int i)
     int a = (i - 1) >> 1;  // arithmetic shift == Python floor division, (0-1)//2 = -1
     int b = i >> 1;
     return Ec[-a] * Ec[b];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-column sums of the bias matrix against NW weight vectors over the insert sizes [lo, hi):
+//     out_t[col] = sum_i wt_t[i] * Bp[i, col]                 (the operands of every sliding window sum of BiasMat2D:
+//                                                              Occupancy.py:136-140, tracks.py:209-222 on chunkmat2d.py:140-156)
+// Sizes 2j+1 and 2j+2 share their left tap, so a column costs sum_j E[c-j] (w[2j+1] E[c+j] + w[2j+2] E[c+j+1]);
+// size 0 has the taps of size 2, size 1 a single tap.  A thread owns two adjacent columns and walks j two steps at a
+// time: both tap windows slide as aligned pairs (one 16-byte shared load per side for 8 cells), the paired weights are
+// broadcast loads.  Block = PC_THREADS threads = 2 * PC_THREADS columns of chunk blockIdx.y; column 0 of a chunk is
+// genomic start - pad and lands at out_t[out_off[c] + 2 * pad * c].
+#define PC_THREADS 128
+template <int NW>
+struct PairColsumArgs {
+    const int32_t *start;
+    const int64_t *out_off, *bias_off;
+    const int32_t *seq_start;
+    const double *E;
+    const double *wt[NW];
+    double *out[NW];
+    int pwm_up, lo, hi, pad;
+};
+
+template <int NW>
+static __global__ void __launch_bounds__(PC_THREADS) k_pair_colsums(PairColsumArgs<NW> a)
+{
+    extern __shared__ __align__(16) double sm_pc[];
+    const int J2 = (max(1, a.hi / 2) + 1) & ~1;
+    const int off0 = J2 + 2, nE = off0 + 2 * PC_THREADS + J2 + 4;
+    double2 *s_wp = reinterpret_cast<double2 *>(sm_pc);            // [NW][J2] (w[2j+1], w[2j+2])
+    double *s_E = sm_pc + 2 * (size_t)NW * J2;                     // element off0 + t is E at the tile's column t
+    const int c = blockIdx.y;
+    const int L = (int)(a.out_off[c + 1] - a.out_off[c]);
+    const int ncol = L + 2 * a.pad;
+    const int col0 = blockIdx.x * (2 * PC_THREADS);
+    if (col0 >= ncol) return;
+    double w1[NW];
+#pragma unroll
+    for (int t = 0; t < NW; t++) {
+        const double *w = a.wt[t];
+        auto W = [&](int i) { return (i >= a.lo && i < a.hi) ? w[i] : 0.0; };
+        for (int j = threadIdx.x; j < J2; j += PC_THREADS)
+            s_wp[t * J2 + j] = make_double2(j == 0 ? 0.0 : W(2 * j + 1), W(2 * j + 2) + (j == 0 ? W(0) : 0.0));
+        w1[t] = W(1);
+    }
+    const int64_t e_lo = a.bias_off[c], e_hi = a.bias_off[c + 1];
+    const int64_t eb = e_lo - (int64_t)(a.seq_start[c] + a.pwm_up) + (a.start[c] - a.pad + col0 - off0);
+    for (int i = threadIdx.x; i < nE; i += PC_THREADS) {   // the last elements of reach only meet zero weights and may lie off the track
+        const int64_t idx = eb + i;
+        s_E[i] = (idx >= e_lo && idx < e_hi) ? a.E[idx] : 0.0;
+    }
+    __syncthreads();
+    const int col = col0 + 2 * threadIdx.x;
+    if (col >= ncol) return;
+    const double *Ec = s_E + off0 + 2 * threadIdx.x;
+    double2 Lc = *reinterpret_cast<const double2 *>(Ec), Rc = Lc;   // (E[c-j], E[c-j+1]) and (E[c+j], E[c+j+1]) at j = 0
+    double s0[NW], s1[NW];
+#pragma unroll
+    for (int t = 0; t < NW; t++) {
+        s0[t] = w1[t] * Lc.x;
+        s1[t] = w1[t] * Lc.y;
+    }
+#pragma unroll 2
+    for (int j = 0; j < J2; j += 2) {
+        const double2 Ln = *reinterpret_cast<const double2 *>(Ec - j - 2);   // (E[c-j-2], E[c-j-1])
+        const double2 Rn = *reinterpret_cast<const double2 *>(Ec + j + 2);   // (E[c+j+2], E[c+j+3])
+#pragma unroll
+        for (int t = 0; t < NW; t++) {
+            const double2 wa = s_wp[t * J2 + j], wb = s_wp[t * J2 + j + 1];
+            s0[t] = fma(Lc.x, fma(wa.x, Rc.x, wa.y * Rc.y), s0[t]);   // column c,   step j
+            s1[t] = fma(Lc.y, fma(wa.x, Rc.y, wa.y * Rn.x), s1[t]);   // column c+1, step j
+            s0[t] = fma(Ln.y, fma(wb.x, Rc.y, wb.y * Rn.x), s0[t]);   // column c,   step j+1
+            s1[t] = fma(Lc.x, fma(wb.x, Rn.x, wb.y * Rn.y), s1[t]);   // column c+1, step j+1
+        }
+        Lc = Ln;
+        Rc = Rn;
+    }
+    const int64_t o = a.out_off[c] + 2 * (int64_t)a.pad * c + col;
+#pragma unroll
+    for (int t = 0; t < NW; t++) {
+        a.out[t][o] = s0[t];
+        if (col + 1 < ncol) a.out[t][o + 1] = s1[t];
+    }
+}
+
+template <int NW>
+static inline size_t pair_colsums_smem(int hi)
+{
+    const int J2 = (std::max(1, hi / 2) + 1) & ~1;
+    return sizeof(double) * (2 * (size_t)NW * J2 + (J2 + 2) + 2 * PC_THREADS + J2 + 4);
 }
 
 // ATAC shift + centre of a fragment, pyatac/fragments.pyx:26-36.  Returns false when the row is outside

@@ -2,7 +2,7 @@
 // without fit/getFuzz (host scipy optimiser).
 //
 // Stages (per batch, every chunk in parallel):
-//   k_nuc_colsums   cB[c] = sum_{i in [lv,uv)} f_i * Bp[i,c]                      (bias coverage operand, :56-58)
+//   k_pair_colsums  cB[c] = sum_{i in [lv,uv)} f_i * Bp[i,c]                      (bias coverage operand, :56-58)
 //   k_nuc_bx_fp64   bx[x] = sum_i sum_k f_i V[i,k] Bp[i, x-w+k]   dense background xcor, fp64 CUDA cores  (:60-63)
 //                   (nb200_xcor_tc.cu holds the tcgen05 version of the same contraction)
 //   k_nuc_tracks    nuc_cov / nfr_cov from the CSC prefix, bias coverage, sparse signal xcor (:29-36),
@@ -13,42 +13,6 @@
 //                   (multinomial_cov.pyx:20-31) and z-score (:123-127), fp64, one block per candidate
 //   k_nuc_reduce    nonredundant set = reduce_peaks by z, sep 120 (:312-315)
 #include "nb200_dev.cuh"
-
-// ---------------------------------------------------------------------------------------------
-#define NC_TILE 128
-__global__ void __launch_bounds__(NC_TILE) k_nuc_colsums(const int32_t *__restrict__ start, const int64_t *__restrict__ out_off,
-                                                         const int64_t *__restrict__ bias_off,
-                                                         const int32_t *__restrict__ seq_start, int pwm_up,
-                                                         const double *__restrict__ E, const double *__restrict__ f, int lv,
-                                                         int uv, int w, double *__restrict__ cB)
-{
-    extern __shared__ double sm_nc[];
-    double *s_f = sm_nc, *s_E = sm_nc + uv;  // s_E[NC_TILE + uv + 2]
-    const int c = blockIdx.y;
-    const int L = (int)(out_off[c + 1] - out_off[c]);
-    const int ncol = L + 2 * w;
-    const int j0 = blockIdx.x * NC_TILE;
-    if (j0 >= ncol) return;
-    for (int i = threadIdx.x; i < uv; i += blockDim.x) s_f[i] = f[i];
-    const int half = uv / 2;
-    const int g0 = start[c] - w + j0;
-    const int64_t eb = bias_off[c] - (int64_t)(seq_start[c] + pwm_up);
-    const int nE = NC_TILE + 2 * half + 2;
-    for (int i = threadIdx.x; i < nE; i += blockDim.x) s_E[i] = E[eb + g0 - half + i];
-    __syncthreads();
-    const int j = j0 + threadIdx.x;
-    if (j >= ncol) return;
-    const double *Ec = s_E + half + threadIdx.x;
-    double acc = 0.0;
-    double ta = Ec[-((lv - 1) >> 1)], tb = Ec[lv >> 1];  // consecutive sizes share one tap
-    for (int i = lv; i < uv; i++) {
-        acc += s_f[i] * ((i == 1) ? ta : ta * tb);
-        const int in = i + 1;
-        if (in & 1) ta = Ec[-((in - 1) >> 1)];
-        else tb = Ec[in >> 1];
-    }
-    cB[out_off[c] + 2 * (int64_t)w * c + j] = acc;
-}
 
 // ---------------------------------------------------------------------------------------------
 // Dense background cross-correlation, fp64.  One block = BX_NT threads x BX_XT consecutive outputs
@@ -156,23 +120,39 @@ struct NucTrackArgs {
 };
 
 #define NT_TILE 256
+#define NT_FRAG_CAP 2048   // fragments of a tile staged in shared memory (denser tiles read them from global memory)
 __global__ void __launch_bounds__(NT_TILE) k_nuc_tracks(NucTrackArgs a)
 {
-    extern __shared__ double sm_nt[];  // cB tile [NT_TILE + 2w]
+    extern __shared__ __align__(16) double sm_nt[];  // cB tile [NT_TILE + 2w (+8)], sums of 8 [..], fragment tile
     const int c = blockIdx.y;
     const int64_t oo = a.out_off[c];
     const int L = (int)(a.out_off[c + 1] - oo);
     const int x0 = blockIdx.x * NT_TILE;
     if (x0 >= L) return;
+    const int ncb = (NT_TILE + 2 * a.w + 8) & ~7;
+    double *s_cb = sm_nt, *s_b8 = sm_nt + ncb;                       // s_b8[m] = sum of s_cb[8m .. 8m+7]
+    int2 *s_ent = reinterpret_cast<int2 *>(sm_nt + ncb + ncb / 8);
+    const int32_t *cp = a.col_ptr + a.col_off[c];
+    const int2 *en = a.ent + a.frag_off[c];
+    const int nx = min(NT_TILE, L - x0);
+    // fragments of the whole tile: columns [x0 - w, x0 + nx - 1 + w]
+    const int te0 = cp[x0 - a.w + a.csc_pad], te1 = cp[x0 + nx - 1 + a.w + 1 + a.csc_pad];
+    const bool staged = (te1 - te0) <= NT_FRAG_CAP;
+    if (staged)
+        for (int i = threadIdx.x; i < te1 - te0; i += NT_TILE) s_ent[i] = en[te0 + i];
     if (a.use_bias) {
         const int64_t co = oo + 2 * (int64_t)a.w * c + x0;
-        const int nc = min(NT_TILE, L - x0) + 2 * a.w;
-        for (int i = threadIdx.x; i < nc; i += blockDim.x) sm_nt[i] = a.cB[co + i];
+        const int nc = nx + 2 * a.w;
+        for (int i = threadIdx.x; i < ncb; i += NT_TILE) s_cb[i] = (i < nc) ? a.cB[co + i] : 0.0;
         __syncthreads();
+        for (int m = threadIdx.x; m < ncb / 8; m += NT_TILE) {
+            const double *q = s_cb + 8 * m;
+            s_b8[m] = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
+        }
     }
+    __syncthreads();
     const int x = x0 + threadIdx.x;
     if (x >= L) return;
-    const int32_t *cp = a.col_ptr + a.col_off[c];
     const int lo = x - a.w + a.csc_pad, hi = x + a.w + 1 + a.csc_pad;
     const int e0 = cp[lo], e1 = cp[hi];
     int nlow = 0;
@@ -183,8 +163,16 @@ __global__ void __launch_bounds__(NT_TILE) k_nuc_tracks(NucTrackArgs a)
     const double nuc_cov = (double)(e1 - e0 - nlow), nfr_cov = (double)nlow;
     double bcov, bxv;
     if (a.use_bias) {
+        // window [t, t + W) = head up to the next multiple of 8, whole groups of 8, tail
+        const int t = threadIdx.x, t1 = t + a.W;
+        const int g0 = (t + 7) >> 3, g1 = t1 >> 3;
         double s = 0.0;
-        for (int k = 0; k < a.W; k++) s += sm_nt[threadIdx.x + k];
+        if (g0 <= g1) {
+            for (int k = t; k < 8 * g0; k++) s += s_cb[k];
+            for (int m = g0; m < g1; m++) s += s_b8[m];
+            for (int k = 8 * g1; k < t1; k++) s += s_cb[k];
+        } else
+            for (int k = t; k < t1; k++) s += s_cb[k];
         bcov = s;
         bxv = a.bx[oo + x];
     } else {
@@ -192,12 +180,19 @@ __global__ void __launch_bounds__(NT_TILE) k_nuc_tracks(NucTrackArgs a)
         bxv = a.bx_nobias;
     }
     // sparse signal xcor: every fragment centred within +-w contributes one VMat entry
-    const int2 *en = a.ent + a.frag_off[c];
     double sig = 0.0;
     const int kb = a.w - (x + a.csc_pad);
-    for (int e = e0; e < e1; e++) {
-        const int2 v = en[e];
-        if (v.y >= a.lv && v.y < a.uv) sig += a.V[(size_t)(v.y - a.lv) * a.W + (v.x + kb)];
+    if (staged) {
+        const int2 *se = s_ent - te0;
+        for (int e = e0; e < e1; e++) {
+            const int2 v = se[e];
+            if (v.y >= a.lv && v.y < a.uv) sig += __ldg(a.V + (size_t)(v.y - a.lv) * a.W + (v.x + kb));
+        }
+    } else {
+        for (int e = e0; e < e1; e++) {
+            const int2 v = en[e];
+            if (v.y >= a.lv && v.y < a.uv) sig += a.V[(size_t)(v.y - a.lv) * a.W + (v.x + kb)];
+        }
     }
     const double bg = bxv * nuc_cov / bcov;  // NucleosomeCalling.py:64
     a.nuc_cov[oo + x] = nuc_cov;
@@ -648,13 +643,23 @@ int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
         NB_CUDA(ctx, b->n_bx.reserve(sizeof(double) * tl));
         NB_CUDA(ctx, b->n_cB.reserve(sizeof(double) * (tl + 2 * (size_t)w * n)));
         {
-            size_t smem = sizeof(double) * ((size_t)uv + NC_TILE + 2 * (uv / 2) + 8);
-            if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_nuc_colsums, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PairColsumArgs<1> pa;
+            pa.start = b->d_start.as<int32_t>();
+            pa.out_off = b->d_out_off.as<int64_t>();
+            pa.bias_off = b->d_bias_off.as<int64_t>();
+            pa.seq_start = b->d_seq_start.as<int32_t>();
+            pa.E = b->d_E.as<double>();
+            pa.wt[0] = r.sizes.as<double>();
+            pa.out[0] = b->n_cB.as<double>();
+            pa.pwm_up = r.pwm_up;
+            pa.lo = lv;
+            pa.hi = uv;
+            pa.pad = w;
+            const size_t smem = pair_colsums_smem<1>(uv);
+            if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_pair_colsums<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ProfScope ps(ctx, b->stream, "k_nuc_colsums");
-            dim3 grid((unsigned)div_up64(b->max_len + 2 * w, NC_TILE), n);
-            k_nuc_colsums<<<grid, NC_TILE, smem, b->stream>>>(b->d_start.as<int32_t>(), b->d_out_off.as<int64_t>(),
-                                                              b->d_bias_off.as<int64_t>(), b->d_seq_start.as<int32_t>(), r.pwm_up,
-                                                              b->d_E.as<double>(), r.sizes.as<double>(), lv, uv, w, b->n_cB.as<double>());
+            dim3 grid((unsigned)div_up64(b->max_len + 2 * w, 2 * PC_THREADS), n);
+            k_pair_colsums<1><<<grid, PC_THREADS, smem, b->stream>>>(pa);
             NB_LAUNCH_CHECK(ctx);
         }
         int mode = p.xcor_mode;
@@ -697,7 +702,8 @@ int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
             s += rs * r.h_sizes[lv + i];
         }
         a.bx_nobias = s;
-        size_t smem = sizeof(double) * (NT_TILE + 2 * (size_t)w + 2);
+        const size_t ncb = (NT_TILE + 2 * (size_t)w + 8) & ~(size_t)7;
+        size_t smem = sizeof(double) * (ncb + ncb / 8 + NT_FRAG_CAP);
         if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_nuc_tracks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ProfScope ps(ctx, b->stream, "k_nuc_tracks");
         dim3 grid((unsigned)div_up64(b->max_len, NT_TILE), n);

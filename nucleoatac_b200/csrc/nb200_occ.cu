@@ -1,7 +1,8 @@
 // nb200_occ.cu -- OccChunk.process on the device (nucleoatac/Occupancy.py:195-253, run_occ.py:23-39).
 //
 // Stages (per batch, every chunk in parallel):
-//   k_occ_colsums  per-column sums  cn[c] = sum_i pn[i]*Bp[i,c],  cf[c] = sum_i pf[i]*Bp[i,c]   (bias only)
+//   k_pair_colsums per-column sums  cn[c] = sum_i pn[i]*Bp[i,c],  cf[c] = sum_i pf[i]*Bp[i,c]   (bias only; nb200_dev.cuh,
+//                  profiled as "k_occ_colsums")
 //   k_occ_mle      one window per 8 lanes: the window's fragments from the CSC fragment matrix, 101-point alpha
 //                  log-likelihood grid in fp64 (as the log of a product), first-max argmax and the
 //                  likelihood-ratio confidence bounds                                   (Occupancy.py:104-146)
@@ -10,50 +11,6 @@
 #include <algorithm>
 
 #include "nb200_dev.cuh"
-
-// ---------------------------------------------------------------------------------------------
-#define OC_TILE 128
-__global__ void __launch_bounds__(OC_TILE) k_occ_colsums(const int32_t *__restrict__ start, const int64_t *__restrict__ out_off,
-                                                         const int64_t *__restrict__ bias_off,
-                                                         const int32_t *__restrict__ seq_start, int pwm_up,
-                                                         const double *__restrict__ E, const double *__restrict__ pn,
-                                                         const double *__restrict__ pf, int upper, int flank,
-                                                         double *__restrict__ cn, double *__restrict__ cf)
-{
-    extern __shared__ double sm_oc[];
-    double *s_pn = sm_oc, *s_pf = sm_oc + upper, *s_E = sm_oc + 2 * upper;  // s_E[OC_TILE + upper + 2]
-    const int c = blockIdx.y;
-    const int L = (int)(out_off[c + 1] - out_off[c]);
-    const int ncol = L + 2 * flank;
-    const int j0 = blockIdx.x * OC_TILE;
-    if (j0 >= ncol) return;
-    for (int i = threadIdx.x; i < upper; i += blockDim.x) {
-        s_pn[i] = pn[i];
-        s_pf[i] = pf[i];
-    }
-    const int half = upper / 2;
-    const int g0 = start[c] - flank + j0;                 // genomic coordinate of the tile's first column
-    const int64_t eb = bias_off[c] - (int64_t)(seq_start[c] + pwm_up);  // E index = eb + genomic
-    const int nE = OC_TILE + 2 * half + 2;
-    for (int i = threadIdx.x; i < nE; i += blockDim.x) s_E[i] = E[eb + g0 - half + i];
-    __syncthreads();
-    const int j = j0 + threadIdx.x;
-    if (j >= ncol) return;
-    const double *Ec = s_E + half + threadIdx.x;
-    double an = 0.0, af = 0.0;
-    double ta = Ec[1], tb = Ec[0];  // i = 0: taps c+1 and c; consecutive sizes share one tap
-    for (int i = 0; i < upper; i++) {
-        const double bp = (i == 1) ? ta : ta * tb;
-        an += s_pn[i] * bp;
-        af += s_pf[i] * bp;
-        const int in = i + 1;
-        if (in & 1) ta = Ec[-((in - 1) >> 1)];
-        else tb = Ec[in >> 1];
-    }
-    const int64_t o = out_off[c] + 2 * (int64_t)flank * c + j;
-    cn[o] = an;
-    cf[o] = af;
-}
 
 // ---------------------------------------------------------------------------------------------
 struct OccMleArgs {
@@ -444,14 +401,25 @@ int nb200_occ_run(nb200_ctx *ctx, nb200_dbatch *b)
         const size_t ncs = tl + 2 * (size_t)p.flank * n;
         NB_CUDA(ctx, b->o_cn.reserve(sizeof(double) * ncs));
         NB_CUDA(ctx, b->o_cf.reserve(sizeof(double) * ncs));
-        size_t smem = sizeof(double) * (3 * (size_t)p.upper + OC_TILE + 8);
-        if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_occ_colsums, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PairColsumArgs<2> pa;
+        pa.start = b->d_start.as<int32_t>();
+        pa.out_off = b->d_out_off.as<int64_t>();
+        pa.bias_off = b->d_bias_off.as<int64_t>();
+        pa.seq_start = b->d_seq_start.as<int32_t>();
+        pa.E = b->d_E.as<double>();
+        pa.wt[0] = r.nuc_probs.as<double>();
+        pa.wt[1] = r.nfr_probs.as<double>();
+        pa.out[0] = b->o_cn.as<double>();
+        pa.out[1] = b->o_cf.as<double>();
+        pa.pwm_up = r.pwm_up;
+        pa.lo = 0;
+        pa.hi = p.upper;
+        pa.pad = p.flank;
+        const size_t smem = pair_colsums_smem<2>(p.upper);
+        if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_pair_colsums<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ProfScope ps(ctx, b->stream, "k_occ_colsums");
-        dim3 grid((unsigned)div_up64(b->max_len + 2 * p.flank, OC_TILE), n);
-        k_occ_colsums<<<grid, OC_TILE, smem, b->stream>>>(b->d_start.as<int32_t>(), b->d_out_off.as<int64_t>(),
-                                                          b->d_bias_off.as<int64_t>(), b->d_seq_start.as<int32_t>(), r.pwm_up,
-                                                          b->d_E.as<double>(), r.nuc_probs.as<double>(), r.nfr_probs.as<double>(),
-                                                          p.upper, p.flank, b->o_cn.as<double>(), b->o_cf.as<double>());
+        dim3 grid((unsigned)div_up64(b->max_len + 2 * p.flank, 2 * PC_THREADS), n);
+        k_pair_colsums<2><<<grid, PC_THREADS, smem, b->stream>>>(pa);
         NB_LAUNCH_CHECK(ctx);
     }
     {
