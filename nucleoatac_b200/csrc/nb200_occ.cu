@@ -9,6 +9,8 @@
 //   k_smooth_same  NaN-aware gaussian smoothing of the three tracks                     (Occupancy.py:147-153)
 //   k_occ_peaks    coverage, call_peaks + OccPeak filter + getNucDist, one block per chunk (Occupancy.py:221-240)
 #include <algorithm>
+#include <climits>
+#include <cmath>
 
 #include "nb200_dev.cuh"
 
@@ -24,6 +26,8 @@ struct OccMleArgs {
     int pwm_up, upper, flank, step, halfstep, csc_pad, n_alpha, use_bias;
     int pn_has_zero, pf_has_zero, both_zero;
     double cutoff, sn_nobias, sf_nobias;
+    double thr_m;   // exp(-cutoff/2) = thr_m * 2^thr_e, thr_m in [1,2) (NaN for a NaN cutoff); thr_zero: it underflows to 0
+    int thr_e, thr_zero;
 };
 
 // One window per 8-lane group, 4 windows per warp (Occupancy.py:104-146).  The bias of a fragment's insert size over the
@@ -139,40 +143,72 @@ __global__ void __launch_bounds__(MLE_WARPS * 32) k_occ_mle(OccMleArgs a)
     }
     double occ = nb_nan(), lo = nb_nan(), hi = nb_nan();
     {
-        // NaN / zero products (log 0) -> -inf like `logliks[np.isnan(logliks)] = -inf`; first maximum (np.argmax)
-        double best = nb_ninf();
-        int besti = 1 << 30;
+        // Everything the reference does with the log-likelihoods is a comparison (np.argmax; 2*(max - ll) < cutoff,
+        // Occupancy.py:115-119), and log is monotone: compare the products themselves, as exact (binary exponent,
+        // mantissa in [1,2)) pairs -- no logarithm.  Dead grid points (0*log 0 = NaN -> -inf) and zero / NaN products
+        // (log 0 = -inf) get the key (INT_MIN, 0).  The interval test ll > max - cutoff/2 is prod > max_prod * exp(-cutoff/2).
+        int ke[NQ];
 #pragma unroll
         for (int q = 0; q < NQ; q++) {
-            double acc = nb_ninf();
-            if (!((dead >> q) & 1) && mant[q] > 0.0) acc = log(mant[q]) + (double)ex[q] * 0.6931471805599453094;
-            mant[q] = acc;
+            double mq = mant[q];
+            int e = ex[q];
+            const bool alive = !((dead >> q) & 1) && mq > 0.0;
+            if (alive && mq < 2.2250738585072014e-308) {  // subnormal: make it normal first
+                mq *= 18446744073709551616.0;            // 2^64
+                e -= 64;
+            }
+            const long long bits = __double_as_longlong(mq);
+            const int e2 = (int)((bits >> 52) & 0x7ff);
+            ke[q] = alive ? e + e2 - 1023 : INT_MIN;
+            mant[q] = alive ? __longlong_as_double((bits & 0x800fffffffffffffLL) | 0x3ff0000000000000LL) : 0.0;
+        }
+        int beste = INT_MIN, besti = 1 << 30;
+        double bestm = 0.0;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {  // first maximum (np.argmax): strictly greater while walking up the grid
             const int ai = r + 8 * q;
-            if (ai < a.n_alpha && acc > best) {
-                best = acc;
+            if (ai < a.n_alpha && (ke[q] > beste || (ke[q] == beste && mant[q] > bestm))) {
+                beste = ke[q];
+                bestm = mant[q];
                 besti = ai;
             }
         }
         if (besti == (1 << 30) && r < a.n_alpha) besti = r;  // all -inf on this lane: its first alpha ties with the others
 #pragma unroll
         for (int o = 4; o > 0; o >>= 1) {
-            const double ob = __shfl_xor_sync(NB_FULL, best, o);
+            const int oe = __shfl_xor_sync(NB_FULL, beste, o);
+            const double om = __shfl_xor_sync(NB_FULL, bestm, o);
             const int oi = __shfl_xor_sync(NB_FULL, besti, o);
-            if (ob > best || (ob == best && oi < besti)) {
-                best = ob;
+            const bool gt = oe > beste || (oe == beste && om > bestm), eq = oe == beste && om == bestm;
+            if (gt || (eq && oi < besti)) {
+                beste = oe;
+                bestm = om;
                 besti = oi;
+            }
+        }
+        // threshold = max_prod * exp(-cutoff/2), canonical again
+        int te = INT_MIN;       // no grid point passes when the maximum is -inf (2*(-inf - -inf) = NaN) or the cutoff is NaN
+        double tm = 0.0;
+        bool none = (beste == INT_MIN) || !(a.thr_m == a.thr_m);
+        if (!none) {
+            if (a.thr_zero) {   // exp(-cutoff/2) underflows: every finite log-likelihood passes
+                te = INT_MIN + 1;
+            } else {
+                tm = bestm * a.thr_m;           // [1, 4)
+                te = beste + a.thr_e;
+                if (tm >= 2.0) {
+                    tm *= 0.5;
+                    te += 1;
+                }
             }
         }
         int okmin = 1 << 30, okmax = -1;
 #pragma unroll
         for (int q = 0; q < NQ; q++) {
             const int ai = r + 8 * q;
-            if (ai < a.n_alpha) {
-                const double ratio = 2.0 * (best - mant[q]);  // Occupancy.py:116
-                if (ratio < a.cutoff) {
-                    okmin = min(okmin, ai);
-                    okmax = max(okmax, ai);
-                }
+            if (ai < a.n_alpha && !none && (ke[q] > te || (ke[q] == te && mant[q] > tm))) {  // Occupancy.py:116-119
+                okmin = min(okmin, ai);
+                okmax = max(okmax, ai);
             }
         }
 #pragma unroll
@@ -453,6 +489,14 @@ int nb200_occ_run(nb200_ctx *ctx, nb200_dbatch *b)
         a.pf_has_zero = r.pf_has_zero;
         a.both_zero = r.both_zero;
         a.cutoff = r.cutoff;
+        {
+            const double k = exp(-0.5 * r.cutoff);
+            int e = 0;
+            const double m = frexp(k, &e);   // k = m * 2^e, m in [0.5, 1)
+            a.thr_zero = (k == 0.0) ? 1 : 0;
+            a.thr_m = (k > 0.0 && std::isfinite(k)) ? 2.0 * m : (k == 0.0 ? 1.0 : (double)NAN);  // NaN: nothing passes
+            a.thr_e = e - 1;
+        }
         a.sn_nobias = r.pn_sum * window;
         a.sf_nobias = r.pf_sum * window;
         int max_win = (b->max_len - halfstep + p.step - 1) / p.step;
