@@ -258,7 +258,7 @@ int nb200_batch_free(nb200_ctx *ctx, nb200_dbatch *b)
                       &b->d_seq, &b->d_out_off, &b->d_bias_off, &b->d_E, &b->d_col_off, &b->d_col_ptr, &b->d_col_low,
                       &b->d_cursor, &b->d_ent, &b->o_vals, &b->o_lower, &b->o_upper, &b->o_svals, &b->o_slower,
                       &b->o_supper, &b->o_cov, &b->o_nuc_dist, &b->o_peak_count, &b->o_peak_pos, &b->o_peak_occ,
-                      &b->o_peak_lower, &b->o_peak_upper, &b->o_peak_reads, &b->o_cn, &b->o_cf,
+                      &b->o_peak_lower, &b->o_peak_upper, &b->o_peak_reads, &b->o_cn, &b->o_cf, &b->o_wsn, &b->o_wsf,
                       &b->o_peak_off, &b->n_signal, &b->n_bg, &b->n_norm, &b->n_smooth, &b->n_nuc_cov, &b->n_nfr_cov,
                       &b->n_bx, &b->n_bcov, &b->n_cB, &b->n_comb, &b->n_cand_bcov, &b->n_cand_count, &b->n_cand_pos, &b->n_cand_flag,
                       &b->n_cand_z, &b->n_cand_lr, &b->n_cand_norm, &b->n_cand_sig, &b->n_cand_cov, &b->n_cand_nfr,

@@ -183,6 +183,7 @@ struct nb200_dbatch {
     DevBuf o_vals, o_lower, o_upper, o_svals, o_slower, o_supper, o_cov, o_nuc_dist;
     DevBuf o_peak_count, o_peak_pos, o_peak_occ, o_peak_lower, o_peak_upper, o_peak_reads;
     DevBuf o_cn, o_cf;          // per-column sums of pn*Bp, pf*Bp over [start-flank, end+flank)
+    DevBuf o_wsn, o_wsf;        // their sums over every occupancy window (k_occ_winsums)
     DevBuf o_peak_off;          // int64 [n+1]
     std::vector<int64_t> h_opeak_off;
     bool occ_done = false;

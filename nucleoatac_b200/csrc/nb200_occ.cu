@@ -10,6 +10,7 @@
 //   k_occ_peaks    coverage, call_peaks + OccPeak filter + getNucDist, one block per chunk (Occupancy.py:221-240)
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
 #include <cmath>
 
 #include "nb200_dev.cuh"
@@ -22,6 +23,7 @@ struct OccMleArgs {
     const int32_t *col_ptr;
     const int2 *ent;
     const double *E, *cn, *cf, *pn, *pf, *alphas;
+    const double *wsn, *wsf;   // per window: sums of cn / cf over its 2*flank+1 columns (k_occ_winsums); window k of chunk c at out_off[c]/step + c + k
     double *vals, *lower, *upper_b;
     int pwm_up, upper, flank, step, halfstep, csc_pad, n_alpha, use_bias;
     int pn_has_zero, pf_has_zero, both_zero;
@@ -29,6 +31,51 @@ struct OccMleArgs {
     double thr_m;   // exp(-cutoff/2) = thr_m * 2^thr_e, thr_m in [1,2) (NaN for a NaN cutoff); thr_zero: it underflows to 0
     int thr_e, thr_zero;
 };
+
+// Window sums of the per-column sums: SN[k] = sum of cn over the 2*flank+1 columns of window k (t = halfstep + k*step), SF
+// likewise from cf -- the bias model's normalisers of Occupancy.py:106-109.  Block = WS_WIN consecutive windows of a chunk,
+// their columns staged in shared memory; a lane's columns are `step` doubles apart (conflict free for odd steps).
+#define WS_WIN 128
+__global__ void __launch_bounds__(WS_WIN) k_occ_winsums(const int64_t *__restrict__ out_off, const double *__restrict__ cn,
+                                                        const double *__restrict__ cf, int flank, int step, int halfstep,
+                                                        double *__restrict__ wsn, double *__restrict__ wsf)
+{
+    extern __shared__ double sm_ws[];
+    const int c = blockIdx.y;
+    const int64_t oo = out_off[c];
+    const int L = (int)(out_off[c + 1] - oo);
+    const int nwin = (L - halfstep + step - 1) / step;
+    const int k0 = blockIdx.x * WS_WIN;
+    if (k0 >= nwin) return;
+    const int window = 2 * flank + 1;
+    const int nk = min(WS_WIN, nwin - k0);
+    const int ncol = (nk - 1) * step + window;
+    double *s_n = sm_ws, *s_f = sm_ws + (WS_WIN - 1) * step + window;
+    const int64_t co = oo + 2 * (int64_t)flank * c + halfstep + (int64_t)k0 * step;  // colsum index of the first column of window k0
+    for (int i = threadIdx.x; i < ncol; i += WS_WIN) {
+        s_n[i] = cn[co + i];
+        s_f[i] = cf[co + i];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x >= nk) return;
+    const double *pn = s_n + threadIdx.x * step, *pf = s_f + threadIdx.x * step;
+    double n4[4] = {0.0, 0.0, 0.0, 0.0}, f4[4] = {0.0, 0.0, 0.0, 0.0};
+    int k = 0;
+    for (; k + 4 <= window; k += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            n4[u] += pn[k + u];
+            f4[u] += pf[k + u];
+        }
+    }
+    for (; k < window; k++) {
+        n4[0] += pn[k];
+        f4[0] += pf[k];
+    }
+    const int64_t wo = oo / step + c + k0 + threadIdx.x;
+    wsn[wo] = (n4[0] + n4[1]) + (n4[2] + n4[3]);
+    wsf[wo] = (f4[0] + f4[1]) + (f4[2] + f4[3]);
+}
 
 // One window per 8-lane group, 4 windows per warp (Occupancy.py:104-146).  The bias of a fragment's insert size over the
 // window multiplies both mixture components (nuc[s] = pn[s]*bias[s]/SN, nfr[s] = pf[s]*bias[s]/SF, Occupancy.py:106-109),
@@ -38,8 +85,9 @@ struct OccMleArgs {
 // in alpha) and the running product renormalised every 32 factors: one log per alpha instead of one per (alpha, fragment).
 #define MLE_WARPS 4
 #define MLE_GROUPS 4
-template <int NQ>  // alphas per lane: lane r of a group owns alphas r, r + 8, ...
-__global__ void __launch_bounds__(MLE_WARPS * 32) k_occ_mle(OccMleArgs a)
+#define MLE_ITERS 8
+template <int NQ, int LB>  // NQ alphas per lane: lane r of a group owns alphas r, r + 8, ...; LB resident blocks per SM
+__global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle(OccMleArgs a)
 {
     extern __shared__ double sm_mle[];  // pn[upper], pf[upper]
     __shared__ double s_d[MLE_WARPS][32], s_q[MLE_WARPS][32], s_p[MLE_WARPS][32];
@@ -54,50 +102,43 @@ __global__ void __launch_bounds__(MLE_WARPS * 32) k_occ_mle(OccMleArgs a)
     const int64_t oo = a.out_off[c];
     const int L = (int)(a.out_off[c + 1] - oo);
     const int nwin = (L - a.halfstep + a.step - 1) / a.step;  // windows at t = halfstep + k*step < L
-    const int wi = (blockIdx.x * MLE_WARPS + warp) * MLE_GROUPS + g;
-    if ((blockIdx.x * MLE_WARPS + warp) * MLE_GROUPS >= nwin) return;  // whole warp past the last window
+    const int32_t *cp = a.col_ptr + a.col_off[c];
+    const int2 *en = a.ent + a.frag_off[c];
+    // grid constants of this lane: its alphas and which of them are dead (0 * log 0 = NaN -> -inf, Occupancy.py:112-114)
+    double al[NQ];
+    unsigned dead = 0;
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+        const int ai = r + 8 * q;
+        al[q] = (ai < a.n_alpha) ? a.alphas[ai] : 0.5;
+        if ((ai >= a.n_alpha) || a.both_zero || (al[q] == 0.0 && a.pf_has_zero) || (al[q] == 1.0 && a.pn_has_zero)) dead |= 1u << q;
+    }
+    const bool last_is_one = (al[NQ - 1] == 1.0);  // alpha == 1 (only ever the last grid value, checked on the host)
+  for (int it = 0; it < MLE_ITERS; it++) {   // a warp scores MLE_ITERS groups of 4 windows
+    const int wbase = ((blockIdx.x * MLE_ITERS + it) * MLE_WARPS + warp) * MLE_GROUPS;
+    if (wbase >= nwin) break;  // whole warp past the last window
+    const int wi = wbase + g;
     const bool valid = wi < nwin;
     const int t = a.halfstep + wi * a.step;
-    const int32_t *cp = a.col_ptr + a.col_off[c];
-    const int window = 2 * a.flank + 1;
     const int e0 = valid ? cp[t - a.flank + a.csc_pad] : 0, e1 = valid ? cp[t + a.flank + 1 + a.csc_pad] : 0;
     const int n = e1 - e0;
     int nmax = n;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(NB_FULL, nmax, o));
     double SN = a.sn_nobias, SF = a.sf_nobias;
-    if (a.use_bias) {
-        double sn = 0.0, sf = 0.0;
-        if (n > 0) {
-            const int64_t co = oo + 2 * (int64_t)a.flank * c + t;  // colsum index of the first window column
-            for (int k = r; k < window; k += 8) {
-                sn += a.cn[co + k];
-                sf += a.cf[co + k];
-            }
-        }
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
-            sn += __shfl_xor_sync(NB_FULL, sn, o);
-            sf += __shfl_xor_sync(NB_FULL, sf, o);
-        }
-        SN = sn;
-        SF = sf;
+    if (a.use_bias && valid) {
+        const int64_t wo = oo / a.step + c + wi;
+        SN = a.wsn[wo];
+        SF = a.wsf[wo];
     }
     const double rSN = 1.0 / SN, rSF = 1.0 / SF;
-    double al[NQ], mant[NQ];
+    double mant[NQ];
     int ex[NQ];
-    unsigned dead = 0;
 #pragma unroll
     for (int q = 0; q < NQ; q++) {
-        const int ai = r + 8 * q;
-        al[q] = (ai < a.n_alpha) ? a.alphas[ai] : 0.5;
         mant[q] = 1.0;
         ex[q] = 0;
-        // 0 * log(0) = NaN -> -inf (Occupancy.py:112-114) for sizes with no reads but zero probability
-        if ((ai >= a.n_alpha) || a.both_zero || (al[q] == 0.0 && a.pf_has_zero) || (al[q] == 1.0 && a.pn_has_zero)) dead |= 1u << q;
     }
-    const bool last_is_one = (al[NQ - 1] == 1.0);  // alpha == 1 (only ever the last grid value, checked on the host)
-    const int2 *en = a.ent + a.frag_off[c];
     for (int base = 0; base < nmax; base += 8) {
         {   // lane (g, r) prepares fragment base + r of window g: nuc_probs / sum, nfr_probs / sum, Occupancy.py:106-109
             const int idx = base + r;
@@ -222,19 +263,22 @@ __global__ void __launch_bounds__(MLE_WARPS * 32) k_occ_mle(OccMleArgs a)
             hi = a.alphas[okmax];
         }
     }
-    if (!valid) return;
-    const int left = t - a.halfstep, right = min(t + a.halfstep + 1, L);
-    for (int x = left + r; x < right; x += 8) {
-        a.vals[oo + x] = occ;
-        a.lower[oo + x] = lo;
-        a.upper_b[oo + x] = hi;
-    }
-    if (wi == nwin - 1)  // positions past the last window stay NaN (np.ones(n)*nan, Occupancy.py:133-135)
-        for (int x = right + r; x < L; x += 8) {
-            a.vals[oo + x] = nb_nan();
-            a.lower[oo + x] = nb_nan();
-            a.upper_b[oo + x] = nb_nan();
+    if (valid) {
+        const int left = t - a.halfstep, right = min(t + a.halfstep + 1, L);
+        for (int x = left + r; x < right; x += 8) {
+            a.vals[oo + x] = occ;
+            a.lower[oo + x] = lo;
+            a.upper_b[oo + x] = hi;
         }
+        if (wi == nwin - 1)  // positions past the last window stay NaN (np.ones(n)*nan, Occupancy.py:133-135)
+            for (int x = right + r; x < L; x += 8) {
+                a.vals[oo + x] = nb_nan();
+                a.lower[oo + x] = nb_nan();
+                a.upper_b[oo + x] = nb_nan();
+            }
+    }
+    __syncwarp();
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -502,12 +546,31 @@ int nb200_occ_run(nb200_ctx *ctx, nb200_dbatch *b)
         int max_win = (b->max_len - halfstep + p.step - 1) / p.step;
         if (max_win < 1) max_win = 1;
         const size_t smem = sizeof(double) * 2 * (size_t)p.upper;
+        a.wsn = a.wsf = nullptr;
+        if (p.use_bias) {
+            const size_t nws = tl / p.step + n + 2;
+            NB_CUDA(ctx, b->o_wsn.reserve(sizeof(double) * nws));
+            NB_CUDA(ctx, b->o_wsf.reserve(sizeof(double) * nws));
+            a.wsn = b->o_wsn.as<double>();
+            a.wsf = b->o_wsf.as<double>();
+            const size_t wsm = sizeof(double) * 2 * ((size_t)(WS_WIN - 1) * p.step + window);
+            if (wsm > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_occ_winsums, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm));
+            ProfScope ps(ctx, b->stream, "k_occ_winsums");
+            dim3 wgrid((unsigned)div_up64(max_win, WS_WIN), n);
+            k_occ_winsums<<<wgrid, WS_WIN, wsm, b->stream>>>(a.out_off, a.cn, a.cf, p.flank, p.step, halfstep, b->o_wsn.as<double>(),
+                                                            b->o_wsf.as<double>());
+            NB_LAUNCH_CHECK(ctx);
+        }
         ProfScope ps(ctx, b->stream, "k_occ_mle");
-        dim3 grid((unsigned)div_up64(max_win, MLE_WARPS * MLE_GROUPS), n);
-        if (r.n_alpha <= 104)
-            k_occ_mle<13><<<grid, MLE_WARPS * 32, smem, b->stream>>>(a);
-        else
-            k_occ_mle<16><<<grid, MLE_WARPS * 32, smem, b->stream>>>(a);
+        dim3 grid((unsigned)div_up64(max_win, MLE_WARPS * MLE_GROUPS * MLE_ITERS), n);
+        static const int mle_lb = getenv("NB200_MLE_LB") ? atoi(getenv("NB200_MLE_LB")) : 4;
+        if (r.n_alpha <= 104) {
+            if (mle_lb >= 5)
+                k_occ_mle<13, 5><<<grid, MLE_WARPS * 32, smem, b->stream>>>(a);
+            else
+                k_occ_mle<13, 4><<<grid, MLE_WARPS * 32, smem, b->stream>>>(a);
+        } else
+            k_occ_mle<16, 4><<<grid, MLE_WARPS * 32, smem, b->stream>>>(a);
         NB_LAUNCH_CHECK(ctx);
     }
     {
