@@ -34,7 +34,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "bp scored/sec (occ+nuc), synthetic 10 kb chunks, 251x251 VMat"
 R_V, W_V = 251, 251
-TC_DRAM_BYTES_PER_CHUNK = 17.55e6 / 200  # measured, see roofline.traffic_source
+TC_DRAM_BYTES_PER_CHUNK = 35.40e6 / 400  # measured, see roofline.traffic_source
 
 
 def load_peaks():
@@ -292,6 +292,16 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     e2e_s = time.perf_counter() - t0
     clk = clocks.stop()
+    # the copies alone (no compute in flight): the host-link floor under the end-to-end number
+    d2h_alone_s = None
+    if hs[0] is not None and args.path == "both":
+        eng.sync(hs[0])
+        t1 = time.perf_counter()
+        for _ in range(3):
+            eng.nuc_download(hs[0], outs[0][1])
+            eng.occ_download(hs[0], outs[0][0])
+        eng.sync(hs[0])
+        d2h_alone_s = (time.perf_counter() - t1) / 3
 
     # ---- end-of-run reductions (the only collectives on the path): nuc_dist and fragment sizes
     nd = outs[(K - 1) & 1][0]["nuc_dist"].sum(axis=0) if args.path != "nuc" else np.zeros(wl.upper)
@@ -325,8 +335,8 @@ def run_ours(args, rank, world, local_rank):
         achieved = flop_per_launch / k_avg_s / 1e12 if k_avg_s > 0 else 0.0
         roofline = dict(bound="tensor", kernel=kname, achieved=achieved, peak=peaks["tf_sustained"], unit="TFLOP/s",
                         frac=achieved / peaks["tf_sustained"], traffic=TC_DRAM_BYTES_PER_CHUNK * B if kname == "k_nuc_bx_tc" else None,
-                        traffic_source="ncu --set full, dram__bytes_read+write of k_nuc_bx_tc: 17.55 MB per 200-chunk launch "
-                                       "(profiles/r1_tc_path_ncu_full.txt), scaled to this launch's chunk count", peak_source=peaks["source"] + " bf16 sustained",
+                        traffic_source="ncu --set full, dram__bytes_read+write of k_nuc_bx_tc: 35.40 MB per 400-chunk launch "
+                                       "(profiles/r1_final_ncu_full.txt), scaled to this launch's chunk count", peak_source=peaks["source"] + " bf16 sustained",
                         kernel_ms_per_launch=kms / max(kcount, 1), kernel_share_of_step=kms / total_ms if total_ms else None,
                         algorithmic_flop_per_bp=2.0 * R_V * W_V,
                         per_kernel_ms={k: round(v[1] / K, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])})
@@ -342,6 +352,8 @@ def run_ours(args, rank, world, local_rank):
                     roofline=roofline, cpu_baseline=cpu,
                     e2e=dict(value=bp_step * K * world / e2e_s, unit="bp/s", h2d_bytes_per_step=int(h2d_b), d2h_bytes_per_step=int(d2h_b),
                              ms_per_step=e2e_s / K * 1e3,
+                             d2h_alone_ms_per_step=None if d2h_alone_s is None else d2h_alone_s * 1e3,
+                             d2h_alone_gbs=None if d2h_alone_s is None else d2h_b / d2h_alone_s / 1e9,
                              d2h="3 smoothed occupancy tracks + peaks + nuc_dist, nucleoatac_signal + smooth + call table (f64)"),
                     gpu_launches=launches, clocks=clk, wall_s_device_pass=t_wall, gen_s=t_gen,
                     checks=dict(nuc_dist_sum=float(nd.sum()), fragment_size_count=int(fs.sum())))

@@ -189,11 +189,19 @@ int nb200_batch_upload(nb200_ctx *ctx, const nb200_batch *h, nb200_dbatch **io)
     if (!b) {
         b = new nb200_dbatch();
         cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_pass, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_copied_occ, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_copied_nuc, cudaEventDisableTiming);
         if (e != cudaSuccess) {
-            delete b;
+            nb200_batch_free(nullptr, b);
             return nb200_cuda_fail(ctx, e, "cudaStreamCreate", __FILE__, __LINE__);
         }
         *io = b;
+    } else {
+        // the arrays of the previous use may still be on their way to the host
+        NB_CUDA(ctx, cudaStreamWaitEvent(b->stream, b->ev_copied_occ, 0));
+        NB_CUDA(ctx, cudaStreamWaitEvent(b->stream, b->ev_copied_nuc, 0));
     }
     const int n = h->n_chunks;
     b->n_chunks = n;
@@ -254,6 +262,7 @@ int nb200_batch_free(nb200_ctx *ctx, nb200_dbatch *b)
     if (!b) return NB200_OK;
     if (ctx) cudaSetDevice(ctx->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
+    if (b->copy_stream) cudaStreamSynchronize(b->copy_stream);
     DevBuf *bufs[] = {&b->d_start, &b->d_end, &b->d_frag_off, &b->d_pos, &b->d_tlen, &b->d_seq_off, &b->d_seq_start,
                       &b->d_seq, &b->d_out_off, &b->d_bias_off, &b->d_E, &b->d_col_off, &b->d_col_ptr, &b->d_col_low,
                       &b->d_cursor, &b->d_ent, &b->o_vals, &b->o_lower, &b->o_upper, &b->o_svals, &b->o_slower,
@@ -266,6 +275,10 @@ int nb200_batch_free(nb200_ctx *ctx, nb200_dbatch *b)
     for (auto d : bufs) d->release();
     if (b->ev_start) cudaEventDestroy(b->ev_start);
     if (b->ev_stop) cudaEventDestroy(b->ev_stop);
+    if (b->ev_pass) cudaEventDestroy(b->ev_pass);
+    if (b->ev_copied_occ) cudaEventDestroy(b->ev_copied_occ);
+    if (b->ev_copied_nuc) cudaEventDestroy(b->ev_copied_nuc);
+    if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
     return NB200_OK;
@@ -275,6 +288,7 @@ int nb200_batch_sync(nb200_ctx *ctx, nb200_dbatch *b)
 {
     if (!ctx || !b) return nb200_fail(ctx, NB200_ERR_ARG, "nb200_batch_sync: NULL argument");
     NB_CUDA(ctx, cudaStreamSynchronize(b->stream));
+    NB_CUDA(ctx, cudaStreamSynchronize(b->copy_stream));
     NB_CUDA(ctx, cudaGetLastError());
     return NB200_OK;
 }

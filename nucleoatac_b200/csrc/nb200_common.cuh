@@ -153,6 +153,10 @@ void nb200_prof_collect(nb200_ctx *ctx);  // drain pending events (sync)
 // ---------------------------------------------------------------------------------------------
 struct nb200_dbatch {
     cudaStream_t stream = nullptr;
+    // results go back on their own stream, ordered after the producing pass by an event, so the next pass (of this or
+    // another batch) computes while they are on the wire; a pass / upload waits for the copies that read what it rewrites
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_pass = nullptr, ev_copied_occ = nullptr, ev_copied_nuc = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     int n_chunks = 0;
     int64_t total_len = 0;   // sum of chunk lengths

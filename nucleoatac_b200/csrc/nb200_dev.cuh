@@ -255,20 +255,28 @@ struct SmoothTracks {
     const double *in[3];
     double *out[3];
 };
-// Each thread owns SM_XT consecutive outputs and slides a register window over the taps; the tile is stored
-// SM_XT-way interleaved in shared memory (element e at (e % XT) * Q + e / XT) so those reads are conflict free.
-// Tiles without NaN / zero padding take the fast path (denominator = sum of the window, as np.convolve of the
-// window with an all-ones indicator gives); the others evaluate the NaN-aware form tap by tap.
+// out[n] = sum_d wd[d] x[n + d], wd[d] = w[h - d].  Each thread owns SM_XT = 4 consecutive outputs and walks the taps two
+// at a time: the inputs of (n .. n+3) x (d, d+1) are three aligned pairs that slide by one pair per step, so a step is one
+// 16-byte load of x, one broadcast 16-byte load of the tap pair and 8 FMAs.  Tiles without NaN / zero padding take this
+// fast path (denominator = sum of the window, as np.convolve of the window with an all-ones indicator gives); the others
+// evaluate the NaN-aware form tap by tap.
+static inline size_t smooth_same_smem(int wlen)   // taps (padded) + staged tile + NaN prefix counts
+{
+    const size_t T2 = (size_t)wlen + 4, nX = SM_TILE + T2 + 4;
+    return sizeof(double) * (T2 + nX) + sizeof(int) * (nX + 2) + 16;
+}
 static __global__ void __launch_bounds__(SM_THREADS) k_smooth_same(SmoothTracks tr, const int64_t *__restrict__ out_off,
                                                                  const double *__restrict__ win, int wlen, int clip_neg)
 {
-    extern __shared__ double sm_s[];
+    extern __shared__ __align__(16) double sm_s[];
     __shared__ int s_slow;
-    const int wpad = (wlen + SM_XT - 1) / SM_XT * SM_XT;
-    const int nX = SM_TILE + wpad;                       // elements staged per tile (multiple of XT)
-    const int Q = nX / SM_XT;
-    double *s_w = sm_s;                 // [wpad] window, zero padded
-    double *s_x = sm_s + wpad;          // [nX] interleaved
+    __shared__ double s_den;
+    const int h = (wlen - 1) / 2;
+    const int dlo = -((wlen - h) & ~1);                  // first (even) tap offset: d in [h - wlen + 1, h] is covered by
+    const int T2 = (h - dlo + 2) & ~1;                   //   T2 (even) taps from dlo on, zero padded
+    const int nX = SM_TILE + T2 + 4;
+    double *s_w = sm_s;                 // [T2] wd, zero padded
+    double *s_x = sm_s + T2;            // [nX] s_x[j] = x[x0 + dlo + j]
     const int c = blockIdx.y;
     const int64_t o = out_off[c];
     const int L = (int)(out_off[c + 1] - o);
@@ -276,12 +284,20 @@ static __global__ void __launch_bounds__(SM_THREADS) k_smooth_same(SmoothTracks 
     if (x0 >= L) return;
     const double *in = tr.in[blockIdx.z] + o;
     double *out = tr.out[blockIdx.z] + o;
-    const int h = (wlen - 1) / 2;
     if (threadIdx.x == 0) s_slow = 0;
-    for (int i = threadIdx.x; i < wpad; i += blockDim.x) s_w[i] = (i < wlen) ? win[i] : 0.0;
+    for (int k = threadIdx.x; k < T2; k += blockDim.x) {
+        const int m = h - (dlo + k);
+        s_w[k] = (m >= 0 && m < wlen) ? win[m] : 0.0;
+    }
+    if (threadIdx.x < 32) {             // sum of the window
+        double d = 0.0;
+        for (int m = threadIdx.x; m < wlen; m += 32) d += win[m];
+        d = warp_sum(d);
+        if (threadIdx.x == 0) s_den = d;
+    }
     __syncthreads();
-    // s_x element j <-> global index lo + j; the taps of output n are indices n + h - m, m in [0, wlen)
-    const int lo = x0 + h - (wpad - 1);
+    const int lo = x0 + dlo;
+    const int n_end = min(x0 + SM_TILE, L);
     int slow = 0;
     for (int j = threadIdx.x; j < nX; j += blockDim.x) {
         const int idx = lo + j;
@@ -291,60 +307,65 @@ static __global__ void __launch_bounds__(SM_THREADS) k_smooth_same(SmoothTracks 
             if (clip_neg && v < 0) v = 0.0;
         }
         if (v != v) {
-            if (idx > x0 + h - wlen && idx < min(x0 + SM_TILE, L) + h) slow = 1;  // a real tap of this tile is missing
-            else v = 0.0;                                                          // only ever multiplied by padded (zero) taps
+            if (idx >= x0 + h - wlen + 1 && idx <= n_end - 1 + h) slow = 1;  // a real tap of this tile is missing
+            else v = 0.0;                                                    // only ever multiplied by padded (zero) taps
         }
-        s_x[(j % SM_XT) * Q + j / SM_XT] = v;
+        s_x[j] = v;
     }
     if (slow) s_slow = 1;
     __syncthreads();
+    // In a tile with missing taps (chunk edges, NaN stretches) only the threads whose own window holds one go tap by tap:
+    // s_cnt[j] = number of NaN among s_x[0 .. j)
+    bool my_slow = false;
+    if (s_slow) {
+        int *s_cnt = reinterpret_cast<int *>(s_x + nX);
+        if (threadIdx.x < 32) {
+            int run = 0;
+            for (int j0 = 0; j0 < nX; j0 += 32) {
+                const int j = j0 + threadIdx.x;
+                const bool bad = j < nX && s_x[j] != s_x[j];
+                const unsigned m = __ballot_sync(NB_FULL, bad);
+                if (j < nX) s_cnt[j] = run + __popc(m & ((1u << threadIdx.x) - 1u));
+                run += __popc(m);
+            }
+            if (threadIdx.x == 0) s_cnt[nX] = run;
+        }
+        __syncthreads();
+        const int a = threadIdx.x * SM_XT, b = min(a + T2 + SM_XT, nX);
+        my_slow = s_cnt[b] != s_cnt[a];
+    }
     const int n0 = x0 + threadIdx.x * SM_XT;
     if (n0 >= L) return;
-    if (!s_slow) {
-        double den = 0.0;
-        for (int m = 0; m < wlen; m++) den += s_w[m];
-        double acc[SM_XT], wv[SM_XT];
-#pragma unroll
-        for (int u = 0; u < SM_XT; u++) acc[u] = 0.0;
-        // window registers hold elements e0 + u, e0 = (n0 + h - m) - lo for the current tap group
-        const int t = threadIdx.x;
-        int e0 = n0 + h - lo;            // multiple of XT offset: (x0 + t*XT + h) - (x0 + h - wpad + 1) = t*XT + wpad - 1
-#pragma unroll
-        for (int u = 0; u < SM_XT; u++) {
-            const int e = e0 + u;
-            wv[u] = s_x[(e % SM_XT) * Q + e / SM_XT];
+    if (!my_slow) {
+        const double2 *px = reinterpret_cast<const double2 *>(s_x + threadIdx.x * SM_XT);
+        const double2 *pw = reinterpret_cast<const double2 *>(s_w);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        double2 A = px[0], B = px[1];
+#pragma unroll 4
+        for (int k2 = 0; k2 < T2 / 2; k2++) {
+            const double2 C = px[k2 + 2], w = pw[k2];
+            a0 = fma(w.x, A.x, fma(w.y, A.y, a0));
+            a1 = fma(w.x, A.y, fma(w.y, B.x, a1));
+            a2 = fma(w.x, B.x, fma(w.y, B.y, a2));
+            a3 = fma(w.x, B.y, fma(w.y, C.x, a3));
+            A = B;
+            B = C;
         }
-        for (int m0 = 0; m0 < wpad; m0 += SM_XT) {
-            double nw[SM_XT];
-#pragma unroll
-            for (int mm = 0; mm < SM_XT; mm++) {
-                const double w = s_w[m0 + mm];
-#pragma unroll
-                for (int u = 0; u < SM_XT; u++) {
-                    const int wi = u - mm;
-                    acc[u] = fma(w, wi >= 0 ? wv[wi] : nw[-wi - 1], acc[u]);
-                }
-                const int e = e0 - m0 - mm - 1;   // next lower element
-                nw[mm] = (e >= 0) ? s_x[(e % SM_XT) * Q + e / SM_XT] : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < SM_XT; u++) wv[u] = nw[SM_XT - 1 - u];
-        }
-#pragma unroll
-        for (int u = 0; u < SM_XT; u++)
-            if (n0 + u < L) out[n0 + u] = acc[u] / den;
-        (void)t;
+        const double den = s_den;
+        if (n0 < L) out[n0] = a0 / den;
+        if (n0 + 1 < L) out[n0 + 1] = a1 / den;
+        if (n0 + 2 < L) out[n0 + 2] = a2 / den;
+        if (n0 + 3 < L) out[n0 + 3] = a3 / den;
     } else {
         for (int u = 0; u < SM_XT; u++) {
             const int n = n0 + u;
             if (n >= L) break;
             double num = 0.0, den = 0.0;
             for (int m = 0; m < wlen; m++) {
-                const int e = n + h - m - lo;
-                const double v = s_x[(e % SM_XT) * Q + e / SM_XT];
+                const double v = s_x[n + h - m - lo];
                 if (v == v) {
-                    num += s_w[m] * v;
-                    den += s_w[m];
+                    num += win[m] * v;
+                    den += win[m];
                 }
             }
             out[n] = (den == 0.0) ? nb_nan() : num / den;

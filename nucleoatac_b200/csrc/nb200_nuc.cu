@@ -598,6 +598,7 @@ int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
         return nb200_fail(ctx, NB200_ERR_STATE, "nb200_set_fragment_sizes missing or shorter than the VMat's upper size");
     if (r.v_upper > NB200_MAX_UPPER) return nb200_fail(ctx, NB200_ERR_ARG, "VMat upper > %d unsupported", NB200_MAX_UPPER);
     NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    NB_CUDA(ctx, cudaStreamWaitEvent(b->stream, b->ev_copied_nuc, 0));   // a download of the previous pass may still read the arrays
     const int n = b->n_chunks;
     const int W = r.v_cols, w = r.v_w, lv = r.v_lower, uv = r.v_upper;
     if (b->min_len < p.smooth_len)
@@ -714,7 +715,7 @@ int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
         SmoothTracks tr;
         tr.in[0] = tr.in[1] = tr.in[2] = b->n_norm.as<double>();
         tr.out[0] = tr.out[1] = tr.out[2] = b->n_smooth.as<double>();
-        size_t smem = sizeof(double) * (SM_TILE + 2 * (size_t)p.smooth_len + 16);
+        size_t smem = smooth_same_smem(p.smooth_len);
         if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_smooth_same, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ProfScope ps(ctx, b->stream, "k_smooth_same");
         dim3 grid((unsigned)div_up64(b->max_len, SM_TILE), n, 1);
@@ -830,7 +831,7 @@ int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
 static int d2h(nb200_ctx *ctx, nb200_dbatch *b, void *dst, const DevBuf &src, size_t bytes)
 {
     if (!dst || !bytes) return NB200_OK;
-    NB_CUDA(ctx, cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, b->stream));
+    NB_CUDA(ctx, cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, b->copy_stream));
     return NB200_OK;
 }
 
@@ -840,6 +841,12 @@ int nb200_nuc_download(nb200_ctx *ctx, nb200_dbatch *b, const nb200_nuc_out *o)
     if (!b->nuc_done) return nb200_fail(ctx, NB200_ERR_STATE, "nb200_nuc_download: nb200_nuc_run has not been called on this batch");
     const size_t tb = sizeof(double) * (size_t)b->total_len;
     const int n = b->n_chunks;
+    NB_CUDA(ctx, cudaEventRecord(b->ev_pass, b->stream));            // copies start once the pass has finished ...
+    NB_CUDA(ctx, cudaStreamWaitEvent(b->copy_stream, b->ev_pass, 0));
+    struct Copied {                                                  // ... and the next pass over these arrays waits for them
+        nb200_dbatch *b;
+        ~Copied() { cudaEventRecord(b->ev_copied_nuc, b->copy_stream); }
+    } copied{b};
     NB_CHECK(d2h(ctx, b, o->nuc_signal, b->n_signal, tb));
     NB_CHECK(d2h(ctx, b, o->background, b->n_bg, tb));
     NB_CHECK(d2h(ctx, b, o->norm_signal, b->n_norm, tb));

@@ -433,6 +433,7 @@ int nb200_occ_run(nb200_ctx *ctx, nb200_dbatch *b)
         return nb200_fail(ctx, NB200_ERR_STATE, "nb200_set_occ_model missing or its size range differs from --upper");
     if (p.upper > NB200_MAX_UPPER) return nb200_fail(ctx, NB200_ERR_ARG, "upper > %d unsupported", NB200_MAX_UPPER);
     NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    NB_CUDA(ctx, cudaStreamWaitEvent(b->stream, b->ev_copied_occ, 0));   // a download of the previous pass may still read the arrays
     const int n = b->n_chunks;
     const int window = 2 * p.flank + 1;
     const int halfstep = (p.step - 1) / 2;
@@ -581,7 +582,7 @@ int nb200_occ_run(nb200_ctx *ctx, nb200_dbatch *b)
         tr.out[0] = b->o_svals.as<double>();
         tr.out[1] = b->o_slower.as<double>();
         tr.out[2] = b->o_supper.as<double>();
-        size_t smem = sizeof(double) * (SM_TILE + 2 * (size_t)p.smooth_len + 16);
+        size_t smem = smooth_same_smem(p.smooth_len);
         if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_smooth_same, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ProfScope ps(ctx, b->stream, "k_smooth_same");
         dim3 grid((unsigned)div_up64(b->max_len, SM_TILE), n, 3);
@@ -630,7 +631,7 @@ int nb200_occ_run(nb200_ctx *ctx, nb200_dbatch *b)
 static int d2h(nb200_ctx *ctx, nb200_dbatch *b, void *dst, const DevBuf &src, size_t bytes)
 {
     if (!dst || !bytes) return NB200_OK;
-    NB_CUDA(ctx, cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, b->stream));
+    NB_CUDA(ctx, cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, b->copy_stream));
     return NB200_OK;
 }
 
@@ -640,6 +641,12 @@ int nb200_occ_download(nb200_ctx *ctx, nb200_dbatch *b, const nb200_occ_out *o)
     if (!b->occ_done) return nb200_fail(ctx, NB200_ERR_STATE, "nb200_occ_download: nb200_occ_run has not been called on this batch");
     const size_t tb = sizeof(double) * (size_t)b->total_len;
     const int n = b->n_chunks;
+    NB_CUDA(ctx, cudaEventRecord(b->ev_pass, b->stream));            // copies start once the pass has finished ...
+    NB_CUDA(ctx, cudaStreamWaitEvent(b->copy_stream, b->ev_pass, 0));
+    struct Copied {                                                  // ... and the next pass over these arrays waits for them
+        nb200_dbatch *b;
+        ~Copied() { cudaEventRecord(b->ev_copied_occ, b->copy_stream); }
+    } copied{b};
     NB_CHECK(d2h(ctx, b, o->smoothed_vals, b->o_svals, tb));
     NB_CHECK(d2h(ctx, b, o->smoothed_lower, b->o_slower, tb));
     NB_CHECK(d2h(ctx, b, o->smoothed_upper, b->o_supper, tb));
