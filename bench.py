@@ -13,7 +13,7 @@ Printed JSON line (rank 0):
   value   whole-job bp/s with the step's inputs already resident in HBM (CUDA-event time of the
           compute of each step, max over ranks)
   e2e     the same metric through the public API with HOST buffers: pinned H2D of reads+sequence,
-          compute, D2H of every track and call table, double-buffered on two streams, wall clock
+          compute, D2H of every track and call table, three batches in flight (compute + copy stream each), wall clock
           bracketed by device synchronisation
   roofline / cpu_baseline / clocks / gpu_launches as the task contract asks.
 `--impl reference` times the CPU restatement of the reference algorithm (oracle/, multiprocessing
@@ -48,33 +48,79 @@ def load_peaks():
 
 # ----------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
+    """SM clock + throttle reasons sampled every 100 ms during the timed regions, through NVML in-process (pynvml);
+    an `nvidia-smi -lms` subprocess is the fallback (its polling takes a driver lock often enough to cost the
+    multi-stream end-to-end pass ~5 ms per step, so it is not the default)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu):
-        self.gpu, self.rows, self.proc = gpu, [], None
+        self.gpu, self.rows, self.proc, self.nvml, self.stop_flag = gpu, [], None, None, False
+        self.source = None
+
+    def _visible_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.gpu])
+            except Exception:
+                pass
+        return self.gpu
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._visible_index())
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self._visible_index()), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.source = "nvidia-smi"
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        nv = self.nvml
+        bits = [("hw_slowdown", getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8))),
+                ("hw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40))),
+                ("sw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20))),
+                ("sw_power_cap", getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)))]
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = int(get_reasons(self.h))
+                self.rows.append([sm, self.mx, None] + [("Active" if mask & b else "Not Active") for _, b in bits])
+            except Exception:
+                pass
+            time.sleep(0.1)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
-        if not self.proc:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.t.join(timeout=2)
+        elif self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        else:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no NVML / nvidia-smi"])
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
@@ -82,12 +128,12 @@ class ClockSampler:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
                 for n, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
+                    if str(v).lower().startswith("active"):
                         reasons.add(n)
             except Exception:
                 pass
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                    reasons=sorted(reasons), samples=len(sm), source=self.source)
 
 
 # ----------------------------------------------------------------------------- batch generation
@@ -225,9 +271,10 @@ def run_ours(args, rank, world, local_rank):
         n.pop("nuc_signal")
         n.pop("background")
         return o, n
-    outs = [default_outputs(batches[0]) for _ in range(2)]
+    NBUF = 3  # batches in flight end to end: one computing, one on the wire to the host, one being enqueued
+    outs = [default_outputs(batches[0]) for _ in range(NBUF)]
     bp_step = batches[0].total_len
-    hs = [None, None]
+    hs = [None] * NBUF
 
     def barrier():
         if dist is not None:
@@ -264,23 +311,27 @@ def run_ours(args, rank, world, local_rank):
     eng.profile(False)
     total_ms = float(np.sum(dev_ms))
 
-    # ---- pass B: end to end with host buffers, double buffered on two streams
-    def e2e_loop(idx):
+    # ---- pass B: end to end with host buffers, NBUF batches in flight (each with its compute and copy stream)
+    def e2e_loop(idx, download=True, compute=True):
         h2d = d2h = 0
         for n, i in enumerate(idx):
-            s = n & 1
-            if hs[s] is not None and n >= 2:
-                eng.sync(hs[s])  # results of step n-2 are on the host; its buffers can be recycled
+            s = n % NBUF
+            if hs[s] is not None and n >= NBUF:
+                eng.sync(hs[s])  # results of step n-NBUF are on the host; its buffers can be recycled
             hs[s] = eng.upload(batches[i], hs[s])
             d2h = 0
             if args.path != "occ":
-                eng.nuc_run(hs[s])
-                d2h += eng.nuc_download(hs[s], outs[s][1])
+                if compute or n < NBUF:
+                    eng.nuc_run(hs[s])
+                if download:
+                    d2h += eng.nuc_download(hs[s], outs[s][1])
             if args.path != "nuc":
-                eng.occ_run(hs[s])
-                d2h += eng.occ_download(hs[s], outs[s][0])
+                if compute or n < NBUF:
+                    eng.occ_run(hs[s])
+                if download:
+                    d2h += eng.occ_download(hs[s], outs[s][0])
             h2d = eng.h2d_bytes(hs[s])
-        for s in (0, 1):
+        for s in range(NBUF):
             if hs[s] is not None:
                 eng.sync(hs[s])
         return h2d, d2h
@@ -292,6 +343,12 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     e2e_s = time.perf_counter() - t0
     clk = clocks.stop()
+    if os.environ.get("NB200_E2E_DIAG"):  # developer aid: which leg of the pipeline costs what
+        for name, kw in (("compute only", dict(download=False)), ("both", dict())):
+            e2e_loop(range(Wm), **kw)
+            t1 = time.perf_counter()
+            e2e_loop(range(Wm, Wm + K), **kw)
+            sys.stderr.write("[e2e diag] %-12s %.2f ms per step\n" % (name, (time.perf_counter() - t1) / K * 1e3))
     # the copies alone (no compute in flight): the host-link floor under the end-to-end number
     d2h_alone_s = None
     if hs[0] is not None and args.path == "both":
@@ -304,7 +361,7 @@ def run_ours(args, rank, world, local_rank):
         d2h_alone_s = (time.perf_counter() - t1) / 3
 
     # ---- end-of-run reductions (the only collectives on the path): nuc_dist and fragment sizes
-    nd = outs[(K - 1) & 1][0]["nuc_dist"].sum(axis=0) if args.path != "nuc" else np.zeros(wl.upper)
+    nd = outs[(K - 1) % NBUF][0]["nuc_dist"].sum(axis=0) if args.path != "nuc" else np.zeros(wl.upper)
     fs = eng.fragment_sizes(batches[-1].starts, batches[-1].ends, batches[-1].frag_off, batches[-1].frag_pos,
                             batches[-1].frag_tlen, 0, wl.upper)
     if dist is not None:

@@ -1,4 +1,4 @@
-"""Command line: `python -m nucleoatac_b200 occ|nuc ...` with the reference's flags (nucleoatac/cli.py:96-125,
+"""Command line: `python -m nucleoatac_b200 occ|nuc|vprocess|merge|nfr|run ...` with the reference's flags (nucleoatac/cli.py:96-125,
 203-240) plus `--gpus`, `--batch` and `--xcor_mode`.  `--cores` is accepted and ignored (the device replaces the pool)."""
 import argparse
 import os
@@ -70,7 +70,24 @@ def build_parser():
     g.add_argument("--out", metavar="out_basename", help="output file basename")
     g.add_argument("--sep", metavar="min_separation", default=120, help="minimum separation between call")
     g.add_argument("--min_occ", metavar="min_occ", default=0.1, help="minimum lower bound occupancy of nucleosomes to be considered for excluding NFR. default is 0.1")
-    rn = sub.add_parser("run", help="Main nucleoatac utility: occ, vprocess, nuc and merge in one go (the NFR step of the reference is not part of this package)")
+    nf = sub.add_parser("nfr", help="nucleoatac function: Call NFRs")
+    g = nf.add_argument_group("Required", "Necessary arguments")
+    g.add_argument("--bed", metavar="bed_file", required=True, help="Peaks in bed format")
+    g.add_argument("--occ_track", metavar="occ_file", required=True, help="bgzip compressed, tabix-indexed bedgraph file with occcupancy track.")
+    g.add_argument("--calls", metavar="nucpos_file", required=True, help="bed file with nucleosome center calls")
+    g = nf.add_argument_group("Insertion track options", "Either input insertion track or bamfile")
+    g.add_argument("--ins_track", metavar="ins_file", help="bgzip compressed, tabix-indexed bedgraph file with insertion track. will be generated if not included")
+    g.add_argument("--bam", metavar="bam_file", help="Sorted (and indexed) BAM file")
+    g = nf.add_argument_group("Bias calculation information", "Highly recommended. If fasta is not provided, will not calculate bias")
+    g.add_argument("--fasta", metavar="genome_seq", help="Indexed fasta file")
+    g.add_argument("--pwm", metavar="Tn5_PWM", default="Human", help="PWM descriptor file. Default is Human.PWM.txt included in package")
+    g = nf.add_argument_group("General options", "optional")
+    g.add_argument("--out", metavar="out_basename", help="output file basename")
+    g.add_argument("--cores", metavar="num_cores", default=1, type=int, help="Number of cores to use (ignored)")
+    g = nf.add_argument_group("NFR determination parameters")
+    g.add_argument("--max_occ", metavar="float", default=0.1, type=float, help="Maximum mean occupancy for NFR. Default is 0.1")
+    g.add_argument("--max_occ_upper", metavar="float", default=0.25, type=float, help="Maximum for minimum of  upper bound occupancy in NFR. Default is 0.25")
+    rn = sub.add_parser("run", help="Main nucleoatac utility: occ, vprocess, nuc, merge and nfr in one go")
     g = rn.add_argument_group("Required", "Necessary arguments")
     g.add_argument("--bed", metavar="bed_file", required=True, help="Regions for which to do stuff.")
     g.add_argument("--bam", metavar="bam_file", required=True, help="Accepts sorted BAM file")
@@ -80,7 +97,7 @@ def build_parser():
     g.add_argument("--pwm", metavar="Tn5_PWM", default="Human", help="PWM descriptor file. Default is Human.PWM.txt included in package")
     g.add_argument("--cores", metavar="num_cores", default=1, type=int, help="Number of cores to use (ignored)")
     g.add_argument("--write_all", action="store_true", default=False, help="write all tracks")
-    for sp in (occ, nuc):
+    for sp in (occ, nuc, nf):
         g = sp.add_argument_group("Device options", "")
         g.add_argument("--device", default=0, type=int, help="CUDA device of this process")
         g.add_argument("--rank", default=0, type=int, help="shard index: this process scores chunks k with k %% world == rank")
@@ -111,7 +128,11 @@ def nucleoatac_main(argv=None):
         print("---------Merging----------------------------------------------------")
         from .merge import run_merge
         run_merge(args)
-    elif args.command == "run":  # nucleoatac/cli.py:34-64 without the final nfr step
+    elif args.command == "nfr":
+        print("---------Calling NFR positions--------------------------------------")
+        from .run_nfr import run_nfr
+        run_nfr(args)
+    elif args.command == "run":  # nucleoatac/cli.py:34-64
         p = build_parser()
         base = ["--bed", args.bed, "--bam", args.bam, "--fasta", args.fasta, "--pwm", args.pwm, "--out", args.out]
         print("---------Step1: Computing Occupancy and Nucleosomal Insert Distribution---------")
@@ -128,6 +149,11 @@ def nucleoatac_main(argv=None):
         from .merge import run_merge
         run_merge(p.parse_args(["merge", "--occpeaks", args.out + ".occpeaks.bed.gz", "--nucpos", args.out + ".nucpos.bed.gz",
                                 "--out", args.out]))
+        print("---------Step5: Calling NFR positions-------------------------------------------")
+        from .run_nfr import run_nfr
+        run_nfr(p.parse_args(["nfr", "--bed", args.bed, "--occ_track", args.out + ".occ.bedgraph.gz", "--calls",
+                              args.out + ".nucmap_combined.bed.gz", "--out", args.out, "--fasta", args.fasta, "--pwm", args.pwm,
+                              "--bam", args.bam]))
     elif args.command == "vprocess":
         print("---------Processing VPlot-----------------------------------------")
         from .run_vprocess import run_vprocess

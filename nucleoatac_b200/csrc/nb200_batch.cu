@@ -126,8 +126,8 @@ int nb200_prep_bias(nb200_ctx *ctx, nb200_dbatch *b)
     }
     b->n_bias = boff[n];
     NB_CUDA(ctx, b->d_bias_off.reserve(sizeof(int64_t) * (n + 1)));
-    NB_CUDA(ctx, cudaMemcpyAsync(b->d_bias_off.p, boff.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, b->stream));
-    NB_CUDA(ctx, cudaStreamSynchronize(b->stream));  // boff is a local
+    memcpy(b->pin_slot(1), boff.data(), sizeof(int64_t) * (n + 1));
+    NB_CUDA(ctx, cudaMemcpyAsync(b->d_bias_off.p, b->pin_slot(1), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, b->stream));
     NB_CUDA(ctx, b->d_E.reserve(sizeof(double) * b->n_bias));
     {
         ProfScope ps(ctx, b->stream, "k_bias_track");
@@ -153,8 +153,8 @@ int nb200_prep_csc(nb200_ctx *ctx, nb200_dbatch *b, int pad, int upper, int atac
     for (int c = 0; c < n; c++) coff[c + 1] = coff[c] + (b->h_end[c] - b->h_start[c]) + 2 * (int64_t)pad + 1;
     b->n_colptr = coff[n];
     NB_CUDA(ctx, b->d_col_off.reserve(sizeof(int64_t) * (n + 1)));
-    NB_CUDA(ctx, cudaMemcpyAsync(b->d_col_off.p, coff.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, b->stream));
-    NB_CUDA(ctx, cudaStreamSynchronize(b->stream));
+    memcpy(b->pin_slot(2), coff.data(), sizeof(int64_t) * (n + 1));
+    NB_CUDA(ctx, cudaMemcpyAsync(b->d_col_off.p, b->pin_slot(2), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, b->stream));
     NB_CUDA(ctx, b->d_col_ptr.reserve(sizeof(int32_t) * b->n_colptr));
     NB_CUDA(ctx, b->d_cursor.reserve(sizeof(int32_t) * b->n_colptr));
     if (lower_split > 0) NB_CUDA(ctx, b->d_col_low.reserve(sizeof(int32_t) * b->n_colptr));
@@ -204,6 +204,14 @@ int nb200_batch_upload(nb200_ctx *ctx, const nb200_batch *h, nb200_dbatch **io)
         NB_CUDA(ctx, cudaStreamWaitEvent(b->stream, b->ev_copied_nuc, 0));
     }
     const int n = h->n_chunks;
+    if (b->h_pin_cap < (size_t)n + 1) {
+        NB_CUDA(ctx, cudaStreamSynchronize(b->stream));
+        if (b->h_pin) cudaFreeHost(b->h_pin);
+        b->h_pin = nullptr;
+        b->h_pin_cap = 0;
+        NB_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&b->h_pin), sizeof(int64_t) * 5 * ((size_t)n + 1), cudaHostAllocDefault));
+        b->h_pin_cap = (size_t)n + 1;
+    }
     b->n_chunks = n;
     b->h_start.assign(h->chunk_start, h->chunk_start + n);
     b->h_end.assign(h->chunk_end, h->chunk_end + n);
@@ -248,7 +256,8 @@ int nb200_batch_upload(nb200_ctx *ctx, const nb200_batch *h, nb200_dbatch **io)
     NB_CHECK(up(b->d_frag_off, h->frag_off, sizeof(int64_t) * (n + 1)));
     NB_CHECK(up(b->d_pos, h->frag_pos, sizeof(int32_t) * b->n_frag));
     NB_CHECK(up(b->d_tlen, h->frag_tlen, sizeof(int32_t) * b->n_frag));
-    NB_CHECK(up(b->d_out_off, b->h_out_off.data(), sizeof(int64_t) * (n + 1)));
+    memcpy(b->pin_slot(0), b->h_out_off.data(), sizeof(int64_t) * (n + 1));
+    NB_CHECK(up(b->d_out_off, b->pin_slot(0), sizeof(int64_t) * (n + 1)));
     if (b->have_seq) {
         NB_CHECK(up(b->d_seq_off, h->seq_off, sizeof(int64_t) * (n + 1)));
         NB_CHECK(up(b->d_seq_start, h->seq_start, sizeof(int32_t) * n));
@@ -275,6 +284,7 @@ int nb200_batch_free(nb200_ctx *ctx, nb200_dbatch *b)
     for (auto d : bufs) d->release();
     if (b->ev_start) cudaEventDestroy(b->ev_start);
     if (b->ev_stop) cudaEventDestroy(b->ev_stop);
+    if (b->h_pin) cudaFreeHost(b->h_pin);
     if (b->ev_pass) cudaEventDestroy(b->ev_pass);
     if (b->ev_copied_occ) cudaEventDestroy(b->ev_copied_occ);
     if (b->ev_copied_nuc) cudaEventDestroy(b->ev_copied_nuc);

@@ -158,6 +158,11 @@ struct nb200_dbatch {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_pass = nullptr, ev_copied_occ = nullptr, ev_copied_nuc = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    // pinned staging for the small per-chunk offset tables a pass uploads (5 slots of n_chunks + 1 int64): a copy from
+    // pageable memory would synchronise the stream with the host in the middle of a pass
+    int64_t *h_pin = nullptr;
+    size_t h_pin_cap = 0;   // elements per slot
+    int64_t *pin_slot(int slot) { return h_pin + (size_t)slot * h_pin_cap; }
     int n_chunks = 0;
     int64_t total_len = 0;   // sum of chunk lengths
     int64_t n_frag = 0;

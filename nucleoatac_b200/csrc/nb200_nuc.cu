@@ -630,7 +630,9 @@ int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
     for (int c = 0; c < n; c++) b->h_ncand_off[c + 1] = b->h_ncand_off[c] + (b->h_end[c] - b->h_start[c]) / p.redundant_sep + 2;
     const size_t nc = (size_t)b->h_ncand_off[n];
     NB_CUDA(ctx, b->n_cand_off.reserve(sizeof(int64_t) * (n + 1)));
-    NB_CUDA(ctx, cudaMemcpyAsync(b->n_cand_off.p, b->h_ncand_off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, b->stream));
+    if (b->nuc_done) NB_CUDA(ctx, cudaStreamSynchronize(b->stream));  // re-run: the staging slot may still be in flight
+    memcpy(b->pin_slot(3), b->h_ncand_off.data(), sizeof(int64_t) * (n + 1));
+    NB_CUDA(ctx, cudaMemcpyAsync(b->n_cand_off.p, b->pin_slot(3), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, b->stream));
     NB_CUDA(ctx, b->n_cand_count.reserve(sizeof(int32_t) * n));
     NB_CUDA(ctx, b->n_cand_pos.reserve(sizeof(int32_t) * nc));
     NB_CUDA(ctx, b->n_cand_flag.reserve(sizeof(int32_t) * nc));

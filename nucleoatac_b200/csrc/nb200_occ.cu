@@ -472,7 +472,9 @@ int nb200_occ_run(nb200_ctx *ctx, nb200_dbatch *b)
     for (int c = 0; c < n; c++) b->h_opeak_off[c + 1] = b->h_opeak_off[c] + (b->h_end[c] - b->h_start[c]) / p.sep + 2;
     const size_t np = (size_t)b->h_opeak_off[n];
     NB_CUDA(ctx, b->o_peak_off.reserve(sizeof(int64_t) * (n + 1)));
-    NB_CUDA(ctx, cudaMemcpyAsync(b->o_peak_off.p, b->h_opeak_off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, b->stream));
+    if (b->occ_done) NB_CUDA(ctx, cudaStreamSynchronize(b->stream));  // re-run: the staging slot may still be in flight
+    memcpy(b->pin_slot(4), b->h_opeak_off.data(), sizeof(int64_t) * (n + 1));
+    NB_CUDA(ctx, cudaMemcpyAsync(b->o_peak_off.p, b->pin_slot(4), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, b->stream));
     NB_CUDA(ctx, b->o_peak_count.reserve(sizeof(int32_t) * n));
     NB_CUDA(ctx, b->o_peak_pos.reserve(sizeof(int32_t) * np));
     DevBuf *pk[] = {&b->o_peak_occ, &b->o_peak_lower, &b->o_peak_upper, &b->o_peak_reads};

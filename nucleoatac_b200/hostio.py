@@ -460,6 +460,10 @@ class TabixFile:
             self.bins.append(bd)
         self.fh = open(path_gz, "rb")
 
+    @property
+    def contigs(self):
+        return self.names
+
     def fetch(self, chrom, start, end):
         """Lines (split on tabs) overlapping [start, end)."""
         if chrom not in self.names:

@@ -195,3 +195,46 @@ def test_cli_nuc_and_occ(files, tmp_path):
     np.testing.assert_allclose([float(g[3]) for g in got], [float(x[3]) for x in exp], rtol=1e-9)
     np.testing.assert_allclose(FragmentSizes.open(out + ".nuc_dist.txt").get(), nd, rtol=1e-9, atol=1e-12)
     assert os.path.exists(out + ".occpeaks.bed.gz") and os.path.exists(out + ".fragmentsizes.txt")
+
+
+def test_cli_nfr(files, tmp_path):
+    """`nucleoatac nfr` on files (after occ -> nuc -> merge wrote its inputs), NFRCalling.py:51-111 / run_nfr.py:72-127:
+    insertion track bit-exact, NFR rows equal to the oracle's on the same tracks and calls."""
+    from nucleoatac_b200.cli import nucleoatac_main
+    from nucleoatac_b200 import hostio
+    from oracle import refnfr
+    wl = files["wl"]
+    out = str(tmp_path / "run")
+    base = ["--bed", files["bed"], "--bam", files["bam"], "--fasta", files["fasta"], "--out", out]
+    assert nucleoatac_main(["occ"] + base + ["--sizes", files["sizes"]]) == 0
+    assert nucleoatac_main(["nuc"] + base + ["--vmat", files["vmat"], "--sizes", files["sizes"], "--occ_track", out + ".occ.bedgraph.gz"]) == 0
+    assert nucleoatac_main(["merge", "--occpeaks", out + ".occpeaks.bed.gz", "--nucpos", out + ".nucpos.bed.gz", "--out", out]) == 0
+    # loose thresholds so that the synthetic data yields regions
+    assert nucleoatac_main(["nfr", "--bed", files["bed"], "--occ_track", out + ".occ.bedgraph.gz", "--calls", out + ".nucmap_combined.bed.gz",
+                            "--bam", files["bam"], "--fasta", files["fasta"], "--out", out, "--max_occ", "0.9", "--max_occ_upper", "1.1"]) == 0
+    got_nfr = _read(out + ".nfrpos.bed.gz")
+    got_ins = _read(out + ".ins.bedgraph.gz")
+    assert os.path.exists(out + ".nfrpos.bed.gz.tbi") and os.path.exists(out + ".ins.bedgraph.gz.tbi")
+    occ_rows, upp_rows = _read(out + ".occ.bedgraph.gz"), _read(out + ".occ.upper_bound.bedgraph.gz")
+    calls = _read(out + ".nucmap_combined.bed.gz")
+
+    def region(rows, s, e):
+        v = np.full(e - s, np.nan)
+        for r in rows:
+            a, b = int(r[1]), int(r[2])
+            if b > s and a < e:
+                v[max(a - s, 0):min(b - s, e - s)] = float(r[3])
+        return v
+    exp_nfr, exp_ins = [], ""
+    for (s, e, pos, tlen, seq, s0) in sorted(files["chunks"], key=lambda c: c[0]):
+        s, e = s + 60, e - 60  # run_nfr reads the BED without slop (run_nfr.py:84-91)
+        lb = _bias(files, (s, e), wl)
+        dy = [int(r[1]) for r in calls if int(r[1]) < e and int(r[2]) > s]
+        recs, ins = refnfr.process_nfr_chunk(pos, tlen, s, e, dy, region(occ_rows, s, e), region(upp_rows, s, e), lb,
+                                             max_occ=0.9, max_occ_upper=1.1)
+        exp_nfr += [refnfr.nfr_bed("chrS", r).split("\t") for r in recs]
+        exp_ins += ra.write_track("chrS", s, e, ins)
+    assert got_ins == [l.split("\t") for l in exp_ins.splitlines()]
+    assert len(got_nfr) == len(exp_nfr) and len(got_nfr) > 0
+    assert [g[:3] for g in got_nfr] == [x[:3] for x in exp_nfr]
+    np.testing.assert_allclose([[float(v) for v in g[3:7]] for g in got_nfr], [[float(v) for v in x[3:7]] for x in exp_nfr], rtol=1e-9)

@@ -108,6 +108,8 @@ def test_cli_flags_match_reference():
     from nucleoatac_b200.cli import build_parser
     a = build_parser().parse_args("occ --bed b --bam m --out o".split())
     assert (a.upper, a.flank, a.min_occ, a.nuc_sep, a.confidence_interval, a.step, a.pwm, a.cores) == (251, 60, 0.1, 120, 0.9, 5, "Human", 1)
+    a = build_parser().parse_args("nfr --bed b --occ_track o.occ.bedgraph.gz --calls c.bed.gz --bam m".split())
+    assert (a.max_occ, a.max_occ_upper, a.pwm, a.ins_track, a.fasta, a.out) == (0.1, 0.25, "Human", None, None, None)
     a = build_parser().parse_args("nuc --bed b --bam m --out o --vmat v --not_atac --write_all".split())
     assert (a.min_z, a.min_lr, a.nuc_sep, a.redundant_sep, a.sd, a.atac, a.write_all) == (3, 0, 120, 25, 10, False, True)
 

@@ -221,3 +221,27 @@ def test_golden_nuc(example, golden):
         gold_vals = golden[name + "_vals"][:, :9]  # column 13 (fuzz) is the host L-BFGS-B fit, not on the device path
         ok, worst = track_close(gold_vals, np.array([m[2:] for m in mine]), slack=6.0)
         assert ok, (name, worst)
+
+
+def test_golden_nfr():
+    """`nucleoatac nfr` as `nucleoatac run` wires it (cli.py:47-49; --max_occ 0.1, --max_occ_upper 0.25 of cli.py:167-170):
+    the oracle reproduces example_results/example.nfrpos.bed.gz row for row as text and example.ins.bedgraph.gz exactly."""
+    import os
+    from oracle import refnfr
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nfr_golden.npz"))
+    names = [str(x) for x in z["chrom_names"]]
+    nucs = [str(x) for x in z["pwm_nucleotides"]]
+    text, n_chunks = "", len(z["chunk_start"])
+    for i in range(n_chunks):
+        s, e = int(z["chunk_start"][i]), int(z["chunk_end"][i])
+        a, b = z["frag_off"][i:i + 2]
+        sa, sb = z["seq_off"][i:i + 2]
+        ta, tb = z["track_off"][i:i + 2]
+        na, nb = z["nuc_off"][i:i + 2]
+        lb = ra.log_bias_track(bytes(z["seq"][sa:sb]).decode(), z["pwm"], nucs)
+        assert len(lb) == e - s
+        recs, ins = refnfr.process_nfr_chunk(z["frag_pos"][a:b], z["frag_tlen"][a:b], s, e, z["nuc_pos"][na:nb], z["occ"][ta:tb],
+                                             z["occ_upper"][ta:tb], lb, max_occ=0.1, max_occ_upper=0.25)
+        assert np.array_equal(ins, z["gold_ins"][ta:tb])  # integer counts: bit-exact
+        text += "".join(refnfr.nfr_bed(names[int(z["chunk_chrom"][i])], r) + "\n" for r in recs)
+    assert text == str(z["gold_nfr_text"]) and len(z["gold_nfr_left"]) == 14
