@@ -192,6 +192,21 @@ int nb200_profile_get(nb200_ctx *ctx, int i, const char **name, int64_t *launche
 /* write `bytes` of device memory to evict L2 between timed iterations */
 int nb200_flush_l2(nb200_ctx *ctx, nb200_dbatch *b);
 
+/* ---- pyatac tools either side of the scoring path --------------------------- */
+/* _vplotHelper summed over sites, pyatac/make_vplot.py:22-43 (+ ChunkMat2D.get(flip=...), chunkmat2d.py:21-54):
+ * site s is centred at centers[s] (Chunk.center, chunk.py:41-54), flips[s] != 0 for strand "-", its reads (fetched for
+ * [centre - flank - 1 - upper, centre + 1 + flank + upper)) are pos/tlen[frag_off[s] .. frag_off[s+1]).
+ * out[upper-lower][2*flank+1] = sum over sites of the site matrix, each divided by its own sum when scale != 0
+ * (a site without fragments then makes every cell NaN, as 0/0 does in the reference).  Unscaled sums are exact. */
+int nb200_vplot(nb200_ctx *ctx, int32_t n_sites, const int32_t *centers, const int32_t *flips, const int64_t *frag_off,
+                const int32_t *pos, const int32_t *tlen, int32_t flank, int32_t lower, int32_t upper, int32_t atac,
+                int32_t scale, double *out);
+/* _covHelper without the final scaling, pyatac/get_cov.py:22-31 + CoverageTrack.calculateCoverage, tracks.py:209-222:
+ * out[x] = number of fragments with size in [lower, upper) whose centre lies within window_len/2 of start + x
+ * (an even window is made one longer, pyatac/utils.py:34-36); out has end-start values.  Exact. */
+int nb200_coverage(nb200_ctx *ctx, const int32_t *pos, const int32_t *tlen, int64_t n, int32_t start, int32_t end,
+                   int32_t lower, int32_t upper, int32_t window_len, int32_t atac, double *out);
+
 /* ---- host-side output formatting --------------------------------------------------------- */
 /* Track.write_track, pyatac/tracks.py:37-74: run-length bedgraph rows "chrom\tstart\tend\tvalue\n" with the
  * reference's number format (Python-2 str(float)).  Pure host code, no context.  Returns the bytes needed; the

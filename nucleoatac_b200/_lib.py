@@ -111,6 +111,8 @@ def load():
     _sig(lib, "nb200_reduce_peaks", I, vp, c_int32_p, c_double_p, i32, i32, c_int32_p)
     _sig(lib, "nb200_calculate_occupancy", I, vp, c_double_p, c_double_p, i32, c_double_p)
     _sig(lib, "nb200_multinomial_cov", I, vp, c_double_p, c_double_p, i64, i32, c_double_p)
+    _sig(lib, "nb200_vplot", I, vp, i32, c_int32_p, c_int32_p, c_int64_p, c_int32_p, c_int32_p, i32, i32, i32, i32, i32, c_double_p)
+    _sig(lib, "nb200_coverage", I, vp, c_int32_p, c_int32_p, i64, i32, i32, i32, i32, i32, i32, c_double_p)
     _sig(lib, "nb200_batch_upload", I, vp, C.POINTER(Batch), C.POINTER(vp))
     _sig(lib, "nb200_batch_free", I, vp, vp)
     _sig(lib, "nb200_batch_sync", I, vp, vp)
@@ -151,7 +153,7 @@ EXPORTS = [
     "nb200_batch_h2d_bytes", "nb200_occ_run", "nb200_nuc_run", "nb200_occ_download", "nb200_nuc_download",
     "nb200_occ_d2h_bytes", "nb200_nuc_d2h_bytes", "nb200_timer_start", "nb200_timer_stop", "nb200_timer_elapsed_ms",
     "nb200_profile_enable", "nb200_profile_reset", "nb200_profile_count", "nb200_profile_get", "nb200_flush_l2",
-    "nb200_format_track", "nb200_bgzip_tabix",
+    "nb200_format_track", "nb200_bgzip_tabix", "nb200_vplot", "nb200_coverage",
     "nb200_nccl_unique_id", "nb200_nccl_init", "nb200_allreduce_f64", "nb200_allreduce_i64", "nb200_nccl_finalize",
 ]
 

@@ -400,6 +400,24 @@ class Engine:
                                                  window_len, L.ptr(out, C.c_double)))
         return out
 
+    def coverage(self, pos, tlen, start, end, lower, upper, window_len, atac=True):
+        """pyatac/get_cov.py:22-31 without the final scaling, straight from the reads (no dense matrix)."""
+        pos, tlen = L.as_i32(pos), L.as_i32(tlen)
+        out = np.empty(end - start, dtype=np.float64)
+        self.check(self.lib.nb200_coverage(self.h, L.ptr(pos, C.c_int32), L.ptr(tlen, C.c_int32), len(pos), start, end, lower,
+                                           upper, int(window_len), int(bool(atac)), L.ptr(out, C.c_double)))
+        return out
+
+    def vplot(self, centers, flips, frag_off, pos, tlen, flank, lower, upper, atac=True, scale=False):
+        """Sum of the per-site V-plot matrices (pyatac/make_vplot.py:22-43): float64 [upper-lower, 2*flank+1]."""
+        centers, flips, frag_off = L.as_i32(centers), L.as_i32(flips), L.as_i64(frag_off)
+        pos, tlen = L.as_i32(pos), L.as_i32(tlen)
+        out = np.empty((upper - lower, 2 * flank + 1), dtype=np.float64)
+        self.check(self.lib.nb200_vplot(self.h, len(centers), L.ptr(centers, C.c_int32), L.ptr(flips, C.c_int32),
+                                        L.ptr(frag_off, C.c_int64), L.ptr(pos, C.c_int32), L.ptr(tlen, C.c_int32), int(flank),
+                                        int(lower), int(upper), int(bool(atac)), int(bool(scale)), L.ptr(out, C.c_double)))
+        return out
+
     def smooth(self, sig, w, mode="same", norm=True):
         sig, w = L.as_f64(sig), L.as_f64(w)
         n = len(sig) if mode == "same" else len(sig) - len(w) + 1
