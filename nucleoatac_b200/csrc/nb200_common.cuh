@@ -66,6 +66,7 @@ struct RunConst {
     //   pair[t][j][k] = (T[2j+1,k], T[2j+2,k]) (j = 0: (0, T[0,k] + T[2,k])), one[t][k] = T[1,k]; zero outside [lower, upper),
     //   J2 x W2 (both even) double2 per template
     DevBuf vp_pair, vp_one;
+    DevBuf vp_pair32, vp_one32;   // template V of the same layout in fp32 (k_cand_screen)
     int vp_J2 = 0, vp_W2 = 0;
     std::vector<double> h_vmat;
     // fragment sizes

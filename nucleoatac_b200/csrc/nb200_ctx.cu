@@ -125,7 +125,7 @@ int nb200_ctx_destroy(nb200_ctx *c)
     RunConst &r = c->rc;
     DevBuf *bufs[] = {&r.log_pwm, &r.nuc_code, &r.vmat,   &r.vmat_fp, &r.sizes,  &r.nuc_probs, &r.nfr_probs,
                       &r.alphas,  &r.jitter,   &r.occ_win, &r.nuc_win, &c->s0,     &c->s1,    &c->s2,       &c->s3,
-                      &c->s4,     &c->flush,   &r.vp_pair, &r.vp_one};
+                      &c->s4,     &c->flush,   &r.vp_pair, &r.vp_one, &r.vp_pair32, &r.vp_one32};
     for (auto b : bufs) b->release();
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -209,6 +209,12 @@ static int rebuild_scaled_vmat(nb200_ctx *ctx)
             }
         NB_CHECK(upload(ctx, r.vp_pair, pair.data(), pair.size() * sizeof(double)));
         NB_CHECK(upload(ctx, r.vp_one, one.data(), one.size() * sizeof(double)));
+        // template 0 (V) once more in fp32 for the candidate screen
+        std::vector<float> pair32((size_t)J2 * W2 * 2), one32((size_t)W2);
+        for (size_t i = 0; i < pair32.size(); i++) pair32[i] = (float)pair[i];
+        for (size_t i = 0; i < one32.size(); i++) one32[i] = (float)one[i];
+        NB_CHECK(upload(ctx, r.vp_pair32, pair32.data(), pair32.size() * sizeof(float)));
+        NB_CHECK(upload(ctx, r.vp_one32, one32.data(), one32.size() * sizeof(float)));
         r.vp_J2 = J2;
         r.vp_W2 = W2;
     }

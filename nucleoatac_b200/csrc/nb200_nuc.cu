@@ -152,8 +152,10 @@ __global__ void __launch_bounds__(NT_TILE) k_nuc_tracks(NucTrackArgs a)
     }
     __syncthreads();
     const int x = x0 + threadIdx.x;
-    if (x >= L) return;
-    const int lo = x - a.w + a.csc_pad, hi = x + a.w + 1 + a.csc_pad;
+    const bool valid = x < L;
+    if (!__any_sync(NB_FULL, valid)) return;
+    const int xc = valid ? x : L - 1;   // lanes past the chunk end shadow its last position and store nothing
+    const int lo = xc - a.w + a.csc_pad, hi = xc + a.w + 1 + a.csc_pad;
     const int e0 = cp[lo], e1 = cp[hi];
     int nlow = 0;
     if (a.col_low) {
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(NT_TILE) k_nuc_tracks(NucTrackArgs a)
     double bcov, bxv;
     if (a.use_bias) {
         // window [t, t + W) = head up to the next multiple of 8, whole groups of 8, tail
-        const int t = threadIdx.x, t1 = t + a.W;
+        const int t = xc - x0, t1 = t + a.W;
         const int g0 = (t + 7) >> 3, g1 = t1 >> 3;
         double s = 0.0;
         if (g0 <= g1) {
@@ -174,26 +176,42 @@ __global__ void __launch_bounds__(NT_TILE) k_nuc_tracks(NucTrackArgs a)
         } else
             for (int k = t; k < t1; k++) s += s_cb[k];
         bcov = s;
-        bxv = a.bx[oo + x];
+        bxv = a.bx[oo + xc];
     } else {
         bcov = a.bcov_nobias;
         bxv = a.bx_nobias;
     }
-    // sparse signal xcor: every fragment centred within +-w contributes one VMat entry
+    // sparse signal xcor: every fragment centred within +-w contributes one VMat entry.  The warp walks the union of its
+    // lanes' fragment ranges in lockstep: the entry is a broadcast read, its VMat row is read by the lanes whose window
+    // holds the fragment at consecutive (descending) columns -- one coalesced segment per fragment instead of one
+    // scattered gather per lane.  Every lane still adds its own fragments in ascending order (same sums as a per-lane loop).
     double sig = 0.0;
-    const int kb = a.w - (x + a.csc_pad);
-    if (staged) {
-        const int2 *se = s_ent - te0;
-        for (int e = e0; e < e1; e++) {
-            const int2 v = se[e];
-            if (v.y >= a.lv && v.y < a.uv) sig += __ldg(a.V + (size_t)(v.y - a.lv) * a.W + (v.x + kb));
-        }
-    } else {
-        for (int e = e0; e < e1; e++) {
-            const int2 v = en[e];
-            if (v.y >= a.lv && v.y < a.uv) sig += a.V[(size_t)(v.y - a.lv) * a.W + (v.x + kb)];
-        }
+    const int kb = a.w - (xc + a.csc_pad);
+    const int we0 = __shfl_sync(NB_FULL, e0, 0), we1 = __reduce_max_sync(NB_FULL, e1);
+    const int2 *se_g = en;
+    const int2 *se_s = s_ent - te0;
+    // Four fragments per trip so that four VMat reads are in flight per warp (the loop is latency bound otherwise).
+    // Branch-free: a lane that does not own the fragment reads V[0] and discards it.
+#define NT_WALK(SE)                                                                          \
+    for (int e = we0; e < we1; e += 4) {                                                     \
+        double t[4];                                                                         \
+        bool ok[4];                                                                          \
+        _Pragma("unroll") for (int u = 0; u < 4; u++) {                                      \
+            const int ee = e + u;                                                            \
+            const int2 v = SE[min(ee, we1 - 1)];                                             \
+            ok[u] = v.y >= a.lv && v.y < a.uv && ee >= e0 && ee < e1;                        \
+            const int off = ok[u] ? (v.y - a.lv) * a.W + (v.x + kb) : 0;                     \
+            t[u] = __ldg(a.V + off);                                                         \
+        }                                                                                    \
+        _Pragma("unroll") for (int u = 0; u < 4; u++) sig += ok[u] ? t[u] : 0.0;             \
     }
+    if (staged) {
+        NT_WALK(se_s)
+    } else {
+        NT_WALK(se_g)
+    }
+#undef NT_WALK
+    if (!valid) return;
     const double bg = bxv * nuc_cov / bcov;  // NucleosomeCalling.py:64
     a.nuc_cov[oo + x] = nuc_cov;
     a.nfr_cov[oo + x] = nfr_cov;
@@ -408,6 +426,180 @@ __device__ __forceinline__ void pair_window_sums(const double2 *__restrict__ T, 
             a1 = na1;
             b0 = nb0;
             b1 = nb1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Candidate screen.  A candidate survives NucleosomeCalling.py:302-310 only if its likelihood ratio exceeds min_lr, and
+// the reference keeps nothing of a candidate that does not (its LR is never written).  On real and synthetic data well
+// under 1 % of the candidates pass, yet every one of them needs the dense window sum S_VB = sum V*Bp (63 001 cells at
+// 251x251).  The screen evaluates S_VB in fp32 (same paired two-tap walk, half the shared-memory / L1 traffic per cell,
+// 8 candidates per template load), forms the likelihood ratio with it, and passes on to the exact fp64 kernel
+// (k_cand_stats) every candidate whose approximate LR is not below min_lr by more than a rigorous error margin:
+// |LR32 - LR| = n * |log(S32 / S_VB)| <= n * CS_EPS32, where n = fragments in the window and CS_EPS32 is ~8x the worst-case
+// rounding of the fp32 accumulation chains (<= ~190 FMAs of positive terms per thread, 1.2e-5).  Anything non-finite goes to
+// the exact kernel too.  Decisions, LR and z of every kept nucleosome therefore come from the fp64 path; a rejected
+// candidate's cand_lr holds the fp32-screen value (within n * CS_EPS32 of the exact one).
+#define CS_EPS32 1e-4
+#define CS_SCREEN_GROUP 8
+
+template <int NG>
+__device__ __forceinline__ void pair_window_sums_f32(const float2 *__restrict__ T, const float *__restrict__ t1, int J2, int W2,
+                                                     const float *s_E, int nEw2, int off0, float *acc)
+{
+    const int ncp = W2 >> 1, tpc = min(ncp, CS_THREADS), rows_par = CS_THREADS / tpc;
+    const int cp0 = threadIdx.x % tpc, rr = threadIdx.x / tpc;
+    const int jseg = ((J2 / 2 + rows_par - 1) / rows_par) * 2;
+    const int j0 = rr * jseg, j1 = min(J2, j0 + jseg);
+    if (rr >= rows_par || j0 >= j1) return;
+    for (int cp = cp0; cp < ncp; cp += tpc) {
+        const int k = 2 * cp;
+        const float *Ec = s_E + off0 + k;
+        float2 L[NG], Rt[NG];   // carries: (E[c-j], E[c-j+1]) and (E[c+j], E[c+j+1])
+#pragma unroll
+        for (int cg = 0; cg < NG; cg++) {
+            L[cg] = *reinterpret_cast<const float2 *>(Ec + cg * nEw2 - j0);
+            Rt[cg] = *reinterpret_cast<const float2 *>(Ec + cg * nEw2 + j0);
+        }
+        if (j0 == 0) {  // insert size 1: a single tap
+            const float2 c1 = *reinterpret_cast<const float2 *>(t1 + k);
+#pragma unroll
+            for (int cg = 0; cg < NG; cg++) acc[cg] = fmaf(c1.x, L[cg].x, fmaf(c1.y, L[cg].y, acc[cg]));
+        }
+        const float2 *Tp = T + (size_t)j0 * W2 + k;
+        float2 a0 = __ldg(Tp), a1 = __ldg(Tp + 1), b0 = __ldg(Tp + W2), b1 = __ldg(Tp + W2 + 1);
+#pragma unroll 2
+        for (int j = j0; j < j1; j += 2) {
+            Tp += 2 * (size_t)W2;
+            float2 na0 = a0, na1 = a1, nb0 = b0, nb1 = b1;
+            if (j + 2 < j1) {
+                na0 = __ldg(Tp);
+                na1 = __ldg(Tp + 1);
+                nb0 = __ldg(Tp + W2);
+                nb1 = __ldg(Tp + W2 + 1);
+            }
+#pragma unroll
+            for (int cg = 0; cg < NG; cg++) {
+                const float2 Ln = *reinterpret_cast<const float2 *>(Ec + cg * nEw2 - j - 2);
+                const float2 Rn = *reinterpret_cast<const float2 *>(Ec + cg * nEw2 + j + 2);
+                const float2 Lc = L[cg], Rc = Rt[cg];
+                float s = acc[cg];
+                s = fmaf(Lc.x, fmaf(a0.x, Rc.x, a0.y * Rc.y), s);
+                s = fmaf(Lc.y, fmaf(a1.x, Rc.y, a1.y * Rn.x), s);
+                s = fmaf(Ln.y, fmaf(b0.x, Rc.y, b0.y * Rn.x), s);
+                s = fmaf(Lc.x, fmaf(b1.x, Rn.x, b1.y * Rn.y), s);
+                acc[cg] = s;
+                L[cg] = Ln;
+                Rt[cg] = Rn;
+            }
+            a0 = na0;
+            a1 = na1;
+            b0 = nb0;
+            b1 = nb1;
+        }
+    }
+}
+
+struct ScreenArgs {
+    CandArgs c;
+    const float2 *pair32;
+    const float *one32;
+    int2 *confirm;            // work list of the exact kernel
+    int32_t *confirm_count;
+};
+
+__global__ void __launch_bounds__(CS_THREADS, 2) k_cand_screen(ScreenArgs sa)
+{
+    constexpr int NG = CS_SCREEN_GROUP, NWARP = CS_THREADS / 32;
+    static_assert(NWARP % NG == 0, "warps must divide evenly over the candidates of a group");
+    const CandArgs &a = sa.c;
+    extern __shared__ __align__(16) float sm_sc[];
+    __shared__ float s_part[NG][NWARP];
+    const int off0 = a.J2 + 2, nEw = off0 + a.W2 + a.J2 + 4;   // same window layout as k_cand_stats
+    float *s_E = sm_sc;                      // [NG][nEw]
+    const int nwork = a.work_count[0];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int g0 = blockIdx.x * NG; g0 < nwork; g0 += gridDim.x * NG) {
+        const int ng = min(NG, nwork - g0);
+        if (a.lr_is_nan) {  // 0*log(0) cells make both likelihoods NaN in the reference: nothing passes
+            if (tid < ng) {
+                const int2 it = a.work[g0 + tid];
+                a.cand_lr[a.cand_off[it.x] + it.y] = nb_nan();
+            }
+            continue;
+        }
+        __syncthreads();
+        for (int cg = 0; cg < NG; cg++) {
+            if (cg < ng && a.use_bias) {
+                const int2 it = a.work[g0 + cg];
+                const int c = it.x;
+                const int P = a.cand_pos[a.cand_off[c] + it.y];
+                const int64_t e_lo = a.bias_off[c], e_hi = a.bias_off[c + 1];
+                const int64_t eb = e_lo - (int64_t)(a.seq_start[c] + a.pwm_up) + (P - a.w - off0);
+                for (int i = tid; i < nEw; i += CS_THREADS) {
+                    const int64_t idx = eb + i;
+                    s_E[cg * nEw + i] = (idx >= e_lo && idx < e_hi) ? (float)a.E[idx] : 0.0f;
+                }
+            } else
+                for (int i = tid; i < nEw; i += CS_THREADS) s_E[cg * nEw + i] = a.use_bias ? 0.0f : 1.0f;
+        }
+        __syncthreads();
+        float sVB[NG];
+#pragma unroll
+        for (int cg = 0; cg < NG; cg++) sVB[cg] = 0.0f;
+        pair_window_sums_f32<NG>(sa.pair32, sa.one32, a.J2, a.W2, s_E, nEw, off0, sVB);
+#pragma unroll
+        for (int cg = 0; cg < NG; cg++) {
+            float v = sVB[cg];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(NB_FULL, v, o);
+            if (lane == 0) s_part[cg][wid] = v;
+        }
+        __syncthreads();
+        // sparse likelihoods (NucleosomeCalling.py:110-122) with the fp32 normaliser; fp64 bias cells straight from the track
+        {
+            constexpr int WPC = NWARP / NG;
+            const int cg = wid % NG, sub = wid / NG;
+            if (cg < ng) {
+                double cVB = 0.0;
+#pragma unroll
+                for (int w2 = 0; w2 < NWARP; w2++) cVB += (double)s_part[cg][w2];
+                const int2 it = a.work[g0 + cg];
+                const int c = it.x;
+                const int64_t ci = a.cand_off[c] + it.y;
+                const double cB = a.cand_bcov[ci];
+                const int P = a.cand_pos[ci], x = P - a.start[c];
+                const int32_t *cp = a.col_ptr + a.col_off[c];
+                const int2 *en = a.ent + a.frag_off[c];
+                const int e0 = cp[x - a.w + a.csc_pad], e1 = cp[x + a.w + 1 + a.csc_pad];
+                const int kb = a.w - (x + a.csc_pad);
+                const double *Eg = a.use_bias ? a.E + (a.bias_off[c] - (int64_t)(a.seq_start[c] + a.pwm_up) + (P - a.w)) : nullptr;   // E[P - w + k] = Eg[k]
+                double nl = 0.0, ul = 0.0;
+                for (int e = e0 + sub * 32 + lane; e < e1; e += 32 * WPC) {
+                    const int2 v = en[e];
+                    const int r = v.y - a.lv;
+                    if (r >= 0 && r < a.R) {
+                        const int k = v.x + kb;
+                        const double bp = a.use_bias ? bias_cell(Eg + k, v.y) : 1.0;
+                        nl += log(__dmul_rn(a.V[(size_t)r * a.W + k], bp) / cVB);
+                        ul += log(__dmul_rn(bp, a.f[a.lv + r]) / cB);
+                    }
+                }
+                nl = warp_sum(nl);
+                ul = warp_sum(ul);
+                static_assert(WPC == 1, "one warp per candidate: the warp's sums are the candidate's");
+                if (lane == 0) {
+                    const double lr = nl - ul;
+                    const double margin = (double)(e1 - e0) * CS_EPS32 + 1e-6;
+                    const bool sane = cVB > 1e-30 && cVB < 1e30;
+                    if (!sane || !(lr <= a.min_lr - margin)) {
+                        const int slot = atomicAdd(sa.confirm_count, 1);
+                        sa.confirm[slot] = it;
+                    } else
+                        a.cand_lr[ci] = lr;
+                }
+            }
         }
     }
 }
@@ -638,7 +830,7 @@ int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
     NB_CUDA(ctx, b->n_cand_flag.reserve(sizeof(int32_t) * nc));
     DevBuf *cd[] = {&b->n_cand_z, &b->n_cand_lr, &b->n_cand_norm, &b->n_cand_sig, &b->n_cand_cov, &b->n_cand_nfr, &b->n_cand_smooth, &b->n_cand_bcov};
     for (auto t : cd) NB_CUDA(ctx, t->reserve(sizeof(double) * nc));
-    NB_CUDA(ctx, b->n_work.reserve(sizeof(int2) * nc));
+    NB_CUDA(ctx, b->n_work.reserve(sizeof(int2) * 2 * nc));   // [0, nc): candidates to screen, [nc, 2 nc): those the exact kernel confirms
     NB_CUDA(ctx, b->n_work_count.reserve(sizeof(int32_t) * 4));
     NB_CUDA(ctx, cudaMemsetAsync(b->n_work_count.p, 0, sizeof(int32_t) * 4, b->stream));
 
@@ -800,6 +992,25 @@ int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
         a.lr_is_nan = (r.v_has_zero || r.f_has_zero) ? 1 : 0;
         a.min_lr = p.min_lr;
         a.min_z = p.min_z;
+        static const int cs_screen = getenv("NB200_CS_SCREEN") ? atoi(getenv("NB200_CS_SCREEN")) : 1;
+        if (cs_screen) {
+            ScreenArgs sa;
+            sa.c = a;
+            sa.pair32 = r.vp_pair32.as<float2>();
+            sa.one32 = r.vp_one32.as<float>();
+            sa.confirm = b->n_work.as<int2>() + b->h_ncand_off.back();
+            sa.confirm_count = b->n_work_count.as<int32_t>() + 1;
+            const size_t smem32 = sizeof(float) * (CS_SCREEN_GROUP * ((size_t)r.vp_W2 + 2 * r.vp_J2 + 6) + 8);
+            if (smem32 > 48 * 1024)
+                NB_CUDA(ctx, cudaFuncSetAttribute(k_cand_screen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
+            {
+                ProfScope ps(ctx, b->stream, "k_cand_screen");
+                k_cand_screen<<<ctx->sm_count * 4, CS_THREADS, smem32, b->stream>>>(sa);
+                NB_LAUNCH_CHECK(ctx);
+            }
+            a.work = sa.confirm;
+            a.work_count = sa.confirm_count;
+        }
         ProfScope ps(ctx, b->stream, "k_cand_stats");
         static const int cs_group = getenv("NB200_CS_GROUP") ? atoi(getenv("NB200_CS_GROUP")) : CS_GROUP_DEFAULT;
         const int G = cs_group <= 4 ? 4 : 8;
