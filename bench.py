@@ -229,7 +229,7 @@ def run_reference(args, rank, world):
                                   sample="%d steps x %d chunks through oracle/ (CPU restatement of the reference: fft correlate, "
                                          "O(n^2) calculateCov), Pool(%d) of %d visible cores" % (args.steps, per_step, nworkers, cores)),
                 e2e=dict(value=val, unit="bp/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -414,7 +414,7 @@ def run_ours(args, rank, world, local_rank):
                              d2h="3 smoothed occupancy tracks + peaks + nuc_dist, nucleoatac_signal + smooth + call table (f64)"),
                     gpu_launches=launches, clocks=clk, wall_s_device_pass=t_wall, gen_s=t_gen,
                     checks=dict(nuc_dist_sum=float(nd.sum()), fragment_size_count=int(fs.sum())))
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     for h in hs:
         if h is not None:
             eng.free_batch(h)
@@ -423,7 +423,23 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(text):
+    """The one JSON line goes to the process's original stdout; everything libraries write to fd 1 meanwhile (NCCL prints
+    its version banner there) is sent to stderr so that stdout carries exactly that line."""
+    if _JSON_FD is None:
+        print(text, flush=True)
+    else:
+        os.write(_JSON_FD, (text + "\n").encode())
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=25)

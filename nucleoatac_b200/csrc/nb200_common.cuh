@@ -60,6 +60,7 @@ struct RunConst {
     int v_rows = 0, v_cols = 0, v_lower = 0, v_upper = 0, v_w = 0;
     int v_wpad = 0;   // v_cols rounded up to a multiple of 16 (zero padded rows of vmat_fp)
     bool v_has_zero = false;
+    bool v_nonneg = false;    // every VMat entry is >= 0 and finite (precondition of the candidates' likelihood-ratio bound)
     DevBuf vmat;      // f64 [R][W]
     DevBuf vmat_fp;   // f64 [R][Wpad]  f_i * V, zero padded (operand of the dense background xcor)
     // "paired" templates of the candidate statistics (k_cand_stats): for T in {V, f*V, f*V^2}
@@ -74,6 +75,7 @@ struct RunConst {
     int sizes_upper = 0;
     bool f_has_zero = false;  // a zero frequency inside [v_lower, v_upper)
     double f_sum_v = 0.0;     // sum of f over [v_lower, v_upper)
+    double f_max_v = 0.0;     // max of f over [v_lower, v_upper); < 0 when some f is negative / not finite
     DevBuf sizes;     // f64 [upper]
     std::vector<double> h_sizes;
     // occupancy model

@@ -180,10 +180,13 @@ static int rebuild_scaled_vmat(nb200_ctx *ctx)
     std::vector<double> vf((size_t)r.v_rows * r.v_wpad, 0.0);
     r.f_has_zero = false;
     r.f_sum_v = 0.0;
+    r.f_max_v = 0.0;
     for (int i = 0; i < r.v_rows; i++) {
         double f = r.h_sizes[r.v_lower + i];
         if (!(f != 0.0)) r.f_has_zero = true;
         r.f_sum_v += f;
+        if (!(f >= 0.0 && f < 1e300)) r.f_max_v = -1.0;
+        else if (r.f_max_v >= 0.0 && f > r.f_max_v) r.f_max_v = f;
         for (int k = 0; k < r.v_cols; k++) vf[(size_t)i * r.v_wpad + k] = f * r.h_vmat[(size_t)i * r.v_cols + k];
     }
     NB_CHECK(upload(ctx, r.vmat_fp, vf.data(), vf.size() * sizeof(double)));
@@ -257,8 +260,11 @@ int nb200_set_vmat(nb200_ctx *ctx, const double *mat, int nrow, int ncol, int lo
     size_t n = (size_t)nrow * ncol;
     r.h_vmat.assign(mat, mat + n);
     r.v_has_zero = false;
-    for (size_t i = 0; i < n; i++)
+    r.v_nonneg = true;
+    for (size_t i = 0; i < n; i++) {
         if (mat[i] == 0.0) r.v_has_zero = true;
+        if (!(mat[i] >= 0.0 && mat[i] < 1e300)) r.v_nonneg = false;
+    }
     NB_CHECK(upload(ctx, r.vmat, mat, n * sizeof(double)));
     r.v_rows = nrow;
     r.v_cols = ncol;

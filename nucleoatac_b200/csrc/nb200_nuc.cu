@@ -120,7 +120,8 @@ struct NucTrackArgs {
 };
 
 #define NT_TILE 256
-#define NT_FRAG_CAP 2048   // fragments of a tile staged in shared memory (denser tiles read them from global memory)
+#define NT_FRAG_CAP 512    // fragments of a tile staged in shared memory (denser tiles read them from global memory); kept small:
+                           // the VMat gathers are L2 -> L1 traffic and every KB of shared memory is a KB less of L1
 __global__ void __launch_bounds__(NT_TILE) k_nuc_tracks(NucTrackArgs a)
 {
     extern __shared__ __align__(16) double sm_nt[];  // cB tile [NT_TILE + 2w (+8)], sums of 8 [..], fragment tile
@@ -188,29 +189,12 @@ __global__ void __launch_bounds__(NT_TILE) k_nuc_tracks(NucTrackArgs a)
     double sig = 0.0;
     const int kb = a.w - (xc + a.csc_pad);
     const int we0 = __shfl_sync(NB_FULL, e0, 0), we1 = __reduce_max_sync(NB_FULL, e1);
-    const int2 *se_g = en;
-    const int2 *se_s = s_ent - te0;
-    // Four fragments per trip so that four VMat reads are in flight per warp (the loop is latency bound otherwise).
-    // Branch-free: a lane that does not own the fragment reads V[0] and discards it.
-#define NT_WALK(SE)                                                                          \
-    for (int e = we0; e < we1; e += 4) {                                                     \
-        double t[4];                                                                         \
-        bool ok[4];                                                                          \
-        _Pragma("unroll") for (int u = 0; u < 4; u++) {                                      \
-            const int ee = e + u;                                                            \
-            const int2 v = SE[min(ee, we1 - 1)];                                             \
-            ok[u] = v.y >= a.lv && v.y < a.uv && ee >= e0 && ee < e1;                        \
-            const int off = ok[u] ? (v.y - a.lv) * a.W + (v.x + kb) : 0;                     \
-            t[u] = __ldg(a.V + off);                                                         \
-        }                                                                                    \
-        _Pragma("unroll") for (int u = 0; u < 4; u++) sig += ok[u] ? t[u] : 0.0;             \
+    const int2 *se = staged ? (s_ent - te0) : en;
+    for (int e = we0; e < we1; e++) {
+        const int2 v = se[e];
+        if (v.y < a.lv || v.y >= a.uv) continue;   // warp-uniform
+        if (e >= e0 && e < e1) sig += __ldg(a.V + (size_t)(v.y - a.lv) * a.W + (v.x + kb));
     }
-    if (staged) {
-        NT_WALK(se_s)
-    } else {
-        NT_WALK(se_g)
-    }
-#undef NT_WALK
     if (!valid) return;
     const double bg = bxv * nuc_cov / bcov;  // NucleosomeCalling.py:64
     a.nuc_cov[oo + x] = nuc_cov;
@@ -501,6 +485,77 @@ __device__ __forceinline__ void pair_window_sums_f32(const float2 *__restrict__ 
     }
 }
 
+// First stage of the cascade: an upper bound of the likelihood ratio from quantities the pass already has.  With V >= 0
+// and f >= 0,  bx = sum f_i V Bp <= f_max * sum V Bp = f_max * S_VB  (bx = the background cross-correlation at the
+// candidate, NucleosomeCalling.py:60-63), so log S_VB >= log(bx / f_max) and
+//     LR <= sum_frag [ log(V bp f_max / bx) - log(bp f / S_B) ].
+// bx may come from the tensor-core path (relative error ~1e-6, all terms positive): it is taken 1 % smaller.  On the
+// synthetic workload and the example data the bound alone rejects ~97 % of the candidates with a warp-sized sparse sum;
+// the rest go to the fp32 screen.  A candidate rejected here keeps the bound in cand_lr (the reference drops its LR).
+struct BoundArgs {
+    CandArgs c;
+    const double *bx;          // raw background xcor track (packed per position), or nullptr without bias
+    double bx_nobias, f_max;
+    int bound_ok;              // V >= 0, f >= 0, f_max > 0
+    int2 *next;                // work list of the screen
+    int32_t *next_count;
+};
+
+__global__ void __launch_bounds__(256) k_cand_bound(BoundArgs ba)
+{
+    const CandArgs &a = ba.c;
+    const int nwork = a.work_count[0];
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int wk = blockIdx.x * wpb + (threadIdx.x >> 5); wk < nwork; wk += gridDim.x * wpb) {
+        const int2 it = a.work[wk];
+        const int c = it.x;
+        const int64_t ci = a.cand_off[c] + it.y;
+        if (a.lr_is_nan) {  // 0*log(0) cells make both likelihoods NaN in the reference: nothing passes
+            if (lane == 0) a.cand_lr[ci] = nb_nan();
+            continue;
+        }
+        bool pass_on = !ba.bound_ok;
+        double lr_ub = 0.0;
+        int nfr = 0;
+        if (ba.bound_ok) {
+            const int P = a.cand_pos[ci], x = P - a.start[c];
+            const double bxv = a.use_bias ? ba.bx[a.out_off[c] + x] : ba.bx_nobias;
+            const double cB = a.cand_bcov[ci];
+            const int32_t *cp = a.col_ptr + a.col_off[c];
+            const int2 *en = a.ent + a.frag_off[c];
+            const int e0 = cp[x - a.w + a.csc_pad], e1 = cp[x + a.w + 1 + a.csc_pad];
+            const int kb = a.w - (x + a.csc_pad);
+            const double *Eg = a.use_bias ? a.E + (a.bias_off[c] - (int64_t)(a.seq_start[c] + a.pwm_up) + (P - a.w)) : nullptr;
+            const double c1 = ba.f_max / (0.99 * bxv);
+            double nl = 0.0, ul = 0.0;
+            for (int e = e0 + lane; e < e1; e += 32) {
+                const int2 v = en[e];
+                const int r = v.y - a.lv;
+                if (r >= 0 && r < a.R) {
+                    const int k = v.x + kb;
+                    const double bp = a.use_bias ? bias_cell(Eg + k, v.y) : 1.0;
+                    nl += log(a.V[(size_t)r * a.W + k] * bp * c1);
+                    ul += log(__dmul_rn(bp, a.f[a.lv + r]) / cB);
+                }
+            }
+            nl = warp_sum(nl);
+            ul = warp_sum(ul);
+            lr_ub = nl - ul;
+            nfr = e1 - e0;
+            const double margin = (double)nfr * CS_EPS32 + 1e-6;
+            pass_on = !(bxv > 1e-300 && bxv < 1e300) || !(lr_ub <= a.min_lr - margin);
+        }
+        if (lane == 0) {
+            if (pass_on) {
+                const int slot = atomicAdd(ba.next_count, 1);
+                ba.next[slot] = it;
+            } else
+                a.cand_lr[ci] = lr_ub;
+        }
+    }
+}
+
 struct ScreenArgs {
     CandArgs c;
     const float2 *pair32;
@@ -785,6 +840,7 @@ int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
     if (!ctx->nuc_configured) return nb200_fail(ctx, NB200_ERR_STATE, "nb200_nuc_configure has not been called");
     RunConst &r = ctx->rc;
     const nb200_nuc_params &p = ctx->nuc;
+    double bx_nobias = 0.0;   // the background xcor without --fasta (a constant), set where the tracks are launched
     if (!r.have_vmat) return nb200_fail(ctx, NB200_ERR_STATE, "nb200_set_vmat has not been called");
     if (!r.have_sizes || r.sizes_upper < r.v_upper)
         return nb200_fail(ctx, NB200_ERR_STATE, "nb200_set_fragment_sizes missing or shorter than the VMat's upper size");
@@ -830,7 +886,7 @@ int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
     NB_CUDA(ctx, b->n_cand_flag.reserve(sizeof(int32_t) * nc));
     DevBuf *cd[] = {&b->n_cand_z, &b->n_cand_lr, &b->n_cand_norm, &b->n_cand_sig, &b->n_cand_cov, &b->n_cand_nfr, &b->n_cand_smooth, &b->n_cand_bcov};
     for (auto t : cd) NB_CUDA(ctx, t->reserve(sizeof(double) * nc));
-    NB_CUDA(ctx, b->n_work.reserve(sizeof(int2) * 2 * nc));   // [0, nc): candidates to screen, [nc, 2 nc): those the exact kernel confirms
+    NB_CUDA(ctx, b->n_work.reserve(sizeof(int2) * 3 * nc));   // [0, nc): candidates with reads, [nc, 2 nc): past the bound, [2 nc, 3 nc): past the fp32 screen
     NB_CUDA(ctx, b->n_work_count.reserve(sizeof(int32_t) * 4));
     NB_CUDA(ctx, cudaMemsetAsync(b->n_work_count.p, 0, sizeof(int32_t) * 4, b->stream));
 
@@ -897,6 +953,7 @@ int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
             s += rs * r.h_sizes[lv + i];
         }
         a.bx_nobias = s;
+        bx_nobias = s;
         const size_t ncb = (NT_TILE + 2 * (size_t)w + 8) & ~(size_t)7;
         size_t smem = sizeof(double) * (ncb + ncb / 8 + NT_FRAG_CAP);
         if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_nuc_tracks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -992,14 +1049,33 @@ int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
         a.lr_is_nan = (r.v_has_zero || r.f_has_zero) ? 1 : 0;
         a.min_lr = p.min_lr;
         a.min_z = p.min_z;
-        static const int cs_screen = getenv("NB200_CS_SCREEN") ? atoi(getenv("NB200_CS_SCREEN")) : 1;
+        // cascade: cheap upper bound of LR -> fp32 screen -> exact fp64 statistics (NB200_CS_SCREEN=0: exact for all)
+        const int cs_screen = getenv("NB200_CS_SCREEN") ? atoi(getenv("NB200_CS_SCREEN")) : 1;
+        int cs_group_exact = 0;
         if (cs_screen) {
+            const int64_t ncap = b->h_ncand_off.back();
+            int32_t *counts = b->n_work_count.as<int32_t>();
+            BoundArgs ba;
+            ba.c = a;
+            ba.bx = p.use_bias ? b->n_bx.as<double>() : nullptr;
+            ba.bx_nobias = bx_nobias;
+            ba.f_max = r.f_max_v;
+            ba.bound_ok = (r.v_nonneg && r.f_max_v > 0.0 && !getenv("NB200_CS_NOBOUND")) ? 1 : 0;
+            ba.next = b->n_work.as<int2>() + ncap;
+            ba.next_count = counts + 1;
+            {
+                ProfScope ps(ctx, b->stream, "k_cand_bound");
+                k_cand_bound<<<ctx->sm_count * 8, 256, 0, b->stream>>>(ba);
+                NB_LAUNCH_CHECK(ctx);
+            }
             ScreenArgs sa;
             sa.c = a;
+            sa.c.work = ba.next;
+            sa.c.work_count = ba.next_count;
             sa.pair32 = r.vp_pair32.as<float2>();
             sa.one32 = r.vp_one32.as<float>();
-            sa.confirm = b->n_work.as<int2>() + b->h_ncand_off.back();
-            sa.confirm_count = b->n_work_count.as<int32_t>() + 1;
+            sa.confirm = b->n_work.as<int2>() + 2 * ncap;
+            sa.confirm_count = counts + 2;
             const size_t smem32 = sizeof(float) * (CS_SCREEN_GROUP * ((size_t)r.vp_W2 + 2 * r.vp_J2 + 6) + 8);
             if (smem32 > 48 * 1024)
                 NB_CUDA(ctx, cudaFuncSetAttribute(k_cand_screen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
@@ -1010,12 +1086,13 @@ int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
             }
             a.work = sa.confirm;
             a.work_count = sa.confirm_count;
+            cs_group_exact = 4;
         }
         ProfScope ps(ctx, b->stream, "k_cand_stats");
         static const int cs_group = getenv("NB200_CS_GROUP") ? atoi(getenv("NB200_CS_GROUP")) : CS_GROUP_DEFAULT;
-        const int G = cs_group <= 4 ? 4 : 8;
+        const int G = cs_group_exact ? cs_group_exact : (cs_group <= 4 ? 4 : 8);
         size_t smem = sizeof(double) * (G * ((size_t)r.vp_W2 + 2 * r.vp_J2 + 6) + r.v_rows);
-        auto kern = G == 4 ? k_cand_stats<4> : k_cand_stats<8>;
+        auto kern = G == 1 ? k_cand_stats<1> : (G == 4 ? k_cand_stats<4> : k_cand_stats<8>);
         if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<ctx->sm_count * 4, CS_THREADS, smem, b->stream>>>(a);
         NB_LAUNCH_CHECK(ctx);

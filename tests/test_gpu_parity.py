@@ -3,6 +3,8 @@
 Bars (BASELINE.json north_star): counts / coverage / peak and call positions bit-exact; float
 tracks and statistics within 1e-5 relative -- the fp64 device path is held to 1e-9 here.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -32,6 +34,22 @@ def close(a, b, rtol=RTOL, atol=0.0, what=""):
     if m.any():
         err = np.abs(a[m] - b[m]) - atol - rtol * np.abs(a[m])
         assert err.max() <= 0, (what, float(np.abs(a[m] - b[m]).max()), int(np.argmax(err)))
+
+
+def check_lr(rec, got, what=""):
+    """The likelihood ratio of a candidate against the oracle's.  A candidate with LR > min_lr (= 0 here) goes on to the
+    z-score and its LR is an output (nucpos column 8): fp64, tight.  The reference drops a candidate with LR <= min_lr
+    (NucleosomeCalling.py:305-306) and never reports its LR; the device rejects those through a cascade (k_cand_bound:
+    rigorous upper bound, k_cand_screen: fp32 within LR_SCREEN_EPS per fragment) and leaves the stage's value in cand_lr:
+    never above the threshold, never below the exact LR by more than the screen's margin.  NB200_CS_SCREEN=0 computes
+    every LR exactly (test_nuc_exact_lr_mode)."""
+    exact = os.environ.get("NB200_CS_SCREEN") == "0"
+    if np.isnan(rec["lr"]):
+        assert np.isnan(got), (what, got)
+    elif rec["lr"] > 0 or exact:
+        close(rec["lr"], got, 1e-8, atol=1e-9, what=what)
+    else:
+        assert got <= 0.0 and got >= rec["lr"] - (LR_SCREEN_EPS * rec["nuc_cov"] + 1e-6), (what, rec["lr"], got)
 
 
 def example_batch(example, idx):
@@ -128,10 +146,7 @@ def check_nuc_chunk(out, pb, j, r, start, rtol=RTOL):
         exp_flag = 0
         if rec["nuc_cov"] > 1:
             exp_flag |= 1
-            if rec["lr"] > 0:
-                close(rec["lr"], out["cand_lr"][co + q], 1e-8, atol=1e-9, what=(j, q, "lr"))
-            else:  # not an output of the reference (NucleosomeCalling.py:305-306 drops the candidate): fp32-screened, see k_cand_screen
-                close(rec["lr"], out["cand_lr"][co + q], 0.0, atol=LR_SCREEN_EPS * rec["nuc_cov"] + 1e-6, what=(j, q, "lr screened"))
+            check_lr(rec, out["cand_lr"][co + q], what=(j, q, "lr"))
             if rec["lr"] > 0:
                 exp_flag |= 2
                 close(rec["z"], out["cand_z"][co + q], 1e-8, what=(j, q, "z"))
@@ -159,6 +174,36 @@ def test_nuc_example(eng, example, use_bias):
         bt = oracle_bias(example, i, span) if use_bias else None
         r = refnuc.process_nuc_chunk(*example.reads(i), s, e, params, bias_track=bt, bias_track_start=span[0], fit=False,
                                      xcor_method="direct" if (e - s) < 1500 else "auto")
+        check_nuc_chunk(out, pb, j, r, s)
+
+
+@pytest.mark.parametrize("mode", ["exact", "no_bound"])
+def test_nuc_exact_lr_mode(eng, example, mode, monkeypatch):
+    """The candidate cascade switched off stage by stage: NB200_CS_SCREEN=0 scores every candidate with the fp64 kernel (every
+    LR tight against the oracle); NB200_CS_NOBOUND=1 sends every candidate through the fp32 screen.  Flags, z and the
+    kept nucleosomes must not depend on the stages."""
+    if mode == "exact":
+        monkeypatch.setenv("NB200_CS_SCREEN", "0")
+    else:
+        monkeypatch.setenv("NB200_CS_NOBOUND", "1")
+    params = refnuc.NucParams(example.vmat, example.fragmentsizes, sd=10)
+    eng.set_pwm(example.pwm, example.pwm_up, example.pwm_down, example.nucleotides)
+    eng.set_vmat(*example.vmat)
+    eng.set_fragment_sizes(example.fragmentsizes)
+    eng.configure_nuc(sd=10, use_bias=True, xcor_mode=1)
+    idx = list(range(0, example.n_chunks, 3))
+    pb = example_batch(example, idx)
+    count = lambda k: eng.profile_report().get(k, (0, 0.0))[0]
+    before = {k: count(k) for k in ("k_cand_bound", "k_cand_screen", "k_cand_stats")}
+    out = eng.process_nuc(pb)
+    launched = {k: count(k) - before[k] for k in before}
+    assert launched == (dict(k_cand_bound=0, k_cand_screen=0, k_cand_stats=1) if mode == "exact" else
+                        dict(k_cand_bound=1, k_cand_screen=1, k_cand_stats=1))
+    for j, i in enumerate(idx):
+        _, s, e = example.chunk(i)
+        _, _, span = refnuc.nuc_geometry(s, e, params)
+        r = refnuc.process_nuc_chunk(*example.reads(i), s, e, params, bias_track=oracle_bias(example, i, span),
+                                     bias_track_start=span[0], fit=False, xcor_method="direct" if (e - s) < 1500 else "auto")
         check_nuc_chunk(out, pb, j, r, s)
 
 
@@ -391,10 +436,7 @@ def test_nuc_tensor_core_path(eng, example, which):
         for q, p in enumerate(mine):
             rec = by_pos.get(p)
             if rec is not None and rec["nuc_cov"] > 1:
-                if rec["lr"] > 0:
-                    close(rec["lr"], out["cand_lr"][co + q], 1e-8, atol=1e-9)  # statistics of kept candidates stay fp64
-                else:
-                    close(rec["lr"], out["cand_lr"][co + q], 0.0, atol=LR_SCREEN_EPS * rec["nuc_cov"] + 1e-6)
+                check_lr(rec, out["cand_lr"][co + q])  # statistics of kept candidates stay fp64
                 if rec["lr"] > 0:
                     close(rec["z"], out["cand_z"][co + q], TC_RTOL, atol=TC_RTOL)
     print("tensor-core path worst error / signal scale: %.2e; candidate flips at near-ties: %s" % (worst, flips))
