@@ -248,7 +248,7 @@ __device__ __forceinline__ int block_compact_slot(int flag, int *base_sh, int *r
 // clip_neg: values < 0 are taken as 0 first (NucChunk.smoothSignal, NucleosomeCalling.py:278-280).
 // grid (tiles, chunks, tracks); block SM_TILE threads; dynamic smem (SM_TILE + 2*wlen) doubles.
 // ---------------------------------------------------------------------------------------------
-#define SM_TILE 256
+#define SM_TILE 512
 #define SM_XT 4
 #define SM_THREADS (SM_TILE / SM_XT)
 struct SmoothTracks {
@@ -260,10 +260,13 @@ struct SmoothTracks {
 // 16-byte load of x, one broadcast 16-byte load of the tap pair and 8 FMAs.  Tiles without NaN / zero padding take this
 // fast path (denominator = sum of the window, as np.convolve of the window with an all-ones indicator gives); the others
 // evaluate the NaN-aware form tap by tap.
+// The staged tile is stored with 16 bytes of padding after every 128 (SM_PHYS): a thread's pairs are 32 bytes apart, which
+// would put lanes i and i + 4 of a quarter warp on the same banks; with the padding the 16-byte loads are conflict free.
+#define SM_PHYS(j) ((j) + (((j) >> 4) << 1))
 static inline size_t smooth_same_smem(int wlen)   // taps (padded) + staged tile + NaN prefix counts
 {
-    const size_t T2 = (size_t)wlen + 4, nX = SM_TILE + T2 + 4;
-    return sizeof(double) * (T2 + nX) + sizeof(int) * (nX + 2) + 16;
+    const size_t T2 = (size_t)wlen + 4, nX = SM_TILE + T2 + 4, nXp = nX + 2 * (nX / 16 + 1);   // staged tile incl. row padding
+    return sizeof(double) * (T2 + nXp) + sizeof(int) * (nX + 2) + 16;
 }
 static __global__ void __launch_bounds__(SM_THREADS) k_smooth_same(SmoothTracks tr, const int64_t *__restrict__ out_off,
                                                                  const double *__restrict__ win, int wlen, int clip_neg)
@@ -276,7 +279,8 @@ static __global__ void __launch_bounds__(SM_THREADS) k_smooth_same(SmoothTracks 
     const int T2 = (h - dlo + 2) & ~1;                   //   T2 (even) taps from dlo on, zero padded
     const int nX = SM_TILE + T2 + 4;
     double *s_w = sm_s;                 // [T2] wd, zero padded
-    double *s_x = sm_s + T2;            // [nX] s_x[j] = x[x0 + dlo + j]
+    double *s_x = sm_s + T2;            // [nX, padded] s_x[SM_PHYS(j)] = x[x0 + dlo + j]
+    const int nXp = nX + 2 * (nX / 16 + 1);
     const int c = blockIdx.y;
     const int64_t o = out_off[c];
     const int L = (int)(out_off[c + 1] - o);
@@ -310,7 +314,7 @@ static __global__ void __launch_bounds__(SM_THREADS) k_smooth_same(SmoothTracks 
             if (idx >= x0 + h - wlen + 1 && idx <= n_end - 1 + h) slow = 1;  // a real tap of this tile is missing
             else v = 0.0;                                                    // only ever multiplied by padded (zero) taps
         }
-        s_x[j] = v;
+        s_x[SM_PHYS(j)] = v;
     }
     if (slow) s_slow = 1;
     __syncthreads();
@@ -318,12 +322,12 @@ static __global__ void __launch_bounds__(SM_THREADS) k_smooth_same(SmoothTracks 
     // s_cnt[j] = number of NaN among s_x[0 .. j)
     bool my_slow = false;
     if (s_slow) {
-        int *s_cnt = reinterpret_cast<int *>(s_x + nX);
+        int *s_cnt = reinterpret_cast<int *>(s_x + nXp);
         if (threadIdx.x < 32) {
             int run = 0;
             for (int j0 = 0; j0 < nX; j0 += 32) {
                 const int j = j0 + threadIdx.x;
-                const bool bad = j < nX && s_x[j] != s_x[j];
+                const bool bad = j < nX && s_x[SM_PHYS(j)] != s_x[SM_PHYS(j)];
                 const unsigned m = __ballot_sync(NB_FULL, bad);
                 if (j < nX) s_cnt[j] = run + __popc(m & ((1u << threadIdx.x) - 1u));
                 run += __popc(m);
@@ -337,13 +341,15 @@ static __global__ void __launch_bounds__(SM_THREADS) k_smooth_same(SmoothTracks 
     const int n0 = x0 + threadIdx.x * SM_XT;
     if (n0 >= L) return;
     if (!my_slow) {
-        const double2 *px = reinterpret_cast<const double2 *>(s_x + threadIdx.x * SM_XT);
+        const double2 *px = reinterpret_cast<const double2 *>(s_x);   // pair q of the tile sits at px[q + (q >> 3)]
         const double2 *pw = reinterpret_cast<const double2 *>(s_w);
+        const int q0 = threadIdx.x * (SM_XT / 2);
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        double2 A = px[0], B = px[1];
+        double2 A = px[q0 + (q0 >> 3)], B = px[q0 + 1 + ((q0 + 1) >> 3)];
 #pragma unroll 4
         for (int k2 = 0; k2 < T2 / 2; k2++) {
-            const double2 C = px[k2 + 2], w = pw[k2];
+            const int q = q0 + k2 + 2;
+            const double2 C = px[q + (q >> 3)], w = pw[k2];
             a0 = fma(w.x, A.x, fma(w.y, A.y, a0));
             a1 = fma(w.x, A.y, fma(w.y, B.x, a1));
             a2 = fma(w.x, B.x, fma(w.y, B.y, a2));
@@ -362,7 +368,7 @@ static __global__ void __launch_bounds__(SM_THREADS) k_smooth_same(SmoothTracks 
             if (n >= L) break;
             double num = 0.0, den = 0.0;
             for (int m = 0; m < wlen; m++) {
-                const double v = s_x[n + h - m - lo];
+                const double v = s_x[SM_PHYS(n + h - m - lo)];
                 if (v == v) {
                     num += win[m] * v;
                     den += win[m];
