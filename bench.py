@@ -34,7 +34,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "bp scored/sec (occ+nuc), synthetic 10 kb chunks, 251x251 VMat"
 R_V, W_V = 251, 251
-TC_DRAM_BYTES_PER_CHUNK = 35.40e6 / 400  # measured, see roofline.traffic_source
+TC_DRAM_BYTES_PER_CHUNK = 35.35e6 / 400  # measured, see roofline.traffic_source
 
 
 def load_peaks():
@@ -392,8 +392,8 @@ def run_ours(args, rank, world, local_rank):
         achieved = flop_per_launch / k_avg_s / 1e12 if k_avg_s > 0 else 0.0
         roofline = dict(bound="tensor", kernel=kname, achieved=achieved, peak=peaks["tf_sustained"], unit="TFLOP/s",
                         frac=achieved / peaks["tf_sustained"], traffic=TC_DRAM_BYTES_PER_CHUNK * B if kname == "k_nuc_bx_tc" else None,
-                        traffic_source="ncu --set full, dram__bytes_read+write of k_nuc_bx_tc: 35.40 MB per 400-chunk launch "
-                                       "(profiles/r1_final_ncu_full.txt), scaled to this launch's chunk count", peak_source=peaks["source"] + " bf16 sustained",
+                        traffic_source="ncu --set full, dram__bytes_read+write of k_nuc_bx_tc: 35.35 MB per 400-chunk launch "
+                                       "(profiles/r1_final2_ncu_full.txt), scaled to this launch's chunk count", peak_source=peaks["source"] + " bf16 sustained",
                         kernel_ms_per_launch=kms / max(kcount, 1), kernel_share_of_step=kms / total_ms if total_ms else None,
                         algorithmic_flop_per_bp=2.0 * R_V * W_V,
                         per_kernel_ms={k: round(v[1] / K, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])})
