@@ -244,6 +244,7 @@ int nb200_batch_upload(nb200_ctx *ctx, const nb200_batch *h, nb200_dbatch **io)
     b->bias_done = false;
     b->csc_pad = b->csc_upper = b->csc_atac = b->csc_lower_split = -1;
     b->occ_done = b->nuc_done = false;
+    b->occ_cols_gen = -1;
     b->h2d_bytes = 0;
     auto up = [&](DevBuf &d, const void *src, size_t bytes) -> int {
         NB_CUDA(ctx, d.reserve(bytes ? bytes : 1));

@@ -102,6 +102,7 @@ struct nb200_ctx {
     nb200_occ_params occ{};
     nb200_nuc_params nuc{};
     bool occ_configured = false, nuc_configured = false;
+    int occ_gen = 0;   // bumped whenever something the occupancy column sums depend on changes (model, parameters, PWM)
     // scratch for the primitive (single-call) paths
     DevBuf s0, s1, s2, s3, s4;
     // profiling
@@ -199,6 +200,7 @@ struct nb200_dbatch {
     DevBuf o_peak_off;          // int64 [n+1]
     std::vector<int64_t> h_opeak_off;
     bool occ_done = false;
+    int occ_cols_gen = -1;      // ctx->occ_gen the column sums o_cn / o_cf of this batch were computed for (-1: not computed)
     int occ_upper = 0;
     // nuc outputs (device)
     DevBuf n_signal, n_bg, n_norm, n_smooth, n_nuc_cov, n_nfr_cov, n_bx, n_bcov, n_cB, n_comb, n_cand_bcov;

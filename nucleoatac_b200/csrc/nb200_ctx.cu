@@ -246,6 +246,7 @@ int nb200_set_pwm(nb200_ctx *ctx, const double *log_pwm, int n_nuc, int up, int 
     r.pwm_width = width;
     r.n_nuc = n_nuc;
     r.have_pwm = true;
+    ctx->occ_gen++;
     return NB200_OK;
 }
 
@@ -311,6 +312,7 @@ int nb200_set_occ_model(nb200_ctx *ctx, const double *nuc_probs, const double *n
     r.n_alpha = n_alpha;
     r.cutoff = cutoff;
     r.have_occ_model = true;
+    ctx->occ_gen++;
     return NB200_OK;
 }
 
@@ -333,6 +335,7 @@ int nb200_occ_configure(nb200_ctx *ctx, const nb200_occ_params *p)
     NB_CHECK(upload(ctx, ctx->rc.occ_win, p->smooth_win, sizeof(double) * p->smooth_len));
     ctx->occ.smooth_win = nullptr;
     ctx->occ_configured = true;
+    ctx->occ_gen++;
     return NB200_OK;
 }
 

@@ -65,8 +65,9 @@ __device__ __forceinline__ double bias_cell(const double *Ec, int i)
 // Sizes 2j+1 and 2j+2 share their left tap, so a column costs sum_j E[c-j] (w[2j+1] E[c+j] + w[2j+2] E[c+j+1]);
 // size 0 has the taps of size 2, size 1 a single tap.  A thread owns two adjacent columns and walks j two steps at a
 // time: both tap windows slide as aligned pairs (one 16-byte shared load per side for 8 cells), the paired weights are
-// broadcast loads.  Block = PC_THREADS threads = 2 * PC_THREADS columns of chunk blockIdx.y; column 0 of a chunk is
-// genomic start - pad and lands at out_t[out_off[c] + 2 * pad * c].
+// broadcast loads.  Block = PC_THREADS threads = 2 * PC_THREADS columns of chunk blockIdx.y.  Every weight vector t has its
+// own column range [start - pad_t, end + pad_t), whose first column lands at out_t[out_off[c] + 2 * pad_t * c]; the tile
+// grid runs over the widest range, so one pass serves occupancy (pad = flank) and nucleosome calling (pad = w) together.
 #define PC_THREADS 128
 template <int NW>
 struct PairColsumArgs {
@@ -76,33 +77,41 @@ struct PairColsumArgs {
     const double *E;
     const double *wt[NW];
     double *out[NW];
-    int pwm_up, lo, hi, pad;
+    int pwm_up;
+    int lo[NW], hi[NW], pad[NW];   // per weight vector: its insert sizes [lo, hi) and the pad of its output columns
 };
 
 template <int NW>
 static __global__ void __launch_bounds__(PC_THREADS) k_pair_colsums(PairColsumArgs<NW> a)
 {
     extern __shared__ __align__(16) double sm_pc[];
-    const int J2 = (max(1, a.hi / 2) + 1) & ~1;
+    int hmax = a.hi[0], pmax = a.pad[0];
+#pragma unroll
+    for (int t = 1; t < NW; t++) {
+        hmax = max(hmax, a.hi[t]);
+        pmax = max(pmax, a.pad[t]);
+    }
+    const int J2 = (max(1, hmax / 2) + 1) & ~1;
     const int off0 = J2 + 2, nE = off0 + 2 * PC_THREADS + J2 + 4;
     double2 *s_wp = reinterpret_cast<double2 *>(sm_pc);            // [NW][J2] (w[2j+1], w[2j+2])
     double *s_E = sm_pc + 2 * (size_t)NW * J2;                     // element off0 + t is E at the tile's column t
     const int c = blockIdx.y;
     const int L = (int)(a.out_off[c + 1] - a.out_off[c]);
-    const int ncol = L + 2 * a.pad;
+    const int ncol = L + 2 * pmax;
     const int col0 = blockIdx.x * (2 * PC_THREADS);
     if (col0 >= ncol) return;
     double w1[NW];
 #pragma unroll
     for (int t = 0; t < NW; t++) {
         const double *w = a.wt[t];
-        auto W = [&](int i) { return (i >= a.lo && i < a.hi) ? w[i] : 0.0; };
+        const int lo = a.lo[t], hi = a.hi[t];
+        auto W = [&](int i) { return (i >= lo && i < hi) ? w[i] : 0.0; };
         for (int j = threadIdx.x; j < J2; j += PC_THREADS)
             s_wp[t * J2 + j] = make_double2(j == 0 ? 0.0 : W(2 * j + 1), W(2 * j + 2) + (j == 0 ? W(0) : 0.0));
         w1[t] = W(1);
     }
     const int64_t e_lo = a.bias_off[c], e_hi = a.bias_off[c + 1];
-    const int64_t eb = e_lo - (int64_t)(a.seq_start[c] + a.pwm_up) + (a.start[c] - a.pad + col0 - off0);
+    const int64_t eb = e_lo - (int64_t)(a.seq_start[c] + a.pwm_up) + (a.start[c] - pmax + col0 - off0);
     for (int i = threadIdx.x; i < nE; i += PC_THREADS) {   // the last elements of reach only meet zero weights and may lie off the track
         const int64_t idx = eb + i;
         s_E[i] = (idx >= e_lo && idx < e_hi) ? a.E[idx] : 0.0;
@@ -133,11 +142,12 @@ static __global__ void __launch_bounds__(PC_THREADS) k_pair_colsums(PairColsumAr
         Lc = Ln;
         Rc = Rn;
     }
-    const int64_t o = a.out_off[c] + 2 * (int64_t)a.pad * c + col;
 #pragma unroll
     for (int t = 0; t < NW; t++) {
-        a.out[t][o] = s0[t];
-        if (col + 1 < ncol) a.out[t][o + 1] = s1[t];
+        const int ct = col - (pmax - a.pad[t]), nt = L + 2 * a.pad[t];   // column within this weight's own range
+        const int64_t o = a.out_off[c] + 2 * (int64_t)a.pad[t] * c + ct;
+        if (ct >= 0 && ct < nt) a.out[t][o] = s0[t];
+        if (ct + 1 >= 0 && ct + 1 < nt) a.out[t][o + 1] = s1[t];
     }
 }
 

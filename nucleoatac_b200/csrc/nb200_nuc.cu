@@ -893,7 +893,46 @@ int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
     if (p.use_bias) {
         NB_CUDA(ctx, b->n_bx.reserve(sizeof(double) * tl));
         NB_CUDA(ctx, b->n_cB.reserve(sizeof(double) * (tl + 2 * (size_t)w * n)));
-        {
+        // One pass over the columns serves nucleosome calling (cB, weights f over [lv, uv), pad w) and, when the occupancy
+        // path is configured with bias too, its two column sums (cn / cf, weights pn / pf over [0, upper), pad flank): the
+        // tap walk and the E loads are shared, nb200_occ_run of this batch then skips its own pass.
+        const nb200_occ_params &po = ctx->occ;
+        const bool merge_occ = ctx->occ_configured && po.use_bias && r.have_occ_model && po.upper <= r.occ_upper &&
+                               b->occ_cols_gen != ctx->occ_gen && !getenv("NB200_NO_MERGED_COLSUMS");
+        if (merge_occ) {
+            const size_t ncs = tl + 2 * (size_t)po.flank * n;
+            NB_CUDA(ctx, b->o_cn.reserve(sizeof(double) * ncs));
+            NB_CUDA(ctx, b->o_cf.reserve(sizeof(double) * ncs));
+            PairColsumArgs<3> pa;
+            pa.start = b->d_start.as<int32_t>();
+            pa.out_off = b->d_out_off.as<int64_t>();
+            pa.bias_off = b->d_bias_off.as<int64_t>();
+            pa.seq_start = b->d_seq_start.as<int32_t>();
+            pa.E = b->d_E.as<double>();
+            pa.pwm_up = r.pwm_up;
+            pa.wt[0] = r.sizes.as<double>();
+            pa.out[0] = b->n_cB.as<double>();
+            pa.lo[0] = lv;
+            pa.hi[0] = uv;
+            pa.pad[0] = w;
+            pa.wt[1] = r.nuc_probs.as<double>();
+            pa.wt[2] = r.nfr_probs.as<double>();
+            pa.out[1] = b->o_cn.as<double>();
+            pa.out[2] = b->o_cf.as<double>();
+            for (int t = 1; t < 3; t++) {
+                pa.lo[t] = 0;
+                pa.hi[t] = po.upper;
+                pa.pad[t] = po.flank;
+            }
+            const int hmax = std::max(uv, (int)po.upper), pmax = std::max(w, (int)po.flank);
+            const size_t smem = pair_colsums_smem<3>(hmax);
+            if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_pair_colsums<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ProfScope ps(ctx, b->stream, "k_colsums_merged");
+            dim3 grid((unsigned)div_up64(b->max_len + 2 * pmax, 2 * PC_THREADS), n);
+            k_pair_colsums<3><<<grid, PC_THREADS, smem, b->stream>>>(pa);
+            NB_LAUNCH_CHECK(ctx);
+            b->occ_cols_gen = ctx->occ_gen;
+        } else {
             PairColsumArgs<1> pa;
             pa.start = b->d_start.as<int32_t>();
             pa.out_off = b->d_out_off.as<int64_t>();
@@ -903,9 +942,9 @@ int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
             pa.wt[0] = r.sizes.as<double>();
             pa.out[0] = b->n_cB.as<double>();
             pa.pwm_up = r.pwm_up;
-            pa.lo = lv;
-            pa.hi = uv;
-            pa.pad = w;
+            pa.lo[0] = lv;
+            pa.hi[0] = uv;
+            pa.pad[0] = w;
             const size_t smem = pair_colsums_smem<1>(uv);
             if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_pair_colsums<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ProfScope ps(ctx, b->stream, "k_nuc_colsums");

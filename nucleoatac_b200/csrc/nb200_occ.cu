@@ -480,7 +480,7 @@ int nb200_occ_run(nb200_ctx *ctx, nb200_dbatch *b)
     DevBuf *pk[] = {&b->o_peak_occ, &b->o_peak_lower, &b->o_peak_upper, &b->o_peak_reads};
     for (auto t : pk) NB_CUDA(ctx, t->reserve(sizeof(double) * np));
 
-    if (p.use_bias) {
+    if (p.use_bias && b->occ_cols_gen != ctx->occ_gen) {   // else: nb200_nuc_run of this batch already made them (one merged pass)
         const size_t ncs = tl + 2 * (size_t)p.flank * n;
         NB_CUDA(ctx, b->o_cn.reserve(sizeof(double) * ncs));
         NB_CUDA(ctx, b->o_cf.reserve(sizeof(double) * ncs));
@@ -495,15 +495,18 @@ int nb200_occ_run(nb200_ctx *ctx, nb200_dbatch *b)
         pa.out[0] = b->o_cn.as<double>();
         pa.out[1] = b->o_cf.as<double>();
         pa.pwm_up = r.pwm_up;
-        pa.lo = 0;
-        pa.hi = p.upper;
-        pa.pad = p.flank;
+        for (int t = 0; t < 2; t++) {
+            pa.lo[t] = 0;
+            pa.hi[t] = p.upper;
+            pa.pad[t] = p.flank;
+        }
         const size_t smem = pair_colsums_smem<2>(p.upper);
         if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_pair_colsums<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ProfScope ps(ctx, b->stream, "k_occ_colsums");
         dim3 grid((unsigned)div_up64(b->max_len + 2 * p.flank, 2 * PC_THREADS), n);
         k_pair_colsums<2><<<grid, PC_THREADS, smem, b->stream>>>(pa);
         NB_LAUNCH_CHECK(ctx);
+        b->occ_cols_gen = ctx->occ_gen;
     }
     {
         OccMleArgs a;

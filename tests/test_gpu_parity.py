@@ -106,6 +106,41 @@ def test_occ_example(eng, example, use_bias):
         check_occ_chunk(out, pb, j, r, 251)
 
 
+def test_merged_colsums_occ_after_nuc(eng, example):
+    """nb200_nuc_run computes the occupancy column sums in the same pass as its own when both paths are configured
+    (k_colsums_merged); nb200_occ_run of that batch then skips its pass.  Every occupancy output must be bit-identical to
+    the stand-alone occ pass, for both VMat geometries (pad w = 60 and w = 125 against flank = 60)."""
+    from nucleoatac_b200 import synth
+    params = refocc.OccParams(example.occ_fit[1], example.occ_fit[2], upper=251)
+    cp = params.occ_calc_params
+    eng.set_pwm(example.pwm, example.pwm_up, example.pwm_down, example.nucleotides)
+    eng.set_occ_model(cp.nuc_probs, cp.nfr_probs, cp.alphas, cp.cutoff)
+    eng.configure_occ(upper=251, use_bias=True)
+    pb = example_batch(example, list(range(0, example.n_chunks, 2)))
+    alone = eng.process_occ(pb)
+    wl = synth.Workload(251, 251)
+    count = lambda k: eng.profile_report().get(k, (0, 0.0))[0]
+    for vm, fs in ((example.vmat, example.fragmentsizes), ((wl.vmat, wl.v_lower, wl.v_upper), wl.fragmentsizes)):
+        eng.set_vmat(*vm)
+        eng.set_fragment_sizes(fs)
+        eng.configure_nuc(sd=10, use_bias=True, xcor_mode=1)
+        before = (count("k_colsums_merged"), count("k_occ_colsums"))
+        h = eng.upload(pb)
+        eng.nuc_run(h)
+        eng.occ_run(h)
+        out = eng.occ_alloc(pb)
+        eng.occ_download(h, out)
+        eng.sync(h)
+        eng.free_batch(h)
+        assert (count("k_colsums_merged") - before[0], count("k_occ_colsums") - before[1]) == (1, 0)
+        used = np.concatenate([np.arange(o, o + c) for o, c in zip(alone["peak_off"][:-1], alone["peak_count"])]).astype(np.int64)
+        for k in alone:
+            a, b = np.asarray(alone[k]), np.asarray(out[k])
+            if k.startswith("peak_") and k not in ("peak_count", "peak_off"):
+                a, b = a[used], b[used]   # the capacity slots past peak_count are never written
+            assert np.array_equal(a, b, equal_nan=a.dtype.kind == "f"), k
+
+
 def test_occ_golden_direct(eng, example, golden):
     """Device occ tracks straight against the reference's shipped example_results (12 printed digits)."""
     from tests.fixtures import track_close
