@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnucleo_b200.so")
+LIB_PATH = os.environ.get("NB200_LIB") or os.path.join(HERE, "libnucleo_b200.so")  # NB200_LIB: developer override (kernel variants)
 
 c_int32_p = C.POINTER(C.c_int32)
 c_int64_p = C.POINTER(C.c_int64)

@@ -68,7 +68,9 @@ __device__ __forceinline__ double bias_cell(const double *Ec, int i)
 // broadcast loads.  Block = PC_THREADS threads = 2 * PC_THREADS columns of chunk blockIdx.y.  Every weight vector t has its
 // own column range [start - pad_t, end + pad_t), whose first column lands at out_t[out_off[c] + 2 * pad_t * c]; the tile
 // grid runs over the widest range, so one pass serves occupancy (pad = flank) and nucleosome calling (pad = w) together.
+#ifndef PC_THREADS
 #define PC_THREADS 128
+#endif
 template <int NW>
 struct PairColsumArgs {
     const int32_t *start;
@@ -258,7 +260,9 @@ __device__ __forceinline__ int block_compact_slot(int flag, int *base_sh, int *r
 // clip_neg: values < 0 are taken as 0 first (NucChunk.smoothSignal, NucleosomeCalling.py:278-280).
 // grid (tiles, chunks, tracks); block SM_TILE threads; dynamic smem (SM_TILE + 2*wlen) doubles.
 // ---------------------------------------------------------------------------------------------
+#ifndef SM_TILE
 #define SM_TILE 512
+#endif
 #define SM_XT 4
 #define SM_THREADS (SM_TILE / SM_XT)
 struct SmoothTracks {

@@ -119,7 +119,9 @@ struct NucTrackArgs {
     double bcov_nobias, bx_nobias;
 };
 
+#ifndef NT_TILE
 #define NT_TILE 256
+#endif
 #define NT_FRAG_CAP 512    // fragments of a tile staged in shared memory (denser tiles read them from global memory); kept small:
                            // the VMat gathers are L2 -> L1 traffic and every KB of shared memory is a KB less of L1
 __global__ void __launch_bounds__(NT_TILE) k_nuc_tracks(NucTrackArgs a)
@@ -426,7 +428,9 @@ __device__ __forceinline__ void pair_window_sums(const double2 *__restrict__ T, 
 // the exact kernel too.  Decisions, LR and z of every kept nucleosome therefore come from the fp64 path; a rejected
 // candidate's cand_lr holds the fp32-screen value (within n * CS_EPS32 of the exact one).
 #define CS_EPS32 1e-4
+#ifndef CS_SCREEN_GROUP
 #define CS_SCREEN_GROUP 8
+#endif
 
 template <int NG>
 __device__ __forceinline__ void pair_window_sums_f32(const float2 *__restrict__ T, const float *__restrict__ t1, int J2, int W2,

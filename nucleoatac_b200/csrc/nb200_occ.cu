@@ -35,7 +35,9 @@ struct OccMleArgs {
 // Window sums of the per-column sums: SN[k] = sum of cn over the 2*flank+1 columns of window k (t = halfstep + k*step), SF
 // likewise from cf -- the bias model's normalisers of Occupancy.py:106-109.  Block = WS_WIN consecutive windows of a chunk,
 // their columns staged in shared memory; a lane's columns are `step` doubles apart (conflict free for odd steps).
+#ifndef WS_WIN
 #define WS_WIN 128
+#endif
 __global__ void __launch_bounds__(WS_WIN) k_occ_winsums(const int64_t *__restrict__ out_off, const double *__restrict__ cn,
                                                         const double *__restrict__ cf, int flank, int step, int halfstep,
                                                         double *__restrict__ wsn, double *__restrict__ wsf)
@@ -85,7 +87,9 @@ __global__ void __launch_bounds__(WS_WIN) k_occ_winsums(const int64_t *__restric
 // in alpha) and the running product renormalised every 32 factors: one log per alpha instead of one per (alpha, fragment).
 #define MLE_WARPS 4
 #define MLE_GROUPS 4
+#ifndef MLE_ITERS
 #define MLE_ITERS 8
+#endif
 template <int NQ, int LB>  // NQ alphas per lane: lane r of a group owns alphas r, r + 8, ...; LB resident blocks per SM
 __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle(OccMleArgs a)
 {

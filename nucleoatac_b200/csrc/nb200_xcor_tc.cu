@@ -42,7 +42,9 @@
 #define TC_XT 2                           // x-tiles of 128 outputs per work item (they share every G stage)
 #define TC_M 128
 #define TC_TX (TC_XT * TC_M)
+#ifndef TC_N
 #define TC_N 192                          // slab width (a taps): one accumulator of TC_N TMEM columns per x-tile
+#endif
 #define TC_MAX_STAGES 5
 #define TC_TMEM_COLS 512                  // allocation (power of two >= TC_XT * TC_N); one persistent CTA per SM
 #define TC_BLOCK_BYTES (TC_N * 16 * 2 * 2)      // one untrimmed K16 block of G: hi + lo images
