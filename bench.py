@@ -249,6 +249,9 @@ def run_ours(args, rank, world, local_rank):
     t_gen = time.perf_counter()
     batches = generate_batches(K + Wm, rank, world, B)
     t_gen = time.perf_counter() - t_gen
+    from nucleoatac_b200 import dist as nbdist
+    affinity0 = os.sched_getaffinity(0)
+    host = nbdist.bind_to_gpu_numa(local_rank)   # before the pinned buffers exist: they should sit on the GPU's socket
     # pinned staging of every step's inputs (H2D source) and two pinned result sets (D2H target)
     pinned = []
     for pb in batches:
@@ -393,10 +396,12 @@ def run_ours(args, rank, world, local_rank):
         roofline = dict(bound="tensor", kernel=kname, achieved=achieved, peak=peaks["tf_sustained"], unit="TFLOP/s",
                         frac=achieved / peaks["tf_sustained"], traffic=TC_DRAM_BYTES_PER_CHUNK * B if kname == "k_nuc_bx_tc" else None,
                         traffic_source="ncu --set full, dram__bytes_read+write of k_nuc_bx_tc: 35.35 MB per 400-chunk launch "
-                                       "(profiles/r1_final2_ncu_full.txt), scaled to this launch's chunk count", peak_source=peaks["source"] + " bf16 sustained",
+                                       "(profiles/r1_final3_ncu_full.txt), scaled to this launch's chunk count", peak_source=peaks["source"] + " bf16 sustained",
                         kernel_ms_per_launch=kms / max(kcount, 1), kernel_share_of_step=kms / total_ms if total_ms else None,
                         algorithmic_flop_per_bp=2.0 * R_V * W_V,
                         per_kernel_ms={k: round(v[1] / K, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])})
+        os.sched_setaffinity(0, affinity0)   # the CPU arm gets every core (and the default memory policy) the process started with
+        nbdist.reset_mempolicy()
         cpu = None if args.no_cpu_baseline else cpu_baseline_sample(list(range(0, max(4, (os.cpu_count() or 2) - 1))))
         value = bp_step * K * world / (total_ms * 1e-3)
         line = dict(metric=METRIC, value=value, unit="bp/s", n_gpus=world, steps=K, warmup=Wm, ms_per_step=total_ms / K,
@@ -412,7 +417,7 @@ def run_ours(args, rank, world, local_rank):
                              d2h_alone_ms_per_step=None if d2h_alone_s is None else d2h_alone_s * 1e3,
                              d2h_alone_gbs=None if d2h_alone_s is None else d2h_b / d2h_alone_s / 1e9,
                              d2h="3 smoothed occupancy tracks + peaks + nuc_dist, nucleoatac_signal + smooth + call table (f64)"),
-                    gpu_launches=launches, clocks=clk, wall_s_device_pass=t_wall, gen_s=t_gen,
+                    gpu_launches=launches, clocks=clk, host=host, wall_s_device_pass=t_wall, gen_s=t_gen,
                     checks=dict(nuc_dist_sum=float(nd.sum()), fragment_size_count=int(fs.sum())))
         emit(json.dumps(line))
     for h in hs:

@@ -85,3 +85,64 @@ class ShardWriter:
             fh.close()
             os.remove("%s.rank%d" % (path, r))
             os.remove("%s.rank%d.idx" % (path, r))
+
+
+def bind_to_gpu_numa(device=0):
+    """Pin this process (CPU affinity + preferred memory node) to the NUMA node the GPU hangs off, before any pinned host
+    buffer is allocated: on a two-socket host a D2H copy into memory of the other socket crosses the inter-socket link and
+    runs at roughly half the PCIe rate (32 vs 55 GB/s measured on the B200 boxes).  Best effort: returns a dict describing
+    what was done, never raises."""
+    info = dict(gpu_numa_node=None, cpus_bound=None, mempolicy=None)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        idx = device
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                idx = int(vis.split(",")[device])
+            except Exception:
+                idx = device
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:   # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as fh:
+            node = int(fh.read().strip())
+        info["gpu_numa_node"] = node
+        if node < 0:
+            return info
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                if "-" in part:
+                    a, b = part.split("-")
+                    cpus.update(range(int(a), int(b) + 1))
+                elif part:
+                    cpus.add(int(part))
+        mine = os.sched_getaffinity(0) & cpus
+        if mine:
+            os.sched_setaffinity(0, mine)
+            info["cpus_bound"] = len(mine)
+        try:   # set_mempolicy(MPOL_PREFERRED, {node}): pinned buffers land next to the GPU even if no local CPU is ours
+            import ctypes
+            libc = ctypes.CDLL(None, use_errno=True)
+            mask = (ctypes.c_ulong * 16)()
+            mask[node // 64] = 1 << (node % 64)
+            rc = libc.syscall(238, 1, ctypes.byref(mask), 16 * 64 + 1)   # x86-64: __NR_set_mempolicy = 238, MPOL_PREFERRED = 1
+            info["mempolicy"] = "preferred" if rc == 0 else "errno %d" % ctypes.get_errno()
+        except Exception as ex:
+            info["mempolicy"] = "failed: %s" % ex
+    except Exception as ex:
+        info["error"] = str(ex)[:200]
+    return info
+
+
+def reset_mempolicy():
+    """Back to the default memory policy (undoes the preference set by bind_to_gpu_numa)."""
+    try:
+        import ctypes
+        ctypes.CDLL(None, use_errno=True).syscall(238, 0, None, 0)
+    except Exception:
+        pass
