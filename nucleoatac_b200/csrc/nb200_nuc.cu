@@ -493,8 +493,9 @@ __device__ __forceinline__ void pair_window_sums_f32(const float2 *__restrict__ 
 // and f >= 0,  bx = sum f_i V Bp <= f_max * sum V Bp = f_max * S_VB  (bx = the background cross-correlation at the
 // candidate, NucleosomeCalling.py:60-63), so log S_VB >= log(bx / f_max) and
 //     LR <= sum_frag [ log(V bp f_max / bx) - log(bp f / S_B) ].
-// bx may come from the tensor-core path (relative error ~1e-6, all terms positive): it is taken 1 % smaller.  On the
-// synthetic workload and the example data the bound alone rejects ~97 % of the candidates with a warp-sized sparse sum;
+// bx may come from the tensor-core path (relative error ~1e-6 of the chunk's scale, all terms positive): it is taken at
+// half its value, which costs n*log 2 of slack and tolerates any plausible rounding of bx.  On the synthetic workload
+// and the example data the bound alone still rejects ~96 % of the candidates with a warp-sized sparse sum;
 // the rest go to the fp32 screen.  A candidate rejected here keeps the bound in cand_lr (the reference drops its LR).
 struct BoundArgs {
     CandArgs c;
@@ -531,7 +532,7 @@ __global__ void __launch_bounds__(256) k_cand_bound(BoundArgs ba)
             const int e0 = cp[x - a.w + a.csc_pad], e1 = cp[x + a.w + 1 + a.csc_pad];
             const int kb = a.w - (x + a.csc_pad);
             const double *Eg = a.use_bias ? a.E + (a.bias_off[c] - (int64_t)(a.seq_start[c] + a.pwm_up) + (P - a.w)) : nullptr;
-            const double c1 = ba.f_max / (0.99 * bxv);
+            const double c1 = ba.f_max / (0.5 * bxv);
             double nl = 0.0, ul = 0.0;
             for (int e = e0 + lane; e < e1; e += 32) {
                 const int2 v = en[e];
