@@ -171,6 +171,10 @@ typedef struct {
     const int64_t *cand_off; /* [n_chunks+1] capacities (>= len/redundant_sep + 2 suffices) */
     int32_t *cand_pos;       /* genomic position, ascending */
     int32_t *cand_flag;      /* bit0 nuc_cov>min_reads, bit1 lr>min_lr, bit2 z>=min_z (kept), bit3 nonredundant */
+    /* cand_lr / cand_z are the fp64 statistics of NucleosomeCalling.py:110-127 for every candidate with bit1 set (the
+     * only ones the reference reports).  For a candidate rejected on the likelihood ratio (bit0 set, bit1 clear) cand_lr
+     * holds the value of the stage that rejected it -- an upper bound of, or an fp32-normalised approximation to, its
+     * LR, never above min_lr -- and cand_z is NaN (environment NB200_CS_SCREEN=0: exact LR for every candidate). */
     double *cand_z, *cand_lr, *cand_norm_signal, *cand_nuc_signal, *cand_nuc_cov, *cand_nfr_cov, *cand_smoothed;
 } nb200_nuc_out;
 
