@@ -272,15 +272,16 @@ struct SmoothTracks {
 // out[n] = sum_d wd[d] x[n + d], wd[d] = w[h - d].  Each thread owns SM_XT = 4 consecutive outputs and walks the taps two
 // at a time: the inputs of (n .. n+3) x (d, d+1) are three aligned pairs that slide by one pair per step, so a step is one
 // 16-byte load of x, one broadcast 16-byte load of the tap pair and 8 FMAs.  Tiles without NaN / zero padding take this
-// fast path (denominator = sum of the window, as np.convolve of the window with an all-ones indicator gives); the others
-// evaluate the NaN-aware form tap by tap.
+// fast path (denominator = sum of the window, as np.convolve of the window with an all-ones indicator gives).  A thread
+// whose window holds a missing value (chunk edges, NaN stretches) runs the same walk on two arrays -- the values with the
+// missing ones zeroed and a 1/0 presence indicator -- i.e. utils.smooth's two convolutions, 16 FMAs per step.
 // The staged tile is stored with 16 bytes of padding after every 128 (SM_PHYS): a thread's pairs are 32 bytes apart, which
 // would put lanes i and i + 4 of a quarter warp on the same banks; with the padding the 16-byte loads are conflict free.
 #define SM_PHYS(j) ((j) + (((j) >> 4) << 1))
 static inline size_t smooth_same_smem(int wlen)   // taps (padded) + staged tile + NaN prefix counts
 {
     const size_t T2 = (size_t)wlen + 4, nX = SM_TILE + T2 + 4, nXp = nX + 2 * (nX / 16 + 1);   // staged tile incl. row padding
-    return sizeof(double) * (T2 + nXp) + sizeof(int) * (nX + 2) + 16;
+    return sizeof(double) * (T2 + 2 * nXp) + sizeof(int) * (nX + 2) + 16;   // taps, tile, presence indicator, NaN prefix counts
 }
 static __global__ void __launch_bounds__(SM_THREADS) k_smooth_same(SmoothTracks tr, const int64_t *__restrict__ out_off,
                                                                  const double *__restrict__ win, int wlen, int clip_neg)
@@ -295,6 +296,7 @@ static __global__ void __launch_bounds__(SM_THREADS) k_smooth_same(SmoothTracks 
     double *s_w = sm_s;                 // [T2] wd, zero padded
     double *s_x = sm_s + T2;            // [nX, padded] s_x[SM_PHYS(j)] = x[x0 + dlo + j]
     const int nXp = nX + 2 * (nX / 16 + 1);
+    double *s_i = s_x + nXp;            // [nX, padded] 1.0 where s_x holds a value, 0.0 where it is missing (NaN / off the chunk)
     const int c = blockIdx.y;
     const int64_t o = out_off[c];
     const int L = (int)(out_off[c + 1] - o);
@@ -324,11 +326,13 @@ static __global__ void __launch_bounds__(SM_THREADS) k_smooth_same(SmoothTracks 
             v = in[idx];
             if (clip_neg && v < 0) v = 0.0;
         }
-        if (v != v) {
+        const bool missing = v != v;
+        if (missing) {
             if (idx >= x0 + h - wlen + 1 && idx <= n_end - 1 + h) slow = 1;  // a real tap of this tile is missing
-            else v = 0.0;                                                    // only ever multiplied by padded (zero) taps
+            v = 0.0;
         }
         s_x[SM_PHYS(j)] = v;
+        s_i[SM_PHYS(j)] = missing ? 0.0 : 1.0;
     }
     if (slow) s_slow = 1;
     __syncthreads();
@@ -336,12 +340,12 @@ static __global__ void __launch_bounds__(SM_THREADS) k_smooth_same(SmoothTracks 
     // s_cnt[j] = number of NaN among s_x[0 .. j)
     bool my_slow = false;
     if (s_slow) {
-        int *s_cnt = reinterpret_cast<int *>(s_x + nXp);
+        int *s_cnt = reinterpret_cast<int *>(s_i + nXp);
         if (threadIdx.x < 32) {
             int run = 0;
             for (int j0 = 0; j0 < nX; j0 += 32) {
                 const int j = j0 + threadIdx.x;
-                const bool bad = j < nX && s_x[SM_PHYS(j)] != s_x[SM_PHYS(j)];
+                const bool bad = j < nX && s_i[SM_PHYS(j)] == 0.0;
                 const unsigned m = __ballot_sync(NB_FULL, bad);
                 if (j < nX) s_cnt[j] = run + __popc(m & ((1u << threadIdx.x) - 1u));
                 run += __popc(m);
@@ -354,11 +358,13 @@ static __global__ void __launch_bounds__(SM_THREADS) k_smooth_same(SmoothTracks 
     }
     const int n0 = x0 + threadIdx.x * SM_XT;
     if (n0 >= L) return;
-    if (!my_slow) {
-        const double2 *px = reinterpret_cast<const double2 *>(s_x);   // pair q of the tile sits at px[q + (q >> 3)]
+    // out[n0 .. n0+3] of the correlation of `src` (padded tile layout) with the taps: one 16-byte load of the tile, one
+    // broadcast 16-byte load of the tap pair and 8 FMAs per step
+    auto walk = [&](const double *src, double &a0, double &a1, double &a2, double &a3) {
+        const double2 *px = reinterpret_cast<const double2 *>(src);   // pair q of the tile sits at px[q + (q >> 3)]
         const double2 *pw = reinterpret_cast<const double2 *>(s_w);
         const int q0 = threadIdx.x * (SM_XT / 2);
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        a0 = a1 = a2 = a3 = 0.0;
         double2 A = px[q0 + (q0 >> 3)], B = px[q0 + 1 + ((q0 + 1) >> 3)];
 #pragma unroll 4
         for (int k2 = 0; k2 < T2 / 2; k2++) {
@@ -371,25 +377,22 @@ static __global__ void __launch_bounds__(SM_THREADS) k_smooth_same(SmoothTracks 
             A = B;
             B = C;
         }
+    };
+    double a0, a1, a2, a3;
+    walk(s_x, a0, a1, a2, a3);
+    if (!my_slow) {
         const double den = s_den;
         if (n0 < L) out[n0] = a0 / den;
         if (n0 + 1 < L) out[n0 + 1] = a1 / den;
         if (n0 + 2 < L) out[n0 + 2] = a2 / den;
         if (n0 + 3 < L) out[n0 + 3] = a3 / den;
-    } else {
-        for (int u = 0; u < SM_XT; u++) {
-            const int n = n0 + u;
-            if (n >= L) break;
-            double num = 0.0, den = 0.0;
-            for (int m = 0; m < wlen; m++) {
-                const double v = s_x[SM_PHYS(n + h - m - lo)];
-                if (v == v) {
-                    num += win[m] * v;
-                    den += win[m];
-                }
-            }
-            out[n] = (den == 0.0) ? nb_nan() : num / den;
-        }
+    } else {   // the same walk over the presence indicator gives the denominators; smoothed_norm == 0 -> NaN (utils.py:49)
+        double d0, d1, d2, d3;
+        walk(s_i, d0, d1, d2, d3);
+        if (n0 < L) out[n0] = (d0 == 0.0) ? nb_nan() : a0 / d0;
+        if (n0 + 1 < L) out[n0 + 1] = (d1 == 0.0) ? nb_nan() : a1 / d1;
+        if (n0 + 2 < L) out[n0 + 2] = (d2 == 0.0) ? nb_nan() : a2 / d2;
+        if (n0 + 3 < L) out[n0 + 3] = (d3 == 0.0) ? nb_nan() : a3 / d3;
     }
 }
 
