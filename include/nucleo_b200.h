@@ -222,6 +222,19 @@ int64_t nb200_format_track(const char *chrom, int64_t start, const double *vals,
  * pass: plain sorted BED / bedgraph -> BGZF file + .tbi.  Pure host code (zlib, `threads` deflate workers). */
 int nb200_bgzip_tabix(const char *path_plain, const char *path_gz, int threads, char *err, int errcap);
 
+/* ---- host-side BAM decode ------------------------------------------------------------------ */
+/* The reads the path consumes -- pysam AlignmentFile.fetch + `is_proper_pair and not is_reverse` of
+ * pyatac/fragments.pyx:21-25,47-50,128-131 -- for n_regions regions at once, decoded by `threads` host threads (zlib).
+ * voffset[r] = BGZF virtual offset to start scanning region r from (the .bai linear index entry of its first 16 kb
+ * window), tid[r] its reference id, [start[r], end[r]) the region.  frag_off[n_regions+1] receives the CSR offsets,
+ * *pos / *tlen library-allocated int32 arrays of frag_off[n_regions] values (release with nb200_free).  Reads are kept when
+ * pos < end and pos + max(l_seq,1) + 64 > start: a superset of htslib's overlap test; every consumer re-checks its own
+ * cell bounds like fragments.pyx:37 does.  Pure host code, no context. */
+int nb200_bam_fetch_many(const char *path, int32_t n_regions, const uint64_t *voffset, const int32_t *tid,
+                         const int32_t *start, const int32_t *end, int32_t threads, int64_t *frag_off, int32_t **pos,
+                         int32_t **tlen, char *err, int errcap);
+void nb200_free(void *p);
+
 /* ---- multi-GPU end-of-run reductions (NCCL over NVLink) ----------------------------------- */
 /* fragment-size histogram (fragments.pyx:122-145), nuc_dist (run_occ.py:117-121), V-plot sum
  * (pyatac/make_vplot.py:70-73).  unique_id is the 128-byte ncclUniqueId from rank 0. */

@@ -10,7 +10,7 @@ from .bias import PWM, InsertionBiasTrack
 from .chunk import Chunk
 from .chunkmat2d import BiasMat2D, FragmentMat2D
 from .engine import FLAG_NONREDUNDANT, FLAG_Z, PackedBatch, default_engine
-from .fragments import fetch_reads
+from .fragments import fetch_reads, fetch_reads_many
 from .multinomial_cov import calculateCov
 from .tracks import CoverageTrack, InsertionTrack, Track
 from .utils import call_peaks, fmt12, read_chrom_sizes_from_bam, reduce_peaks
@@ -197,8 +197,8 @@ class NucParameters:
     def pack(self, chunks):
         items = []
         pad = self.pad()
-        for c in chunks:
-            pos, tlen = fetch_reads(self.bam, c.chrom, c.start - pad - self.upper, c.end + pad + self.upper)
+        reads = fetch_reads_many(self.bam, [(c.chrom, c.start - pad - self.upper, c.end + pad + self.upper) for c in chunks])
+        for c, (pos, tlen) in zip(chunks, reads):
             sq, s0 = None, 0
             if self.fasta is not None:
                 s0 = c.start - self.window - self.upper // 2 - self.pwm.up

@@ -8,7 +8,7 @@ from .bias import PWM, InsertionBiasTrack
 from .chunk import Chunk
 from .chunkmat2d import BiasMat2D, FragmentMat2D
 from .engine import PackedBatch, default_engine
-from .fragments import fetch_reads
+from .fragments import fetch_reads, fetch_reads_many
 from .fragmentsizes import FragmentSizes
 from .tracks import CoverageTrack, Track
 from .utils import call_peaks, fmt12, read_chrom_sizes_from_fasta, smooth
@@ -167,8 +167,8 @@ class OccupancyParameters:
     def pack(self, chunks):
         """Host-side gather of a batch: reads from the BAM, sequence from the FASTA (the only host work per chunk)."""
         items = []
-        for c in chunks:
-            pos, tlen = fetch_reads(self.bam, c.chrom, c.start - self.flank - self.upper, c.end + self.flank + self.upper)
+        reads = fetch_reads_many(self.bam, [(c.chrom, c.start - self.flank - self.upper, c.end + self.flank + self.upper) for c in chunks])
+        for c, (pos, tlen) in zip(chunks, reads):
             sq, s0 = None, 0
             if self.fasta is not None:
                 s0 = c.start - self.window - self.upper // 2 - self.pwm.up

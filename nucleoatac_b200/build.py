@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libnucleo_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["nb200_ctx.cu", "nb200_batch.cu", "nb200_occ.cu", "nb200_nuc.cu", "nb200_prims.cu", "nb200_xcor_tc.cu", "nb200_hostfmt.cu", "nb200_hostio.cu", "nb200_pyatac.cu"]
+SOURCES = ["nb200_ctx.cu", "nb200_batch.cu", "nb200_occ.cu", "nb200_nuc.cu", "nb200_prims.cu", "nb200_xcor_tc.cu", "nb200_hostfmt.cu", "nb200_hostio.cu", "nb200_pyatac.cu", "nb200_bamio.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--fmad=true", "-Xptxas", "-v"]
 

@@ -20,6 +20,13 @@ def fetch_reads(bamfile, chrom, start, end):
     return _bam(bamfile).fetch_fragments(chrom, max(0, start), end)
 
 
+def fetch_reads_many(bamfile, regions):
+    """fetch_reads for a list of (chrom, start, end) in one native, multi-threaded BAM decode (nb200_bam_fetch_many):
+    -> list of (pos, tlen) array views, one per region."""
+    off, pos, tlen = _bam(bamfile).fetch_fragments_many([(c, max(0, s), e) for c, s, e in regions])
+    return [(pos[off[i]:off[i + 1]], tlen[off[i]:off[i + 1]]) for i in range(len(regions))]
+
+
 def makeFragmentMat(bamfile, chrom, start, end, lower, upper, atac=1):
     """pyatac/fragments.pyx:17-40 -> float64 [(upper-lower), (end-start)] count matrix."""
     pos, tlen = fetch_reads(bamfile, chrom, start - upper, end + upper)
@@ -34,18 +41,12 @@ def getInsertions(bamfile, chrom, start, end, lower, upper, atac=1):
 
 def getFragmentSizesFromChunkList(chunks, bamfile, lower, upper, atac=1):
     """pyatac/fragments.pyx:122-145 -> float64 [upper-lower] counts of fragments centred inside the chunks."""
-    starts, ends, off, ps, ts = [], [], [0], [], []
-    for c in chunks:
-        pos, tlen = fetch_reads(bamfile, c.chrom, c.start - upper, c.end + upper)
-        starts.append(c.start)
-        ends.append(c.end)
-        ps.append(pos)
-        ts.append(tlen)
-        off.append(off[-1] + len(pos))
-    if not starts:
+    chunks = list(chunks)
+    if not chunks:
         return np.zeros(upper - lower)
-    cat = lambda xs: np.concatenate(xs) if xs else np.zeros(0, np.int32)
-    return default_engine().fragment_sizes(starts, ends, off, cat(ps), cat(ts), lower, upper, atac).astype(np.float64)
+    off, pos, tlen = _bam(bamfile).fetch_fragments_many([(c.chrom, max(0, c.start - upper), c.end + upper) for c in chunks])
+    starts, ends = [c.start for c in chunks], [c.end for c in chunks]
+    return default_engine().fragment_sizes(starts, ends, off, pos, tlen, lower, upper, atac).astype(np.float64)
 
 
 def getAllFragmentSizes(bamfile, lower, upper, atac=1):

@@ -188,10 +188,12 @@ class BamFile:
             yield tid, pos, flag, tlen, pos + max(l_seq, 1) + 64
             p += 4 + bs
 
-    def _fetch_indexed(self, tid, start, end):
+    def _start_voffset(self, tid, start):
+        """BGZF virtual offset to scan a region of reference `tid` from: the linear-index entry of the 16 kb window holding
+        `start` (the previous non-empty one if that window has no reads); None when the reference has no reads."""
         lin = self._index[tid]
         if len(lin) == 0:
-            return np.zeros(0, np.int32), np.zeros(0, np.int32)
+            return None
         w = min(max(start, 0) >> 14, len(lin) - 1)
         voff = int(lin[w])
         if voff == 0:  # window without reads: walk back to the previous non-empty one
@@ -199,10 +201,16 @@ class BamFile:
             if len(nz) == 0:
                 nz2 = np.nonzero(lin)[0]
                 if len(nz2) == 0:
-                    return np.zeros(0, np.int32), np.zeros(0, np.int32)
+                    return None
                 voff = int(lin[nz2[0]])
             else:
                 voff = int(lin[nz[-1]])
+        return voff
+
+    def _fetch_indexed(self, tid, start, end):
+        voff = self._start_voffset(tid, start)
+        if voff is None:
+            return np.zeros(0, np.int32), np.zeros(0, np.int32)
         ps, ts = [], []
         for rtid, pos, flag, tlen, rend in self._records(voff):
             if rtid != tid or pos >= end:
@@ -234,6 +242,50 @@ class BamFile:
                 per[tid][1].append(tlen)
         self._all = {i: (np.asarray(p, dtype=np.int32), np.asarray(t, dtype=np.int32)) for i, (p, t) in per.items()}
 
+    def fetch_fragments_many(self, regions, threads=None):
+        """(frag_off int64[n+1], pos int32[], tlen int32[]) of the proper-pair forward reads of every (chrom, start, end)
+        in `regions`, CSR-packed in region order.  With a .bai index the decode is native and multi-threaded
+        (nb200_bam_fetch_many); without one it falls back to the per-region reader."""
+        n = len(regions)
+        if self._index is None or n == 0:
+            ps, ts, off = [], [], [0]
+            for chrom, start, end in regions:
+                p, t = self.fetch_fragments(chrom, start, end)
+                ps.append(p)
+                ts.append(t)
+                off.append(off[-1] + len(p))
+            cat = lambda xs: np.concatenate(xs) if xs else np.zeros(0, np.int32)
+            return np.asarray(off, dtype=np.int64), cat(ps), cat(ts)
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        voff, tids = np.zeros(n, dtype=np.uint64), np.full(n, -1, dtype=np.int32)
+        starts, ends = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+        for i, (chrom, start, end) in enumerate(regions):
+            tid = self._tid.get(chrom)
+            v = None if tid is None else self._start_voffset(tid, max(0, start))
+            if v is None:
+                continue   # unknown reference / reference without reads: voffset 0, tid -1 -> skipped by the library
+            voff[i], tids[i], starts[i], ends[i] = v, tid, max(0, start), end
+        if threads is None:
+            threads = max(1, min(16, len(os.sched_getaffinity(0)), n))
+        off = np.zeros(n + 1, dtype=np.int64)
+        pp, tp = _lib.c_int32_p(), _lib.c_int32_p()
+        err = C.create_string_buffer(512)
+        st = lib.nb200_bam_fetch_many(self.path.encode(), n, voff.ctypes.data_as(C.POINTER(C.c_uint64)), _lib.ptr(tids, C.c_int32),
+                                      _lib.ptr(starts, C.c_int32), _lib.ptr(ends, C.c_int32), int(threads), _lib.ptr(off, C.c_int64),
+                                      C.byref(pp), C.byref(tp), err, 512)
+        if st != 0:
+            raise IOError(err.value.decode() or "nb200_bam_fetch_many failed")
+        total = int(off[-1])
+        try:
+            pos = np.ctypeslib.as_array(pp, shape=(max(total, 1),))[:total].copy()
+            tlen = np.ctypeslib.as_array(tp, shape=(max(total, 1),))[:total].copy()
+        finally:
+            lib.nb200_free(pp)
+            lib.nb200_free(tp)
+        return off, pos, tlen
+
     def fetch_fragments(self, chrom, start, end):
         if chrom not in self._tid:
             return np.zeros(0, np.int32), np.zeros(0, np.int32)
@@ -246,6 +298,76 @@ class BamFile:
         # without an index: a superset by position (the device re-checks every cell bound, fragments.pyx:37)
         sel = (pos >= start - 5000) & (pos < end)
         return pos[sel], tlen[sel]
+
+
+def index_bam(path, out=None):
+    """Write a .bai for a coordinate-sorted BAM (`samtools index` for the needs of this package): the 16 kb linear index
+    only -- for every window the virtual offset of the first record that overlaps it -- and no bins, which is what
+    BamFile's region fetch uses.  Plain Python: meant for small files and the tests."""
+    bam = BamFile.__new__(BamFile)
+    BamFile.__init__(bam, path)
+    fh = bam.fh
+    # position of the first record = end of the header, found by re-walking it block by block
+    coff, ubase = 0, 0          # compressed offset of the current block, and of the block the buffer starts in
+    data, size = _read_block(fh, 0)
+    buf, next_coff = bytearray(data), size
+    starts = [(0, 0, len(data))]  # (offset in buf, coff, length) of every block in buf
+
+    def grow():
+        nonlocal next_coff
+        d, sz = _read_block(fh, next_coff)
+        if sz == 0:
+            return False
+        starts.append((len(buf), next_coff, len(d)))
+        buf.extend(d)
+        next_coff += sz
+        return True
+
+    def voffset(p):
+        for b0, c0, ln in reversed(starts):
+            if p >= b0 and (p < b0 + ln or ln == 0):
+                return (c0 << 16) | (p - b0)
+        b0, c0, ln = starts[-1]
+        return (next_coff << 16) if p == b0 + ln else None
+
+    def need(p, n):
+        while len(buf) - p < n:
+            if not grow():
+                return False
+        return True
+    need(0, 12)
+    l_text = struct.unpack_from("<i", buf, 4)[0]
+    p = 8 + l_text
+    need(p, 4)
+    n_ref = struct.unpack_from("<i", buf, p)[0]
+    p += 4
+    for _ in range(n_ref):
+        need(p, 4)
+        l_name = struct.unpack_from("<i", buf, p)[0]
+        need(p, 8 + l_name)
+        p += 8 + l_name
+    linear = [dict() for _ in range(n_ref)]
+    while need(p, 4):
+        bs = struct.unpack_from("<i", buf, p)[0]
+        if not need(p, 4 + bs):
+            break
+        tid, pos, _l, _m, _b, _c, _flag, l_seq = struct.unpack_from("<iiBBHHHi", buf, p + 4)
+        if tid >= 0:
+            v = voffset(p)
+            for w in range(max(pos, 0) >> 14, (max(pos, 0) + max(l_seq, 1) - 1 >> 14) + 1):
+                if w not in linear[tid]:
+                    linear[tid][w] = v
+        p += 4 + bs
+    bam.close()
+    out = out or path + ".bai"
+    with open(out, "wb") as o:
+        o.write(b"BAI\x01" + struct.pack("<i", n_ref))
+        for t in range(n_ref):
+            n_intv = (max(linear[t]) + 1) if linear[t] else 0
+            o.write(struct.pack("<ii", 0, n_intv))
+            o.write(np.asarray([linear[t].get(w, 0) for w in range(n_intv)], dtype="<u8").tobytes())
+        o.write(struct.pack("<Q", 0))
+    return out
 
 
 # ----------------------------------------------------------------------------------------- FASTA

@@ -11,7 +11,7 @@ from . import dist, hostio
 from .bias import InsertionBiasTrack, PWM
 from .chunk import ChunkList
 from .engine import default_engine
-from .fragments import fetch_reads, getAllFragmentSizes, getFragmentSizesFromChunkList
+from .fragments import _bam, fetch_reads, getAllFragmentSizes, getFragmentSizesFromChunkList
 from .fragmentsizes import FragmentSizes
 from .tracks import CoverageTrack, InsertionTrack
 from .utils import read_chrom_sizes_from_bam, read_chrom_sizes_from_fasta
@@ -40,16 +40,12 @@ def vplot_sum(chunks, bam, flank, lower, upper, atac=True, scale=False, device=0
     eng = default_engine(device)
     total = np.zeros((upper - lower, 2 * flank + 1))
     for i0 in range(0, len(chunks), sites_per_call):
-        centers, flips, off, ps, ts = [], [], [0], [], []
-        for ch in chunks[i0:i0 + sites_per_call]:
-            c = ch.center(new=True)
-            pos, tlen = fetch_reads(bam, c.chrom, c.start - flank - 1 - upper, c.end + flank + upper)
-            centers.append(c.start)
-            flips.append(1 if c.strand == "-" else 0)
-            ps.append(pos)
-            ts.append(tlen)
-            off.append(off[-1] + len(pos))
-        total += eng.vplot(centers, flips, off, np.concatenate(ps), np.concatenate(ts), flank, lower, upper, atac, scale)
+        sites = [ch.center(new=True) for ch in chunks[i0:i0 + sites_per_call]]
+        off, pos, tlen = _bam(bam).fetch_fragments_many([(c.chrom, max(0, c.start - flank - 1 - upper), c.end + flank + upper)
+                                                         for c in sites])
+        centers = [c.start for c in sites]
+        flips = [1 if c.strand == "-" else 0 for c in sites]
+        total += eng.vplot(centers, flips, off, pos, tlen, flank, lower, upper, atac, scale)
     return total
 
 

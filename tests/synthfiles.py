@@ -52,6 +52,7 @@ def make_files(tmpdir, ks=(2, 0, 5), R=251, W=251):
     hostio.FastaFile(fa).close()  # builds the .fai
     bam = os.path.join(tmpdir, "reads.bam")
     write_bam(bam, {"chrS": length}, reads)
+    hostio.index_bam(bam)  # .bai -> the drivers decode regions with the native reader (nb200_bam_fetch_many)
     bed = os.path.join(tmpdir, "regions.bed")
     with open(bed, "w") as fh:  # the drivers slop by nuc_sep/2 = 60 on both sides
         for (s, e, *_r) in sorted(chunks, key=lambda c: c[0]):  # the reference requires a sorted BED (docs/nucleoatac.md:10)

@@ -233,3 +233,44 @@ def test_merge_reproduces_shipped_nucmap(tmp_path, golden):
     assert nucleoatac_main(["merge", "--occpeaks", occ, "--nucpos", nuc, "--out", out]) == 0
     assert gz.open(out + ".nucmap_combined.bed.gz", "rt").read() == str(golden["nucmap_combined_text"])
     assert os.path.exists(out + ".nucmap_combined.bed.gz.tbi")
+
+
+def test_native_bam_reader_matches_python(tmp_path):
+    """nb200_bam_fetch_many (native, threaded) against the pure-Python region reader on an indexed synthetic BAM with
+    several references (one without reads): same reads, same order, for regions inside, across and past the data, an
+    unknown reference, and every thread count; index_bam's linear index against a scan of the whole file."""
+    import numpy as np
+    from nucleoatac_b200 import hostio
+    from tests.synthfiles import write_bam
+    rng = np.random.default_rng(5)
+    sizes = {"chrA": 300000, "chrEmpty": 50000, "chrB": 120000}
+    reads = []
+    for tid, name in ((0, "chrA"), (2, "chrB")):
+        n = 20000 if tid == 0 else 3000
+        pos = np.sort(rng.integers(0, sizes[name] - 600, n))
+        tl = rng.integers(30, 500, n)
+        reads += [(tid, int(p), int(t)) for p, t in zip(pos, tl)]
+    bam = str(tmp_path / "multi.bam")
+    write_bam(bam, sizes, reads)
+    hostio.index_bam(bam)
+    b = hostio.BamFile(bam)
+    assert b._index is not None and len(b._index) == 3 and len(b._index[1]) == 0
+    regions = [("chrA", 0, 1000), ("chrA", 16384, 16385), ("chrA", 299000, 400000), ("chrEmpty", 0, 50000), ("chrB", 0, 120000),
+               ("chrNope", 5, 10), ("chrB", 119990, 119999), ("chrA", 150000, 150001)]
+    for _ in range(40):
+        name = ("chrA", "chrB")[int(rng.integers(0, 2))]
+        s0 = int(rng.integers(-3000, sizes[name]))
+        regions.append((name, s0, s0 + int(rng.integers(1, 60000))))
+    expect = [b._fetch_indexed(b._tid[c], max(0, s0), e) if c in b._tid else (np.zeros(0, np.int32), np.zeros(0, np.int32))
+              for c, s0, e in regions]
+    assert sum(len(p) for p, _ in expect) > 10000
+    for threads in (1, 3, 16):
+        off, pos, tlen = b.fetch_fragments_many([(c, max(0, s0), e) for c, s0, e in regions], threads=threads)
+        assert off[0] == 0 and len(off) == len(regions) + 1 and off[-1] == len(pos) == len(tlen)
+        for i, (p, t) in enumerate(expect):
+            assert np.array_equal(pos[off[i]:off[i + 1]], p) and np.array_equal(tlen[off[i]:off[i + 1]], t), (threads, regions[i])
+    # every forward proper-pair read of a reference is found through the index
+    allp, _ = b._fetch_indexed(0, 0, sizes["chrA"])
+    assert len(allp) == 20000 and np.all(np.diff(allp) >= 0)
+    off, pos, tlen = b.fetch_fragments_many([])
+    assert len(off) == 1 and len(pos) == 0
