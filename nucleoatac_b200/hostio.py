@@ -290,8 +290,9 @@ class BamFile:
         if chrom not in self._tid:
             return np.zeros(0, np.int32), np.zeros(0, np.int32)
         tid = self._tid[chrom]
-        if self._index is not None:
-            return self._fetch_indexed(tid, max(0, start), end)
+        if self._index is not None:   # native reader; _fetch_indexed is its pure-Python twin (kept as the cross-check)
+            _off, pos, tlen = self.fetch_fragments_many([(chrom, max(0, start), end)], threads=1)
+            return pos, tlen
         if self._all is None:
             self._load_all()
         pos, tlen = self._all[tid]
