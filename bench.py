@@ -441,6 +441,24 @@ def emit(text):
 
 
 def main():
+    try:
+        fn = _main
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("TORCHELASTIC_ERROR_FILE"):
+            from torch.distributed.elastic.multiprocessing.errors import record   # torchrun's own per-rank error file
+            fn = record(_main)
+        fn()
+    except BaseException as ex:   # a rank that dies must say why: the traceback is the LAST thing on its stderr
+        if isinstance(ex, SystemExit) and not ex.code:
+            raise
+        import traceback
+        sys.stdout.flush()
+        sys.stderr.write("\n[bench.py rank %s/%s pid %d] FAILED:\n%s\n" % (os.environ.get("RANK", "0"), os.environ.get("WORLD_SIZE", "1"),
+                                                                       os.getpid(), traceback.format_exc()))
+        sys.stderr.flush()
+        os._exit(1)   # no atexit / NCCL teardown that could hang or bury the traceback under watchdog noise
+
+
+def _main():
     global _JSON_FD
     sys.stdout.flush()
     _JSON_FD = os.dup(1)

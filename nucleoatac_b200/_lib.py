@@ -174,7 +174,13 @@ def as_f64(a):
 
 
 def as_i32(a):
-    return np.ascontiguousarray(a, dtype=np.int32)
+    """int32 view/copy for the C-ABI; a value outside int32 raises instead of wrapping (numpy casts int64 arrays silently)."""
+    if isinstance(a, np.ndarray) and a.dtype == np.int32:
+        return np.ascontiguousarray(a)
+    b = np.asarray(a)
+    if b.size and b.dtype.kind in "iu" and b.dtype.itemsize > 4 and (int(b.min()) < -2 ** 31 or int(b.max()) >= 2 ** 31):
+        raise OverflowError("coordinate outside int32: %d .. %d" % (int(b.min()), int(b.max())))
+    return np.ascontiguousarray(b, dtype=np.int32)
 
 
 def as_i64(a):

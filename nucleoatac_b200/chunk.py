@@ -58,7 +58,9 @@ class ChunkList(list):
             c.slop(chromDict, up=up, down=down)
 
     def merge(self, new=False, sep=-1):
-        """Merge neighbours closer than `sep` (chunk.py:109-125); the list must be sorted."""
+        """Merge neighbours closer than `sep` (chunk.py:109-125); an unsorted list is sorted first, as the reference does."""
+        if not self.isSorted():
+            self.sort()
         out = ChunkList()
         if len(self):
             prev = Chunk(self[0].chrom, self[0].start, self[0].end, weight=self[0].weight, name=self[0].name, strand=self[0].strand)

@@ -97,7 +97,8 @@ def build_parser():
     g.add_argument("--pwm", metavar="Tn5_PWM", default="Human", help="PWM descriptor file. Default is Human.PWM.txt included in package")
     g.add_argument("--cores", metavar="num_cores", default=1, type=int, help="Number of cores to use (ignored)")
     g.add_argument("--write_all", action="store_true", default=False, help="write all tracks")
-    for sp in (occ, nuc, nf):
+    rn.add_argument("--xcor_mode", default=0, type=int, help="0 auto (tcgen05), 1 fp64 CUDA cores, 2 tcgen05 tensor cores")
+    for sp in (occ, nuc, nf, rn):
         g = sp.add_argument_group("Device options", "")
         g.add_argument("--device", default=0, type=int, help="CUDA device of this process")
         g.add_argument("--rank", default=0, type=int, help="shard index: this process scores chunks k with k %% world == rank")
@@ -111,11 +112,7 @@ def nucleoatac_main(argv=None):
     t0 = time.time()
     if getattr(args, "world", 1) == 1 and int(os.environ.get("WORLD_SIZE", "1")) > 1:  # launched by torchrun
         from . import dist
-        args.rank, args.world, args.device = dist.env_rank_world()
-        import torch.distributed as td
-        if not td.is_initialized():
-            import torch
-            td.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+        args.rank, args.world, args.device = dist.init_from_env()   # binds this process to cuda:LOCAL_RANK before NCCL starts
     if args.command == "occ":
         print("---------Computing Occupancy and Nucleosomal Insert Distribution----")
         from .run_occ import run_occ
@@ -133,27 +130,36 @@ def nucleoatac_main(argv=None):
         from .run_nfr import run_nfr
         run_nfr(args)
     elif args.command == "run":  # nucleoatac/cli.py:34-64
+        from . import dist
         p = build_parser()
         base = ["--bed", args.bed, "--bam", args.bam, "--fasta", args.fasta, "--pwm", args.pwm, "--out", args.out]
+        # every sharded step runs on this process's shard and device; the host-only steps (vprocess, merge) run on rank 0
+        # between barriers, so that no two ranks write the same file
+        shard = ["--rank", str(args.rank), "--world", str(args.world), "--device", str(args.device), "--batch", str(args.batch)]
         print("---------Step1: Computing Occupancy and Nucleosomal Insert Distribution---------")
         from .run_occ import run_occ
-        run_occ(p.parse_args(["occ"] + base))
+        run_occ(p.parse_args(["occ"] + base + shard))
         print("---------Step2: Processing Vplot------------------------------------------------")
-        from .run_vprocess import run_vprocess
-        run_vprocess(p.parse_args(["vprocess", "--sizes", args.out + ".nuc_dist.txt", "--out", args.out]))
+        if args.rank == 0:
+            from .run_vprocess import run_vprocess
+            run_vprocess(p.parse_args(["vprocess", "--sizes", args.out + ".nuc_dist.txt", "--out", args.out]))
+        dist.barrier(args.world)
         print("---------Step3: Obtaining nucleosome signal and calling positions---------------")
         from .run_nuc import run_nuc
-        run_nuc(p.parse_args(["nuc"] + base + ["--occ_track", args.out + ".occ.bedgraph.gz", "--vmat", args.out + ".VMat",
-                                               "--sizes", args.out + ".fragmentsizes.txt"] + (["--write_all"] if args.write_all else [])))
+        run_nuc(p.parse_args(["nuc"] + base + shard + ["--occ_track", args.out + ".occ.bedgraph.gz", "--vmat", args.out + ".VMat",
+                                                       "--sizes", args.out + ".fragmentsizes.txt", "--xcor_mode", str(args.xcor_mode)]
+                             + (["--write_all"] if args.write_all else [])))
         print("---------Step4: Making combined nucleosome position map ------------------------")
-        from .merge import run_merge
-        run_merge(p.parse_args(["merge", "--occpeaks", args.out + ".occpeaks.bed.gz", "--nucpos", args.out + ".nucpos.bed.gz",
-                                "--out", args.out]))
+        if args.rank == 0:
+            from .merge import run_merge
+            run_merge(p.parse_args(["merge", "--occpeaks", args.out + ".occpeaks.bed.gz", "--nucpos", args.out + ".nucpos.bed.gz",
+                                    "--out", args.out]))
+        dist.barrier(args.world)
         print("---------Step5: Calling NFR positions-------------------------------------------")
         from .run_nfr import run_nfr
         run_nfr(p.parse_args(["nfr", "--bed", args.bed, "--occ_track", args.out + ".occ.bedgraph.gz", "--calls",
                               args.out + ".nucmap_combined.bed.gz", "--out", args.out, "--fasta", args.fasta, "--pwm", args.pwm,
-                              "--bam", args.bam]))
+                              "--bam", args.bam] + shard))
     elif args.command == "vprocess":
         print("---------Processing VPlot-----------------------------------------")
         from .run_vprocess import run_vprocess

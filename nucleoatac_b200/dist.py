@@ -26,23 +26,65 @@ def _dist():
     return None
 
 
-def allreduce_sum(arr):
-    """Sum a numpy array over all ranks (identity without an initialised process group)."""
+def init_from_env(device=None):
+    """Join the torchrun rendezvous (env://): NCCL with this process bound to its own GPU (LOCAL_RANK), gloo without a
+    GPU.  The device is set BEFORE the group exists so that every collective's tensors land on this rank's GPU."""
+    import torch
+    import torch.distributed as td
+    rank, world, local = env_rank_world()
+    if td.is_initialized():
+        return rank, world, local
+    if torch.cuda.is_available():
+        dev = local if device is None else int(device)
+        torch.cuda.set_device(dev)
+        td.init_process_group("nccl", device_id=torch.device("cuda", dev))
+    else:
+        td.init_process_group("gloo")
+    return rank, world, local
+
+
+def require_group(world):
+    """A sharded run (world > 1) needs the reductions: refuse to hand back per-shard partial sums."""
+    if world > 1 and _dist() is None:
+        if "MASTER_ADDR" in os.environ and "RANK" in os.environ and "WORLD_SIZE" in os.environ:
+            init_from_env()
+            return
+        raise RuntimeError("--world %d without a process group: launch with `python -m torch.distributed.run --nproc-per-node %d "
+                           "--master-addr 127.0.0.1 ...` (or export MASTER_ADDR/MASTER_PORT/RANK/WORLD_SIZE) so that fragment sizes, "
+                           "nuc_dist and V-plot sums are reduced over the shards" % (world, world))
+
+
+def allreduce_sum(arr, world=None):
+    """Sum a numpy array over all ranks.  Identity for a single-rank run; a sharded run (`world` > 1) without an
+    initialised process group is an error, not a silent partial sum."""
     dist = _dist()
-    if dist is None or dist.get_world_size() == 1:
+    if dist is None:
+        if world is not None and world > 1:
+            require_group(world)
+            dist = _dist()
+        if dist is None:
+            return arr
+    if dist.get_world_size() == 1:
         return arr
     import torch
     t = torch.from_numpy(np.ascontiguousarray(arr))
     if dist.get_backend() == "nccl":
-        t = t.cuda()
+        t = t.cuda(torch.cuda.current_device())   # the device init_from_env bound this rank to
     dist.all_reduce(t)
     return t.cpu().numpy()
 
 
-def barrier():
+def barrier(world=None):
     dist = _dist()
+    if dist is None and world is not None and world > 1:
+        require_group(world)
+        dist = _dist()
     if dist is not None and dist.get_world_size() > 1:
-        dist.barrier()
+        if dist.get_backend() == "nccl":
+            import torch
+            dist.barrier(device_ids=[torch.cuda.current_device()])
+        else:
+            dist.barrier()
 
 
 class ShardWriter:

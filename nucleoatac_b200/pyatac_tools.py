@@ -58,11 +58,11 @@ def make_vplot(args):
     mine = ChunkList(*dist.shard(chunks, rank, world))
     result = vplot_sum(mine, args.bam, args.flank, args.lower, args.upper, args.atac, args.scale,
                        device=getattr(args, "device", 0))
-    result = dist.allreduce_sum(result)  # make_vplot.py:70-73: sum of the per-set matrices
+    result = dist.allreduce_sum(result, world)  # make_vplot.py:70-73: sum of the per-set matrices
     vmat = VMat(result, args.lower, args.upper)
     if rank == 0:
         vmat.save(args.out + ".VMat")
-    dist.barrier()
+    dist.barrier(world)
     return vmat
 
 
@@ -91,11 +91,11 @@ def _write_tracks(args, suffix, chunks, make_track):
         track.write_track(writer)
         writer.end_chunk()
     writer.close()
-    dist.barrier()
+    dist.barrier(world)
     if rank == 0:
         dist.ShardWriter.merge(path, world, len(chunks))
         _finish(path, path + ".gz")
-    dist.barrier()
+    dist.barrier(world)
 
 
 def get_ins(args, bases=50000, splitsize=1000):
@@ -165,14 +165,14 @@ def get_sizes(args):
         chunks.merge()
         counts = np.asarray(getFragmentSizesFromChunkList(dist.shard(chunks, rank, world), args.bam, args.lower, args.upper,
                                                           args.atac), dtype=np.float64)
-        counts = dist.allreduce_sum(counts)
+        counts = dist.allreduce_sum(counts, world)
     else:
         counts = getAllFragmentSizes(args.bam, args.lower, args.upper, args.atac)
     total = np.sum(counts)
     sizes = FragmentSizes(args.lower, args.upper, atac=args.atac, vals=counts / (total + (total == 0)))
     if rank == 0:
         sizes.save(args.out + ".fragmentsizes.txt")
-    dist.barrier()
+    dist.barrier(world)
     return sizes
 
 
@@ -238,11 +238,7 @@ def build_parser():
 def pyatac_main(argv=None):
     args = build_parser().parse_args(argv)
     if getattr(args, "world", 1) == 1 and int(os.environ.get("WORLD_SIZE", "1")) > 1:  # launched by torchrun
-        args.rank, args.world, args.device = dist.env_rank_world()
-        import torch
-        import torch.distributed as td
-        if not td.is_initialized():
-            td.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+        args.rank, args.world, args.device = dist.init_from_env()   # binds this process to cuda:LOCAL_RANK before NCCL starts
     cmds = dict(sizes=get_sizes, bias=make_bias_track, vplot=make_vplot, ins=get_ins, cov=get_cov)
     if args.command not in cmds:
         build_parser().print_help()

@@ -51,11 +51,11 @@ def run_nfr(args):
     nfr_writer.close()
     if ins_writer is not None:
         ins_writer.close()
-    dist.barrier()
+    dist.barrier(world)
     if rank == 0:
         dist.ShardWriter.merge(args.out + ".nfrpos.bed", world, len(chunks))
         _finish(args.out + ".nfrpos.bed", args.out + ".nfrpos.bed.gz")
         if ins_writer is not None:
             dist.ShardWriter.merge(args.out + ".ins.bedgraph", world, len(chunks))
             _finish(args.out + ".ins.bedgraph", args.out + ".ins.bedgraph.gz")
-    dist.barrier()
+    dist.barrier(world)

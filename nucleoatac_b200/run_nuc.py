@@ -64,11 +64,11 @@ def run_nuc(args, score=process_chunks):
             nc.removeData()
     for h in handles.values():
         h.close()
-    dist.barrier()
+    dist.barrier(world)
     if rank == 0:
         for n in outputs:
             plain = args.out + "." + n + ext(n)
             dist.ShardWriter.merge(plain, world, len(chunks))
             hostio.bgzip_tabix(plain, plain + ".gz")  # tabix_compress + tabix_index, run_nuc.py:194-201
             os.remove(plain)
-    dist.barrier()
+    dist.barrier(world)

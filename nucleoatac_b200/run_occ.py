@@ -39,7 +39,7 @@ def run_occ(args, score=process_chunks, count_sizes=getFragmentSizesFromChunkLis
         tmp = FragmentSizes.open(args.sizes)
         fragment_dist.fragmentsizes = FragmentSizes(0, args.upper, vals=tmp.get(0, args.upper))
     else:  # fragments.pyx:122-145, one shard per rank, summed exactly (integer-valued counts)
-        counts = dist.allreduce_sum(np.asarray(count_sizes(dist.shard(chunks, rank, world), args.bam, 0, args.upper), dtype=np.float64))
+        counts = dist.allreduce_sum(np.asarray(count_sizes(dist.shard(chunks, rank, world), args.bam, 0, args.upper), dtype=np.float64), world)
         total = np.sum(counts)
         fragment_dist.fragmentsizes = FragmentSizes(0, args.upper, vals=counts / (total + (total == 0)))
     fragment_dist.modelNFR()
@@ -74,8 +74,8 @@ def run_occ(args, score=process_chunks, count_sizes=getFragmentSizesFromChunkLis
             oc.removeData()
     for w in writers + [peaks_writer]:
         w.close()
-    nuc_dist = dist.allreduce_sum(nuc_dist)  # run_occ.py:117-121 summed over the shards
-    dist.barrier()
+    nuc_dist = dist.allreduce_sum(nuc_dist, world)  # run_occ.py:117-121 summed over the shards
+    dist.barrier(world)
     if rank == 0:
         dist.ShardWriter.merge(args.out + ".occpeaks.bed", world, len(chunks))
         _finish(args.out + ".occpeaks.bed", args.out + ".occpeaks.bed.gz")
@@ -83,5 +83,5 @@ def run_occ(args, score=process_chunks, count_sizes=getFragmentSizesFromChunkLis
             dist.ShardWriter.merge(args.out + "." + n + ".bedgraph", world, len(chunks))
             _finish(args.out + "." + n + ".bedgraph", args.out + "." + n + ".bedgraph.gz")
         FragmentSizes(0, args.upper, vals=nuc_dist).save(args.out + ".nuc_dist.txt")
-    dist.barrier()
+    dist.barrier(world)
     return nuc_dist

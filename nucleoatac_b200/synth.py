@@ -1,8 +1,10 @@
 """Deterministic synthetic workload for the occ+nuc scoring path (BASELINE.json configs).
 
 Host-side, numpy only, shared by the parity tests, bench.py (GPU arm, CPU baseline and the
-reference arm) so that all of them score the same reads.  Chunk k of the virtual contig is
-[10 000 + 12 000 k, +10 000); its reads depend only on (seed, k).
+reference arm) so that all of them score the same reads.  Coordinates are per contig like the
+reference's (pyatac/chunk.py:132-175): chunk k lies on virtual contig k // 100 000 at
+[10 000 + 12 000 (k mod 100 000), +10 000), so any chunk count (configs[3]: 500 000) stays inside
+int32; its reads depend only on (seed, k).
 
   reads      n ~ Poisson(density * L) fragments; insert size from the 3-component mixture
              0.55 * (Gamma(2.2, 22) + 38)  +  0.35 * N(188, 18)  +  0.10 * N(370, 30), rounded, kept if
@@ -25,13 +27,26 @@ SEED = 20261017
 CHUNK_LEN = 10000
 CHUNK_STRIDE = 12000
 CHUNK0 = 10000
+CHUNKS_PER_CONTIG = 100000   # 1.2 Gbp per virtual contig: the largest coordinate stays below 2^31
 SEQ_MARGIN = 400
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+def chunk_contig(k):
+    """Name of the virtual contig chunk k lies on."""
+    return "synth%d" % (k // CHUNKS_PER_CONTIG)
+
+
 def chunk_span(k, length=CHUNK_LEN):
-    s = CHUNK0 + k * CHUNK_STRIDE
+    s = CHUNK0 + (k % CHUNKS_PER_CONTIG) * CHUNK_STRIDE
     return s, s + length
+
+
+def _checked_i32(a, what):
+    a = np.asarray(a, dtype=np.int64)
+    if a.size and (a.min() < -2 ** 31 or a.max() >= 2 ** 31):
+        raise OverflowError("%s does not fit int32 (BAM coordinates are int32 per contig)" % what)
+    return a.astype(np.int32)
 
 
 def _sizes(rng, n):
@@ -64,8 +79,8 @@ def make_chunk(k, length=CHUNK_LEN, density=0.25, seed=SEED, with_seq=True, seq_
     size, centre = size[ok], centre[ok]
     left = centre - (size - 1) // 2
     order = np.argsort(left, kind="stable")  # BAM order: coordinate sorted
-    pos = (left[order] - 4).astype(np.int32)
-    tlen = (size[order] + 8).astype(np.int32)
+    pos = _checked_i32(left[order] - 4, "read position")
+    tlen = _checked_i32(size[order] + 8, "template length")
     seq = None
     if with_seq:
         codes = rng.choice(5, size=length + 2 * seq_margin, p=[0.2997, 0.1998, 0.1998, 0.2997, 0.001])

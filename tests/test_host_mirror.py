@@ -274,3 +274,80 @@ def test_native_bam_reader_matches_python(tmp_path):
     assert len(allp) == 20000 and np.all(np.diff(allp) >= 0)
     off, pos, tlen = b.fetch_fragments_many([])
     assert len(off) == 1 and len(pos) == 0
+
+
+def test_merge_sorts_unsorted_bed():
+    """pyatac/chunk.py:109-125: merge() sorts first when the list is not sorted (an unsorted BED must not lose bases)."""
+    cl = ChunkList(Chunk("chr1", 500, 900), Chunk("chr1", 100, 600), Chunk("chr1", 550, 700), Chunk("chr0", 5, 9))
+    cl.merge()
+    assert [(c.chrom, c.start, c.end) for c in cl] == [("chr0", 5, 9), ("chr1", 100, 900)]
+    assert cl.isSorted()
+
+
+def test_modelNFR_reproduces_shipped_occ_fit(example):
+    """FragmentMixDistribution.modelNFR (nucleoatac/Occupancy.py:29-66) against rows 2-3 of the reference's shipped
+    example_results/example.occ_fit.txt (nuc_fit, nfr_fit), from the shipped fragment sizes (row 1)."""
+    from nucleoatac_b200.fragmentsizes import FragmentSizes
+    from nucleoatac_b200.Occupancy import FragmentMixDistribution
+    fd = FragmentMixDistribution(0, 251)
+    fd.fragmentsizes = FragmentSizes(0, 251, vals=np.array(example.occ_fit[0]))
+    fd.modelNFR()
+    np.testing.assert_allclose(fd.nuc_fit.get(0, 251), example.occ_fit[1], rtol=1e-9, atol=1e-15)
+    np.testing.assert_allclose(fd.nfr_fit.get(0, 251), example.occ_fit[2], rtol=1e-9, atol=1e-15)
+
+
+def test_synthetic_chunks_stay_inside_int32():
+    """BASELINE configs[3] (500 000 x 10 kb chunks, 8 GPUs): per-contig coordinates like pyatac/chunk.py:132-175, so chunk
+    499 999 (and bench.py's largest index at N=8) is generatable, and an out-of-range coordinate raises instead of wrapping."""
+    from nucleoatac_b200 import synth
+    from nucleoatac_b200.engine import PackedBatch
+    for k in (178955, 178956, 199999, 399999, 499999, 28 * 2000 * 8 + 7):
+        s, e, pos, tlen, seq, s0 = synth.make_chunk(k, with_seq=(k == 499999))
+        assert 0 < s < e < 2 ** 31 and e - s == synth.CHUNK_LEN
+        assert pos.dtype == np.int32 and len(pos) > 1500 and pos.min() > s - 2000 and pos.max() < e + 2000
+        assert np.all(np.diff(pos) >= 0)
+    assert synth.chunk_contig(499999) == "synth4" and synth.chunk_contig(0) == "synth0"
+    # same reads as chunk k on the first contig would have: the generator depends on (seed, k) only through rng and offset
+    a, b = synth.make_chunk(5, with_seq=False), synth.make_chunk(100005, with_seq=False)
+    assert a[0] == b[0] and len(a[2]) != 0 and not np.array_equal(a[2][:50], b[2][:50])
+    pb = PackedBatch.from_chunks([synth.make_chunk(k, with_seq=False) for k in (499998, 499999)])
+    assert pb.total_len == 20000
+    with pytest.raises(OverflowError):
+        PackedBatch(np.array([2 ** 31 + 5]), np.array([2 ** 31 + 10]), [0, 0], np.zeros(0, np.int32), np.zeros(0, np.int32))
+    with pytest.raises(OverflowError):
+        synth._checked_i32(np.array([2 ** 31]), "x")
+
+
+def test_sharded_run_without_process_group_is_an_error(monkeypatch):
+    """--rank/--world given by hand without a rendezvous: the reductions refuse to return per-shard partial sums."""
+    from nucleoatac_b200 import dist
+    for k in ("MASTER_ADDR", "RANK", "WORLD_SIZE"):
+        monkeypatch.delenv(k, raising=False)
+    x = np.arange(4.0)
+    assert dist.allreduce_sum(x, 1) is x and dist.allreduce_sum(x) is x
+    with pytest.raises(RuntimeError, match="process group"):
+        dist.allreduce_sum(x, 2)
+    with pytest.raises(RuntimeError, match="process group"):
+        dist.barrier(2)
+
+
+def test_cli_run_propagates_shard_and_device(monkeypatch, tmp_path):
+    """`nucleoatac run` hands rank / world / device / batch / xcor_mode to every sharded step and keeps the host-only
+    steps (vprocess, merge) on rank 0."""
+    from nucleoatac_b200 import cli, dist
+    import nucleoatac_b200.merge as M, nucleoatac_b200.run_nfr as NF, nucleoatac_b200.run_nuc as N, nucleoatac_b200.run_occ as O, \
+        nucleoatac_b200.run_vprocess as V
+    seen = []
+    monkeypatch.setattr(O, "run_occ", lambda a: seen.append(("occ", a.rank, a.world, a.device, a.batch)))
+    monkeypatch.setattr(N, "run_nuc", lambda a: seen.append(("nuc", a.rank, a.world, a.device, a.batch, a.xcor_mode)))
+    monkeypatch.setattr(NF, "run_nfr", lambda a: seen.append(("nfr", a.rank, a.world, a.device, a.batch)))
+    monkeypatch.setattr(V, "run_vprocess", lambda a: seen.append(("vprocess",)))
+    monkeypatch.setattr(M, "run_merge", lambda a: seen.append(("merge",)))
+    monkeypatch.setattr(dist, "barrier", lambda world=None: seen.append(("barrier", world)))
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    base = ["run", "--bed", "a.bed", "--bam", "a.bam", "--fasta", "a.fa", "--out", str(tmp_path / "o")]
+    cli.nucleoatac_main(base + ["--rank", "1", "--world", "4", "--device", "1", "--batch", "64", "--xcor_mode", "1"])
+    assert seen == [("occ", 1, 4, 1, 64), ("barrier", 4), ("nuc", 1, 4, 1, 64, 1), ("barrier", 4), ("nfr", 1, 4, 1, 64)]
+    seen.clear()
+    cli.nucleoatac_main(base)
+    assert [s[0] for s in seen] == ["occ", "vprocess", "barrier", "nuc", "merge", "barrier", "nfr"]
