@@ -183,6 +183,37 @@ int nb200_nuc_download(nb200_ctx *ctx, nb200_dbatch *b, const nb200_nuc_out *out
 int64_t nb200_occ_d2h_bytes(nb200_dbatch *b, const nb200_occ_out *out);
 int64_t nb200_nuc_d2h_bytes(nb200_dbatch *b, const nb200_nuc_out *out);
 
+/* The same results with the per-position tracks delivered as float32: they are converted on the device (round to nearest,
+ * relative error <= 6e-8, well inside the 1e-5 the scoring path is specified to) and cross the host link at 4 bytes per
+ * position and track instead of 8.  What the reference does with these tracks is print them (Track.write_track,
+ * pyatac/tracks.py:37-74) and read single positions back (run_nuc.py --occ_track); peak / candidate tables, counts and
+ * nuc_dist keep their types.  Fields as in nb200_occ_out / nb200_nuc_out. */
+typedef struct {
+    float *smoothed_vals, *smoothed_lower, *smoothed_upper;
+    float *vals, *lower_bound, *upper_bound;
+    float *cov;
+    double *nuc_dist;
+    int32_t *peak_count;
+    const int64_t *peak_off;
+    int32_t *peak_pos;
+    double *peak_occ, *peak_lower, *peak_upper, *peak_reads;
+} nb200_occ_out32;
+
+typedef struct {
+    float *nuc_signal, *background, *norm_signal, *smoothed;
+    float *nuc_cov, *nfr_cov;
+    int32_t *cand_count;
+    const int64_t *cand_off;
+    int32_t *cand_pos;
+    int32_t *cand_flag;
+    double *cand_z, *cand_lr, *cand_norm_signal, *cand_nuc_signal, *cand_nuc_cov, *cand_nfr_cov, *cand_smoothed;
+} nb200_nuc_out32;
+
+int nb200_occ_download32(nb200_ctx *ctx, nb200_dbatch *b, const nb200_occ_out32 *out);
+int nb200_nuc_download32(nb200_ctx *ctx, nb200_dbatch *b, const nb200_nuc_out32 *out);
+int64_t nb200_occ_d2h_bytes32(nb200_dbatch *b, const nb200_occ_out32 *out);
+int64_t nb200_nuc_d2h_bytes32(nb200_dbatch *b, const nb200_nuc_out32 *out);
+
 /* ---- measurement ------------------------------------------------------------------------ */
 /* CUDA-event bracket on the batch stream. */
 int nb200_timer_start(nb200_ctx *ctx, nb200_dbatch *b);

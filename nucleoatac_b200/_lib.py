@@ -63,6 +63,17 @@ class NucOut(C.Structure):
                 ("cand_nfr_cov", c_double_p), ("cand_smoothed", c_double_p)]
 
 
+c_float_p = C.POINTER(C.c_float)
+
+
+class OccOut32(C.Structure):   # nb200_occ_out32: the per-position tracks as float32
+    _fields_ = [(n, c_float_p if i < 7 else t) for i, (n, t) in enumerate(OccOut._fields_)]
+
+
+class NucOut32(C.Structure):   # nb200_nuc_out32
+    _fields_ = [(n, c_float_p if i < 6 else t) for i, (n, t) in enumerate(NucOut._fields_)]
+
+
 _lib = None
 
 
@@ -124,6 +135,10 @@ def load():
     _sig(lib, "nb200_nuc_download", I, vp, vp, C.POINTER(NucOut))
     _sig(lib, "nb200_occ_d2h_bytes", i64, vp, C.POINTER(OccOut))
     _sig(lib, "nb200_nuc_d2h_bytes", i64, vp, C.POINTER(NucOut))
+    _sig(lib, "nb200_occ_download32", I, vp, vp, C.POINTER(OccOut32))
+    _sig(lib, "nb200_nuc_download32", I, vp, vp, C.POINTER(NucOut32))
+    _sig(lib, "nb200_occ_d2h_bytes32", i64, vp, C.POINTER(OccOut32))
+    _sig(lib, "nb200_nuc_d2h_bytes32", i64, vp, C.POINTER(NucOut32))
     _sig(lib, "nb200_timer_start", I, vp, vp)
     _sig(lib, "nb200_timer_stop", I, vp, vp)
     _sig(lib, "nb200_timer_elapsed_ms", I, vp, vp, C.POINTER(C.c_float))
@@ -154,7 +169,8 @@ EXPORTS = [
     "nb200_coverage_dense", "nb200_smooth", "nb200_call_peaks", "nb200_reduce_peaks", "nb200_calculate_occupancy",
     "nb200_multinomial_cov", "nb200_batch_upload", "nb200_batch_free", "nb200_batch_sync", "nb200_batch_total_len",
     "nb200_batch_h2d_bytes", "nb200_occ_run", "nb200_nuc_run", "nb200_occ_download", "nb200_nuc_download",
-    "nb200_occ_d2h_bytes", "nb200_nuc_d2h_bytes", "nb200_timer_start", "nb200_timer_stop", "nb200_timer_elapsed_ms",
+    "nb200_occ_d2h_bytes", "nb200_nuc_d2h_bytes", "nb200_occ_download32", "nb200_nuc_download32", "nb200_occ_d2h_bytes32",
+    "nb200_nuc_d2h_bytes32", "nb200_timer_start", "nb200_timer_stop", "nb200_timer_elapsed_ms",
     "nb200_profile_enable", "nb200_profile_reset", "nb200_profile_count", "nb200_profile_get", "nb200_flush_l2",
     "nb200_format_track", "nb200_bgzip_tabix", "nb200_vplot", "nb200_coverage", "nb200_bam_fetch_many", "nb200_free",
     "nb200_nccl_unique_id", "nb200_nccl_init", "nb200_allreduce_f64", "nb200_allreduce_i64", "nb200_nccl_finalize",

@@ -281,7 +281,8 @@ int nb200_batch_free(nb200_ctx *ctx, nb200_dbatch *b)
                       &b->o_peak_off, &b->n_signal, &b->n_bg, &b->n_norm, &b->n_smooth, &b->n_nuc_cov, &b->n_nfr_cov,
                       &b->n_bx, &b->n_bcov, &b->n_cB, &b->n_comb, &b->n_cand_bcov, &b->n_cand_count, &b->n_cand_pos, &b->n_cand_flag,
                       &b->n_cand_z, &b->n_cand_lr, &b->n_cand_norm, &b->n_cand_sig, &b->n_cand_cov, &b->n_cand_nfr,
-                      &b->n_cand_smooth, &b->n_cand_off, &b->n_work, &b->n_work_count, &b->sc_i32, &b->sc_f64, &b->sc_u8};
+                      &b->n_cand_smooth, &b->n_cand_off, &b->n_work, &b->n_work_count, &b->sc_i32, &b->sc_f64, &b->sc_u8,
+                      &b->pack32_occ, &b->pack32_nuc, &b->o_wv};
     for (auto d : bufs) d->release();
     if (b->ev_start) cudaEventDestroy(b->ev_start);
     if (b->ev_stop) cudaEventDestroy(b->ev_stop);

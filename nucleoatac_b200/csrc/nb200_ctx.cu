@@ -2,6 +2,7 @@
 #include <dlfcn.h>
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "nb200_common.cuh"
 
@@ -78,6 +79,18 @@ void nb200_prof_collect(nb200_ctx *ctx)
     ctx->pending.clear();
 }
 
+int nb200_fifo_enter(nb200_ctx *ctx, cudaStream_t st)
+{
+    if (ctx->fifo) NB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_fifo, 0));   // a never-recorded event is complete
+    return NB200_OK;
+}
+
+int nb200_fifo_leave(nb200_ctx *ctx, cudaStream_t st)
+{
+    if (ctx->fifo) NB_CUDA(ctx, cudaEventRecord(ctx->ev_fifo, st));
+    return NB200_OK;
+}
+
 extern "C" {
 
 int nb200_ctx_create(int device, nb200_ctx **out)
@@ -110,6 +123,13 @@ int nb200_ctx_create(int device, nb200_ctx **out)
         delete c;
         return nb200_cuda_fail(nullptr, e, "cudaStreamCreate", __FILE__, __LINE__);
     }
+    e = cudaEventCreateWithFlags(&c->ev_fifo, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        cudaStreamDestroy(c->stream);
+        delete c;
+        return nb200_cuda_fail(nullptr, e, "cudaEventCreate", __FILE__, __LINE__);
+    }
+    c->fifo = getenv("NB200_NO_FIFO") == nullptr;   // developer switch: let the passes of different batches time-slice
     *out = c;
     return NB200_OK;
 }
@@ -127,6 +147,7 @@ int nb200_ctx_destroy(nb200_ctx *c)
                       &r.alphas,  &r.jitter,   &r.occ_win, &r.nuc_win, &c->s0,     &c->s1,    &c->s2,       &c->s3,
                       &c->s4,     &c->flush,   &r.vp_pair, &r.vp_one, &r.vp_pair32, &r.vp_one32};
     for (auto b : bufs) b->release();
+    if (c->ev_fifo) cudaEventDestroy(c->ev_fifo);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return NB200_OK;

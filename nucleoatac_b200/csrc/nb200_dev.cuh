@@ -397,6 +397,28 @@ static __global__ void __launch_bounds__(SM_THREADS) k_smooth_same(SmoothTracks 
 }
 
 // ---------------------------------------------------------------------------------------------
+// float64 -> float32 conversion of up to 8 packed tracks in one launch (the *_download32 staging): grid-stride over
+// quads, 2 x 16-byte loads and one 16-byte store per thread and step; blockIdx.y = track.
+// ---------------------------------------------------------------------------------------------
+struct Pack32Args {
+    const double *src[8];
+    float *dst[8];
+    int64_t n;
+};
+static __global__ void __launch_bounds__(256) k_pack_f32(Pack32Args a)
+{
+    const double *__restrict__ src = a.src[blockIdx.y];
+    float *__restrict__ dst = a.dst[blockIdx.y];
+    const int64_t nq = a.n >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
+        const double2 u = reinterpret_cast<const double2 *>(src)[2 * q], v = reinterpret_cast<const double2 *>(src)[2 * q + 1];
+        reinterpret_cast<float4 *>(dst)[q] = make_float4((float)u.x, (float)u.y, (float)v.x, (float)v.y);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) dst[4 * nq + threadIdx.x] = (float)src[4 * nq + threadIdx.x];
+}
+
+// ---------------------------------------------------------------------------------------------
 // K2: InsertionBiasTrack.computeBias, pyatac/bias.py:85-92 + seq.py:37-45.
 //   b[p] = sum_j logPWM[nuc(seq[p - up + j]), j]   (non-ACGT contributes 0: all-zero one-hot column)
 // written as E[p] = exp(b[p]) and / or b[p].  grid (tiles, chunks); block 256; the sequence tile is

@@ -852,6 +852,7 @@ int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
     if (r.v_upper > NB200_MAX_UPPER) return nb200_fail(ctx, NB200_ERR_ARG, "VMat upper > %d unsupported", NB200_MAX_UPPER);
     NB_CUDA(ctx, cudaSetDevice(ctx->device));
     NB_CUDA(ctx, cudaStreamWaitEvent(b->stream, b->ev_copied_nuc, 0));   // a download of the previous pass may still read the arrays
+    NB_CHECK(nb200_fifo_enter(ctx, b->stream));                          // passes run first-in first-out across batches
     const int n = b->n_chunks;
     const int W = r.v_cols, w = r.v_w, lv = r.v_lower, uv = r.v_upper;
     if (b->min_len < p.smooth_len)
@@ -1158,6 +1159,7 @@ int nb200_nuc_run(nb200_ctx *ctx, nb200_dbatch *b)
         k_nuc_reduce<<<n, 256, 0, b->stream>>>(a);
         NB_LAUNCH_CHECK(ctx);
     }
+    NB_CHECK(nb200_fifo_leave(ctx, b->stream));
     b->nuc_done = true;
     return NB200_OK;
 }
@@ -1169,30 +1171,52 @@ static int d2h(nb200_ctx *ctx, nb200_dbatch *b, void *dst, const DevBuf &src, si
     return NB200_OK;
 }
 
-int nb200_nuc_download(nb200_ctx *ctx, nb200_dbatch *b, const nb200_nuc_out *o)
+}  // extern "C"
+
+template <typename T, typename Out>
+static int nuc_download_impl(nb200_ctx *ctx, nb200_dbatch *b, const Out *o, const char *who)
 {
-    if (!ctx || !b || !o) return nb200_fail(ctx, NB200_ERR_ARG, "nb200_nuc_download: NULL argument");
-    if (!b->nuc_done) return nb200_fail(ctx, NB200_ERR_STATE, "nb200_nuc_download: nb200_nuc_run has not been called on this batch");
-    const size_t tb = sizeof(double) * (size_t)b->total_len;
+    if (!ctx || !b || !o) return nb200_fail(ctx, NB200_ERR_ARG, "%s: NULL argument", who);
+    if (!b->nuc_done) return nb200_fail(ctx, NB200_ERR_STATE, "%s: nb200_nuc_run has not been called on this batch", who);
+    const size_t tl = (size_t)b->total_len, tb = sizeof(T) * tl;
     const int n = b->n_chunks;
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
     NB_CUDA(ctx, cudaEventRecord(b->ev_pass, b->stream));            // copies start once the pass has finished ...
     NB_CUDA(ctx, cudaStreamWaitEvent(b->copy_stream, b->ev_pass, 0));
     struct Copied {                                                  // ... and the next pass over these arrays waits for them
         nb200_dbatch *b;
         ~Copied() { cudaEventRecord(b->ev_copied_nuc, b->copy_stream); }
     } copied{b};
-    NB_CHECK(d2h(ctx, b, o->nuc_signal, b->n_signal, tb));
-    NB_CHECK(d2h(ctx, b, o->background, b->n_bg, tb));
-    NB_CHECK(d2h(ctx, b, o->norm_signal, b->n_norm, tb));
-    NB_CHECK(d2h(ctx, b, o->smoothed, b->n_smooth, tb));
-    NB_CHECK(d2h(ctx, b, o->nuc_cov, b->n_nuc_cov, tb));
-    NB_CHECK(d2h(ctx, b, o->nfr_cov, b->n_nfr_cov, tb));
+    T *host[6] = {o->nuc_signal, o->background, o->norm_signal, o->smoothed, o->nuc_cov, o->nfr_cov};
+    const DevBuf *dev[6] = {&b->n_signal, &b->n_bg, &b->n_norm, &b->n_smooth, &b->n_nuc_cov, &b->n_nfr_cov};
+    if (sizeof(T) == sizeof(double)) {
+        for (int t = 0; t < 6; t++) NB_CHECK(d2h(ctx, b, host[t], *dev[t], tb));
+    } else {   // float32 tracks: converted on the device (k_pack_f32 on the copy stream, after the pass), then copied
+        Pack32Args pa;
+        int nt = 0, which[6];
+        for (int t = 0; t < 6; t++)
+            if (host[t]) which[nt++] = t;
+        if (nt && tl) {
+            const size_t slab = (tl + 3) & ~(size_t)3;
+            NB_CUDA(ctx, b->pack32_nuc.reserve(sizeof(float) * slab * nt));
+            for (int k = 0; k < nt; k++) {
+                pa.src[k] = dev[which[k]]->template as<double>();
+                pa.dst[k] = b->pack32_nuc.as<float>() + slab * k;
+            }
+            pa.n = (int64_t)tl;
+            ProfScope ps(ctx, b->copy_stream, "k_pack_f32");
+            k_pack_f32<<<dim3((unsigned)std::min<int64_t>(div_up64((int64_t)tl, 4 * 256), ctx->sm_count * 8), nt), 256, 0, b->copy_stream>>>(pa);
+            NB_LAUNCH_CHECK(ctx);
+        }
+        for (int k = 0; k < nt; k++)
+            NB_CUDA(ctx, cudaMemcpyAsync(host[which[k]], pa.dst[k], tb, cudaMemcpyDeviceToHost, b->copy_stream));
+    }
     NB_CHECK(d2h(ctx, b, o->cand_count, b->n_cand_count, sizeof(int32_t) * n));
     if (o->cand_pos) {
-        if (!o->cand_off) return nb200_fail(ctx, NB200_ERR_ARG, "nb200_nuc_download: cand_off is required with cand_pos");
+        if (!o->cand_off) return nb200_fail(ctx, NB200_ERR_ARG, "%s: cand_off is required with cand_pos", who);
         for (int c = 0; c <= n; c++)
             if (o->cand_off[c] != b->h_ncand_off[c])
-                return nb200_fail(ctx, NB200_ERR_CAPACITY, "nb200_nuc_download: cand_off must equal len/redundant_sep+2 capacities (chunk %d)", c);
+                return nb200_fail(ctx, NB200_ERR_CAPACITY, "%s: cand_off must equal len/redundant_sep+2 capacities (chunk %d)", who, c);
         const size_t nc = (size_t)b->h_ncand_off[n];
         NB_CHECK(d2h(ctx, b, o->cand_pos, b->n_cand_pos, sizeof(int32_t) * nc));
         NB_CHECK(d2h(ctx, b, o->cand_flag, b->n_cand_flag, sizeof(int32_t) * nc));
@@ -1207,10 +1231,11 @@ int nb200_nuc_download(nb200_ctx *ctx, nb200_dbatch *b, const nb200_nuc_out *o)
     return NB200_OK;
 }
 
-int64_t nb200_nuc_d2h_bytes(nb200_dbatch *b, const nb200_nuc_out *o)
+template <typename Out>
+static int64_t nuc_d2h_bytes_impl(nb200_dbatch *b, const Out *o, int64_t elem)
 {
     if (!b || !o) return 0;
-    const int64_t tb = 8 * b->total_len;
+    const int64_t tb = elem * b->total_len;
     int64_t s = 0;
     const void *tr[] = {o->nuc_signal, o->background, o->norm_signal, o->smoothed, o->nuc_cov, o->nfr_cov};
     for (auto p : tr)
@@ -1226,5 +1251,18 @@ int64_t nb200_nuc_d2h_bytes(nb200_dbatch *b, const nb200_nuc_out *o)
     }
     return s;
 }
+
+extern "C" {
+
+int nb200_nuc_download(nb200_ctx *ctx, nb200_dbatch *b, const nb200_nuc_out *o)
+{
+    return nuc_download_impl<double>(ctx, b, o, "nb200_nuc_download");
+}
+int nb200_nuc_download32(nb200_ctx *ctx, nb200_dbatch *b, const nb200_nuc_out32 *o)
+{
+    return nuc_download_impl<float>(ctx, b, o, "nb200_nuc_download32");
+}
+int64_t nb200_nuc_d2h_bytes(nb200_dbatch *b, const nb200_nuc_out *o) { return nuc_d2h_bytes_impl(b, o, 8); }
+int64_t nb200_nuc_d2h_bytes32(nb200_dbatch *b, const nb200_nuc_out32 *o) { return nuc_d2h_bytes_impl(b, o, 4); }
 
 }  // extern "C"

@@ -25,6 +25,8 @@ struct OccMleArgs {
     const double *E, *cn, *cf, *pn, *pf, *alphas;
     const double *wsn, *wsf;   // per window: sums of cn / cf over its 2*flank+1 columns (k_occ_winsums); window k of chunk c at out_off[c]/step + c + k
     double *vals, *lower, *upper_b;
+    double *wv;            // per-window occ / lower / upper (3 slabs of wv_stride), or null
+    int64_t wv_stride;
     int pwm_up, upper, flank, step, halfstep, csc_pad, n_alpha, use_bias;
     int pn_has_zero, pf_has_zero, both_zero;
     double cutoff, sn_nobias, sf_nobias;
@@ -268,6 +270,12 @@ __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle(OccMleArgs a)
         }
     }
     if (valid) {
+        if (r == 0 && a.wv) {   // per-window values (the block smoother's input)
+            const int64_t wo = oo / a.step + c + wi;
+            a.wv[wo] = occ;
+            a.wv[a.wv_stride + wo] = lo;
+            a.wv[2 * a.wv_stride + wo] = hi;
+        }
         const int left = t - a.halfstep, right = min(t + a.halfstep + 1, L);
         for (int x = left + r; x < right; x += 8) {
             a.vals[oo + x] = occ;
@@ -283,6 +291,568 @@ __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle(OccMleArgs a)
     }
     __syncwarp();
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Guarded search over the alpha grid (the default occupancy kernel).
+//
+// log L(alpha) = sum_f log(q_f + alpha (p_f - q_f)) is concave in alpha, so (a) the first maximum over the grid lies strictly
+// between the neighbours of the best point of any coarser sub-grid and (b) the grid points passing the likelihood-ratio
+// test 2 (max - ll) < cutoff form one interval around it.  Three rounds of 16 grid points per window (8 lanes x 2) replace
+// the scan of all 101:
+//   round 1  16 evenly spaced points c_0 .. c_15 (spacing <= 8)
+//   round 2  every grid point strictly between the neighbours of the best coarse point -> the first maximum, exactly as
+//            np.argmax over the whole grid finds it
+//   round 3  the grid points inside the two coarse intervals in which the pass / fail status changes -> both bounds
+// Every comparison is the exact (exponent, mantissa) comparison of k_occ_mle on identically computed products, so the
+// result is the full scan's whenever the computed values are ordered like the true ones.  That can only fail at ties at
+// rounding level; a window whose decisive values come within 1e-11 (relative) of each other -- the best coarse point
+// against its neighbours, any evaluated point against the interval threshold -- is re-scored by a scan of the whole grid
+// (the warp does it together; windows without fragments never tie: they are NaN by Occupancy.py:141).
+// The window's fragments are prepared once (scaled p, q, p - q) into a per-window shared-memory cache; fragments beyond
+// MLS_CAP are prepared again in every round.
+#ifndef MLS_CAP
+#define MLS_CAP 48
+#endif
+#define MLS_GROUP_STRIDE (2 * MLS_CAP + 2)
+#define MLS_TIE 1e-11
+struct MleKey {   // canonical likelihood: 2^e * m, m in [1, 2); e = INT_MIN: -inf (dead grid point, zero / NaN product)
+    int e;
+    double m;
+};
+__device__ __forceinline__ bool key_gt(const MleKey &a, const MleKey &b) { return a.e > b.e || (a.e == b.e && a.m > b.m); }
+// a >= b * (1 - tol): the two likelihoods are equal at rounding level or a is the larger one
+__device__ __forceinline__ bool key_close_or_above(const MleKey &a, const MleKey &b, double tol)
+{
+    if (b.e == INT_MIN) return true;
+    if (a.e == INT_MIN) return false;
+    if (a.e > b.e) return true;
+    if (a.e == b.e) return a.m >= b.m * (1.0 - tol);
+    if (a.e == b.e - 1) return a.m * 0.5 >= b.m * (1.0 - tol);
+    return false;
+}
+__device__ __forceinline__ bool key_close(const MleKey &a, const MleKey &b, double tol)
+{
+    return key_close_or_above(a, b, tol) && key_close_or_above(b, a, tol);
+}
+
+template <int LB>
+__global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle_search(OccMleArgs a)
+{
+    extern __shared__ __align__(16) double sm_mle[];  // pn[upper], pf[upper] | per window group: (d, q)[MLS_CAP], (0, p)[MLS_CAP]
+    __shared__ double s_d[MLE_WARPS][32], s_q[MLE_WARPS][32], s_p[MLE_WARPS][32];   // overflow fragments (index >= MLS_CAP)
+    const int up2 = (a.upper + 1) & ~1;
+    double *s_pn = sm_mle, *s_pf = sm_mle + up2;
+    for (int i = threadIdx.x; i < a.upper; i += blockDim.x) {
+        s_pn[i] = a.pn[i];
+        s_pf[i] = a.pf[i];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3, r = lane & 7;
+    // group regions are 2 * MLS_CAP + 2 entries apart (32 bytes modulo a 128-byte row) and the (0, p) copy sits one entry
+    // past MLS_CAP: the four groups of a warp and the two arrays read eight different 16-byte bank slots
+    double2 *c_dq = reinterpret_cast<double2 *>(sm_mle + 2 * up2) + (size_t)(warp * MLE_GROUPS + g) * MLS_GROUP_STRIDE;
+    double2 *c_0p = c_dq + MLS_CAP + 1;
+    const int c = blockIdx.y;
+    const int64_t oo = a.out_off[c];
+    const int L = (int)(a.out_off[c + 1] - oo);
+    const int nwin = (L - a.halfstep + a.step - 1) / a.step;
+    const int32_t *cp = a.col_ptr + a.col_off[c];
+    const int2 *en = a.ent + a.frag_off[c];
+    const int NA = a.n_alpha;
+    const int last = NA - 1;
+    const unsigned gmask = 0xffu << (8 * g);
+  for (int it = 0; it < MLE_ITERS; it++) {
+    const int wbase = ((blockIdx.x * MLE_ITERS + it) * MLE_WARPS + warp) * MLE_GROUPS;
+    if (wbase >= nwin) break;
+    const int wi = wbase + g;
+    const bool valid = wi < nwin;
+    const int t = a.halfstep + wi * a.step;
+    const int e0 = valid ? cp[t - a.flank + a.csc_pad] : 0, e1 = valid ? cp[t + a.flank + 1 + a.csc_pad] : 0;
+    const int n = e1 - e0;
+    int nmax = n;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(NB_FULL, nmax, o));
+    double SN = a.sn_nobias, SF = a.sf_nobias;
+    if (a.use_bias && valid) {
+        const int64_t wo = oo / a.step + c + wi;
+        SN = a.wsn[wo];
+        SF = a.wsf[wo];
+    }
+    const double rSN = 1.0 / SN, rSF = 1.0 / SF;
+    // lane (g, r) prepares fragment idx of window g: nuc_probs / sum, nfr_probs / sum (Occupancy.py:106-109), the pair
+    // scaled by a power of two so that max(p, q) is in [1, 2) (exact, constant in alpha); padding fragments are the factor 1
+    auto prep = [&](int idx, double &pv, double &qv) {
+        pv = 1.0;
+        qv = 1.0;
+        if (idx < n) {
+            const int sz = en[e0 + idx].y;
+            pv = s_pn[sz] * rSN;
+            qv = s_pf[sz] * rSF;
+            const long long mb = __double_as_longlong(fmax(pv, qv));
+            const int e2 = (int)((mb >> 52) & 0x7ff);
+            if (e2 > 0 && e2 < 0x7fe) {
+                const double sc = __longlong_as_double((long long)(2046 - e2) << 52);
+                pv *= sc;
+                qv *= sc;
+            }
+        }
+    };
+    const int ncache = min((nmax + 7) & ~7, MLS_CAP);
+    __syncwarp();   // the previous iteration's readers of the cache are done
+    for (int base = 0; base < ncache; base += 8) {
+        double pv, qv;
+        prep(base + r, pv, qv);
+        c_dq[base + r] = make_double2(pv - qv, qv);   // alpha p + (1 - alpha) q = q + alpha (p - q): one FMA per (fragment, alpha)
+        c_0p[base + r] = make_double2(0.0, pv);       // alpha == 1 takes p itself (q + (p - q) would lose p when p << q)
+    }
+    __syncwarp();
+    // ---- one round: this lane's two grid points i0, i1 (-1: none) -> canonical keys
+    // may_one (warp uniform): some lane of the warp may hold alpha == 1, which reads the (0, p) copy instead of (d, q);
+    // only the coarse round and the full scan touch the last grid point, the other rounds share one load per fragment
+    auto eval2 = [&](int i0, int i1, MleKey &k0, MleKey &k1, const bool may_one) {
+        const double al0 = (i0 >= 0) ? a.alphas[i0] : 0.5, al1 = (i1 >= 0) ? a.alphas[i1] : 0.5;
+        const bool one0 = al0 == 1.0, one1 = al1 == 1.0;
+        const double2 *src0 = one0 ? c_0p : c_dq, *src1 = one1 ? c_0p : c_dq;
+        double m0 = 1.0, m1 = 1.0;
+        int x0 = 0, x1 = 0;
+        auto renorm = [](double &m, int &x) {
+            const long long bits = __double_as_longlong(m);
+            const int e2 = (int)((bits >> 52) & 0x7ff);
+            if (e2 != 0 && e2 != 0x7ff) {
+                x += e2 - 1023;
+                m = __longlong_as_double(bits - ((long long)(e2 - 1023) << 52));
+            }
+        };
+        if (may_one) {
+            for (int j0 = 0; j0 < ncache; j0 += 8) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const double2 u = src0[j0 + j], v = src1[j0 + j];
+                    m0 *= fma(al0, u.x, u.y);
+                    m1 *= fma(al1, v.x, v.y);
+                }
+                if ((j0 & 24) == 24) {   // every 32 factors (each in (2^-7, 2) away from the grid ends)
+                    renorm(m0, x0);
+                    renorm(m1, x1);
+                }
+            }
+        } else {
+            for (int j0 = 0; j0 < ncache; j0 += 8) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const double2 u = c_dq[j0 + j];
+                    m0 *= fma(al0, u.x, u.y);
+                    m1 *= fma(al1, u.x, u.y);
+                }
+                if ((j0 & 24) == 24) {
+                    renorm(m0, x0);
+                    renorm(m1, x1);
+                }
+            }
+        }
+        for (int base = MLS_CAP; base < nmax; base += 8) {   // windows with more fragments than the cache holds
+            double pv, qv;
+            prep(base + r, pv, qv);
+            s_d[warp][lane] = pv - qv;
+            s_q[warp][lane] = qv;
+            s_p[warp][lane] = pv;
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const double dj = s_d[warp][8 * g + j], qj = s_q[warp][8 * g + j], pj = s_p[warp][8 * g + j];
+                m0 *= one0 ? pj : fma(al0, dj, qj);
+                m1 *= one1 ? pj : fma(al1, dj, qj);
+            }
+            __syncwarp();
+            if ((base & 24) == 24) {
+                renorm(m0, x0);
+                renorm(m1, x1);
+            }
+        }
+        auto canon = [&](int i, double al, double m, int x) {
+            MleKey k;
+            const bool dead = (i < 0) || a.both_zero || (al == 0.0 && a.pf_has_zero) || (al == 1.0 && a.pn_has_zero);
+            const bool alive = !dead && m > 0.0;   // zero / NaN products: log = -inf / NaN -> -inf (Occupancy.py:112-114)
+            if (alive && m < 2.2250738585072014e-308) {   // subnormal: make it normal first
+                m *= 18446744073709551616.0;             // 2^64
+                x -= 64;
+            }
+            const long long bits = __double_as_longlong(m);
+            const int e2 = (int)((bits >> 52) & 0x7ff);
+            k.e = alive ? x + e2 - 1023 : INT_MIN;
+            k.m = alive ? __longlong_as_double((bits & 0x800fffffffffffffLL) | 0x3ff0000000000000LL) : 0.0;
+            return k;
+        };
+        k0 = canon(i0, al0, m0, x0);
+        k1 = canon(i1, al1, m1, x1);
+    };
+    // first maximum over the group: larger key, ties to the smaller grid index
+    auto group_best = [&](MleKey &bk, int &bi) {
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            MleKey ok;
+            ok.e = __shfl_xor_sync(NB_FULL, bk.e, o);
+            ok.m = __shfl_xor_sync(NB_FULL, bk.m, o);
+            const int oi = __shfl_xor_sync(NB_FULL, bi, o);
+            if (key_gt(ok, bk) || (ok.e == bk.e && ok.m == bk.m && oi < bi)) {
+                bk = ok;
+                bi = oi;
+            }
+        }
+    };
+    auto take = [&](MleKey &bk, int &bi, const MleKey &k, int i) {   // i >= 0 evaluated
+        if (i >= 0 && (bi < 0 || key_gt(k, bk) || (k.e == bk.e && k.m == bk.m && i < bi))) {
+            bk = k;
+            bi = i;
+        }
+    };
+    const int BIG = 1 << 30;
+    // ---- round 1: coarse points c_j = (j * last) / 15, j = r and r + 8
+    const int j0c = r, j1c = r + 8;
+    const int ci0 = (j0c * last) / 15, ci1 = (j1c * last) / 15;
+    MleKey ck0, ck1;
+    eval2(ci0, ci1, ck0, ck1, true);
+    MleKey bk;
+    bk.e = INT_MIN;
+    bk.m = 0.0;
+    int bi = -1;
+    take(bk, bi, ck0, ci0);
+    take(bk, bi, ck1, ci1);
+    if (bi < 0) bi = BIG;
+    group_best(bk, bi);
+    // coarse ordinal of the best point and the keys of its coarse neighbours (lane j & 7 holds ordinal j in slot j >> 3)
+    int bj = (ci0 == bi) ? j0c : ((ci1 == bi) ? j1c : -1);
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) bj = max(bj, __shfl_xor_sync(NB_FULL, bj, o));
+    auto coarse_key = [&](int j, MleKey &k, int &idx) {   // every lane of the group calls it with the same j in [0, 15]
+        const int src = (lane & 24) | (j & 7);
+        const int e_lo = __shfl_sync(NB_FULL, ck0.e, src), e_hi = __shfl_sync(NB_FULL, ck1.e, src);
+        const double m_lo = __shfl_sync(NB_FULL, ck0.m, src), m_hi = __shfl_sync(NB_FULL, ck1.m, src);
+        k.e = (j >> 3) ? e_hi : e_lo;
+        k.m = (j >> 3) ? m_hi : m_lo;
+        idx = (j * last) / 15;
+    };
+    bool tie = false;
+    const bool all_dead = (bk.e == INT_MIN);
+    const int bjc = max(bj, 0);
+    MleKey kl, kr;
+    int il, ir;
+    coarse_key(max(bjc - 1, 0), kl, il);
+    coarse_key(min(bjc + 1, 15), kr, ir);
+    int LO = (bjc > 0) ? il : 0, HI = (bjc < 15) ? ir : last;     // evaluated contiguous range after round 2: [LO, HI]
+    if (!all_dead) {
+        if (bjc > 0 && il != bi && key_close_or_above(kl, bk, MLS_TIE)) tie = true;
+        if (bjc < 15 && ir != bi && key_close_or_above(kr, bk, MLS_TIE)) tie = true;
+    }
+    // ---- round 2: the unknown points of (LO, HI): every index strictly inside except the best coarse point itself
+    // (coarse spacing <= 8: at most 14 of them)
+    MleKey rk0, rk1;
+    int ri0 = -1, ri1 = -1;
+    {
+        const int lo_u = LO + ((bjc > 0) ? 1 : 0), hi_u = HI - ((bjc < 15) ? 1 : 0);   // the ends are coarse points unless at the grid ends
+        auto kth = [&](int k) {   // k-th unknown index, -1 past the end
+            int idx = lo_u + k;
+            if (idx >= bi) idx++;                       // skip the best coarse point
+            return (idx <= hi_u) ? idx : -1;
+        };
+        ri0 = kth(r);
+        ri1 = kth(r + 8);
+        if (all_dead) ri0 = ri1 = -1;
+        eval2(ri0, ri1, rk0, rk1, false);
+        int nbi = bi;
+        MleKey nbk = bk;
+        take(nbk, nbi, rk0, ri0);
+        take(nbk, nbi, rk1, ri1);
+        group_best(nbk, nbi);
+        bk = nbk;
+        bi = nbi;
+    }
+    // ---- threshold = max * exp(-cutoff / 2), canonical
+    MleKey th;
+    th.e = INT_MIN;
+    th.m = 0.0;
+    bool none = all_dead || !(a.thr_m == a.thr_m);
+    if (!none) {
+        if (a.thr_zero) {
+            th.e = INT_MIN + 1;
+        } else {
+            th.m = bk.m * a.thr_m;
+            th.e = bk.e + a.thr_e;
+            if (th.m >= 2.0) {
+                th.m *= 0.5;
+                th.e += 1;
+            }
+        }
+    }
+    auto passes = [&](const MleKey &k) { return !none && key_gt(k, th); };
+    auto near_thr = [&](const MleKey &k, int i) { return i >= 0 && !none && !a.thr_zero && k.e != INT_MIN && key_close(k, th, MLS_TIE); };
+    // pass / fail over everything evaluated so far: the smallest / largest passing index, and per coarse ordinal a bit
+    int okmin = BIG, okmax = -1;
+    auto note = [&](const MleKey &k, int i) {
+        if (i >= 0 && passes(k)) {
+            okmin = min(okmin, i);
+            okmax = max(okmax, i);
+        }
+        if (near_thr(k, i)) tie = true;
+    };
+    note(ck0, ci0);
+    note(ck1, ci1);
+    note(rk0, ri0);
+    note(rk1, ri1);
+    const unsigned pass_lo = __ballot_sync(NB_FULL, passes(ck0)) >> (8 * g) & 0xffu;    // coarse ordinals 0..7
+    const unsigned pass_hi = __ballot_sync(NB_FULL, passes(ck1)) >> (8 * g) & 0xffu;    // coarse ordinals 8..15
+    const unsigned cpass = pass_lo | (pass_hi << 8);
+    // ---- round 3: the coarse intervals in which the status changes.  Left: the last failing coarse point below the
+    // evaluated range [LO, HI] (if LO itself passes); right: the first failing coarse point above it (if HI passes).
+    int li0 = -1, li1 = -1;
+    {
+        int l_from = -1, l_to = -2, r_from = -1, r_to = -2;   // unknown index ranges [from, to]
+        if (!none && bjc > 1) {
+            const int jlo = bjc - 1;                     // ordinal of LO
+            if ((cpass >> jlo) & 1) {                    // LO passes: look further left
+                int jf = -1;
+                for (int j = jlo - 1; j >= 0; j--)
+                    if (!((cpass >> j) & 1)) {
+                        jf = j;
+                        break;
+                    }
+                if (jf >= 0) {
+                    l_from = (jf * last) / 15 + 1;
+                    l_to = ((jf + 1) * last) / 15 - 1;
+                }
+            }
+        }
+        if (!none && bjc < 14) {
+            const int jhi = bjc + 1;
+            if ((cpass >> jhi) & 1) {
+                int jf = -1;
+                for (int j = jhi + 1; j <= 15; j++)
+                    if (!((cpass >> j) & 1)) {
+                        jf = j;
+                        break;
+                    }
+                if (jf >= 0) {
+                    r_from = ((jf - 1) * last) / 15 + 1;
+                    r_to = (jf * last) / 15 - 1;
+                }
+            }
+        }
+        // slots 0..7 (first grid point of a lane) serve the left interval, 8..15 the right one (each holds <= 7 points)
+        li0 = (l_from + r <= l_to) ? l_from + r : -1;
+        li1 = (r_from + r <= r_to) ? r_from + r : -1;
+        if (__ballot_sync(NB_FULL, li0 >= 0 || li1 >= 0)) {   // some window of the warp has an interval left to resolve
+            MleKey k0, k1;
+            eval2(li0, li1, k0, k1, false);
+            note(k0, li0);
+            note(k1, li1);
+        }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        okmin = min(okmin, __shfl_xor_sync(NB_FULL, okmin, o));
+        okmax = max(okmax, __shfl_xor_sync(NB_FULL, okmax, o));
+    }
+    tie = (__ballot_sync(NB_FULL, tie && valid && n > 0) & gmask) != 0;
+    // ---- windows with rounding-level ties: scan of the whole grid, the warp together (rare)
+    if (__ballot_sync(NB_FULL, tie)) {
+        MleKey fk;
+        fk.e = INT_MIN;
+        fk.m = 0.0;
+        int fi = -1;
+        for (int b0 = 0; b0 < NA; b0 += 16) {
+            const int i0 = (b0 + r < NA) ? b0 + r : -1, i1 = (b0 + 8 + r < NA) ? b0 + 8 + r : -1;
+            MleKey k0, k1;
+            eval2(i0, i1, k0, k1, true);
+            take(fk, fi, k0, i0);
+            take(fk, fi, k1, i1);
+        }
+        if (fi < 0) fi = BIG;
+        group_best(fk, fi);
+        MleKey fth;
+        fth.e = INT_MIN;
+        fth.m = 0.0;
+        const bool fnone = (fk.e == INT_MIN) || !(a.thr_m == a.thr_m);
+        if (!fnone) {
+            if (a.thr_zero) {
+                fth.e = INT_MIN + 1;
+            } else {
+                fth.m = fk.m * a.thr_m;
+                fth.e = fk.e + a.thr_e;
+                if (fth.m >= 2.0) {
+                    fth.m *= 0.5;
+                    fth.e += 1;
+                }
+            }
+        }
+        int fmin = BIG, fmax = -1;
+        for (int b0 = 0; b0 < NA; b0 += 16) {
+            const int i0 = (b0 + r < NA) ? b0 + r : -1, i1 = (b0 + 8 + r < NA) ? b0 + 8 + r : -1;
+            MleKey k0, k1;
+            eval2(i0, i1, k0, k1, true);
+            if (i0 >= 0 && !fnone && key_gt(k0, fth)) {
+                fmin = min(fmin, i0);
+                fmax = max(fmax, i0);
+            }
+            if (i1 >= 0 && !fnone && key_gt(k1, fth)) {
+                fmin = min(fmin, i1);
+                fmax = max(fmax, i1);
+            }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            fmin = min(fmin, __shfl_xor_sync(NB_FULL, fmin, o));
+            fmax = max(fmax, __shfl_xor_sync(NB_FULL, fmax, o));
+        }
+        if (tie) {
+            bi = fi;
+            okmin = fmin;
+            okmax = fmax;
+        }
+    }
+    double occ = nb_nan(), lo = nb_nan(), hi = nb_nan();
+    if (n > 0 && okmax >= 0 && bi >= 0 && bi < NA) {  // Occupancy.py:141 `if sum(new_inserts)>0`
+        occ = a.alphas[bi];
+        lo = a.alphas[okmin];
+        hi = a.alphas[okmax];
+    }
+    if (valid) {
+        if (r == 0 && a.wv) {   // per-window values (the block smoother's input): window wi of chunk c at oo / step + c + wi
+            const int64_t wo = oo / a.step + c + wi;
+            a.wv[wo] = occ;
+            a.wv[a.wv_stride + wo] = lo;
+            a.wv[2 * a.wv_stride + wo] = hi;
+        }
+        const int left = t - a.halfstep, right = min(t + a.halfstep + 1, L);
+        for (int x = left + r; x < right; x += 8) {
+            a.vals[oo + x] = occ;
+            a.lower[oo + x] = lo;
+            a.upper_b[oo + x] = hi;
+        }
+        if (wi == nwin - 1)  // positions past the last window stay NaN (np.ones(n)*nan, Occupancy.py:133-135)
+            for (int x = right + r; x < L; x += 8) {
+                a.vals[oo + x] = nb_nan();
+                a.lower[oo + x] = nb_nan();
+                a.upper_b[oo + x] = nb_nan();
+            }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// OccupancyTrack.makeSmoothed (Occupancy.py:147-153 -> pyatac/utils.py:23-52, mode 'same', norm) on the per-window values.
+// The unsmoothed tracks are constant over blocks of `step` positions (block k = window k covers [k S, k S + S), Occupancy.py
+// :142-146), so the 2 flank + 1 taps of an output collapse to ~(2 flank + 1) / S + 1 block taps:
+//     out[n] = sum_b V[b] T[n - b S + h] / sum_b I[b] T[n - b S + h],     T[i] = sum_{t < S} w[i - t]
+// with V[b] the window's value (0 where it is NaN), I[b] its presence (0 for NaN windows and for blocks off the chunk, which
+// is utils.smooth's zero padding) and h = (wlen - 1) / 2.  A thread owns the S outputs of one block and the three tracks
+// (they are NaN together); block values are staged in shared memory as (V0, V1), (V2, I) pairs.  The only case the block
+// form does not cover -- a last window cut short by the chunk end -- goes tap by tap for the outputs that reach it.
+#define SB_THREADS 128
+template <int S>
+__global__ void __launch_bounds__(SB_THREADS) k_occ_smooth_blocks(const double *__restrict__ wv, int64_t wv_stride,
+                                                                  const int64_t *__restrict__ out_off, const double *__restrict__ win,
+                                                                  int wlen, int halfstep, double *__restrict__ o0, double *__restrict__ o1,
+                                                                  double *__restrict__ o2)
+{
+    extern __shared__ __align__(16) double sm_sb[];
+    const int h = (wlen - 1) / 2;
+    const int R = (h + S - 1) / S;                   // block reach on either side
+    const int nT = wlen + S - 1;
+    const int padL = R * S - h;                      // T is stored from index -padL on: no bounds checks in the tap loop
+    const int nTs = (2 * R + 1) * S;                 // stored entries: indices h - R S .. h + R S + S - 1
+    const int nTp = (nTs + 1) & ~1;
+    double *s_T = sm_sb;                             // [nTp], s_T[i + padL] = T[i]
+    double2 *s_v = reinterpret_cast<double2 *>(sm_sb + nTp);   // [(SB_THREADS + 2 R)][2]: (V0, V1), (V2, I)
+    const int c = blockIdx.y;
+    const int64_t oo = out_off[c];
+    const int L = (int)(out_off[c + 1] - oo);
+    const int nwin = (L - halfstep + S - 1) / S;
+    const int nblk = (L + S - 1) / S;                // blocks that hold an output
+    const int bt0 = blockIdx.x * SB_THREADS;
+    if (bt0 >= nblk) return;
+    const int64_t wo0 = oo / S + c;                  // window 0 of this chunk
+    for (int k = threadIdx.x; k < nTs; k += SB_THREADS) {
+        const int i = k - padL;
+        double t = 0.0;
+#pragma unroll
+        for (int u = 0; u < S; u++) {
+            const int m = i - u;
+            if (m >= 0 && m < wlen) t += win[m];
+        }
+        s_T[k] = t;
+    }
+    for (int i = threadIdx.x; i < SB_THREADS + 2 * R; i += SB_THREADS) {
+        const int b = bt0 - R + i;
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, pres = 0.0;
+        if (b >= 0 && b < nwin) {
+            v0 = wv[wo0 + b];
+            if (v0 == v0) {
+                v1 = wv[wv_stride + wo0 + b];
+                v2 = wv[2 * wv_stride + wo0 + b];
+                pres = 1.0;
+            } else
+                v0 = 0.0;
+        }
+        s_v[2 * i] = make_double2(v0, v1);
+        s_v[2 * i + 1] = make_double2(v2, pres);
+    }
+    __syncthreads();
+    const int b0 = bt0 + threadIdx.x;
+    if (b0 >= nblk) return;
+    const int n0 = b0 * S;
+    const bool partial = (int64_t)nwin * S > L;      // the last window's block is cut short by the chunk end
+    if (partial && b0 + R >= nwin - 1) {
+        for (int u = 0; u < S; u++) {
+            const int n = n0 + u;
+            if (n >= L) break;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, den = 0.0;
+            for (int m = 0; m < wlen; m++) {
+                const int j = n + h - m;
+                if (j < 0 || j >= L) continue;
+                const int b = j / S;
+                if (b >= nwin) continue;
+                const double v0 = wv[wo0 + b];
+                if (v0 != v0) continue;
+                const double w = win[m];
+                a0 = fma(w, v0, a0);
+                a1 = fma(w, wv[wv_stride + wo0 + b], a1);
+                a2 = fma(w, wv[2 * wv_stride + wo0 + b], a2);
+                den += w;
+            }
+            o0[oo + n] = (den == 0.0) ? nb_nan() : a0 / den;
+            o1[oo + n] = (den == 0.0) ? nb_nan() : a1 / den;
+            o2[oo + n] = (den == 0.0) ? nb_nan() : a2 / den;
+        }
+        return;
+    }
+    double a0[S], a1[S], a2[S], dn[S];
+#pragma unroll
+    for (int u = 0; u < S; u++) a0[u] = a1[u] = a2[u] = dn[u] = 0.0;
+    // block b0 + d contributes to output u through T[u - d S + h]; d runs over [-R, R]
+    for (int d = -R; d <= R; d++) {
+        const int i = threadIdx.x + R + d;
+        const double2 p = s_v[2 * i], q = s_v[2 * i + 1];
+        const double *Tb = s_T + (R - d) * S;         // T[h - d S + u] at Tb[u]
+#pragma unroll
+        for (int u = 0; u < S; u++) {
+            const double w = Tb[u];
+            a0[u] = fma(w, p.x, a0[u]);
+            a1[u] = fma(w, p.y, a1[u]);
+            a2[u] = fma(w, q.x, a2[u]);
+            dn[u] = fma(w, q.y, dn[u]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < S; u++) {
+        const int n = n0 + u;
+        if (n < L) {
+            const bool z = dn[u] == 0.0;   // smoothed_norm == 0 -> NaN (utils.py:49)
+            o0[oo + n] = z ? nb_nan() : a0[u] / dn[u];
+            o1[oo + n] = z ? nb_nan() : a1[u] / dn[u];
+            o2[oo + n] = z ? nb_nan() : a2[u] / dn[u];
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -438,6 +1008,7 @@ int nb200_occ_run(nb200_ctx *ctx, nb200_dbatch *b)
     if (p.upper > NB200_MAX_UPPER) return nb200_fail(ctx, NB200_ERR_ARG, "upper > %d unsupported", NB200_MAX_UPPER);
     NB_CUDA(ctx, cudaSetDevice(ctx->device));
     NB_CUDA(ctx, cudaStreamWaitEvent(b->stream, b->ev_copied_occ, 0));   // a download of the previous pass may still read the arrays
+    NB_CHECK(nb200_fifo_enter(ctx, b->stream));                          // passes run first-in first-out across batches
     const int n = b->n_chunks;
     const int window = 2 * p.flank + 1;
     const int halfstep = (p.step - 1) / 2;
@@ -571,10 +1142,22 @@ int nb200_occ_run(nb200_ctx *ctx, nb200_dbatch *b)
                                                             b->o_wsf.as<double>());
             NB_LAUNCH_CHECK(ctx);
         }
-        ProfScope ps(ctx, b->stream, "k_occ_mle");
+        // per-window values for the block smoother (3 slabs)
+        a.wv_stride = (int64_t)(tl / p.step + n + 2);
+        NB_CUDA(ctx, b->o_wv.reserve(sizeof(double) * 3 * (size_t)a.wv_stride));
+        a.wv = b->o_wv.as<double>();
+        const bool mle_full = getenv("NB200_MLE_FULL") != nullptr;   // developer switch: scan the whole grid for every window
+        const bool mle_search = !mle_full && r.n_alpha >= 17 && r.n_alpha <= 121;   // 3 rounds of 16 grid points need a coarse spacing <= 8
+        ProfScope ps(ctx, b->stream, mle_search ? "k_occ_mle_search" : "k_occ_mle");
         dim3 grid((unsigned)div_up64(max_win, MLE_WARPS * MLE_GROUPS * MLE_ITERS), n);
         static const int mle_lb = getenv("NB200_MLE_LB") ? atoi(getenv("NB200_MLE_LB")) : 4;
-        if (r.n_alpha <= 104) {
+        if (mle_search) {
+            const size_t smem_s = sizeof(double) * 2 * (size_t)((p.upper + 1) & ~1) + sizeof(double2) * (size_t)MLE_WARPS * MLE_GROUPS * MLS_GROUP_STRIDE;
+            static const int mls_lb = getenv("NB200_MLS_LB") ? atoi(getenv("NB200_MLS_LB")) : 4;
+            auto kern = mls_lb >= 6 ? k_occ_mle_search<6> : (mls_lb == 5 ? k_occ_mle_search<5> : k_occ_mle_search<4>);
+            if (smem_s > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+            kern<<<grid, MLE_WARPS * 32, smem_s, b->stream>>>(a);
+        } else if (r.n_alpha <= 104) {
             if (mle_lb >= 5)
                 k_occ_mle<13, 5><<<grid, MLE_WARPS * 32, smem, b->stream>>>(a);
             else
@@ -591,12 +1174,24 @@ int nb200_occ_run(nb200_ctx *ctx, nb200_dbatch *b)
         tr.out[0] = b->o_svals.as<double>();
         tr.out[1] = b->o_slower.as<double>();
         tr.out[2] = b->o_supper.as<double>();
-        size_t smem = smooth_same_smem(p.smooth_len);
-        if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_smooth_same, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ProfScope ps(ctx, b->stream, "k_smooth_same");
-        dim3 grid((unsigned)div_up64(b->max_len, SM_TILE), n, 3);
-        k_smooth_same<<<grid, SM_THREADS, smem, b->stream>>>(tr, b->d_out_off.as<int64_t>(), r.occ_win.as<double>(), p.smooth_len, 0);
-        NB_LAUNCH_CHECK(ctx);
+        const bool dense_smooth = getenv("NB200_OCC_SMOOTH_DENSE") != nullptr;   // developer switch: tap-by-tap smoothing
+        if (p.step == 5 && !dense_smooth) {   // block form on the per-window values (the default step)
+            const int R = ((p.smooth_len - 1) / 2 + 4) / 5;
+            const size_t smem = sizeof(double) * (size_t)(((2 * R + 1) * 5 + 1) & ~1) + sizeof(double2) * 2 * (size_t)(SB_THREADS + 2 * R);
+            if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_occ_smooth_blocks<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ProfScope ps(ctx, b->stream, "k_occ_smooth_blocks");
+            dim3 grid((unsigned)div_up64(div_up64(b->max_len, 5), SB_THREADS), n);
+            k_occ_smooth_blocks<5><<<grid, SB_THREADS, smem, b->stream>>>(b->o_wv.as<double>(), (int64_t)(tl / p.step + n + 2), b->d_out_off.as<int64_t>(),
+                                                                         r.occ_win.as<double>(), p.smooth_len, halfstep, tr.out[0], tr.out[1], tr.out[2]);
+            NB_LAUNCH_CHECK(ctx);
+        } else {
+            size_t smem = smooth_same_smem(p.smooth_len);
+            if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_smooth_same, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ProfScope ps(ctx, b->stream, "k_smooth_same");
+            dim3 grid((unsigned)div_up64(b->max_len, SM_TILE), n, 3);
+            k_smooth_same<<<grid, SM_THREADS, smem, b->stream>>>(tr, b->d_out_off.as<int64_t>(), r.occ_win.as<double>(), p.smooth_len, 0);
+            NB_LAUNCH_CHECK(ctx);
+        }
     }
     {
         OccPeakArgs a;
@@ -633,6 +1228,7 @@ int nb200_occ_run(nb200_ctx *ctx, nb200_dbatch *b)
         NB_LAUNCH_CHECK(ctx);
     }
     b->occ_upper = p.upper;
+    NB_CHECK(nb200_fifo_leave(ctx, b->stream));
     b->occ_done = true;
     return NB200_OK;
 }
@@ -644,32 +1240,55 @@ static int d2h(nb200_ctx *ctx, nb200_dbatch *b, void *dst, const DevBuf &src, si
     return NB200_OK;
 }
 
-int nb200_occ_download(nb200_ctx *ctx, nb200_dbatch *b, const nb200_occ_out *o)
+}  // extern "C"
+
+// Shared body of nb200_occ_download / nb200_occ_download32: T = double copies the tracks as they are, T = float converts
+// them on the device first (k_pack_f32 on the copy stream, after the pass) and copies the float32 slabs.
+template <typename T, typename Out>
+static int occ_download_impl(nb200_ctx *ctx, nb200_dbatch *b, const Out *o, const char *who)
 {
-    if (!ctx || !b || !o) return nb200_fail(ctx, NB200_ERR_ARG, "nb200_occ_download: NULL argument");
-    if (!b->occ_done) return nb200_fail(ctx, NB200_ERR_STATE, "nb200_occ_download: nb200_occ_run has not been called on this batch");
-    const size_t tb = sizeof(double) * (size_t)b->total_len;
+    if (!ctx || !b || !o) return nb200_fail(ctx, NB200_ERR_ARG, "%s: NULL argument", who);
+    if (!b->occ_done) return nb200_fail(ctx, NB200_ERR_STATE, "%s: nb200_occ_run has not been called on this batch", who);
+    const size_t tl = (size_t)b->total_len, tb = sizeof(T) * tl;
     const int n = b->n_chunks;
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
     NB_CUDA(ctx, cudaEventRecord(b->ev_pass, b->stream));            // copies start once the pass has finished ...
     NB_CUDA(ctx, cudaStreamWaitEvent(b->copy_stream, b->ev_pass, 0));
     struct Copied {                                                  // ... and the next pass over these arrays waits for them
         nb200_dbatch *b;
         ~Copied() { cudaEventRecord(b->ev_copied_occ, b->copy_stream); }
     } copied{b};
-    NB_CHECK(d2h(ctx, b, o->smoothed_vals, b->o_svals, tb));
-    NB_CHECK(d2h(ctx, b, o->smoothed_lower, b->o_slower, tb));
-    NB_CHECK(d2h(ctx, b, o->smoothed_upper, b->o_supper, tb));
-    NB_CHECK(d2h(ctx, b, o->vals, b->o_vals, tb));
-    NB_CHECK(d2h(ctx, b, o->lower_bound, b->o_lower, tb));
-    NB_CHECK(d2h(ctx, b, o->upper_bound, b->o_upper, tb));
-    NB_CHECK(d2h(ctx, b, o->cov, b->o_cov, tb));
+    T *host[7] = {o->smoothed_vals, o->smoothed_lower, o->smoothed_upper, o->vals, o->lower_bound, o->upper_bound, o->cov};
+    const DevBuf *dev[7] = {&b->o_svals, &b->o_slower, &b->o_supper, &b->o_vals, &b->o_lower, &b->o_upper, &b->o_cov};
+    if (sizeof(T) == sizeof(double)) {
+        for (int t = 0; t < 7; t++) NB_CHECK(d2h(ctx, b, host[t], *dev[t], tb));
+    } else {
+        Pack32Args pa;
+        int nt = 0, which[7];
+        for (int t = 0; t < 7; t++)
+            if (host[t]) which[nt++] = t;
+        if (nt && tl) {
+            const size_t slab = (tl + 3) & ~(size_t)3;
+            NB_CUDA(ctx, b->pack32_occ.reserve(sizeof(float) * slab * nt));
+            for (int k = 0; k < nt; k++) {
+                pa.src[k] = dev[which[k]]->template as<double>();
+                pa.dst[k] = b->pack32_occ.as<float>() + slab * k;
+            }
+            pa.n = (int64_t)tl;
+            ProfScope ps(ctx, b->copy_stream, "k_pack_f32");
+            k_pack_f32<<<dim3((unsigned)std::min<int64_t>(div_up64((int64_t)tl, 4 * 256), ctx->sm_count * 8), nt), 256, 0, b->copy_stream>>>(pa);
+            NB_LAUNCH_CHECK(ctx);
+        }
+        for (int k = 0; k < nt; k++)
+            NB_CUDA(ctx, cudaMemcpyAsync(host[which[k]], pa.dst[k], tb, cudaMemcpyDeviceToHost, b->copy_stream));
+    }
     NB_CHECK(d2h(ctx, b, o->nuc_dist, b->o_nuc_dist, sizeof(double) * (size_t)n * ctx->occ.upper));
     NB_CHECK(d2h(ctx, b, o->peak_count, b->o_peak_count, sizeof(int32_t) * n));
     if (o->peak_pos) {
-        if (!o->peak_off) return nb200_fail(ctx, NB200_ERR_ARG, "nb200_occ_download: peak_off is required with peak_pos");
+        if (!o->peak_off) return nb200_fail(ctx, NB200_ERR_ARG, "%s: peak_off is required with peak_pos", who);
         for (int c = 0; c <= n; c++)
             if (o->peak_off[c] != b->h_opeak_off[c])
-                return nb200_fail(ctx, NB200_ERR_CAPACITY, "nb200_occ_download: peak_off must equal len/sep+2 capacities (chunk %d)", c);
+                return nb200_fail(ctx, NB200_ERR_CAPACITY, "%s: peak_off must equal len/sep+2 capacities (chunk %d)", who, c);
         const size_t np = (size_t)b->h_opeak_off[n];
         NB_CHECK(d2h(ctx, b, o->peak_pos, b->o_peak_pos, sizeof(int32_t) * np));
         NB_CHECK(d2h(ctx, b, o->peak_occ, b->o_peak_occ, sizeof(double) * np));
@@ -680,10 +1299,11 @@ int nb200_occ_download(nb200_ctx *ctx, nb200_dbatch *b, const nb200_occ_out *o)
     return NB200_OK;
 }
 
-int64_t nb200_occ_d2h_bytes(nb200_dbatch *b, const nb200_occ_out *o)
+template <typename Out>
+static int64_t occ_d2h_bytes_impl(nb200_dbatch *b, const Out *o, int64_t elem)
 {
     if (!b || !o) return 0;
-    const int64_t tb = 8 * b->total_len;
+    const int64_t tb = elem * b->total_len;
     int64_t s = 0;
     const void *tr[] = {o->smoothed_vals, o->smoothed_lower, o->smoothed_upper, o->vals, o->lower_bound, o->upper_bound, o->cov};
     for (auto p : tr)
@@ -699,5 +1319,18 @@ int64_t nb200_occ_d2h_bytes(nb200_dbatch *b, const nb200_occ_out *o)
     }
     return s;
 }
+
+extern "C" {
+
+int nb200_occ_download(nb200_ctx *ctx, nb200_dbatch *b, const nb200_occ_out *o)
+{
+    return occ_download_impl<double>(ctx, b, o, "nb200_occ_download");
+}
+int nb200_occ_download32(nb200_ctx *ctx, nb200_dbatch *b, const nb200_occ_out32 *o)
+{
+    return occ_download_impl<float>(ctx, b, o, "nb200_occ_download32");
+}
+int64_t nb200_occ_d2h_bytes(nb200_dbatch *b, const nb200_occ_out *o) { return occ_d2h_bytes_impl(b, o, 8); }
+int64_t nb200_occ_d2h_bytes32(nb200_dbatch *b, const nb200_occ_out32 *o) { return occ_d2h_bytes_impl(b, o, 4); }
 
 }  // extern "C"

@@ -64,6 +64,7 @@ struct TcPlan {
     int n_stages = 0, n_achunks = 0, n_blocks = 0;
     int sG = 0;           // G scaled by 2^sG
     int has_row1 = 0;     // insert size 1 has a single tap (linear term), kept out of G
+    int pair = 1;         // 1: images laid out for CTA pairs (cta_group::2: each CTA stages half of the rows of a block)
     double density = 0.0; // MMA columns issued / (NAp * NBp / 16)
     DevBuf g_img, stage_tab, block_tab, t_row1, emax;
     std::vector<int4> h_tab, h_blk;
@@ -126,6 +127,39 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                  "r"(bytes), "r"(bar)
                  : "memory");
 }
+// barrier shared by the two CTAs of a pair: waits acquire at cluster scope, the peer arrives through its cluster address
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    int spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!done && ++spins > (1 << 20)) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta)   // arrive on `bar` of CTA `cta` of the cluster
+{
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(bar), "r"(cta));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar)
@@ -177,6 +211,39 @@ __device__ __forceinline__ void tc_commit_e(uint32_t bar)
         "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
         : "memory");
 }
+// CTA-pair forms (cta_group::2): one MMA of M = 256 spans the two CTAs of the pair -- rows 0..127 from the leader's A
+// operand and accumulator, rows 128..255 from the peer's, each CTA's shared memory holding half of the N rows of B.
+// Issued by the leader only; a commit can arrive on the same barrier of both CTAs (multicast mask 0b11).
+__device__ __forceinline__ void tc_mma_f16_e2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                              uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_e2_both(uint32_t bar)
+{
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t.reg .b16 m;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "mov.b16 m, 3;\n\t"
+        "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}" ::"r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_e2_local(uint32_t bar)
+{
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+        : "memory");
+}
 // K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 8x16B core matrices,
 // SBO = byte stride between 8-row groups, LBO = byte stride between the 16-byte K chunks, version 1 (sm_100).
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo)
@@ -213,6 +280,7 @@ struct TcArgs {
     unsigned long long *dbg;  // NB200_TC_DEBUG: per-CTA clock sums (8 words), else null
     int pwm_up, A0, B0, NAp, NBp, gmin, span, n_stages, n_achunks, n_blocks, sG, has_row1, W, w, epad, stagger;
     int n_chunks, tiles_per_chunk, ring;   // work items = n_chunks * tiles_per_chunk; ring = G stages resident in smem
+    int slot_bytes;                        // bytes of one ring slot in this CTA's shared memory
 };
 
 // Persistent kernel: one CTA per SM walks the work items (chunk, pair of x-tiles) it = blockIdx.x + i * gridDim.x.
@@ -221,17 +289,28 @@ struct TcArgs {
 //   prod  (1 thread) cp.async.bulk of the G stages through the ring (continues across items)
 //   mma   (2 warps)  tcgen05.mma of x-tile j into its TMEM accumulator, N trimmed per K16 block
 //   epi   (8 warps)  tcgen05.ld of a finished slab, contraction with E, bx store at the end of the item
-template <bool DBG>
+// PAIR: the CTAs 2p, 2p + 1 form a cluster on one TPC and contract their x-tiles together with cta_group::2 MMAs of
+// M = 256: the leader (cluster rank 0) issues for both, every CTA stages only half of the rows of each block of G (B is
+// split across the pair's shared memories), so the shared-memory traffic per MMA and SM falls from A 4 KB + B 6 KB to
+// A 4 KB + B 3 KB and G crosses L2 -> SMEM once per pair.  A work item of a pair is 4 x-tiles (512 outputs): rank r
+// takes outputs [x0 + 256 r, x0 + 256 r + 256).  Barriers that gather both CTAs live in the leader: the peer arrives
+// through the cluster address space (its two otherwise idle MMA warps relay "stage landed"), the leader's commits
+// arrive on both CTAs at once (multicast).
+template <bool DBG, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
 {
     extern __shared__ __align__(128) unsigned char sm_tc[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;        // 0 = leader (issues the MMAs)
+    const int it_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, it_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int item_w = PAIR ? 2 * TC_TX : TC_TX;                // outputs per work item
+    const int x_rank = (int)rank * TC_TX;                       // this CTA's offset inside the item
 
     // ---- shared memory carve-up
     const int nZ = (TC_TX + a.NBp) / 8;                     // 128-byte chunks per Z part
     const int spanp = (a.epad + a.span + 31) & ~31;
     unsigned char *p = sm_tc;
-    unsigned char *s_stage = p;            p += (size_t)a.ring * TC_SLOT_BYTES;
+    unsigned char *s_stage = p;            p += (size_t)a.ring * a.slot_bytes;
     unsigned char *s_z = p;                p += (size_t)4 * nZ * 128;             // [set][hi|lo][nZ * 128]
     float *s_Eb = reinterpret_cast<float *>(p);             // [set][epad + span] E over genomic [g0 + gmin, ...), rounded to fp32
     p += sizeof(float) * 2 * spanp;                         //   (epad: the epilogue's 32-float runs start on 128-byte lines)
@@ -245,33 +324,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
     p += sizeof(int4) * a.n_stages;
     int4 *s_blk = reinterpret_cast<int4 *>(p);
     p += sizeof(int4) * a.n_blocks;
-    uint64_t *s_bar = reinterpret_cast<uint64_t *>(p);      // full[ring], empty[ring], tfull[tile], tempty[tile], zfull[2], zempty[2]
-    p += sizeof(uint64_t) * (2 * TC_MAX_STAGES + 2 * TC_XT + 4 + 1);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(p);      // full[ring], empty[ring], tfull[tile], tempty[tile], zfull[2], zempty[2], stag, zpair[2]
+    p += sizeof(uint64_t) * (2 * TC_MAX_STAGES + 2 * TC_XT + 4 + 1 + 2);
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(p);
     const uint32_t bar_full = smem_u32(s_bar), bar_empty = bar_full + 8 * TC_MAX_STAGES, bar_tfull = bar_empty + 8 * TC_MAX_STAGES,
                    bar_tempty = bar_tfull + 8 * TC_XT, bar_zfull = bar_tempty + 8 * TC_XT, bar_zempty = bar_zfull + 16,
-                   bar_stag = bar_zempty + 16;
+                   bar_stag = bar_zempty + 16, bar_zpair = bar_stag + 8;   // zpair (leader): the operands of BOTH CTAs are ready
 
     // ---- one-time setup
     if (threadIdx.x == 0) {
         for (int i = 0; i < a.ring; i++) {
-            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_full + 8 * i, (PAIR && rank == 0) ? 2 : 1);   // own bulk copy (+ the peer's "landed" relay)
             mbar_init(bar_empty + 8 * i, TC_XT);                // one commit per MMA warp
         }
         for (int i = 0; i < TC_XT; i++) {
             mbar_init(bar_tfull + 8 * i, 1);
-            mbar_init(bar_tempty + 8 * i, 4);                   // the 4 epilogue warps of the tile
+            mbar_init(bar_tempty + 8 * i, PAIR ? 8 : 4);        // the 4 epilogue warps of the tile (of both CTAs)
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(bar_zfull + 8 * i, TC_PREP_WARPS);
             mbar_init(bar_zempty + 8 * i, TC_EPI_WARPS + TC_XT);   // epilogue warps (E window) + the MMA warps' commits (Z)
+            mbar_init(bar_zpair + 8 * i, 2 * TC_PREP_WARPS);
         }
         mbar_init(bar_stag, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == TC_WARP_MMA) {  // TMEM: all 512 columns (one CTA per SM by shared-memory footprint)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(TC_TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(TC_TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(TC_TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     if (a.has_row1)
         for (int i = threadIdx.x; i < Wp; i += TC_THREADS) s_t1[i] = (i < a.W) ? (float)a.t_row1[i] : 0.f;
@@ -282,7 +367,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
     if (emax > 0.0) frexp(32768.0 / emax, &eexp);
     const int sE = eexp - 1;
     tc_fence_before();
-    __syncthreads();
+    if (PAIR)
+        cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / multicast commit
+    else
+        __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
     const long long t_begin = DBG ? clock64() : 0;
@@ -296,10 +384,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
         const int boff = a.B0 - a.gmin;  // s_E index of the first b tap of output 0
         long long w_ze = 0;
         int n = 0;
-        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-            const int c = it / a.tiles_per_chunk, x0 = (it - c * a.tiles_per_chunk) * TC_TX;
+        for (int it = it_first; it < n_items; it += it_step) {
+            const int c = it / a.tiles_per_chunk, xb = (it - c * a.tiles_per_chunk) * item_w, x0 = xb + x_rank;
             const int64_t oo = a.out_off[c];
-            if (x0 >= (int)(a.out_off[c + 1] - oo)) continue;
+            if (xb >= (int)(a.out_off[c + 1] - oo)) continue;
             const int set = n & 1;
             const long long t0 = DBG ? clock64() : 0;
             mbar_wait(bar_zempty + 8 * set, ((n >> 1) & 1) ^ 1);
@@ -326,7 +414,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
                 *reinterpret_cast<uint4 *>(zh + (size_t)e * 16) = *reinterpret_cast<uint4 *>(hi);
                 *reinterpret_cast<uint4 *>(zl + (size_t)e * 16) = *reinterpret_cast<uint4 *>(lo);
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+            if (PAIR)
+                asm volatile("fence.proxy.async;" ::: "memory");              // ... also to the leader's MMAs reading this CTA's memory
+            else
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
             if (a.has_row1) {
                 // insert size 1: Bp[1,c] = E[c] (one tap) -> lin[x] = sum_k t1[k] E[x - w + k], a plain 1-D correlation.  Two warps,
                 // 4 consecutive outputs per lane, 4 taps per step from one aligned 16-byte load (64 FMAs per smem wavefront).
@@ -354,7 +445,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_zfull + 8 * set);
+            if (lane == 0) {
+                mbar_arrive(bar_zfull + 8 * set);
+                if (PAIR) mbar_arrive_cluster(bar_zpair + 8 * set, 0);
+            }
             n++;
         }
         if (DBG && tid == 0) dbg[6] = (unsigned long long)w_ze;
@@ -364,14 +458,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
             const unsigned char *g_img = a.g_img;
             int slot = 0;
             uint32_t ph = 0;
-            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-                const int c = it / a.tiles_per_chunk, x0 = (it - c * a.tiles_per_chunk) * TC_TX;
-                if (x0 >= (int)(a.out_off[c + 1] - a.out_off[c])) continue;
+            for (int it = it_first; it < n_items; it += it_step) {
+                const int c = it / a.tiles_per_chunk, xb = (it - c * a.tiles_per_chunk) * item_w;
+                if (xb >= (int)(a.out_off[c + 1] - a.out_off[c])) continue;
                 for (int s = 0; s < a.n_stages; s++) {
                     const int4 st = s_tab[s];
+                    const uint32_t bytes = PAIR ? (uint32_t)st.z >> 1 : (uint32_t)st.z;   // a pair's stage image: rank 0's half, then rank 1's
                     mbar_wait(bar_empty + 8 * slot, ph ^ 1);
-                    mbar_expect_tx(bar_full + 8 * slot, (uint32_t)st.z);
-                    bulk_g2s(smem_u32(s_stage + (size_t)slot * TC_SLOT_BYTES), g_img + (size_t)st.w * 16, (uint32_t)st.z, bar_full + 8 * slot);
+                    mbar_expect_tx(bar_full + 8 * slot, bytes);
+                    bulk_g2s(smem_u32(s_stage + (size_t)slot * a.slot_bytes), g_img + (size_t)st.w * 16 + (size_t)rank * bytes, bytes, bar_full + 8 * slot);
+                    if (++slot == a.ring) {
+                        slot = 0;
+                        ph ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (PAIR && rank != 0) {
+        // ===== peer of a pair: its MMA warps issue nothing; warp 0 of them tells the leader when this CTA's half of a stage has landed
+        if (warp == TC_WARP_MMA) {
+            int slot = 0;
+            uint32_t ph = 0;
+            for (int it = it_first; it < n_items; it += it_step) {
+                const int c = it / a.tiles_per_chunk, xb = (it - c * a.tiles_per_chunk) * item_w;
+                if (xb >= (int)(a.out_off[c + 1] - a.out_off[c])) continue;
+                for (int s = 0; s < a.n_stages; s++) {
+                    mbar_wait(bar_full + 8 * slot, ph);
+                    if (lane == 0) mbar_arrive_cluster(bar_full + 8 * slot, 0);
+                    __syncwarp();
                     if (++slot == a.ring) {
                         slot = 0;
                         ph ^= 1;
@@ -389,13 +503,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
         long long w_zf = 0, w_te = 0, w_full = 0;
         int n = 0, gq = 0, slot = 0;
         uint32_t ph = 0;
-        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-            const int c = it / a.tiles_per_chunk, x0 = (it - c * a.tiles_per_chunk) * TC_TX;
-            if (x0 >= (int)(a.out_off[c + 1] - a.out_off[c])) continue;
+        for (int it = it_first; it < n_items; it += it_step) {
+            const int c = it / a.tiles_per_chunk, xb = (it - c * a.tiles_per_chunk) * item_w;
+            if (xb >= (int)(a.out_off[c + 1] - a.out_off[c])) continue;
             const int set = n & 1;
             {
                 const long long t0 = DBG ? clock64() : 0;
-                mbar_wait(bar_zfull + 8 * set, (n >> 1) & 1);
+                if (PAIR)
+                    mbar_wait_cluster(bar_zpair + 8 * set, (n >> 1) & 1);   // both CTAs' operands
+                else
+                    mbar_wait(bar_zfull + 8 * set, (n >> 1) & 1);
                 tc_fence_after();
                 if (DBG) w_zf += clock64() - t0;
             }
@@ -412,15 +529,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
                 const bool first = (st.y >> 8) & 1, last = (st.y >> 9) & 1;
                 if (first) {  // the accumulator of this tile is free once its previous slab has been read back
                     const long long t0 = DBG ? clock64() : 0;
-                    mbar_wait(bar_tempty + 8 * j, (gq & 1) ^ 1);
+                    if (PAIR)
+                        mbar_wait_cluster(bar_tempty + 8 * j, (gq & 1) ^ 1);
+                    else
+                        mbar_wait(bar_tempty + 8 * j, (gq & 1) ^ 1);
                     tc_fence_after();
                     if (DBG) w_te += clock64() - t0;
                 }
                 const long long t1 = DBG ? clock64() : 0;
-                mbar_wait(bar_full + 8 * slot, ph);
+                if (PAIR)
+                    mbar_wait_cluster(bar_full + 8 * slot, ph);
+                else
+                    mbar_wait(bar_full + 8 * slot, ph);
                 tc_fence_after();
                 if (DBG) w_full += clock64() - t1;
-                const uint32_t sb = (smem_u32(s_stage + (size_t)slot * TC_SLOT_BYTES) >> 4) & 0x3FFF;
+                const uint32_t sb = (smem_u32(s_stage + (size_t)slot * a.slot_bytes) >> 4) & 0x3FFF;
                 uint32_t acc0 = first ? 0u : 1u;   // the first block of a slab is stored untrimmed: it initialises all TC_N columns
                 for (int t = 0; t < nblk; t++) {
                     const int4 bk = s_blk[b0 + t];   // {A advance, n_lo, instruction descriptor, B descriptor low word (relative)}
@@ -428,23 +551,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
                     const uint32_t bl = bh + 2u * ((uint32_t)bk.w >> 16);           // lo image follows (N_t * 32 B)
                     const uint32_t ah = a_hi0 + (uint32_t)bk.x, al = a_lo0 + (uint32_t)bk.x;
                     const uint32_t d = d0 + (uint32_t)bk.y;
-                    tc_mma_f16_e(d, ah, desc_hi, bh, desc_hi, (uint32_t)bk.z, acc0);   // hi * hi
-                    tc_mma_f16_e(d, ah, desc_hi, bl, desc_hi, (uint32_t)bk.z, 1u);     // hi * lo
-                    tc_mma_f16_e(d, al, desc_hi, bh, desc_hi, (uint32_t)bk.z, 1u);     // lo * hi
+                    if (PAIR) {
+                        tc_mma_f16_e2(d, ah, desc_hi, bh, desc_hi, (uint32_t)bk.z, acc0);   // hi * hi
+                        tc_mma_f16_e2(d, ah, desc_hi, bl, desc_hi, (uint32_t)bk.z, 1u);     // hi * lo
+                        tc_mma_f16_e2(d, al, desc_hi, bh, desc_hi, (uint32_t)bk.z, 1u);     // lo * hi
+                    } else {
+                        tc_mma_f16_e(d, ah, desc_hi, bh, desc_hi, (uint32_t)bk.z, acc0);
+                        tc_mma_f16_e(d, ah, desc_hi, bl, desc_hi, (uint32_t)bk.z, 1u);
+                        tc_mma_f16_e(d, al, desc_hi, bh, desc_hi, (uint32_t)bk.z, 1u);
+                    }
                     acc0 = 1u;
                 }
-                tc_commit_e(bar_empty + 8 * slot);                     // smem slot reusable once these MMAs retire
-                if (n == 0 && j == 0 && s == a.stagger) tc_commit_e(bar_stag);
-                if (last) {
-                    tc_commit_e(bar_tfull + 8 * j);                    // slab of H complete in TMEM
-                    gq++;
+                if (PAIR) {
+                    tc_commit_e2_both(bar_empty + 8 * slot);           // both CTAs' slots reusable once these MMAs retire
+                    if (n == 0 && j == 0 && s == a.stagger) tc_commit_e2_local(bar_stag);
+                    if (last) {
+                        tc_commit_e2_both(bar_tfull + 8 * j);          // slab of H complete in both CTAs' TMEM
+                        gq++;
+                    }
+                } else {
+                    tc_commit_e(bar_empty + 8 * slot);                 // smem slot reusable once these MMAs retire
+                    if (n == 0 && j == 0 && s == a.stagger) tc_commit_e(bar_stag);
+                    if (last) {
+                        tc_commit_e(bar_tfull + 8 * j);                // slab of H complete in TMEM
+                        gq++;
+                    }
                 }
                 if (++slot == a.ring) {
                     slot = 0;
                     ph ^= 1;
                 }
             }
-            tc_commit_e(bar_zempty + 8 * set);                         // Z set free once every MMA of the item has retired
+            if (PAIR)
+                tc_commit_e2_both(bar_zempty + 8 * set);
+            else
+                tc_commit_e(bar_zempty + 8 * set);                     // Z set free once every MMA of the item has retired
             n++;
         }
         if (DBG && j == 0 && lane == 0) {
@@ -462,11 +603,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
         const uint32_t t0addr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(j * TC_N);
         long long w_tf = 0, t_epi = 0;
         int n = 0, gq = 0;
-        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-            const int c = it / a.tiles_per_chunk, x0 = (it - c * a.tiles_per_chunk) * TC_TX;
+        for (int it = it_first; it < n_items; it += it_step) {
+            const int c = it / a.tiles_per_chunk, xb = (it - c * a.tiles_per_chunk) * item_w, x0 = xb + x_rank;
             const int64_t oo = a.out_off[c];
             const int L = (int)(a.out_off[c + 1] - oo);
-            if (x0 >= L) continue;
+            if (xb >= L) continue;
             const int set = n & 1;
             mbar_wait(bar_zfull + 8 * set, (n >> 1) & 1);
             const float *s_E = s_Eb + (size_t)set * spanp + a.epad;
@@ -493,7 +634,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
                     } else {
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_tempty + 8 * j);
+                        if (lane == 0) {
+                            if (PAIR)
+                                mbar_arrive_cluster(bar_tempty + 8 * j, 0);   // the leader's barrier gathers both CTAs
+                            else
+                                mbar_arrive(bar_tempty + 8 * j);
+                        }
                     }
                     float f[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -516,10 +662,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR)
+        cluster_sync_all();   // no CTA leaves (or frees its TMEM) while its partner's MMAs / arrives may still touch it
+    else
+        __syncthreads();
     if (warp == TC_WARP_MMA) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS) : "memory");
+        if (PAIR)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS) : "memory");
     }
 }
 
@@ -584,6 +736,8 @@ int nb200_tc_setup(nb200_ctx *ctx)
     // matrices, (n/8, k/8) at ((k/8) * (N_t/8) + n/8) * 128 B, row n%8, element k%8.
     pl->h_tab.clear();
     pl->h_blk.clear();
+    pl->pair = (getenv("NB200_TC_PAIR") && atoi(getenv("NB200_TC_PAIR")) == 0) ? 0 : 1;   // developer switch: single-CTA MMAs
+    const int NR = pl->pair ? 2 : 1;   // CTAs sharing a block of G
     std::vector<unsigned char> img;
     const int nkb = pl->NBp / 16;
     long long cols_issued = 0;
@@ -611,28 +765,43 @@ int nb200_tc_setup(nb200_ctx *ctx)
             const size_t base = img.size();
             int bytes = 0, cnt = 0;
             const size_t bi_start = bi;
-            while (bi < blks.size() && cnt < TC_MAX_STAGE_BLOCKS && bytes + blks[bi].n_t * 64 <= TC_SLOT_BYTES) {
-                const Blk &bk = blks[bi];
-                const uint32_t idesc = (1u << 4) | ((uint32_t)(bk.n_t >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);  // f16 x f16 -> f32
-                pl->h_blk.push_back(make_int4(16 * bk.kb, bk.n_lo, (int)idesc, (bytes >> 4) | (bk.n_t << 16)));
-                img.resize(base + bytes + (size_t)bk.n_t * 64, 0);
-                __half *hi = reinterpret_cast<__half *>(img.data() + base + bytes);
-                __half *lo = hi + (size_t)bk.n_t * 16;
-                for (int n = 0; n < bk.n_t; n++)
-                    for (int k = 0; k < 16; k++) {
-                        const double g = G[(size_t)(q * TC_N + bk.n_lo + n) * pl->NBp + bk.kb * 16 + k] * sc;
-                        const float gf = (float)g;
-                        const __half h = __float2half_rn(gf);
-                        const __half l = __float2half_rn(gf - __half2float(h));
-                        const size_t off = ((size_t)(k / 8) * (bk.n_t / 8) + n / 8) * 64 + (n % 8) * 8 + (k % 8);
-                        hi[off] = h;
-                        lo[off] = l;
-                    }
-                bytes += bk.n_t * 64;
-                cols_issued += bk.n_t;
+            // which blocks go into this stage (their images together fit a ring slot)
+            size_t bj = bi;
+            while (bj < blks.size() && cnt < TC_MAX_STAGE_BLOCKS && bytes + blks[bj].n_t * 64 <= TC_SLOT_BYTES) {
+                bytes += blks[bj].n_t * 64;
                 cnt++;
-                bi++;
+                bj++;
             }
+            img.resize(base + bytes, 0);
+            // stage image: for every CTA of the pair (one without pairs) its share of the rows of each block -- rank r holds
+            // rows [r n_t / NR, (r + 1) n_t / NR) as a canonical hi image followed by the lo image
+            const int rank_bytes = bytes / NR;
+            for (int rk = 0; rk < NR; rk++) {
+                int off_r = 0;
+                for (size_t bb = bi; bb < bj; bb++) {
+                    const Blk &bk = blks[bb];
+                    const int nh = bk.n_t / NR;   // n_t is a multiple of 16: the halves are multiples of 8 rows
+                    if (rk == 0) {
+                        const uint32_t idesc = (1u << 4) | ((uint32_t)(bk.n_t >> 3) << 17) | ((uint32_t)((TC_M * NR) >> 4) << 24);  // f16 x f16 -> f32, M = 128 per CTA
+                        pl->h_blk.push_back(make_int4(16 * bk.kb, bk.n_lo, (int)idesc, (off_r >> 4) | (nh << 16)));
+                        cols_issued += bk.n_t;
+                    }
+                    __half *hi = reinterpret_cast<__half *>(img.data() + base + (size_t)rk * rank_bytes + off_r);
+                    __half *lo = hi + (size_t)nh * 16;
+                    for (int n = 0; n < nh; n++)
+                        for (int k = 0; k < 16; k++) {
+                            const double g = G[(size_t)(q * TC_N + bk.n_lo + rk * nh + n) * pl->NBp + bk.kb * 16 + k] * sc;
+                            const float gf = (float)g;
+                            const __half h = __float2half_rn(gf);
+                            const __half l = __float2half_rn(gf - __half2float(h));
+                            const size_t off = ((size_t)(k / 8) * (nh / 8) + n / 8) * 64 + (n % 8) * 8 + (k % 8);
+                            hi[off] = h;
+                            lo[off] = l;
+                        }
+                    off_r += nh * 64;
+                }
+            }
+            bi = bj;
             const int flags = (bi_start == 0 ? 1 : 0) | (bi == blks.size() ? 2 : 0);
             pl->h_tab.push_back(make_int4(first_blk, cnt | (flags << 8), bytes, (int)(base >> 4)));
         }
@@ -715,24 +884,28 @@ int nb200_nuc_bx_tc(nb200_ctx *ctx, nb200_dbatch *b)
     a.W = r.v_cols;
     a.w = r.v_w;
     a.n_chunks = b->n_chunks;
-    a.tiles_per_chunk = (int)div_up64(b->max_len, TC_TX);
+    const int pair = pl->pair;
+    a.tiles_per_chunk = (int)div_up64(b->max_len, TC_TX * (pair ? 2 : 1));
+    a.slot_bytes = TC_SLOT_BYTES / (pair ? 2 : 1);
     const int nZ = (TC_TX + pl->NBp) / 8;
     const size_t fixed = 4 * (size_t)nZ * 128 + sizeof(float) * 2 * ((a.epad + pl->span + 31) & ~31) +
                          sizeof(float) * (pl->has_row1 ? (((r.v_cols + 3) & ~3) + 2 * (TC_TX + ((r.v_cols + 3) & ~3) + 8) + 2 * TC_TX) : 0) + sizeof(int4) * (pl->n_stages + pl->n_blocks) +
-                         8 * (2 * TC_MAX_STAGES + 2 * TC_XT + 4 + 1) + 16 + 128;
+                         8 * (2 * TC_MAX_STAGES + 2 * TC_XT + 4 + 1 + 2) + 16 + 128;
     int ring = TC_MAX_STAGES;
-    while (ring > 2 && fixed + (size_t)ring * TC_SLOT_BYTES > 227 * 1024) ring--;
-    const size_t smem = (fixed + (size_t)ring * TC_SLOT_BYTES + 127) / 128 * 128;
+    while (ring > 2 && fixed + (size_t)ring * a.slot_bytes > 227 * 1024) ring--;
+    const size_t smem = (fixed + (size_t)ring * a.slot_bytes + 127) / 128 * 128;
     if (smem > 227 * 1024) return nb200_fail(ctx, NB200_ERR_ARG, "VMat too large for the tcgen05 background kernel");
     a.ring = ring;
     static const int stag_env = getenv("NB200_TC_STAGGER") ? atoi(getenv("NB200_TC_STAGGER")) : 2;
     a.stagger = stag_env < 0 ? -1 : std::min(std::min(stag_env, ring - 2), pl->n_stages - 1);
-    NB_CUDA(ctx, cudaFuncSetAttribute(k_nuc_bx_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    NB_CUDA(ctx, cudaFuncSetAttribute(k_nuc_bx_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static const bool tc_debug = getenv("NB200_TC_DEBUG") != nullptr;
+    void (*kern)(TcArgs) = pair ? (tc_debug ? k_nuc_bx_tc<true, true> : k_nuc_bx_tc<false, true>)
+                                : (tc_debug ? k_nuc_bx_tc<true, false> : k_nuc_bx_tc<false, false>);
+    NB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps(ctx, b->stream, "k_nuc_bx_tc");
     const int n_items = a.n_chunks * a.tiles_per_chunk;
-    dim3 grid((unsigned)std::max(1, std::min(ctx->sm_count, n_items)));
-    static const bool tc_debug = getenv("NB200_TC_DEBUG") != nullptr;
+    // one persistent CTA per SM; with pairs one cluster of 2 CTAs per TPC, both walking the same items
+    dim3 grid(pair ? (unsigned)(2 * std::max(1, std::min(ctx->sm_count / 2, n_items))) : (unsigned)std::max(1, std::min(ctx->sm_count, n_items)));
     unsigned long long *d_dbg = nullptr;
     const size_t n_cta = grid.x;
     if (tc_debug) {
@@ -740,10 +913,21 @@ int nb200_nuc_bx_tc(nb200_ctx *ctx, nb200_dbatch *b)
         NB_CUDA(ctx, cudaMemsetAsync(d_dbg, 0, n_cta * 8 * sizeof(unsigned long long), b->stream));
         a.dbg = d_dbg;
     }
-    if (tc_debug)
-        k_nuc_bx_tc<true><<<grid, TC_THREADS, smem, b->stream>>>(a);
-    else
-        k_nuc_bx_tc<false><<<grid, TC_THREADS, smem, b->stream>>>(a);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = b->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = pair ? 2 : 1;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        NB_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, a));
+    }
     NB_LAUNCH_CHECK(ctx);
     if (tc_debug) {  // developer aid: mean clock counts per CTA of the waits of each warp role
         std::vector<unsigned long long> h(n_cta * 8);

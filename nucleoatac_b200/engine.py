@@ -203,33 +203,36 @@ class Engine:
         sep = self.nuc_params["redundant_sep"]
         return np.concatenate(([0], np.cumsum(pb.lengths // sep + 2))).astype(np.int64)
 
-    def occ_alloc(self, pb, raw=True, alloc=None):
-        """Host result buffers for nb200_occ_download (pinned when alloc=self.pinned)."""
+    def occ_alloc(self, pb, raw=True, alloc=None, track_dtype=np.float64):
+        """Host result buffers for nb200_occ_download (pinned when alloc=self.pinned); track_dtype=np.float32 makes the
+        per-position tracks float32 (nb200_occ_download32: converted on the device, half the bytes on the host link)."""
         alloc = alloc or (lambda shape, dt: np.empty(shape, dtype=dt))
         n, tl, up = pb.n, pb.total_len, self.occ_params["upper"]
         po = self.occ_capacity(pb)
-        out = dict(smoothed_vals=alloc(tl, np.float64), smoothed_lower=alloc(tl, np.float64),
-                   smoothed_upper=alloc(tl, np.float64), cov=alloc(tl, np.float64), nuc_dist=alloc((n, up), np.float64),
+        td = np.dtype(track_dtype)
+        out = dict(smoothed_vals=alloc(tl, td), smoothed_lower=alloc(tl, td),
+                   smoothed_upper=alloc(tl, td), cov=alloc(tl, td), nuc_dist=alloc((n, up), np.float64),
                    peak_count=alloc(n, np.int32), peak_off=po, peak_pos=alloc(int(po[-1]), np.int32),
                    peak_occ=alloc(int(po[-1]), np.float64), peak_lower=alloc(int(po[-1]), np.float64),
                    peak_upper=alloc(int(po[-1]), np.float64), peak_reads=alloc(int(po[-1]), np.float64))
         if raw:
-            out.update(vals=alloc(tl, np.float64), lower_bound=alloc(tl, np.float64), upper_bound=alloc(tl, np.float64))
+            out.update(vals=alloc(tl, td), lower_bound=alloc(tl, td), upper_bound=alloc(tl, td))
         return out
 
-    def nuc_alloc(self, pb, cov=True, alloc=None):
+    def nuc_alloc(self, pb, cov=True, alloc=None, track_dtype=np.float64):
         alloc = alloc or (lambda shape, dt: np.empty(shape, dtype=dt))
         n, tl = pb.n, pb.total_len
         co = self.nuc_capacity(pb)
         nc = int(co[-1])
-        out = dict(nuc_signal=alloc(tl, np.float64), background=alloc(tl, np.float64), norm_signal=alloc(tl, np.float64),
-                   smoothed=alloc(tl, np.float64), cand_count=alloc(n, np.int32), cand_off=co,
+        td = np.dtype(track_dtype)
+        out = dict(nuc_signal=alloc(tl, td), background=alloc(tl, td), norm_signal=alloc(tl, td),
+                   smoothed=alloc(tl, td), cand_count=alloc(n, np.int32), cand_off=co,
                    cand_pos=alloc(nc, np.int32), cand_flag=alloc(nc, np.int32), cand_z=alloc(nc, np.float64),
                    cand_lr=alloc(nc, np.float64), cand_norm_signal=alloc(nc, np.float64),
                    cand_nuc_signal=alloc(nc, np.float64), cand_nuc_cov=alloc(nc, np.float64),
                    cand_nfr_cov=alloc(nc, np.float64), cand_smoothed=alloc(nc, np.float64))
         if cov:
-            out.update(nuc_cov=alloc(tl, np.float64), nfr_cov=alloc(tl, np.float64))
+            out.update(nuc_cov=alloc(tl, td), nfr_cov=alloc(tl, td))
         return out
 
     @staticmethod
@@ -240,12 +243,33 @@ class Engine:
                 setattr(struct, name, a.ctypes.data_as(ctype))
         return struct
 
+    @staticmethod
+    def _track_dtype(out, names):
+        """float64 or float32: the dtype of the track buffers in `out` (they must agree; it picks the C entry point)."""
+        kinds = {out[n].dtype for n in names if out.get(n) is not None}
+        if len(kinds) > 1 or (kinds and next(iter(kinds)) not in (np.dtype(np.float64), np.dtype(np.float32))):
+            raise TypeError("track buffers must be all float64 or all float32, got %s" % sorted(str(k) for k in kinds))
+        return next(iter(kinds)) if kinds else np.dtype(np.float64)
+
+    OCC_TRACKS = ("smoothed_vals", "smoothed_lower", "smoothed_upper", "vals", "lower_bound", "upper_bound", "cov")
+    NUC_TRACKS = ("nuc_signal", "background", "norm_signal", "smoothed", "nuc_cov", "nfr_cov")
+
     def occ_download(self, h, out):
+        """Enqueue the D2H of the occ results into `out` (float64 tracks: nb200_occ_download; float32 tracks:
+        nb200_occ_download32, converted on the device).  Returns the bytes that cross the link."""
+        if self._track_dtype(out, self.OCC_TRACKS) == np.float32:
+            o = self._fill(L.OccOut32(), out)
+            self.check(self.lib.nb200_occ_download32(self.h, h, C.byref(o)))
+            return int(self.lib.nb200_occ_d2h_bytes32(h, C.byref(o)))
         o = self._fill(L.OccOut(), out)
         self.check(self.lib.nb200_occ_download(self.h, h, C.byref(o)))
         return int(self.lib.nb200_occ_d2h_bytes(h, C.byref(o)))
 
     def nuc_download(self, h, out):
+        if self._track_dtype(out, self.NUC_TRACKS) == np.float32:
+            o = self._fill(L.NucOut32(), out)
+            self.check(self.lib.nb200_nuc_download32(self.h, h, C.byref(o)))
+            return int(self.lib.nb200_nuc_d2h_bytes32(h, C.byref(o)))
         o = self._fill(L.NucOut(), out)
         self.check(self.lib.nb200_nuc_download(self.h, h, C.byref(o)))
         return int(self.lib.nb200_nuc_d2h_bytes(h, C.byref(o)))

@@ -42,7 +42,8 @@ def test_struct_layouts_match_header():
     h = open(os.path.join(ROOT, "include", "nucleo_b200.h")).read()
     h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
     for cname, cls in (("nb200_occ_params", _lib.OccParams), ("nb200_nuc_params", _lib.NucParams), ("nb200_batch", _lib.Batch),
-                       ("nb200_occ_out", _lib.OccOut), ("nb200_nuc_out", _lib.NucOut)):
+                       ("nb200_occ_out", _lib.OccOut), ("nb200_nuc_out", _lib.NucOut), ("nb200_occ_out32", _lib.OccOut32),
+                       ("nb200_nuc_out32", _lib.NucOut32)):
         body = re.search(r"typedef struct \{([^{}]*)\} " + cname + ";", h).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         names = []
@@ -53,6 +54,12 @@ def test_struct_layouts_match_header():
             for part in decl.split(","):
                 names.append(re.findall(r"([A-Za-z_][A-Za-z0-9_]*)\s*$", part.strip())[0])
         assert names == [f[0] for f in cls._fields_], cname
+    # the float32 variants differ from the float64 ones in the type of the per-position tracks only
+    for c64, c32, ntr in ((_lib.OccOut, _lib.OccOut32, 7), (_lib.NucOut, _lib.NucOut32, 6)):
+        for i, ((n64, t64), (n32, t32)) in enumerate(zip(c64._fields_, c32._fields_)):
+            assert n64 == n32 and (t32 is _lib.c_float_p if i < ntr else t32 is t64), n64
+        body = re.search(r"typedef struct \{([^{}]*)\} nb200_%s_out32;" % ("occ" if ntr == 7 else "nuc"), h).group(1)
+        assert len(re.findall(r"\bfloat \*", body)) >= 1 and "double *" in body
 
 
 def test_no_cpu_fallback(lib):

@@ -1,0 +1,188 @@
+"""GPU parity of the round-2 kernels through the C-ABI: the guarded occupancy search against the full grid scan, the
+block-form smoother against the tap-by-tap one, float32 track delivery, the tcgen05 contraction over the VMat size sweep
+of BASELINE.json configs[4] against the fp64 oracle, and first-in first-out ordering of passes across batches."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import refalgo as ra, refnuc, refocc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from nucleoatac_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def _mixed_batch():
+    """48 synthetic chunks: the bench's density, sparse ones (windows without fragments), very dense ones (more fragments per
+    window than the kernel's cache holds) and lengths that are not multiples of the window step."""
+    from nucleoatac_b200 import synth
+    from nucleoatac_b200.engine import PackedBatch
+    chunks = []
+    for k in range(48):
+        length = 10000 if k % 4 else (3001 + 7 * k)
+        density = (0.25, 0.25, 0.02, 1.5, 0.25, 0.005, 0.25, 0.6)[k % 8]
+        chunks.append(synth.make_chunk(k, length=length, density=density))
+    return PackedBatch.from_chunks(chunks)
+
+
+def _occ(eng, pb, env=None):
+    old = {k: os.environ.get(k) for k in (env or {})}
+    os.environ.update(env or {})
+    try:
+        eng.profile_reset()
+        out = eng.process_occ(pb)
+        return out, eng.profile_report()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("use_bias", [True, False])
+def test_occ_search_equals_full_scan(eng, use_bias):
+    """k_occ_mle_search (3 rounds of 16 grid points, Occupancy.py:104-120) must return what the scan of all 101 grid points
+    returns -- bit for bit, on every window -- and the block-form smoother what the tap-by-tap smoother returns."""
+    from nucleoatac_b200 import synth
+    wl = synth.Workload(251, 251)
+    wl.configure(eng, use_bias=use_bias)
+    pb = _mixed_batch()
+    new, prof_new = _occ(eng, pb)
+    full, prof_full = _occ(eng, pb, {"NB200_MLE_FULL": "1", "NB200_OCC_SMOOTH_DENSE": "1"})
+    ran = lambda prof, k: prof.get(k, (0, 0.0))[0] > 0      # launches since profile_reset
+    assert ran(prof_new, "k_occ_mle_search") and ran(prof_new, "k_occ_smooth_blocks") and not ran(prof_new, "k_occ_mle")
+    assert ran(prof_full, "k_occ_mle") and ran(prof_full, "k_smooth_same") and not ran(prof_full, "k_occ_mle_search")
+    nwin = 0
+    for key in ("vals", "lower_bound", "upper_bound"):
+        assert np.array_equal(new[key], full[key], equal_nan=True), key
+        nwin = int((~np.isnan(new[key])).sum()) // 5
+    assert nwin > 50000 and np.isnan(new["vals"]).sum() > 1000     # both populated and empty windows were compared
+    for key in ("smoothed_vals", "smoothed_lower", "smoothed_upper"):
+        assert np.array_equal(np.isnan(new[key]), np.isnan(full[key])), key
+        np.testing.assert_allclose(new[key], full[key], rtol=1e-12, atol=1e-15, equal_nan=True, err_msg=key)
+    assert np.array_equal(new["cov"], full["cov"])
+    assert np.array_equal(new["peak_count"], full["peak_count"])
+    n = int(new["peak_off"][-1])
+    sel = np.zeros(n, bool)
+    for j in range(pb.n):
+        sel[int(new["peak_off"][j]):int(new["peak_off"][j]) + int(new["peak_count"][j])] = True
+    assert np.array_equal(new["peak_pos"][sel], full["peak_pos"][sel])
+    np.testing.assert_allclose(new["nuc_dist"], full["nuc_dist"], rtol=1e-12, atol=1e-15)
+
+
+def test_occ_search_other_grids(eng):
+    """Grids other than linspace(0, 1, 101): 17 and 121 points go through the search, 16 / 122 points take the scan; a
+    cutoff of 0 (nothing but the maximum passes) and a huge one (everything passes)."""
+    from nucleoatac_b200 import synth
+    wl = synth.Workload(251, 251)
+    wl.configure(eng, use_bias=True)
+    pb = synth.make_batch(3, 6)
+    for n_alpha, cutoff in ((17, None), (121, None), (101, 0.0), (101, 1e9), (64, 2.0)):
+        eng.set_occ_model(wl.nuc_probs, wl.nfr_probs, alphas=np.linspace(0, 1, n_alpha), cutoff=cutoff)
+        eng.configure_occ(upper=wl.upper, use_bias=True)
+        new, prof = _occ(eng, pb)
+        full, _ = _occ(eng, pb, {"NB200_MLE_FULL": "1"})
+        assert prof.get("k_occ_mle_search", (0, 0.0))[0] > 0
+        for key in ("vals", "lower_bound", "upper_bound"):
+            assert np.array_equal(new[key], full[key], equal_nan=True), (n_alpha, cutoff, key)
+    wl.configure(eng, use_bias=True)
+
+
+def test_download32_is_the_rounded_float64(eng):
+    """nb200_{occ,nuc}_download32: every per-position track equals float32(the float64 track); tables are unchanged."""
+    from nucleoatac_b200 import synth
+    wl = synth.Workload(251, 251)
+    wl.configure(eng, use_bias=True, xcor_mode=2)
+    pb = synth.make_batch(11, 5)
+    h = eng.upload(pb)
+    eng.nuc_run(h)
+    eng.occ_run(h)
+    n64, o64 = eng.nuc_alloc(pb), eng.occ_alloc(pb)
+    n32, o32 = eng.nuc_alloc(pb, track_dtype=np.float32), eng.occ_alloc(pb, track_dtype=np.float32)
+    b64 = eng.nuc_download(h, n64) + eng.occ_download(h, o64)
+    b32 = eng.nuc_download(h, n32) + eng.occ_download(h, o32)
+    eng.sync(h)
+    eng.free_batch(h)
+    tl = pb.total_len
+    assert b64 - b32 == 4 * tl * (len(eng.NUC_TRACKS) + len(eng.OCC_TRACKS))
+    for out64, out32, names in ((n64, n32, eng.NUC_TRACKS), (o64, o32, eng.OCC_TRACKS)):
+        for k, v in out64.items():
+            if k in names:
+                assert out32[k].dtype == np.float32
+                assert np.array_equal(out32[k], v.astype(np.float32), equal_nan=True), k
+            else:
+                assert np.array_equal(out32[k], v, equal_nan=True), k
+    with pytest.raises(TypeError):
+        bad = dict(o32)
+        bad["cov"] = o64["cov"]
+        eng._track_dtype(bad, eng.OCC_TRACKS)
+
+
+@pytest.mark.parametrize("size", [101, 151, 201, 301, 401, 501])
+def test_tensor_core_vmat_sweep(eng, size):
+    """BASELINE configs[4]: the tcgen05 background cross-correlation (NucleosomeCalling.py:60-63) at VMat sizes 101^2 .. 501^2
+    against the fp64 oracle: every track within 1e-5 of the signal scale (north_star: floats within 1e-5), coverage exact."""
+    from nucleoatac_b200 import synth
+    from nucleoatac_b200.engine import PackedBatch
+    wl = synth.Workload(size, size, upper=max(251, size))
+    wl.configure(eng, use_bias=True, xcor_mode=2)
+    params = refnuc.NucParams((wl.vmat, wl.v_lower, wl.v_upper), wl.fragmentsizes, sd=10)
+    margin = size + size // 2 + 40
+    chunks = [synth.make_chunk(k, length=3000, seq_margin=margin) for k in (2, 9)]
+    pb = PackedBatch.from_chunks(chunks)
+    eng.profile_reset()
+    out = eng.process_nuc(pb)
+    assert eng.profile_report().get("k_nuc_bx_tc", (0, 0.0))[0] > 0
+    worst = 0.0
+    for j, (s, e, pos, tlen, seq, s0) in enumerate(chunks):
+        _, _, span = refnuc.nuc_geometry(s, e, params)
+        bt = ra.log_bias_track(bytes(seq).decode()[span[0] - 10 - s0:span[1] + 10 - s0], wl.pwm, wl.nucleotides)
+        r = refnuc.process_nuc_chunk(pos, tlen, s, e, params, bias_track=bt, bias_track_start=span[0], fit=False)
+        a, b = int(pb.out_off[j]), int(pb.out_off[j + 1])
+        scale = max(float(np.abs(r["nuc_signal"]).max()), float(np.abs(r["bias"]).max()), 1e-300)
+        for key, okey in (("background", "bias"), ("norm_signal", "norm_signal"), ("smoothed", "smoothed")):
+            err = float(np.abs(out[key][a:b] - r[okey]).max()) / scale
+            worst = max(worst, err)
+            assert err <= 1e-5, (size, j, key, err)
+        assert np.array_equal(out["nuc_cov"][a:b], r["nuc_cov"])
+    print("VMat %dx%d: worst |error| / signal scale = %.2e (bar 1e-5)" % (size, size, worst))
+
+
+def test_batches_in_flight_give_identical_results(eng):
+    """Three batches in flight (own streams, passes chained first-in first-out, copies overlapping the next pass) return
+    what each returns when run alone."""
+    from nucleoatac_b200 import synth
+    wl = synth.Workload(251, 251)
+    wl.configure(eng, use_bias=True, xcor_mode=2)
+    pbs = [synth.make_batch(20 + 7 * i, 4 + i) for i in range(3)]
+    alone = [(eng.process_nuc(pb), eng.process_occ(pb, raw=False)) for pb in pbs]
+    hs, outs = [], []
+    for rep in range(2):           # second round recycles the handles while the first round's copies may still be running
+        for i, pb in enumerate(pbs):
+            h = eng.upload(pb, hs[i] if rep else None)
+            if not rep:
+                hs.append(h)
+                outs.append((eng.nuc_alloc(pb, track_dtype=np.float32), eng.occ_alloc(pb, raw=False, track_dtype=np.float32)))
+            eng.nuc_run(h)
+            eng.nuc_download(h, outs[i][0])
+            eng.occ_run(h)
+            eng.occ_download(h, outs[i][1])
+    for h in hs:
+        eng.sync(h)
+        eng.free_batch(h)
+    for (n1, o1), (n2, o2) in zip(alone, outs):
+        for k in ("norm_signal", "smoothed"):
+            assert np.array_equal(n1[k].astype(np.float32), n2[k], equal_nan=True), k
+        for k in ("cand_pos", "cand_flag", "cand_count"):
+            assert np.array_equal(n1[k], n2[k]), k
+        for k in ("smoothed_vals", "smoothed_lower", "smoothed_upper"):
+            assert np.array_equal(o1[k].astype(np.float32), o2[k], equal_nan=True), k
+        assert np.array_equal(o1["peak_pos"], o2["peak_pos"]) and np.array_equal(o1["nuc_dist"], o2["nuc_dist"])
