@@ -13,8 +13,9 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libnucleo_b200.so")
+_TAG = os.environ.get("NB200_BUILD_TAG", "")   # developer kernel variants: own object directory and library name
+OBJ = os.path.join(HERE, "build" + ("_" + _TAG if _TAG else ""))
+LIB = os.path.join(HERE, "libnucleo_b200%s.so" % ("_" + _TAG if _TAG else ""))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 SOURCES = ["nb200_ctx.cu", "nb200_batch.cu", "nb200_occ.cu", "nb200_nuc.cu", "nb200_prims.cu", "nb200_xcor_tc.cu", "nb200_hostfmt.cu", "nb200_hostio.cu", "nb200_pyatac.cu", "nb200_bamio.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
@@ -27,12 +28,17 @@ def _deps_mtime():
     return max(os.path.getmtime(h) for h in hdrs)
 
 
+def _extra_defs():
+    """Developer kernel variants: NB200_NVCC_DEFS="-DTC_EPI_MODE=2 -DTC_N=224" (with NB200_LIB for a separate output file)."""
+    return os.environ.get("NB200_NVCC_DEFS", "").split()
+
+
 def _compile(src, force, hdr_mtime, log):
     obj = os.path.join(OBJ, src[:-3] + ".o")
     path = os.path.join(CSRC, src)
     if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(path), hdr_mtime):
         return obj
-    res = subprocess.run([NVCC] + FLAGS + ["-c", path, "-o", obj], capture_output=True, text=True)
+    res = subprocess.run([NVCC] + FLAGS + _extra_defs() + ["-c", path, "-o", obj], capture_output=True, text=True)
     log.append((src, res.stderr))
     if res.returncode != 0:
         raise RuntimeError("nvcc failed on %s:\n%s" % (src, res.stderr))

@@ -756,6 +756,7 @@ __global__ void __launch_bounds__(SB_THREADS) k_occ_smooth_blocks(const double *
                                                                   double *__restrict__ o2)
 {
     extern __shared__ __align__(16) double sm_sb[];
+    __shared__ double s_den;                         // sum of the window, summed like k_smooth_same does
     const int h = (wlen - 1) / 2;
     const int R = (h + S - 1) / S;                   // block reach on either side
     const int nT = wlen + S - 1;
@@ -772,6 +773,12 @@ __global__ void __launch_bounds__(SB_THREADS) k_occ_smooth_blocks(const double *
     const int bt0 = blockIdx.x * SB_THREADS;
     if (bt0 >= nblk) return;
     const int64_t wo0 = oo / S + c;                  // window 0 of this chunk
+    if (threadIdx.x < 32) {
+        double d = 0.0;
+        for (int m = threadIdx.x; m < wlen; m += 32) d += win[m];
+        d = warp_sum(d);
+        if (threadIdx.x == 0) s_den = d;
+    }
     for (int k = threadIdx.x; k < nTs; k += SB_THREADS) {
         const int i = k - padL;
         double t = 0.0;
@@ -801,38 +808,72 @@ __global__ void __launch_bounds__(SB_THREADS) k_occ_smooth_blocks(const double *
     const int b0 = bt0 + threadIdx.x;
     if (b0 >= nblk) return;
     const int n0 = b0 * S;
-    const bool partial = (int64_t)nwin * S > L;      // the last window's block is cut short by the chunk end
-    if (partial && b0 + R >= nwin - 1) {
+    // Outputs whose window holds a missing value (a NaN window, the chunk edges) or reaches a last block cut short by the
+    // chunk end go tap by tap, in the order and association of k_smooth_same (taps from dlo on in pairs, the odd tap of a
+    // pair first), so that they are bit-identical to the tap-by-tap smoother: where few windows are present the smoothed
+    // track has plateaus on which call_peaks' 1e-12 jitter (utils.py:94-97) decides, and the last bit must not depend
+    // on which smoother ran.
+    const bool partial = (int64_t)nwin * S > L;
+    bool slow = partial && b0 + R >= nwin - 1;
+    for (int d = -R; d <= R && !slow; d++) slow = s_v[2 * (threadIdx.x + R + d) + 1].y == 0.0;
+    if (slow) {
+        const int dlo = -((wlen - h) & ~1);
+        const int T2 = (h - dlo + 2) & ~1;
+        const int nvalid = min(L, nwin * S);              // positions with a window value
+        auto tapw = [&](int k) {                          // wd[k] = w[h - (dlo + k)], zero padded
+            const int m = h - (dlo + k);
+            return (m >= 0 && m < wlen) ? win[m] : 0.0;
+        };
         for (int u = 0; u < S; u++) {
             const int n = n0 + u;
             if (n >= L) break;
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, den = 0.0;
-            for (int m = 0; m < wlen; m++) {
-                const int j = n + h - m;
-                if (j < 0 || j >= L) continue;
-                const int b = j / S;
-                if (b >= nwin) continue;
-                const double v0 = wv[wo0 + b];
-                if (v0 != v0) continue;
-                const double w = win[m];
-                a0 = fma(w, v0, a0);
-                a1 = fma(w, wv[wv_stride + wo0 + b], a1);
-                a2 = fma(w, wv[2 * wv_stride + wo0 + b], a2);
-                den += w;
+            bool miss = false;                            // a real tap of this output is missing
+            for (int k = 0; k < T2; k += 2) {
+                const double wx = tapw(k), wy = tapw(k + 1);
+                double x0[2], x1[2], x2[2], pi[2];
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int j = n + dlo + k + e;
+                    x0[e] = x1[e] = x2[e] = pi[e] = 0.0;
+                    if (j >= 0 && j < nvalid) {
+                        const int i = j / S - (bt0 - R);      // tile slot of the block
+                        if (i >= 0 && i < SB_THREADS + 2 * R) {
+                            const double2 p = s_v[2 * i], q = s_v[2 * i + 1];
+                            x0[e] = p.x;
+                            x1[e] = p.y;
+                            x2[e] = q.x;
+                            pi[e] = q.y;
+                        }
+                    }
+                }
+                a0 = fma(wx, x0[0], fma(wy, x0[1], a0));
+                a1 = fma(wx, x1[0], fma(wy, x1[1], a1));
+                a2 = fma(wx, x2[0], fma(wy, x2[1], a2));
+                den = fma(wx, pi[0], fma(wy, pi[1], den));
+                miss = miss || (wx != 0.0 && pi[0] == 0.0) || (wy != 0.0 && pi[1] == 0.0);
             }
+            if (!miss) den = s_den;                       // k_smooth_same's fast path divides by the window's sum
             o0[oo + n] = (den == 0.0) ? nb_nan() : a0 / den;
             o1[oo + n] = (den == 0.0) ? nb_nan() : a1 / den;
             o2[oo + n] = (den == 0.0) ? nb_nan() : a2 / den;
         }
         return;
     }
+    // Every block in reach is present.  The sums run over the differences to the centre block's values: a stretch of
+    // equal windows then smooths to exactly that value whatever the output's phase inside its block, like the tap-by-tap
+    // sum (and numpy's) gives one constant there -- on such plateaus call_peaks' jitter alone must pick the maxima.
     double a0[S], a1[S], a2[S], dn[S];
 #pragma unroll
     for (int u = 0; u < S; u++) a0[u] = a1[u] = a2[u] = dn[u] = 0.0;
+    const double2 cp = s_v[2 * (threadIdx.x + R)], cq = s_v[2 * (threadIdx.x + R) + 1];   // centre block (V0, V1), (V2, 1)
     // block b0 + d contributes to output u through T[u - d S + h]; d runs over [-R, R]
     for (int d = -R; d <= R; d++) {
         const int i = threadIdx.x + R + d;
-        const double2 p = s_v[2 * i], q = s_v[2 * i + 1];
+        double2 p = s_v[2 * i], q = s_v[2 * i + 1];
+        p.x -= cp.x;
+        p.y -= cp.y;
+        q.x -= cq.x;
         const double *Tb = s_T + (R - d) * S;         // T[h - d S + u] at Tb[u]
 #pragma unroll
         for (int u = 0; u < S; u++) {
@@ -847,10 +888,9 @@ __global__ void __launch_bounds__(SB_THREADS) k_occ_smooth_blocks(const double *
     for (int u = 0; u < S; u++) {
         const int n = n0 + u;
         if (n < L) {
-            const bool z = dn[u] == 0.0;   // smoothed_norm == 0 -> NaN (utils.py:49)
-            o0[oo + n] = z ? nb_nan() : a0[u] / dn[u];
-            o1[oo + n] = z ? nb_nan() : a1[u] / dn[u];
-            o2[oo + n] = z ? nb_nan() : a2[u] / dn[u];
+            o0[oo + n] = cp.x + a0[u] / dn[u];   // dn = sum of the window over present taps > 0 here
+            o1[oo + n] = cp.y + a1[u] / dn[u];
+            o2[oo + n] = cq.x + a2[u] / dn[u];
         }
     }
 }

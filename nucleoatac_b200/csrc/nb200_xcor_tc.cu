@@ -65,6 +65,7 @@ struct TcPlan {
     int sG = 0;           // G scaled by 2^sG
     int has_row1 = 0;     // insert size 1 has a single tap (linear term), kept out of G
     int pair = 1;         // 1: images laid out for CTA pairs (cta_group::2: each CTA stages half of the rows of a block)
+    size_t img_bytes = 0; // whole G image (all stages, both halves)
     double density = 0.0; // MMA columns issued / (NAp * NBp / 16)
     DevBuf g_img, stage_tab, block_tab, t_row1, emax;
     std::vector<int4> h_tab, h_blk;
@@ -98,6 +99,28 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+// Protocol-bug aid: a wait that gives up records who waited on what in host-mapped memory (if the host installed some,
+// NB200_TC_DEBUG) before it traps, so that the host can say which barrier starved.
+__device__ int *g_tc_trap_info = nullptr;
+__device__ __noinline__ void tc_trap(uint32_t bar, uint32_t parity, int kind)
+{
+    int *t = g_tc_trap_info;
+    if (t) {
+        if ((threadIdx.x & 31) == 0) {   // one record per starving warp
+            const int slot = atomicAdd(t, 1);
+            if (slot < 500) {
+                int *r = t + 16 + 4 * slot;
+                r[0] = (int)blockIdx.x;
+                r[1] = (int)threadIdx.x;
+                r[2] = (int)bar;
+                r[3] = (int)parity | (kind << 8);
+            }
+            __threadfence_system();
+        }
+        for (int i = 0; i < 200000; i++) __nanosleep(1000);   // let the other starving warps report before the context dies
+    }
+    __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t done = 0;
@@ -110,7 +133,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
-        if (!done && ++spins > (1 << 20)) __trap();  // never hang the GPU on a protocol bug
+        if (!done && ++spins > (1 << 20)) tc_trap(bar, parity, 0);  // never hang the GPU on a protocol bug
     }
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar)
@@ -140,7 +163,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
-        if (!done && ++spins > (1 << 20)) __trap();
+        if (!done && ++spins > (1 << 20)) tc_trap(bar, parity, 1);
     }
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta)   // arrive on `bar` of CTA `cta` of the cluster
@@ -227,6 +250,44 @@ __device__ __forceinline__ void tc_mma_f16_e2(uint32_t d_tmem, uint32_t a_lo, ui
         "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// The three MMAs of one K16 block -- hi*hi (accumulate = acc0), hi*lo, lo*hi -- behind ONE election: the issuing warp
+// pays for every operand it moves into uniform registers and for every election / vote, so that set-up is shared by
+// the block's three instructions (SASS: ~35 instructions per block instead of ~70).  CG = 1: single CTA, 2: CTA pair.
+template <int CG>
+__device__ __forceinline__ void tc_mma3_e(uint32_t d_tmem, uint32_t a_hi_lo, uint32_t a_lo_lo, uint32_t b_hi_lo, uint32_t b_lo_lo, uint32_t desc_hi,
+                                          uint32_t idesc, uint32_t acc0)
+{
+    if (CG == 2)
+        asm volatile(
+            "{\n\t.reg .pred p, q, e;\n\t.reg .b64 dah, dal, dbh, dbl;\n\t"
+            "elect.sync _|e, 0xffffffff;\n\t"
+            "mov.b64 dah, {%1, %5};\n\t"
+            "mov.b64 dal, {%2, %5};\n\t"
+            "mov.b64 dbh, {%3, %5};\n\t"
+            "mov.b64 dbl, {%4, %5};\n\t"
+            "setp.ne.b32 p, %7, 0;\n\t"
+            "setp.eq.b32 q, %5, %5;\n\t"
+            "@e tcgen05.mma.cta_group::2.kind::f16 [%0], dah, dbh, %6, p;\n\t"
+            "@e tcgen05.mma.cta_group::2.kind::f16 [%0], dah, dbl, %6, q;\n\t"
+            "@e tcgen05.mma.cta_group::2.kind::f16 [%0], dal, dbh, %6, q;\n\t}" ::"r"(d_tmem),
+            "r"(a_hi_lo), "r"(a_lo_lo), "r"(b_hi_lo), "r"(b_lo_lo), "r"(desc_hi), "r"(idesc), "r"(acc0)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p, q, e;\n\t.reg .b64 dah, dal, dbh, dbl;\n\t"
+            "elect.sync _|e, 0xffffffff;\n\t"
+            "mov.b64 dah, {%1, %5};\n\t"
+            "mov.b64 dal, {%2, %5};\n\t"
+            "mov.b64 dbh, {%3, %5};\n\t"
+            "mov.b64 dbl, {%4, %5};\n\t"
+            "setp.ne.b32 p, %7, 0;\n\t"
+            "setp.eq.b32 q, %5, %5;\n\t"
+            "@e tcgen05.mma.cta_group::1.kind::f16 [%0], dah, dbh, %6, p;\n\t"
+            "@e tcgen05.mma.cta_group::1.kind::f16 [%0], dah, dbl, %6, q;\n\t"
+            "@e tcgen05.mma.cta_group::1.kind::f16 [%0], dal, dbh, %6, q;\n\t}" ::"r"(d_tmem),
+            "r"(a_hi_lo), "r"(a_lo_lo), "r"(b_hi_lo), "r"(b_lo_lo), "r"(desc_hi), "r"(idesc), "r"(acc0)
+            : "memory");
+}
 __device__ __forceinline__ void tc_commit_e2_both(uint32_t bar)
 {
     asm volatile(
@@ -281,6 +342,7 @@ struct TcArgs {
     int pwm_up, A0, B0, NAp, NBp, gmin, span, n_stages, n_achunks, n_blocks, sG, has_row1, W, w, epad, stagger;
     int n_chunks, tiles_per_chunk, ring;   // work items = n_chunks * tiles_per_chunk; ring = G stages resident in smem
     int slot_bytes;                        // bytes of one ring slot in this CTA's shared memory
+    int res_bytes;                         // resident mode: bytes of this CTA's share of the whole G image
 };
 
 // Persistent kernel: one CTA per SM walks the work items (chunk, pair of x-tiles) it = blockIdx.x + i * gridDim.x.
@@ -296,7 +358,12 @@ struct TcArgs {
 // takes outputs [x0 + 256 r, x0 + 256 r + 256).  Barriers that gather both CTAs live in the leader: the peer arrives
 // through the cluster address space (its two otherwise idle MMA warps relay "stage landed"), the leader's commits
 // arrive on both CTAs at once (multicast).
-template <bool DBG, bool PAIR>
+// RES (with PAIR): a CTA's half of the whole G image fits its shared memory next to the operands (251 x 251: 154 KB), so it
+// is loaded ONCE per kernel instead of being streamed from L2 for every work item: no producer loop, no ring, no "stage
+// landed" waits.  With every block always at hand one issuing warp takes the slabs of the two x-tiles in turn --
+// (tile 0, slab 0), (tile 1, slab 0), (tile 0, slab 1), ... -- so the read-back of a tile's accumulator runs under the other
+// tile's MMAs.
+template <bool DBG, bool PAIR, bool RES>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
 {
     extern __shared__ __align__(128) unsigned char sm_tc[];
@@ -310,7 +377,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
     const int nZ = (TC_TX + a.NBp) / 8;                     // 128-byte chunks per Z part
     const int spanp = (a.epad + a.span + 31) & ~31;
     unsigned char *p = sm_tc;
-    unsigned char *s_stage = p;            p += (size_t)a.ring * a.slot_bytes;
+    unsigned char *s_stage = p;            p += RES ? (size_t)a.res_bytes : (size_t)a.ring * a.slot_bytes;
     unsigned char *s_z = p;                p += (size_t)4 * nZ * 128;             // [set][hi|lo][nZ * 128]
     float *s_Eb = reinterpret_cast<float *>(p);             // [set][epad + span] E over genomic [g0 + gmin, ...), rounded to fp32
     p += sizeof(float) * 2 * spanp;                         //   (epad: the epilogue's 32-float runs start on 128-byte lines)
@@ -323,7 +390,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
     int4 *s_tab = reinterpret_cast<int4 *>(p);              // stage + block tables (kept out of the issue loop's global-load latency)
     p += sizeof(int4) * a.n_stages;
     int4 *s_blk = reinterpret_cast<int4 *>(p);
-    p += sizeof(int4) * a.n_blocks;
+    p += sizeof(int4) * (a.n_blocks + 1);                   // one spare entry: the resident issue loop reads one block ahead
+    int *s_soff = reinterpret_cast<int *>(p);               // resident mode: byte offset of every stage's image in s_stage
+    p += sizeof(int) * ((a.n_stages + 3) & ~3);
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(p);      // full[ring], empty[ring], tfull[tile], tempty[tile], zfull[2], zempty[2], stag, zpair[2]
     p += sizeof(uint64_t) * (2 * TC_MAX_STAGES + 2 * TC_XT + 4 + 1 + 2);
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(p);
@@ -343,7 +412,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(bar_zfull + 8 * i, TC_PREP_WARPS);
-            mbar_init(bar_zempty + 8 * i, TC_EPI_WARPS + TC_XT);   // epilogue warps (E window) + the MMA warps' commits (Z)
+            mbar_init(bar_zempty + 8 * i, TC_EPI_WARPS + (RES ? 1 : TC_XT));   // epilogue warps (E window) + the MMA warps' commits (Z)
             mbar_init(bar_zpair + 8 * i, 2 * TC_PREP_WARPS);
         }
         mbar_init(bar_stag, 1);
@@ -361,7 +430,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
     if (a.has_row1)
         for (int i = threadIdx.x; i < Wp; i += TC_THREADS) s_t1[i] = (i < a.W) ? (float)a.t_row1[i] : 0.f;
     for (int i = threadIdx.x; i < a.n_stages; i += TC_THREADS) s_tab[i] = a.tab[i];
-    for (int i = threadIdx.x; i < a.n_blocks; i += TC_THREADS) s_blk[i] = a.blk[i];
+    for (int i = threadIdx.x; i <= a.n_blocks; i += TC_THREADS) s_blk[i] = (i < a.n_blocks) ? a.blk[i] : make_int4(0, 0, 0, 0);
+    if (RES && threadIdx.x == 0) {
+        int off = 0;
+        for (int i = 0; i < a.n_stages; i++) {
+            s_soff[i] = off;
+            off += a.tab[i].z >> 1;
+        }
+    }
     int eexp = 1;
     const double emax = a.emax[0];
     if (emax > 0.0) frexp(32768.0 / emax, &eexp);
@@ -373,6 +449,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
         __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
+    if (DBG && threadIdx.x == 0 && blockIdx.x < 2 && g_tc_trap_info) {   // where the barriers of CTA 0 / 1 live, for reading a trap record
+        g_tc_trap_info[8 + 2 * blockIdx.x] = (int)bar_full;
+        g_tc_trap_info[9 + 2 * blockIdx.x] = (int)tmem;
+    }
     const long long t_begin = DBG ? clock64() : 0;
     unsigned long long *dbg = DBG ? a.dbg + 8 * (size_t)blockIdx.x : nullptr;
     const int n_items = a.n_chunks * a.tiles_per_chunk;
@@ -454,7 +534,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
         if (DBG && tid == 0) dbg[6] = (unsigned long long)w_ze;
     } else if (warp == TC_WARP_PROD) {
         // ===== producer: stream the G stages (hi + lo images of the trimmed K16 blocks) through the ring, once per item =====
-        if (lane == 0) {
+        if (RES) {
+            if (lane == 0) {   // this CTA's half of every stage image, once
+                mbar_expect_tx(bar_full, (uint32_t)a.res_bytes);
+                for (int s = 0; s < a.n_stages; s++) {
+                    const int4 st = s_tab[s];
+                    const uint32_t bytes = (uint32_t)st.z >> 1;
+                    bulk_g2s(smem_u32(s_stage + s_soff[s]), a.g_img + (size_t)st.w * 16 + (size_t)rank * bytes, bytes, bar_full);
+                }
+            }
+        } else if (lane == 0) {
             const unsigned char *g_img = a.g_img;
             int slot = 0;
             uint32_t ph = 0;
@@ -474,9 +563,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
                 }
             }
         }
-    } else if (PAIR && rank != 0) {
+    } else if (PAIR && rank != 0 && warp >= TC_WARP_MMA) {
         // ===== peer of a pair: its MMA warps issue nothing; warp 0 of them tells the leader when this CTA's half of a stage has landed
-        if (warp == TC_WARP_MMA) {
+        if (RES) {
+            if (warp == TC_WARP_MMA) {
+                mbar_wait(bar_full, 0);
+                if (lane == 0) mbar_arrive_cluster(bar_full, 0);
+                __syncwarp();
+            }
+        } else if (warp == TC_WARP_MMA) {
             int slot = 0;
             uint32_t ph = 0;
             for (int it = it_first; it < n_items; it += it_step) {
@@ -491,6 +586,74 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
                         ph ^= 1;
                     }
                 }
+            }
+        }
+    } else if (RES && warp >= TC_WARP_MMA) {
+        // ===== resident G: one issuing warp (of the leader), slabs of the two x-tiles in turn
+        if (warp == TC_WARP_MMA) {
+            const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+            const uint32_t sbase = (smem_u32(s_stage) >> 4) & 0x3FFF;
+            long long w_zf = 0, w_te = 0;
+            int n = 0, gq0 = 0, gq1 = 0;
+            mbar_wait_cluster(bar_full, 0);   // both CTAs' halves of G have landed
+            tc_fence_after();
+            for (int it = it_first; it < n_items; it += it_step) {
+                const int c = it / a.tiles_per_chunk, xb = (it - c * a.tiles_per_chunk) * item_w;
+                if (xb >= (int)(a.out_off[c + 1] - a.out_off[c])) continue;
+                const int set = n & 1;
+                {
+                    const long long t0 = DBG ? clock64() : 0;
+                    mbar_wait_cluster(bar_zpair + 8 * set, (n >> 1) & 1);
+                    tc_fence_after();
+                    if (DBG) w_zf += clock64() - t0;
+                }
+                const uint32_t zb = smem_u32(s_z + (size_t)set * 2 * nZ * 128);
+                for (int s0 = 0; s0 < a.n_stages;) {
+                    int s1 = s0;
+                    while (!((s_tab[s1].y >> 9) & 1)) s1++;   // last stage of this slab
+#pragma unroll
+                    for (int j = 0; j < TC_XT; j++) {
+                        const uint32_t zj = zb + 2048u * j;
+                        const uint32_t a_hi0 = ((zj >> 4) & 0x3FFF) | ((128u >> 4) << 16);
+                        const uint32_t a_lo0 = (((zj + (uint32_t)nZ * 128u) >> 4) & 0x3FFF) | ((128u >> 4) << 16);
+                        const uint32_t d0 = tmem + (uint32_t)(j * TC_N);
+                        {
+                            const long long t0 = DBG ? clock64() : 0;
+                            mbar_wait_cluster(bar_tempty + 8 * j, ((j ? gq1 : gq0) & 1) ^ 1);
+                            tc_fence_after();
+                            if (DBG) w_te += clock64() - t0;
+                        }
+                        uint32_t acc0 = 0u;   // the first block of a slab is stored untrimmed: it initialises all TC_N columns
+                        for (int s = s0; s <= s1; s++) {
+                            const int4 st = s_tab[s];
+                            const int b0 = st.x, nblk = st.y & 0xff;
+                            const uint32_t sb = sbase + ((uint32_t)s_soff[s] >> 4);
+                            int4 bk = s_blk[b0];
+                            for (int t = 0; t < nblk; t++) {
+                                const int4 nx = s_blk[b0 + t + 1];   // next entry in flight while this block is issued (the table has a spare entry)
+                                const uint32_t bh = (uint32_t)bk.w + sb;
+                                const uint32_t bl = bh + 2u * ((uint32_t)bk.w >> 16);
+                                tc_mma3_e<2>(d0 + (uint32_t)bk.y, a_hi0 + (uint32_t)bk.x, a_lo0 + (uint32_t)bk.x, bh, bl, desc_hi, (uint32_t)bk.z, acc0);
+                                acc0 = 1u;
+                                bk = nx;
+                            }
+                        }
+                        tc_commit_e2_both(bar_tfull + 8 * j);   // slab of H complete in both CTAs' TMEM
+                        if (j)
+                            gq1++;
+                        else
+                            gq0++;
+                    }
+                    s0 = s1 + 1;
+                }
+                tc_commit_e2_both(bar_zempty + 8 * set);        // Z set free once every MMA of the item has retired
+                n++;
+            }
+            if (DBG && lane == 0) {
+                dbg[1] = (unsigned long long)w_zf;
+                dbg[2] = (unsigned long long)w_te;
+                dbg[3] = 0;
+                dbg[7] = (unsigned long long)n;
             }
         }
     } else if (warp >= TC_WARP_MMA) {
@@ -551,15 +714,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
                     const uint32_t bl = bh + 2u * ((uint32_t)bk.w >> 16);           // lo image follows (N_t * 32 B)
                     const uint32_t ah = a_hi0 + (uint32_t)bk.x, al = a_lo0 + (uint32_t)bk.x;
                     const uint32_t d = d0 + (uint32_t)bk.y;
-                    if (PAIR) {
-                        tc_mma_f16_e2(d, ah, desc_hi, bh, desc_hi, (uint32_t)bk.z, acc0);   // hi * hi
-                        tc_mma_f16_e2(d, ah, desc_hi, bl, desc_hi, (uint32_t)bk.z, 1u);     // hi * lo
-                        tc_mma_f16_e2(d, al, desc_hi, bh, desc_hi, (uint32_t)bk.z, 1u);     // lo * hi
-                    } else {
-                        tc_mma_f16_e(d, ah, desc_hi, bh, desc_hi, (uint32_t)bk.z, acc0);
-                        tc_mma_f16_e(d, ah, desc_hi, bl, desc_hi, (uint32_t)bk.z, 1u);
-                        tc_mma_f16_e(d, al, desc_hi, bh, desc_hi, (uint32_t)bk.z, 1u);
-                    }
+                    if (PAIR)
+                        tc_mma3_e<2>(d, ah, al, bh, bl, desc_hi, (uint32_t)bk.z, acc0);   // hi * hi, hi * lo, lo * hi
+                    else
+                        tc_mma3_e<1>(d, ah, al, bh, bl, desc_hi, (uint32_t)bk.z, acc0);
                     acc0 = 1u;
                 }
                 if (PAIR) {
@@ -810,6 +968,7 @@ int nb200_tc_setup(nb200_ctx *ctx)
     pl->n_stages = (int)pl->h_tab.size();
     pl->density = (double)cols_issued / ((double)pl->NAp * nkb);
     NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    pl->img_bytes = img.size();
     NB_CUDA(ctx, pl->g_img.reserve(img.size()));
     NB_CUDA(ctx, cudaMemcpy(pl->g_img.p, img.data(), img.size(), cudaMemcpyHostToDevice));
     NB_CUDA(ctx, pl->stage_tab.reserve(sizeof(int4) * pl->h_tab.size()));
@@ -889,18 +1048,23 @@ int nb200_nuc_bx_tc(nb200_ctx *ctx, nb200_dbatch *b)
     a.slot_bytes = TC_SLOT_BYTES / (pair ? 2 : 1);
     const int nZ = (TC_TX + pl->NBp) / 8;
     const size_t fixed = 4 * (size_t)nZ * 128 + sizeof(float) * 2 * ((a.epad + pl->span + 31) & ~31) +
-                         sizeof(float) * (pl->has_row1 ? (((r.v_cols + 3) & ~3) + 2 * (TC_TX + ((r.v_cols + 3) & ~3) + 8) + 2 * TC_TX) : 0) + sizeof(int4) * (pl->n_stages + pl->n_blocks) +
-                         8 * (2 * TC_MAX_STAGES + 2 * TC_XT + 4 + 1 + 2) + 16 + 128;
+                         sizeof(float) * (pl->has_row1 ? (((r.v_cols + 3) & ~3) + 2 * (TC_TX + ((r.v_cols + 3) & ~3) + 8) + 2 * TC_TX) : 0) + sizeof(int4) * (pl->n_stages + pl->n_blocks + 1) +
+                         8 * (2 * TC_MAX_STAGES + 2 * TC_XT + 4 + 1 + 2) + 16 + 128 + sizeof(int) * ((pl->n_stages + 3) & ~3);
+    // resident mode: this CTA's half of the whole image stays in shared memory for the life of the kernel (when it fits)
+    static const bool res_env = !(getenv("NB200_TC_RES") && atoi(getenv("NB200_TC_RES")) == 0);
+    const bool res = pair && res_env && fixed + pl->img_bytes / 2 + 256 <= 227 * 1024;
+    a.res_bytes = res ? (int)(pl->img_bytes / 2) : 0;
     int ring = TC_MAX_STAGES;
     while (ring > 2 && fixed + (size_t)ring * a.slot_bytes > 227 * 1024) ring--;
-    const size_t smem = (fixed + (size_t)ring * a.slot_bytes + 127) / 128 * 128;
+    const size_t smem = ((res ? fixed + (size_t)a.res_bytes : fixed + (size_t)ring * a.slot_bytes) + 127) / 128 * 128;
     if (smem > 227 * 1024) return nb200_fail(ctx, NB200_ERR_ARG, "VMat too large for the tcgen05 background kernel");
     a.ring = ring;
     static const int stag_env = getenv("NB200_TC_STAGGER") ? atoi(getenv("NB200_TC_STAGGER")) : 2;
     a.stagger = stag_env < 0 ? -1 : std::min(std::min(stag_env, ring - 2), pl->n_stages - 1);
     static const bool tc_debug = getenv("NB200_TC_DEBUG") != nullptr;
-    void (*kern)(TcArgs) = pair ? (tc_debug ? k_nuc_bx_tc<true, true> : k_nuc_bx_tc<false, true>)
-                                : (tc_debug ? k_nuc_bx_tc<true, false> : k_nuc_bx_tc<false, false>);
+    void (*kern)(TcArgs) = res    ? (tc_debug ? k_nuc_bx_tc<true, true, true> : k_nuc_bx_tc<false, true, true>)
+                           : pair ? (tc_debug ? k_nuc_bx_tc<true, true, false> : k_nuc_bx_tc<false, true, false>)
+                                  : (tc_debug ? k_nuc_bx_tc<true, false, false> : k_nuc_bx_tc<false, false, false>);
     NB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps(ctx, b->stream, "k_nuc_bx_tc");
     const int n_items = a.n_chunks * a.tiles_per_chunk;
@@ -908,6 +1072,14 @@ int nb200_nuc_bx_tc(nb200_ctx *ctx, nb200_dbatch *b)
     dim3 grid(pair ? (unsigned)(2 * std::max(1, std::min(ctx->sm_count / 2, n_items))) : (unsigned)std::max(1, std::min(ctx->sm_count, n_items)));
     unsigned long long *d_dbg = nullptr;
     const size_t n_cta = grid.x;
+    static int *h_trap = nullptr;
+    if (tc_debug && !h_trap) {
+        NB_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&h_trap), 2100 * sizeof(int), cudaHostAllocMapped));
+        memset(h_trap, 0, 2100 * sizeof(int));
+        int *d_trap = nullptr;
+        NB_CUDA(ctx, cudaHostGetDevicePointer(reinterpret_cast<void **>(&d_trap), h_trap, 0));
+        NB_CUDA(ctx, cudaMemcpyToSymbol(g_tc_trap_info, &d_trap, sizeof(d_trap)));
+    }
     if (tc_debug) {
         NB_CUDA(ctx, cudaMalloc(&d_dbg, n_cta * 8 * sizeof(unsigned long long)));
         NB_CUDA(ctx, cudaMemsetAsync(d_dbg, 0, n_cta * 8 * sizeof(unsigned long long), b->stream));
@@ -931,7 +1103,27 @@ int nb200_nuc_bx_tc(nb200_ctx *ctx, nb200_dbatch *b)
     NB_LAUNCH_CHECK(ctx);
     if (tc_debug) {  // developer aid: mean clock counts per CTA of the waits of each warp role
         std::vector<unsigned long long> h(n_cta * 8);
-        NB_CUDA(ctx, cudaStreamSynchronize(b->stream));
+        {
+            cudaError_t e = cudaStreamSynchronize(b->stream);
+            if (e != cudaSuccess) {   // which barriers starved (records of tc_trap)
+                fprintf(stderr, "[tc debug] kernel failed (%s); %d starving warps | bar_full of CTA0 0x%x CTA1 0x%x tmem 0x%x 0x%x; pair %d resident %d "
+                                "ring %d stages %d slabs %d grid %u\n", cudaGetErrorString(e), h_trap[0], h_trap[8], h_trap[10], h_trap[9], h_trap[11], pair,
+                        (int)res, ring, pl->n_stages, pl->n_achunks, grid.x);
+                int hist[2][16][32][2] = {};   // rank, warp, barrier slot, parity -> count
+                for (int i = 0; i < std::min(h_trap[0], 500); i++) {
+                    const int *r = h_trap + 16 + 4 * i;
+                    const int sl = ((r[2] & 0xffffff) - (h_trap[8] & 0xffffff)) / 8;
+                    if (sl >= 0 && sl < 32 && (r[1] >> 5) < 16) hist[r[0] & 1][r[1] >> 5][sl][r[3] & 1]++;
+                }
+                for (int rk = 0; rk < 2; rk++)
+                    for (int w = 0; w < 16; w++)
+                        for (int sl = 0; sl < 32; sl++)
+                            for (int pa = 0; pa < 2; pa++)
+                                if (hist[rk][w][sl][pa])
+                                    fprintf(stderr, "[tc debug]   rank %d warp %2d waits on barrier slot %2d parity %d: %d CTAs\n", rk, w, sl, pa, hist[rk][w][sl][pa]);
+                return nb200_cuda_fail(ctx, e, "k_nuc_bx_tc (debug sync)", __FILE__, __LINE__);
+            }
+        }
         NB_CUDA(ctx, cudaMemcpy(h.data(), d_dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         cudaFree(d_dbg);
         double m[8] = {0};
@@ -939,7 +1131,8 @@ int nb200_nuc_bx_tc(nb200_ctx *ctx, nb200_dbatch *b)
             for (int k = 0; k < 8; k++) m[k] += (double)h[8 * i + k];
         static const char *nm[8] = {"cta_total", "mma_wait_operands", "mma_wait_tmem_empty", "mma_wait_stage_full", "epi_wait_tmem_full",
                                     "epi_compute", "prep_wait_set_empty", "items"};
-        fprintf(stderr, "[tc debug] %zu CTAs, ring %d (%d stages, %d slabs per item):", n_cta, ring, pl->n_stages, pl->n_achunks);
+        fprintf(stderr, "[tc debug] %zu CTAs, pair %d resident %d (%d bytes), ring %d (%d stages, %d slabs per item), smem %zu:", n_cta, pair, (int)res,
+                a.res_bytes, ring, pl->n_stages, pl->n_achunks, smem);
         for (int k = 0; k < 8; k++) fprintf(stderr, " %s=%.0f", nm[k], m[k] / (double)n_cta);
         fprintf(stderr, "\n");
     }
