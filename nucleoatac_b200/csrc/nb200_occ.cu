@@ -740,6 +740,364 @@ __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle_search(OccMleArg
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same guarded search with ONE THREAD PER WINDOW (the default).  In the group form above the search logic -- a few
+// hundred instructions of index arithmetic, shuffles and votes per window -- is executed by all 32 lanes for 4 windows, and
+// ncu shows it, not the fp64 pipe, bounding the kernel (19 % of the instructions were DFMA / DMUL).  Here a lane owns a
+// window outright: it prepares the window's fragments once into its own column of a shared-memory cache, evaluates 16
+// grid points per round as 16 independent product chains (one 16-byte load per fragment and round), and runs the search
+// logic for itself -- no shuffles, no votes, no barriers; the logic is paid once per window by one lane.  The arithmetic
+// per (window, grid point) is the group kernel's, operation for operation, so the results are bit-identical.
+// Rounds: 0 coarse (16 evenly spaced points), 1 the unknown points between the neighbours of the best coarse point,
+// 2 the two coarse intervals in which pass / fail changes; a window with a rounding-level tie scans the whole grid
+// (stages 3.. for the maximum, then for the interval) while the other lanes of its warp wait.
+#define MTW_THREADS 128
+#ifndef MTW_CAP
+#define MTW_CAP 48
+#endif
+// branch-free forms for the per-lane search logic (no short-circuit evaluation: the logic is straight-line selects)
+__device__ __forceinline__ bool keyx_gt(int ae, double am, int be, double bm) { return (ae > be) | ((ae == be) & (am > bm)); }
+__device__ __forceinline__ MleKey keyx_scale(const MleKey &k, double f)   // k * f for f in (0.5, 2), canonical; -inf stays -inf
+{
+    MleKey r;
+    double m = k.m * f;
+    int e = k.e;
+    const bool lo = m < 1.0, hi = m >= 2.0;
+    m = lo ? m * 2.0 : (hi ? m * 0.5 : m);
+    e += hi ? 1 : (lo ? -1 : 0);
+    r.e = (k.e == INT_MIN) ? INT_MIN : e;
+    r.m = (k.e == INT_MIN) ? 0.0 : m;
+    return r;
+}
+template <int LB>
+__global__ void __launch_bounds__(MTW_THREADS, LB) k_occ_mle_tw(OccMleArgs a)
+{
+    extern __shared__ __align__(16) double sm_mle[];   // pn[upper], pf[upper], alphas[n_alpha] | cache (d, q)[MTW_CAP][MTW_THREADS]
+    const int up2 = (a.upper + 1) & ~1, na2 = (a.n_alpha + 1) & ~1;
+    double *s_pn = sm_mle, *s_pf = sm_mle + up2, *s_al = sm_mle + 2 * up2;
+    double2 *cache = reinterpret_cast<double2 *>(sm_mle + 2 * up2 + na2) + threadIdx.x;   // entry f of this lane at cache[f * MTW_THREADS]
+    for (int i = threadIdx.x; i < a.upper; i += MTW_THREADS) {
+        s_pn[i] = a.pn[i];
+        s_pf[i] = a.pf[i];
+    }
+    for (int i = threadIdx.x; i < a.n_alpha; i += MTW_THREADS) s_al[i] = a.alphas[i];
+    __syncthreads();
+    const int c = blockIdx.y;
+    const int64_t oo = a.out_off[c];
+    const int L = (int)(a.out_off[c + 1] - oo);
+    const int nwin = (L - a.halfstep + a.step - 1) / a.step;
+    const int wi = blockIdx.x * MTW_THREADS + threadIdx.x;
+    if (wi >= nwin) return;
+    const int32_t *cp = a.col_ptr + a.col_off[c];
+    const int2 *en = a.ent + a.frag_off[c];
+    const int NA = a.n_alpha, last = NA - 1;
+    const int t = a.halfstep + wi * a.step;
+    const int e0 = cp[t - a.flank + a.csc_pad], e1 = cp[t + a.flank + 1 + a.csc_pad];
+    const int n = e1 - e0;
+    double SN = a.sn_nobias, SF = a.sf_nobias;
+    if (a.use_bias) {
+        const int64_t wo = oo / a.step + c + wi;
+        SN = a.wsn[wo];
+        SF = a.wsf[wo];
+    }
+    const double rSN = 1.0 / SN, rSF = 1.0 / SF;
+    // fragment f: nuc_probs / sum, nfr_probs / sum (Occupancy.py:106-109), the pair scaled by a power of two so that
+    // max(p, q) is in [1, 2) (exact, constant in alpha)
+    auto prep = [&](int f, double &pv, double &qv) {
+        const int sz = en[e0 + f].y;
+        pv = s_pn[sz] * rSN;
+        qv = s_pf[sz] * rSF;
+        const long long mb = __double_as_longlong(fmax(pv, qv));
+        const int e2 = (int)((mb >> 52) & 0x7ff);
+        if (e2 > 0 && e2 < 0x7fe) {
+            const double sc = __longlong_as_double((long long)(2046 - e2) << 52);
+            pv *= sc;
+            qv *= sc;
+        }
+    };
+    auto renorm = [](double &m, int &x) {
+        const long long bits = __double_as_longlong(m);
+        const int e2 = (int)((bits >> 52) & 0x7ff);
+        if (e2 != 0 && e2 != 0x7ff) {
+            x += e2 - 1023;
+            m = __longlong_as_double(bits - ((long long)(e2 - 1023) << 52));
+        }
+    };
+    auto canon = [&](bool dead, double m, int x) {
+        MleKey k;
+        const bool alive = !dead & (m > 0.0);   // zero / NaN products: log = -inf / NaN -> -inf (Occupancy.py:112-114)
+        const bool sub = m < 2.2250738585072014e-308;   // subnormal: make it normal first
+        m = sub ? m * 18446744073709551616.0 : m;      // 2^64
+        x = sub ? x - 64 : x;
+        const long long bits = __double_as_longlong(m);
+        const int e2 = (int)((bits >> 52) & 0x7ff);
+        k.e = alive ? x + e2 - 1023 : INT_MIN;
+        k.m = alive ? __longlong_as_double((bits & 0x800fffffffffffffLL) | 0x3ff0000000000000LL) : 0.0;
+        return k;
+    };
+    // ---- the window's fragments, once: cache (p - q, q); the product of the p's is L(alpha = 1) (q + (p - q) would lose p << q)
+    MleKey key_one;
+    {
+        double m1 = 1.0;
+        int x1 = 0;
+        for (int f0 = 0; f0 < n; f0 += 4) {   // four fragments at a time: their size loads are in flight together
+            int sz[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) sz[u] = (f0 + u < n) ? en[e0 + f0 + u].y : 0;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int f = f0 + u;
+                if (f < n) {
+                    double pv = s_pn[sz[u]] * rSN, qv = s_pf[sz[u]] * rSF;
+                    const long long mb = __double_as_longlong(fmax(pv, qv));
+                    const int e2 = (int)((mb >> 52) & 0x7ff);
+                    if (e2 > 0 && e2 < 0x7fe) {
+                        const double sc = __longlong_as_double((long long)(2046 - e2) << 52);
+                        pv *= sc;
+                        qv *= sc;
+                    }
+                    if (f < MTW_CAP) cache[f * MTW_THREADS] = make_double2(pv - qv, qv);
+                    m1 *= pv;
+                    if ((f & 31) == 31) renorm(m1, x1);
+                }
+            }
+        }
+        key_one = canon(a.both_zero || a.pn_has_zero, m1, x1);
+    }
+    // ---- 16 grid points (index -1: none) -> canonical keys
+    // ---- 16 grid points idx[] (-1: none) -> canonical keys Ke[], Km[] (straight-line code, used by every round below)
+#define MTW_EVAL16()                                                                                                       \
+    {                                                                                                                      \
+        double al[16];                                                                                                     \
+        _Pragma("unroll") for (int k = 0; k < 16; k++)                                                                     \
+        {                                                                                                                  \
+            al[k] = (idx[k] >= 0) ? s_al[idx[k]] : 0.5;                                                                    \
+            Km[k] = 1.0;                                                                                                   \
+            Ke[k] = 0;                                                                                                     \
+        }                                                                                                                  \
+        const int nc = min(n, MTW_CAP);                                                                                    \
+        for (int f0 = 0; f0 < nc; f0 += 32) { /* 32 factors (each in (2^-7, 2) away from the grid ends), then exponents out */ \
+            const int f1 = min(f0 + 32, nc);                                                                               \
+            _Pragma("unroll 2") for (int f = f0; f < f1; f++)                                                              \
+            {                                                                                                              \
+                const double2 u = cache[f * MTW_THREADS];                                                                  \
+                _Pragma("unroll") for (int k = 0; k < 16; k++) Km[k] *= fma(al[k], u.x, u.y);                              \
+            }                                                                                                              \
+            _Pragma("unroll") for (int k = 0; k < 16; k++) renorm(Km[k], Ke[k]);                                           \
+        }                                                                                                                  \
+        _Pragma("unroll 1") for (int f = MTW_CAP; f < n; f++) { /* more fragments than the cache holds: prepared again */  \
+            double pv, qv;                                                                                                 \
+            prep(f, pv, qv);                                                                                               \
+            const double dv = pv - qv;                                                                                     \
+            _Pragma("unroll") for (int k = 0; k < 16; k++) Km[k] *= fma(al[k], dv, qv);                                    \
+            if ((f & 31) == 31) {                                                                                          \
+                _Pragma("unroll") for (int k = 0; k < 16; k++) renorm(Km[k], Ke[k]);                                       \
+            }                                                                                                              \
+        }                                                                                                                  \
+        _Pragma("unroll") for (int k = 0; k < 16; k++)                                                                     \
+        {                                                                                                                  \
+            const bool dead = (idx[k] < 0) || a.both_zero || (al[k] == 0.0 && a.pf_has_zero) || (al[k] == 1.0 && a.pn_has_zero); \
+            const MleKey kk = (al[k] == 1.0 && idx[k] >= 0) ? key_one : canon(dead, Km[k], Ke[k]);                         \
+            Ke[k] = kk.e;                                                                                                  \
+            Km[k] = kk.m;                                                                                                  \
+        }                                                                                                                  \
+    }
+    const int BIG = 1 << 30;
+    auto mk = [](int e, double m) {
+        MleKey k;
+        k.e = e;
+        k.m = m;
+        return k;
+    };
+    MleKey bk = mk(INT_MIN, 0.0), th = mk(INT_MIN, 0.0), th_lo = th, th_hi = th;
+    int bi = BIG, okmin = BIG, okmax = -1;
+    bool tie = false, none = true;
+    auto take = [&](int ke, double km, int i) {   // first maximum: larger key, ties to the smaller grid index
+        const bool better = (i >= 0) & (keyx_gt(ke, km, bk.e, bk.m) | ((ke == bk.e) & (km == bk.m) & (i < bi)));
+        bk.e = better ? ke : bk.e;
+        bk.m = better ? km : bk.m;
+        bi = better ? i : bi;
+    };
+    auto set_threshold = [&]() {   // max * exp(-cutoff / 2), canonical; nothing passes when the maximum is -inf or the cutoff NaN
+        none = (bk.e == INT_MIN) || !(a.thr_m == a.thr_m);
+        th = mk(INT_MIN, 0.0);
+        if (!none) {
+            if (a.thr_zero) {
+                th.e = INT_MIN + 1;
+            } else {
+                th.m = bk.m * a.thr_m;
+                th.e = bk.e + a.thr_e;
+                if (th.m >= 2.0) {
+                    th.m *= 0.5;
+                    th.e += 1;
+                }
+            }
+        }
+        // a likelihood within MLS_TIE (relative) of the threshold is a rounding-level tie: band (th_lo, th_hi)
+        const bool band = !none && !a.thr_zero;
+        th_lo = band ? keyx_scale(th, 1.0 - MLS_TIE) : mk(INT_MAX, 0.0);
+        th_hi = band ? keyx_scale(th, 1.0 + MLS_TIE) : mk(INT_MIN, 0.0);
+    };
+    auto note = [&](int ke, double km, int i, bool check_tie) {
+        const bool p = (i >= 0) & !none & keyx_gt(ke, km, th.e, th.m);
+        okmin = p ? min(okmin, i) : okmin;
+        okmax = p ? max(okmax, i) : okmax;
+        if (check_tie) tie = tie | ((i >= 0) & (ke != INT_MIN) & keyx_gt(ke, km, th_lo.e, th_lo.m) & keyx_gt(th_hi.e, th_hi.m, ke, km));
+        return p;
+    };
+    if (n > 0) {
+        int idx[16], Ke[16];
+        double Km[16];
+        // ---- round 0: coarse points c_k = (k * last) / 15
+#pragma unroll
+        for (int k = 0; k < 16; k++) idx[k] = (k * last) / 15;
+        MTW_EVAL16();
+        int cke[16];
+        double ckm[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            cke[k] = Ke[k];
+            ckm[k] = Km[k];
+            take(Ke[k], Km[k], idx[k]);
+        }
+        int bj = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            if (idx[k] == bi) bj = k;
+        {   // a coarse neighbour of the best coarse point within MLS_TIE of it (or above): rounding-level tie
+            const MleKey b_lo = keyx_scale(bk, 1.0 - MLS_TIE);
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                tie = tie | (((k == bj - 1) | (k == bj + 1)) & (bk.e != INT_MIN) & (cke[k] != INT_MIN) & !keyx_gt(b_lo.e, b_lo.m, cke[k], ckm[k]));
+        }
+        const int LO = (bj > 0) ? ((bj - 1) * last) / 15 : 0, HI = (bj < 15) ? ((bj + 1) * last) / 15 : last;
+        // ---- round 1: the unknown points strictly inside (LO, HI) but the best coarse point (coarse spacing <= 8: at most 14)
+        {
+            const int lo_u = LO + ((bj > 0) ? 1 : 0), hi_u = HI - ((bj < 15) ? 1 : 0);
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                int i = lo_u + k;
+                if (i >= bi) i++;                       // skip the best coarse point
+                idx[k] = (i <= hi_u && bk.e != INT_MIN) ? i : -1;
+                any = any || idx[k] >= 0;
+            }
+            if (any) {
+                MTW_EVAL16();
+#pragma unroll
+                for (int k = 0; k < 16; k++) take(Ke[k], Km[k], idx[k]);
+            }
+            set_threshold();
+            if (any) {
+#pragma unroll
+                for (int k = 0; k < 16; k++) note(Ke[k], Km[k], idx[k], true);
+            }
+        }
+        unsigned cpass = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            if (note(cke[k], ckm[k], (k * last) / 15, true)) cpass |= 1u << k;
+        // ---- round 2: the coarse intervals in which pass / fail changes
+        {
+            int l_from = -1, l_to = -2, r_from = -1, r_to = -2;
+            if (!none && bj > 1 && ((cpass >> (bj - 1)) & 1)) {          // LO passes: the last failing coarse point below it
+                const unsigned failing = ~cpass & ((1u << (bj - 1)) - 1u);
+                if (failing) {
+                    const int jf = 31 - __clz(failing);
+                    l_from = (jf * last) / 15 + 1;
+                    l_to = ((jf + 1) * last) / 15 - 1;
+                }
+            }
+            if (!none && bj < 14 && ((cpass >> (bj + 1)) & 1)) {         // HI passes: the first failing coarse point above it
+                const unsigned failing = ~cpass & 0xffffu & ~((2u << (bj + 1)) - 1u);
+                if (failing) {
+                    const int jf = __ffs(failing) - 1;
+                    r_from = ((jf - 1) * last) / 15 + 1;
+                    r_to = (jf * last) / 15 - 1;
+                }
+            }
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                idx[k] = (l_from + k <= l_to) ? l_from + k : -1;
+                idx[8 + k] = (r_from + k <= r_to) ? r_from + k : -1;
+                any = any || idx[k] >= 0 || idx[8 + k] >= 0;
+            }
+            if (any) {
+                MTW_EVAL16();
+#pragma unroll
+                for (int k = 0; k < 16; k++) note(Ke[k], Km[k], idx[k], true);
+            }
+        }
+        // ---- rounding-level tie somewhere decisive: scan the whole grid, one grid point at a time, twice (maximum, then
+        // interval).  Rare, so small code matters more than speed here.
+        if (tie) {
+            auto eval1 = [&](int i) {
+                const double al1 = s_al[i];
+                double m = 1.0;
+                int x = 0;
+#pragma unroll 1
+                for (int f = 0; f < n; f++) {
+                    double dv, qv;
+                    if (f < MTW_CAP) {
+                        const double2 u = cache[f * MTW_THREADS];
+                        dv = u.x;
+                        qv = u.y;
+                    } else {
+                        double pv;
+                        prep(f, pv, qv);
+                        dv = pv - qv;
+                    }
+                    m *= fma(al1, dv, qv);
+                    if ((f & 31) == 31) renorm(m, x);
+                }
+                const bool dead = a.both_zero || (al1 == 0.0 && a.pf_has_zero) || (al1 == 1.0 && a.pn_has_zero);
+                return (al1 == 1.0) ? key_one : canon(dead, m, x);
+            };
+            bk = mk(INT_MIN, 0.0);
+            bi = BIG;
+#pragma unroll 1
+            for (int i = 0; i < NA; i++) {
+                const MleKey k1 = eval1(i);
+                take(k1.e, k1.m, i);
+            }
+            set_threshold();
+            okmin = BIG;
+            okmax = -1;
+#pragma unroll 1
+            for (int i = 0; i < NA; i++) {
+                const MleKey k1 = eval1(i);
+                note(k1.e, k1.m, i, false);
+            }
+        }
+    }
+#undef MTW_EVAL16
+    double occ = nb_nan(), lo = nb_nan(), hi = nb_nan();
+    if (n > 0 && okmax >= 0 && bi >= 0 && bi < NA) {  // Occupancy.py:141 `if sum(new_inserts)>0`
+        occ = s_al[bi];
+        lo = s_al[okmin];
+        hi = s_al[okmax];
+    }
+    if (a.wv) {   // per-window values (the block smoother's input): window wi of chunk c at oo / step + c + wi
+        const int64_t wo = oo / a.step + c + wi;
+        a.wv[wo] = occ;
+        a.wv[a.wv_stride + wo] = lo;
+        a.wv[2 * a.wv_stride + wo] = hi;
+    }
+    const int left = t - a.halfstep, right = min(t + a.halfstep + 1, L);
+    for (int x = left; x < right; x++) {
+        a.vals[oo + x] = occ;
+        a.lower[oo + x] = lo;
+        a.upper_b[oo + x] = hi;
+    }
+    if (wi == nwin - 1)  // positions past the last window stay NaN (np.ones(n)*nan, Occupancy.py:133-135)
+        for (int x = right; x < L; x++) {
+            a.vals[oo + x] = nb_nan();
+            a.lower[oo + x] = nb_nan();
+            a.upper_b[oo + x] = nb_nan();
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
 // OccupancyTrack.makeSmoothed (Occupancy.py:147-153 -> pyatac/utils.py:23-52, mode 'same', norm) on the per-window values.
 // The unsmoothed tracks are constant over blocks of `step` positions (block k = window k covers [k S, k S + S), Occupancy.py
 // :142-146), so the 2 flank + 1 taps of an output collapse to ~(2 flank + 1) / S + 1 block taps:
@@ -765,6 +1123,7 @@ __global__ void __launch_bounds__(SB_THREADS) k_occ_smooth_blocks(const double *
     const int nTp = (nTs + 1) & ~1;
     double *s_T = sm_sb;                             // [nTp], s_T[i + padL] = T[i]
     double2 *s_v = reinterpret_cast<double2 *>(sm_sb + nTp);   // [(SB_THREADS + 2 R)][2]: (V0, V1), (V2, I)
+    int *s_cnt = reinterpret_cast<int *>(s_v + 2 * (SB_THREADS + 2 * R));   // [SB_THREADS + 2 R + 1] prefix count of missing blocks
     const int c = blockIdx.y;
     const int64_t oo = out_off[c];
     const int L = (int)(out_off[c + 1] - oo);
@@ -805,6 +1164,18 @@ __global__ void __launch_bounds__(SB_THREADS) k_occ_smooth_blocks(const double *
         s_v[2 * i + 1] = make_double2(v2, pres);
     }
     __syncthreads();
+    if (threadIdx.x < 32) {   // s_cnt[i] = missing blocks among tile slots [0, i)
+        int run = 0;
+        for (int i0 = 0; i0 < SB_THREADS + 2 * R; i0 += 32) {
+            const int i = i0 + threadIdx.x;
+            const bool bad = i < SB_THREADS + 2 * R && s_v[2 * i + 1].y == 0.0;
+            const unsigned mk = __ballot_sync(NB_FULL, bad);
+            if (i <= SB_THREADS + 2 * R) s_cnt[i] = run + __popc(mk & ((1u << threadIdx.x) - 1u));
+            run += __popc(mk);
+        }
+        if (threadIdx.x == 0) s_cnt[SB_THREADS + 2 * R] = run;
+    }
+    __syncthreads();
     const int b0 = bt0 + threadIdx.x;
     if (b0 >= nblk) return;
     const int n0 = b0 * S;
@@ -814,8 +1185,7 @@ __global__ void __launch_bounds__(SB_THREADS) k_occ_smooth_blocks(const double *
     // track has plateaus on which call_peaks' 1e-12 jitter (utils.py:94-97) decides, and the last bit must not depend
     // on which smoother ran.
     const bool partial = (int64_t)nwin * S > L;
-    bool slow = partial && b0 + R >= nwin - 1;
-    for (int d = -R; d <= R && !slow; d++) slow = s_v[2 * (threadIdx.x + R + d) + 1].y == 0.0;
+    const bool slow = (partial && b0 + R >= nwin - 1) || s_cnt[threadIdx.x + 2 * R + 1] != s_cnt[threadIdx.x];   // a missing block in [b0 - R, b0 + R]
     if (slow) {
         const int dlo = -((wlen - h) & ~1);
         const int T2 = (h - dlo + 2) & ~1;
@@ -1186,12 +1556,24 @@ int nb200_occ_run(nb200_ctx *ctx, nb200_dbatch *b)
         a.wv_stride = (int64_t)(tl / p.step + n + 2);
         NB_CUDA(ctx, b->o_wv.reserve(sizeof(double) * 3 * (size_t)a.wv_stride));
         a.wv = b->o_wv.as<double>();
-        const bool mle_full = getenv("NB200_MLE_FULL") != nullptr;   // developer switch: scan the whole grid for every window
-        const bool mle_search = !mle_full && r.n_alpha >= 17 && r.n_alpha <= 121;   // 3 rounds of 16 grid points need a coarse spacing <= 8
-        ProfScope ps(ctx, b->stream, mle_search ? "k_occ_mle_search" : "k_occ_mle");
+        // Three kernels return bit-identical grids.  The scan of all grid points (k_occ_mle) is the default: the guarded
+        // searches do 48 instead of 104 evaluations per window, but their search logic costs more instructions than the
+        // evaluations it saves (measured per 20 Mbp: scan 3.29 ms, one thread per window 3.61 ms, 8 lanes per window 3.72 ms).
+        // NB200_MLE_SEARCH=tw | group selects a search (grids of 17..121 points: its 16 coarse points need a spacing <= 8).
+        const char *mle_env = getenv("NB200_MLE_SEARCH");
+        const bool mle_search = mle_env && (!strcmp(mle_env, "tw") || !strcmp(mle_env, "group")) && r.n_alpha >= 17 && r.n_alpha <= 121;
+        const bool mle_group = mle_search && !strcmp(mle_env, "group");
+        ProfScope ps(ctx, b->stream, mle_search ? (mle_group ? "k_occ_mle_search" : "k_occ_mle_tw") : "k_occ_mle");
         dim3 grid((unsigned)div_up64(max_win, MLE_WARPS * MLE_GROUPS * MLE_ITERS), n);
         static const int mle_lb = getenv("NB200_MLE_LB") ? atoi(getenv("NB200_MLE_LB")) : 4;
-        if (mle_search) {
+        if (mle_search && !mle_group) {   // one thread per window
+            const size_t smem_t = sizeof(double) * (2 * (size_t)((p.upper + 1) & ~1) + (size_t)((r.n_alpha + 1) & ~1)) + sizeof(double2) * (size_t)MTW_CAP * MTW_THREADS;
+            static const int mtw_lb = getenv("NB200_MTW_LB") ? atoi(getenv("NB200_MTW_LB")) : 2;
+            auto kern = mtw_lb >= 3 ? k_occ_mle_tw<3> : (mtw_lb == 2 ? k_occ_mle_tw<2> : k_occ_mle_tw<1>);
+            NB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+            dim3 tgrid((unsigned)div_up64(max_win, MTW_THREADS), n);
+            kern<<<tgrid, MTW_THREADS, smem_t, b->stream>>>(a);
+        } else if (mle_search) {
             const size_t smem_s = sizeof(double) * 2 * (size_t)((p.upper + 1) & ~1) + sizeof(double2) * (size_t)MLE_WARPS * MLE_GROUPS * MLS_GROUP_STRIDE;
             static const int mls_lb = getenv("NB200_MLS_LB") ? atoi(getenv("NB200_MLS_LB")) : 4;
             auto kern = mls_lb >= 6 ? k_occ_mle_search<6> : (mls_lb == 5 ? k_occ_mle_search<5> : k_occ_mle_search<4>);
@@ -1217,7 +1599,8 @@ int nb200_occ_run(nb200_ctx *ctx, nb200_dbatch *b)
         const bool dense_smooth = getenv("NB200_OCC_SMOOTH_DENSE") != nullptr;   // developer switch: tap-by-tap smoothing
         if (p.step == 5 && !dense_smooth) {   // block form on the per-window values (the default step)
             const int R = ((p.smooth_len - 1) / 2 + 4) / 5;
-            const size_t smem = sizeof(double) * (size_t)(((2 * R + 1) * 5 + 1) & ~1) + sizeof(double2) * 2 * (size_t)(SB_THREADS + 2 * R);
+            const size_t smem = sizeof(double) * (size_t)(((2 * R + 1) * 5 + 1) & ~1) + sizeof(double2) * 2 * (size_t)(SB_THREADS + 2 * R) +
+                                sizeof(int) * (size_t)(SB_THREADS + 2 * R + 4);
             if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_occ_smooth_blocks<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ProfScope ps(ctx, b->stream, "k_occ_smooth_blocks");
             dim3 grid((unsigned)div_up64(div_up64(b->max_len, 5), SB_THREADS), n);

@@ -49,17 +49,25 @@ def _occ(eng, pb, env=None):
 
 @pytest.mark.parametrize("use_bias", [True, False])
 def test_occ_search_equals_full_scan(eng, use_bias):
-    """k_occ_mle_search (3 rounds of 16 grid points, Occupancy.py:104-120) must return what the scan of all 101 grid points
-    returns -- bit for bit, on every window -- and the block-form smoother what the tap-by-tap smoother returns."""
+    """The guarded searches over the alpha grid (3 rounds of 16 grid points, Occupancy.py:104-120; NB200_MLE_SEARCH=tw: one
+    thread per window, =group: 8 lanes per window) must return what the default scan of all 101 grid points returns -- bit
+    for bit, on every window -- and the block-form smoother what the tap-by-tap smoother returns."""
     from nucleoatac_b200 import synth
     wl = synth.Workload(251, 251)
     wl.configure(eng, use_bias=use_bias)
     pb = _mixed_batch()
     new, prof_new = _occ(eng, pb)
-    full, prof_full = _occ(eng, pb, {"NB200_MLE_FULL": "1", "NB200_OCC_SMOOTH_DENSE": "1"})
+    tw, prof_tw = _occ(eng, pb, {"NB200_MLE_SEARCH": "tw"})
+    grp, prof_grp = _occ(eng, pb, {"NB200_MLE_SEARCH": "group"})
+    full, prof_full = _occ(eng, pb, {"NB200_OCC_SMOOTH_DENSE": "1"})
     ran = lambda prof, k: prof.get(k, (0, 0.0))[0] > 0      # launches since profile_reset
-    assert ran(prof_new, "k_occ_mle_search") and ran(prof_new, "k_occ_smooth_blocks") and not ran(prof_new, "k_occ_mle")
-    assert ran(prof_full, "k_occ_mle") and ran(prof_full, "k_smooth_same") and not ran(prof_full, "k_occ_mle_search")
+    assert ran(prof_new, "k_occ_mle") and ran(prof_new, "k_occ_smooth_blocks") and not ran(prof_new, "k_occ_mle_tw")
+    assert ran(prof_tw, "k_occ_mle_tw") and not ran(prof_tw, "k_occ_mle")
+    assert ran(prof_grp, "k_occ_mle_search") and not ran(prof_grp, "k_occ_mle_tw")
+    assert ran(prof_full, "k_occ_mle") and ran(prof_full, "k_smooth_same") and not ran(prof_full, "k_occ_smooth_blocks")
+    for other, what in ((tw, "thread-per-window search"), (grp, "group search")):
+        for key in ("vals", "lower_bound", "upper_bound", "smoothed_vals", "smoothed_lower", "smoothed_upper", "peak_pos", "peak_count"):
+            assert np.array_equal(new[key], other[key], equal_nan=True), (what, key)
     nwin = 0
     for key in ("vals", "lower_bound", "upper_bound"):
         assert np.array_equal(new[key], full[key], equal_nan=True), key
@@ -102,8 +110,8 @@ def test_occ_search_equals_full_scan(eng, use_bias):
 
 
 def test_occ_search_other_grids(eng):
-    """Grids other than linspace(0, 1, 101): 17 and 121 points go through the search, 16 / 122 points take the scan; a
-    cutoff of 0 (nothing but the maximum passes) and a huge one (everything passes)."""
+    """Grids other than linspace(0, 1, 101): 17, 64 and 121 points go through the search; a cutoff of 0 (nothing but the maximum
+    passes) and a huge one (everything passes)."""
     from nucleoatac_b200 import synth
     wl = synth.Workload(251, 251)
     wl.configure(eng, use_bias=True)
@@ -111,11 +119,13 @@ def test_occ_search_other_grids(eng):
     for n_alpha, cutoff in ((17, None), (121, None), (101, 0.0), (101, 1e9), (64, 2.0)):
         eng.set_occ_model(wl.nuc_probs, wl.nfr_probs, alphas=np.linspace(0, 1, n_alpha), cutoff=cutoff)
         eng.configure_occ(upper=wl.upper, use_bias=True)
-        new, prof = _occ(eng, pb)
-        full, _ = _occ(eng, pb, {"NB200_MLE_FULL": "1"})
-        assert prof.get("k_occ_mle_search", (0, 0.0))[0] > 0
+        full, _ = _occ(eng, pb)
+        tw, prof = _occ(eng, pb, {"NB200_MLE_SEARCH": "tw"})
+        grp, _ = _occ(eng, pb, {"NB200_MLE_SEARCH": "group"})
+        assert prof.get("k_occ_mle_tw", (0, 0.0))[0] > 0
         for key in ("vals", "lower_bound", "upper_bound"):
-            assert np.array_equal(new[key], full[key], equal_nan=True), (n_alpha, cutoff, key)
+            assert np.array_equal(tw[key], full[key], equal_nan=True), (n_alpha, cutoff, key, "tw")
+            assert np.array_equal(grp[key], full[key], equal_nan=True), (n_alpha, cutoff, key, "group")
     wl.configure(eng, use_bias=True)
 
 
@@ -202,11 +212,15 @@ def test_batches_in_flight_give_identical_results(eng):
     for h in hs:
         eng.sync(h)
         eng.free_batch(h)
+    def valid(out, off, count, key):   # the filled slots of a capacity-sized table
+        return np.concatenate([out[key][int(o):int(o) + int(c)] for o, c in zip(out[off][:-1], out[count])] + [np.zeros(0, out[key].dtype)])
     for (n1, o1), (n2, o2) in zip(alone, outs):
         for k in ("norm_signal", "smoothed"):
             assert np.array_equal(n1[k].astype(np.float32), n2[k], equal_nan=True), k
-        for k in ("cand_pos", "cand_flag", "cand_count"):
-            assert np.array_equal(n1[k], n2[k]), k
+        assert np.array_equal(n1["cand_count"], n2["cand_count"])
+        for k in ("cand_pos", "cand_flag", "cand_z"):
+            assert np.array_equal(valid(n1, "cand_off", "cand_count", k), valid(n2, "cand_off", "cand_count", k), equal_nan=True), k
         for k in ("smoothed_vals", "smoothed_lower", "smoothed_upper"):
             assert np.array_equal(o1[k].astype(np.float32), o2[k], equal_nan=True), k
-        assert np.array_equal(o1["peak_pos"], o2["peak_pos"]) and np.array_equal(o1["nuc_dist"], o2["nuc_dist"])
+        assert np.array_equal(o1["peak_count"], o2["peak_count"]) and np.array_equal(o1["nuc_dist"], o2["nuc_dist"])
+        assert np.array_equal(valid(o1, "peak_off", "peak_count", "peak_pos"), valid(o2, "peak_off", "peak_count", "peak_pos"))
