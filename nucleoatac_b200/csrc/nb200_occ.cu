@@ -1122,8 +1122,9 @@ __global__ void __launch_bounds__(SB_THREADS) k_occ_smooth_blocks(const double *
     const int nTs = (2 * R + 1) * S;                 // stored entries: indices h - R S .. h + R S + S - 1
     const int nTp = (nTs + 1) & ~1;
     double *s_T = sm_sb;                             // [nTp], s_T[i + padL] = T[i]
-    double2 *s_v = reinterpret_cast<double2 *>(sm_sb + nTp);   // [(SB_THREADS + 2 R)][2]: (V0, V1), (V2, I)
-    int *s_cnt = reinterpret_cast<int *>(s_v + 2 * (SB_THREADS + 2 * R));   // [SB_THREADS + 2 R + 1] prefix count of missing blocks
+    double2 *s_vp = reinterpret_cast<double2 *>(sm_sb + nTp);  // [SB_THREADS + 2 R] (V0, V1) of every block in reach of the tile
+    double2 *s_vq = s_vp + (SB_THREADS + 2 * R);               // [SB_THREADS + 2 R] (V2, I): two arrays, so a warp's 16-byte loads are contiguous
+    int *s_cnt = reinterpret_cast<int *>(s_vq + (SB_THREADS + 2 * R));   // [SB_THREADS + 2 R + 1] prefix count of missing blocks
     const int c = blockIdx.y;
     const int64_t oo = out_off[c];
     const int L = (int)(out_off[c + 1] - oo);
@@ -1160,15 +1161,15 @@ __global__ void __launch_bounds__(SB_THREADS) k_occ_smooth_blocks(const double *
             } else
                 v0 = 0.0;
         }
-        s_v[2 * i] = make_double2(v0, v1);
-        s_v[2 * i + 1] = make_double2(v2, pres);
+        s_vp[i] = make_double2(v0, v1);
+        s_vq[i] = make_double2(v2, pres);
     }
     __syncthreads();
     if (threadIdx.x < 32) {   // s_cnt[i] = missing blocks among tile slots [0, i)
         int run = 0;
         for (int i0 = 0; i0 < SB_THREADS + 2 * R; i0 += 32) {
             const int i = i0 + threadIdx.x;
-            const bool bad = i < SB_THREADS + 2 * R && s_v[2 * i + 1].y == 0.0;
+            const bool bad = i < SB_THREADS + 2 * R && s_vq[i].y == 0.0;
             const unsigned mk = __ballot_sync(NB_FULL, bad);
             if (i <= SB_THREADS + 2 * R) s_cnt[i] = run + __popc(mk & ((1u << threadIdx.x) - 1u));
             run += __popc(mk);
@@ -1209,7 +1210,7 @@ __global__ void __launch_bounds__(SB_THREADS) k_occ_smooth_blocks(const double *
                     if (j >= 0 && j < nvalid) {
                         const int i = j / S - (bt0 - R);      // tile slot of the block
                         if (i >= 0 && i < SB_THREADS + 2 * R) {
-                            const double2 p = s_v[2 * i], q = s_v[2 * i + 1];
+                            const double2 p = s_vp[i], q = s_vq[i];
                             x0[e] = p.x;
                             x1[e] = p.y;
                             x2[e] = q.x;
@@ -1236,11 +1237,11 @@ __global__ void __launch_bounds__(SB_THREADS) k_occ_smooth_blocks(const double *
     double a0[S], a1[S], a2[S], dn[S];
 #pragma unroll
     for (int u = 0; u < S; u++) a0[u] = a1[u] = a2[u] = dn[u] = 0.0;
-    const double2 cp = s_v[2 * (threadIdx.x + R)], cq = s_v[2 * (threadIdx.x + R) + 1];   // centre block (V0, V1), (V2, 1)
+    const double2 cp = s_vp[threadIdx.x + R], cq = s_vq[threadIdx.x + R];   // centre block (V0, V1), (V2, 1)
     // block b0 + d contributes to output u through T[u - d S + h]; d runs over [-R, R]
     for (int d = -R; d <= R; d++) {
         const int i = threadIdx.x + R + d;
-        double2 p = s_v[2 * i], q = s_v[2 * i + 1];
+        double2 p = s_vp[i], q = s_vq[i];
         p.x -= cp.x;
         p.y -= cp.y;
         q.x -= cq.x;

@@ -22,16 +22,21 @@ __device__ __forceinline__ int vplot_col(int centre, int size, int c, int flank,
 }
 
 // One block per site.  Pass 1 (scale only): the site's in-plot fragment count; pass 2: add 1 (or 1 / count) per fragment.
-// Unscaled sums are integers in float64 and therefore exact whatever the order of the atomics.
+// Unscaled sums are integers in float64 and therefore exact whatever the order of the atomics.  Scaled sums (a site adds
+// 1 / count per fragment, make_vplot.py:34-35) are accumulated as 128-bit fixed-point integers -- units of 2^-64, a low word
+// with its carries counted into a high word -- because integer addition commutes: the result does not depend on the order in
+// which the sites' atomics land (a floating-point atomicAdd would make the last bits vary from run to run), and it is
+// closer to the exact sum (each term is off by < 2^-64) than a float64 sum in any order.
 __global__ void __launch_bounds__(256) k_vplot(const int32_t *__restrict__ centers, const int32_t *__restrict__ flips,
                                                const int64_t *__restrict__ frag_off, const int32_t *__restrict__ pos,
                                                const int32_t *__restrict__ tlen, int flank, int lower, int upper, int atac,
-                                               int scale, double *__restrict__ out, int32_t *__restrict__ empty_sites)
+                                               int scale, double *__restrict__ out, unsigned long long *__restrict__ fix,
+                                               int32_t *__restrict__ empty_sites)
 {
     __shared__ int red[32];
     const int s = blockIdx.x, c = centers[s], flip = flips[s], ncol = 2 * flank + 1;
     const int64_t f0 = frag_off[s], f1 = frag_off[s + 1];
-    double wgt = 1.0;
+    unsigned long long w_hi = 0, w_lo = 0;   // 1 / count in units of 2^-64
     if (scale) {
         int cnt = 0;
         for (int64_t f = f0 + threadIdx.x; f < f1; f += blockDim.x) {
@@ -48,15 +53,35 @@ __global__ void __launch_bounds__(256) k_vplot(const int32_t *__restrict__ cente
             if (threadIdx.x == 0) atomicAdd(empty_sites, 1);
             return;
         }
-        wgt = 1.0 / (double)cnt;
+        if (cnt == 1)
+            w_hi = 1;
+        else
+            w_lo = 0xffffffffffffffffull / (unsigned long long)cnt + ((0xffffffffffffffffull % (unsigned long long)cnt) + 1 == (unsigned long long)cnt ? 1 : 0);  // floor(2^64 / cnt)
     }
     for (int64_t f = f0 + threadIdx.x; f < f1; f += blockDim.x) {
         int l, i;
         frag_geometry(pos[f], tlen[f], atac, l, i);
         if (i < lower || i >= upper) continue;
         const int t = vplot_col(l + floordiv2(i - 1), i, c, flank, flip);
-        if (t >= 0) atomicAdd(&out[(size_t)(i - lower) * ncol + t], wgt);
+        if (t < 0) continue;
+        const size_t cell = (size_t)(i - lower) * ncol + t;
+        if (!scale) {
+            atomicAdd(&out[cell], 1.0);
+        } else {
+            if (w_lo) {
+                const unsigned long long old = atomicAdd(&fix[2 * cell], w_lo);
+                if (old + w_lo < old) atomicAdd(&fix[2 * cell + 1], 1ull);   // carry out of the low word
+            }
+            if (w_hi) atomicAdd(&fix[2 * cell + 1], w_hi);
+        }
     }
+}
+
+// fixed-point sums -> float64: hi + lo * 2^-64 (hi is a small integer, the conversion of lo rounds once)
+__global__ void k_vplot_finish(const unsigned long long *__restrict__ fix, size_t cells, double *__restrict__ out)
+{
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < cells) out[c] = (double)fix[2 * c + 1] + (double)fix[2 * c] * 5.421010862427522e-20;
 }
 
 // Fragment-centre histogram over the genomic columns [start - half, start - half + ncol), sizes in [lower, upper)
@@ -94,8 +119,10 @@ int nb200_vplot(nb200_ctx *ctx, int32_t n_sites, const int32_t *centers, const i
     NB_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t cells = (size_t)(upper - lower) * (2 * (size_t)flank + 1), bytes = sizeof(double) * cells;
     int32_t empty = 0;
-    NB_CUDA(ctx, ctx->s4.reserve(bytes + sizeof(int32_t)));
-    NB_CUDA(ctx, cudaMemsetAsync(ctx->s4.p, 0, bytes + sizeof(int32_t), ctx->stream));
+    // layout of s4: float64 plot | empty-site counter (padded to 16 bytes) | 128-bit fixed-point sums (scaled mode)
+    const size_t fix_off = bytes + 16, total = fix_off + (scale ? 2 * sizeof(unsigned long long) * cells : 0);
+    NB_CUDA(ctx, ctx->s4.reserve(total));
+    NB_CUDA(ctx, cudaMemsetAsync(ctx->s4.p, 0, total, ctx->stream));
     if (n_sites > 0) {
         const int64_t n = frag_off[n_sites];
         if (n > 0 && (!pos || !tlen)) return nb200_fail(ctx, NB200_ERR_ARG, "nb200_vplot: NULL read arrays");
@@ -109,8 +136,13 @@ int nb200_vplot(nb200_ctx *ctx, int32_t n_sites, const int32_t *centers, const i
             ProfScope ps(ctx, ctx->stream, "k_vplot");
             k_vplot<<<n_sites, 256, 0, ctx->stream>>>(ctx->s2.as<int32_t>(), ctx->s3.as<int32_t>(), ctx->flush.as<int64_t>(),
                                                       ctx->s0.as<int32_t>(), ctx->s1.as<int32_t>(), flank, lower, upper, atac, scale,
-                                                      ctx->s4.as<double>(), d_empty);
+                                                      ctx->s4.as<double>(), reinterpret_cast<unsigned long long *>(ctx->s4.as<char>() + fix_off), d_empty);
             NB_LAUNCH_CHECK(ctx);
+            if (scale) {
+                k_vplot_finish<<<(unsigned)div_up64((int64_t)cells, 256), 256, 0, ctx->stream>>>(
+                    reinterpret_cast<unsigned long long *>(ctx->s4.as<char>() + fix_off), cells, ctx->s4.as<double>());
+                NB_LAUNCH_CHECK(ctx);
+            }
         }
         NB_CUDA(ctx, cudaMemcpyAsync(&empty, d_empty, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     }

@@ -2,10 +2,13 @@
 the per-site V-plot matrix with the strand flip, the coverage helper and the insertion helper, literally as the
 reference computes them (dense float64 matrices).
 
-Parity status: these helpers are compositions of functions that are pinned (`make_fragment_mat` on
-tests/test_chunkmat2d.py, `get_insertions` on tests/test_tracks.py, `calculate_coverage` / `smooth` through the shipped
-example tracks); the reference holds no known-answer test or shipped output for the tools themselves, so the flip
-arithmetic below is pinned only by reading pyatac/chunkmat2d.py:41-54 (a literal, loop-for-loop restatement).
+Parity status: PINNED where the reference holds data -- `ins_chunk` reproduces the shipped example_results/example.ins.bedgraph.gz
+value for value (the track `nucleoatac nfr` wrote with the same InsertionTrack.calculateInsertions), `cov_chunk` the 160 read
+counts of the shipped example.occpeaks.bed.gz (OccChunk.cov at the peaks = the same CoverageTrack.calculateCoverage), `mat_get`
+without flip the reference's own known answer (tests/test_chunkmat2d.py:12-17); see tests/test_oracle_pyatac.py.  The reference
+holds NO vector for the strand flip of ChunkMat2D.get (chunkmat2d.py:41-54) nor for `pyatac vplot` as a whole (its only pyatac
+test is a smoke run of `pyatac sizes`, tests/test_cli.py:38-46; example.VMat comes from the bundled S. cer V-plot, not from
+example.bam): the flip below is a loop-for-loop restatement, checked by its mirror-image property.
 """
 import numpy as np
 

@@ -41,7 +41,15 @@ def test_vplot_primitive(lower, upper, flank, atac):
     assert got.shape == (upper - lower, 2 * flank + 1) and got.sum() > 0
     np.testing.assert_array_equal(got, exp)  # integer counts: bit-exact
     got = eng.vplot(centers, flips, off, np.concatenate(ps), np.concatenate(ts), flank, lower, upper, atac, True)
-    np.testing.assert_allclose(got, exp_scaled, rtol=1e-12, atol=1e-15)  # float sums, order of the atomics differs
+    np.testing.assert_allclose(got, exp_scaled, rtol=1e-12, atol=1e-15)  # the reference sums float64 terms site by site
+    # scaled sums are accumulated as 128-bit fixed-point integers: independent of the order of the atomics, so repeated runs
+    # (and the sites in another order) give bit-identical plots
+    for trial in range(3):
+        perm = np.random.default_rng(trial).permutation(len(centers))
+        off_p = np.concatenate(([0], np.cumsum([off[k + 1] - off[k] for k in perm])))
+        again = eng.vplot([centers[k] for k in perm], [flips[k] for k in perm], off_p, np.concatenate([ps[k] for k in perm]),
+                          np.concatenate([ts[k] for k in perm]), flank, lower, upper, atac, True)
+        assert np.array_equal(again, got), trial
     # a site without fragments under --scale: 0/0 in every cell of its matrix, the sum is NaN everywhere (make_vplot.py:34-35)
     off2 = off + [off[-1]]
     got = eng.vplot(centers + [10 ** 6], flips + [0], off2, np.concatenate(ps), np.concatenate(ts), flank, lower, upper, atac, True)

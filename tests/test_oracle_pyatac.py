@@ -50,3 +50,48 @@ def test_cov_chunk_is_windowed_centre_count():
         half, weff = window // 2, window + (window % 2 == 0)
         exp = np.array([np.sum(ok & (centre >= x - half) & (centre < x - half + weff)) for x in range(start, end)], dtype=float)
         np.testing.assert_array_equal(rp.cov_chunk(pos, tlen, start, end, lower, upper, window, float(window)), exp)
+
+
+# ----------------------------------------------------------------------------- pins on reference-held data
+def test_mat_get_reference_kat():
+    """ChunkMat2D.get without flip: the reference's own known answer (tests/test_chunkmat2d.py:12-17)."""
+    mat = np.zeros((200, 500))
+    mat[100, 5] = 1
+    np.testing.assert_array_equal(rp.mat_get(mat, 500, 0, 100, 102, 505, 507), np.array([[1, 0], [0, 0]]))
+
+
+def test_ins_chunk_reproduces_shipped_ins_track():
+    """`pyatac ins` without smoothing writes InsertionTrack.calculateInsertions (pyatac/get_ins.py:20-28 -> tracks.py:159-163);
+    the reference shipped exactly that track for the example regions as example_results/example.ins.bedgraph.gz
+    (written by `nucleoatac nfr`, NFRCalling.py:73-76).  The checker of the tool must reproduce it value for value."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nfr_golden.npz"))
+    n = len(z["chunk_start"])
+    total = 0
+    for i in range(n):
+        s, e = int(z["chunk_start"][i]), int(z["chunk_end"][i])
+        a, b = int(z["frag_off"][i]), int(z["frag_off"][i + 1])
+        t0, t1 = int(z["track_off"][i]), int(z["track_off"][i + 1])
+        start, vals = rp.ins_chunk(z["frag_pos"][a:b], z["frag_tlen"][a:b], s, e, 0, 2000)
+        assert start == s and len(vals) == t1 - t0
+        np.testing.assert_array_equal(vals, z["gold_ins"][t0:t1])
+        total += int(vals.sum())
+    assert total > 10000
+
+
+def test_cov_chunk_reproduces_shipped_occpeak_read_counts(example, golden):
+    """`pyatac cov` = CoverageTrack.calculateCoverage times scale / window (pyatac/get_cov.py:22-31).  The reference shipped 160
+    values of that very function (window 121, sizes [0, 251)): the `reads` column of example_results/example.occpeaks.bed.gz
+    is OccChunk.cov at the peak (Occupancy.py:155-168, 221-227).  With scale = window the tool's helper must give them."""
+    starts = np.array([example.chunk(i)[1] for i in range(example.n_chunks)])
+    ends = np.array([example.chunk(i)[2] for i in range(example.n_chunks)])
+    chroms = [example.chunk(i)[0] for i in range(example.n_chunks)]
+    hits = 0
+    for c, p, row in zip(golden["occpeaks_chrom"], golden["occpeaks_pos"], golden["occpeaks_vals"]):
+        cname = example.chrom_names[int(c)]
+        i = [k for k in range(example.n_chunks) if chroms[k] == cname and starts[k] <= p < ends[k]][0]
+        pos, tlen = example.reads(i)
+        got = rp.cov_chunk(pos, tlen, int(p), int(p) + 1, 0, 251, 121, 121.0)
+        assert got.shape == (1,) and got[0] == row[3], (cname, int(p), got, row[3])
+        hits += 1
+    assert hits == 160
