@@ -36,12 +36,17 @@ struct BlockReader {
     {
         if (zs_ok) inflateEnd(&zs);
     }
-    // append the next BGZF block to buf; false at end of file or on error (err set)
+    // append the next BGZF block to buf; false at a clean end of file (no byte left at a block boundary, err empty) or on
+    // error (err set: a file that stops in the middle of a block is truncated, not finished)
     bool next_block()
     {
         unsigned char head[18];
         ssize_t got = pread(fd, head, 18, (off_t)coff);
-        if (got < 18) return false;
+        if (got == 0) return false;
+        if (got < 18) {
+            err = got < 0 ? "read error" : "truncated BGZF block header";
+            return false;
+        }
         if (!(head[0] == 31 && head[1] == 139 && head[2] == 8 && head[3] == 4)) {
             err = "not a BGZF block";
             return false;
@@ -53,7 +58,10 @@ struct BlockReader {
             bsize = (head[16] | (head[17] << 8)) + 1u;
         else {
             std::vector<unsigned char> extra(xlen);
-            if (pread(fd, extra.data(), xlen, (off_t)coff + 12) < (ssize_t)xlen) return false;
+            if (pread(fd, extra.data(), xlen, (off_t)coff + 12) < (ssize_t)xlen) {
+                err = "truncated BGZF block header";
+                return false;
+            }
             for (unsigned o = 0; o + 4 <= xlen;) {
                 const unsigned slen = extra[o + 2] | (extra[o + 3] << 8);
                 if (extra[o] == 66 && extra[o + 1] == 67 && o + 6 <= xlen) bsize = (extra[o + 4] | (extra[o + 5] << 8)) + 1u;
@@ -70,6 +78,10 @@ struct BlockReader {
             return false;
         }
         const uint32_t isize = cbuf[clen + 4] | (cbuf[clen + 5] << 8) | (cbuf[clen + 6] << 16) | ((uint32_t)cbuf[clen + 7] << 24);
+        if (isize > 65536) {   // a BGZF block inflates to at most 64 KiB: anything else is a corrupt (or hostile) trailer
+            err = "BGZF block with an impossible uncompressed size";
+            return false;
+        }
         coff += bsize;
         if (isize == 0) return true;     // empty block (e.g. the EOF marker): nothing to append
         if (p > 0) {                      // drop what has been consumed
@@ -126,13 +138,19 @@ bool fetch_region(int fd, uint64_t voffset, int32_t tid, int32_t start, int32_t 
     }
     br.p = uoff;
     for (;;) {
-        if (!br.need(4)) break;
+        if (!br.need(4)) {
+            if (br.err.empty() && br.buf.size() - br.p > 0) br.err = "truncated BAM record";   // file ends inside a record length
+            break;
+        }
         const int32_t bs = rd_i32(br.buf.data() + br.p);
         if (bs < 32) {
             err = "corrupt BAM record";
             return false;
         }
-        if (!br.need(4 + (size_t)bs)) break;
+        if (!br.need(4 + (size_t)bs)) {
+            if (br.err.empty()) br.err = "truncated BAM record";   // the file ends in the middle of a record
+            break;
+        }
         const unsigned char *q = br.buf.data() + br.p + 4;
         const int32_t rtid = rd_i32(q), rpos = rd_i32(q + 4);
         const unsigned flag = q[14] | (q[15] << 8);

@@ -70,37 +70,53 @@ size_t bgzf_block(const unsigned char *src, size_t n, unsigned char *dst, int le
 
 const unsigned char BGZF_EOF[28] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0, 0x1b, 0, 0x03, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
-// deflate `data` as BGZF into `fh`; returns compressed offsets of every block (+ the end offset)
-bool bgzf_write(FILE *fh, const std::vector<unsigned char> &data, int threads, int level, std::vector<uint64_t> &coff)
+// deflate n bytes (whole BLOCK-sized blocks, the last one may be short) as BGZF blocks into `fh`, `threads` blocks at a
+// time; appends the compressed offset of every block to coff and advances pos
+bool bgzf_write_blocks(FILE *fh, const unsigned char *data, size_t n, int threads, int level, std::vector<uint64_t> &coff, uint64_t &pos)
 {
-    const size_t nblk = (data.size() + BLOCK - 1) / BLOCK;
+    const size_t nblk = (n + BLOCK - 1) / BLOCK;
+    if (threads < 1) threads = 1;
     std::vector<std::vector<unsigned char>> out(nblk);
     std::vector<size_t> olen(nblk, 0);
-    if (threads < 1) threads = 1;
-    const size_t wave = (size_t)threads * 64;
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++)
+        pool.emplace_back([&, t]() {
+            for (size_t b = (size_t)t; b < nblk; b += (size_t)threads) {
+                const size_t len = (b + 1) * BLOCK <= n ? BLOCK : n - b * BLOCK;
+                out[b].resize(65536);
+                olen[b] = bgzf_block(data + b * BLOCK, len, out[b].data(), level);
+            }
+        });
+    for (auto &th : pool) th.join();
+    for (size_t b = 0; b < nblk; b++) {
+        coff.push_back(pos);
+        if (fwrite(out[b].data(), 1, olen[b], fh) != olen[b]) return false;
+        pos += olen[b];
+    }
+    return true;
+}
+
+// deflate `data` as BGZF into `fh` with the EOF marker; returns compressed offsets of every block (+ the end offset)
+bool bgzf_write(FILE *fh, const std::vector<unsigned char> &data, int threads, int level, std::vector<uint64_t> &coff)
+{
     coff.clear();
     uint64_t pos = 0;
-    for (size_t b0 = 0; b0 < nblk; b0 += wave) {
-        const size_t b1 = b0 + wave < nblk ? b0 + wave : nblk;
-        std::vector<std::thread> pool;
-        for (int t = 0; t < threads; t++)
-            pool.emplace_back([&, t]() {
-                for (size_t b = b0 + (size_t)t; b < b1; b += (size_t)threads) {
-                    const size_t n = (b + 1) * BLOCK <= data.size() ? BLOCK : data.size() - b * BLOCK;
-                    out[b].resize(65536);
-                    olen[b] = bgzf_block(data.data() + b * BLOCK, n, out[b].data(), level);
-                }
-            });
-        for (auto &th : pool) th.join();
-        for (size_t b = b0; b < b1; b++) {
-            coff.push_back(pos);
-            if (fwrite(out[b].data(), 1, olen[b], fh) != olen[b]) return false;
-            pos += olen[b];
-            std::vector<unsigned char>().swap(out[b]);
-        }
-    }
+    if (!bgzf_write_blocks(fh, data.data(), data.size(), threads, level, coff, pos)) return false;
     coff.push_back(pos);
     return fwrite(BGZF_EOF, 1, 28, fh) == 28;
+}
+
+// decimal integer in [p, end) (no terminator needed: the text buffer is not NUL-terminated); returns the first byte after
+// the digits, or nullptr when there is no digit
+const char *parse_i64(const char *p, const char *end, int64_t &v)
+{
+    bool neg = false;
+    if (p < end && (*p == '-' || *p == '+')) neg = *p++ == '-';
+    if (p >= end || *p < '0' || *p > '9') return nullptr;
+    int64_t x = 0;
+    while (p < end && *p >= '0' && *p <= '9') x = x * 10 + (*p++ - '0');
+    v = neg ? -x : x;
+    return p;
 }
 
 // virtual offset of uncompressed position u; a position at the very end of the data is the start of the block that
@@ -125,63 +141,109 @@ int nb200_bgzip_tabix(const char *path_plain, const char *path_gz, int threads, 
     };
     FILE *in = fopen(path_plain, "rb");
     if (!in) return fail("cannot open the input file");
-    std::vector<unsigned char> data;
-    {
-        unsigned char buf[1 << 16];
-        size_t n;
-        while ((n = fread(buf, 1, sizeof(buf), in)) > 0) data.insert(data.end(), buf, buf + n);
+    FILE *out = fopen(path_gz, "wb");
+    if (!out) {
         fclose(in);
+        return fail("cannot open the output file");
     }
-    // ---- index from the text
+    // The file streams through in waves of whole BGZF blocks (genome-wide tracks are many GB, the reference streams them
+    // through tabix_compress too): a wave is deflated by the thread pool and written, and its rows are indexed by their
+    // uncompressed offsets; only the per-block compressed offsets and the index stay in memory.
+    if (threads < 1) threads = 1;
+    const size_t wave_bytes = (size_t)threads * 64 * BLOCK;
+    std::vector<unsigned char> wave(wave_bytes);
     std::vector<std::string> names;
     std::map<std::string, int> tid;
     std::vector<RefIndex> refs;
-    size_t p = 0;
-    const size_t N = data.size();
-    int cur = -1;
-    std::string cur_name;
-    while (p < N) {
-        const unsigned char *nl = (const unsigned char *)memchr(data.data() + p, '\n', N - p);
-        const size_t e = nl ? (size_t)(nl - data.data()) + 1 : N;
-        if (data[p] != '#' && e - p > 1) {
-            const unsigned char *t1 = (const unsigned char *)memchr(data.data() + p, '\t', e - p);
-            if (!t1) return fail("row without tab-separated columns");
-            const size_t ln = (size_t)(t1 - (data.data() + p));
-            if (cur < 0 || cur_name.size() != ln || memcmp(cur_name.data(), data.data() + p, ln) != 0) {
-                cur_name.assign((const char *)data.data() + p, ln);
-                auto it = tid.find(cur_name);
-                if (it == tid.end()) {
-                    cur = (int)names.size();
-                    tid[cur_name] = cur;
-                    names.push_back(cur_name);
-                    refs.emplace_back();
-                } else
-                    cur = it->second;
-            }
-            char *endp;
-            const int64_t beg = strtoll((const char *)t1 + 1, &endp, 10);
-            if (*endp != '\t') return fail("bad start column");
-            int64_t end = strtoll(endp + 1, &endp, 10);
-            if (end <= beg) end = beg + 1;
-            RefIndex &r = refs[cur];
-            auto &chunks = r.bins[reg2bin(beg, end)];
-            if (!chunks.empty() && chunks.back().end == p)
-                chunks.back().end = e;
-            else
-                chunks.push_back({(uint64_t)p, (uint64_t)e});
-            const int64_t w0 = beg >> 14, w1 = (end - 1) >> 14;
-            if ((int64_t)r.linear.size() <= w1) r.linear.resize((size_t)w1 + 1, -1);
-            for (int64_t w = w0; w <= w1; w++)
-                if (r.linear[w] < 0) r.linear[w] = (int64_t)p;
-        }
-        p = e;
-    }
-    // ---- compress
-    FILE *out = fopen(path_gz, "wb");
-    if (!out) return fail("cannot open the output file");
     std::vector<uint64_t> coff;
-    const bool ok = bgzf_write(out, data, threads, 6, coff);
+    uint64_t cpos = 0, N = 0;        // compressed / uncompressed bytes so far
+    int cur = -1;
+    std::string cur_name, carry;     // carry: the start of a row that continues in the next wave (it begins at offset N - carry.size())
+    const char *bad = nullptr;
+    auto index_row = [&](const char *row, size_t len, uint64_t off) {   // row [off, off + len) incl. its newline, if any
+        if (row[0] == '#' || len <= 1) return;
+        const char *end = row + len;
+        const char *t1 = (const char *)memchr(row, '\t', len);
+        if (!t1) {
+            bad = "row without tab-separated columns";
+            return;
+        }
+        const size_t ln = (size_t)(t1 - row);
+        if (cur < 0 || cur_name.size() != ln || memcmp(cur_name.data(), row, ln) != 0) {
+            cur_name.assign(row, ln);
+            auto it = tid.find(cur_name);
+            if (it == tid.end()) {
+                cur = (int)names.size();
+                tid[cur_name] = cur;
+                names.push_back(cur_name);
+                refs.emplace_back();
+            } else
+                cur = it->second;
+        }
+        int64_t beg = 0, stop = 0;
+        const char *q = parse_i64(t1 + 1, end, beg);
+        if (!q || q >= end || *q != '\t') {
+            bad = "bad start column";
+            return;
+        }
+        q = parse_i64(q + 1, end, stop);
+        if (!q) {
+            bad = "bad end column";
+            return;
+        }
+        if (stop <= beg) stop = beg + 1;
+        RefIndex &r = refs[cur];
+        auto &chunks = r.bins[reg2bin(beg, stop)];
+        if (!chunks.empty() && chunks.back().end == off)
+            chunks.back().end = off + len;
+        else
+            chunks.push_back({off, off + len});
+        const int64_t w0 = beg >> 14, w1 = (stop - 1) >> 14;
+        if ((int64_t)r.linear.size() <= w1) r.linear.resize((size_t)w1 + 1, -1);
+        for (int64_t w = w0; w <= w1; w++)
+            if (r.linear[w] < 0) r.linear[w] = (int64_t)off;
+    };
+    bool ok = true;
+    for (;;) {
+        size_t got = 0, n;
+        while (got < wave_bytes && (n = fread(wave.data() + got, 1, wave_bytes - got, in)) > 0) got += n;
+        if (got == 0) break;
+        ok = bgzf_write_blocks(out, wave.data(), got, threads, 6, coff, cpos);
+        if (!ok) break;
+        // rows of this wave; a row that began in the previous wave is completed first
+        size_t p = 0;
+        if (!carry.empty()) {
+            const unsigned char *nl = (const unsigned char *)memchr(wave.data(), '\n', got);
+            const size_t take = nl ? (size_t)(nl - wave.data()) + 1 : got;
+            const uint64_t off = N - carry.size();
+            carry.append((const char *)wave.data(), take);
+            p = take;
+            if (nl) {
+                index_row(carry.data(), carry.size(), off);
+                carry.clear();
+            }
+        }
+        while (p < got && !bad) {
+            const unsigned char *nl = (const unsigned char *)memchr(wave.data() + p, '\n', got - p);
+            if (!nl) {
+                carry.assign((const char *)wave.data() + p, got - p);
+                break;
+            }
+            const size_t e = (size_t)(nl - wave.data()) + 1;
+            index_row((const char *)wave.data() + p, e - p, N + p);
+            p = e;
+        }
+        N += got;
+        if (bad || got < wave_bytes) break;
+    }
+    fclose(in);
+    if (ok && !bad && !carry.empty()) index_row(carry.data(), carry.size(), N - carry.size());   // last row without a newline
+    if (ok && !bad) {
+        coff.push_back(cpos);
+        ok = fwrite(BGZF_EOF, 1, 28, out) == 28;
+    }
     fclose(out);
+    if (bad) return fail(bad);
     if (!ok) return fail("write error");
     // ---- .tbi
     std::vector<unsigned char> tbi;

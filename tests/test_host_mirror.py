@@ -274,6 +274,24 @@ def test_native_bam_reader_matches_python(tmp_path):
     assert len(allp) == 20000 and np.all(np.diff(allp) >= 0)
     off, pos, tlen = b.fetch_fragments_many([])
     assert len(off) == 1 and len(pos) == 0
+    # a BAM cut in the middle of a block (or of a record) is an error, not a short read list; the untrusted uncompressed
+    # size in a block trailer is bounded
+    raw = open(bam, "rb").read()
+    cut = str(tmp_path / "cut.bam")
+    open(cut, "wb").write(raw[:len(raw) // 2 + 13])
+    import shutil
+    shutil.copy(bam + ".bai", cut + ".bai")
+    bc = hostio.BamFile(cut)
+    with pytest.raises(IOError, match="truncated"):
+        bc.fetch_fragments_many([("chrA", 0, sizes["chrA"]), ("chrB", 0, sizes["chrB"])], threads=2)
+    bad = bytearray(raw)
+    bsize = (bad[16] | (bad[17] << 8)) + 1                      # first block: patch ISIZE (last 4 bytes) to 1 GiB
+    bad[bsize - 4:bsize] = (1 << 30).to_bytes(4, "little")
+    evil = str(tmp_path / "evil.bam")
+    open(evil, "wb").write(bytes(bad))
+    shutil.copy(bam + ".bai", evil + ".bai")
+    with pytest.raises(IOError, match="impossible uncompressed size|inflate"):
+        hostio.BamFile(evil).fetch_fragments_many([("chrA", 0, 1000)], threads=1)
 
 
 def test_merge_sorts_unsorted_bed():
@@ -351,3 +369,29 @@ def test_cli_run_propagates_shard_and_device(monkeypatch, tmp_path):
     seen.clear()
     cli.nucleoatac_main(base)
     assert [s[0] for s in seen] == ["occ", "vprocess", "barrier", "nuc", "merge", "barrier", "nfr"]
+
+
+def test_bgzip_tabix_streams_in_waves(tmp_path):
+    """nb200_bgzip_tabix streams the text in waves of BGZF blocks: a file of several waves (1 thread: 4 MB per wave), with rows
+    straddling the wave boundaries and no newline after the last row, gives the same .gz and .tbi as one wave (8 threads)."""
+    rng = np.random.RandomState(3)
+    rows, pos = [], 0
+    for k in range(260000):
+        pos += int(rng.randint(1, 40))
+        rows.append("chr%d\t%d\t%d\t%s" % (1 + k // 130000, pos % 50000000 + (k // 130000) * 0, pos % 50000000 + 1, repr(float(rng.rand()))))
+        if k == 129999:
+            pos = 0
+    text = "\n".join(rows)          # no trailing newline
+    plain = tmp_path / "t.bedgraph"
+    plain.write_text(text)
+    assert plain.stat().st_size > 2 * 64 * 0xff00
+    outs = []
+    for threads in (1, 8):
+        gz = str(tmp_path / ("t%d.bedgraph.gz" % threads))
+        hostio.bgzip_tabix(str(plain), gz, threads=threads)
+        outs.append((open(gz, "rb").read(), open(gz + ".tbi", "rb").read()))
+    assert outs[0] == outs[1]
+    assert gzip.open(str(tmp_path / "t1.bedgraph.gz"), "rt").read() == text
+    got = list(hostio.TabixFile(str(tmp_path / "t1.bedgraph.gz")).fetch("chr2", 1000, 1200))
+    exp = [r for r in rows[130000:] if 1000 <= int(r.split("\t")[1]) < 1200]
+    assert [("\t".join(g) if isinstance(g, (list, tuple)) else g) for g in got] == exp and len(exp) > 3
