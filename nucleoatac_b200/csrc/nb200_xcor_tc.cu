@@ -69,6 +69,12 @@ struct TcPlan {
     double density = 0.0; // MMA columns issued / (NAp * NBp / 16)
     DevBuf g_img, stage_tab, block_tab, t_row1, emax;
     std::vector<int4> h_tab, h_blk;
+    // second plan, for k_nuc_bx_ts (hi half of the Hankel operand in tensor memory): slabs of TS_N rows, every block image resident
+    bool ts_ok = false;
+    int ts_slabs = 0, ts_blocks = 0, ts_rank_bytes = 0, ts_c_split = 0, ts_c_end = 0, ts_q_need2 = -1;
+    DevBuf ts_img;
+    std::vector<int4> ts_blk;     // block and slab tables: passed to the kernel by value (TsTab)
+    std::vector<int2> ts_slab;
 };
 
 static TcPlan *plan_of(nb200_ctx *ctx, bool create)
@@ -86,6 +92,7 @@ void nb200_tc_release(nb200_ctx *ctx)
     pl->block_tab.release();
     pl->t_row1.release();
     pl->emax.release();
+    pl->ts_img.release();
     delete pl;
     ctx->tc_plan = nullptr;
 }
@@ -171,6 +178,14 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
     uint32_t ra;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(bar), "r"(cta));
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+// Same without memory ordering: for hand-offs whose payload is tensor memory (ordered by tcgen05.fence / tcgen05.wait), not
+// generic memory.  The .release form costs a MEMBAR.ALL.GPU per arrive (SASS), ~1 k clk on the read-back path of every slab.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar, uint32_t cta)
+{
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(bar), "r"(cta));
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all()
 {
@@ -325,6 +340,36 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t *r)
         : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t *r)
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+        "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// The three MMAs of one K16 block of a CTA pair with the hi half of the A operand in TENSOR MEMORY (tcgen05.mma [d], [a], b-desc):
+// hi * hi and hi * lo read A from TMEM, lo * hi reads the lo Hankel rows from shared memory.
+__device__ __forceinline__ void tc_mma3_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t a_lo_lo, uint32_t b_hi_lo, uint32_t b_lo_lo, uint32_t desc_hi,
+                                           uint32_t idesc, uint32_t acc0)
+{
+    asm volatile(
+        "{\n\t.reg .pred p, q, e;\n\t.reg .b64 dal, dbh, dbl;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "mov.b64 dal, {%2, %5};\n\t"
+        "mov.b64 dbh, {%3, %5};\n\t"
+        "mov.b64 dbl, {%4, %5};\n\t"
+        "setp.ne.b32 p, %7, 0;\n\t"
+        "setp.eq.b32 q, %5, %5;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], dbh, %6, p;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], dbl, %6, q;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], dal, dbh, %6, q;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(a_lo_lo), "r"(b_hi_lo), "r"(b_lo_lo), "r"(desc_hi), "r"(idesc), "r"(acc0)
+        : "memory");
+}
 
 // ---------------------------------------------------------------------------------------------
 struct TcArgs {
@@ -794,7 +839,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
                         __syncwarp();
                         if (lane == 0) {
                             if (PAIR)
-                                mbar_arrive_cluster(bar_tempty + 8 * j, 0);   // the leader's barrier gathers both CTAs
+                                mbar_arrive_cluster_relaxed(bar_tempty + 8 * j, 0);   // the leader's barrier gathers both CTAs
                             else
                                 mbar_arrive(bar_tempty + 8 * j);
                         }
@@ -830,6 +875,487 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
             asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS) : "memory");
         else
             asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS) : "memory");
+    }
+}
+
+// =============================================================================================
+// k_nuc_bx_ts -- the same contraction with the hi half of the Hankel operand in TENSOR MEMORY
+// =============================================================================================
+// What bounds k_nuc_bx_tc (measured with a stand-alone issue loop, profiles/r2_mma_microbench.txt): the 128 B/clk shared-memory
+// pipe of an SM is shared by the MMAs' operand fetches -- which win -- and the epilogue's loads of E.  An MMA with both
+// operands in shared memory costs max(N/2, (4096 + 16 N)/128) clk in a pair (the A tile alone is 32 clk of the pipe), and
+// while MMAs of N <= 128 run the epilogue gets 11-23 B/clk of E, so a slab drains more slowly than the next one is
+// contracted.  Two of the three MMAs of a block read the SAME hi rows: with those in tensor memory (tcgen05.mma [d], [a],
+// b-desc) they fetch only G, MMAs run at N/2 clk down to N = 32 and the epilogue keeps 55-70 B/clk.
+//
+// TMEM (512 columns): two accumulators of TS_N = 128 columns + the expanded hi operand of ONE x-tile, A[m][k] = Es_hi[m + k]
+// as packed halves (column 256 + k/2; NBp/2 <= 192 columns at 251 x 251).  The x-tiles of a CTA are therefore contracted
+// one after the other, slab by slab through the two accumulators (unit u -> accumulator u & 1); the two groups of four
+// epilogue warps take alternate units and add their partial sums per tile through shared memory.  The operand is
+// written by the operand-generation warps (tcgen05.st from the hi Hankel rows they produced in shared memory) in two
+// parts: the columns that slab 0 reads (K blocks < kb_split) as soon as the previous tile's last MMA that reads them has
+// retired (a commit in the middle of its last slab), the rest when the previous tile is complete -- under slab 0 of the new
+// tile.  CTA pairs, resident G and the fused issue of a block's three MMAs are as in k_nuc_bx_tc<.., true, true>.
+#ifndef TS_N
+#define TS_N 128                          // slab width = accumulator columns
+#define TS_NACC 2                         // accumulators the slabs go round (measured: 128 x 2 6.16 ms, 96 x 3 6.53 ms per 20 Mbp)
+#endif
+#define TS_ACOL (TS_NACC * TS_N)          // first TMEM column of the hi operand
+#define TS_MAXCOL (TC_TMEM_COLS - TS_ACOL)
+#define TS_BARS 23                        // gfull, zfull[2], zempty[2], zpair[2], tfull[3], tempty[3], afull[2], afree[2], linfull[2], pfull[4]
+// 13 warps (152 registers per thread, so that an epilogue thread holds a whole 128-column slab and hands the accumulator back
+// as soon as its four tcgen05.ld have landed): 0-7 epilogue, 8 issuing warp (+ the one-off load of G), 9-12 operand
+// generation and expansion into tensor memory (warp & 3 = 1, 2, 3, 0: the four TMEM lane quarters)
+#define TS_WARP_MMA TC_EPI_WARPS
+#define TS_WARP_PREP (TC_EPI_WARPS + 1)
+#define TS_THREADS (32 * (TC_EPI_WARPS + 1 + TC_PREP_WARPS))
+
+struct TsArgs {
+    const int32_t *start;
+    const int64_t *out_off, *bias_off;
+    const int32_t *seq_start;
+    const double *E;
+    const double *emax;
+    const unsigned char *g_img;   // [rank]: that CTA's half of every block image (hi image, then lo image)
+    const double *t_row1;
+    double *bx;
+    unsigned long long *dbg;
+    int pwm_up, A0, B0, NBp, gmin, span, n_slabs, n_blocks, sG, has_row1, W, w, epad;
+    int n_chunks, tiles_per_chunk;
+    int rank_bytes;           // bytes of one CTA's image
+    int c_split, c_end;       // hi-operand columns of part 1 / in all (multiples of 32)
+    int q_need2;              // first slab that reads part 2 (-1: none)
+    int nZ;                   // 128-byte chunks per Hankel part
+};
+
+// The block list travels as a kernel parameter (constant bank): with its entries and every loop counter of the issuing warp
+// warp-uniform, ptxas keeps the whole issue loop on the uniform datapath (LDCU / UIADD3 / UMOV / UTCHMMA, no election, no
+// R2UR) -- ~15 instructions per block instead of ~45, which matters because a block trimmed to N <= 96 occupies the tensor
+// pipe for less time than the 45-instruction form takes to issue.
+#define TS_MAX_BLOCKS 192
+#define TS_MAX_SLABS 8
+struct TsTab {
+    int4 blk[TS_MAX_BLOCKS];   // per K16 block {K block | flags << 16 (bit 0: part 1 of the hi operand is read no more after it), first row n_lo, instruction descriptor, image offset / 16 | rows per CTA << 16}
+    int2 slab[TS_MAX_SLABS];   // per slab {first block, blocks}
+};
+
+template <bool DBG>
+__global__ void __launch_bounds__(TS_THREADS, 1) k_nuc_bx_ts(const __grid_constant__ TsTab tab, const __grid_constant__ TsArgs a)
+{
+    extern __shared__ __align__(128) unsigned char sm_tc[];
+    // the warp index through a lane-0 shuffle: the value the compiler can prove warp-uniform (the branch on it is what lets
+    // the issuing warp's loop stay on the uniform datapath)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const uint32_t rank = blockIdx.x & 1u;                      // = %cluster_ctarank for clusters of (2, 1, 1), but provably warp-uniform; 0 = leader
+    const int it_first = (int)(blockIdx.x >> 1), it_step = (int)(gridDim.x >> 1);
+    const int item_w = 2 * TC_TX;                               // outputs per work item of the pair
+    const int x_rank = (int)rank * TC_TX;
+
+    // ---- shared memory carve-up
+    const int nZ = a.nZ;
+    // The fp32 E window of an item is kept FOUR times, copy s shifted by s elements (cp_s[i] = E[i + s]): whatever a thread's
+    // first element, one of the copies has it on a 16-byte boundary, so the epilogue reads its 32 consecutive values per chunk
+    // with 8 LDS.128 instead of 32 LDS.32 (with every register holding accumulator columns the loads cannot be batched, and
+    // the one-at-a-time LDS latency was the epilogue's whole cost).  Copy stride = 8 mod 32 words: the 8 lanes of a
+    // quarter-warp (4 copies x 2 consecutive 16-byte groups) fall into 8 different bank quads.
+    const int cplen = ((a.span + 3 + 31) & ~31) + 8;
+    unsigned char *p = sm_tc;
+    unsigned char *s_stage = p;            p += (size_t)a.rank_bytes;
+    unsigned char *s_zhi = p;              p += (size_t)nZ * 128;                 // hi Hankel rows: only the source of the expansion into TMEM (one set)
+    unsigned char *s_zlo = p;              p += (size_t)2 * nZ * 128;             // [set][nZ * 128] lo Hankel rows (MMA operand)
+    float *s_cpb = reinterpret_cast<float *>(p);            p += sizeof(float) * 2 * 4 * cplen;   // [set][copy][cplen]
+    const int Wp = (a.W + 3) & ~3;
+    float *s_t1 = reinterpret_cast<float *>(p);             p += sizeof(float) * (a.has_row1 ? Wp : 0);
+    float *s_linb = reinterpret_cast<float *>(p);           p += sizeof(float) * (a.has_row1 ? 2 * TC_TX : 0);
+    double *s_part = reinterpret_cast<double *>(p);         p += sizeof(double) * 4 * TC_M;       // [tile & 3][128]: the partial sums of the group that does not finish the tile
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(p);      p += sizeof(uint64_t) * (TS_BARS + 1);
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(p);
+    const uint32_t bar_gfull = smem_u32(s_bar), bar_zfull = bar_gfull + 8, bar_zempty = bar_zfull + 16, bar_zpair = bar_zempty + 16,
+                   bar_tfull = bar_zpair + 16, bar_tempty = bar_tfull + 8 * TS_NACC, bar_afull = bar_tempty + 8 * TS_NACC, bar_afree = bar_afull + 16,
+                   bar_linfull = bar_afree + 16, bar_pfull = bar_linfull + 16;
+
+    // ---- one-time setup
+    if (threadIdx.x == 0) {
+        mbar_init(bar_gfull, rank == 0 ? 2 : 1);                // own bulk copies (+ the peer's "landed" relay)
+        for (int i = 0; i < 2; i++) {
+            mbar_init(bar_zfull + 8 * i, TC_PREP_WARPS);
+            mbar_init(bar_zempty + 8 * i, TC_EPI_WARPS + 1);    // epilogue warps (E window) + the commit of the item's MMAs (lo rows)
+            mbar_init(bar_zpair + 8 * i, 2 * TC_PREP_WARPS);
+            mbar_init(bar_afull + 8 * i, 2 * TC_PREP_WARPS);    // part i of the hi operand written, in both CTAs
+            mbar_init(bar_afree + 8 * i, 1);
+            mbar_init(bar_linfull + 8 * i, TC_PREP_WARPS);      // the size-1 term of the item
+        }
+        for (int i = 0; i < 4; i++) mbar_init(bar_pfull + 8 * i, 4);   // the 4 warps of the depositing group
+        for (int i = 0; i < TS_NACC; i++) {
+            mbar_init(bar_tfull + 8 * i, 1);
+            mbar_init(bar_tempty + 8 * i, 8);                   // the 4 warps of the group that reads the slab, in both CTAs
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == TS_WARP_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    if (a.has_row1)
+        for (int i = threadIdx.x; i < Wp; i += TS_THREADS) s_t1[i] = (i < a.W) ? (float)a.t_row1[i] : 0.f;
+    int eexp = 1;
+    const double emax = a.emax[0];
+    if (emax > 0.0) frexp(32768.0 / emax, &eexp);
+    const int sE = eexp - 1;
+    tc_fence_before();
+    cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / multicast commit
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    if (DBG && threadIdx.x == 0 && blockIdx.x < 2 && g_tc_trap_info) {
+        g_tc_trap_info[8 + 2 * blockIdx.x] = (int)bar_gfull;
+        g_tc_trap_info[9 + 2 * blockIdx.x] = (int)tmem;
+    }
+    const long long t_begin = DBG ? clock64() : 0;
+    unsigned long long *dbg = DBG ? a.dbg + 16 * (size_t)blockIdx.x : nullptr;
+    const int n_items = a.n_chunks * a.tiles_per_chunk;
+    auto item_valid = [&](int it) {
+        const int c = it / a.tiles_per_chunk, xb = (it - c * a.tiles_per_chunk) * item_w;
+        return xb < (int)(a.out_off[c + 1] - a.out_off[c]);
+    };
+    auto next_valid = [&](int it) {
+        while (it < n_items && !item_valid(it)) it += it_step;
+        return it;
+    };
+
+    if (warp >= TS_WARP_PREP) {
+        // ===== operand generation (for the next item) and the hi operand of every tile into tensor memory
+        const int tid = threadIdx.x - 32 * TS_WARP_PREP;
+        const int wq = warp & 3, m = wq * 32 + lane;          // the TMEM lane quarter this warp may touch; row of the tile
+        const float scale = (float)ldexp(1.0, sE);
+        const int boff = a.B0 - a.gmin;
+        long long w_ze = 0, w_af = 0, t_prep = 0, t_fill = 0, t_eload = 0, t_lin = 0;
+        auto prep_item = [&](int it, int n) {
+            const int c = it / a.tiles_per_chunk, xb = (it - c * a.tiles_per_chunk) * item_w, x0 = xb + x_rank;
+            const int set = n & 1;
+            // the E window first into registers (the loads do not depend on the set being free), then wait for the set
+            const int64_t e_lo = a.bias_off[c], e_hi = a.bias_off[c + 1];
+            const int64_t ebase = e_lo - (int64_t)(a.seq_start[c] + a.pwm_up) + (int64_t)a.start[c] + x0 + a.gmin;
+            constexpr int EPF = 8;                               // covers spans up to 8 * 128 = 1024 positions; longer ones in a second round
+            float ev[EPF];
+#pragma unroll
+            for (int k = 0; k < EPF; k++) {
+                const int i = tid + k * TC_PREP_THREADS;
+                const int64_t idx = ebase + i;
+                ev[k] = (i < a.span && idx >= e_lo && idx < e_hi) ? (float)a.E[idx] : 0.f;   // out of track / past the window -> 0
+            }
+            const long long t0 = DBG ? clock64() : 0;
+            mbar_wait(bar_zempty + 8 * set, ((n >> 1) & 1) ^ 1);
+            const long long tp0 = DBG ? clock64() : 0;
+            if (DBG) w_ze += tp0 - t0;
+            float *s_E = s_cpb + (size_t)set * 4 * cplen;   // copy 0; copy s at + s * cplen
+            auto put = [&](int i, float v) {   // element i of the window into the four copies (zeros past the window: every copy is defined up to cplen)
+#pragma unroll
+                for (int sft = 0; sft < 4; sft++)
+                    if (i >= sft && i - sft < cplen) s_E[sft * cplen + i - sft] = v;
+            };
+#pragma unroll
+            for (int k = 0; k < EPF; k++) {
+                const int i = tid + k * TC_PREP_THREADS;
+                if (i < cplen + 3) put(i, ev[k]);
+            }
+            for (int i = tid + EPF * TC_PREP_THREADS; i < cplen + 3; i += TC_PREP_THREADS) {
+                const int64_t idx = ebase + i;
+                put(i, (i < a.span && idx >= e_lo && idx < e_hi) ? (float)a.E[idx] : 0.f);
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_PREP_THREADS) : "memory");
+            if (DBG) t_eload += clock64() - tp0;
+            unsigned char *zh = s_zhi, *zl = s_zlo + (size_t)set * nZ * 128;
+            for (int e = tid; e < nZ * 8; e += TC_PREP_THREADS) {
+                __align__(16) __half hi[8], lo[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int idx = boff + e + j;
+                    const float v = (idx < a.span) ? s_E[idx] * scale : 0.f;
+                    hi[j] = __float2half_rn(v);
+                    lo[j] = __float2half_rn(v - __half2float(hi[j]));
+                }
+                *reinterpret_cast<uint4 *>(zh + (size_t)e * 16) = *reinterpret_cast<uint4 *>(hi);
+                *reinterpret_cast<uint4 *>(zl + (size_t)e * 16) = *reinterpret_cast<uint4 *>(lo);
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");   // the lo rows are read by the leader's MMAs
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_PREP_THREADS) : "memory");   // every hi row is in place before any thread expands its tile row from them
+            if (DBG) t_prep += clock64() - tp0;
+            if (lane == 0) {
+                mbar_arrive(bar_zfull + 8 * set);
+                mbar_arrive_cluster(bar_zpair + 8 * set, 0);
+            }
+        };
+        // insert size 1: Bp[1,c] = E[c] (one tap) -> lin[x] = sum_k t1[k] E[x - w + k], a plain 1-D correlation in fp32: two
+        // consecutive outputs per thread, 4 taps per step.  Only the epilogue's last addition needs it, so it runs when these
+        // warps have nothing else due (after the operand of the item's first tile is in tensor memory).
+        auto lin_item = [&](int n) {
+            const int set = n & 1;
+            const long long tl0 = DBG ? clock64() : 0;
+            const int sh = -a.w - a.gmin;                    // >= 0: element x + k of the window shifted by sh is tap k of output x
+            const float *s_E1 = s_cpb + (size_t)(set * 4 + (sh & 3)) * cplen + (sh & ~3);   // the copy that has it 16-byte aligned
+            {
+                const float2 *e2 = reinterpret_cast<const float2 *>(s_E1 + 2 * tid);
+                const float4 *t4 = reinterpret_cast<const float4 *>(s_t1);
+                float l0a = 0.f, l0b = 0.f, l1a = 0.f, l1b = 0.f;
+                float2 ea = e2[0], eb = e2[1];
+#pragma unroll 4
+                for (int k4 = 0; k4 < Wp / 4; k4++) {
+                    const float4 t = t4[k4];
+                    const float2 ec = e2[2 * k4 + 2], ed = e2[2 * k4 + 3];
+                    l0a = fmaf(t.x, ea.x, fmaf(t.y, ea.y, l0a));
+                    l0b = fmaf(t.z, eb.x, fmaf(t.w, eb.y, l0b));
+                    l1a = fmaf(t.x, ea.y, fmaf(t.y, eb.x, l1a));
+                    l1b = fmaf(t.z, eb.y, fmaf(t.w, ec.x, l1b));
+                    ea = ec;
+                    eb = ed;
+                }
+                *reinterpret_cast<float2 *>(s_linb + (size_t)set * TC_TX + 2 * tid) = make_float2(l0a + l0b, l1a + l1b);
+            }
+            if (DBG) t_lin += clock64() - tl0;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_linfull + 8 * set);
+        };
+        // columns [c0, c1) of the hi operand of tile j: row m holds Es_hi[128 j + m + k], k = 2 c, 2 c + 1 -> the 16-byte Hankel rows
+        // 128 j + m + 8 i are its columns 4 i .. 4 i + 3
+        auto fill = [&](int set, int j, int part, int tcnt) {
+            const int c0 = part ? a.c_split : 0, c1 = part ? a.c_end : a.c_split;
+            const long long t0 = DBG ? clock64() : 0;
+            mbar_wait(bar_afree + 8 * part, (tcnt & 1) ^ 1);   // the previous tile's MMAs that read these columns have retired
+            tc_fence_after();
+            const long long tf0 = DBG ? clock64() : 0;
+            if (DBG) w_af += tf0 - t0;
+            const unsigned char *zrow = s_zhi + (size_t)(TC_M * j + m) * 16;
+            const uint32_t ta = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)TS_ACOL;
+            for (int c = c0; c < c1; c += 32) {
+                uint32_t v[32];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const uint4 q = *reinterpret_cast<const uint4 *>(zrow + (size_t)(c / 4 + i) * 128);
+                    v[4 * i] = q.x;
+                    v[4 * i + 1] = q.y;
+                    v[4 * i + 2] = q.z;
+                    v[4 * i + 3] = q.w;
+                }
+                tc_st32(ta + (uint32_t)c, v);
+            }
+            tc_wait_st();
+            if (DBG) t_fill += clock64() - tf0;
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster_relaxed(bar_afull + 8 * part, 0);   // the stores have completed (tcgen05.wait::st)
+        };
+        int it = next_valid(it_first), n = 0, tcnt = 0;
+        if (it < n_items) prep_item(it, 0);
+        while (it < n_items) {
+            const int nx = next_valid(it + it_step);
+            const int set = n & 1;
+            for (int j = 0; j < TC_XT; j++, tcnt++) {
+                fill(set, j, 0, tcnt);
+                fill(set, j, 1, tcnt);
+                if (j == 0 && a.has_row1) lin_item(n);   // nothing else is due before the last slab of tile 0
+            }
+            // under the MMAs of tile 1: the set it overwrites was released an item ago, and nothing is due from these warps
+            // before the last slab of tile 1
+            if (nx < n_items) prep_item(nx, n + 1);
+            it = nx;
+            n++;
+        }
+        if (DBG && tid == 0) {
+            dbg[8] = (unsigned long long)w_ze;
+            dbg[9] = (unsigned long long)w_af;
+            dbg[10] = (unsigned long long)t_prep;
+            dbg[11] = (unsigned long long)t_eload;
+            dbg[12] = (unsigned long long)t_lin;
+            dbg[13] = (unsigned long long)t_fill;
+        }
+    } else if (warp == TS_WARP_MMA && rank != 0) {
+        // ===== peer: loads its half of every block image and tells the leader when it has landed
+        if (lane == 0) {
+            mbar_expect_tx(bar_gfull, (uint32_t)a.rank_bytes);
+            const unsigned char *src = a.g_img + (size_t)rank * a.rank_bytes;
+            for (int off = 0; off < a.rank_bytes; off += 32768) bulk_g2s(smem_u32(s_stage + off), src + off, (uint32_t)min(32768, a.rank_bytes - off), bar_gfull);
+        }
+        __syncwarp();
+        mbar_wait(bar_gfull, 0);
+        if (lane == 0) mbar_arrive_cluster(bar_gfull, 0);
+        __syncwarp();
+    } else if (warp == TS_WARP_MMA) {
+        // ===== the issuing warp (leader): tiles one after the other, slabs through the two accumulators.  Everything in this
+        // loop derives from kernel parameters and loop counters (warp-uniform): see TsTab.
+        const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+        const uint32_t sbase = (smem_u32(s_stage) >> 4) & 0x3FFF;
+        long long w_zf = 0, w_te = 0, w_af = 0;
+        int n = 0, tcnt = 0;
+        uint32_t ab = 0, aph = 0;   // accumulator of the current slab (slabs go round the TS_NACC accumulators) and its use parity
+        if (lane == 0) {   // this CTA's half of every block image, once
+            mbar_expect_tx(bar_gfull, (uint32_t)a.rank_bytes);
+            for (int off = 0; off < a.rank_bytes; off += 32768) bulk_g2s(smem_u32(s_stage + off), a.g_img + off, (uint32_t)min(32768, a.rank_bytes - off), bar_gfull);
+        }
+        __syncwarp();
+        mbar_wait_cluster(bar_gfull, 0);
+        tc_fence_after();
+        for (int it = it_first; it < n_items; it += it_step) {
+            if (!item_valid(it)) continue;
+            const int set = n & 1;
+            {
+                const long long t0 = DBG ? clock64() : 0;
+                mbar_wait_cluster(bar_zpair + 8 * set, (n >> 1) & 1);   // the lo rows of both CTAs
+                tc_fence_after();
+                if (DBG) w_zf += clock64() - t0;
+            }
+            const uint32_t zb = smem_u32(s_zlo + (size_t)set * nZ * 128);
+            for (int j = 0; j < TC_XT; j++, tcnt++) {
+                const uint32_t a_lo0 = (((zb + 2048u * j) >> 4) & 0x3FFF) | ((128u >> 4) << 16);
+                for (int q = 0; q < a.n_slabs; q++) {
+                    if (q == 0 || q == a.q_need2) {
+                        const long long t0 = DBG ? clock64() : 0;
+                        mbar_wait_cluster(bar_afull + 8 * (q == 0 ? 0 : 1), tcnt & 1);   // the columns of the hi operand this slab reads are written
+                        tc_fence_after();
+                        if (DBG) w_af += clock64() - t0;
+                    }
+                    {
+                        const long long t0 = DBG ? clock64() : 0;
+                        mbar_wait_cluster(bar_tempty + 8 * ab, aph ^ 1u);
+                        tc_fence_after();
+                        if (DBG) w_te += clock64() - t0;
+                    }
+                    const uint32_t d0 = tmem + ab * TS_N;
+                    const int2 sl = tab.slab[q];
+                    uint32_t acc0 = 0u;   // the first block of a slab is stored untrimmed: it initialises all TS_N columns
+                    for (int t = 0; t < sl.y; t++) {
+                        const int4 bk = tab.blk[sl.x + t];
+                        const uint32_t kb = (uint32_t)bk.x & 0xffffu;
+                        const uint32_t bh = (uint32_t)bk.w + sbase;
+                        const uint32_t bl = bh + 2u * ((uint32_t)bk.w >> 16);
+#ifndef TS_NO_MMA
+                        tc_mma3_ts(d0 + (uint32_t)bk.y, tmem + (uint32_t)TS_ACOL + 8u * kb, a_lo0 + 16u * kb, bh, bl, desc_hi, (uint32_t)bk.z, acc0);
+#endif
+                        acc0 = 1u;
+                        if ((bk.x >> 16) & 1) tc_commit_e2_both(bar_afree);   // nothing issued after this block reads part 1 of this tile's operand
+                    }
+                    tc_commit_e2_both(bar_tfull + 8 * ab);
+                    if (++ab == TS_NACC) {
+                        ab = 0;
+                        aph ^= 1u;
+                    }
+                }
+                tc_commit_e2_both(bar_afree + 8);
+            }
+            tc_commit_e2_both(bar_zempty + 8 * set);
+            n++;
+        }
+        if (DBG && lane == 0) {
+            dbg[1] = (unsigned long long)w_zf;
+            dbg[2] = (unsigned long long)w_te;
+            dbg[3] = (unsigned long long)w_af;
+            dbg[7] = (unsigned long long)n;
+        }
+    } else if (warp < TC_EPI_WARPS) {
+        // ===== epilogue: bx[x] = sum_n E[x + A0 + n] * H[x, n]; group g (4 warps, one TMEM lane quarter each) reads every other
+        // slab, keeps a partial sum per tile and adds the other group's through shared memory
+        const int grp = warp >> 2, wq = warp & 3;
+        const int m = wq * 32 + lane;
+        const int aoff = a.A0 - a.gmin;
+        const double unscale = ldexp(1.0, -(sE + a.sG));
+        const uint32_t tqaddr = tmem + ((uint32_t)(wq * 32) << 16);
+        long long w_tf = 0, t_epi = 0, w_ld = 0;
+        int n = 0, tcnt = 0;
+        uint32_t u = 0, ab = 0, aph = 0;
+        for (int it = it_first; it < n_items; it += it_step) {
+            const int c = it / a.tiles_per_chunk, xb = (it - c * a.tiles_per_chunk) * item_w, x0 = xb + x_rank;
+            const int64_t oo = a.out_off[c];
+            const int L = (int)(a.out_off[c + 1] - oo);
+            if (xb >= L) continue;
+            const int set = n & 1;
+            mbar_wait(bar_zfull + 8 * set, (n >> 1) & 1);
+            // this thread's window starts at element aoff + m (+ multiples of 32): the copy shifted by (aoff + m) & 3 has it aligned
+            const float *s_E = s_cpb + (size_t)(set * 4 + ((aoff + m) & 3)) * cplen + ((aoff + m) & ~3);
+            for (int j = 0; j < TC_XT; j++, tcnt++) {
+                double acc[4] = {0.0, 0.0, 0.0, 0.0};
+                for (int q = 0; q < a.n_slabs; q++, u++) {
+                    const uint32_t cab = ab, cph = aph;   // this slab's accumulator and use parity
+                    if (++ab == TS_NACC) {
+                        ab = 0;
+                        aph ^= 1u;
+                    }
+                    if ((int)(u & 1u) != grp) continue;
+                    const uint32_t t0addr = tqaddr + cab * TS_N;
+                    const long long t0 = DBG ? clock64() : 0;
+                    mbar_wait(bar_tfull + 8 * cab, cph);
+                    tc_fence_after();
+                    const long long t1 = DBG ? clock64() : 0;
+                    if (DBG) w_tf += t1 - t0;
+                    const float4 *Ew = reinterpret_cast<const float4 *>(s_E + TC_M * j + TS_N * q);
+                    // two register sets for the 32-column chunks of a slab: the tcgen05.ld of chunk h + 2 goes out as soon as chunk h has
+                    // been contracted; the accumulator returns to the issuing warp when the last chunk has landed
+                    constexpr int NCH = TS_N / 32;
+                    static_assert(TS_N % 32 == 0 && NCH >= 2, "slab = whole 32-column chunks");
+                    uint32_t r[2][32];
+                    tc_ld32(t0addr, r[0]);
+                    tc_ld32(t0addr + 32u, r[1]);
+#pragma unroll
+                    for (int h = 0; h < NCH; h++) {
+                        if (h < NCH - 1) {
+                            const long long tw = DBG ? clock64() : 0;
+                            tc_wait_ld();
+                            if (DBG) w_ld += clock64() - tw;
+                        }
+                        if (h == NCH - 2) {   // the last chunk has landed too: the rest of the slab is in registers
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_cluster_relaxed(bar_tempty + 8 * cab, 0);
+                        }
+                        float f[4] = {0.f, 0.f, 0.f, 0.f};   // runs of 8 products in fp32, the runs in fp64 (as in k_nuc_bx_tc)
+#pragma unroll
+                        for (int g4 = 0; g4 < 8; g4++) {
+                            const float4 e = Ew[8 * h + g4];
+                            float v = f[g4 >> 1];
+                            v = fmaf(__uint_as_float(r[h & 1][4 * g4]), e.x, v);
+                            v = fmaf(__uint_as_float(r[h & 1][4 * g4 + 1]), e.y, v);
+                            v = fmaf(__uint_as_float(r[h & 1][4 * g4 + 2]), e.z, v);
+                            v = fmaf(__uint_as_float(r[h & 1][4 * g4 + 3]), e.w, v);
+                            f[g4 >> 1] = v;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; k++) acc[k] += (double)f[k];
+                        if (h + 2 < NCH) tc_ld32(t0addr + (uint32_t)(32 * (h + 2)), r[h & 1]);
+                    }
+                    if (DBG) t_epi += clock64() - t1;
+                }
+                // The group that read the tile's LAST slab finishes the tile; the other one leaves its partial sums in shared memory
+                // and goes on (no rendezvous: it may be up to TS_NACC slabs ahead, less than the 4 tiles the buffers cover).
+                const double part = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+                double *sp = s_part + (size_t)(tcnt & 3) * TC_M;
+                const uint32_t bar_p = bar_pfull + 8 * (uint32_t)(tcnt & 3);
+                if (grp != (int)((u - 1u) & 1u)) {
+                    sp[m] = part;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_p);   // release: the partial sums are visible to the waiting group
+                } else {
+                    if (a.has_row1 && j == 0) mbar_wait(bar_linfull + 8 * set, (n >> 1) & 1);
+                    mbar_wait(bar_p, (uint32_t)(tcnt >> 2) & 1u);
+                    const int x = x0 + TC_M * j + m;
+                    const double lin = a.has_row1 ? (double)s_linb[(size_t)set * TC_TX + TC_M * j + m] : 0.0;  // size-1 term (prep warps)
+                    const double p0 = grp ? sp[m] : part, p1 = grp ? part : sp[m];   // group 0's part first, whoever adds: one order of summation
+                    if (x < L) a.bx[oo + x] = (p0 + p1) * unscale + lin;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_zempty + 8 * set);      // this warp no longer reads the E window of the set
+            n++;
+        }
+        if (DBG && threadIdx.x == 0) {
+            dbg[4] = (unsigned long long)w_tf;
+            dbg[5] = (unsigned long long)t_epi;
+            dbg[6] = (unsigned long long)w_ld;
+            dbg[0] = (unsigned long long)(clock64() - t_begin);
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();   // no CTA leaves (or frees its TMEM) while its partner's MMAs / arrives may still touch it
+    if (warp == TS_WARP_MMA) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS) : "memory");
     }
 }
 
@@ -975,6 +1501,83 @@ int nb200_tc_setup(nb200_ctx *ctx)
     NB_CUDA(ctx, cudaMemcpy(pl->stage_tab.p, pl->h_tab.data(), sizeof(int4) * pl->h_tab.size(), cudaMemcpyHostToDevice));
     NB_CUDA(ctx, pl->block_tab.reserve(sizeof(int4) * pl->h_blk.size()));
     NB_CUDA(ctx, cudaMemcpy(pl->block_tab.p, pl->h_blk.data(), sizeof(int4) * pl->h_blk.size(), cudaMemcpyHostToDevice));
+    // ---- second plan (k_nuc_bx_ts): slabs of TS_N rows, all block images resident, one contiguous region per CTA of the pair
+    pl->ts_ok = false;
+    {
+        const int n_sl = (pl->NA + TS_N - 1) / TS_N;
+        const int c_end = (pl->NBp / 2 + 31) / 32 * 32;
+        struct Blk { int q, kb, n_lo, n_t; };
+        std::vector<Blk> blks;
+        std::vector<int2> slabs;
+        for (int q = 0; q < n_sl; q++) {
+            const int first = (int)blks.size();
+            for (int kb = 0; kb < nkb; kb++) {
+                int r_lo = TS_N, r_hi = -1;
+                for (int n = 0; n < TS_N && q * TS_N + n < pl->NAp; n++)
+                    for (int k = 0; k < 16; k++)
+                        if (G[(size_t)(q * TS_N + n) * pl->NBp + kb * 16 + k] != 0.0) {
+                            r_lo = std::min(r_lo, n);
+                            r_hi = std::max(r_hi, n);
+                        }
+                if (r_hi < 0) continue;
+                blks.push_back({q, kb, r_lo / 16 * 16, (r_hi + 16) / 16 * 16 - r_lo / 16 * 16});
+            }
+            if ((int)blks.size() == first) blks.push_back({q, 0, 0, TS_N});
+            blks[first].n_lo = 0;   // the first MMA of a slab initialises every accumulator column
+            blks[first].n_t = TS_N;
+            slabs.push_back(make_int2(first, (int)blks.size() - first));
+        }
+        // part 1 of the hi operand = the K blocks slab 0 reads (rounded up to 32 columns = 4 K blocks)
+        int kmax0 = 0;
+        for (const Blk &b : blks)
+            if (b.q == 0) kmax0 = std::max(kmax0, b.kb);
+        const int kb_split = std::min((kmax0 + 1 + 3) / 4 * 4, c_end / 8);
+        int last_p1 = 0, q_need2 = -1;   // the last block (in issue order) that reads part 1; the first slab that reads part 2
+        for (size_t i = 0; i < blks.size(); i++) {
+            if (blks[i].kb < kb_split) last_p1 = (int)i;
+            else if (q_need2 < 0) q_need2 = blks[i].q;
+        }
+        size_t rank_bytes = 0;
+        for (const Blk &b : blks) rank_bytes += (size_t)b.n_t * 32;   // half of the rows, hi + lo, 16 halves each
+        std::vector<unsigned char> timg(2 * rank_bytes, 0);
+        std::vector<int4> tblk;
+        size_t off = 0;
+        for (size_t i = 0; i < blks.size(); i++) {
+            const Blk &b = blks[i];
+            const int nh = b.n_t / 2;
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(b.n_t >> 3) << 17) | ((uint32_t)((TC_M * 2) >> 4) << 24);
+            tblk.push_back(make_int4(b.kb | (((int)i == last_p1 ? 1 : 0) << 16), b.n_lo, (int)idesc, (int)(off >> 4) | (nh << 16)));
+            for (int rk = 0; rk < 2; rk++) {
+                __half *hi = reinterpret_cast<__half *>(timg.data() + (size_t)rk * rank_bytes + off);
+                __half *lo = hi + (size_t)nh * 16;
+                for (int n = 0; n < nh; n++)
+                    for (int k = 0; k < 16; k++) {
+                        const int row = b.q * TS_N + b.n_lo + rk * nh + n;
+                        const double g = (row < pl->NAp ? G[(size_t)row * pl->NBp + b.kb * 16 + k] : 0.0) * sc;
+                        const float gf = (float)g;
+                        const __half h = __float2half_rn(gf);
+                        const __half l = __float2half_rn(gf - __half2float(h));
+                        const size_t o = ((size_t)(k / 8) * (nh / 8) + n / 8) * 64 + (n % 8) * 8 + (k % 8);
+                        hi[o] = h;
+                        lo[o] = l;
+                    }
+            }
+            off += (size_t)nh * 64;
+        }
+        if (c_end <= TS_MAXCOL && rank_bytes < (size_t)200 * 1024 && tblk.size() <= TS_MAX_BLOCKS && slabs.size() <= TS_MAX_SLABS) {
+            pl->ts_slabs = n_sl;
+            pl->ts_blocks = (int)tblk.size();
+            pl->ts_rank_bytes = (int)rank_bytes;
+            pl->ts_c_end = c_end;
+            pl->ts_c_split = kb_split * 8;
+            pl->ts_q_need2 = q_need2;
+            NB_CUDA(ctx, pl->ts_img.reserve(timg.size()));
+            NB_CUDA(ctx, cudaMemcpy(pl->ts_img.p, timg.data(), timg.size(), cudaMemcpyHostToDevice));
+            pl->ts_blk = tblk;
+            pl->ts_slab = slabs;
+            pl->ts_ok = true;
+        }
+    }
     std::vector<double> t1(W, 0.0);
     if (pl->has_row1)
         for (int k = 0; k < W; k++) t1[k] = r.h_sizes[1] * r.h_vmat[(size_t)(1 - lv) * W + k];
@@ -1013,6 +1616,115 @@ int nb200_nuc_bx_tc(nb200_ctx *ctx, nb200_dbatch *b)
         ProfScope ps(ctx, b->stream, "k_emax");
         k_emax<<<ctx->sm_count * 4, 256, 0, b->stream>>>(b->d_E.as<double>(), b->n_bias, pl->emax.as<unsigned long long>());
         NB_LAUNCH_CHECK(ctx);
+    }
+    static const bool tc_debug = getenv("NB200_TC_DEBUG") != nullptr;
+    static int *h_trap = nullptr;
+    if (tc_debug && !h_trap) {
+        NB_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&h_trap), 2100 * sizeof(int), cudaHostAllocMapped));
+        memset(h_trap, 0, 2100 * sizeof(int));
+        int *d_trap = nullptr;
+        NB_CUDA(ctx, cudaHostGetDevicePointer(reinterpret_cast<void **>(&d_trap), h_trap, 0));
+        NB_CUDA(ctx, cudaMemcpyToSymbol(g_tc_trap_info, &d_trap, sizeof(d_trap)));
+    }
+    static const bool ts_env = !(getenv("NB200_TC_TS") && atoi(getenv("NB200_TC_TS")) == 0);
+    if (pl->ts_ok && ts_env && ctx->sm_count >= 2) {
+        // ---- hi operand in tensor memory (k_nuc_bx_ts) whenever the whole image fits next to the operands
+        TsArgs t;
+        t.start = b->d_start.as<int32_t>();
+        t.out_off = b->d_out_off.as<int64_t>();
+        t.bias_off = b->d_bias_off.as<int64_t>();
+        t.seq_start = b->d_seq_start.as<int32_t>();
+        t.E = b->d_E.as<double>();
+        t.emax = pl->emax.as<double>();
+        t.g_img = pl->ts_img.as<unsigned char>();
+        t.t_row1 = pl->t_row1.as<double>();
+        t.bx = b->n_bx.as<double>();
+        t.dbg = nullptr;
+        t.pwm_up = r.pwm_up;
+        t.A0 = pl->A0;
+        t.B0 = pl->B0;
+        t.NBp = pl->NBp;
+        t.gmin = pl->gmin;
+        t.n_slabs = pl->ts_slabs;
+        t.n_blocks = pl->ts_blocks;
+        t.sG = pl->sG;
+        t.has_row1 = pl->has_row1;
+        t.W = r.v_cols;
+        t.w = r.v_w;
+        t.epad = (32 - ((pl->A0 - pl->gmin) & 31)) & 31;
+        t.n_chunks = b->n_chunks;
+        t.tiles_per_chunk = (int)div_up64(b->max_len, 2 * TC_TX);
+        t.rank_bytes = pl->ts_rank_bytes;
+        t.c_split = pl->ts_c_split;
+        t.c_end = pl->ts_c_end;
+        t.q_need2 = pl->ts_q_need2;
+        // the E window must also cover the a taps of the last slab (TS_N granularity) and the rows the hi operand is expanded from
+        const int gmax = std::max(std::max(TC_TX - 1 + pl->A0 + pl->ts_slabs * TS_N - 1, TC_TX + pl->B0 + std::max(pl->NBp, 2 * pl->ts_c_end) + 8), TC_TX - 1 + r.v_w);
+        t.span = std::max(pl->span, gmax - pl->gmin + 1);
+        t.nZ = (TC_TX + std::max(pl->NBp, 2 * pl->ts_c_end) + 7) / 8;
+        const int Wp4 = (r.v_cols + 3) & ~3;
+        const int cplen = ((t.span + 3 + 31) & ~31) + 8;
+        const size_t smem_ts = ((size_t)t.rank_bytes + 3 * (size_t)t.nZ * 128 + sizeof(float) * 2 * 4 * cplen +
+                                sizeof(float) * (pl->has_row1 ? (Wp4 + 2 * TC_TX) : 0) + sizeof(double) * 4 * TC_M + 8 * (TS_BARS + 1) + 16 + 127) / 128 * 128;
+        if (smem_ts <= 227 * 1024) {
+            void (*kern)(TsTab, TsArgs) = tc_debug ? k_nuc_bx_ts<true> : k_nuc_bx_ts<false>;
+            static TsTab tab;   // filled per launch: the launch copies the parameter
+            memset(&tab, 0, sizeof(tab));
+            memcpy(tab.blk, pl->ts_blk.data(), sizeof(int4) * pl->ts_blk.size());
+            memcpy(tab.slab, pl->ts_slab.data(), sizeof(int2) * pl->ts_slab.size());
+            NB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ts));
+            ProfScope ps(ctx, b->stream, "k_nuc_bx_tc");
+            const int n_items = t.n_chunks * t.tiles_per_chunk;
+            dim3 grid((unsigned)(2 * std::max(1, std::min(ctx->sm_count / 2, n_items))));
+            unsigned long long *d_dbg = nullptr;
+            if (tc_debug) {
+                NB_CUDA(ctx, cudaMalloc(&d_dbg, (size_t)grid.x * 16 * sizeof(unsigned long long)));
+                NB_CUDA(ctx, cudaMemsetAsync(d_dbg, 0, (size_t)grid.x * 16 * sizeof(unsigned long long), b->stream));
+                t.dbg = d_dbg;
+            }
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = grid;
+            cfg.blockDim = dim3(TS_THREADS);
+            cfg.dynamicSmemBytes = smem_ts;
+            cfg.stream = b->stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            NB_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, tab, t));
+            NB_LAUNCH_CHECK(ctx);
+            if (tc_debug) {
+                std::vector<unsigned long long> h((size_t)grid.x * 16);
+                cudaError_t e = cudaStreamSynchronize(b->stream);
+                if (e != cudaSuccess) {
+                    fprintf(stderr, "[ts debug] kernel failed (%s); %d starving warps | first barrier of CTA0 0x%x CTA1 0x%x tmem 0x%x 0x%x; slabs %d blocks %d "
+                                    "c_split %d c_end %d q_need2 %d grid %u\n", cudaGetErrorString(e), h_trap[0], h_trap[8], h_trap[10], h_trap[9], h_trap[11],
+                            t.n_slabs, t.n_blocks, t.c_split, t.c_end, t.q_need2, grid.x);
+                    for (int i = 0; i < std::min(h_trap[0], 60); i++) {
+                        const int *rr = h_trap + 16 + 4 * i;
+                        fprintf(stderr, "[ts debug]   CTA %d warp %d waits on barrier %d parity %d\n", rr[0], rr[1] >> 5,
+                                ((rr[2] & 0xffffff) - (h_trap[8 + 2 * (rr[0] & 1)] & 0xffffff)) / 8, rr[3] & 1);
+                    }
+                    return nb200_cuda_fail(ctx, e, "k_nuc_bx_ts (debug sync)", __FILE__, __LINE__);
+                }
+                NB_CUDA(ctx, cudaMemcpy(h.data(), d_dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+                cudaFree(d_dbg);
+                double mm[16] = {0};
+                for (size_t i = 0; i < grid.x; i++)
+                    for (int k = 0; k < 16; k++) mm[k] += (double)h[16 * i + k];
+                static const char *nm[16] = {"cta_total", "mma_wait_lo_rows", "mma_wait_tmem_empty", "mma_wait_hi_operand", "epi_wait_tmem_full",
+                                            "epi_compute", "epi_wait_ld", "items",
+                                            "prep_wait_set_empty", "fill_wait_free", "prep_item", "prep_E_load", "prep_row1", "fill_body", "-", "-"};
+                fprintf(stderr, "[ts debug] %u CTAs, image %d bytes per CTA, %d slabs, %d blocks, hi operand %d + %d columns, smem %zu:", grid.x, t.rank_bytes,
+                        t.n_slabs, t.n_blocks, t.c_split, t.c_end - t.c_split, smem_ts);
+                for (int k = 0; k < 14; k++) fprintf(stderr, " %s=%.0f", nm[k], mm[k] / (double)grid.x);
+                fprintf(stderr, "\n");
+            }
+            return NB200_OK;
+        }
     }
     TcArgs a;
     a.start = b->d_start.as<int32_t>();
@@ -1061,7 +1773,6 @@ int nb200_nuc_bx_tc(nb200_ctx *ctx, nb200_dbatch *b)
     a.ring = ring;
     static const int stag_env = getenv("NB200_TC_STAGGER") ? atoi(getenv("NB200_TC_STAGGER")) : 2;
     a.stagger = stag_env < 0 ? -1 : std::min(std::min(stag_env, ring - 2), pl->n_stages - 1);
-    static const bool tc_debug = getenv("NB200_TC_DEBUG") != nullptr;
     void (*kern)(TcArgs) = res    ? (tc_debug ? k_nuc_bx_tc<true, true, true> : k_nuc_bx_tc<false, true, true>)
                            : pair ? (tc_debug ? k_nuc_bx_tc<true, true, false> : k_nuc_bx_tc<false, true, false>)
                                   : (tc_debug ? k_nuc_bx_tc<true, false, false> : k_nuc_bx_tc<false, false, false>);
@@ -1072,14 +1783,6 @@ int nb200_nuc_bx_tc(nb200_ctx *ctx, nb200_dbatch *b)
     dim3 grid(pair ? (unsigned)(2 * std::max(1, std::min(ctx->sm_count / 2, n_items))) : (unsigned)std::max(1, std::min(ctx->sm_count, n_items)));
     unsigned long long *d_dbg = nullptr;
     const size_t n_cta = grid.x;
-    static int *h_trap = nullptr;
-    if (tc_debug && !h_trap) {
-        NB_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&h_trap), 2100 * sizeof(int), cudaHostAllocMapped));
-        memset(h_trap, 0, 2100 * sizeof(int));
-        int *d_trap = nullptr;
-        NB_CUDA(ctx, cudaHostGetDevicePointer(reinterpret_cast<void **>(&d_trap), h_trap, 0));
-        NB_CUDA(ctx, cudaMemcpyToSymbol(g_tc_trap_info, &d_trap, sizeof(d_trap)));
-    }
     if (tc_debug) {
         NB_CUDA(ctx, cudaMalloc(&d_dbg, n_cta * 8 * sizeof(unsigned long long)));
         NB_CUDA(ctx, cudaMemsetAsync(d_dbg, 0, n_cta * 8 * sizeof(unsigned long long), b->stream));
