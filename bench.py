@@ -34,7 +34,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "bp scored/sec (occ+nuc), synthetic 10 kb chunks, 251x251 VMat"
 R_V, W_V = 251, 251
-TC_DRAM_BYTES_PER_CHUNK = (34.483e6 + 0.785e6) / 400  # measured, see roofline.traffic_source
+TC_DRAM_BYTES_PER_CHUNK = (34.486e6 + 2.158e6) / 400  # measured, see roofline.traffic_source
 DTYPE = "f64 (tracks, statistics) + fp16x2-split operands / fp32 TMEM accumulation in the tcgen05 background xcor"
 SM_COUNT = 148
 FP64_FMA_PER_CLK_SM = 64     # B200: 64 DFMA per clock and SM (2 flops each); peak = SMs * 64 * 2 * clock
@@ -412,8 +412,8 @@ def run_ours(args, rank, world, local_rank):
         achieved = flop_per_launch / k_avg_s / 1e12 if k_avg_s > 0 else 0.0
         roofline = dict(bound="tensor", kernel=kname, achieved=achieved, peak=peaks["tf_sustained"], unit="TFLOP/s",
                         frac=achieved / peaks["tf_sustained"], traffic=TC_DRAM_BYTES_PER_CHUNK * B if kname == "k_nuc_bx_tc" else None,
-                        traffic_source="ncu --set full, dram__bytes_read+write of k_nuc_bx_tc: 35.27 MB per 400-chunk launch "
-                                       "(profiles/r2_ncu_full.txt), scaled to this launch's chunk count", peak_source=peaks["source"] + " bf16 sustained",
+                        traffic_source="ncu --set full, dram__bytes_read+write of the tcgen05 kernel (k_nuc_bx_ts): 36.64 MB per 400-chunk launch "
+                                       "(profiles/r2b_ncu_ts.txt), scaled to this launch's chunk count", peak_source=peaks["source"] + " bf16 sustained",
                         kernel_ms_per_launch=kms / max(kcount, 1), kernel_share_of_step=kms / total_ms if total_ms else None,
                         algorithmic_flop_per_bp=2.0 * R_V * W_V,
                         tolerance="background / norm_signal / smoothed within 1e-5 of the signal scale max(|signal|, |background|) of the chunk "

@@ -815,9 +815,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
             mbar_wait(bar_zfull + 8 * set, (n >> 1) & 1);
             const float *s_E = s_Eb + (size_t)set * spanp + a.epad;
             const double lin = a.has_row1 ? (double)s_linb[(size_t)set * TC_TX + TC_M * j + m] : 0.0;  // size-1 term (prep warps)
-            // H (fp32 from TMEM) x E (fp32): runs of 8 products are summed in fp32 (4 independent chains per 32 columns),
-            // the runs in fp64 -- rounding ~1e-7 of a run, below the fp16-split error of H itself
-            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            // H (fp32 from TMEM) x E (fp32): runs of 8 products are summed in fp32 (4 independent chains per 32 columns), the
+            // four runs of a chunk in fp32 too, the chunks in fp64 -- rounding ~1e-7 of a chunk of positive terms, below the
+            // fp16-split error of H itself (one conversion + one fp64 add per chunk: the fp64 pipe stalls the epilogue otherwise)
+            double acc[2] = {0.0, 0.0};
             for (int q = 0; q < a.n_achunks; q++, gq++) {
                 const long long t0 = DBG ? clock64() : 0;
                 mbar_wait(bar_tfull + 8 * j, gq & 1);
@@ -847,13 +848,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
                     float f[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int nn = 0; nn < 32; nn++) f[nn >> 3] = fmaf(__uint_as_float(r[h & 1][nn]), Ew[32 * h + nn], f[nn >> 3]);
-#pragma unroll
-                    for (int u = 0; u < 4; u++) acc[u] += (double)f[u];
+                    acc[h & 1] += (double)((f[0] + f[1]) + (f[2] + f[3]));
                 }
                 if (DBG) t_epi += clock64() - t1;
             }
             const int x = x0 + TC_M * j + m;
-            if (x < L) a.bx[oo + x] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) * unscale + lin;
+            if (x < L) a.bx[oo + x] = (acc[0] + acc[1]) * unscale + lin;
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_zempty + 8 * set);      // this warp no longer reads the E window of the set
             n++;
@@ -881,7 +881,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
 // =============================================================================================
 // k_nuc_bx_ts -- the same contraction with the hi half of the Hankel operand in TENSOR MEMORY
 // =============================================================================================
-// What bounds k_nuc_bx_tc (measured with a stand-alone issue loop, profiles/r2_mma_microbench.txt): the 128 B/clk shared-memory
+// What bounds k_nuc_bx_tc (measured with a stand-alone issue loop, profiles/r2b_mma_microbench.txt): the 128 B/clk shared-memory
 // pipe of an SM is shared by the MMAs' operand fetches -- which win -- and the epilogue's loads of E.  An MMA with both
 // operands in shared memory costs max(N/2, (4096 + 16 N)/128) clk in a pair (the A tile alone is 32 clk of the pipe), and
 // while MMAs of N <= 128 run the epilogue gets 11-23 B/clk of E, so a slab drains more slowly than the next one is
@@ -899,6 +899,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
 #ifndef TS_N
 #define TS_N 128                          // slab width = accumulator columns
 #define TS_NACC 2                         // accumulators the slabs go round (measured: 128 x 2 6.16 ms, 96 x 3 6.53 ms per 20 Mbp)
+#endif
+#ifndef TS_EPI_BUF
+#define TS_EPI_BUF 2                      // 32-register sets an epilogue thread reads a slab through
 #endif
 #define TS_ACOL (TS_NACC * TS_N)          // first TMEM column of the hi operand
 #define TS_MAXCOL (TC_TMEM_COLS - TS_ACOL)
@@ -924,7 +927,7 @@ struct TsArgs {
     int n_chunks, tiles_per_chunk;
     int rank_bytes;           // bytes of one CTA's image
     int c_split, c_end;       // hi-operand columns of part 1 / in all (multiples of 32)
-    int q_need2;              // first slab that reads part 2 (-1: none)
+    int q_need2;              // the slab before which part 2 is waited for: the first one that reads it (the last slab if none does)
     int nZ;                   // 128-byte chunks per Hankel part
 };
 
@@ -1207,9 +1210,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_nuc_bx_ts(const __grid_consta
             for (int j = 0; j < TC_XT; j++, tcnt++) {
                 const uint32_t a_lo0 = (((zb + 2048u * j) >> 4) & 0x3FFF) | ((128u >> 4) << 16);
                 for (int q = 0; q < a.n_slabs; q++) {
-                    if (q == 0 || q == a.q_need2) {
+                    if (q == 0 || q == a.q_need2) {   // the columns of the hi operand this slab reads are written (both parts, if both start here)
                         const long long t0 = DBG ? clock64() : 0;
-                        mbar_wait_cluster(bar_afull + 8 * (q == 0 ? 0 : 1), tcnt & 1);   // the columns of the hi operand this slab reads are written
+                        if (q == 0) mbar_wait_cluster(bar_afull, tcnt & 1);
+                        if (q == a.q_need2) mbar_wait_cluster(bar_afull + 8, tcnt & 1);
                         tc_fence_after();
                         if (DBG) w_af += clock64() - t0;
                     }
@@ -1271,7 +1275,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_nuc_bx_ts(const __grid_consta
             // this thread's window starts at element aoff + m (+ multiples of 32): the copy shifted by (aoff + m) & 3 has it aligned
             const float *s_E = s_cpb + (size_t)(set * 4 + ((aoff + m) & 3)) * cplen + ((aoff + m) & ~3);
             for (int j = 0; j < TC_XT; j++, tcnt++) {
-                double acc[4] = {0.0, 0.0, 0.0, 0.0};
+                double acc[2] = {0.0, 0.0};
                 for (int q = 0; q < a.n_slabs; q++, u++) {
                     const uint32_t cab = ab, cph = aph;   // this slab's accumulator and use parity
                     if (++ab == TS_NACC) {
@@ -1286,45 +1290,46 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_nuc_bx_ts(const __grid_consta
                     const long long t1 = DBG ? clock64() : 0;
                     if (DBG) w_tf += t1 - t0;
                     const float4 *Ew = reinterpret_cast<const float4 *>(s_E + TC_M * j + TS_N * q);
-                    // two register sets for the 32-column chunks of a slab: the tcgen05.ld of chunk h + 2 goes out as soon as chunk h has
-                    // been contracted; the accumulator returns to the issuing warp when the last chunk has landed
-                    constexpr int NCH = TS_N / 32;
-                    static_assert(TS_N % 32 == 0 && NCH >= 2, "slab = whole 32-column chunks");
-                    uint32_t r[2][32];
-                    tc_ld32(t0addr, r[0]);
-                    tc_ld32(t0addr + 32u, r[1]);
+                    // TS_EPI_BUF register sets for the 32-column chunks of a slab: the tcgen05.ld of chunk h + TS_EPI_BUF goes out as soon as
+                    // chunk h has been contracted; the accumulator returns to the issuing warp when the last chunk has landed
+                    constexpr int NCH = TS_N / 32, NB = TS_EPI_BUF;
+                    static_assert(TS_N % 32 == 0 && NCH >= NB, "slab = whole 32-column chunks");
+                    uint32_t r[NB][32];
+#pragma unroll
+                    for (int h = 0; h < NB; h++) tc_ld32(t0addr + (uint32_t)(32 * h), r[h]);
 #pragma unroll
                     for (int h = 0; h < NCH; h++) {
-                        if (h < NCH - 1) {
+                        if (h <= NCH - NB) {   // something new has been requested since the last wait
                             const long long tw = DBG ? clock64() : 0;
                             tc_wait_ld();
                             if (DBG) w_ld += clock64() - tw;
                         }
-                        if (h == NCH - 2) {   // the last chunk has landed too: the rest of the slab is in registers
+                        if (h == NCH - NB) {   // the last chunk has landed too: the rest of the slab is in registers
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive_cluster_relaxed(bar_tempty + 8 * cab, 0);
                         }
-                        float f[4] = {0.f, 0.f, 0.f, 0.f};   // runs of 8 products in fp32, the runs in fp64 (as in k_nuc_bx_tc)
+                        float f[4] = {0.f, 0.f, 0.f, 0.f};   // four runs of 8 products in fp32
 #pragma unroll
                         for (int g4 = 0; g4 < 8; g4++) {
                             const float4 e = Ew[8 * h + g4];
                             float v = f[g4 >> 1];
-                            v = fmaf(__uint_as_float(r[h & 1][4 * g4]), e.x, v);
-                            v = fmaf(__uint_as_float(r[h & 1][4 * g4 + 1]), e.y, v);
-                            v = fmaf(__uint_as_float(r[h & 1][4 * g4 + 2]), e.z, v);
-                            v = fmaf(__uint_as_float(r[h & 1][4 * g4 + 3]), e.w, v);
+                            v = fmaf(__uint_as_float(r[h % NB][4 * g4]), e.x, v);
+                            v = fmaf(__uint_as_float(r[h % NB][4 * g4 + 1]), e.y, v);
+                            v = fmaf(__uint_as_float(r[h % NB][4 * g4 + 2]), e.z, v);
+                            v = fmaf(__uint_as_float(r[h % NB][4 * g4 + 3]), e.w, v);
                             f[g4 >> 1] = v;
                         }
-#pragma unroll
-                        for (int k = 0; k < 4; k++) acc[k] += (double)f[k];
-                        if (h + 2 < NCH) tc_ld32(t0addr + (uint32_t)(32 * (h + 2)), r[h & 1]);
+                        // one conversion + one fp64 add per 32 columns: the epilogue warps stall on the fp64 pipe otherwise (ncu: a third
+                        // of their issue stalls were DADD waiting for it); the two extra fp32 roundings are 1e-7 of a chunk of positive terms
+                        acc[h & 1] += (double)((f[0] + f[1]) + (f[2] + f[3]));
+                        if (h + NB < NCH) tc_ld32(t0addr + (uint32_t)(32 * (h + NB)), r[h % NB]);
                     }
                     if (DBG) t_epi += clock64() - t1;
                 }
                 // The group that read the tile's LAST slab finishes the tile; the other one leaves its partial sums in shared memory
                 // and goes on (no rendezvous: it may be up to TS_NACC slabs ahead, less than the 4 tiles the buffers cover).
-                const double part = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+                const double part = acc[0] + acc[1];
                 double *sp = s_part + (size_t)(tcnt & 3) * TC_M;
                 const uint32_t bar_p = bar_pfull + 8 * (uint32_t)(tcnt & 3);
                 if (grp != (int)((u - 1u) & 1u)) {
@@ -1570,7 +1575,7 @@ int nb200_tc_setup(nb200_ctx *ctx)
             pl->ts_rank_bytes = (int)rank_bytes;
             pl->ts_c_end = c_end;
             pl->ts_c_split = kb_split * 8;
-            pl->ts_q_need2 = q_need2;
+            pl->ts_q_need2 = q_need2 >= 0 ? q_need2 : n_sl - 1;   // every phase of every barrier has its wait
             NB_CUDA(ctx, pl->ts_img.reserve(timg.size()));
             NB_CUDA(ctx, cudaMemcpy(pl->ts_img.p, timg.data(), timg.size(), cudaMemcpyHostToDevice));
             pl->ts_blk = tblk;
@@ -1626,7 +1631,7 @@ int nb200_nuc_bx_tc(nb200_ctx *ctx, nb200_dbatch *b)
         NB_CUDA(ctx, cudaHostGetDevicePointer(reinterpret_cast<void **>(&d_trap), h_trap, 0));
         NB_CUDA(ctx, cudaMemcpyToSymbol(g_tc_trap_info, &d_trap, sizeof(d_trap)));
     }
-    static const bool ts_env = !(getenv("NB200_TC_TS") && atoi(getenv("NB200_TC_TS")) == 0);
+    const bool ts_env = !(getenv("NB200_TC_TS") && atoi(getenv("NB200_TC_TS")) == 0);   // read per call: the tests compare the two kernels in one process
     if (pl->ts_ok && ts_env && ctx->sm_count >= 2) {
         // ---- hi operand in tensor memory (k_nuc_bx_ts) whenever the whole image fits next to the operands
         TsArgs t;

@@ -159,6 +159,13 @@ def test_download32_is_the_rounded_float64(eng):
         eng._track_dtype(bad, eng.OCC_TRACKS)
 
 
+def _shrink_vmat(eng, wl):
+    """An earlier test may have left a larger VMat than this workload's fragment sizes cover (the library refuses sizes that
+    do not reach vmat.upper): long sizes first, then the smaller VMat, then Workload.configure can set its own sizes."""
+    eng.set_fragment_sizes(np.full(1200, 1.0 / 1200))
+    eng.set_vmat(wl.vmat, wl.v_lower, wl.v_upper)
+
+
 @pytest.mark.parametrize("size", [101, 151, 201, 301, 401, 501])
 def test_tensor_core_vmat_sweep(eng, size):
     """BASELINE configs[4]: the tcgen05 background cross-correlation (NucleosomeCalling.py:60-63) at VMat sizes 101^2 .. 501^2
@@ -166,6 +173,7 @@ def test_tensor_core_vmat_sweep(eng, size):
     from nucleoatac_b200 import synth
     from nucleoatac_b200.engine import PackedBatch
     wl = synth.Workload(size, size, upper=max(251, size))
+    _shrink_vmat(eng, wl)
     wl.configure(eng, use_bias=True, xcor_mode=2)
     params = refnuc.NucParams((wl.vmat, wl.v_lower, wl.v_upper), wl.fragmentsizes, sd=10)
     margin = size + size // 2 + 40
@@ -194,7 +202,7 @@ def test_batches_in_flight_give_identical_results(eng):
     what each returns when run alone."""
     from nucleoatac_b200 import synth
     wl = synth.Workload(251, 251)
-    eng.set_fragment_sizes(np.full(600, 1.0 / 600))   # an earlier test may have left a larger VMat than this workload's sizes cover
+    _shrink_vmat(eng, wl)
     wl.configure(eng, use_bias=True, xcor_mode=2)
     pbs = [synth.make_batch(20 + 7 * i, 4 + i) for i in range(3)]
     alone = [(eng.process_nuc(pb), eng.process_occ(pb, raw=False)) for pb in pbs]
@@ -224,3 +232,44 @@ def test_batches_in_flight_give_identical_results(eng):
             assert np.array_equal(o1[k].astype(np.float32), o2[k], equal_nan=True), k
         assert np.array_equal(o1["peak_count"], o2["peak_count"]) and np.array_equal(o1["nuc_dist"], o2["nuc_dist"])
         assert np.array_equal(valid(o1, "peak_off", "peak_count", "peak_pos"), valid(o2, "peak_off", "peak_count", "peak_pos"))
+
+
+@pytest.mark.parametrize("size", [(251, 251), (201, 151), (146, 121)])
+def test_both_tensor_core_kernels_agree(eng, size, monkeypatch):
+    """The two tcgen05 forms of the background cross-correlation (NucleosomeCalling.py:60-63) -- hi Hankel operand in tensor
+    memory (k_nuc_bx_ts, the default when G fits in shared memory) and both operands in shared memory (k_nuc_bx_tc,
+    NB200_TC_TS=0) -- against the exact fp64 CUDA-core kernel on ragged chunks (partial x-tiles, an empty chunk): each within
+    1e-5 of the signal scale, each bit-reproducible run to run, the same candidates from all three."""
+    from nucleoatac_b200 import synth
+    from nucleoatac_b200.engine import PackedBatch
+    R, W = size
+    wl = synth.Workload(R, W)
+    _shrink_vmat(eng, wl)
+    margin = W + R // 2 + 40
+    specs = [(3, 700), (5, 5000), (8, 129), (11, 2049), (12, 10000)]
+    chunks = [synth.make_chunk(k, length=L, seq_margin=margin) for k, L in specs]
+    s, e, pos, tlen, seq, s0 = chunks[2]
+    chunks[2] = (s, e, pos[:0], tlen[:0], seq, s0)   # a chunk without reads
+    pb = PackedBatch.from_chunks(chunks)
+    wl.configure(eng, use_bias=True, xcor_mode=1)
+    exact = eng.process_nuc(pb)
+    scale = float(np.abs(exact["background"]).max())
+    wl.configure(eng, use_bias=True, xcor_mode=2)
+    outs = {}
+    for ts in ("1", "0"):
+        monkeypatch.setenv("NB200_TC_TS", ts)
+        eng.profile_reset()
+        a = eng.process_nuc(pb)
+        b = eng.process_nuc(pb)
+        assert eng.profile_report().get("k_nuc_bx_tc", (0, 0.0))[0] == 2
+        assert np.array_equal(a["background"], b["background"]), "not reproducible (NB200_TC_TS=%s)" % ts
+        err = float(np.abs(a["background"] - exact["background"]).max()) / scale
+        assert err <= 1e-5, (size, ts, err)
+        assert np.array_equal(a["cand_count"], exact["cand_count"])
+        for j in range(len(chunks)):
+            co, cn = int(a["cand_off"][j]), int(a["cand_count"][j])
+            assert np.array_equal(a["cand_pos"][co:co + cn], exact["cand_pos"][co:co + cn])
+            assert np.array_equal(a["cand_flag"][co:co + cn] & 4, exact["cand_flag"][co:co + cn] & 4)
+        outs[ts] = (a, err)
+    d = float(np.abs(outs["1"][0]["background"] - outs["0"][0]["background"]).max()) / scale
+    print("VMat %dx%d: |error| / scale: tensor-memory form %.2e, shared-memory form %.2e, difference %.2e" % (R, W, outs["1"][1], outs["0"][1], d))
