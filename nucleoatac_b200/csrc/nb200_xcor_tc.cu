@@ -351,6 +351,16 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t *r)
         : "memory");
 }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// hi + lo += s, error-free (Knuth's two-sum): the epilogues accumulate their fp32 chunk sums as an unevaluated pair of floats
+// (~48 bits) instead of in fp64 -- on this part a warp's DADD waits for the fp64 pipe long enough to show as a fifth of
+// the kernel's issue stalls (ncu source page), and the pair costs seven FADDs on the idle fp32 pipe
+__device__ __forceinline__ void two_sum_acc(float &hi, float &lo, float s)
+{
+    const float t = hi + s;
+    const float bp = t - hi;
+    lo += (hi - (t - bp)) + (s - bp);
+    hi = t;
+}
 // The three MMAs of one K16 block of a CTA pair with the hi half of the A operand in TENSOR MEMORY (tcgen05.mma [d], [a], b-desc):
 // hi * hi and hi * lo read A from TMEM, lo * hi reads the lo Hankel rows from shared memory.
 __device__ __forceinline__ void tc_mma3_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t a_lo_lo, uint32_t b_hi_lo, uint32_t b_lo_lo, uint32_t desc_hi,
@@ -816,9 +826,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
             const float *s_E = s_Eb + (size_t)set * spanp + a.epad;
             const double lin = a.has_row1 ? (double)s_linb[(size_t)set * TC_TX + TC_M * j + m] : 0.0;  // size-1 term (prep warps)
             // H (fp32 from TMEM) x E (fp32): runs of 8 products are summed in fp32 (4 independent chains per 32 columns), the
-            // four runs of a chunk in fp32 too, the chunks in fp64 -- rounding ~1e-7 of a chunk of positive terms, below the
-            // fp16-split error of H itself (one conversion + one fp64 add per chunk: the fp64 pipe stalls the epilogue otherwise)
-            double acc[2] = {0.0, 0.0};
+            // four runs of a chunk in fp32 too, the chunks as an error-free float pair -- rounding ~1e-7 of a chunk of positive
+            // terms, below the fp16-split error of H itself (no fp64 in the loop: see two_sum_acc)
+            float acc_hi = 0.f, acc_lo = 0.f;
             for (int q = 0; q < a.n_achunks; q++, gq++) {
                 const long long t0 = DBG ? clock64() : 0;
                 mbar_wait(bar_tfull + 8 * j, gq & 1);
@@ -848,12 +858,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
                     float f[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int nn = 0; nn < 32; nn++) f[nn >> 3] = fmaf(__uint_as_float(r[h & 1][nn]), Ew[32 * h + nn], f[nn >> 3]);
-                    acc[h & 1] += (double)((f[0] + f[1]) + (f[2] + f[3]));
+                    two_sum_acc(acc_hi, acc_lo, (f[0] + f[1]) + (f[2] + f[3]));
                 }
                 if (DBG) t_epi += clock64() - t1;
             }
             const int x = x0 + TC_M * j + m;
-            if (x < L) a.bx[oo + x] = (acc[0] + acc[1]) * unscale + lin;
+            if (x < L) a.bx[oo + x] = ((double)acc_hi + (double)acc_lo) * unscale + lin;
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_zempty + 8 * set);      // this warp no longer reads the E window of the set
             n++;
@@ -900,8 +910,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
 #define TS_N 128                          // slab width = accumulator columns
 #define TS_NACC 2                         // accumulators the slabs go round (measured: 128 x 2 6.16 ms, 96 x 3 6.53 ms per 20 Mbp)
 #endif
+#ifndef TS_FIN32
+#define TS_FIN32 1                        // the last additions of an output in fp32 too (A/B in one run: 5.64 -> 5.54 ms; with TS_EPI_BUF 3: 5.49)
+#endif
 #ifndef TS_EPI_BUF
-#define TS_EPI_BUF 2                      // 32-register sets an epilogue thread reads a slab through
+#define TS_EPI_BUF 3                      // 32-register sets an epilogue thread reads a slab through
 #endif
 #define TS_ACOL (TS_NACC * TS_N)          // first TMEM column of the hi operand
 #define TS_MAXCOL (TC_TMEM_COLS - TS_ACOL)
@@ -970,7 +983,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_nuc_bx_ts(const __grid_consta
     const int Wp = (a.W + 3) & ~3;
     float *s_t1 = reinterpret_cast<float *>(p);             p += sizeof(float) * (a.has_row1 ? Wp : 0);
     float *s_linb = reinterpret_cast<float *>(p);           p += sizeof(float) * (a.has_row1 ? 2 * TC_TX : 0);
-    double *s_part = reinterpret_cast<double *>(p);         p += sizeof(double) * 4 * TC_M;       // [tile & 3][128]: the partial sums of the group that does not finish the tile
+    double *s_part = reinterpret_cast<double *>(p);         p += sizeof(double) * 4 * TC_M;       // [tile & 3][128]: the partial sums of the group that does not finish the tile (a double or a float pair)
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(p);      p += sizeof(uint64_t) * (TS_BARS + 1);
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(p);
     const uint32_t bar_gfull = smem_u32(s_bar), bar_zfull = bar_gfull + 8, bar_zempty = bar_zfull + 16, bar_zpair = bar_zempty + 16,
@@ -1261,6 +1274,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_nuc_bx_ts(const __grid_consta
         const int m = wq * 32 + lane;
         const int aoff = a.A0 - a.gmin;
         const double unscale = ldexp(1.0, -(sE + a.sG));
+#if TS_FIN32
+        const bool unscale_f32 = sE + a.sG > -100 && sE + a.sG < 100;
+        const float unscale_f = unscale_f32 ? (float)unscale : 0.f;
+#endif
         const uint32_t tqaddr = tmem + ((uint32_t)(wq * 32) << 16);
         long long w_tf = 0, t_epi = 0, w_ld = 0;
         int n = 0, tcnt = 0;
@@ -1275,7 +1292,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_nuc_bx_ts(const __grid_consta
             // this thread's window starts at element aoff + m (+ multiples of 32): the copy shifted by (aoff + m) & 3 has it aligned
             const float *s_E = s_cpb + (size_t)(set * 4 + ((aoff + m) & 3)) * cplen + ((aoff + m) & ~3);
             for (int j = 0; j < TC_XT; j++, tcnt++) {
-                double acc[2] = {0.0, 0.0};
+                float acc_hi = 0.f, acc_lo = 0.f;
                 for (int q = 0; q < a.n_slabs; q++, u++) {
                     const uint32_t cab = ab, cph = aph;   // this slab's accumulator and use parity
                     if (++ab == TS_NACC) {
@@ -1320,16 +1337,39 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_nuc_bx_ts(const __grid_consta
                             v = fmaf(__uint_as_float(r[h % NB][4 * g4 + 3]), e.w, v);
                             f[g4 >> 1] = v;
                         }
-                        // one conversion + one fp64 add per 32 columns: the epilogue warps stall on the fp64 pipe otherwise (ncu: a third
-                        // of their issue stalls were DADD waiting for it); the two extra fp32 roundings are 1e-7 of a chunk of positive terms
-                        acc[h & 1] += (double)((f[0] + f[1]) + (f[2] + f[3]));
+                        // the chunk's four runs in fp32 (two more roundings: 1e-7 of a chunk of positive terms), the chunks as a float pair
+                        two_sum_acc(acc_hi, acc_lo, (f[0] + f[1]) + (f[2] + f[3]));
                         if (h + NB < NCH) tc_ld32(t0addr + (uint32_t)(32 * (h + NB)), r[h % NB]);
                     }
                     if (DBG) t_epi += clock64() - t1;
                 }
                 // The group that read the tile's LAST slab finishes the tile; the other one leaves its partial sums in shared memory
                 // and goes on (no rendezvous: it may be up to TS_NACC slabs ahead, less than the 4 tiles the buffers cover).
-                const double part = acc[0] + acc[1];
+#if TS_FIN32
+                float2 *sp = reinterpret_cast<float2 *>(s_part) + (size_t)(tcnt & 3) * TC_M;
+                const uint32_t bar_p = bar_pfull + 8 * (uint32_t)(tcnt & 3);
+                if (grp != (int)((u - 1u) & 1u)) {
+                    sp[m] = make_float2(acc_hi, acc_lo);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_p);   // release: the partial sums are visible to the waiting group
+                } else {
+                    if (a.has_row1 && j == 0) mbar_wait(bar_linfull + 8 * set, (n >> 1) & 1);
+                    mbar_wait(bar_p, (uint32_t)(tcnt >> 2) & 1u);
+                    const int x = x0 + TC_M * j + m;
+                    const float lin = a.has_row1 ? s_linb[(size_t)set * TC_TX + TC_M * j + m] : 0.f;  // size-1 term (prep warps)
+                    const float2 o = sp[m];
+                    // group 0's pair first, whoever adds: one order of summation; sum and power-of-two unscaling in fp32 when the scale is an fp32 normal
+                    const float h0 = grp ? o.x : acc_hi, l0 = grp ? o.y : acc_lo, h1 = grp ? acc_hi : o.x, l1 = grp ? acc_lo : o.y;
+                    if (x < L) {
+                        if (unscale_f32)
+                            a.bx[oo + x] = (double)fmaf((h0 + h1) + (l0 + l1), unscale_f, lin);
+                        else
+                            a.bx[oo + x] = (((double)h0 + (double)h1) + ((double)l0 + (double)l1)) * unscale + (double)lin;
+                    }
+                }
+            }
+#else
+                const double part = (double)acc_hi + (double)acc_lo;
                 double *sp = s_part + (size_t)(tcnt & 3) * TC_M;
                 const uint32_t bar_p = bar_pfull + 8 * (uint32_t)(tcnt & 3);
                 if (grp != (int)((u - 1u) & 1u)) {
@@ -1345,6 +1385,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_nuc_bx_ts(const __grid_consta
                     if (x < L) a.bx[oo + x] = (p0 + p1) * unscale + lin;
                 }
             }
+#endif
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_zempty + 8 * set);      // this warp no longer reads the E window of the set
             n++;
