@@ -71,6 +71,9 @@ __device__ __forceinline__ double bias_cell(const double *Ec, int i)
 #ifndef PC_THREADS
 #define PC_THREADS 128
 #endif
+#ifndef PC_SHARED_PRODUCTS
+#define PC_SHARED_PRODUCTS 1
+#endif
 template <int NW>
 struct PairColsumArgs {
     const int32_t *start;
@@ -133,6 +136,23 @@ static __global__ void __launch_bounds__(PC_THREADS) k_pair_colsums(PairColsumAr
     for (int j = 0; j < J2; j += 2) {
         const double2 Ln = *reinterpret_cast<const double2 *>(Ec - j - 2);   // (E[c-j-2], E[c-j-1])
         const double2 Rn = *reinterpret_cast<const double2 *>(Ec + j + 2);   // (E[c+j+2], E[c+j+3])
+#if PC_SHARED_PRODUCTS
+        // the two-tap products E[l] E[r] of the four cells (column, step) are the same for every weight vector: 8 multiplies +
+        // 8 FMAs per weight instead of 12 operations per weight (NW = 3: 32 instead of 36); also the reference's own order
+        // (Bp = E[l] E[r] first, chunkmat2d.py:140-153, then the weighted sum)
+        const double p00 = Lc.x * Rc.x, p01 = Lc.x * Rc.y;   // column c,   step j:   sizes 2j+1, 2j+2
+        const double p10 = Lc.y * Rc.y, p11 = Lc.y * Rn.x;   // column c+1, step j
+        const double q00 = Ln.y * Rc.y, q01 = Ln.y * Rn.x;   // column c,   step j+1
+        const double q10 = Lc.x * Rn.x, q11 = Lc.x * Rn.y;   // column c+1, step j+1
+#pragma unroll
+        for (int t = 0; t < NW; t++) {
+            const double2 wa = s_wp[t * J2 + j], wb = s_wp[t * J2 + j + 1];
+            s0[t] = fma(wa.y, p01, fma(wa.x, p00, s0[t]));
+            s1[t] = fma(wa.y, p11, fma(wa.x, p10, s1[t]));
+            s0[t] = fma(wb.y, q01, fma(wb.x, q00, s0[t]));
+            s1[t] = fma(wb.y, q11, fma(wb.x, q10, s1[t]));
+        }
+#else
 #pragma unroll
         for (int t = 0; t < NW; t++) {
             const double2 wa = s_wp[t * J2 + j], wb = s_wp[t * J2 + j + 1];
@@ -141,6 +161,7 @@ static __global__ void __launch_bounds__(PC_THREADS) k_pair_colsums(PairColsumAr
             s0[t] = fma(Ln.y, fma(wb.x, Rc.y, wb.y * Rn.x), s0[t]);   // column c,   step j+1
             s1[t] = fma(Lc.x, fma(wb.x, Rn.x, wb.y * Rn.y), s1[t]);   // column c+1, step j+1
         }
+#endif
         Lc = Ln;
         Rc = Rn;
     }
