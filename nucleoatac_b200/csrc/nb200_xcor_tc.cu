@@ -1714,7 +1714,7 @@ int nb200_nuc_bx_tc(nb200_ctx *ctx, nb200_dbatch *b)
                                 sizeof(float) * (pl->has_row1 ? (Wp4 + 2 * TC_TX) : 0) + sizeof(double) * 4 * TC_M + 8 * (TS_BARS + 1) + 16 + 127) / 128 * 128;
         if (smem_ts <= 227 * 1024) {
             void (*kern)(TsTab, TsArgs) = tc_debug ? k_nuc_bx_ts<true> : k_nuc_bx_ts<false>;
-            static TsTab tab;   // filled per launch: the launch copies the parameter
+            TsTab tab;   // 3 KB, passed by value: the launch copies the parameter
             memset(&tab, 0, sizeof(tab));
             memcpy(tab.blk, pl->ts_blk.data(), sizeof(int4) * pl->ts_blk.size());
             memcpy(tab.slab, pl->ts_slab.data(), sizeof(int2) * pl->ts_slab.size());
