@@ -17,18 +17,18 @@
 // ring.  fp64-grade accuracy of the operands comes from a 2-term fp16 split (hi + lo, 22 bits) of both operands,
 // scaled by powers of two into the fp16 range: three MMAs hi*hi + hi*lo + lo*hi accumulate in fp32 TMEM.
 //
-// Persistent kernel, one CTA per SM, work item = (chunk, 2 x-tiles of 128 outputs).  H is produced in slabs of
-// TC_N = 192 columns (a taps); every K16 block of a slab is contracted by MMAs whose N is TRIMMED to the 16-row
-// granules of G that are non-zero in that block (the non-zero region of G is a hexagon inside the NA x NB box), so
-// the tensor pipe neither multiplies nor fetches the zero corners: 7.8 k MMA cycles per x-tile at 251x251 against
-// 10.8 k for untrimmed 128-wide slabs, and the A operand is fetched once per 192 instead of 128 columns.
-// TMEM holds one 192-column accumulator per x-tile; the two x-tiles are independent accumulation streams (one issuing
-// warp each), so while the finished slab of one tile is read back the tensor pipe contracts the other tile.  Warp
-// roles (connected by mbarriers only): 0-7 epilogue (tcgen05.ld of H, contraction with the fp32 track in runs of 8
-// summed in fp64), 8 bulk-copy producer, 9-10 MMA issuers (the whole warp runs the loop, one elected lane issues),
-// 11-14 operand generation for the NEXT item (E window -> fp32 + fp16 hi/lo Hankel rows, double-buffered).  What
-// bounds it is the shared-memory data pipe (MMA operand fetches + the epilogue's E reads, which are laid out so that
-// a warp's 32 consecutive floats never straddle a 128-byte line).
+// Two kernels, both persistent (one CTA per SM, CTA pairs on a TPC contracting their x-tiles with cta_group::2 MMAs of
+// M = 256), warp-specialised and connected by mbarriers only:
+//   k_nuc_bx_ts  the default whenever a CTA's half of the G image fits in shared memory (up to ~251 x 251): G resident, the hi
+//                half of the Hankel operand of one x-tile expanded in TENSOR MEMORY (two of a block's three MMAs read A from
+//                TMEM), issue loop on the uniform datapath, slabs of 128 columns through two accumulators;
+//   k_nuc_bx_tc  both operands in shared memory, G streamed L2 -> SMEM through a ring (or resident), slabs of 192 columns,
+//                one accumulator per x-tile: larger VMats, and NB200_TC_TS=0.
+// H is produced in slabs (a taps); every K16 block of a slab is contracted by MMAs whose N is TRIMMED to the 16-row granules
+// of G that are non-zero in that block (the non-zero region of G is a hexagon inside the NA x NB box), so the tensor pipe
+// neither multiplies nor fetches the zero corners.  The epilogue warps read a finished slab back (tcgen05.ld) and contract
+// it with the fp32 track: runs of 8 products in fp32, a 32-column chunk's runs in fp32, the chunks as an error-free float
+// pair.  What each kernel is bound by, and what was measured on the way, is in DESIGN.md section 3.
 #include <cuda_fp16.h>
 
 #include <algorithm>
@@ -200,47 +200,6 @@ __device__ __forceinline__ uint32_t cluster_ctarank()
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// same, descriptors given as (low word, high word): the issuing thread only does 32-bit adds on the low word
-__device__ __forceinline__ void tc_mma_f16_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
-                                             uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-        "mov.b64 da, {%1, %2};\n\t"
-        "mov.b64 db, {%3, %4};\n\t"
-        "setp.ne.b32 p, %6, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
-        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// Whole-warp (convergent) forms: every lane executes the call, one elected lane issues.  Keeping the issuing warp convergent
-// lets ptxas emit a bare ELECT + predicated UTCHMMA instead of a per-instruction election loop.
-__device__ __forceinline__ void tc_mma_f16_e(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
-                                             uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
-        "elect.sync _|e, 0xffffffff;\n\t"
-        "mov.b64 da, {%1, %2};\n\t"
-        "mov.b64 db, {%3, %4};\n\t"
-        "setp.ne.b32 p, %6, 0;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
-        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
 __device__ __forceinline__ void tc_commit_e(uint32_t bar)
 {
     asm volatile(
@@ -249,22 +208,11 @@ __device__ __forceinline__ void tc_commit_e(uint32_t bar)
         "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
         : "memory");
 }
-// CTA-pair forms (cta_group::2): one MMA of M = 256 spans the two CTAs of the pair -- rows 0..127 from the leader's A
-// operand and accumulator, rows 128..255 from the peer's, each CTA's shared memory holding half of the N rows of B.
-// Issued by the leader only; a commit can arrive on the same barrier of both CTAs (multicast mask 0b11).
-__device__ __forceinline__ void tc_mma_f16_e2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
-                                              uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
-        "elect.sync _|e, 0xffffffff;\n\t"
-        "mov.b64 da, {%1, %2};\n\t"
-        "mov.b64 db, {%3, %4};\n\t"
-        "setp.ne.b32 p, %6, 0;\n\t"
-        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
-        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
+// Shared-memory operands are K-major, no-swizzle matrix descriptors (cute::UMMA::SmemDescriptor): 8x16B core matrices, low
+// word = start address >> 4 | (LBO >> 4) << 16 (LBO = byte stride between the 16-byte K chunks), high word = SBO >> 4 (byte
+// stride between 8-row groups) | version 1 << 14.  CTA-pair forms (cta_group::2): one MMA of M = 256 spans the two CTAs of
+// the pair -- rows 0..127 from the leader's A operand and accumulator, rows 128..255 from the peer's, each CTA's shared
+// memory holding half of the N rows of B; issued by the leader only; a commit can arrive on the same barrier of both CTAs.
 // The three MMAs of one K16 block -- hi*hi (accumulate = acc0), hi*lo, lo*hi -- behind ONE election: the issuing warp
 // pays for every operand it moves into uniform registers and for every election / vote, so that set-up is shared by
 // the block's three instructions (SASS: ~35 instructions per block instead of ~70).  CG = 1: single CTA, 2: CTA pair.
@@ -319,13 +267,6 @@ __device__ __forceinline__ void tc_commit_e2_local(uint32_t bar)
         "elect.sync _|e, 0xffffffff;\n\t"
         "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
         : "memory");
-}
-// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 8x16B core matrices,
-// SBO = byte stride between 8-row groups, LBO = byte stride between the 16-byte K chunks, version 1 (sm_100).
-__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo)
-{
-    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
-           (1ull << 46);
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t *r)
 {

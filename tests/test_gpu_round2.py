@@ -273,3 +273,32 @@ def test_both_tensor_core_kernels_agree(eng, size, monkeypatch):
         outs[ts] = (a, err)
     d = float(np.abs(outs["1"][0]["background"] - outs["0"][0]["background"]).max()) / scale
     print("VMat %dx%d: |error| / scale: tensor-memory form %.2e, shared-memory form %.2e, difference %.2e" % (R, W, outs["1"][1], outs["0"][1], d))
+
+
+@pytest.mark.parametrize("shape", [(60, 41, 0), (121, 201, 0), (200, 101, 30), (33, 251, 100), (251, 101, 0), (97, 63, 150), (250, 249, 1),
+                                   (16, 17, 120), (280, 121, 0)])
+def test_tensor_core_vmat_shapes(eng, shape, monkeypatch):
+    """VMat shapes off the beaten path (rows != columns, lower > 0 -- without the single-tap size-1 row --, a few rows only, more
+    than two or fewer than two slabs of a taps): both tcgen05 kernels against the exact fp64 kernel, 1e-5 of the signal scale.
+    The block plan of k_nuc_bx_ts (slabs, the split of the tensor-memory operand, which slab waits for its second part)
+    derives from the shape."""
+    from nucleoatac_b200 import synth
+    from nucleoatac_b200.engine import PackedBatch
+    R, W, lower = shape
+    wl = synth.Workload(R, W, upper=lower + R, lower=lower)
+    _shrink_vmat(eng, wl)
+    margin = W + (lower + R) // 2 + 40
+    chunks = [synth.make_chunk(k, length=L, seq_margin=margin) for k, L in ((21, 1500), (22, 513), (23, 3100))]
+    pb = PackedBatch.from_chunks(chunks)
+    wl.configure(eng, use_bias=True, xcor_mode=1)
+    exact = eng.process_nuc(pb)["background"]
+    scale = float(np.abs(exact).max())
+    assert scale > 0.0, "the fragment-size distribution has no mass on this VMat's rows: nothing to compare"
+    wl.configure(eng, use_bias=True, xcor_mode=2)
+    errs = []
+    for ts in ("1", "0"):
+        monkeypatch.setenv("NB200_TC_TS", ts)
+        got = eng.process_nuc(pb)["background"]
+        errs.append(float(np.abs(got - exact).max()) / scale)
+        assert errs[-1] <= 1e-5, (shape, ts, errs[-1])
+    print("VMat %dx%d, sizes from %d: |error| / scale %.2e (tensor-memory form), %.2e (shared-memory form)" % (R, W, lower, errs[0], errs[1]))
