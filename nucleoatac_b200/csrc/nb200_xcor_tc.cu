@@ -1428,6 +1428,12 @@ int nb200_tc_setup(nb200_ctx *ctx)
             blks.push_back({kb, n_lo, n_hi - n_lo});
         }
         if (blks.empty()) blks.push_back({0, 0, TC_N});  // keep every slab present (one zero block)
+        {   // the untrimmed first block of the slab: the widest one instead of the first in K order (see the second plan below)
+            size_t widest = 0;
+            for (size_t i = 1; i < blks.size(); i++)
+                if (blks[i].n_t > blks[widest].n_t) widest = i;
+            std::rotate(blks.begin(), blks.begin() + widest, blks.begin() + widest + 1);
+        }
         blks[0].n_lo = 0;
         blks[0].n_t = TC_N;
         size_t bi = 0;
@@ -1510,7 +1516,14 @@ int nb200_tc_setup(nb200_ctx *ctx)
                 blks.push_back({q, kb, r_lo / 16 * 16, (r_hi + 16) / 16 * 16 - r_lo / 16 * 16});
             }
             if ((int)blks.size() == first) blks.push_back({q, 0, 0, TS_N});
-            blks[first].n_lo = 0;   // the first MMA of a slab initialises every accumulator column
+            // the first MMA of a slab initialises every accumulator column, so it is issued untrimmed: take the block that is
+            // (closest to) full width anyway instead of the first in K order, whose rows are a corner of the hexagon
+            // (251 x 251: 320 of 4912 MMA columns per x-tile saved; 5.44 -> 5.27 ms in an interleaved A/B)
+            int widest = first;
+            for (int i = first; i < (int)blks.size(); i++)
+                if (blks[i].n_t > blks[widest].n_t) widest = i;
+            std::rotate(blks.begin() + first, blks.begin() + widest, blks.begin() + widest + 1);
+            blks[first].n_lo = 0;
             blks[first].n_t = TS_N;
             slabs.push_back(make_int2(first, (int)blks.size() - first));
         }
