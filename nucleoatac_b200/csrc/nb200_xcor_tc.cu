@@ -1626,7 +1626,11 @@ int nb200_nuc_bx_tc(nb200_ctx *ctx, nb200_dbatch *b)
         NB_CUDA(ctx, cudaHostGetDevicePointer(reinterpret_cast<void **>(&d_trap), h_trap, 0));
         NB_CUDA(ctx, cudaMemcpyToSymbol(g_tc_trap_info, &d_trap, sizeof(d_trap)));
     }
-    const bool ts_env = !(getenv("NB200_TC_TS") && atoi(getenv("NB200_TC_TS")) == 0);   // read per call: the tests compare the two kernels in one process
+    // NB200_TC_TS = 1 / 0 forces / forbids the tensor-memory kernel (read per call: the tests compare the two kernels in one
+    // process).  By default it is used from ~24 K16 blocks per x-tile on: below that (VMats under ~151 x 151) an x-tile is
+    // so short that expanding its operand into tensor memory costs more than it saves (101 x 101: 9.6 % against 12.9 % of peak).
+    const char *ts_e = getenv("NB200_TC_TS");
+    const bool ts_env = ts_e ? atoi(ts_e) != 0 : pl->ts_blocks >= 24;
     if (pl->ts_ok && ts_env && ctx->sm_count >= 2) {
         // ---- hi operand in tensor memory (k_nuc_bx_ts) whenever the whole image fits next to the operands
         TsArgs t;
