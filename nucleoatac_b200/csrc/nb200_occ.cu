@@ -23,13 +23,13 @@ struct OccMleArgs {
     const int32_t *col_ptr;
     const int2 *ent;
     const double *E, *cn, *cf, *pn, *pf, *alphas;
-    const double *wsn, *wsf;   // per window: sums of cn / cf over its 2*flank+1 columns (k_occ_winsums); window k of chunk c at out_off[c]/step + c + k
+    const double *wsn, *wsf;   // per window: RECIPROCALS of the sums of cn / cf over its 2*flank+1 columns (k_occ_winsums); window k of chunk c at out_off[c]/step + c + k
     double *vals, *lower, *upper_b;
     double *wv;            // per-window occ / lower / upper (3 slabs of wv_stride), or null
     int64_t wv_stride;
     int pwm_up, upper, flank, step, halfstep, csc_pad, n_alpha, use_bias;
     int pn_has_zero, pf_has_zero, both_zero;
-    double cutoff, sn_nobias, sf_nobias;
+    double cutoff, sn_nobias, sf_nobias;   // the last two: 1 / (sum of the model over a window) without a bias model
     double thr_m;   // exp(-cutoff/2) = thr_m * 2^thr_e, thr_m in [1,2) (NaN for a NaN cutoff); thr_zero: it underflows to 0
     int thr_e, thr_zero;
 };
@@ -77,8 +77,10 @@ __global__ void __launch_bounds__(WS_WIN) k_occ_winsums(const int64_t *__restric
         f4[0] += pf[k];
     }
     const int64_t wo = oo / step + c + k0 + threadIdx.x;
-    wsn[wo] = (n4[0] + n4[1]) + (n4[2] + n4[3]);
-    wsf[wo] = (f4[0] + f4[1]) + (f4[2] + f4[3]);
+    // stored as reciprocals: every lane of the likelihood kernels would otherwise divide by the same two sums (the division
+    // is the same correctly rounded IEEE operation here as there, so the grids are bit-identical)
+    wsn[wo] = 1.0 / ((n4[0] + n4[1]) + (n4[2] + n4[3]));
+    wsf[wo] = 1.0 / ((f4[0] + f4[1]) + (f4[2] + f4[3]));
 }
 
 // One window per 8-lane group, 4 windows per warp (Occupancy.py:104-146).  The bias of a fragment's insert size over the
@@ -131,13 +133,12 @@ __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle(OccMleArgs a)
     int nmax = n;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(NB_FULL, nmax, o));
-    double SN = a.sn_nobias, SF = a.sf_nobias;
+    double rSN = a.sn_nobias, rSF = a.sf_nobias;   // reciprocals of the window's normalisers
     if (a.use_bias && valid) {
         const int64_t wo = oo / a.step + c + wi;
-        SN = a.wsn[wo];
-        SF = a.wsf[wo];
+        rSN = a.wsn[wo];
+        rSF = a.wsf[wo];
     }
-    const double rSN = 1.0 / SN, rSF = 1.0 / SF;
     double mant[NQ];
     int ex[NQ];
 #pragma unroll
@@ -373,13 +374,12 @@ __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle_search(OccMleArg
     int nmax = n;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(NB_FULL, nmax, o));
-    double SN = a.sn_nobias, SF = a.sf_nobias;
+    double rSN = a.sn_nobias, rSF = a.sf_nobias;   // reciprocals of the window's normalisers
     if (a.use_bias && valid) {
         const int64_t wo = oo / a.step + c + wi;
-        SN = a.wsn[wo];
-        SF = a.wsf[wo];
+        rSN = a.wsn[wo];
+        rSF = a.wsf[wo];
     }
-    const double rSN = 1.0 / SN, rSF = 1.0 / SF;
     // lane (g, r) prepares fragment idx of window g: nuc_probs / sum, nfr_probs / sum (Occupancy.py:106-109), the pair
     // scaled by a power of two so that max(p, q) is in [1, 2) (exact, constant in alpha); padding fragments are the factor 1
     auto prep = [&](int idx, double &pv, double &qv) {
@@ -793,13 +793,12 @@ __global__ void __launch_bounds__(MTW_THREADS, LB) k_occ_mle_tw(OccMleArgs a)
     const int t = a.halfstep + wi * a.step;
     const int e0 = cp[t - a.flank + a.csc_pad], e1 = cp[t + a.flank + 1 + a.csc_pad];
     const int n = e1 - e0;
-    double SN = a.sn_nobias, SF = a.sf_nobias;
+    double rSN = a.sn_nobias, rSF = a.sf_nobias;   // reciprocals of the window's normalisers
     if (a.use_bias) {
         const int64_t wo = oo / a.step + c + wi;
-        SN = a.wsn[wo];
-        SF = a.wsf[wo];
+        rSN = a.wsn[wo];
+        rSF = a.wsf[wo];
     }
-    const double rSN = 1.0 / SN, rSF = 1.0 / SF;
     // fragment f: nuc_probs / sum, nfr_probs / sum (Occupancy.py:106-109), the pair scaled by a power of two so that
     // max(p, q) is in [1, 2) (exact, constant in alpha)
     auto prep = [&](int f, double &pv, double &qv) {
@@ -1533,8 +1532,8 @@ int nb200_occ_run(nb200_ctx *ctx, nb200_dbatch *b)
             a.thr_m = (k > 0.0 && std::isfinite(k)) ? 2.0 * m : (k == 0.0 ? 1.0 : (double)NAN);  // NaN: nothing passes
             a.thr_e = e - 1;
         }
-        a.sn_nobias = r.pn_sum * window;
-        a.sf_nobias = r.pf_sum * window;
+        a.sn_nobias = 1.0 / (r.pn_sum * window);
+        a.sf_nobias = 1.0 / (r.pf_sum * window);
         int max_win = (b->max_len - halfstep + p.step - 1) / p.step;
         if (max_win < 1) max_win = 1;
         const size_t smem = sizeof(double) * 2 * (size_t)p.upper;
