@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle(OccMleArgs a)
             mant[NQ - 1] *= v;
         }
         __syncwarp();
-        if ((base & 24) == 24) {  // every 32 factors (each in (2^-7, 2) away from the grid ends): exponent -> ex
+        if ((base & 56) == 56) {  // every 64 factors (each in (2^-7, 2) away from the grid ends, so the product stays above 2^-448): exponent -> ex
 #pragma unroll
             for (int q = 0; q < NQ; q++) {
                 const long long bits = __double_as_longlong(mant[q]);
