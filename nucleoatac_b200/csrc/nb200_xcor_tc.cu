@@ -71,7 +71,7 @@ struct TcPlan {
     std::vector<int4> h_tab, h_blk;
     // second plan, for k_nuc_bx_ts (hi half of the Hankel operand in tensor memory): slabs of TS_N rows, every block image resident
     bool ts_ok = false;
-    int ts_slabs = 0, ts_blocks = 0, ts_rank_bytes = 0, ts_c_split = 0, ts_c_end = 0, ts_q_need2 = -1;
+    int ts_slabs = 0, ts_blocks = 0, ts_rank_bytes = 0, ts_c_split = 0, ts_c_end = 0, ts_q_need2 = -1, ts_t_need2 = 0;
     DevBuf ts_img;
     std::vector<int4> ts_blk;     // block and slab tables: passed to the kernel by value (TsTab)
     std::vector<int2> ts_slab;
@@ -844,9 +844,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_nuc_bx_tc(TcArgs a)
 // one after the other, slab by slab through the two accumulators (unit u -> accumulator u & 1); the two groups of four
 // epilogue warps take alternate units and add their partial sums per tile through shared memory.  The operand is
 // written by the operand-generation warps (tcgen05.st from the hi Hankel rows they produced in shared memory) in two
-// parts: the columns that slab 0 reads (K blocks < kb_split) as soon as the previous tile's last MMA that reads them has
-// retired (a commit in the middle of its last slab), the rest when the previous tile is complete -- under slab 0 of the new
-// tile.  CTA pairs, resident G and the fused issue of a block's three MMAs are as in k_nuc_bx_tc<.., true, true>.
+// parts: the K blocks the tile's last slab does not read as soon as the previous tile's last MMA that reads them has
+// retired (a commit a whole slab before its end), the rest when the previous tile is complete -- under the part-1 blocks
+// of slab 0 of the new tile, which are issued first.  CTA pairs, resident G and the fused issue of a block's three MMAs are as in k_nuc_bx_tc<.., true, true>.
 #ifndef TS_N
 #define TS_N 128                          // slab width = accumulator columns
 #define TS_NACC 2                         // accumulators the slabs go round (measured: 128 x 2 6.16 ms, 96 x 3 6.53 ms per 20 Mbp)
@@ -881,7 +881,7 @@ struct TsArgs {
     int n_chunks, tiles_per_chunk;
     int rank_bytes;           // bytes of one CTA's image
     int c_split, c_end;       // hi-operand columns of part 1 / in all (multiples of 32)
-    int q_need2;              // the slab before which part 2 is waited for: the first one that reads it (the last slab if none does)
+    int q_need2, t_need2;     // the first block (in issue order) that reads part 2 of the operand: its slab and its position in the slab
     int nZ;                   // 128-byte chunks per Hankel part
 };
 
@@ -892,7 +892,7 @@ struct TsArgs {
 #define TS_MAX_BLOCKS 192
 #define TS_MAX_SLABS 8
 struct TsTab {
-    int4 blk[TS_MAX_BLOCKS];   // per K16 block {K block | flags << 16 (bit 0: part 1 of the hi operand is read no more after it), first row n_lo, instruction descriptor, image offset / 16 | rows per CTA << 16}
+    int4 blk[TS_MAX_BLOCKS];   // per K16 block {K block | flags << 16 (bit 0: part 1 of the hi operand is read no more after it, bit 2: the first block that reads part 2), first row n_lo, instruction descriptor, image offset / 16 | rows per CTA << 16}
     int2 slab[TS_MAX_SLABS];   // per slab {first block, blocks}
 };
 
@@ -1164,10 +1164,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_nuc_bx_ts(const __grid_consta
             for (int j = 0; j < TC_XT; j++, tcnt++) {
                 const uint32_t a_lo0 = (((zb + 2048u * j) >> 4) & 0x3FFF) | ((128u >> 4) << 16);
                 for (int q = 0; q < a.n_slabs; q++) {
-                    if (q == 0 || q == a.q_need2) {   // the columns of the hi operand this slab reads are written (both parts, if both start here)
+                    if (q == 0) {   // part 1 of the tile's hi operand is written
                         const long long t0 = DBG ? clock64() : 0;
-                        if (q == 0) mbar_wait_cluster(bar_afull, tcnt & 1);
-                        if (q == a.q_need2) mbar_wait_cluster(bar_afull + 8, tcnt & 1);
+                        mbar_wait_cluster(bar_afull, tcnt & 1);
                         tc_fence_after();
                         if (DBG) w_af += clock64() - t0;
                     }
@@ -1180,16 +1179,29 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_nuc_bx_ts(const __grid_consta
                     const uint32_t d0 = tmem + ab * TS_N;
                     const int2 sl = tab.slab[q];
                     uint32_t acc0 = 0u;   // the first block of a slab is stored untrimmed: it initialises all TS_N columns
-                    for (int t = 0; t < sl.y; t++) {
-                        const int4 bk = tab.blk[sl.x + t];
-                        const uint32_t kb = (uint32_t)bk.x & 0xffffu;
-                        const uint32_t bh = (uint32_t)bk.w + sbase;
-                        const uint32_t bl = bh + 2u * ((uint32_t)bk.w >> 16);
+                    auto issue = [&](int t0, int t1) {
+                        for (int t = t0; t < t1; t++) {
+                            const int4 bk = tab.blk[sl.x + t];
+                            const uint32_t kb = (uint32_t)bk.x & 0xffffu;
+                            const uint32_t bh = (uint32_t)bk.w + sbase;
+                            const uint32_t bl = bh + 2u * ((uint32_t)bk.w >> 16);
 #ifndef TS_NO_MMA
-                        tc_mma3_ts(d0 + (uint32_t)bk.y, tmem + (uint32_t)TS_ACOL + 8u * kb, a_lo0 + 16u * kb, bh, bl, desc_hi, (uint32_t)bk.z, acc0);
+                            tc_mma3_ts(d0 + (uint32_t)bk.y, tmem + (uint32_t)TS_ACOL + 8u * kb, a_lo0 + 16u * kb, bh, bl, desc_hi, (uint32_t)bk.z, acc0);
 #endif
-                        acc0 = 1u;
-                        if ((bk.x >> 16) & 1) tc_commit_e2_both(bar_afree);   // nothing issued after this block reads part 1 of this tile's operand
+                            acc0 = 1u;
+                            if ((bk.x >> 16) & 1) tc_commit_e2_both(bar_afree);   // nothing issued after this block reads part 1 of this tile's operand
+                        }
+                    };
+                    // the slab that holds the tile's first reader of part 2 is issued in two runs with the wait in between (a wait
+                    // INSIDE the block loop puts the loop back on per-thread registers)
+                    const int tsplit = (q == a.q_need2) ? a.t_need2 : sl.y;
+                    issue(0, tsplit);
+                    if (q == a.q_need2) {
+                        const long long t0 = DBG ? clock64() : 0;
+                        mbar_wait_cluster(bar_afull + 8, tcnt & 1);
+                        tc_fence_after();
+                        if (DBG) w_af += clock64() - t0;
+                        issue(tsplit, sl.y);
                     }
                     tc_commit_e2_both(bar_tfull + 8 * ab);
                     if (++ab == TS_NACC) {
@@ -1502,8 +1514,8 @@ int nb200_tc_setup(nb200_ctx *ctx)
         struct Blk { int q, kb, n_lo, n_t; };
         std::vector<Blk> blks;
         std::vector<int2> slabs;
+        std::vector<std::vector<Blk>> per_slab(n_sl);
         for (int q = 0; q < n_sl; q++) {
-            const int first = (int)blks.size();
             for (int kb = 0; kb < nkb; kb++) {
                 int r_lo = TS_N, r_hi = -1;
                 for (int n = 0; n < TS_N && q * TS_N + n < pl->NAp; n++)
@@ -1513,30 +1525,47 @@ int nb200_tc_setup(nb200_ctx *ctx)
                             r_hi = std::max(r_hi, n);
                         }
                 if (r_hi < 0) continue;
-                blks.push_back({q, kb, r_lo / 16 * 16, (r_hi + 16) / 16 * 16 - r_lo / 16 * 16});
+                per_slab[q].push_back({q, kb, r_lo / 16 * 16, (r_hi + 16) / 16 * 16 - r_lo / 16 * 16});
             }
-            if ((int)blks.size() == first) blks.push_back({q, 0, 0, TS_N});
+            if (per_slab[q].empty()) per_slab[q].push_back({q, 0, 0, TS_N});
+        }
+        // The hi operand is written in two parts (32-column = 4-K-block granularity).  Part 1 = the K blocks the LAST slab does
+        // not read: they are free a whole slab before the tile ends, so the next tile's part 1 is in place long before it
+        // starts; slab 0 contracts its part-1 blocks first, and part 2 -- free only when the tile is complete -- is written
+        // under them.  Without such a range (one slab, or a last slab that reads K block 0) part 1 = what slab 0 reads.
+        int kmax0 = 0, kmin_last = nkb;
+        for (const Blk &b : per_slab[0]) kmax0 = std::max(kmax0, b.kb);
+        for (const Blk &b : per_slab[n_sl - 1]) kmin_last = std::min(kmin_last, b.kb);
+        const bool early = n_sl >= 2 && kmin_last / 4 * 4 >= 4 && !(getenv("NB200_TC_EARLY") && atoi(getenv("NB200_TC_EARLY")) == 0);
+        const int kb_split = early ? kmin_last / 4 * 4 : std::min((kmax0 + 1 + 3) / 4 * 4, c_end / 8);
+        for (int q = 0; q < n_sl; q++) {
+            std::vector<Blk> &v = per_slab[q];
+            if (q == 0 && early)   // part-1 blocks first (K order is kept inside each group)
+                std::stable_partition(v.begin(), v.end(), [&](const Blk &b) { return b.kb < kb_split; });
             // the first MMA of a slab initialises every accumulator column, so it is issued untrimmed: take the block that is
             // (closest to) full width anyway instead of the first in K order, whose rows are a corner of the hexagon
             // (251 x 251: 320 of 4912 MMA columns per x-tile saved; 5.44 -> 5.27 ms in an interleaved A/B)
-            int widest = first;
-            for (int i = first; i < (int)blks.size(); i++)
-                if (blks[i].n_t > blks[widest].n_t) widest = i;
-            std::rotate(blks.begin() + first, blks.begin() + widest, blks.begin() + widest + 1);
-            blks[first].n_lo = 0;
-            blks[first].n_t = TS_N;
-            slabs.push_back(make_int2(first, (int)blks.size() - first));
+            size_t cand_end = v.size();
+            if (q == 0 && early) {
+                cand_end = 0;
+                while (cand_end < v.size() && v[cand_end].kb < kb_split) cand_end++;
+                if (cand_end == 0) cand_end = v.size();
+            }
+            size_t widest = 0;
+            for (size_t i = 1; i < cand_end; i++)
+                if (v[i].n_t > v[widest].n_t) widest = i;
+            std::rotate(v.begin(), v.begin() + widest, v.begin() + widest + 1);
+            v[0].n_lo = 0;
+            v[0].n_t = TS_N;
+            slabs.push_back(make_int2((int)blks.size(), (int)v.size()));
+            blks.insert(blks.end(), v.begin(), v.end());
         }
-        // part 1 of the hi operand = the K blocks slab 0 reads (rounded up to 32 columns = 4 K blocks)
-        int kmax0 = 0;
-        for (const Blk &b : blks)
-            if (b.q == 0) kmax0 = std::max(kmax0, b.kb);
-        const int kb_split = std::min((kmax0 + 1 + 3) / 4 * 4, c_end / 8);
-        int last_p1 = 0, q_need2 = -1;   // the last block (in issue order) that reads part 1; the first slab that reads part 2
+        int last_p1 = 0, first_p2 = -1;   // in issue order: the last block that reads part 1, the first that reads part 2
         for (size_t i = 0; i < blks.size(); i++) {
             if (blks[i].kb < kb_split) last_p1 = (int)i;
-            else if (q_need2 < 0) q_need2 = blks[i].q;
+            else if (first_p2 < 0) first_p2 = (int)i;
         }
+        if (first_p2 < 0) first_p2 = (int)blks.size() - 1;   // nobody reads part 2: its barrier phase is consumed before the last block
         size_t rank_bytes = 0;
         for (const Blk &b : blks) rank_bytes += (size_t)b.n_t * 32;   // half of the rows, hi + lo, 16 halves each
         std::vector<unsigned char> timg(2 * rank_bytes, 0);
@@ -1546,7 +1575,8 @@ int nb200_tc_setup(nb200_ctx *ctx)
             const Blk &b = blks[i];
             const int nh = b.n_t / 2;
             const uint32_t idesc = (1u << 4) | ((uint32_t)(b.n_t >> 3) << 17) | ((uint32_t)((TC_M * 2) >> 4) << 24);
-            tblk.push_back(make_int4(b.kb | (((int)i == last_p1 ? 1 : 0) << 16), b.n_lo, (int)idesc, (int)(off >> 4) | (nh << 16)));
+            const int flags = ((int)i == last_p1 ? 1 : 0) | ((int)i == first_p2 ? 4 : 0);
+            tblk.push_back(make_int4(b.kb | (flags << 16), b.n_lo, (int)idesc, (int)(off >> 4) | (nh << 16)));
             for (int rk = 0; rk < 2; rk++) {
                 __half *hi = reinterpret_cast<__half *>(timg.data() + (size_t)rk * rank_bytes + off);
                 __half *lo = hi + (size_t)nh * 16;
@@ -1570,7 +1600,8 @@ int nb200_tc_setup(nb200_ctx *ctx)
             pl->ts_rank_bytes = (int)rank_bytes;
             pl->ts_c_end = c_end;
             pl->ts_c_split = kb_split * 8;
-            pl->ts_q_need2 = q_need2 >= 0 ? q_need2 : n_sl - 1;   // every phase of every barrier has its wait
+            pl->ts_q_need2 = blks[first_p2].q;
+            pl->ts_t_need2 = first_p2 - slabs[blks[first_p2].q].x;
             NB_CUDA(ctx, pl->ts_img.reserve(timg.size()));
             NB_CUDA(ctx, cudaMemcpy(pl->ts_img.p, timg.data(), timg.size(), cudaMemcpyHostToDevice));
             pl->ts_blk = tblk;
@@ -1662,6 +1693,7 @@ int nb200_nuc_bx_tc(nb200_ctx *ctx, nb200_dbatch *b)
         t.c_split = pl->ts_c_split;
         t.c_end = pl->ts_c_end;
         t.q_need2 = pl->ts_q_need2;
+        t.t_need2 = pl->ts_t_need2;
         // the E window must also cover the a taps of the last slab (TS_N granularity) and the rows the hi operand is expanded from
         const int gmax = std::max(std::max(TC_TX - 1 + pl->A0 + pl->ts_slabs * TS_N - 1, TC_TX + pl->B0 + std::max(pl->NBp, 2 * pl->ts_c_end) + 8), TC_TX - 1 + r.v_w);
         t.span = std::max(pl->span, gmax - pl->gmin + 1);
