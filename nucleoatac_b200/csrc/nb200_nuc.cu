@@ -230,6 +230,7 @@ __global__ void __launch_bounds__(PK_THREADS_N) k_nuc_peaks(NucPeakArgs a)
 {
     __shared__ double red_d[32];
     __shared__ int red_i[32];
+    __shared__ int s_cnt[32 * (PK_THREADS_N / 32)];
     __shared__ int s_base, s_flag;
     const int c = blockIdx.x;
     const int64_t oo = a.out_off[c];
@@ -241,11 +242,28 @@ __global__ void __launch_bounds__(PK_THREADS_N) k_nuc_peaks(NucPeakArgs a)
     const int tid = threadIdx.x;
     double mn = CUDART_INF;
     int nnan = 0;
-    for (int x = tid; x < L; x += blockDim.x) {
-        double v = a.norm[oo + x] + a.smooth[oo + x];  // NucleosomeCalling.py:297
-        cb[x] = v;
-        if (v != v) nnan++;
-        else mn = fmin(mn, v);
+    {   // four positions in flight per thread: the pass is load latency
+        const double *__restrict__ nr = a.norm + oo, *__restrict__ sr = a.smooth + oo;
+        double *__restrict__ cw = cb;
+        const int stride = (int)blockDim.x;
+        int x = tid;
+        for (; x + 3 * stride < L; x += 4 * stride) {
+            double v4[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) v4[u] = nr[x + u * stride] + sr[x + u * stride];  // NucleosomeCalling.py:297
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                cw[x + u * stride] = v4[u];
+                if (v4[u] != v4[u]) nnan++;
+                else mn = fmin(mn, v4[u]);
+            }
+        }
+        for (; x < L; x += stride) {
+            const double v = nr[x] + sr[x];
+            cw[x] = v;
+            if (v != v) nnan++;
+            else mn = fmin(mn, v);
+        }
     }
     for (int o = 16; o > 0; o >>= 1) {
         mn = fmin(mn, __shfl_xor_sync(NB_FULL, mn, o));
@@ -272,26 +290,23 @@ __global__ void __launch_bounds__(PK_THREADS_N) k_nuc_peaks(NucPeakArgs a)
                 if (cb[x] != cb[x]) cb[x] = mn;
         __syncthreads();
         const int lo = max(0, a.boundary), hi = L - a.boundary;
-        for (int x0 = 0; x0 < L; x0 += blockDim.x) {
-            const int x = x0 + tid;
-            int flag = 0;
-            double v = 0.0;
-            if (x >= lo && x < hi) {
-                v = cb[x];
+        block_compact_ordered(
+            L, s_cnt, red_i, &s_base,
+            [&](int x) {
+                if (x < lo || x >= hi) return false;
+                const double v = cb[x];
                 const double j0 = v * (1.0 + a.jitter[x]);
-                flag = (v >= a.min_signal);
+                bool flag = (v >= a.min_signal);
                 for (int d = 1; d <= a.order && flag; d++) {  // argrelmax(order), mode='clip'
                     const int xl = max(x - d, 0), xr = min(x + d, L - 1);
                     flag = (j0 > cb[xl] * (1.0 + a.jitter[xl])) && (j0 > cb[xr] * (1.0 + a.jitter[xr]));
                 }
-            }
-            int slot = block_compact_slot(flag, &s_base, red_i);
-            if (flag) {
+                return flag;
+            },
+            [&](int x, int slot) {
                 cpos[slot] = x;
-                cval[slot] = v;
-            }
-        }
-        __syncthreads();
+                cval[slot] = cb[x];
+            });
         m = s_base;
         block_nms(cpos, cval, cst, m, a.sep, &s_flag);
     }

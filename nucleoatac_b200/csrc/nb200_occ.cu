@@ -1281,6 +1281,7 @@ struct OccPeakArgs {
     int32_t *peak_count, *peak_pos;
     double *peak_occ, *peak_lower, *peak_upper, *peak_reads, *nuc_dist;
     int upper, flank, sep, csc_pad;
+    int n_hist;                      // insert-size histograms in shared memory (getNucDist: that many peaks per round)
     double min_occ;
 };
 
@@ -1289,9 +1290,11 @@ __global__ void __launch_bounds__(PK_THREADS) k_occ_peaks(OccPeakArgs a)
 {
     extern __shared__ unsigned char sm_pk[];
     double *s_nd = reinterpret_cast<double *>(sm_pk);          // [upper]
-    int *s_hist = reinterpret_cast<int *>(s_nd + a.upper);      // [upper]
+    int *s_hist = reinterpret_cast<int *>(s_nd + a.upper);      // [n_hist][upper]
     __shared__ double red_d[32];
     __shared__ int red_i[32];
+    __shared__ int s_cnt[32 * (PK_THREADS / 32)];
+    __shared__ double s_tot[PK_THREADS / 32];
     __shared__ int s_base, s_flag;
     const int c = blockIdx.x;
     const int64_t oo = a.out_off[c];
@@ -1303,16 +1306,43 @@ __global__ void __launch_bounds__(PK_THREADS) k_occ_peaks(OccPeakArgs a)
     double *cval = a.sc_val + oo;
     unsigned char *cst = a.sc_state + oo;
     const int tid = threadIdx.x;
-    // coverage: flat window over fragment centres = difference of the CSC prefix (tracks.py:209-222)
-    for (int x = tid; x < L; x += blockDim.x)
-        cov[x] = (double)(cp[x + a.flank + 1 + a.csc_pad] - cp[x - a.flank + a.csc_pad]);
-    // NaN -> min (utils.py:86-91)
+#ifdef PK_TIMING
+    long long pk_t[8];
+    pk_t[0] = clock64();
+#endif
+    // coverage: flat window over fragment centres = difference of the CSC prefix (tracks.py:209-222); in the same pass the
+    // minimum and the NaN count for NaN -> min (utils.py:86-91).  One loop, four positions in flight per thread: the two
+    // separate loops were a quarter of the kernel, all of it load latency.
     double mn = CUDART_INF;
     int nnan = 0;
-    for (int x = tid; x < L; x += blockDim.x) {
-        double v = sv[x];
-        if (v != v) nnan++;
-        else mn = fmin(mn, v);
+    {
+        const int32_t *__restrict__ cpr = cp + a.csc_pad;
+        const double *__restrict__ svr = sv;
+        double *__restrict__ covw = cov;
+        const int stride = (int)blockDim.x;
+        int x = tid;
+        for (; x + 3 * stride < L; x += 4 * stride) {
+            int hi4[4], lo4[4];
+            double v4[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                hi4[u] = cpr[x + u * stride + a.flank + 1];
+                lo4[u] = cpr[x + u * stride - a.flank];
+                v4[u] = svr[x + u * stride];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                covw[x + u * stride] = (double)(hi4[u] - lo4[u]);
+                if (v4[u] != v4[u]) nnan++;
+                else mn = fmin(mn, v4[u]);
+            }
+        }
+        for (; x < L; x += stride) {
+            covw[x] = (double)(cpr[x + a.flank + 1] - cpr[x - a.flank]);
+            const double v = svr[x];
+            if (v != v) nnan++;
+            else mn = fmin(mn, v);
+        }
     }
     for (int o = 16; o > 0; o >>= 1) {
         mn = fmin(mn, __shfl_xor_sync(NB_FULL, mn, o));
@@ -1333,6 +1363,9 @@ __global__ void __launch_bounds__(PK_THREADS) k_occ_peaks(OccPeakArgs a)
     for (int i = tid; i < a.upper; i += blockDim.x) s_nd[i] = 0.0;
     if (tid == 0) s_base = 0;
     __syncthreads();
+#ifdef PK_TIMING
+    pk_t[1] = clock64();
+#endif
     int m = 0;
     if (nnan < L) {
         if (nnan > 0)
@@ -1342,28 +1375,30 @@ __global__ void __launch_bounds__(PK_THREADS) k_occ_peaks(OccPeakArgs a)
         // strict local maxima of sig*(1+jitter), order 1 (argrelmax, clip mode), utils.py:94-100
         const int boundary = a.sep / 2;
         const int lo = max(1, boundary), hi = min(L - 1, L - boundary);
-        for (int x0 = 0; x0 < L; x0 += blockDim.x) {
-            const int x = x0 + tid;
-            int flag = 0;
-            double v = 0.0;
-            if (x >= lo && x < hi) {
-                v = sv[x];
-                double j0 = v * (1.0 + a.jitter[x]);
-                double jl = sv[x - 1] * (1.0 + a.jitter[x - 1]);
-                double jr = sv[x + 1] * (1.0 + a.jitter[x + 1]);
-                flag = (j0 > jl) && (j0 > jr) && (v >= a.min_occ);
-            }
-            int slot = block_compact_slot(flag, &s_base, red_i);
-            if (flag) {
+        block_compact_ordered(
+            L, s_cnt, red_i, &s_base,
+            [&](int x) {
+                if (x < lo || x >= hi) return false;
+                const double v = sv[x];
+                const double j0 = v * (1.0 + a.jitter[x]);
+                const double jl = sv[x - 1] * (1.0 + a.jitter[x - 1]);
+                const double jr = sv[x + 1] * (1.0 + a.jitter[x + 1]);
+                return (j0 > jl) && (j0 > jr) && (v >= a.min_occ);
+            },
+            [&](int x, int slot) {
                 cpos[slot] = x;
-                cval[slot] = v;
-            }
-        }
-        __syncthreads();
+                cval[slot] = sv[x];
+            });
         m = s_base;
+#ifdef PK_TIMING
+        pk_t[2] = clock64();
+#endif
         block_nms(cpos, cval, cst, m, a.sep, &s_flag);
     }
     __syncthreads();
+#ifdef PK_TIMING
+    pk_t[3] = clock64();
+#endif
     // OccPeak filter (Occupancy.py:228-231) and ordered output
     if (tid == 0) s_base = 0;
     __syncthreads();
@@ -1387,21 +1422,41 @@ __global__ void __launch_bounds__(PK_THREADS) k_occ_peaks(OccPeakArgs a)
     }
     __syncthreads();
     const int npk = min(s_base, cap);
+#ifdef PK_TIMING
+    pk_t[4] = clock64();
+#endif
     if (tid == 0) a.peak_count[c] = (s_base <= cap) ? s_base : -s_base;  // negative: capacity exceeded
     // getNucDist, Occupancy.py:232-240: sum over peaks of the window's insert-size histogram / its total
+    // n_hist peaks per round: a warp builds the histogram of one peak's window (a few dozen fragments), then the sizes are
+    // accumulated peak by peak in the reference's order (a whole-block round per peak was half of this kernel's time)
     const int2 *en = a.ent + a.frag_off[c];
-    for (int k = 0; k < npk; k++) {
-        const int p = a.peak_pos[po + k] - a.start[c];
-        const int e0 = cp[p - a.flank + a.csc_pad], e1 = cp[p + a.flank + 1 + a.csc_pad];
-        for (int i = tid; i < a.upper; i += blockDim.x) s_hist[i] = 0;
+    const int wid = tid >> 5, lane = tid & 31, nwarp = (int)(blockDim.x >> 5);
+    for (int k0 = 0; k0 < npk; k0 += a.n_hist) {
+        const int nk = min(a.n_hist, npk - k0);
+        for (int kk = wid; kk < nk; kk += nwarp) {
+            int *h = s_hist + (size_t)kk * a.upper;
+            for (int i = lane; i < a.upper; i += 32) h[i] = 0;
+            __syncwarp();
+            const int p = a.peak_pos[po + k0 + kk] - a.start[c];
+            const int e0 = cp[p - a.flank + a.csc_pad], e1 = cp[p + a.flank + 1 + a.csc_pad];
+            for (int e = e0 + lane; e < e1; e += 32) atomicAdd(&h[en[e].y], 1);
+            if (lane == 0) s_tot[kk] = (double)(e1 - e0);
+        }
         __syncthreads();
-        for (int e = e0 + tid; e < e1; e += blockDim.x) atomicAdd(&s_hist[en[e].y], 1);
-        __syncthreads();
-        const double tot = (double)(e1 - e0);
-        for (int i = tid; i < a.upper; i += blockDim.x) s_nd[i] += (double)s_hist[i] / tot;
+        for (int i = tid; i < a.upper; i += blockDim.x) {
+            double acc = s_nd[i];
+            for (int kk = 0; kk < nk; kk++) acc += (double)s_hist[(size_t)kk * a.upper + i] / s_tot[kk];
+            s_nd[i] = acc;
+        }
         __syncthreads();
     }
     for (int i = tid; i < a.upper; i += blockDim.x) a.nuc_dist[(int64_t)c * a.upper + i] = s_nd[i];
+#ifdef PK_TIMING
+    pk_t[5] = clock64();
+    if (tid == 0 && (c % 500) == 7)
+        printf("k_occ_peaks chunk %d: L %d m %d npk %d | cov+nan %lld maxima %lld nms %lld filter %lld nuc_dist %lld (clk)\n", c, L, m, npk,
+               pk_t[1] - pk_t[0], pk_t[2] - pk_t[1], pk_t[3] - pk_t[2], pk_t[4] - pk_t[3], pk_t[5] - pk_t[4]);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1645,7 +1700,8 @@ int nb200_occ_run(nb200_ctx *ctx, nb200_dbatch *b)
         a.sep = p.sep;
         a.csc_pad = b->csc_pad;
         a.min_occ = p.min_occ;
-        size_t smem = (size_t)p.upper * 12;
+        a.n_hist = std::max(1, std::min(PK_THREADS / 32, (int)((40 * 1024 - (size_t)p.upper * 8) / ((size_t)p.upper * 4))));
+        size_t smem = (size_t)p.upper * 8 + (size_t)a.n_hist * p.upper * 4;
         ProfScope ps(ctx, b->stream, "k_occ_peaks");
         k_occ_peaks<<<n, PK_THREADS, smem, b->stream>>>(a);
         NB_LAUNCH_CHECK(ctx);
