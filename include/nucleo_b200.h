@@ -266,6 +266,18 @@ int nb200_bam_fetch_many(const char *path, int32_t n_regions, const uint64_t *vo
                          int32_t **tlen, char *err, int errcap);
 void nb200_free(void *p);
 
+/* ---- developer / test aid: the block plan of the tcgen05 background kernel, computed on the host --------------- */
+/* What nb200_set_vmat + nb200_set_fragment_sizes would plan for BiasTrack.calculateBackgroundSignal
+ * (nucleoatac/NucleosomeCalling.py:60-63) with this VMat (rows = insert sizes [lower, upper), `cols` columns) and
+ * fragment-size distribution (n_sizes >= upper values): stats[16] = {eligible for the tensor-memory kernel, slabs, K16
+ * blocks, tensor-memory operand columns of part 1, columns in all, slab and position of the first block that reads part 2,
+ * bytes of one CTA's image of G, NA, NB, MMA columns per x-tile and precision pass, non-zero (row, K block) pairs of G,
+ * non-zeros of G outside every block (must be 0), size-1 term present, 0, 0}; blocks[4 i ..] = the table entry of block i
+ * ({K block | flags << 16, first row, instruction descriptor, image offset / 16 | rows per CTA << 16}; at most max_blocks
+ * entries are copied, blocks may be NULL).  No context, no device: the CPU tests check the plan's invariants over shapes. */
+int nb200_tc_plan_describe(const double *vmat, int32_t lower, int32_t upper, int32_t cols, const double *sizes, int32_t n_sizes,
+                           int32_t *stats, int32_t *blocks, int32_t max_blocks);
+
 /* ---- multi-GPU end-of-run reductions (NCCL over NVLink) ----------------------------------- */
 /* fragment-size histogram (fragments.pyx:122-145), nuc_dist (run_occ.py:117-121), V-plot sum
  * (pyatac/make_vplot.py:70-73).  unique_id is the 128-byte ncclUniqueId from rank 0. */

@@ -1361,14 +1361,18 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_nuc_bx_ts(const __grid_consta
 // ---------------------------------------------------------------------------------------------
 // host side: G images + stage table (once per VMat / fragment-size change)
 // ---------------------------------------------------------------------------------------------
-int nb200_tc_setup(nb200_ctx *ctx)
+// ---------------------------------------------------------------------------------------------
+// Host-only planning (no CUDA calls: also reachable through nb200_tc_plan_describe for the CPU tests)
+// ---------------------------------------------------------------------------------------------
+// Geometry of the bilinear form and the matrix G of a VMat x fragment-size distribution.  false: nothing for the tensor core
+// (a VMat with only the single-tap size 1, or a zero / non-finite G).
+struct TcGeom {
+    int A0 = 0, B0 = 0, NA = 0, NB = 0, NAp = 0, NBp = 0, has_row1 = 0, gmin = 0, span = 0, sG = 0;
+    double sc = 1.0;
+    std::vector<double> G;   // [NAp][NBp], unscaled
+};
+static bool tc_build_geometry(const double *vmat, int lv, int uv, int W, int w, const double *sizes, TcGeom &g)
 {
-    RunConst &r = ctx->rc;
-    TcPlan *pl = plan_of(ctx, true);
-    if (!pl) return NB200_OK;
-    pl->ok = false;
-    if (!r.have_vmat || !r.have_sizes) return NB200_OK;
-    const int lv = r.v_lower, uv = r.v_upper, W = r.v_cols, w = r.v_w, R = r.v_rows;
     auto fd2 = [](int v) { return v >> 1; };  // floor division by 2
     // tap offsets relative to the output position: a = (k-w) - (i-1)//2, b = (k-w) + i//2   (i != 1)
     int amin = INT32_MAX, amax = INT32_MIN, bmin = INT32_MAX, bmax = INT32_MIN;
@@ -1379,40 +1383,195 @@ int nb200_tc_setup(nb200_ctx *ctx)
         bmin = std::min(bmin, -w + fd2(i));
         bmax = std::max(bmax, w + fd2(i));
     }
-    if (amin > amax) return NB200_OK;  // VMat with only size 1: nothing for the tensor core
-    pl->A0 = amin;
-    pl->B0 = bmin;
-    pl->NA = amax - amin + 1;
-    pl->NB = bmax - bmin + 1;
-    pl->NAp = (pl->NA + TC_N - 1) / TC_N * TC_N;
-    pl->NBp = (pl->NB + 15) / 16 * 16;
-    pl->n_achunks = pl->NAp / TC_N;
-    pl->has_row1 = 0;  // size-1 row: a linear term, only paid for when f_1 * V[1,:] is not identically zero
+    if (amin > amax) return false;
+    g.A0 = amin;
+    g.B0 = bmin;
+    g.NA = amax - amin + 1;
+    g.NB = bmax - bmin + 1;
+    g.NAp = (g.NA + TC_N - 1) / TC_N * TC_N;
+    g.NBp = (g.NB + 15) / 16 * 16;
+    g.has_row1 = 0;  // size-1 row: a linear term, only paid for when f_1 * V[1,:] is not identically zero
     if (lv <= 1 && 1 < uv)
         for (int k = 0; k < W; k++)
-            if (r.h_sizes[1] * r.h_vmat[(size_t)(1 - lv) * W + k] != 0.0) pl->has_row1 = 1;
+            if (sizes[1] * vmat[(size_t)(1 - lv) * W + k] != 0.0) g.has_row1 = 1;
     // shared E window: genomic offsets [gmin, gmax] relative to the CTA's first output
-    int gmin = std::min(std::min(amin, bmin), -w);
-    int gmax = std::max(std::max(TC_TX - 1 + pl->A0 + pl->NAp - 1, TC_TX + pl->B0 + pl->NBp + 8), TC_TX - 1 + w);
-    pl->gmin = gmin;
-    pl->span = gmax - gmin + 1;
-    std::vector<double> G((size_t)pl->NAp * pl->NBp, 0.0);
+    const int gmin = std::min(std::min(amin, bmin), -w);
+    const int gmax = std::max(std::max(TC_TX - 1 + g.A0 + g.NAp - 1, TC_TX + g.B0 + g.NBp + 8), TC_TX - 1 + w);
+    g.gmin = gmin;
+    g.span = gmax - gmin + 1;
+    g.G.assign((size_t)g.NAp * g.NBp, 0.0);
     double gmaxv = 0.0;
     for (int i = lv; i < uv; i++) {
         if (i == 1) continue;
-        const double f = r.h_sizes[i];
+        const double f = sizes[i];
         for (int k = 0; k < W; k++) {
-            const int ia = (k - w) - fd2(i - 1) - pl->A0, ib = (k - w) + fd2(i) - pl->B0;
-            const double g = f * r.h_vmat[(size_t)(i - lv) * W + k];
-            G[(size_t)ia * pl->NBp + ib] += g;
-            gmaxv = std::max(gmaxv, fabs(g));
+            const int ia = (k - w) - fd2(i - 1) - g.A0, ib = (k - w) + fd2(i) - g.B0;
+            const double v = f * vmat[(size_t)(i - lv) * W + k];
+            g.G[(size_t)ia * g.NBp + ib] += v;
+            gmaxv = std::max(gmaxv, fabs(v));
         }
     }
-    if (!(gmaxv > 0.0) || !std::isfinite(gmaxv)) return NB200_OK;
+    if (!(gmaxv > 0.0) || !std::isfinite(gmaxv)) return false;
     int ex;
     frexp(32768.0 / gmaxv, &ex);
-    pl->sG = ex - 1;
-    const double sc = ldexp(1.0, pl->sG);
+    g.sG = ex - 1;
+    g.sc = ldexp(1.0, g.sG);
+    return true;
+}
+
+struct TsHostPlan {
+    bool ok = false;
+    int n_slabs = 0, n_blocks = 0, rank_bytes = 0, c_split = 0, c_end = 0, q_need2 = -1, t_need2 = 0;
+    long long mma_cols = 0, uncovered = 0, nonzero_cols = 0;   // MMA columns issued per x-tile and precision pass; non-zeros of G outside every block; non-zero (row, K block) pairs
+    std::vector<int4> blk;
+    std::vector<int2> slab;
+    std::vector<unsigned char> img;   // [rank][blocks]: hi image then lo image of that CTA's half of every block
+};
+
+// Second plan (k_nuc_bx_ts): slabs of TS_N rows of G (NAp x NBp, row-major, scaled by `sc` in the images), all block images
+// resident, one contiguous region per CTA of the pair.
+static void ts_build_plan(const std::vector<double> &G, int NA, int NAp, int NBp, double sc, TsHostPlan &out)
+{
+    out.ok = false;
+    const int nkb = NBp / 16;
+    const int n_sl = (NA + TS_N - 1) / TS_N;
+    const int c_end = (NBp / 2 + 31) / 32 * 32;
+    struct Blk { int q, kb, n_lo, n_t; };
+    std::vector<Blk> blks;
+    std::vector<int2> &slabs = out.slab;
+    slabs.clear();
+    std::vector<std::vector<Blk>> per_slab(n_sl);
+    for (int q = 0; q < n_sl; q++) {
+        for (int kb = 0; kb < nkb; kb++) {
+            int r_lo = TS_N, r_hi = -1;
+            for (int n = 0; n < TS_N && q * TS_N + n < NAp; n++)
+                for (int k = 0; k < 16; k++)
+                    if (G[(size_t)(q * TS_N + n) * NBp + kb * 16 + k] != 0.0) {
+                        r_lo = std::min(r_lo, n);
+                        r_hi = std::max(r_hi, n);
+                    }
+            if (r_hi < 0) continue;
+            per_slab[q].push_back({q, kb, r_lo / 16 * 16, (r_hi + 16) / 16 * 16 - r_lo / 16 * 16});
+        }
+        if (per_slab[q].empty()) per_slab[q].push_back({q, 0, 0, TS_N});
+    }
+    // The hi operand is written in two parts (32-column = 4-K-block granularity).  Part 1 = the K blocks the LAST slab does
+    // not read: they are free a whole slab before the tile ends, so the next tile's part 1 is in place long before it
+    // starts; slab 0 contracts its part-1 blocks first, and part 2 -- free only when the tile is complete -- is written
+    // under them.  Without such a range (one slab, or a last slab that reads K block 0) part 1 = what slab 0 reads.
+    int kmax0 = 0, kmin_last = nkb;
+    for (const Blk &b : per_slab[0]) kmax0 = std::max(kmax0, b.kb);
+    for (const Blk &b : per_slab[n_sl - 1]) kmin_last = std::min(kmin_last, b.kb);
+    const bool early = n_sl >= 2 && kmin_last / 4 * 4 >= 4 && !(getenv("NB200_TC_EARLY") && atoi(getenv("NB200_TC_EARLY")) == 0);
+    const int kb_split = early ? kmin_last / 4 * 4 : std::min((kmax0 + 1 + 3) / 4 * 4, c_end / 8);
+    for (int q = 0; q < n_sl; q++) {
+        std::vector<Blk> &v = per_slab[q];
+        if (q == 0 && early)   // part-1 blocks first (K order is kept inside each group)
+            std::stable_partition(v.begin(), v.end(), [&](const Blk &b) { return b.kb < kb_split; });
+        // the first MMA of a slab initialises every accumulator column, so it is issued untrimmed: take the block that is
+        // (closest to) full width anyway instead of the first in K order, whose rows are a corner of the hexagon
+        // (251 x 251: 320 of 4912 MMA columns per x-tile saved; 5.44 -> 5.27 ms in an interleaved A/B)
+        size_t cand_end = v.size();
+        if (q == 0 && early) {
+            cand_end = 0;
+            while (cand_end < v.size() && v[cand_end].kb < kb_split) cand_end++;
+            if (cand_end == 0) cand_end = v.size();
+        }
+        size_t widest = 0;
+        for (size_t i = 1; i < cand_end; i++)
+            if (v[i].n_t > v[widest].n_t) widest = i;
+        std::rotate(v.begin(), v.begin() + widest, v.begin() + widest + 1);
+        v[0].n_lo = 0;
+        v[0].n_t = TS_N;
+        slabs.push_back(make_int2((int)blks.size(), (int)v.size()));
+        blks.insert(blks.end(), v.begin(), v.end());
+    }
+    int last_p1 = 0, first_p2 = -1;   // in issue order: the last block that reads part 1, the first that reads part 2
+    for (size_t i = 0; i < blks.size(); i++) {
+        if (blks[i].kb < kb_split) last_p1 = (int)i;
+        else if (first_p2 < 0) first_p2 = (int)i;
+    }
+    if (first_p2 < 0) first_p2 = (int)blks.size() - 1;   // nobody reads part 2: its barrier phase is consumed before the last block
+    size_t rank_bytes = 0;
+    for (const Blk &b : blks) rank_bytes += (size_t)b.n_t * 32;   // half of the rows, hi + lo, 16 halves each
+    std::vector<unsigned char> &timg = out.img;
+    timg.assign(2 * rank_bytes, 0);
+    std::vector<int4> &tblk = out.blk;
+    tblk.clear();
+    size_t off = 0;
+    for (size_t i = 0; i < blks.size(); i++) {
+        const Blk &b = blks[i];
+        const int nh = b.n_t / 2;
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(b.n_t >> 3) << 17) | ((uint32_t)((TC_M * 2) >> 4) << 24);
+        const int flags = ((int)i == last_p1 ? 1 : 0) | ((int)i == first_p2 ? 4 : 0);
+        tblk.push_back(make_int4(b.kb | (flags << 16), b.n_lo, (int)idesc, (int)(off >> 4) | (nh << 16)));
+        for (int rk = 0; rk < 2; rk++) {
+            __half *hi = reinterpret_cast<__half *>(timg.data() + (size_t)rk * rank_bytes + off);
+            __half *lo = hi + (size_t)nh * 16;
+            for (int n = 0; n < nh; n++)
+                for (int k = 0; k < 16; k++) {
+                    const int row = b.q * TS_N + b.n_lo + rk * nh + n;
+                    const double g = (row < NAp ? G[(size_t)row * NBp + b.kb * 16 + k] : 0.0) * sc;
+                    const float gf = (float)g;
+                    const __half h = __float2half_rn(gf);
+                    const __half l = __float2half_rn(gf - __half2float(h));
+                    const size_t o = ((size_t)(k / 8) * (nh / 8) + n / 8) * 64 + (n % 8) * 8 + (k % 8);
+                    hi[o] = h;
+                    lo[o] = l;
+                }
+        }
+        off += (size_t)nh * 64;
+    }
+    out.n_slabs = n_sl;
+    out.n_blocks = (int)tblk.size();
+    out.rank_bytes = (int)rank_bytes;
+    out.c_end = c_end;
+    out.c_split = kb_split * 8;
+    out.q_need2 = blks[first_p2].q;
+    out.t_need2 = first_p2 - slabs[blks[first_p2].q].x;
+    out.mma_cols = 0;
+    for (const Blk &b : blks) out.mma_cols += b.n_t;
+    // self-check: every non-zero of G lies inside a block of its slab
+    std::vector<char> covered((size_t)NAp * nkb, 0);
+    for (const Blk &b : blks)
+        for (int n = 0; n < b.n_t; n++)
+            if (b.q * TS_N + b.n_lo + n < NAp) covered[(size_t)(b.q * TS_N + b.n_lo + n) * nkb + b.kb] = 1;
+    out.uncovered = out.nonzero_cols = 0;
+    for (int row = 0; row < NAp; row++)
+        for (int kb = 0; kb < nkb; kb++) {
+            bool nz = false;
+            for (int k = 0; k < 16; k++) nz = nz || G[(size_t)row * NBp + kb * 16 + k] != 0.0;
+            if (nz) {
+                out.nonzero_cols++;
+                if (!covered[(size_t)row * nkb + kb]) out.uncovered++;
+            }
+        }
+    out.ok = c_end <= TS_MAXCOL && rank_bytes < (size_t)200 * 1024 && tblk.size() <= TS_MAX_BLOCKS && slabs.size() <= TS_MAX_SLABS && out.uncovered == 0;
+}
+
+int nb200_tc_setup(nb200_ctx *ctx)
+{
+    RunConst &r = ctx->rc;
+    TcPlan *pl = plan_of(ctx, true);
+    if (!pl) return NB200_OK;
+    pl->ok = false;
+    if (!r.have_vmat || !r.have_sizes) return NB200_OK;
+    const int lv = r.v_lower, uv = r.v_upper, W = r.v_cols, w = r.v_w;
+    TcGeom geo;
+    if (!tc_build_geometry(r.h_vmat.data(), lv, uv, W, w, r.h_sizes.data(), geo)) return NB200_OK;   // nothing for the tensor core
+    pl->A0 = geo.A0;
+    pl->B0 = geo.B0;
+    pl->NA = geo.NA;
+    pl->NB = geo.NB;
+    pl->NAp = geo.NAp;
+    pl->NBp = geo.NBp;
+    pl->n_achunks = pl->NAp / TC_N;
+    pl->has_row1 = geo.has_row1;
+    pl->gmin = geo.gmin;
+    pl->span = geo.span;
+    pl->sG = geo.sG;
+    const std::vector<double> &G = geo.G;
+    const double sc = geo.sc;
     // Per slab (TC_N rows of G = a taps) the K16 blocks that hold a non-zero, each trimmed to the 16-row granules that are
     // non-zero in it; the first block of a slab stays untrimmed (its MMA initialises every accumulator column).  Blocks
     // are packed into stages of at most TC_SLOT_BYTES.  Block image (hi, then lo): canonical K-major no-swizzle core
@@ -1509,103 +1668,20 @@ int nb200_tc_setup(nb200_ctx *ctx)
     // ---- second plan (k_nuc_bx_ts): slabs of TS_N rows, all block images resident, one contiguous region per CTA of the pair
     pl->ts_ok = false;
     {
-        const int n_sl = (pl->NA + TS_N - 1) / TS_N;
-        const int c_end = (pl->NBp / 2 + 31) / 32 * 32;
-        struct Blk { int q, kb, n_lo, n_t; };
-        std::vector<Blk> blks;
-        std::vector<int2> slabs;
-        std::vector<std::vector<Blk>> per_slab(n_sl);
-        for (int q = 0; q < n_sl; q++) {
-            for (int kb = 0; kb < nkb; kb++) {
-                int r_lo = TS_N, r_hi = -1;
-                for (int n = 0; n < TS_N && q * TS_N + n < pl->NAp; n++)
-                    for (int k = 0; k < 16; k++)
-                        if (G[(size_t)(q * TS_N + n) * pl->NBp + kb * 16 + k] != 0.0) {
-                            r_lo = std::min(r_lo, n);
-                            r_hi = std::max(r_hi, n);
-                        }
-                if (r_hi < 0) continue;
-                per_slab[q].push_back({q, kb, r_lo / 16 * 16, (r_hi + 16) / 16 * 16 - r_lo / 16 * 16});
-            }
-            if (per_slab[q].empty()) per_slab[q].push_back({q, 0, 0, TS_N});
-        }
-        // The hi operand is written in two parts (32-column = 4-K-block granularity).  Part 1 = the K blocks the LAST slab does
-        // not read: they are free a whole slab before the tile ends, so the next tile's part 1 is in place long before it
-        // starts; slab 0 contracts its part-1 blocks first, and part 2 -- free only when the tile is complete -- is written
-        // under them.  Without such a range (one slab, or a last slab that reads K block 0) part 1 = what slab 0 reads.
-        int kmax0 = 0, kmin_last = nkb;
-        for (const Blk &b : per_slab[0]) kmax0 = std::max(kmax0, b.kb);
-        for (const Blk &b : per_slab[n_sl - 1]) kmin_last = std::min(kmin_last, b.kb);
-        const bool early = n_sl >= 2 && kmin_last / 4 * 4 >= 4 && !(getenv("NB200_TC_EARLY") && atoi(getenv("NB200_TC_EARLY")) == 0);
-        const int kb_split = early ? kmin_last / 4 * 4 : std::min((kmax0 + 1 + 3) / 4 * 4, c_end / 8);
-        for (int q = 0; q < n_sl; q++) {
-            std::vector<Blk> &v = per_slab[q];
-            if (q == 0 && early)   // part-1 blocks first (K order is kept inside each group)
-                std::stable_partition(v.begin(), v.end(), [&](const Blk &b) { return b.kb < kb_split; });
-            // the first MMA of a slab initialises every accumulator column, so it is issued untrimmed: take the block that is
-            // (closest to) full width anyway instead of the first in K order, whose rows are a corner of the hexagon
-            // (251 x 251: 320 of 4912 MMA columns per x-tile saved; 5.44 -> 5.27 ms in an interleaved A/B)
-            size_t cand_end = v.size();
-            if (q == 0 && early) {
-                cand_end = 0;
-                while (cand_end < v.size() && v[cand_end].kb < kb_split) cand_end++;
-                if (cand_end == 0) cand_end = v.size();
-            }
-            size_t widest = 0;
-            for (size_t i = 1; i < cand_end; i++)
-                if (v[i].n_t > v[widest].n_t) widest = i;
-            std::rotate(v.begin(), v.begin() + widest, v.begin() + widest + 1);
-            v[0].n_lo = 0;
-            v[0].n_t = TS_N;
-            slabs.push_back(make_int2((int)blks.size(), (int)v.size()));
-            blks.insert(blks.end(), v.begin(), v.end());
-        }
-        int last_p1 = 0, first_p2 = -1;   // in issue order: the last block that reads part 1, the first that reads part 2
-        for (size_t i = 0; i < blks.size(); i++) {
-            if (blks[i].kb < kb_split) last_p1 = (int)i;
-            else if (first_p2 < 0) first_p2 = (int)i;
-        }
-        if (first_p2 < 0) first_p2 = (int)blks.size() - 1;   // nobody reads part 2: its barrier phase is consumed before the last block
-        size_t rank_bytes = 0;
-        for (const Blk &b : blks) rank_bytes += (size_t)b.n_t * 32;   // half of the rows, hi + lo, 16 halves each
-        std::vector<unsigned char> timg(2 * rank_bytes, 0);
-        std::vector<int4> tblk;
-        size_t off = 0;
-        for (size_t i = 0; i < blks.size(); i++) {
-            const Blk &b = blks[i];
-            const int nh = b.n_t / 2;
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(b.n_t >> 3) << 17) | ((uint32_t)((TC_M * 2) >> 4) << 24);
-            const int flags = ((int)i == last_p1 ? 1 : 0) | ((int)i == first_p2 ? 4 : 0);
-            tblk.push_back(make_int4(b.kb | (flags << 16), b.n_lo, (int)idesc, (int)(off >> 4) | (nh << 16)));
-            for (int rk = 0; rk < 2; rk++) {
-                __half *hi = reinterpret_cast<__half *>(timg.data() + (size_t)rk * rank_bytes + off);
-                __half *lo = hi + (size_t)nh * 16;
-                for (int n = 0; n < nh; n++)
-                    for (int k = 0; k < 16; k++) {
-                        const int row = b.q * TS_N + b.n_lo + rk * nh + n;
-                        const double g = (row < pl->NAp ? G[(size_t)row * pl->NBp + b.kb * 16 + k] : 0.0) * sc;
-                        const float gf = (float)g;
-                        const __half h = __float2half_rn(gf);
-                        const __half l = __float2half_rn(gf - __half2float(h));
-                        const size_t o = ((size_t)(k / 8) * (nh / 8) + n / 8) * 64 + (n % 8) * 8 + (k % 8);
-                        hi[o] = h;
-                        lo[o] = l;
-                    }
-            }
-            off += (size_t)nh * 64;
-        }
-        if (c_end <= TS_MAXCOL && rank_bytes < (size_t)200 * 1024 && tblk.size() <= TS_MAX_BLOCKS && slabs.size() <= TS_MAX_SLABS) {
-            pl->ts_slabs = n_sl;
-            pl->ts_blocks = (int)tblk.size();
-            pl->ts_rank_bytes = (int)rank_bytes;
-            pl->ts_c_end = c_end;
-            pl->ts_c_split = kb_split * 8;
-            pl->ts_q_need2 = blks[first_p2].q;
-            pl->ts_t_need2 = first_p2 - slabs[blks[first_p2].q].x;
-            NB_CUDA(ctx, pl->ts_img.reserve(timg.size()));
-            NB_CUDA(ctx, cudaMemcpy(pl->ts_img.p, timg.data(), timg.size(), cudaMemcpyHostToDevice));
-            pl->ts_blk = tblk;
-            pl->ts_slab = slabs;
+        TsHostPlan hp;
+        ts_build_plan(G, pl->NA, pl->NAp, pl->NBp, sc, hp);
+        if (hp.ok) {
+            pl->ts_slabs = hp.n_slabs;
+            pl->ts_blocks = hp.n_blocks;
+            pl->ts_rank_bytes = hp.rank_bytes;
+            pl->ts_c_end = hp.c_end;
+            pl->ts_c_split = hp.c_split;
+            pl->ts_q_need2 = hp.q_need2;
+            pl->ts_t_need2 = hp.t_need2;
+            NB_CUDA(ctx, pl->ts_img.reserve(hp.img.size()));
+            NB_CUDA(ctx, cudaMemcpy(pl->ts_img.p, hp.img.data(), hp.img.size(), cudaMemcpyHostToDevice));
+            pl->ts_blk = hp.blk;
+            pl->ts_slab = hp.slab;
             pl->ts_ok = true;
         }
     }
@@ -1623,6 +1699,44 @@ int nb200_tc_available(nb200_ctx *ctx)
 {
     TcPlan *pl = plan_of(ctx, false);
     return pl && pl->ok;
+}
+
+// Developer / test aid, no device needed: the block plan k_nuc_bx_ts would run for this VMat (rows = insert sizes
+// [lower, upper), `cols` columns) and fragment-size distribution (at least `upper` values).  stats[16] = {eligible, slabs,
+// blocks, hi-operand columns of part 1, columns in all, slab and position of the first block that reads part 2, bytes of one
+// CTA's image, NA, NB, MMA columns per x-tile and pass, non-zero (row, K block) pairs of G, non-zeros outside every block,
+// size-1 term present, 0, 0}; blocks[4 * i ..] = the table entry of block i (at most max_blocks are copied).
+extern "C" int nb200_tc_plan_describe(const double *vmat, int32_t lower, int32_t upper, int32_t cols, const double *sizes, int32_t n_sizes,
+                                      int32_t *stats, int32_t *blocks, int32_t max_blocks)
+{
+    if (!vmat || !sizes || !stats || upper <= lower || cols < 1 || n_sizes < upper || lower < 0) return NB200_ERR_ARG;
+    for (int i = 0; i < 16; i++) stats[i] = 0;
+    TcGeom geo;
+    if (!tc_build_geometry(vmat, lower, upper, cols, cols / 2, sizes, geo)) return NB200_OK;
+    TsHostPlan hp;
+    ts_build_plan(geo.G, geo.NA, geo.NAp, geo.NBp, geo.sc, hp);
+    stats[0] = hp.ok ? 1 : 0;
+    stats[1] = hp.n_slabs;
+    stats[2] = hp.n_blocks;
+    stats[3] = hp.c_split;
+    stats[4] = hp.c_end;
+    stats[5] = hp.q_need2;
+    stats[6] = hp.t_need2;
+    stats[7] = hp.rank_bytes;
+    stats[8] = geo.NA;
+    stats[9] = geo.NB;
+    stats[10] = (int32_t)hp.mma_cols;
+    stats[11] = (int32_t)hp.nonzero_cols;
+    stats[12] = (int32_t)hp.uncovered;
+    stats[13] = geo.has_row1;
+    if (blocks)
+        for (int i = 0; i < hp.n_blocks && i < max_blocks; i++) {
+            blocks[4 * i] = hp.blk[i].x;
+            blocks[4 * i + 1] = hp.blk[i].y;
+            blocks[4 * i + 2] = hp.blk[i].z;
+            blocks[4 * i + 3] = hp.blk[i].w;
+        }
+    return NB200_OK;
 }
 
 // max over the batch's E track (E > 0: IEEE bit patterns order like unsigned integers)
