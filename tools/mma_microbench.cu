@@ -1,4 +1,7 @@
-// microbenchmark: cost of back-to-back tcgen05.mma (kind::f16, K16) as a function of N, accumulator dependency, CTA pairs and concurrent tcgen05.ld
+// Microbenchmark behind DESIGN.md section 3 (profiles/r2b_mma_microbench.txt): cost of back-to-back tcgen05.mma (kind::f16, K16) as a
+// function of N, accumulator dependency, CTA pairs, concurrent tcgen05.ld (+ 32 LDS per load) and the A operand in tensor memory.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o mma_microbench tools/mma_microbench.cu && ./mma_microbench
+// (main() holds the last sweep that was run; the three sweeps of the log differ only in the run<>() calls.)
 #include <cuda_fp16.h>
 #include <cstdio>
 #include <cstdlib>
