@@ -521,17 +521,27 @@ static __global__ void __launch_bounds__(256) k_bias_track(const uint8_t *__rest
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_code[i] = nuc_code[i];
     __syncthreads();
     const int nload = (int)min((int64_t)(BT_TILE + width - 1), slen - x0);
-    for (int i = threadIdx.x; i < nload; i += blockDim.x) s_seq[i] = s_code[seq[so + x0 + i]];
+    for (int i = threadIdx.x; i < BT_TILE + width + 3 && i < BT_TILE + NB200_MAX_PWM_WIDTH; i += blockDim.x)
+        s_seq[i] = i < nload ? s_code[seq[so + x0 + i]] : (int8_t)-1;
     __syncthreads();
     const int n = (int)min((int64_t)BT_TILE, blen - x0);
-    for (int t = threadIdx.x; t < n; t += blockDim.x) {
-        double acc = 0.0;
+    // four consecutive positions per thread: four independent chains of `width` dependent additions (each position still adds
+    // its terms in ascending j), and four exp() whose instruction streams interleave
+    for (int t4 = 4 * threadIdx.x; t4 < n; t4 += 4 * blockDim.x) {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
         for (int j = 0; j < width; j++) {
-            int code = s_seq[t + j];
-            if (code >= 0) acc += s_pwm[code * width + j];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int code = s_seq[t4 + u + j];   // (positions past the end of the tile read the -1 padding and are not stored)
+                if (code >= 0) acc[u] += s_pwm[code * width + j];
+            }
         }
-        int64_t o = bias_off[c] + x0 + t;
-        if (E) E[o] = exp(acc);
-        if (b_out) b_out[o] = acc;
+        const int64_t o = bias_off[c] + x0 + t4;
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (t4 + u < n) {
+                if (E) E[o + u] = exp(acc[u]);
+                if (b_out) b_out[o + u] = acc[u];
+            }
     }
 }
