@@ -404,14 +404,14 @@ def run_ours(args, rank, world, local_rank):
         peaks = load_peaks()
         launches = int(sum(v[0] for v in prof.values()))
         # the kernel the roofline is quoted for: the dense background cross-correlation (the path's only contraction)
-        kname = "k_nuc_bx_tc" if "k_nuc_bx_tc" in prof else ("k_nuc_bx_fp64" if "k_nuc_bx_fp64" in prof else "k_occ_mle")
+        kname = next((k for k in ("k_nuc_bx_ts", "k_nuc_bx_tc", "k_nuc_bx_fp64") if k in prof), "k_occ_mle")
         kcount, kms = prof.get(kname, (0, 0.0))
         # algorithmic work of the dominant kernel: the dense background cross-correlation, 2*R*W flop per bp
         flop_per_launch = 2.0 * R_V * W_V * bp_step
         k_avg_s = (kms / max(kcount, 1)) * 1e-3
         achieved = flop_per_launch / k_avg_s / 1e12 if k_avg_s > 0 else 0.0
         roofline = dict(bound="tensor", kernel=kname, achieved=achieved, peak=peaks["tf_sustained"], unit="TFLOP/s",
-                        frac=achieved / peaks["tf_sustained"], traffic=TC_DRAM_BYTES_PER_CHUNK * B if kname == "k_nuc_bx_tc" else None,
+                        frac=achieved / peaks["tf_sustained"], traffic=TC_DRAM_BYTES_PER_CHUNK * B if kname == "k_nuc_bx_ts" else None,
                         traffic_source="ncu --set full, dram__bytes_read+write of the tcgen05 kernel (k_nuc_bx_ts): 36.64 MB per 400-chunk launch "
                                        "(profiles/r2b_ncu_ts.txt), scaled to this launch's chunk count", peak_source=peaks["source"] + " bf16 sustained",
                         kernel_ms_per_launch=kms / max(kcount, 1), kernel_share_of_step=kms / total_ms if total_ms else None,

@@ -94,7 +94,16 @@ __global__ void __launch_bounds__(WS_WIN) k_occ_winsums(const int64_t *__restric
 #ifndef MLE_ITERS
 #define MLE_ITERS 8
 #endif
-template <int NQ, int LB>  // NQ alphas per lane: lane r of a group owns alphas r, r + 8, ...; LB resident blocks per SM
+#ifndef MLE_GL_DEFAULT
+#define MLE_GL_DEFAULT 8
+#endif
+#ifndef MLE_LB_DEFAULT
+#define MLE_LB_DEFAULT 4
+#endif
+// NQ alphas per lane: lane r of a window's GL-lane group owns alphas r, r + GL, ...; LB resident blocks per SM; a warp scores
+// ITERS groups of 32 / GL windows.  GL = 16 (7 alphas per lane, ~64 registers, twice the resident warps) and GL = 8 (13 alphas
+// per lane) return identical grids: a grid point's product takes the same factors in the same order either way.
+template <int NQ, int LB, int GL, int ITERS>
 __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle(OccMleArgs a)
 {
     extern __shared__ double sm_mle[];  // pn[upper], pf[upper]
@@ -105,7 +114,7 @@ __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle(OccMleArgs a)
         s_pf[i] = a.pf[i];
     }
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3, r = lane & 7;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane / GL, r = lane % GL;
     const int c = blockIdx.y;
     const int64_t oo = a.out_off[c];
     const int L = (int)(a.out_off[c + 1] - oo);
@@ -117,13 +126,13 @@ __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle(OccMleArgs a)
     unsigned dead = 0;
 #pragma unroll
     for (int q = 0; q < NQ; q++) {
-        const int ai = r + 8 * q;
+        const int ai = r + GL * q;
         al[q] = (ai < a.n_alpha) ? a.alphas[ai] : 0.5;
         if ((ai >= a.n_alpha) || a.both_zero || (al[q] == 0.0 && a.pf_has_zero) || (al[q] == 1.0 && a.pn_has_zero)) dead |= 1u << q;
     }
     const bool last_is_one = (al[NQ - 1] == 1.0);  // alpha == 1 (only ever the last grid value, checked on the host)
-  for (int it = 0; it < MLE_ITERS; it++) {   // a warp scores MLE_ITERS groups of 4 windows
-    const int wbase = ((blockIdx.x * MLE_ITERS + it) * MLE_WARPS + warp) * MLE_GROUPS;
+  for (int it = 0; it < ITERS; it++) {   // a warp scores ITERS groups of 32 / GL windows
+    const int wbase = ((blockIdx.x * ITERS + it) * MLE_WARPS + warp) * (32 / GL);
     if (wbase >= nwin) break;  // whole warp past the last window
     const int wi = wbase + g;
     const bool valid = wi < nwin;
@@ -146,7 +155,7 @@ __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle(OccMleArgs a)
         mant[q] = 1.0;
         ex[q] = 0;
     }
-    for (int base = 0; base < nmax; base += 8) {
+    for (int base = 0; base < nmax; base += GL) {
         {   // lane (g, r) prepares fragment base + r of window g: nuc_probs / sum, nfr_probs / sum, Occupancy.py:106-109
             const int idx = base + r;
             double pv = 1.0, qv = 1.0;  // padding fragments contribute the factor 1
@@ -168,16 +177,19 @@ __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle(OccMleArgs a)
         }
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const double dj = s_d[warp][8 * g + j], qj = s_q[warp][8 * g + j];
+        for (int j = 0; j < GL; j++) {
+#ifndef MLE_NO_EARLY_OUT
+            if (base + j >= nmax) break;  // warp-uniform: the rest of the round is padding (factors of exactly 1.0 in every window)
+#endif
+            const double dj = s_d[warp][GL * g + j], qj = s_q[warp][GL * g + j];
 #pragma unroll
             for (int q = 0; q < NQ - 1; q++) mant[q] *= fma(al[q], dj, qj);
             double v = fma(al[NQ - 1], dj, qj);
-            if (last_is_one) v = s_p[warp][8 * g + j];
+            if (last_is_one) v = s_p[warp][GL * g + j];
             mant[NQ - 1] *= v;
         }
         __syncwarp();
-        if ((base & 56) == 56) {  // every 64 factors (each in (2^-7, 2) away from the grid ends, so the product stays above 2^-448): exponent -> ex
+        if (((base + GL) & 63) == 0) {  // every 64 factors (each in (2^-7, 2) away from the grid ends, so the product stays above 2^-448): exponent -> ex
 #pragma unroll
             for (int q = 0; q < NQ; q++) {
                 const long long bits = __double_as_longlong(mant[q]);
@@ -214,7 +226,7 @@ __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle(OccMleArgs a)
         double bestm = 0.0;
 #pragma unroll
         for (int q = 0; q < NQ; q++) {  // first maximum (np.argmax): strictly greater while walking up the grid
-            const int ai = r + 8 * q;
+            const int ai = r + GL * q;
             if (ai < a.n_alpha && (ke[q] > beste || (ke[q] == beste && mant[q] > bestm))) {
                 beste = ke[q];
                 bestm = mant[q];
@@ -223,7 +235,7 @@ __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle(OccMleArgs a)
         }
         if (besti == (1 << 30) && r < a.n_alpha) besti = r;  // all -inf on this lane: its first alpha ties with the others
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
+        for (int o = GL / 2; o > 0; o >>= 1) {
             const int oe = __shfl_xor_sync(NB_FULL, beste, o);
             const double om = __shfl_xor_sync(NB_FULL, bestm, o);
             const int oi = __shfl_xor_sync(NB_FULL, besti, o);
@@ -253,14 +265,14 @@ __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle(OccMleArgs a)
         int okmin = 1 << 30, okmax = -1;
 #pragma unroll
         for (int q = 0; q < NQ; q++) {
-            const int ai = r + 8 * q;
+            const int ai = r + GL * q;
             if (ai < a.n_alpha && !none && (ke[q] > te || (ke[q] == te && mant[q] > tm))) {  // Occupancy.py:116-119
                 okmin = min(okmin, ai);
                 okmax = max(okmax, ai);
             }
         }
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
+        for (int o = GL / 2; o > 0; o >>= 1) {
             okmin = min(okmin, __shfl_xor_sync(NB_FULL, okmin, o));
             okmax = max(okmax, __shfl_xor_sync(NB_FULL, okmax, o));
         }
@@ -278,13 +290,13 @@ __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle(OccMleArgs a)
             a.wv[2 * a.wv_stride + wo] = hi;
         }
         const int left = t - a.halfstep, right = min(t + a.halfstep + 1, L);
-        for (int x = left + r; x < right; x += 8) {
+        for (int x = left + r; x < right; x += GL) {
             a.vals[oo + x] = occ;
             a.lower[oo + x] = lo;
             a.upper_b[oo + x] = hi;
         }
         if (wi == nwin - 1)  // positions past the last window stay NaN (np.ones(n)*nan, Occupancy.py:133-135)
-            for (int x = right + r; x < L; x += 8) {
+            for (int x = right + r; x < L; x += GL) {
                 a.vals[oo + x] = nb_nan();
                 a.lower[oo + x] = nb_nan();
                 a.upper_b[oo + x] = nb_nan();
@@ -1619,8 +1631,9 @@ int nb200_occ_run(nb200_ctx *ctx, nb200_dbatch *b)
         const bool mle_search = mle_env && (!strcmp(mle_env, "tw") || !strcmp(mle_env, "group")) && r.n_alpha >= 17 && r.n_alpha <= 121;
         const bool mle_group = mle_search && !strcmp(mle_env, "group");
         ProfScope ps(ctx, b->stream, mle_search ? (mle_group ? "k_occ_mle_search" : "k_occ_mle_tw") : "k_occ_mle");
-        dim3 grid((unsigned)div_up64(max_win, MLE_WARPS * MLE_GROUPS * MLE_ITERS), n);
-        static const int mle_lb = getenv("NB200_MLE_LB") ? atoi(getenv("NB200_MLE_LB")) : 4;
+        dim3 grid((unsigned)div_up64(max_win, MLE_WARPS * MLE_GROUPS * MLE_ITERS), n);   // 128 windows per block in every form
+        const int mle_lb = getenv("NB200_MLE_LB") ? atoi(getenv("NB200_MLE_LB")) : MLE_LB_DEFAULT;   // read per call: tools/mle_ab.py switches forms inside one process
+        const int mle_gl = getenv("NB200_MLE_GL") ? atoi(getenv("NB200_MLE_GL")) : MLE_GL_DEFAULT;   // lanes per window: 8 | 16
         if (mle_search && !mle_group) {   // one thread per window
             const size_t smem_t = sizeof(double) * (2 * (size_t)((p.upper + 1) & ~1) + (size_t)((r.n_alpha + 1) & ~1)) + sizeof(double2) * (size_t)MTW_CAP * MTW_THREADS;
             static const int mtw_lb = getenv("NB200_MTW_LB") ? atoi(getenv("NB200_MTW_LB")) : 2;
@@ -1634,13 +1647,22 @@ int nb200_occ_run(nb200_ctx *ctx, nb200_dbatch *b)
             auto kern = mls_lb >= 6 ? k_occ_mle_search<6> : (mls_lb == 5 ? k_occ_mle_search<5> : k_occ_mle_search<4>);
             if (smem_s > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
             kern<<<grid, MLE_WARPS * 32, smem_s, b->stream>>>(a);
+        } else if (mle_gl == 16) {   // 16 lanes per window
+            if (r.n_alpha > 112)
+                k_occ_mle<8, 6, 16, 2 * MLE_ITERS><<<grid, MLE_WARPS * 32, smem, b->stream>>>(a);
+            else if (mle_lb >= 8)
+                k_occ_mle<7, 8, 16, 2 * MLE_ITERS><<<grid, MLE_WARPS * 32, smem, b->stream>>>(a);
+            else if (mle_lb == 7)
+                k_occ_mle<7, 7, 16, 2 * MLE_ITERS><<<grid, MLE_WARPS * 32, smem, b->stream>>>(a);
+            else
+                k_occ_mle<7, 6, 16, 2 * MLE_ITERS><<<grid, MLE_WARPS * 32, smem, b->stream>>>(a);
         } else if (r.n_alpha <= 104) {
             if (mle_lb >= 5)
-                k_occ_mle<13, 5><<<grid, MLE_WARPS * 32, smem, b->stream>>>(a);
+                k_occ_mle<13, 5, 8, MLE_ITERS><<<grid, MLE_WARPS * 32, smem, b->stream>>>(a);
             else
-                k_occ_mle<13, 4><<<grid, MLE_WARPS * 32, smem, b->stream>>>(a);
+                k_occ_mle<13, 4, 8, MLE_ITERS><<<grid, MLE_WARPS * 32, smem, b->stream>>>(a);
         } else
-            k_occ_mle<16, 4><<<grid, MLE_WARPS * 32, smem, b->stream>>>(a);
+            k_occ_mle<16, 4, 8, MLE_ITERS><<<grid, MLE_WARPS * 32, smem, b->stream>>>(a);
         NB_LAUNCH_CHECK(ctx);
     }
     {

@@ -1823,7 +1823,7 @@ int nb200_nuc_bx_tc(nb200_ctx *ctx, nb200_dbatch *b)
             memcpy(tab.blk, pl->ts_blk.data(), sizeof(int4) * pl->ts_blk.size());
             memcpy(tab.slab, pl->ts_slab.data(), sizeof(int2) * pl->ts_slab.size());
             NB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ts));
-            ProfScope ps(ctx, b->stream, "k_nuc_bx_tc");
+            ProfScope ps(ctx, b->stream, "k_nuc_bx_ts");
             const int n_items = t.n_chunks * t.tiles_per_chunk;
             dim3 grid((unsigned)(2 * std::max(1, std::min(ctx->sm_count / 2, n_items))));
             unsigned long long *d_dbg = nullptr;

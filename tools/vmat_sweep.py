@@ -47,7 +47,7 @@ def main():
         prof = eng.profile_report()
         eng.profile(False)
         bp = steps * batches[0].total_len
-        kname = "k_nuc_bx_tc" if "k_nuc_bx_tc" in prof else "k_nuc_bx_fp64"
+        kname = next((k for k in ("k_nuc_bx_ts", "k_nuc_bx_tc") if k in prof), "k_nuc_bx_fp64")
         kms = prof[kname][1]
         useful = 2.0 * R * W * bp / (kms * 1e-3) / 1e12
         other_ms = total - kms
