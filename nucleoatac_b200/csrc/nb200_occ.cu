@@ -32,6 +32,9 @@ struct OccMleArgs {
     double cutoff, sn_nobias, sf_nobias;   // the last two: 1 / (sum of the model over a window) without a bias model
     double thr_m;   // exp(-cutoff/2) = thr_m * 2^thr_e, thr_m in [1,2) (NaN for a NaN cutoff); thr_zero: it underflows to 0
     int thr_e, thr_zero;
+    double thr_k;   // exp(-cutoff/2) itself; fast_epi: it is a normal number well inside the double range (the direct comparisons of
+    int fast_epi;   // k_occ_mle's short epilogue round exactly like the canonical ones)
+    int stage;      // k_occ_mle stages its block's column pointers / fragment sizes / window normalisers in shared memory
 };
 
 // Window sums of the per-column sums: SN[k] = sum of cn over the 2*flank+1 columns of window k (t = halfstep + k*step), SF
@@ -100,20 +103,24 @@ __global__ void __launch_bounds__(WS_WIN) k_occ_winsums(const int64_t *__restric
 #ifndef MLE_LB_DEFAULT
 #define MLE_LB_DEFAULT 4
 #endif
+#define MLE_WPB (MLE_WARPS * MLE_GROUPS * MLE_ITERS)   // windows per block (consecutive windows of one chunk)
+#ifndef MLE_CAPF
+#define MLE_CAPF 1024                                   // fragment sizes staged per block (the rest is read from global memory)
+#endif
 // NQ alphas per lane: lane r of a window's GL-lane group owns alphas r, r + GL, ...; LB resident blocks per SM; a warp scores
 // ITERS groups of 32 / GL windows.  GL = 16 (7 alphas per lane, ~64 registers, twice the resident warps) and GL = 8 (13 alphas
 // per lane) return identical grids: a grid point's product takes the same factors in the same order either way.
 template <int NQ, int LB, int GL, int ITERS>
 __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle(OccMleArgs a)
 {
-    extern __shared__ double sm_mle[];  // pn[upper], pf[upper]
+    // dynamic: pn[upper], pf[upper] | staged inputs of the block's MLE_WPB consecutive windows (a.stage): wsn[WPB], wsf[WPB],
+    // the column pointers its windows' ends read, the sizes of the first MLE_CAPF fragments under them
+    extern __shared__ double sm_mle[];
     __shared__ double s_d[MLE_WARPS][32], s_q[MLE_WARPS][32], s_p[MLE_WARPS][32];
+    static_assert(MLE_WARPS * (32 / GL) * ITERS == MLE_WPB, "windows per block");
     double *s_pn = sm_mle, *s_pf = sm_mle + a.upper;
-    for (int i = threadIdx.x; i < a.upper; i += blockDim.x) {
-        s_pn[i] = a.pn[i];
-        s_pf[i] = a.pf[i];
-    }
-    __syncthreads();
+    double *s_wsn = s_pf + a.upper, *s_wsf = s_wsn + MLE_WPB;
+    int *s_cp = reinterpret_cast<int *>(s_wsf + MLE_WPB), *s_sz = s_cp + (((MLE_WPB - 1) * a.step + 2 * a.flank + 2 + 3) & ~3);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane / GL, r = lane % GL;
     const int c = blockIdx.y;
     const int64_t oo = a.out_off[c];
@@ -121,6 +128,32 @@ __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle(OccMleArgs a)
     const int nwin = (L - a.halfstep + a.step - 1) / a.step;  // windows at t = halfstep + k*step < L
     const int32_t *cp = a.col_ptr + a.col_off[c];
     const int2 *en = a.ent + a.frag_off[c];
+    const int wb0 = blockIdx.x * MLE_WPB;                       // first window of the block
+    if (wb0 >= nwin) return;
+    const int c_lo = a.halfstep + wb0 * a.step - a.flank + a.csc_pad;   // column pointer the first window starts at
+    int eA = 0;
+    for (int i = threadIdx.x; i < a.upper; i += blockDim.x) {
+        s_pn[i] = a.pn[i];
+        s_pf[i] = a.pf[i];
+    }
+    if (a.stage) {
+        // Every load the warps' loops would otherwise wait for (long-scoreboard stalls were 12 % of the kernel's samples with
+        // four warps per scheduler to hide them) is made once per block, coalesced.
+        const int nw = min(MLE_WPB, nwin - wb0);
+        const int ncp = (nw - 1) * a.step + 2 * a.flank + 2;
+        eA = cp[c_lo];
+        const int nf = min(cp[c_lo + ncp - 1] - eA, MLE_CAPF);
+        for (int i = threadIdx.x; i < ncp; i += blockDim.x) s_cp[i] = cp[c_lo + i];
+        for (int i = threadIdx.x; i < nf; i += blockDim.x) s_sz[i] = en[eA + i].y;
+        if (a.use_bias) {
+            const int64_t wo0 = oo / a.step + c + wb0;
+            for (int i = threadIdx.x; i < nw; i += blockDim.x) {
+                s_wsn[i] = a.wsn[wo0 + i];
+                s_wsf[i] = a.wsf[wo0 + i];
+            }
+        }
+    }
+    __syncthreads();
     // grid constants of this lane: its alphas and which of them are dead (0 * log 0 = NaN -> -inf, Occupancy.py:112-114)
     double al[NQ];
     unsigned dead = 0;
@@ -137,22 +170,37 @@ __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle(OccMleArgs a)
     const int wi = wbase + g;
     const bool valid = wi < nwin;
     const int t = a.halfstep + wi * a.step;
-    const int e0 = valid ? cp[t - a.flank + a.csc_pad] : 0, e1 = valid ? cp[t + a.flank + 1 + a.csc_pad] : 0;
+    int e0 = 0, e1 = 0;
+    if (valid) {
+        if (a.stage) {
+            e0 = s_cp[(wi - wb0) * a.step];
+            e1 = s_cp[(wi - wb0) * a.step + 2 * a.flank + 1];
+        } else {
+            e0 = cp[t - a.flank + a.csc_pad];
+            e1 = cp[t + a.flank + 1 + a.csc_pad];
+        }
+    }
     const int n = e1 - e0;
+    const int so = e0 - eA;   // slot of the window's first fragment in s_sz
     int nmax = n;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(NB_FULL, nmax, o));
     double rSN = a.sn_nobias, rSF = a.sf_nobias;   // reciprocals of the window's normalisers
     if (a.use_bias && valid) {
-        const int64_t wo = oo / a.step + c + wi;
-        rSN = a.wsn[wo];
-        rSF = a.wsf[wo];
+        if (a.stage) {
+            rSN = s_wsn[wi - wb0];
+            rSF = s_wsf[wi - wb0];
+        } else {
+            const int64_t wo = oo / a.step + c + wi;
+            rSN = a.wsn[wo];
+            rSF = a.wsf[wo];
+        }
     }
     double mant[NQ];
     int ex[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; q++) {
-        mant[q] = 1.0;
+        mant[q] = ((dead >> q) & 1) ? 0.0 : 1.0;   // a dead grid point's product is 0 from the start (-inf either way below)
         ex[q] = 0;
     }
     for (int base = 0; base < nmax; base += GL) {
@@ -160,7 +208,7 @@ __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle(OccMleArgs a)
             const int idx = base + r;
             double pv = 1.0, qv = 1.0;  // padding fragments contribute the factor 1
             if (idx < n) {
-                const int sz = en[e0 + idx].y;
+                const int sz = (a.stage && so + idx < MLE_CAPF) ? s_sz[so + idx] : en[e0 + idx].y;
                 pv = s_pn[sz] * rSN;
                 qv = s_pf[sz] * rSF;
                 const long long mb = __double_as_longlong(fmax(pv, qv));
@@ -176,17 +224,20 @@ __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle(OccMleArgs a)
             s_p[warp][lane] = pv;       // alpha == 1 uses p itself (q + (p-q) would lose p when p << q)
         }
         __syncwarp();
-#pragma unroll
-        for (int j = 0; j < GL; j++) {
-#ifndef MLE_NO_EARLY_OUT
-            if (base + j >= nmax) break;  // warp-uniform: the rest of the round is padding (factors of exactly 1.0 in every window)
-#endif
+        auto factor = [&](int j) {   // fragment j of the round into the NQ products of this lane
             const double dj = s_d[warp][GL * g + j], qj = s_q[warp][GL * g + j];
 #pragma unroll
             for (int q = 0; q < NQ - 1; q++) mant[q] *= fma(al[q], dj, qj);
             double v = fma(al[NQ - 1], dj, qj);
             if (last_is_one) v = s_p[warp][GL * g + j];
             mant[NQ - 1] *= v;
+        };
+        if (nmax - base >= GL) {
+#pragma unroll
+            for (int j = 0; j < GL; j++) factor(j);
+        } else {   // last round: only its first nmax - base slots hold a fragment of any window (the rest are factors of exactly 1.0)
+#pragma unroll 1
+            for (int j = 0; j < nmax - base; j++) factor(j);
         }
         __syncwarp();
         if (((base + GL) & 63) == 0) {  // every 64 factors (each in (2^-7, 2) away from the grid ends, so the product stays above 2^-448): exponent -> ex
@@ -202,7 +253,55 @@ __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle(OccMleArgs a)
         }
     }
     double occ = nb_nan(), lo = nb_nan(), hi = nb_nan();
-    {
+    bool done = false;
+    if (nmax <= 64 - GL && a.fast_epi) {
+        // Short epilogue (warp-uniform condition): no product of this warp has been renormalised yet (all ex[] are 0), so the
+        // products are plain doubles and every comparison of the canonical epilogue below is the same comparison made on them
+        // directly -- exact for any pair of non-negative doubles, subnormal or not; dead points and zero / NaN products hold
+        // 0 / NaN and never compare greater.  The one rounded operation, threshold = max * exp(-cutoff/2), rounds like the
+        // canonical mantissa product as long as the result is a normal number: a warp with a maximum below 1e-250 takes the
+        // canonical epilogue instead.
+        double best = 0.0;
+        int besti = 1 << 30;
+#pragma unroll
+        for (int q = 0; q < NQ; q++)
+            if (mant[q] > best) {   // first maximum (np.argmax): strictly greater while walking up the grid
+                best = mant[q];
+                besti = r + GL * q;
+            }
+        if (besti == (1 << 30) && r < a.n_alpha) besti = r;
+#pragma unroll
+        for (int o = GL / 2; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(NB_FULL, best, o);
+            const int oi = __shfl_xor_sync(NB_FULL, besti, o);
+            if (ob > best || (ob == best && oi < besti)) {
+                best = ob;
+                besti = oi;
+            }
+        }
+        if (!__any_sync(NB_FULL, best > 0.0 && best < 1e-250)) {
+            done = true;
+            const double thr = best * a.thr_k;   // Occupancy.py:116-119: ll > max - cutoff/2
+            int okmin = 1 << 30, okmax = -1;
+#pragma unroll
+            for (int q = 0; q < NQ; q++)
+                if (mant[q] > thr) {
+                    okmin = min(okmin, r + GL * q);
+                    okmax = max(okmax, r + GL * q);
+                }
+#pragma unroll
+            for (int o = GL / 2; o > 0; o >>= 1) {
+                okmin = min(okmin, __shfl_xor_sync(NB_FULL, okmin, o));
+                okmax = max(okmax, __shfl_xor_sync(NB_FULL, okmax, o));
+            }
+            if (n > 0 && okmax >= 0 && besti < a.n_alpha) {  // Occupancy.py:141 `if sum(new_inserts)>0`
+                occ = a.alphas[besti];
+                lo = a.alphas[okmin];
+                hi = a.alphas[okmax];
+            }
+        }
+    }
+    if (!done) {
         // Everything the reference does with the log-likelihoods is a comparison (np.argmax; 2*(max - ll) < cutoff,
         // Occupancy.py:115-119), and log is monotone: compare the products themselves, as exact (binary exponent,
         // mantissa in [1,2)) pairs -- no logarithm.  Dead grid points (0*log 0 = NaN -> -inf) and zero / NaN products
@@ -290,12 +389,14 @@ __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle(OccMleArgs a)
             a.wv[2 * a.wv_stride + wo] = hi;
         }
         const int left = t - a.halfstep, right = min(t + a.halfstep + 1, L);
+#pragma unroll 1
         for (int x = left + r; x < right; x += GL) {
             a.vals[oo + x] = occ;
             a.lower[oo + x] = lo;
             a.upper_b[oo + x] = hi;
         }
         if (wi == nwin - 1)  // positions past the last window stay NaN (np.ones(n)*nan, Occupancy.py:133-135)
+#pragma unroll 1
             for (int x = right + r; x < L; x += GL) {
                 a.vals[oo + x] = nb_nan();
                 a.lower[oo + x] = nb_nan();
@@ -1598,12 +1699,22 @@ int nb200_occ_run(nb200_ctx *ctx, nb200_dbatch *b)
             a.thr_zero = (k == 0.0) ? 1 : 0;
             a.thr_m = (k > 0.0 && std::isfinite(k)) ? 2.0 * m : (k == 0.0 ? 1.0 : (double)NAN);  // NaN: nothing passes
             a.thr_e = e - 1;
+            a.thr_k = k;
+            const char *epi = getenv("NB200_MLE_EPI");   // developer switch: "canonical" = always the (exponent, mantissa) epilogue
+            a.fast_epi = (std::isfinite(k) && k >= 1e-30 && k <= 1e30 && !(epi && !strcmp(epi, "canonical"))) ? 1 : 0;
         }
         a.sn_nobias = 1.0 / (r.pn_sum * window);
         a.sf_nobias = 1.0 / (r.pf_sum * window);
         int max_win = (b->max_len - halfstep + p.step - 1) / p.step;
         if (max_win < 1) max_win = 1;
-        const size_t smem = sizeof(double) * 2 * (size_t)p.upper;
+        size_t smem = sizeof(double) * 2 * (size_t)p.upper;
+        {
+            const size_t smem_staged = smem + sizeof(double) * 2 * MLE_WPB +
+                                       sizeof(int) * ((((size_t)(MLE_WPB - 1) * p.step + 2 * (size_t)p.flank + 2 + 3) & ~(size_t)3) + MLE_CAPF);
+            const char *st = getenv("NB200_MLE_STAGE");   // developer switch: "0" = every warp loads its own inputs from global memory
+            a.stage = (smem_staged <= 40 * 1024 && !(st && !strcmp(st, "0"))) ? 1 : 0;   // unusually wide windows / steps: unstaged
+            if (a.stage) smem = smem_staged;
+        }
         a.wsn = a.wsf = nullptr;
         if (p.use_bias) {
             const size_t nws = tl / p.step + n + 2;

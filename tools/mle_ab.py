@@ -25,11 +25,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=2000)
     ap.add_argument("--reps", type=int, default=4)
-    ap.add_argument("--forms", default="8:4,8:5,16:6,16:7,16:8")
+    ap.add_argument("--forms", default="8:4:fast:0,8:4:fast:1,8:5:fast:1,16:6:fast:1", help="lanes per window : resident blocks per SM : epilogue : staged inputs")
     args = ap.parse_args()
     from nucleoatac_b200 import synth
     from nucleoatac_b200.engine import Engine, PackedBatch
-    forms = [tuple(int(v) for v in f.split(":")) for f in args.forms.split(",")]
+    forms = [tuple(f.split(":")) for f in args.forms.split(",")]
     eng = Engine(0)
     wl = synth.Workload(251, 251)
     wl.configure(eng, use_bias=True, xcor_mode=0)
@@ -40,7 +40,7 @@ def main():
     times = {f: [] for f in forms}
     for rep in range(args.reps + 1):
         for f in forms:
-            os.environ["NB200_MLE_GL"], os.environ["NB200_MLE_LB"] = str(f[0]), str(f[1])
+            os.environ["NB200_MLE_GL"], os.environ["NB200_MLE_LB"], os.environ["NB200_MLE_EPI"], os.environ["NB200_MLE_STAGE"] = f
             eng.profile_reset()
             eng.occ_run(h)
             eng.sync(h)
@@ -57,7 +57,7 @@ def main():
             else:
                 times[f].append(eng.profile_report()["k_occ_mle"][1])
     for f in forms:
-        print(json.dumps(dict(kernel="k_occ_mle", lanes_per_window=f[0], blocks_per_sm=f[1], ms=sorted(times[f]), median_ms=float(np.median(times[f])),
+        print(json.dumps(dict(kernel="k_occ_mle", lanes_per_window=int(f[0]), blocks_per_sm=int(f[1]), epilogue=f[2], staged=int(f[3]), ms=sorted(times[f]), median_ms=float(np.median(times[f])),
                               batch=args.batch, identical_to_first=True)))
     eng.free_batch(h)
     eng.close()
