@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle(OccMleArgs a)
     // the column pointers its windows' ends read, the sizes of the first MLE_CAPF fragments under them
     extern __shared__ double sm_mle[];
     __shared__ double s_d[MLE_WARPS][32], s_q[MLE_WARPS][32], s_p[MLE_WARPS][32];
-    static_assert(MLE_WARPS * (32 / GL) * ITERS == MLE_WPB, "windows per block");
+    static_assert(MLE_WARPS * (32 / GL) * ITERS == MLE_WPB && MLE_WPB <= MLE_WARPS * 32, "windows per block (one staged normaliser pair per thread)");
     double *s_pn = sm_mle, *s_pf = sm_mle + a.upper;
     double *s_wsn = s_pf + a.upper, *s_wsf = s_wsn + MLE_WPB;
     int *s_cp = reinterpret_cast<int *>(s_wsf + MLE_WPB), *s_sz = s_cp + (((MLE_WPB - 1) * a.step + 2 * a.flank + 2 + 3) & ~3);
@@ -142,16 +142,43 @@ __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle(OccMleArgs a)
         const int nw = min(MLE_WPB, nwin - wb0);
         const int ncp = (nw - 1) * a.step + 2 * a.flank + 2;
         eA = cp[c_lo];
-        const int nf = min(cp[c_lo + ncp - 1] - eA, MLE_CAPF);
-        for (int i = threadIdx.x; i < ncp; i += blockDim.x) s_cp[i] = cp[c_lo + i];
-        for (int i = threadIdx.x; i < nf; i += blockDim.x) s_sz[i] = en[eA + i].y;
-        if (a.use_bias) {
-            const int64_t wo0 = oo / a.step + c + wb0;
-            for (int i = threadIdx.x; i < nw; i += blockDim.x) {
-                s_wsn[i] = a.wsn[wo0 + i];
-                s_wsf[i] = a.wsf[wo0 + i];
-            }
+        const int eB = cp[c_lo + ncp - 1];
+        // all the loads of a thread are issued before its first store (one exposed global-memory latency per block, not one per pass)
+        int vcp[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int i = threadIdx.x + k * (MLE_WARPS * 32);
+            vcp[k] = (i < ncp) ? cp[c_lo + i] : 0;
         }
+        double vn = 0.0, vf = 0.0;
+        if (a.use_bias && (int)threadIdx.x < nw) {
+            const int64_t wo0 = oo / a.step + c + wb0;
+            vn = a.wsn[wo0 + threadIdx.x];
+            vf = a.wsf[wo0 + threadIdx.x];
+        }
+        const int nf = min(eB - eA, MLE_CAPF);
+        int vsz[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int i = threadIdx.x + k * (MLE_WARPS * 32);
+            vsz[k] = (i < nf) ? en[eA + i].y : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int i = threadIdx.x + k * (MLE_WARPS * 32);
+            if (i < ncp) s_cp[i] = vcp[k];
+        }
+        for (int i = threadIdx.x + 8 * (MLE_WARPS * 32); i < ncp; i += blockDim.x) s_cp[i] = cp[c_lo + i];   // steps / flanks beyond the default
+        if ((int)threadIdx.x < MLE_WPB) {   // slots past the chunk's last window are never read
+            s_wsn[threadIdx.x] = vn;
+            s_wsf[threadIdx.x] = vf;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int i = threadIdx.x + k * (MLE_WARPS * 32);
+            if (i < nf) s_sz[i] = vsz[k];
+        }
+        for (int i = threadIdx.x + 4 * (MLE_WARPS * 32); i < nf; i += blockDim.x) s_sz[i] = en[eA + i].y;
     }
     __syncthreads();
     // grid constants of this lane: its alphas and which of them are dead (0 * log 0 = NaN -> -inf, Occupancy.py:112-114)
