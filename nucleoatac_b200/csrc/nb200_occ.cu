@@ -1261,7 +1261,9 @@ __global__ void __launch_bounds__(SB_THREADS) k_occ_smooth_blocks(const double *
     const int nTs = (2 * R + 1) * S;                 // stored entries: indices h - R S .. h + R S + S - 1
     const int nTp = (nTs + 1) & ~1;
     double *s_T = sm_sb;                             // [nTp], s_T[i + padL] = T[i]
-    double2 *s_vp = reinterpret_cast<double2 *>(sm_sb + nTp);  // [SB_THREADS + 2 R] (V0, V1) of every block in reach of the tile
+    const int nWd = (wlen + 5) & ~1;
+    double *s_wd = sm_sb + nTp;                      // [nWd] the taps in the tap-by-tap path's order, zero padded: s_wd[k] = w[h - (dlo + k)]
+    double2 *s_vp = reinterpret_cast<double2 *>(sm_sb + nTp + nWd);  // [SB_THREADS + 2 R] (V0, V1) of every block in reach of the tile
     double2 *s_vq = s_vp + (SB_THREADS + 2 * R);               // [SB_THREADS + 2 R] (V2, I): two arrays, so a warp's 16-byte loads are contiguous
     int *s_cnt = reinterpret_cast<int *>(s_vq + (SB_THREADS + 2 * R));   // [SB_THREADS + 2 R + 1] prefix count of missing blocks
     const int c = blockIdx.y;
@@ -1288,17 +1290,24 @@ __global__ void __launch_bounds__(SB_THREADS) k_occ_smooth_blocks(const double *
         }
         s_T[k] = t;
     }
+    {
+        const int dlo = -((wlen - h) & ~1);
+        for (int k = threadIdx.x; k < nWd; k += SB_THREADS) {
+            const int m = h - (dlo + k);
+            s_wd[k] = (m >= 0 && m < wlen) ? win[m] : 0.0;
+        }
+    }
     for (int i = threadIdx.x; i < SB_THREADS + 2 * R; i += SB_THREADS) {
         const int b = bt0 - R + i;
         double v0 = 0.0, v1 = 0.0, v2 = 0.0, pres = 0.0;
-        if (b >= 0 && b < nwin) {
+        if (b >= 0 && b < nwin) {   // three independent loads (the bounds of a NaN window are NaN as well and are dropped with it)
             v0 = wv[wo0 + b];
-            if (v0 == v0) {
-                v1 = wv[wv_stride + wo0 + b];
-                v2 = wv[2 * wv_stride + wo0 + b];
+            v1 = wv[wv_stride + wo0 + b];
+            v2 = wv[2 * wv_stride + wo0 + b];
+            if (v0 == v0)
                 pres = 1.0;
-            } else
-                v0 = 0.0;
+            else
+                v0 = v1 = v2 = 0.0;
         }
         s_vp[i] = make_double2(v0, v1);
         s_vq[i] = make_double2(v2, pres);
@@ -1330,10 +1339,7 @@ __global__ void __launch_bounds__(SB_THREADS) k_occ_smooth_blocks(const double *
         const int dlo = -((wlen - h) & ~1);
         const int T2 = (h - dlo + 2) & ~1;
         const int nvalid = min(L, nwin * S);              // positions with a window value
-        auto tapw = [&](int k) {                          // wd[k] = w[h - (dlo + k)], zero padded
-            const int m = h - (dlo + k);
-            return (m >= 0 && m < wlen) ? win[m] : 0.0;
-        };
+        auto tapw = [&](int k) { return s_wd[k]; };       // wd[k] = w[h - (dlo + k)], zero padded
         for (int u = 0; u < S; u++) {
             const int n = n0 + u;
             if (n >= L) break;
@@ -1814,7 +1820,7 @@ int nb200_occ_run(nb200_ctx *ctx, nb200_dbatch *b)
         const bool dense_smooth = getenv("NB200_OCC_SMOOTH_DENSE") != nullptr;   // developer switch: tap-by-tap smoothing
         if (p.step == 5 && !dense_smooth) {   // block form on the per-window values (the default step)
             const int R = ((p.smooth_len - 1) / 2 + 4) / 5;
-            const size_t smem = sizeof(double) * (size_t)(((2 * R + 1) * 5 + 1) & ~1) + sizeof(double2) * 2 * (size_t)(SB_THREADS + 2 * R) +
+            const size_t smem = sizeof(double) * ((size_t)(((2 * R + 1) * 5 + 1) & ~1) + (size_t)((p.smooth_len + 5) & ~1)) + sizeof(double2) * 2 * (size_t)(SB_THREADS + 2 * R) +
                                 sizeof(int) * (size_t)(SB_THREADS + 2 * R + 4);
             if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_occ_smooth_blocks<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ProfScope ps(ctx, b->stream, "k_occ_smooth_blocks");
