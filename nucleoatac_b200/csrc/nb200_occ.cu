@@ -104,6 +104,8 @@ __global__ void __launch_bounds__(WS_WIN) k_occ_winsums(const int64_t *__restric
 #define MLE_LB_DEFAULT 4
 #endif
 #define MLE_WPB (MLE_WARPS * MLE_GROUPS * MLE_ITERS)   // windows per block (consecutive windows of one chunk)
+#define MLE_CPK (((MLE_WPB - 1) * 5 + 2 * 60 + 2 + MLE_WARPS * 32 - 1) / (MLE_WARPS * 32))   // staged column pointers per thread at the default step / flank
+#define MLE_WPK ((MLE_WPB + MLE_WARPS * 32 - 1) / (MLE_WARPS * 32))                             // staged window normalisers per thread
 #ifndef MLE_CAPF
 #define MLE_CAPF 1024                                   // fragment sizes staged per block (the rest is read from global memory)
 #endif
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle(OccMleArgs a)
     // the column pointers its windows' ends read, the sizes of the first MLE_CAPF fragments under them
     extern __shared__ double sm_mle[];
     __shared__ double s_d[MLE_WARPS][32], s_q[MLE_WARPS][32], s_p[MLE_WARPS][32];
-    static_assert(MLE_WARPS * (32 / GL) * ITERS == MLE_WPB && MLE_WPB <= MLE_WARPS * 32, "windows per block (one staged normaliser pair per thread)");
+    static_assert(MLE_WARPS * (32 / GL) * ITERS == MLE_WPB, "windows per block");
     double *s_pn = sm_mle, *s_pf = sm_mle + a.upper;
     double *s_wsn = s_pf + a.upper, *s_wsf = s_wsn + MLE_WPB;
     int *s_cp = reinterpret_cast<int *>(s_wsf + MLE_WPB), *s_sz = s_cp + (((MLE_WPB - 1) * a.step + 2 * a.flank + 2 + 3) & ~3);
@@ -144,17 +146,22 @@ __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle(OccMleArgs a)
         eA = cp[c_lo];
         const int eB = cp[c_lo + ncp - 1];
         // all the loads of a thread are issued before its first store (one exposed global-memory latency per block, not one per pass)
-        int vcp[8];
+        int vcp[MLE_CPK];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
+        for (int k = 0; k < MLE_CPK; k++) {
             const int i = threadIdx.x + k * (MLE_WARPS * 32);
             vcp[k] = (i < ncp) ? cp[c_lo + i] : 0;
         }
-        double vn = 0.0, vf = 0.0;
-        if (a.use_bias && (int)threadIdx.x < nw) {
-            const int64_t wo0 = oo / a.step + c + wb0;
-            vn = a.wsn[wo0 + threadIdx.x];
-            vf = a.wsf[wo0 + threadIdx.x];
+        double vn[MLE_WPK], vf[MLE_WPK];
+#pragma unroll
+        for (int k = 0; k < MLE_WPK; k++) {
+            const int i = threadIdx.x + k * (MLE_WARPS * 32);
+            vn[k] = vf[k] = 0.0;
+            if (a.use_bias && i < nw) {
+                const int64_t wo0 = oo / a.step + c + wb0;
+                vn[k] = a.wsn[wo0 + i];
+                vf[k] = a.wsf[wo0 + i];
+            }
         }
         const int nf = min(eB - eA, MLE_CAPF);
         int vsz[4];
@@ -164,14 +171,18 @@ __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle(OccMleArgs a)
             vsz[k] = (i < nf) ? en[eA + i].y : 0;
         }
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
+        for (int k = 0; k < MLE_CPK; k++) {
             const int i = threadIdx.x + k * (MLE_WARPS * 32);
             if (i < ncp) s_cp[i] = vcp[k];
         }
-        for (int i = threadIdx.x + 8 * (MLE_WARPS * 32); i < ncp; i += blockDim.x) s_cp[i] = cp[c_lo + i];   // steps / flanks beyond the default
-        if ((int)threadIdx.x < MLE_WPB) {   // slots past the chunk's last window are never read
-            s_wsn[threadIdx.x] = vn;
-            s_wsf[threadIdx.x] = vf;
+        for (int i = threadIdx.x + MLE_CPK * (MLE_WARPS * 32); i < ncp; i += blockDim.x) s_cp[i] = cp[c_lo + i];   // steps / flanks beyond the default
+#pragma unroll
+        for (int k = 0; k < MLE_WPK; k++) {   // slots past the chunk's last window are never read
+            const int i = threadIdx.x + k * (MLE_WARPS * 32);
+            if (i < MLE_WPB) {
+                s_wsn[i] = vn[k];
+                s_wsf[i] = vf[k];
+            }
         }
 #pragma unroll
         for (int k = 0; k < 4; k++) {
