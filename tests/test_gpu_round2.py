@@ -109,6 +109,29 @@ def test_occ_search_equals_full_scan(eng, use_bias):
     np.testing.assert_allclose(new["nuc_dist"][dense], full["nuc_dist"][dense], rtol=1e-12, atol=1e-15)
 
 
+def test_occ_scan_forms_agree(eng):
+    """The forms of the grid scan k_occ_mle (Occupancy.py:104-146) -- inputs staged in shared memory or loaded by every warp,
+    the short epilogue on plain doubles or the (exponent, mantissa) one, 8 or 16 lanes per window -- return the same grids
+    bit for bit on sparse, dense (renormalised products, more fragments under a block than its staging area holds) and ragged
+    chunks, with and without the bias model."""
+    from nucleoatac_b200 import synth
+    pb = _mixed_batch()
+    for use_bias in (True, False):
+        wl = synth.Workload(251, 251)
+        wl.configure(eng, use_bias=use_bias)
+        ref, prof = _occ(eng, pb)
+        assert prof.get("k_occ_mle", (0, 0.0))[0] > 0
+        for env in ({"NB200_MLE_STAGE": "0"}, {"NB200_MLE_EPI": "canonical"}, {"NB200_MLE_STAGE": "0", "NB200_MLE_EPI": "canonical"},
+                    {"NB200_MLE_GL": "16", "NB200_MLE_LB": "6"}, {"NB200_MLE_GL": "16", "NB200_MLE_LB": "8", "NB200_MLE_EPI": "canonical"},
+                    {"NB200_MLE_LB": "5"}):
+            out, prof = _occ(eng, pb, env)
+            assert prof.get("k_occ_mle", (0, 0.0))[0] > 0
+            for key in ("vals", "lower_bound", "upper_bound", "smoothed_vals", "peak_pos", "peak_count", "nuc_dist"):
+                assert np.array_equal(ref[key], out[key], equal_nan=True), (use_bias, env, key)
+    wl = synth.Workload(251, 251)
+    wl.configure(eng, use_bias=True)
+
+
 def test_occ_search_other_grids(eng):
     """Grids other than linspace(0, 1, 101): 17, 64 and 121 points go through the search; a cutoff of 0 (nothing but the maximum
     passes) and a huge one (everything passes)."""

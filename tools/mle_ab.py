@@ -25,7 +25,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=2000)
     ap.add_argument("--reps", type=int, default=4)
-    ap.add_argument("--forms", default="8:4:fast:0,8:4:fast:1,8:5:fast:1,16:6:fast:1", help="lanes per window : resident blocks per SM : epilogue : staged inputs")
+    ap.add_argument("--forms", default="8:4:fast:1,8:4:fast:0,8:4:canonical:1,16:6:fast:1", help="lanes per window : resident blocks per SM : epilogue : staged inputs")
     args = ap.parse_args()
     from nucleoatac_b200 import synth
     from nucleoatac_b200.engine import Engine, PackedBatch
