@@ -252,6 +252,9 @@ int64_t nb200_format_track(const char *chrom, int64_t start, const double *vals,
 /* pysam.tabix_compress + pysam.tabix_index(preset="bed") of nucleoatac/run_occ.py:130-136 / run_nuc.py:194-201 in one
  * pass: plain sorted BED / bedgraph -> BGZF file + .tbi.  Pure host code (zlib, `threads` deflate workers). */
 int nb200_bgzip_tabix(const char *path_plain, const char *path_gz, int threads, char *err, int errcap);
+/* The same with a deflate level: -1 = zlib's default (what htslib / pysam.tabix_compress write with: byte-identical files),
+ * 1..9 as zlib.  The .tbi does not depend on the level. */
+int nb200_bgzip_tabix_level(const char *path_plain, const char *path_gz, int threads, int level, char *err, int errcap);
 
 /* ---- host-side BAM decode ------------------------------------------------------------------ */
 /* The reads the path consumes -- pysam AlignmentFile.fetch + `is_proper_pair and not is_reverse` of

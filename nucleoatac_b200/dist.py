@@ -94,14 +94,19 @@ class ShardWriter:
     def __init__(self, path, rank, world):
         self.final, self.world, self.rank = path, world, rank
         self.path = path if world == 1 else "%s.rank%d" % (path, rank)
-        self.fh = open(self.path, "w")
+        self.fh = open(self.path, "wb")
         self.offsets = []
+        self.pos = 0
 
     def write(self, text):
-        self.fh.write(text)
+        self.write_bytes(text.encode())
+
+    def write_bytes(self, data):
+        self.fh.write(data)
+        self.pos += len(data)
 
     def end_chunk(self):
-        self.offsets.append(self.fh.tell())
+        self.offsets.append(self.pos)
 
     def close(self):
         self.fh.close()
@@ -127,6 +132,39 @@ class ShardWriter:
             fh.close()
             os.remove("%s.rank%d" % (path, r))
             os.remove("%s.rank%d.idx" % (path, r))
+
+
+class BatchWriter:
+    """Host side of the drivers' chunk loop: the outputs of a scored batch are formatted on a pool of threads (the native
+    formatter releases the GIL) and written in chunk order by one background thread while the next batch is being scored.
+    The reference does the same with writer processes behind queues (run_occ.py:103-116, run_nuc.py:166-182).  At most one
+    batch is being written while one is scored; an exception of the writer surfaces at the next submit() or at close().
+    The background thread must not touch the device engine (calls on a context are serialised by the caller)."""
+
+    def __init__(self, threads=None):
+        from concurrent.futures import ThreadPoolExecutor
+        self.fmt = ThreadPoolExecutor(max(1, threads or min(16, os.cpu_count() or 1)))
+        self.bg = ThreadPoolExecutor(1)
+        self.prev = None
+
+    def map(self, fn, jobs):
+        return list(self.fmt.map(fn, jobs))
+
+    def submit(self, fn, *args):
+        self.drain()
+        self.prev = self.bg.submit(fn, *args)
+
+    def drain(self):
+        prev, self.prev = self.prev, None
+        if prev is not None:
+            prev.result()
+
+    def close(self):
+        try:
+            self.drain()
+        finally:
+            self.bg.shutdown(wait=True)
+            self.fmt.shutdown(wait=True)
 
 
 def bind_to_gpu_numa(device=0):

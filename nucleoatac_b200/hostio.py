@@ -83,12 +83,17 @@ def bgzip_file(src, dst):
     w.close()
 
 
-def bgzip_tabix(path_plain, path_gz, threads=None):
-    """BGZF-compress a sorted BED / bedgraph and write its .tbi in one native pass (nb200_bgzip_tabix)."""
+def bgzip_tabix(path_plain, path_gz, threads=None, level=None):
+    """BGZF-compress a sorted BED / bedgraph and write its .tbi in one native pass (nb200_bgzip_tabix_level).  `level`: deflate
+    level, default -1 = zlib's default, which is what pysam.tabix_compress writes with (byte-identical files); the environment
+    variable NB200_GZ_LEVEL (1..9) sets it for a whole run -- level 1 is about five times faster on bedgraph text for ~7 %
+    larger files, same rows, same index."""
     import ctypes as C
     from . import _lib
+    if level is None:
+        level = int(os.environ.get("NB200_GZ_LEVEL", "-1"))
     err = C.create_string_buffer(256)
-    st = _lib.load().nb200_bgzip_tabix(path_plain.encode(), path_gz.encode(), int(threads or min(16, os.cpu_count() or 1)), err, 256)
+    st = _lib.load().nb200_bgzip_tabix_level(path_plain.encode(), path_gz.encode(), int(threads or min(16, os.cpu_count() or 1)), int(level), err, 256)
     if st != 0:
         raise IOError("bgzip/tabix of %s failed: %s" % (path_plain, err.value.decode()))
     return path_gz

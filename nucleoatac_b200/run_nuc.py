@@ -42,26 +42,35 @@ def run_nuc(args, score=process_chunks):
     handles = {n: dist.ShardWriter(args.out + "." + n + ext(n), rank, world) for n in outputs}
     mine = ChunkList(*dist.shard(chunks, rank, world))
     batch = max(1, getattr(args, "batch", 256))
-    for group in mine.split(items=batch):
-        nucs = [NucChunk(c) for c in group]
-        try:
-            score(nucs, params)
-        except Exception:
-            print("Caught exception when processing:\n" + ChunkList(*group).asBed() + "\n")
-            raise
-        for nc in nucs:  # run_nuc.py:30-32: what _nucHelper returns per chunk
+    bw = dist.BatchWriter()
+    tracks = [("nucleoatac_signal", "norm_signal"), ("nucleoatac_signal.smooth", "smoothed")]
+    if args.write_all:
+        tracks += [("nucleoatac_background", "bias"), ("nucleoatac_raw", "nuc_signal")]
+
+    def write_batch(nucs):   # behind the scoring of the next batch; host data only.  run_nuc.py:30-32: what _nucHelper returns per chunk
+        texts = bw.map(lambda j: getattr(j[0], j[1]).format_track(), [(nc, attr) for nc in nucs for _, attr in tracks])
+        for i, nc in enumerate(nucs):
             for k in sorted(int(x) for x in nc.nonredundant):
                 nc.nuc_collection[k].write(handles["nucpos"])
             for k in sorted(int(x) for x in nc.redundant):
                 nc.nuc_collection[k].write(handles["nucpos.redundant"])
-            nc.norm_signal.write_track(handles["nucleoatac_signal"])
-            nc.smoothed.write_track(handles["nucleoatac_signal.smooth"])
-            if args.write_all:
-                nc.bias.write_track(handles["nucleoatac_background"])
-                nc.nuc_signal.write_track(handles["nucleoatac_raw"])
+            for t, (name, _) in enumerate(tracks):
+                handles[name].write_bytes(texts[len(tracks) * i + t])
             for h in handles.values():
                 h.end_chunk()
             nc.removeData()
+
+    try:
+        for group in mine.split(items=batch):
+            nucs = [NucChunk(c) for c in group]
+            try:
+                score(nucs, params)
+            except Exception:
+                print("Caught exception when processing:\n" + ChunkList(*group).asBed() + "\n")
+                raise
+            bw.submit(write_batch, nucs)
+    finally:
+        bw.close()
     for h in handles.values():
         h.close()
     dist.barrier(world)

@@ -55,23 +55,32 @@ def run_occ(args, score=process_chunks, count_sizes=getFragmentSizesFromChunkLis
     peaks_writer = dist.ShardWriter(args.out + ".occpeaks.bed", rank, world)
     nuc_dist = np.zeros(args.upper)
     batch = max(1, getattr(args, "batch", 256))
-    for group in mine.split(items=batch):
-        occs = [OccChunk(c) for c in group]
-        try:
-            score(occs, params)
-        except Exception:
-            print("Caught exception when processing:\n" + ChunkList(*group).asBed() + "\n")
-            raise
-        for oc in occs:
-            nuc_dist += oc.getNucDist()
-            oc.occ.write_track(writers[0], vals=oc.occ.smoothed_vals)
-            oc.occ.write_track(writers[1], vals=oc.occ.smoothed_lower)
-            oc.occ.write_track(writers[2], vals=oc.occ.smoothed_upper)
-            for i in sorted(oc.peaks.keys()):
-                oc.peaks[i].write(peaks_writer)
+    bw = dist.BatchWriter()
+
+    def write_batch(occs):   # behind the scoring of the next batch; host data only
+        jobs = [(oc.occ, v) for oc in occs for v in (oc.occ.smoothed_vals, oc.occ.smoothed_lower, oc.occ.smoothed_upper)]
+        texts = bw.map(lambda j: j[0].format_track(vals=j[1]), jobs)
+        for i, oc in enumerate(occs):
+            nuc_dist[:] += oc.getNucDist()
+            for t in range(3):
+                writers[t].write_bytes(texts[3 * i + t])
+            for k in sorted(oc.peaks.keys()):
+                oc.peaks[k].write(peaks_writer)
             for w in writers + [peaks_writer]:
                 w.end_chunk()
             oc.removeData()
+
+    try:
+        for group in mine.split(items=batch):
+            occs = [OccChunk(c) for c in group]
+            try:
+                score(occs, params)
+            except Exception:
+                print("Caught exception when processing:\n" + ChunkList(*group).asBed() + "\n")
+                raise
+            bw.submit(write_batch, occs)
+    finally:
+        bw.close()
     for w in writers + [peaks_writer]:
         w.close()
     nuc_dist = dist.allreduce_sum(nuc_dist, world)  # run_occ.py:117-121 summed over the shards

@@ -395,3 +395,30 @@ def test_bgzip_tabix_streams_in_waves(tmp_path):
     got = list(hostio.TabixFile(str(tmp_path / "t1.bedgraph.gz")).fetch("chr2", 1000, 1200))
     exp = [r for r in rows[130000:] if 1000 <= int(r.split("\t")[1]) < 1200]
     assert [("\t".join(g) if isinstance(g, (list, tuple)) else g) for g in got] == exp and len(exp) > 3
+
+
+def test_bgzip_tabix_level(tmp_path, monkeypatch):
+    """nb200_bgzip_tabix_level: the default level (-1) writes the file nb200_bgzip_tabix writes (pysam.tabix_compress's level,
+    run_occ.py:130-136); level 1 (also through NB200_GZ_LEVEL) writes other bytes that inflate to the same rows and answer
+    the same region queries; a level outside -1, 1..9 is an error."""
+    rng = np.random.RandomState(5)
+    rows = ["chr1\t%d\t%d\t%s" % (100 + k, 101 + k, repr(float(rng.rand()))) for k in range(60000)]
+    text = "\n".join(rows) + "\n"
+    plain = tmp_path / "l.bedgraph"
+    plain.write_text(text)
+    gz = lambda name: str(tmp_path / name)
+    hostio.bgzip_tabix(str(plain), gz("d.gz"), threads=2)
+    hostio.bgzip_tabix(str(plain), gz("m1.gz"), threads=2, level=-1)
+    hostio.bgzip_tabix(str(plain), gz("l1.gz"), threads=2, level=1)
+    monkeypatch.setenv("NB200_GZ_LEVEL", "1")
+    hostio.bgzip_tabix(str(plain), gz("e1.gz"), threads=3)
+    monkeypatch.delenv("NB200_GZ_LEVEL")
+    rd = lambda name: open(gz(name), "rb").read()
+    assert rd("d.gz") == rd("m1.gz") and rd("d.gz.tbi") == rd("m1.gz.tbi")
+    assert rd("l1.gz") == rd("e1.gz") and rd("l1.gz") != rd("d.gz") and len(rd("l1.gz")) > len(rd("d.gz"))
+    assert gzip.open(gz("l1.gz"), "rt").read() == text
+    q = lambda name: list(hostio.TabixFile(gz(name)).fetch("chr1", 30000, 30050))
+    assert q("l1.gz") == q("d.gz") and len(q("d.gz")) == 50
+    for bad in (0, 10, -2):
+        with pytest.raises(IOError):
+            hostio.bgzip_tabix(str(plain), gz("bad.gz"), level=bad)

@@ -127,3 +127,70 @@ def test_shard_writer_merge(tmp_path):
     dist.ShardWriter.merge(str(tmp_path / "x.txt"), world, n)
     assert open(str(tmp_path / "x.txt")).read() == "".join("chunk%d\n" % k * (k % 3) for k in range(n))
     assert dist.shard(list(range(7)), 1, 3) == [1, 4]
+
+
+def test_run_nuc_driver_writes_batches_in_chunk_order(files, tmp_path):
+    """The host side of `nucleoatac nuc` (run_nuc.py:141-201) around an injected scorer: batches of two chunks, tracks
+    formatted on the writer pool behind the scoring of the next batch, rows and calls in chunk order, all six outputs
+    (--write_all) bgzipped + indexed; a scorer that fails surfaces as the run's exception."""
+    import gzip
+    from nucleoatac_b200.cli import build_parser
+    from nucleoatac_b200.NucleosomeCalling import Nucleosome
+    from nucleoatac_b200.run_nuc import run_nuc
+    from nucleoatac_b200.tracks import Track
+    out = str(tmp_path / "n")
+    args = build_parser().parse_args(["nuc", "--bed", files["bed"], "--bam", files["bam"], "--fasta", files["fasta"], "--vmat", files["vmat"],
+                                      "--sizes", files["sizes"], "--out", out, "--batch", "2", "--write_all"])
+    seen = []
+
+    def track(nc, seed):
+        rng = np.random.RandomState(seed + nc.start)
+        v = np.round(rng.rand(nc.end - nc.start), 1)      # runs of equal values
+        v[rng.rand(len(v)) < 0.05] = np.nan
+        return Track(nc.chrom, nc.start, nc.end, vals=v)
+
+    def score(nucs, params):
+        seen.append([nc.start for nc in nucs])
+        for nc in nucs:
+            nc.norm_signal, nc.smoothed, nc.bias, nc.nuc_signal = (track(nc, s) for s in (1, 2, 3, 4))
+            nc.nuc_cov = nc.nfr_cov = track(nc, 5)
+            calls = [nc.start + 100, nc.start + 300, nc.start + 450]
+            nc.nuc_collection = {p: Nucleosome(p, nc) for p in calls}
+            nc.nonredundant, nc.redundant = np.array(calls[::2]), np.array(calls[1:2])
+    run_nuc(args, score=score)
+    assert [len(g) for g in seen] == [2, 2, 1]
+    starts = [s for g in seen for s in g]
+    assert starts == sorted(starts)
+    rd = lambda suffix: gzip.open(out + suffix, "rt").read()
+    for suffix, seed in ((".nucleoatac_signal.bedgraph.gz", 1), (".nucleoatac_signal.smooth.bedgraph.gz", 2),
+                         (".nucleoatac_background.bedgraph.gz", 3), (".nucleoatac_raw.bedgraph.gz", 4)):
+        exp = ""
+        for s in starts:
+            rng = np.random.RandomState(seed + s)
+            end = dict(seen_spans(files))[s]
+            v = np.round(rng.rand(end - s), 1)
+            v[rng.rand(len(v)) < 0.05] = np.nan
+            exp += ra.write_track("chrS", s, end, v)
+        assert rd(suffix) == exp, suffix
+        assert os.path.exists(out + suffix + ".tbi")
+    pos = [int(r.split("\t")[1]) for r in rd(".nucpos.bed.gz").splitlines()]
+    assert pos == [p for s in starts for p in (s + 100, s + 450)]
+    assert [int(r.split("\t")[1]) for r in rd(".nucpos.redundant.bed.gz").splitlines()] == [s + 300 for s in starts]
+    assert not [f for f in os.listdir(str(tmp_path)) if f.endswith(".bedgraph") or f.endswith(".bed")]
+
+    def failing(nucs, params):
+        if len(seen) >= 4:
+            raise RuntimeError("scorer failed")
+        score(nucs, params)
+    with pytest.raises(RuntimeError, match="scorer failed"):
+        run_nuc(args, score=failing)
+
+
+def seen_spans(files):
+    """(start, end) of the chunks the nuc driver makes of the fixture's BED (slop by nuc_sep // 2, merged)."""
+    from nucleoatac_b200.cli import build_parser
+    from nucleoatac_b200.run_nuc import nuc_chunks
+    from nucleoatac_b200.VMat import VMat
+    args = build_parser().parse_args(["nuc", "--bed", files["bed"], "--bam", files["bam"], "--fasta", files["fasta"], "--vmat", files["vmat"],
+                                      "--sizes", files["sizes"], "--out", "x"])
+    return [(c.start, c.end) for c in nuc_chunks(args, VMat.open(files["vmat"]))]
