@@ -46,9 +46,21 @@ class FragmentMixDistribution:
         score = np.ones(boundaries[0] + 1) * float("inf")
         param = [0] * (boundaries[0] + 1)
         pranges = ((0.01, 10), (0.01, 150), (0.01, 1))
+        # optimize.brute(f, pranges, finish=optimize.fmin) as the reference calls it = the 20 x 20 x 20 grid of the ranges
+        # (end points included), its first minimum, then Nelder-Mead from there.  The grid's 8000 objective values are the
+        # same element-by-element arithmetic evaluated on arrays instead of 8000 Python calls per offset (3 s of a run's
+        # fixed cost); the polish is scipy's own.
+        axes = [np.linspace(lo, hi, 20) for lo, hi in pranges]
+        K, TH, A = (g.reshape(-1, 1) for g in np.meshgrid(*axes, indexing="ij"))
         for i in range(15, boundaries[0] + 1):
-            res = optimize.brute(lambda p: np.sum((gamma_fit(x, i, p) - y) ** 2), pranges, full_output=True,
-                                 finish=optimize.fmin)
+            f = lambda p: np.sum((gamma_fit(x, i, p) - y) ** 2)
+            xm = (x - i).astype(np.float64)[None, :]
+            nz = np.where(K >= 1, xm >= 0, xm > 0)
+            with np.errstate(all="ignore"):
+                vals = A * np.where(nz, xm, 1.0) ** (K - 1) * np.exp(-np.where(nz, xm, 1.0) / TH) / (TH ** K * gamma(K))
+            J = np.array([np.sum((row - y) ** 2) for row in np.where(nz, vals, 0.0)])
+            j = int(np.argmin(J))
+            res = optimize.fmin(f, np.array([K[j, 0], TH[j, 0], A[j, 0]]), full_output=1, disp=0)
             score[i], param[i] = res[1], res[0]
         which = int(np.argmin(score))
         self.nfr_fit0 = FragmentSizes(self.lower, self.upper, vals=gamma_fit(np.arange(self.lower, self.upper), which, param[which]))

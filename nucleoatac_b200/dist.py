@@ -17,12 +17,12 @@ def shard(items, rank, world):
 
 
 def _dist():
-    try:
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
-            return dist
-    except ImportError:
-        pass
+    """torch.distributed if a process group is up.  A group can only exist if somebody imported torch.distributed: a
+    single-rank run never pays for the import (several seconds on a cold start, more than scoring a genome)."""
+    import sys
+    dist = sys.modules.get("torch.distributed")
+    if dist is not None and dist.is_available() and dist.is_initialized():
+        return dist
     return None
 
 
