@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(WS_WIN) k_occ_winsums(const int64_t *__restric
 // so it is a factor of the likelihood that does not depend on alpha: it drops out of the argmax and of the likelihood
 // ratios 2*(max - ll).  What a window needs from the bias model is only SN and SF (sums of the per-column sums cn, cf).
 // ll[a] = sum_f log(v_f(a)) is evaluated as log(prod_f v_f) with every factor pre-scaled by a power of two (again constant
-// in alpha) and the running product renormalised every 32 factors: one log per alpha instead of one per (alpha, fragment).
+// in alpha) and the running product renormalised every 64 factors: no logarithm at all, the argmax and the interval test
+// compare the products (epilogues below).
 #define MLE_WARPS 4
 #define MLE_GROUPS 4
 #ifndef MLE_ITERS
@@ -446,7 +447,7 @@ __global__ void __launch_bounds__(MLE_WARPS * 32, LB) k_occ_mle(OccMleArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Guarded search over the alpha grid (the default occupancy kernel).
+// Guarded search over the alpha grid (NB200_MLE_SEARCH=group; the scan k_occ_mle above is the default: it is faster).
 //
 // log L(alpha) = sum_f log(q_f + alpha (p_f - q_f)) is concave in alpha, so (a) the first maximum over the grid lies strictly
 // between the neighbours of the best point of any coarser sub-grid and (b) the grid points passing the likelihood-ratio
