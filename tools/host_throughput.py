@@ -45,9 +45,11 @@ def main():
     out = dict(cores=len(os.sched_getaffinity(0)), regions=len(regions), region_bp=11000)
     bam.fetch_fragments_many(regions[:2])                       # load the library
     for th in (1, out["cores"]):
-        t = time.perf_counter()
-        off, pos, tlen = bam.fetch_fragments_many(regions, threads=th)
-        dt = time.perf_counter() - t
+        dt = 1e30
+        for _ in range(3):   # best of three: the first calls on shared cores are several times slower than the rest
+            t = time.perf_counter()
+            off, pos, tlen = bam.fetch_fragments_many(regions, threads=th)
+            dt = min(dt, time.perf_counter() - t)
         out["bam_decode_Mfrag_s_%dthr" % th] = round(len(pos) / dt / 1e6, 2)
         out["bam_decode_Mbp_s_%dthr" % th] = round(len(regions) * 10000 / dt / 1e6, 1)
     t = time.perf_counter()
