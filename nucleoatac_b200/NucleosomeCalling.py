@@ -118,9 +118,8 @@ class Nucleosome(Chunk):
         except Exception:
             self.occ = self.occ_lower = self.occ_upper = np.nan
 
-    def getFuzz(self, nuctrack):
-        """Fit 1-3 gaussians to the smoothed signal around the call (NucleosomeCalling.py:137-194); host scipy."""
-        from scipy import optimize
+    def fuzz_job(self, nuctrack):
+        """What the fuzziness fit of this call needs (NucleosomeCalling.py:137-194): (left edge, job for fuzz.fit_fuzz)."""
         sep = nuctrack.params.nonredundant_sep
         index = self.start - nuctrack.start
         allnucs = nuctrack.sorted_nuc_keys
@@ -135,23 +134,17 @@ class Nucleosome(Chunk):
         else:
             right = index + sep // 3 + 1
         sig = nuctrack.smoothed.vals[left:right]
-        sig[sig < 0] = 0
-        bounds, guesses = (), ()
-        for m in means:
-            bounds += ((2 ** 2, 50 ** 2), (0.001, max(sig) * 1.1), (m - 10, m + 10))
-            guesses += (nuctrack.params.smooth_sd ** 2, max(sig) * 0.9, m)
+        sig[sig < 0] = 0          # in place, like the reference: later fits of the chunk see the clipped signal
+        return int(left), (np.array(sig), tuple(int(m) for m in means), nuctrack.params.smooth_sd)
 
-        def err(pars, y):
-            xs = np.linspace(0, len(y) - 1, len(y))
-            fit = np.zeros(len(y))
-            for j in range(len(pars) // 3):
-                fit += norm(xs, pars[3 * j], pars[3 * j + 1], pars[3 * j + 2])
-            return sum((fit - y) ** 2)
+    def set_fuzz(self, left, res):
+        self.fuzz, self.weight, self.fit_pos = res[0], res[1], res[2] + left
 
-        res = optimize.minimize(err, guesses, args=(sig,), bounds=bounds, method="L-BFGS-B")
-        self.fuzz = np.sqrt(res["x"][0])
-        self.weight = res["x"][1]
-        self.fit_pos = res["x"][2] + left
+    def getFuzz(self, nuctrack):
+        """Fit 1-3 gaussians to the smoothed signal around the call (NucleosomeCalling.py:137-194); host scipy."""
+        from . import fuzz
+        left, job = self.fuzz_job(nuctrack)
+        self.set_fuzz(left, fuzz.fit_fuzz(job))
 
     def asBed(self):
         return "\t".join([self.chrom, str(self.start), str(self.end)] + [fmt12(getattr(self, k, np.nan)) for k in (
@@ -288,15 +281,29 @@ class NucChunk(Chunk):
                                          self.params.nonredundant_sep)
         self.redundant = np.setdiff1d(self.sorted_nuc_keys, self.nonredundant)
 
-    def fit(self):
+    def fuzz_jobs(self):
+        """(left edges, jobs) of all calls of the chunk in key order (the clipping of the signal is order dependent)."""
+        lefts, jobs = [], []
+        for k in self.sorted_nuc_keys:
+            left, job = self.nuc_collection[int(k)].fuzz_job(self)
+            lefts.append(left)
+            jobs.append(job)
+        return lefts, jobs
+
+    def set_fits(self, lefts, results):
         x = np.linspace(0, self.length() - 1, self.length())
         fit = np.zeros(self.length())
-        for k in self.sorted_nuc_keys:
+        for k, left, res in zip(self.sorted_nuc_keys, lefts, results):
             nuc = self.nuc_collection[int(k)]
-            nuc.getFuzz(self)
+            nuc.set_fuzz(left, res)
             fit += norm(x, nuc.fuzz ** 2, nuc.weight, nuc.fit_pos)
         self.fitted = Track(self.chrom, self.start, self.end, "Fitted Nucleosome Signal")
         self.fitted.assign_track(fit)
+
+    def fit(self):
+        from . import fuzz
+        lefts, jobs = self.fuzz_jobs()
+        self.set_fits(lefts, fuzz.fit_many(jobs))
 
     def makeInsertionTrack(self):
         """Fragment-end counts over the chunk (mat.getIns(), NucleosomeCalling.py:325-327) straight from the reads."""
@@ -369,5 +376,13 @@ def process_chunks(nuc_chunks, params, fit=True):
     out = eng.process_nuc(pb)
     for j, nc in enumerate(nuc_chunks):
         nc.params = params
-        nc._fill(out, pb, j, fit=fit)
+        nc._fill(out, pb, j, fit=False)
+    if fit:   # the fuzziness fits of the whole batch go to the worker pool in one map
+        from . import fuzz
+        per_chunk = [nc.fuzz_jobs() for nc in nuc_chunks]
+        results = fuzz.fit_many([job for _, jobs in per_chunk for job in jobs])
+        at = 0
+        for nc, (lefts, jobs) in zip(nuc_chunks, per_chunk):
+            nc.set_fits(lefts, results[at:at + len(jobs)])
+            at += len(jobs)
     return out

@@ -422,3 +422,34 @@ def test_bgzip_tabix_level(tmp_path, monkeypatch):
     for bad in (0, 10, -2):
         with pytest.raises(IOError):
             hostio.bgzip_tabix(str(plain), gz("bad.gz"), level=bad)
+
+
+def test_fuzz_fits_pool_equals_serial(monkeypatch):
+    """Nucleosome.getFuzz (NucleosomeCalling.py:137-194) as fuzz.fit_fuzz: the fits of a batch on the worker pool are the
+    fits made one by one, value for value; a pool that cannot start falls back to the calling process."""
+    from concurrent.futures.process import BrokenProcessPool
+    from nucleoatac_b200 import fuzz
+    rng = np.random.RandomState(11)
+    jobs = []
+    for k in range(70):
+        n = int(rng.randint(70, 200))
+        x = np.arange(n)
+        m = int(rng.randint(30, n - 30))
+        sig = rng.uniform(0.3, 1.2) * np.exp(-(x - m) ** 2 / (2 * rng.uniform(8, 20) ** 2)) + 0.01 * rng.rand(n)
+        jobs.append((sig, (m,) if k % 3 else (m, min(n - 5, m + 40)), 10))
+    monkeypatch.setenv("NB200_FUZZ_PROCS", "0")
+    serial = fuzz.fit_many(jobs)
+    assert all(2.0 <= f <= 50.0 and w > 0 for f, w, _ in serial)
+    monkeypatch.setenv("NB200_FUZZ_PROCS", "3")
+    try:
+        assert fuzz.fit_many(jobs) == serial
+        assert fuzz._pool is not None
+        assert fuzz.fit_many(jobs[:10]) == serial[:10]          # too few jobs for the pool: fitted here
+    finally:
+        fuzz.close_pool()
+
+    def broken(n):
+        raise BrokenProcessPool("workers did not start")
+    monkeypatch.setattr(fuzz, "_get_pool", broken)
+    monkeypatch.setattr(fuzz, "_broken", False)
+    assert fuzz.fit_many(jobs) == serial and fuzz._broken
