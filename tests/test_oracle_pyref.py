@@ -1,0 +1,88 @@
+"""oracle/ against vectors made by RUNNING THE REFERENCE'S OWN CODE (tests/golden/make_golden_pyref.py: OccChunk.process,
+NucChunk.process and ChunkMat2D.get(flip=True) loaded from /root/reference through a Python-2 compatibility loader) on
+chunks of the synthetic workload -- inputs other than the shipped example.  Grid values, peaks, calls and everything
+integer-valued must be equal; floating-point tracks are the same numpy operations and come out equal to the last bit
+(held to 1e-12); the fuzziness fit is scipy's optimiser in both (1e-6)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import refalgo as ra, refnuc, refocc, refpyatac
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pyref_synth.npz")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+def _case(gold, ci):
+    from nucleoatac_b200 import synth
+    k, length, density = gold["cases"][ci]
+    margin = int(gold["seq_margin"])
+    s, e, pos, tlen, seq, s0 = synth.make_chunk(int(k), length=int(length), density=float(density), seq_margin=margin)
+    return synth.Workload(251, 251), s, e, pos, tlen, bytes(seq).decode(), s0
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2])
+def test_occ_chunk_equals_reference_run(gold, ci):
+    """OccChunk.process + getNucDist (nucleoatac/Occupancy.py:195-253) as the reference itself computed them."""
+    wl, s, e, pos, tlen, sq, s0 = _case(gold, ci)
+    op = refocc.OccParams(wl.nuc_probs, wl.nfr_probs, upper=wl.upper)
+    span = refocc.occ_bias_track_span(s, e, op)
+    bt = ra.log_bias_track(sq[span[0] - 10 - s0:span[1] + 10 - s0], wl.pwm, wl.nucleotides)
+    r = refocc.process_occ_chunk(pos, tlen, s, e, op, bias_track=bt, bias_track_start=span[0])
+    p = "c%d_" % ci
+    for mine, ref in (("vals", "occ_vals"), ("lower_bound", "occ_lower"), ("upper_bound", "occ_upper")):
+        assert np.array_equal(r[mine], gold[p + ref], equal_nan=True), mine         # grid points: equal or it is a different answer
+    assert np.array_equal(r["cov"], gold[p + "occ_cov"])
+    for mine, ref in (("smoothed_vals", "occ_smoothed_vals"), ("smoothed_lower", "occ_smoothed_lower"), ("smoothed_upper", "occ_smoothed_upper")):
+        assert np.array_equal(np.isnan(r[mine]), np.isnan(gold[p + ref])), mine
+        np.testing.assert_allclose(r[mine], gold[p + ref], rtol=1e-12, atol=0, equal_nan=True, err_msg=mine)
+    assert [t[0] for t in r["peaks"]] == list(gold[p + "occ_peak_pos"]) and len(r["peaks"]) > 0
+    np.testing.assert_allclose(np.array([t[1:] for t in r["peaks"]], dtype=np.float64), gold[p + "occ_peak_stats"], rtol=1e-12)
+    np.testing.assert_allclose(r["nuc_dist"], gold[p + "occ_nuc_dist"], rtol=1e-12, atol=1e-15)
+    if ci == 2:
+        assert np.isnan(gold[p + "occ_vals"]).sum() > 100     # the sparse chunk has windows without fragments
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2])
+def test_nuc_chunk_equals_reference_run(gold, ci):
+    """NucChunk.process (nucleoatac/NucleosomeCalling.py:328-340): tracks, calls, z (the reference's own compiled
+    calculateCov in both), likelihood ratio, fuzziness."""
+    wl, s, e, pos, tlen, sq, s0 = _case(gold, ci)
+    par = refnuc.NucParams((wl.vmat, wl.v_lower, wl.v_upper), wl.fragmentsizes, sd=10)
+    _, _, span = refnuc.nuc_geometry(s, e, par)
+    bt = ra.log_bias_track(sq[span[0] - 10 - s0:span[1] + 10 - s0], wl.pwm, wl.nucleotides)
+    r = refnuc.process_nuc_chunk(pos, tlen, s, e, par, bias_track=bt, bias_track_start=span[0], fit=True)
+    p = "c%d_" % ci
+    assert np.array_equal(r["nuc_cov"], gold[p + "nuc_nuc_cov"]) and np.array_equal(r["nfr_cov"], gold[p + "nuc_nfr_cov"])
+    for mine, ref in (("nuc_signal", "nuc_signal"), ("bias", "nuc_background"), ("norm_signal", "nuc_norm_signal"), ("smoothed", "nuc_smoothed")):
+        # same numpy operations; the smoothed track is clipped in place by the reference's getFuzz where calls exist
+        a, b = r[mine], gold[p + ref]
+        if mine == "smoothed":
+            a, b = np.maximum(a, 0), np.maximum(b, 0)
+        np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-15, err_msg=mine)
+    keys = sorted(r["nuc_collection"].keys())
+    assert [k + s for k in keys] == list(gold[p + "nuc_call_pos"])
+    assert sorted(int(k) + s for k in r["nonredundant"]) == list(gold[p + "nuc_nonredundant"])
+    assert sorted(int(k) + s for k in r["redundant"]) == list(gold[p + "nuc_redundant"])
+    cols = ("z", "lr", "norm_signal", "nuc_signal", "nuc_cov", "nfr_cov", "fuzz", "weight", "fit_pos")
+    for row, k in zip(gold[p + "nuc_call_stats"], keys):
+        rec = r["nuc_collection"][k]
+        for c, ref in zip(cols, row):
+            mine = rec[c]                      # fit_pos is relative to the chunk start in the reference as well
+            tol = 1e-6 if c in ("fuzz", "weight", "fit_pos") else 1e-9
+            assert abs(mine - ref) <= tol * max(1.0, abs(ref)), (k, c, mine, ref)
+    if ci == 0:
+        assert len(keys) >= 10
+
+
+def test_chunkmat2d_flip_equals_reference_run(gold):
+    """ChunkMat2D.get(flip=True), pyatac/chunkmat2d.py:41-54 (the strand flip of `pyatac vplot`), on integer matrices."""
+    for fi in range(int(gold["n_flip"])):
+        lower, upper, start, g0, g1, r0, r1 = (int(x) for x in gold["flip%d_args" % fi])
+        got = refpyatac.mat_get(gold["flip%d_mat" % fi], start, lower, r0, r1, g0, g1, flip=True)
+        assert np.array_equal(got, gold["flip%d_out" % fi]), fi
