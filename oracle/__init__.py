@@ -13,5 +13,10 @@ Parity status: PINNED.  ``tests/test_oracle_golden.py`` checks the oracle agains
 test_tracks.py, test_utils.py) and (b) the outputs the reference itself shipped
 in ``example/example_results`` (12 significant digits), via the fixtures under
 ``tests/golden/`` that ``tests/golden/make_golden.py`` extracted in the build
-container (the reference tree does not travel to the GPU box).
+container (the reference tree does not travel to the GPU box), and (c)
+``tests/test_oracle_pyref.py`` against vectors made by RUNNING the reference's own
+``OccChunk.process`` / ``NucChunk.process`` / ``ChunkMat2D.get(flip=True)`` on synthetic
+chunks in the build container (``tests/golden/make_golden_pyref.py``: the reference's
+Python-2 modules loaded through a compatibility loader): occupancy grids, peaks and
+calls equal, every track equal to the last bit.
 """
