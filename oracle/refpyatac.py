@@ -8,7 +8,7 @@ counts of the shipped example.occpeaks.bed.gz (OccChunk.cov at the peaks = the s
 without flip the reference's own known answer (tests/test_chunkmat2d.py:12-17); see tests/test_oracle_pyatac.py.  The reference
 holds NO vector for the strand flip of ChunkMat2D.get (chunkmat2d.py:41-54) nor for `pyatac vplot` as a whole (its only pyatac
 test is a smoke run of `pyatac sizes`, tests/test_cli.py:38-46; example.VMat comes from the bundled S. cer V-plot, not from
-example.bam): the flip below is pinned on vectors made by running the reference's own ChunkMat2D.get(flip=True) in the build
+example.bam): the flip and vplot_site below are pinned on vectors made by running the reference's own ChunkMat2D.get(flip=True) and _vplotHelper in the build
 container (tests/golden/make_golden_pyref.py -> tests/golden/pyref_synth.npz, tests/test_oracle_pyref.py) and checked by its
 mirror-image property.
 """

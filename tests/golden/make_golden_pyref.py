@@ -16,7 +16,8 @@ where they lie under /root/reference (nothing is copied into the repository) thr
   * `nucleoatac.multinomial_cov` = the reference's own .pyx compiled into oracle/_ref (oracle/build.py).
 
 What then runs is the reference's code, unmodified in meaning: `OccChunk.process` (nucleoatac/Occupancy.py:241-248),
-`NucChunk.process` (nucleoatac/NucleosomeCalling.py:328-340) and `ChunkMat2D.get(flip=True)` (pyatac/chunkmat2d.py:21-54)
+`NucChunk.process` (nucleoatac/NucleosomeCalling.py:328-340), `ChunkMat2D.get(flip=True)` (pyatac/chunkmat2d.py:21-54) and
+`_vplotHelper` (pyatac/make_vplot.py:22-43)
 on chunks of the synthetic workload (nucleoatac_b200/synth.py) -- inputs that are not the shipped example.  The vectors
 pin oracle/ (tests/test_oracle_pyref.py) and, through the fixture, the device path (tests/test_gpu_pyref.py).
 """
@@ -205,6 +206,20 @@ def main():
         out["flip%d_args" % fi] = np.array([lower, upper, start, g0, g1, r0, r1], dtype=np.int64)
         flips.append(got.shape)
     out["n_flip"] = np.array(len(flips))
+    # _vplotHelper (pyatac/make_vplot.py:22-43): the aggregate V-plot of a set of stranded sites, plain and --scale
+    sys.modules["VMat"] = M["VMat"]
+    mv = load_py2("pyatac.make_vplot", REF + "/pyatac/make_vplot.py")
+    s, e, pos, tlen, seq, s0 = synth.make_chunk(5, length=6000, density=0.4, seq_margin=SEQ_MARGIN)
+    READS.clear()
+    READS["chrS"] = (pos, tlen)
+    rng = np.random.RandomState(3)
+    sites = [(int(a), int(a + w), st) for a, w, st in zip(rng.randint(s + 400, e - 400, 40), rng.randint(1, 9, 40), rng.choice(["+", "-", "*"], 40))]
+    out["vplot_chunk"] = np.array([5, 6000, 0.4])
+    out["vplot_sites"] = np.array([(a, b, {"+": 1, "-": -1, "*": 0}[st]) for a, b, st in sites], dtype=np.int64)
+    for name, scale in (("vplot_plain", False), ("vplot_scaled", True)):
+        chunks = [Chunk("chrS", a, b, strand=st) for a, b, st in sites]
+        out[name] = mv._vplotHelper((chunks, mv._VplotParams(60, 30, 250, "synthetic.bam", 1, scale)))
+    print("vplot: %d sites, %g fragments in the plain plot" % (len(sites), out["vplot_plain"].sum()))
     np.savez_compressed(os.path.join(HERE, "pyref_synth.npz"), **out)
     print("wrote", os.path.join(HERE, "pyref_synth.npz"), os.path.getsize(os.path.join(HERE, "pyref_synth.npz")), "bytes")
 

@@ -86,3 +86,21 @@ def test_chunkmat2d_flip_equals_reference_run(gold):
         lower, upper, start, g0, g1, r0, r1 = (int(x) for x in gold["flip%d_args" % fi])
         got = refpyatac.mat_get(gold["flip%d_mat" % fi], start, lower, r0, r1, g0, g1, flip=True)
         assert np.array_equal(got, gold["flip%d_out" % fi]), fi
+
+
+def test_vplot_helper_equals_reference_run(gold):
+    """_vplotHelper (pyatac/make_vplot.py:22-43): Chunk.center, the fragment matrix around the site, the strand flip and the
+    per-site scaling, summed over 40 sites of mixed strand and width -- as the reference itself computed them."""
+    from nucleoatac_b200 import synth
+    k, length, density = gold["vplot_chunk"]
+    s, e, pos, tlen, seq, s0 = synth.make_chunk(int(k), length=int(length), density=float(density), seq_margin=int(gold["seq_margin"]))
+    strands = {1: "+", -1: "-", 0: "*"}
+    for name, scale in (("vplot_plain", False), ("vplot_scaled", True)):
+        total = np.zeros((250 - 30, 121))
+        for a, b, st in gold["vplot_sites"]:
+            total += refpyatac.vplot_site(pos, tlen, int(a), int(b), strands[int(st)], 60, 30, 250, atac=True, scale=scale)
+        if scale:
+            np.testing.assert_allclose(total, gold[name], rtol=1e-13, atol=0)
+        else:
+            assert np.array_equal(total, gold[name]) and total.sum() > 1000
+    assert (gold["vplot_sites"][:, 2] == -1).sum() >= 5
