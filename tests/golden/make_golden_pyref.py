@@ -41,6 +41,8 @@ PWM_PATH = REF + "/pyatac/pwm/Human.PWM.txt"
 
 # chunk index, length, density of the synthetic chunks that are scored (nucleoatac_b200/synth.make_chunk)
 CASES = [(2, 10000, 0.25), (7, 3000, 0.25), (11, 2500, 0.02)]
+# further cases for the oracle only (CPU test): chunk, length, density, Tn5 bias model on/off, VMat rows x columns, first size
+CASES2 = [(3, 4000, 0.25, 0, 251, 251, 0), (4, 5000, 0.3, 1, 151, 101, 60), (6, 4000, 0.3, 0, 201, 151, 30)]
 SEQ_MARGIN = 700
 
 
@@ -193,6 +195,36 @@ def main():
                     p + "nuc_nonredundant": np.array(sorted(int(x) + s for x in nc.nonredundant), dtype=np.int64),
                     p + "nuc_redundant": np.array(sorted(int(x) + s for x in nc.redundant), dtype=np.int64)})
         print("case %d (chunk %d, %d bp, density %g): %d occupancy peaks, %d nucleosome calls" % (ci, k, length, density, len(pk), len(keys)))
+    out["cases2"] = np.array(CASES2, dtype=np.float64)
+    for ci, (k, length, density, use_bias, R, W, lower) in enumerate(CASES2):
+        wl2 = synth.Workload(R, W, lower=lower)
+        s, e, pos, tlen, seq, s0 = synth.make_chunk(int(k), length=int(length), density=density, seq_margin=SEQ_MARGIN)
+        GENOME.clear()
+        READS.clear()
+        GENOME["chrS"] = "N" * s0 + bytes(seq).decode() + "N" * 1000
+        READS["chrS"] = (pos, tlen)
+        fasta = "synthetic.fa" if use_bias else None
+        p = "d%d_" % ci
+        if R == 251:   # the occupancy model of the synthetic workload is defined on sizes [0, 251)
+            import pyatac.utils as pu
+            M["Occupancy"].read_chrom_sizes_from_fasta = lambda f: {"chrS": len(GENOME["chrS"])}   # fasta=None: the reference crashes here
+            op = M["Occupancy"].OccupancyParameters(d, 251, fasta, PWM_PATH, bam="synthetic.bam")
+            oc = M["Occupancy"].OccChunk(Chunk("chrS", s, e))
+            oc.process(op)
+            pk = sorted(oc.peaks.keys())
+            out.update({p + "occ_vals": oc.occ.vals, p + "occ_lower": oc.occ.lower_bound, p + "occ_upper": oc.occ.upper_bound,
+                        p + "occ_smoothed_vals": oc.occ.smoothed_vals, p + "occ_cov": oc.cov.vals,
+                        p + "occ_peak_pos": np.array([oc.peaks[x].start for x in pk], dtype=np.int64)})
+        vm = M["VMat"].VMat(wl2.vmat.copy(), wl2.v_lower, wl2.v_upper)
+        npar = M["NucleosomeCalling"].NucParameters(vm, FS(0, wl2.upper, vals=wl2.fragmentsizes.copy()), "synthetic.bam", fasta, PWM_PATH, sd=10)
+        nc = M["NucleosomeCalling"].NucChunk(Chunk("chrS", s, e))
+        nc.process(npar)
+        keys = sorted(nc.nuc_collection.keys())
+        out.update({p + "nuc_signal": nc.nuc_signal.vals, p + "nuc_background": nc.bias.vals, p + "nuc_norm_signal": nc.norm_signal.vals,
+                    p + "nuc_smoothed": nc.smoothed.vals, p + "nuc_nuc_cov": nc.nuc_cov.vals,
+                    p + "nuc_call_pos": np.array([nc.nuc_collection[x].start for x in keys], dtype=np.int64),
+                    p + "nuc_call_zlr": np.array([[nc.nuc_collection[x].z, nc.nuc_collection[x].lr] for x in keys], dtype=np.float64).reshape(len(keys), 2)})
+        print("case2 %d (chunk %d, %d bp, bias %d, VMat %dx%d from size %d): %d nucleosome calls" % (ci, k, length, use_bias, R, W, lower, len(keys)))
     # ChunkMat2D.get with the strand flip (pyatac/chunkmat2d.py:41-54): integer matrices, odd and even first sizes
     rng = np.random.RandomState(7)
     CM = M["chunkmat2d"].ChunkMat2D

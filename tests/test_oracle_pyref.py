@@ -104,3 +104,44 @@ def test_vplot_helper_equals_reference_run(gold):
         else:
             assert np.array_equal(total, gold[name]) and total.sum() > 1000
     assert (gold["vplot_sites"][:, 2] == -1).sum() >= 5
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2])
+def test_other_configurations_equal_reference_run(gold, ci):
+    """The same two reference entry points without a bias model (no --fasta: Occupancy.py:209-211, NucleosomeCalling.py:248)
+    and with V-plots other than 251 x 251 whose first size is not 0 (BASELINE configs[4] shapes)."""
+    from nucleoatac_b200 import synth
+    k, length, density, use_bias, R, W, lower = gold["cases2"][ci]
+    wl = synth.Workload(int(R), int(W), lower=int(lower))
+    s, e, pos, tlen, seq, s0 = synth.make_chunk(int(k), length=int(length), density=float(density), seq_margin=int(gold["seq_margin"]))
+    sq = bytes(seq).decode()
+    p = "d%d_" % ci
+    if int(R) == 251:
+        op = refocc.OccParams(wl.nuc_probs, wl.nfr_probs, upper=251)
+        bt, b0 = None, None
+        if use_bias:
+            span = refocc.occ_bias_track_span(s, e, op)
+            bt, b0 = ra.log_bias_track(sq[span[0] - 10 - s0:span[1] + 10 - s0], wl.pwm, wl.nucleotides), span[0]
+        r = refocc.process_occ_chunk(pos, tlen, s, e, op, bias_track=bt, bias_track_start=b0)
+        for mine, ref in (("vals", "occ_vals"), ("lower_bound", "occ_lower"), ("upper_bound", "occ_upper")):
+            assert np.array_equal(r[mine], gold[p + ref], equal_nan=True), mine
+        assert np.array_equal(r["cov"], gold[p + "occ_cov"])
+        np.testing.assert_allclose(r["smoothed_vals"], gold[p + "occ_smoothed_vals"], rtol=1e-12, equal_nan=True)
+        assert [t[0] for t in r["peaks"]] == list(gold[p + "occ_peak_pos"])
+    par = refnuc.NucParams((wl.vmat, wl.v_lower, wl.v_upper), wl.fragmentsizes, sd=10)
+    bt, b0 = None, None
+    if use_bias:
+        _, _, span = refnuc.nuc_geometry(s, e, par)
+        bt, b0 = ra.log_bias_track(sq[span[0] - 10 - s0:span[1] + 10 - s0], wl.pwm, wl.nucleotides), span[0]
+    r = refnuc.process_nuc_chunk(pos, tlen, s, e, par, bias_track=bt, bias_track_start=b0, fit=False)
+    assert np.array_equal(r["nuc_cov"], gold[p + "nuc_nuc_cov"])
+    for mine, ref in (("nuc_signal", "nuc_signal"), ("bias", "nuc_background"), ("norm_signal", "nuc_norm_signal"), ("smoothed", "nuc_smoothed")):
+        a, b = r[mine], gold[p + ref]
+        if mine == "smoothed":
+            a, b = np.maximum(a, 0), np.maximum(b, 0)
+        np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-15, err_msg=mine)
+    keys = sorted(r["nuc_collection"].keys())
+    assert [k + s for k in keys] == list(gold[p + "nuc_call_pos"])
+    for row, k in zip(gold[p + "nuc_call_zlr"], keys):
+        assert abs(r["nuc_collection"][k]["z"] - row[0]) <= 1e-9 * max(1.0, abs(row[0]))
+        assert abs(r["nuc_collection"][k]["lr"] - row[1]) <= 1e-9 * max(1.0, abs(row[1]))
