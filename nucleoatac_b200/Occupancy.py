@@ -8,7 +8,7 @@ from .bias import PWM, InsertionBiasTrack
 from .chunk import Chunk
 from .chunkmat2d import BiasMat2D, FragmentMat2D
 from .engine import PackedBatch, default_engine
-from .fragments import fetch_reads, fetch_reads_many
+from .fragments import fetch_reads_many
 from .fragmentsizes import FragmentSizes
 from .tracks import CoverageTrack, Track
 from .utils import call_peaks, fmt12, read_chrom_sizes_from_fasta, smooth

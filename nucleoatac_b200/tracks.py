@@ -5,7 +5,7 @@ from .bedgraph import BedGraphFile
 from .chunk import Chunk
 from .engine import default_engine
 from .fragments import getInsertions
-from .utils import fmt12, smooth
+from .utils import smooth
 
 
 class Track(Chunk):

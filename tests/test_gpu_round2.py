@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from oracle import refalgo as ra, refnuc, refocc
+from oracle import refalgo as ra, refnuc
 
 pytestmark = pytest.mark.gpu
 

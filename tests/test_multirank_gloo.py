@@ -10,7 +10,7 @@ import socket
 import numpy as np
 import pytest
 
-from oracle import refalgo as ra, refnuc, refocc
+from oracle import refalgo as ra, refocc
 
 
 def _free_port():
@@ -77,7 +77,6 @@ def _worker(rank, world, port, files, out):
 
 @pytest.fixture(scope="module")
 def files(tmp_path_factory):
-    from nucleoatac_b200 import synth
     from tests.synthfiles import make_files
     d = str(tmp_path_factory.mktemp("mr"))
     f = make_files(d, ks=(0, 1, 2))

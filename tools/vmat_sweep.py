@@ -5,7 +5,6 @@ bf16 peak, and the HBM-side figure (algorithmic bytes of the non-contraction sta
 import json
 import os
 import sys
-import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
