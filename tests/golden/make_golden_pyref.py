@@ -225,6 +225,33 @@ def main():
                     p + "nuc_call_pos": np.array([nc.nuc_collection[x].start for x in keys], dtype=np.int64),
                     p + "nuc_call_zlr": np.array([[nc.nuc_collection[x].z, nc.nuc_collection[x].lr] for x in keys], dtype=np.float64).reshape(len(keys), 2)})
         print("case2 %d (chunk %d, %d bp, bias %d, VMat %dx%d from size %d): %d nucleosome calls" % (ci, k, length, use_bias, R, W, lower, len(keys)))
+    # ChunkList.read -> slop -> merge -> split (pyatac/chunk.py:101-207): what run_occ / run_nuc do with the BED (run_occ.py:83-90)
+    import tempfile
+    rng = np.random.RandomState(13)
+    chroms = {"chrA": 60000, "chrB": 25000, "chrC": 9000}
+    rows = []
+    for c in ("chrA", "chrB", "chrC", "chrUnknown"):
+        at = 0
+        for _ in range(25):
+            at += int(rng.randint(1, 1500))
+            w = int(rng.randint(50, 2500))
+            rows.append((c, at, at + w))                # sorted by start inside a chromosome, many overlaps
+    with tempfile.NamedTemporaryFile("w", suffix=".bed", delete=False) as fh:
+        for r in rows:
+            fh.write("%s\t%d\t%d\n" % r)
+        bed = fh.name
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        cl = M["chunk"].ChunkList.read(bed, chromDict=chroms, min_offset=300, min_length=240)
+    cl.slop(chroms, up=60, down=60)
+    cl.merge()
+    os.remove(bed)
+    out["chunklist_bed"] = np.array([(list(chroms) + ["chrUnknown"]).index(c) for c, _, _ in rows] and
+                                    [((list(chroms) + ["chrUnknown"]).index(c), a, b) for c, a, b in rows], dtype=np.int64)
+    out["chunklist_merged"] = np.array([(list(chroms).index(c.chrom), c.start, c.end) for c in cl], dtype=np.int64)
+    out["chunklist_split3"] = np.array([len(g) for g in cl.split(items=3)], dtype=np.int64)
+    print("chunk list: %d BED rows -> %d merged chunks" % (len(rows), len(cl)))
     # ChunkMat2D.get with the strand flip (pyatac/chunkmat2d.py:41-54): integer matrices, odd and even first sizes
     rng = np.random.RandomState(7)
     CM = M["chunkmat2d"].ChunkMat2D

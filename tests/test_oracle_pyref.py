@@ -145,3 +145,24 @@ def test_other_configurations_equal_reference_run(gold, ci):
     for row, k in zip(gold[p + "nuc_call_zlr"], keys):
         assert abs(r["nuc_collection"][k]["z"] - row[0]) <= 1e-9 * max(1.0, abs(row[0]))
         assert abs(r["nuc_collection"][k]["lr"] - row[1]) <= 1e-9 * max(1.0, abs(row[1]))
+
+
+def test_chunk_list_equals_reference_run(gold, tmp_path):
+    """ChunkList.read -> slop -> merge -> split (pyatac/chunk.py:101-207) on a BED with overlaps, an unknown chromosome and
+    regions near the chromosome ends: the host mirror and the oracle's chunk helpers against the reference's own run."""
+    from nucleoatac_b200.chunk import ChunkList
+    names = ["chrA", "chrB", "chrC", "chrUnknown"]
+    chroms = {"chrA": 60000, "chrB": 25000, "chrC": 9000}
+    bed = tmp_path / "r.bed"
+    bed.write_text("".join("%s\t%d\t%d\n" % (names[c], a, b) for c, a, b in gold["chunklist_bed"]))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        cl = ChunkList.read(str(bed), chromDict=chroms, min_offset=300, min_length=240)
+    cl.slop(chroms, up=60, down=60)
+    cl.merge()
+    want = [(names[c], int(a), int(b)) for c, a, b in gold["chunklist_merged"]]
+    assert [(c.chrom, c.start, c.end) for c in cl] == want and len(want) >= 5
+    assert [len(g) for g in cl.split(items=3)] == list(gold["chunklist_split3"])
+    mine = ra.merge_chunks(ra.slop_chunks(ra.read_bed_chunks(str(bed), chroms, min_offset=300, min_length=240), chroms, 60, 60))
+    assert [tuple(x) for x in mine] == want
