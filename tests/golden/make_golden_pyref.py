@@ -225,6 +225,15 @@ def main():
                     p + "nuc_call_pos": np.array([nc.nuc_collection[x].start for x in keys], dtype=np.int64),
                     p + "nuc_call_zlr": np.array([[nc.nuc_collection[x].z, nc.nuc_collection[x].lr] for x in keys], dtype=np.float64).reshape(len(keys), 2)})
         print("case2 %d (chunk %d, %d bp, bias %d, VMat %dx%d from size %d): %d nucleosome calls" % (ci, k, length, use_bias, R, W, lower, len(keys)))
+    # FragmentMixDistribution.modelNFR (nucleoatac/Occupancy.py:29-66): scipy brute + fmin, on two size distributions
+    np.float = float                    # `np.float('inf')` of the reference (an alias numpy has dropped)
+    for name, vals in (("nfr_synth", wl.fragmentsizes[:251] / wl.fragmentsizes[:251].sum()),
+                       ("nfr_bumpy", (lambda v: v / v.sum())(np.abs(wl.fragmentsizes[:251] * (1 + 0.3 * np.random.RandomState(2).standard_normal(251)))))):
+        fm = M["Occupancy"].FragmentMixDistribution(0, upper=251)
+        fm.fragmentsizes = FS(0, 251, vals=vals.copy())
+        fm.modelNFR()
+        out[name + "_sizes"], out[name + "_nfr_fit"], out[name + "_nuc_fit"] = vals, fm.nfr_fit.get(), fm.nuc_fit.get()
+    print("modelNFR: two fits")
     # ChunkList.read -> slop -> merge -> split (pyatac/chunk.py:101-207): what run_occ / run_nuc do with the BED (run_occ.py:83-90)
     import tempfile
     rng = np.random.RandomState(13)

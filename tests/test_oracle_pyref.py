@@ -166,3 +166,16 @@ def test_chunk_list_equals_reference_run(gold, tmp_path):
     assert [len(g) for g in cl.split(items=3)] == list(gold["chunklist_split3"])
     mine = ra.merge_chunks(ra.slop_chunks(ra.read_bed_chunks(str(bed), chroms, min_offset=300, min_length=240), chroms, 60, 60))
     assert [tuple(x) for x in mine] == want
+
+
+@pytest.mark.parametrize("name", ["nfr_synth", "nfr_bumpy"])
+def test_model_nfr_equals_reference_run(gold, name):
+    """FragmentMixDistribution.modelNFR (nucleoatac/Occupancy.py:29-66) of the host mirror -- the brute-force grid evaluated
+    on arrays, scipy's Nelder-Mead polish -- against the reference's own run of optimize.brute on the same sizes."""
+    from nucleoatac_b200.fragmentsizes import FragmentSizes
+    from nucleoatac_b200.Occupancy import FragmentMixDistribution
+    fm = FragmentMixDistribution(0, upper=251)
+    fm.fragmentsizes = FragmentSizes(0, 251, vals=gold[name + "_sizes"].copy())
+    fm.modelNFR()
+    np.testing.assert_allclose(fm.nfr_fit.get(), gold[name + "_nfr_fit"], rtol=1e-12, atol=0)
+    np.testing.assert_allclose(fm.nuc_fit.get(), gold[name + "_nuc_fit"], rtol=1e-12, atol=0)
