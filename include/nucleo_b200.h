@@ -256,6 +256,11 @@ int nb200_bgzip_tabix(const char *path_plain, const char *path_gz, int threads, 
  * 1..9 as zlib.  The .tbi does not depend on the level. */
 int nb200_bgzip_tabix_level(const char *path_plain, const char *path_gz, int threads, int level, char *err, int errcap);
 
+/* BedGraphFile.read, pyatac/bedgraph.py:6-16 (pysam.Tabixfile.fetch over a bgzip'd bedgraph with a .tbi): out[0 .. end-start) =
+ * `empty`, then the value of every row overlapping [start, end) over the positions it covers.  Pure host code, no context. */
+int nb200_bedgraph_fetch(const char *path_gz, const char *chrom, int64_t start, int64_t end, double empty, double *out, char *err,
+                         int errcap);
+
 /* ---- host-side BAM decode ------------------------------------------------------------------ */
 /* The reads the path consumes -- pysam AlignmentFile.fetch + `is_proper_pair and not is_reverse` of
  * pyatac/fragments.pyx:21-25,47-50,128-131 -- for n_regions regions at once, decoded by `threads` host threads (zlib).

@@ -150,6 +150,7 @@ def load():
     _sig(lib, "nb200_format_track", i64, C.c_char_p, i64, c_double_p, i64, i32, C.c_char_p, i64)
     _sig(lib, "nb200_bgzip_tabix", I, C.c_char_p, C.c_char_p, I, C.c_char_p, I)
     _sig(lib, "nb200_bgzip_tabix_level", I, C.c_char_p, C.c_char_p, I, I, C.c_char_p, I)
+    _sig(lib, "nb200_bedgraph_fetch", I, C.c_char_p, C.c_char_p, i64, i64, dbl, c_double_p, C.c_char_p, I)
     _sig(lib, "nb200_tc_plan_describe", I, c_double_p, I, I, I, c_double_p, I, c_int32_p, c_int32_p, I)
     _sig(lib, "nb200_bam_fetch_many", I, C.c_char_p, i32, C.POINTER(C.c_uint64), c_int32_p, c_int32_p, c_int32_p, i32, c_int64_p,
          C.POINTER(c_int32_p), C.POINTER(c_int32_p), C.c_char_p, I)
@@ -174,7 +175,7 @@ EXPORTS = [
     "nb200_occ_d2h_bytes", "nb200_nuc_d2h_bytes", "nb200_occ_download32", "nb200_nuc_download32", "nb200_occ_d2h_bytes32",
     "nb200_nuc_d2h_bytes32", "nb200_timer_start", "nb200_timer_stop", "nb200_timer_elapsed_ms",
     "nb200_profile_enable", "nb200_profile_reset", "nb200_profile_count", "nb200_profile_get", "nb200_flush_l2",
-    "nb200_format_track", "nb200_bgzip_tabix", "nb200_bgzip_tabix_level", "nb200_tc_plan_describe", "nb200_vplot", "nb200_coverage", "nb200_bam_fetch_many", "nb200_free",
+    "nb200_format_track", "nb200_bgzip_tabix", "nb200_bgzip_tabix_level", "nb200_bedgraph_fetch", "nb200_tc_plan_describe", "nb200_vplot", "nb200_coverage", "nb200_bam_fetch_many", "nb200_free",
     "nb200_nccl_unique_id", "nb200_nccl_init", "nb200_allreduce_f64", "nb200_allreduce_i64", "nb200_nccl_finalize",
 ]
 

@@ -8,6 +8,7 @@
 #include <string.h>
 #include <zlib.h>
 
+#include <charconv>
 #include <map>
 #include <string>
 #include <thread>
@@ -315,3 +316,219 @@ int nb200_bgzip_tabix_level(const char *path_plain, const char *path_gz, int thr
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Region read of a bgzip'd, tabix-indexed bedgraph into a dense array: BedGraphFile.read of pyatac/bedgraph.py:6-16, which the
+// reference does through pysam.Tabixfile.fetch (`--occ_track` of `nucleoatac nuc`, the tracks `nucleoatac nfr` reads).  The
+// linear index of the .tbi gives the block to start from; rows are scanned until the chromosome changes or a row starts at
+// or past `end`.
+namespace {
+
+struct TbiLite {
+    std::vector<std::string> names;
+    std::vector<std::vector<uint64_t>> linear;
+    int sc = 1, bc = 2, ec = 3;
+};
+
+bool load_tbi(const std::string &path, TbiLite &t, std::string &err)
+{
+    gzFile g = gzopen(path.c_str(), "rb");   // BGZF is a multi-member gzip file
+    if (!g) {
+        err = "cannot open the .tbi";
+        return false;
+    }
+    std::vector<unsigned char> raw;
+    unsigned char buf[1 << 16];
+    int n;
+    while ((n = gzread(g, buf, sizeof(buf))) > 0) raw.insert(raw.end(), buf, buf + n);
+    gzclose(g);
+    auto i32 = [&](size_t off, int32_t &v) {
+        if (off + 4 > raw.size()) return false;
+        memcpy(&v, raw.data() + off, 4);
+        return true;
+    };
+    int32_t n_ref = 0, fmt = 0, sc = 0, bc = 0, ec = 0, meta = 0, skip = 0, l_nm = 0;
+    if (raw.size() < 36 || memcmp(raw.data(), "TBI\1", 4) != 0 || !i32(4, n_ref) || !i32(8, fmt) || !i32(12, sc) || !i32(16, bc) || !i32(20, ec) ||
+        !i32(24, meta) || !i32(28, skip) || !i32(32, l_nm) || n_ref < 0 || l_nm < 0 || 36 + (size_t)l_nm > raw.size() || sc < 1 || bc < 1 || ec < 1) {
+        err = "not a tabix index";
+        return false;
+    }
+    t.sc = sc;
+    t.bc = bc;
+    t.ec = ec;
+    size_t off = 36;
+    for (size_t p = off; p < off + (size_t)l_nm;) {
+        const void *z = memchr(raw.data() + p, 0, off + (size_t)l_nm - p);
+        if (!z) break;
+        t.names.emplace_back((const char *)raw.data() + p, (const char *)z);
+        p = (size_t)((const unsigned char *)z - raw.data()) + 1;
+    }
+    off += (size_t)l_nm;
+    for (int r = 0; r < n_ref; r++) {
+        int32_t n_bin = 0;
+        if (!i32(off, n_bin) || n_bin < 0) goto bad;
+        off += 4;
+        for (int b = 0; b < n_bin; b++) {
+            int32_t n_chunk = 0;
+            if (!i32(off + 4, n_chunk) || n_chunk < 0) goto bad;
+            off += 8 + 16 * (size_t)n_chunk;
+        }
+        int32_t n_intv = 0;
+        if (!i32(off, n_intv) || n_intv < 0 || off + 4 + 8 * (size_t)n_intv > raw.size()) goto bad;
+        off += 4;
+        std::vector<uint64_t> lin((size_t)n_intv);
+        if (n_intv) memcpy(lin.data(), raw.data() + off, 8 * (size_t)n_intv);
+        off += 8 * (size_t)n_intv;
+        t.linear.push_back(std::move(lin));
+    }
+    return true;
+bad:
+    err = "truncated tabix index";
+    return false;
+}
+
+// inflate the BGZF block at compressed offset coff into dst (cleared); returns its size on disk, 0 at the end of the file, -1 on error
+long read_bgzf_block(FILE *fh, uint64_t coff, std::vector<unsigned char> &dst)
+{
+    dst.clear();
+    if (fseeko(fh, (off_t)coff, SEEK_SET) != 0) return -1;
+    unsigned char head[18];
+    const size_t got = fread(head, 1, 18, fh);
+    if (got == 0) return 0;
+    if (got < 18 || head[0] != 0x1f || head[1] != 0x8b || head[2] != 8 || head[3] != 4) return -1;
+    const unsigned xlen = head[10] | (head[11] << 8);
+    if (xlen < 6) return -1;
+    std::vector<unsigned char> extra(xlen);
+    memcpy(extra.data(), head + 12, 6);
+    if (xlen > 6 && fread(extra.data() + 6, 1, xlen - 6, fh) != xlen - 6) return -1;
+    long bsize = -1;
+    for (size_t o = 0; o + 4 <= extra.size();) {
+        const unsigned slen = extra[o + 2] | (extra[o + 3] << 8);
+        if (extra[o] == 66 && extra[o + 1] == 67 && o + 6 <= extra.size()) bsize = (long)(extra[o + 4] | (extra[o + 5] << 8)) + 1;
+        o += 4 + slen;
+    }
+    const long clen = bsize - 12 - (long)xlen - 8;
+    if (bsize < 0 || clen < 0) return -1;
+    std::vector<unsigned char> cdata((size_t)clen);
+    if (clen && fread(cdata.data(), 1, (size_t)clen, fh) != (size_t)clen) return -1;
+    dst.resize(65536);
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, -15) != Z_OK) return -1;
+    zs.next_in = cdata.data();
+    zs.avail_in = (uInt)clen;
+    zs.next_out = dst.data();
+    zs.avail_out = (uInt)dst.size();
+    const int rc = inflate(&zs, Z_FINISH);
+    const size_t produced = zs.total_out;
+    inflateEnd(&zs);
+    if (rc != Z_STREAM_END) return -1;
+    dst.resize(produced);
+    return bsize;
+}
+
+}  // namespace
+
+extern "C" int nb200_bedgraph_fetch(const char *path_gz, const char *chrom, int64_t start, int64_t end, double empty, double *out, char *err,
+                                    int errcap)
+{
+    auto fail = [&](const char *msg) {
+        if (err && errcap > 0) snprintf(err, (size_t)errcap, "%s", msg);
+        return 1;
+    };
+    if (!path_gz || !chrom || !out || end < start) return fail("bad argument");
+    const int64_t len = end - start;
+    for (int64_t i = 0; i < len; i++) out[i] = empty;   // np.ones(end - start) * empty, pyatac/bedgraph.py:10
+    TbiLite tbi;
+    std::string e;
+    if (!load_tbi(std::string(path_gz) + ".tbi", tbi, e)) return fail(e.c_str());
+    size_t t = 0;
+    const size_t lc = strlen(chrom);
+    while (t < tbi.names.size() && tbi.names[t] != chrom) t++;
+    if (t >= tbi.names.size() || t >= tbi.linear.size() || tbi.linear[t].empty() || len == 0) return 0;   // nothing on this chromosome
+    const std::vector<uint64_t> &lin = tbi.linear[t];
+    const uint64_t voff = lin[std::min<size_t>((size_t)(std::max<int64_t>(start, 0) >> 14), lin.size() - 1)];
+    FILE *fh = fopen(path_gz, "rb");
+    if (!fh) return fail("cannot open the bedgraph");
+    uint64_t coff = voff >> 16;
+    size_t skip = (size_t)(voff & 0xffff);
+    std::vector<unsigned char> block;
+    std::string line;           // a row may straddle blocks
+    bool matched = false, done = false;
+    const int maxcol = std::max(std::max(tbi.sc, tbi.bc), std::max(tbi.ec, 3));
+    while (!done) {
+        const long size = read_bgzf_block(fh, coff, block);
+        if (size < 0) {
+            fclose(fh);
+            return fail("corrupt BGZF block");
+        }
+        if (size == 0) break;
+        coff += (uint64_t)size;
+        size_t p = std::min(skip, block.size());
+        skip = 0;
+        while (p < block.size() && !done) {
+            const unsigned char *nl = (const unsigned char *)memchr(block.data() + p, '\n', block.size() - p);
+            if (!nl) {
+                line.append((const char *)block.data() + p, block.size() - p);
+                break;
+            }
+            const char *row;
+            size_t rl;
+            if (!line.empty()) {
+                line.append((const char *)block.data() + p, (size_t)(nl - (block.data() + p)));
+                row = line.data();
+                rl = line.size();
+            } else {
+                row = (const char *)block.data() + p;
+                rl = (size_t)(nl - (block.data() + p));
+            }
+            p = (size_t)(nl - block.data()) + 1;
+            // columns
+            const char *col[8] = {nullptr};
+            size_t cl[8] = {0};
+            int nc = 0;
+            for (size_t a = 0; nc < 8;) {
+                const char *tab = (const char *)memchr(row + a, '\t', rl - a);
+                col[nc] = row + a;
+                cl[nc] = tab ? (size_t)(tab - (row + a)) : rl - a;
+                nc++;
+                if (!tab) break;
+                a = (size_t)(tab - row) + 1;
+            }
+            const bool usable = nc >= maxcol && maxcol <= 8 && !(rl > 0 && row[0] == '#');   // short rows and comments are skipped
+            if (usable) {
+                if (cl[tbi.sc - 1] != lc || memcmp(col[tbi.sc - 1], chrom, lc) != 0) {
+                    if (matched) done = true;
+                } else {
+                    int64_t b = 0, en = 0;
+                    if (!parse_i64(col[tbi.bc - 1], col[tbi.bc - 1] + cl[tbi.bc - 1], b) || !parse_i64(col[tbi.ec - 1], col[tbi.ec - 1] + cl[tbi.ec - 1], en)) {
+                        fclose(fh);
+                        return fail("bad coordinate column");
+                    }
+                    if (b >= end)
+                        done = true;
+                    else if (en > start) {
+                        matched = true;
+                        if (nc < 4) {
+                            fclose(fh);
+                            return fail("row without a value column");
+                        }
+                        double v = 0.0;
+                        const char *vb = col[3], *ve = col[3] + cl[3];
+                        while (vb < ve && (*vb == ' ' || *vb == '+')) vb++;
+                        const std::from_chars_result fr = std::from_chars(vb, ve, v);
+                        if (fr.ec != std::errc()) {
+                            fclose(fh);
+                            return fail("bad value column");
+                        }
+                        const int64_t lo = std::max<int64_t>(b - start, 0), hi = std::min<int64_t>(en - start, len);
+                        for (int64_t i = lo; i < hi; i++) out[i] = v;
+                    }
+                }
+            }
+            line.clear();
+        }
+    }
+    fclose(fh);
+    return 0;
+}

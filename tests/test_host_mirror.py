@@ -453,3 +453,40 @@ def test_fuzz_fits_pool_equals_serial(monkeypatch):
     monkeypatch.setattr(fuzz, "_get_pool", broken)
     monkeypatch.setattr(fuzz, "_broken", False)
     assert fuzz.fit_many(jobs) == serial and fuzz._broken
+
+
+def test_native_bedgraph_fetch_equals_python_reader(tmp_path):
+    """nb200_bedgraph_fetch (BedGraphFile.read, pyatac/bedgraph.py:6-16 = pysam.Tabixfile.fetch into a dense array) against the
+    Python tabix reader: run-length rows, gaps (NaN stretches are not written), several chromosomes, regions that start
+    before the first row, straddle a chromosome's last rows, hit nothing, or name an unknown chromosome."""
+    from nucleoatac_b200.bedgraph import BedGraphFile
+    from nucleoatac_b200.tracks import Track
+    rng = np.random.RandomState(9)
+    plain = tmp_path / "b.bedgraph"
+    with open(str(plain), "wb") as fh:
+        for chrom, n in (("chr1", 120000), ("chr2", 40000), ("chrX", 9000)):
+            v = np.round(rng.rand(n), 2)                     # runs of equal values
+            v[rng.rand(n) < 0.02] = np.nan
+            v[5000:7000] = np.nan                            # a long gap
+            v[20000:20600] = 0.0                             # zeros are rows of their own
+            fh.write(Track(chrom, 1000, 1000 + n, vals=v).format_track())
+    gz = str(plain) + ".gz"
+    hostio.bgzip_tabix(str(plain), gz, threads=2)
+    bg = BedGraphFile(gz)
+    assert isinstance(bg.reader, hostio.TabixFile)
+    queries = [("chr1", 0, 3000), ("chr1", 900, 1100), ("chr1", 5500, 6500), ("chr1", 16000, 33500), ("chr1", 65535, 65537), ("chr1", 120500, 122000),
+               ("chr1", 130000, 130100), ("chr2", 1000, 41000), ("chr2", 39990, 41050), ("chrX", 2, 3), ("chrX", 9990, 10010), ("chrNope", 5, 50),
+               ("chr2", 777, 777)]
+    queries += [("chr1", int(a), int(a + w)) for a, w in zip(rng.randint(0, 121000, 12), rng.randint(1, 12000, 12))]
+    n_vals = 0
+    for chrom, a, b in queries:
+        for empty in (np.nan, 0.0):
+            got, want = bg.read(chrom, a, b, empty=empty), bg.read_python(chrom, a, b, empty=empty)
+            assert got.shape == want.shape and np.array_equal(got, want, equal_nan=True), (chrom, a, b, empty)
+        n_vals += int((~np.isnan(got)).sum())
+    assert n_vals > 50000
+    with pytest.raises(IOError):
+        bad = BedGraphFile(gz)                                                # a missing index is an error, not an empty track
+        bad.reader = hostio.TabixFile(gz)
+        bad.reader.path = str(tmp_path / "missing.gz")
+        bad.read("chr1", 0, 10)
