@@ -600,7 +600,7 @@ class TabixFile:
         lin = self.linear[t]
         if not lin:
             return []
-        voff = lin[min(start >> 14, len(lin) - 1)]
+        voff = lin[min(max(start, 0) >> 14, len(lin) - 1)]   # a start left of the chromosome begins at its first window
         coff, uoff = voff >> 16, voff & 0xffff
         out, buf = [], b""
         data, size = _read_block(self.fh, coff)
