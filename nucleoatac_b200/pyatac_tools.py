@@ -82,14 +82,28 @@ def _write_tracks(args, suffix, chunks, make_track):
     rank, world = _rank_world(args)
     path = args.out + suffix + ".bedgraph"
     writer = dist.ShardWriter(path, rank, world)
-    for chunk in dist.shard(chunks, rank, world):
-        try:
-            track = make_track(chunk)
-        except Exception:
-            print("Caught exception when processing:\n" + chunk.asBed() + "\n")
-            raise
-        track.write_track(writer)
-        writer.end_chunk()
+    bw = dist.BatchWriter()
+
+    def write_group(tracks):   # formatted on the pool, written in chunk order, behind the next group's device calls
+        for text in bw.map(lambda t: t.format_track(), tracks):
+            writer.write_bytes(text)
+            writer.end_chunk()
+
+    group = []
+    try:
+        for chunk in dist.shard(chunks, rank, world):
+            try:
+                group.append(make_track(chunk))
+            except Exception:
+                print("Caught exception when processing:\n" + chunk.asBed() + "\n")
+                raise
+            if len(group) >= 64:
+                bw.submit(write_group, group)
+                group = []
+        if group:
+            bw.submit(write_group, group)
+    finally:
+        bw.close()
     writer.close()
     dist.barrier(world)
     if rank == 0:
