@@ -1,5 +1,5 @@
 """Command line: `python -m nucleoatac_b200 occ|nuc|vprocess|merge|nfr|run ...` with the reference's flags (nucleoatac/cli.py:96-125,
-203-240) plus `--gpus`, `--batch` and `--xcor_mode`.  `--cores` is accepted and ignored (the device replaces the pool)."""
+203-240) plus `--gpus`, `--batch` and `--xcor_mode`.  `--cores N` (N > 1) caps the host helper threads / worker processes (the device replaces the scoring pool)."""
 import argparse
 import os
 import time
@@ -18,7 +18,7 @@ def build_parser():
     g.add_argument("--pwm", metavar="Tn5_PWM", default="Human", help="PWM descriptor file. Default is Human.PWM.txt included in package")
     g = occ.add_argument_group("General Options", "")
     g.add_argument("--sizes", metavar="fragmentsizes_file", help="File with fragment size distribution.  Use if don't want calculation of fragment size")
-    g.add_argument("--cores", metavar="int", default=1, type=int, help="Number of cores to use (ignored: chunks are scored on the GPU)")
+    g.add_argument("--cores", metavar="int", default=1, type=int, help="Number of cores to use: chunks are scored on the GPU; a value above 1 caps the host helpers (decode / format / deflate threads, fit workers)")
     g = occ.add_argument_group("Occupancy parameter", "Change with caution")
     g.add_argument("--upper", metavar="int", default=251, type=int, help="upper limit in insert size. default is 251")
     g.add_argument("--flank", metavar="int", default=60, type=int, help="Distance on each side of dyad to include for local occ calculation. Default is 60.")
@@ -38,7 +38,7 @@ def build_parser():
     g = nuc.add_argument_group("General options", "")
     g.add_argument("--sizes", metavar="fragmentsizes_file", help="File with fragment size distribution.  Use if don't want calculation of fragment size")
     g.add_argument("--occ_track", metavar="occ_file", help="bgzip compressed bedgraph file with occcupancy track. Otherwise occ not determined for nuc positions.")
-    g.add_argument("--cores", metavar="num_cores", default=1, type=int, help="Number of cores to use (ignored: chunks are scored on the GPU)")
+    g.add_argument("--cores", metavar="num_cores", default=1, type=int, help="Number of cores to use: chunks are scored on the GPU; a value above 1 caps the host helpers (decode / format / deflate threads, fit workers)")
     g.add_argument("--write_all", action="store_true", default=False, help="write all tracks")
     g.add_argument("--not_atac", dest="atac", action="store_false", default=True, help="data is not atac-seq")
     g = nuc.add_argument_group("Nucleosome calling parameters", "Change with caution")
@@ -110,6 +110,8 @@ def build_parser():
 def nucleoatac_main(argv=None):
     args = build_parser().parse_args(argv)
     t0 = time.time()
+    if getattr(args, "cores", 1) > 1:   # the reference's pool size: an upper bound for the host helpers (threads, worker processes)
+        os.environ.setdefault("NB200_HOST_WORKERS", str(args.cores))
     if getattr(args, "world", 1) == 1 and int(os.environ.get("WORLD_SIZE", "1")) > 1:  # launched by torchrun
         from . import dist
         args.rank, args.world, args.device = dist.init_from_env()   # binds this process to cuda:LOCAL_RANK before NCCL starts

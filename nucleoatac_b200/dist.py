@@ -143,7 +143,8 @@ class BatchWriter:
 
     def __init__(self, threads=None):
         from concurrent.futures import ThreadPoolExecutor
-        self.fmt = ThreadPoolExecutor(max(1, threads or min(16, os.cpu_count() or 1)))
+        from . import hostio
+        self.fmt = ThreadPoolExecutor(max(1, threads or hostio.host_workers()))
         self.bg = ThreadPoolExecutor(1)
         self.prev = None
 

@@ -49,7 +49,11 @@ def n_procs():
     env = os.environ.get("NB200_FUZZ_PROCS")
     if env is not None:
         return max(0, int(env))
-    return max(0, min(16, (os.cpu_count() or 1) - 1))
+    n = min(16, (os.cpu_count() or 1) - 1)
+    host = os.environ.get("NB200_HOST_WORKERS")   # set by the drivers from `--cores N`
+    if host:
+        n = min(n, max(1, int(host)))
+    return max(0, n)
 
 
 def _get_pool(n):

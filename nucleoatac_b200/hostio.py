@@ -83,6 +83,20 @@ def bgzip_file(src, dst):
     w.close()
 
 
+def host_workers(limit=16):
+    """How many host threads / worker processes a helper may use: the cores this process may run on, at most `limit`, at
+    most NB200_HOST_WORKERS when that is set (the drivers set it from `--cores N`, N > 1: the reference's pool size)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    n = min(n, limit)
+    env = os.environ.get("NB200_HOST_WORKERS")
+    if env:
+        n = min(n, max(1, int(env)))
+    return max(1, n)
+
+
 def bgzip_tabix(path_plain, path_gz, threads=None, level=None):
     """BGZF-compress a sorted BED / bedgraph and write its .tbi in one native pass (nb200_bgzip_tabix_level).  `level`: deflate
     level, default -1 = zlib's default, which is what pysam.tabix_compress writes with (byte-identical files); the environment
@@ -93,7 +107,7 @@ def bgzip_tabix(path_plain, path_gz, threads=None, level=None):
     if level is None:
         level = int(os.environ.get("NB200_GZ_LEVEL", "-1"))
     err = C.create_string_buffer(256)
-    st = _lib.load().nb200_bgzip_tabix_level(path_plain.encode(), path_gz.encode(), int(threads or min(16, os.cpu_count() or 1)), int(level), err, 256)
+    st = _lib.load().nb200_bgzip_tabix_level(path_plain.encode(), path_gz.encode(), int(threads or host_workers()), int(level), err, 256)
     if st != 0:
         raise IOError("bgzip/tabix of %s failed: %s" % (path_plain, err.value.decode()))
     return path_gz
@@ -273,7 +287,7 @@ class BamFile:
                 continue   # unknown reference / reference without reads: voffset 0, tid -1 -> skipped by the library
             voff[i], tids[i], starts[i], ends[i] = v, tid, max(0, start), end
         if threads is None:
-            threads = max(1, min(16, len(os.sched_getaffinity(0)), n))
+            threads = max(1, min(host_workers(), n))
         off = np.zeros(n + 1, dtype=np.int64)
         pp, tp = _lib.c_int32_p(), _lib.c_int32_p()
         err = C.create_string_buffer(512)
